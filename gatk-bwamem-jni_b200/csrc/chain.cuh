@@ -1,0 +1,165 @@
+// chain.cuh -- seed chaining, chain weights and the chain filter, one thread per read.
+// Replaces mem_chain / test_and_merge / mem_chain_weight / mem_chain_flt of un-vendored lh3/bwa
+//  behind jnibwa_createAlignments (/root/reference/src/main/c/jnibwa.c:214).
+//
+// Layout: every pool below has one slot per suffix-array lookup of the batch; read r owns the slot range
+// [seed_off[r], seed_off[r+1]).  Chains own their seeds as linked lists through Seed::next, so no per-chain
+// allocation is needed; the kept chains and their seeds are compacted in chain order for the extension stage.
+#pragma once
+#include "util.cuh"
+
+struct ChainW { // working chain
+	i64 pos;
+	i32 head, tail, n, rid;
+	u32 w; i32 kept, first;
+};
+
+struct ChainStageIO {
+	const Intv* intv; int n_intv;
+	const i64* sd_rbeg;       // SA values, in (interval, occurrence) order
+	Seed* S; ChainW* C; u32* ord; u32* tmp; // scratch, one slot per lookup
+	ChainK* ck; Seed* ks;     // outputs (same slot range)
+};
+
+DEV bool chain_test_and_merge(const MemOpt& opt, i64 l_pac, ChainW& c, Seed* S, int sidx, int seed_rid)
+{
+	const Seed& p = S[sidx];
+	const Seed& last = S[c.tail];
+	const Seed& first = S[c.head];
+	i64 qend = last.qbeg + last.len, rend = last.rbeg + last.len;
+	if (seed_rid != c.rid) return false;
+	if (p.qbeg >= first.qbeg && p.qbeg + p.len <= qend && p.rbeg >= first.rbeg && p.rbeg + p.len <= rend) return true; // contained
+	if ((last.rbeg < l_pac || first.rbeg < l_pac) && p.rbeg >= l_pac) return false;
+	i64 xq = p.qbeg - last.qbeg, y = p.rbeg - last.rbeg;
+	if (y >= 0 && xq - y <= opt.w && y - xq <= opt.w && xq - last.len < opt.max_chain_gap && y - last.len < opt.max_chain_gap) {
+		S[c.tail].next = sidx; c.tail = sidx; ++c.n;
+		return true;
+	}
+	return false;
+}
+
+DEV int chain_weight(const ChainW& c, const Seed* S)
+{
+	i64 end = 0; int w = 0, tmp;
+	for (int j = c.head; j >= 0; j = S[j].next) {
+		const Seed& s = S[j];
+		if (s.qbeg >= end) w += s.len;
+		else if (s.qbeg + s.len > end) w += (int)(s.qbeg + s.len - end);
+		end = end > s.qbeg + s.len ? end : (i64)(s.qbeg + s.len);
+	}
+	tmp = w; w = 0; end = 0;
+	for (int j = c.head; j >= 0; j = S[j].next) {
+		const Seed& s = S[j];
+		if (s.rbeg >= end) w += s.len;
+		else if (s.rbeg + s.len > end) w += (int)(s.rbeg + s.len - end);
+		end = end > s.rbeg + s.len ? end : s.rbeg + s.len;
+	}
+	w = w < tmp ? w : tmp;
+	return w < (1 << 30) ? w : (1 << 30) - 1;
+}
+
+struct ChainLtW { const ChainW* C; DEVM bool operator()(u32 a, u32 b) const { return C[a].w > C[b].w; } };
+
+// returns the number of kept chains; *n_kept_seeds gets the number of seeds they hold
+DEV int chain_read(const DevIndex& x, const MemOpt& opt, int len, ChainStageIO& io, int* n_kept_seeds)
+{
+	*n_kept_seeds = 0;
+	if (len < opt.min_seed_len) return 0;
+	Seed* S = io.S; ChainW* C = io.C; u32* ord = io.ord;
+	int nch = 0, si = 0;
+	// l_rep: query bases covered by intervals that are too repetitive to be enumerated fully
+	int b = 0, e = 0, l_rep = 0;
+	for (int i = 0; i < io.n_intv; ++i) {
+		const Intv& p = io.intv[i];
+		if (p.size <= (u64)opt.max_occ) continue;
+		int sb = (int)p.beg, se = (int)p.end;
+		if (sb > e) { l_rep += e - b; b = sb; e = se; }
+		else e = e > se ? e : se;
+	}
+	l_rep += e - b;
+	for (int i = 0; i < io.n_intv; ++i) {
+		const Intv& p = io.intv[i];
+		int slen = (int)(p.end - p.beg);
+		i64 step = p.size > (u64)opt.max_occ ? (i64)(p.size / (u64)opt.max_occ) : 1;
+		int count = 0;
+		for (i64 k = 0; (u64)k < p.size && count < opt.max_occ; k += step, ++count) {
+			int sidx = si++;
+			Seed s; s.rbeg = io.sd_rbeg[sidx]; s.qbeg = (i32)p.beg; s.len = s.score = slen; s.next = -1;
+			S[sidx] = s;
+			int rid = ref_intv2rid(x, s.rbeg, s.rbeg + s.len);
+			if (rid < 0) continue; // spans two contigs or the forward/reverse junction
+			bool to_add = true; int at = 0;
+			if (nch) {
+				int lo = 0, hi = nch;
+				while (lo < hi) { int mid = (lo + hi) >> 1; if (C[ord[mid]].pos < s.rbeg) lo = mid + 1; else hi = mid; }
+				int lower = -1;
+				if (lo < nch && C[ord[lo]].pos == s.rbeg) { lower = (int)ord[lo]; at = lo + 1; }
+				else if (lo > 0) { lower = (int)ord[lo - 1]; at = lo; }
+				else at = 0;
+				if (lower >= 0 && chain_test_and_merge(opt, x.l_pac, C[lower], S, sidx, rid)) to_add = false;
+			}
+			if (to_add) {
+				ChainW c; c.pos = s.rbeg; c.head = c.tail = sidx; c.n = 1; c.rid = rid; c.w = 0; c.kept = 0; c.first = -1;
+				C[nch] = c;
+				for (int j = nch; j > at; --j) ord[j] = ord[j - 1];
+				ord[at] = (u32)nch;
+				++nch;
+			}
+		}
+	}
+	if (nch == 0) return 0;
+	float frac_rep = (float)l_rep / len;
+	// ---- filter (B.5): weights, weight-descending introsort (tie order observable), overlap rule
+	int n = 0;
+	for (int i = 0; i < nch; ++i) {
+		ChainW& c = C[ord[i]];
+		c.first = -1; c.kept = 0;
+		c.w = (u32)chain_weight(c, S);
+		if ((int)c.w >= opt.min_chain_weight) ord[n++] = ord[i];
+	}
+	if (n == 0) return 0;
+	ChainLtW lt; lt.C = C;
+	ks_introsort<u32, ChainLtW>((size_t)n, ord, lt);
+	u32* kl = io.tmp; int nk = 0; // positions (in ord) of chains kept so far
+	C[ord[0]].kept = 3; kl[nk++] = 0;
+	for (int i = 1; i < n; ++i) {
+		ChainW& ci = C[ord[i]];
+		int ib = S[ci.head].qbeg, ie = S[ci.tail].qbeg + S[ci.tail].len;
+		bool large_ovlp = false; int k;
+		for (k = 0; k < nk; ++k) {
+			ChainW& cj = C[ord[kl[k]]];
+			int jb = S[cj.head].qbeg, je = S[cj.tail].qbeg + S[cj.tail].len;
+			int b_max = jb > ib ? jb : ib, e_min = je < ie ? je : ie;
+			if (e_min > b_max) { // ALT contigs are refused at index open, so the is_alt clause is always true
+				int li = ie - ib, lj = je - jb, min_l = li < lj ? li : lj;
+				if ((float)(e_min - b_max) >= (float)min_l * opt.mask_level && min_l < opt.max_chain_gap) {
+					large_ovlp = true;
+					if (cj.first < 0) cj.first = i;
+					if ((float)(int)ci.w < (float)(int)cj.w * opt.drop_ratio && (int)cj.w - (int)ci.w >= opt.min_seed_len << 1) break;
+				}
+			}
+		}
+		if (k == nk) { kl[nk++] = (u32)i; ci.kept = large_ovlp ? 2 : 3; }
+	}
+	for (int i = 0; i < nk; ++i) { ChainW& c = C[ord[kl[i]]]; if (c.first >= 0) C[ord[c.first]].kept = 1; }
+	{
+		int i, k;
+		for (i = k = 0; i < n; ++i) {
+			int kept = C[ord[i]].kept;
+			if (kept == 0 || kept == 3) continue;
+			if (++k >= opt.max_chain_extend) break;
+		}
+		for (; i < n; ++i) if (C[ord[i]].kept < 3) C[ord[i]].kept = 0;
+	}
+	// ---- compact kept chains, seeds in chain order
+	int n_out = 0, n_seed_out = 0;
+	for (int i = 0; i < n; ++i) {
+		ChainW& c = C[ord[i]];
+		if (c.kept == 0) continue;
+		ChainK o; o.seed_start = (u32)n_seed_out; o.n_seeds = (u32)c.n; o.rid = c.rid; o.frac_rep = frac_rep; o.w = c.w; o.kept = c.kept; o.pos = c.pos;
+		for (int j = c.head; j >= 0; j = S[j].next) { Seed s = S[j]; s.next = -1; io.ks[n_seed_out++] = s; }
+		io.ck[n_out++] = o;
+	}
+	*n_kept_seeds = n_seed_out;
+	return n_out;
+}

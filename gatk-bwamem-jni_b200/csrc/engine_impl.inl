@@ -1,0 +1,301 @@
+// engine_impl.inl -- host-side orchestration of one index handle and of createAlignments batches.
+// Included by engine.cu (the product: CUDA runtime, sm_100a kernels) and by tests/cudasim (kernel-debug
+// harness on the host).  The including file provides the small runtime vocabulary used below:
+//   rt_malloc / rt_free / rt_h2d / rt_d2h / rt_memset / rt_sync / rt_scan_u32 and the three launchers
+//   RT_THREADS(body, P, n)  RT_THREADS_TID(body, P, n)  RT_WARPS(wbody, P, n)
+// plus rt_thread_slots() / rt_warp_slots() (how many scratch slots the launchers may touch).
+//
+// Drop-in boundary: jnibwa_openIndex / destroyIndex / getRefContigNames / createAlignments of
+// /root/reference/src/main/c/jnibwa.h:11-16 (definitions at jnibwa.c:154-235).
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+#include <string>
+#include <vector>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include "bwa_image.h"
+#include "pestat_host.h"
+
+namespace b200 {
+
+bool ImageView::parse(const uint8_t* m, size_t l)
+{
+	size_t k = 0;
+	if (l < 1120) return false;
+	memcpy(&primary, m, 8); memcpy(L2, m + 8, 40); memcpy(&seq_len, m + 48, 8); memcpy(&bwt_size, m + 56, 8);
+	memcpy(&sa_intv, m + 72 + 1024, 4); memcpy(&n_sa, m + 72 + 1024 + 8, 8);
+	k = 1120;
+	if (k + bwt_size * 4 > l) return false;
+	bwt = (const uint32_t*)(m + k); k += bwt_size * 4;
+	if (k + n_sa * 8 > l) return false;
+	sa = (const uint64_t*)(m + k); k += n_sa * 8;
+	if (k + 48 > l) return false;
+	memcpy(&l_pac, m + k, 8); memcpy(&n_seqs, m + k + 8, 4); memcpy(&n_holes, m + k + 24, 4);
+	k += 48;
+	k += (size_t)n_holes * 16;
+	if (n_seqs < 0 || k + (size_t)n_seqs * 40 > l) return false;
+	contigs.resize((size_t)n_seqs);
+	for (int i = 0; i < n_seqs; ++i) {
+		const uint8_t* p = m + k + (size_t)i * 40;
+		memcpy(&contigs[i].offset, p, 8); memcpy(&contigs[i].len, p + 8, 4); memcpy(&contigs[i].n_ambs, p + 12, 4);
+		memcpy(&contigs[i].gi, p + 16, 4); memcpy(&contigs[i].is_alt, p + 20, 4);
+	}
+	k += (size_t)n_seqs * 40;
+	for (int i = 0; i < n_seqs; ++i) { // strings are delimited by NUL, never by fixed offsets
+		size_t e = k; while (e < l && m[e]) ++e; if (e >= l) return false;
+		contigs[i].name.assign((const char*)m + k, e - k); k = e + 1;
+		e = k; while (e < l && m[e]) ++e; if (e >= l) return false;
+		contigs[i].anno.assign((const char*)m + k, e - k); k = e + 1;
+	}
+	pac = m + k; k += (size_t)(l_pac / 4 + 1);
+	return k == l; // the reference asserts that the walk ends exactly at the file size
+}
+
+struct DBuf { // growable device buffer
+	void* p = nullptr; size_t cap = 0;
+	bool ensure(size_t bytes) {
+		if (bytes <= cap) return true;
+		if (p) rt_free(p);
+		size_t want = bytes + bytes / 4 + 256;
+		p = rt_malloc(want); cap = p ? want : 0;
+		return p != nullptr;
+	}
+	void release() { if (p) rt_free(p); p = nullptr; cap = 0; }
+	template <class T> T* as() { return (T*)p; }
+};
+
+#define LOG_TAB_N 65536
+
+struct Engine {
+	// host view of the image
+	void* map = nullptr; size_t map_len = 0;
+	ImageView img;
+	// device-resident index
+	DevIndex dx;
+	DBuf d_bwt, d_sa, d_pac, d_ctg, d_log, d_names, d_name_off;
+	std::mutex mu; // one batch at a time per index handle (re-entrant callers are serialised)
+	// batch workspace
+	DBuf b_blob, b_seq, b_seqoff, b_intv, b_nintv, b_nseed, b_smem, b_seedoff, b_rbeg, b_S, b_C, b_ord, b_tmp32, b_ck, b_ks, b_srt, b_regtmp,
+	     b_nck, b_nks, b_nreg, b_regcap, b_regoff, b_regs, b_snap, b_ztmp, b_pairv, b_recs, b_nrec, b_cand, b_pairtab, b_var, b_misc,
+	     b_outwords, b_outoff, b_out, b_wsz, b_wscig, b_wsmd, b_wsxa, b_wsbrow;
+	Counters last_counters; double last_ms[12];
+	std::string last_error;
+
+	bool open_from_fd(int fd);
+	bool upload();
+	void close_all();
+	void* align(const MemOpt* opt, const PeStat* pes0, char* blob, size_t* out_size);
+};
+
+inline bool Engine::open_from_fd(int fd)
+{
+	struct stat st;
+	if (fstat(fd, &st) == -1) { close(fd); return false; }
+	void* m = mmap(0, st.st_size, PROT_READ, MAP_SHARED, fd, 0);
+	close(fd); // the reference takes ownership of fd and closes it (jnibwa.c:158)
+	if (m == MAP_FAILED) return false;
+	map = m; map_len = (size_t)st.st_size;
+	if (!img.parse((const uint8_t*)map, map_len)) { last_error = "malformed index image"; return false; }
+	for (auto& c : img.contigs) if (c.is_alt) { last_error = "ALT contigs are not supported by this engine"; return false; }
+	if (img.sa_intv <= 0 || (img.sa_intv & (img.sa_intv - 1))) { last_error = "SA interval must be a power of two"; return false; }
+	return upload();
+}
+
+inline bool Engine::upload()
+{
+	size_t bwt_bytes = (size_t)img.bwt_size * 4;
+	if (!d_bwt.ensure(bwt_bytes + 64) || !d_sa.ensure((size_t)img.n_sa * 8) || !d_pac.ensure((size_t)(img.l_pac / 4 + 1) + 16)) { last_error = "device allocation failed"; return false; }
+	rt_h2d(d_bwt.p, img.bwt, bwt_bytes);
+	rt_h2d(d_sa.p, img.sa, (size_t)img.n_sa * 8);
+	rt_h2d(d_pac.p, img.pac, (size_t)(img.l_pac / 4 + 1));
+	std::vector<int64_t> off((size_t)img.n_seqs + 1);
+	for (int i = 0; i < img.n_seqs; ++i) off[i] = img.contigs[i].offset;
+	off[img.n_seqs] = img.l_pac;
+	d_ctg.ensure(off.size() * 8); rt_h2d(d_ctg.p, off.data(), off.size() * 8);
+	std::vector<double> lt(LOG_TAB_N);
+	for (int i = 0; i < LOG_TAB_N; ++i) lt[i] = log((double)i); // glibc values (hazard H5)
+	d_log.ensure(lt.size() * 8); rt_h2d(d_log.p, lt.data(), lt.size() * 8);
+	std::string names; std::vector<uint32_t> noff;
+	for (auto& c : img.contigs) { noff.push_back((uint32_t)names.size()); names += c.name; names.push_back('\0'); }
+	noff.push_back((uint32_t)names.size());
+	d_names.ensure(names.size() + 1); rt_h2d(d_names.p, names.data(), names.size());
+	d_name_off.ensure(noff.size() * 4); rt_h2d(d_name_off.p, noff.data(), noff.size() * 4);
+	memset(&dx, 0, sizeof(dx));
+	dx.primary = img.primary; memcpy(dx.L2, img.L2, 40); dx.seq_len = img.seq_len;
+	dx.bwt = (const uint4*)d_bwt.p; dx.sa = (const u64*)d_sa.p; dx.sa_intv = (u32)img.sa_intv;
+	dx.l_pac = img.l_pac; dx.n_seqs = img.n_seqs; dx.ctg_off = (const i64*)d_ctg.p; dx.pac = (const u8*)d_pac.p;
+	dx.log_tab = (const double*)d_log.p; dx.log_tab_n = LOG_TAB_N;
+	rt_sync();
+	return true;
+}
+
+inline void Engine::close_all()
+{
+	DBuf* all[] = { &d_bwt, &d_sa, &d_pac, &d_ctg, &d_log, &d_names, &d_name_off, &b_blob, &b_seq, &b_seqoff, &b_intv, &b_nintv, &b_nseed, &b_smem,
+	                &b_seedoff, &b_rbeg, &b_S, &b_C, &b_ord, &b_tmp32, &b_ck, &b_ks, &b_srt, &b_regtmp, &b_nck, &b_nks, &b_nreg, &b_regcap, &b_regoff,
+	                &b_regs, &b_snap, &b_ztmp, &b_pairv, &b_recs, &b_nrec, &b_cand, &b_pairtab, &b_var, &b_misc, &b_outwords, &b_outoff, &b_out,
+	                &b_wsz, &b_wscig, &b_wsmd, &b_wsxa, &b_wsbrow };
+	for (DBuf* b : all) b->release();
+	if (map) munmap(map, map_len);
+	map = nullptr;
+}
+
+// misc block layout (u32 words): [0] err  [1] work counter  [2] var cursor  [8..] Counters
+inline void* Engine::align(const MemOpt* opt_in, const PeStat* pes0, char* blob_in, size_t* out_size)
+{
+	std::lock_guard<std::mutex> lock(mu);
+	last_error.clear();
+	*out_size = 0;
+	MemOpt opt = *opt_in; // the options live in a caller-owned buffer (…BwaMemIndex.c:146): snapshot them
+	uint32_t n_reads; memcpy(&n_reads, blob_in, 4);
+	const char* base = blob_in + 4;
+	// ---- parse the request on the host: one pass for the read boundaries
+	std::vector<uint64_t> seq_off((size_t)n_reads + 1);
+	int max_len = 0;
+	{
+		const char* p = base;
+		for (uint32_t i = 0; i < n_reads; ++i) {
+			size_t l = strlen(p);
+			seq_off[i] = (uint64_t)(p - base);
+			if ((int)l > max_len) max_len = (int)l;
+			p += l + 1;
+		}
+		seq_off[n_reads] = (uint64_t)(p - base);
+	}
+	const uint64_t blob_len = seq_off[n_reads];
+	const bool pe = (opt.flag & MEM_F_PE) != 0;
+	const int n_units = pe ? (int)(n_reads >> 1) : (int)n_reads;
+	if (n_reads == 0) { void* r = malloc(1); return r; }
+	// ---- option / shape validation: fail loudly instead of approximating
+	if (opt.e_del <= 0 || opt.e_ins <= 0 || opt.a <= 0 || opt.max_occ <= 0 || opt.min_seed_len <= 0) { last_error = "unsupported option values"; return nullptr; }
+	{
+		// mem_flt_chained_seeds (long-read seed re-scoring) is not on this path: refuse reads that would trigger it
+		for (uint32_t i = 0; i < n_reads; ++i) {
+			int l = (int)(seq_off[i + 1] - seq_off[i] - 1);
+			if (l <= 0) continue;
+			double min_l = opt.min_chain_weight ? 1.1f * opt.min_chain_weight : 5.5f * log((double)l);
+			if (!(min_l > 0.05f * l)) { last_error = "read length/min_chain_weight would enable mem_flt_chained_seeds (long-read path not built)"; return nullptr; }
+		}
+	}
+	const int wm_cap = ((max_len + 15) / 16) * 16 + 32;
+	const int intv_cap = max_len < 64 ? 64 : (max_len > 512 ? 512 : max_len);
+
+	BatchParams P;
+	memset(&P, 0, sizeof(P));
+	P.x = dx; P.opt = opt; P.n_reads = (int)n_reads; P.n_units = n_units; P.blob_len = blob_len;
+	P.ctg_names = (const char*)d_names.p; P.ctg_name_off = (const u32*)d_name_off.p;
+	bool ok = true;
+	ok &= b_blob.ensure(blob_len + 16) && b_seq.ensure(blob_len + 16) && b_seqoff.ensure(((size_t)n_reads + 1) * 8);
+	ok &= b_intv.ensure((size_t)n_reads * intv_cap * sizeof(Intv)) && b_nintv.ensure((size_t)n_reads * 4) && b_nseed.ensure((size_t)n_reads * 4);
+	const int64_t tslots = rt_thread_slots(), wslots = rt_warp_slots();
+	ok &= b_smem.ensure((size_t)tslots * 2 * (size_t)(max_len + 1) * sizeof(Intv));
+	ok &= b_seedoff.ensure(((size_t)n_reads + 1) * 8) && b_nck.ensure((size_t)n_reads * 4) && b_nks.ensure((size_t)n_reads * 4) && b_nreg.ensure((size_t)n_reads * 4);
+	ok &= b_regcap.ensure((size_t)n_reads * 4) && b_regoff.ensure(((size_t)n_reads + 1) * 8) && b_nrec.ensure((size_t)n_reads * 4);
+	ok &= b_outwords.ensure((size_t)n_reads * 4) && b_outoff.ensure(((size_t)n_reads + 1) * 8) && b_misc.ensure(1024);
+	if (!ok) { last_error = "device allocation failed"; return nullptr; }
+	rt_memset(b_misc.p, 0, 1024);
+	P.err = b_misc.as<u32>(); P.work_counter = b_misc.as<u32>() + 1; P.var_cursor = b_misc.as<u32>() + 2; P.cnt = (Counters*)(b_misc.as<u32>() + 8);
+	rt_h2d(b_blob.p, base, blob_len);
+	rt_h2d(b_seqoff.p, seq_off.data(), seq_off.size() * 8);
+	P.blob = b_blob.as<u8>(); P.seq = b_seq.as<u8>(); P.seq_off = b_seqoff.as<u64>();
+	P.intv = b_intv.as<Intv>(); P.intv_cap = intv_cap; P.n_intv = b_nintv.as<u32>(); P.n_seed = b_nseed.as<u32>();
+	P.smem_scratch = b_smem.as<Intv>(); P.smem_cap = max_len + 1;
+	P.seed_off = b_seedoff.as<u64>(); P.n_ck = b_nck.as<u32>(); P.n_ks = b_nks.as<u32>(); P.n_reg = b_nreg.as<u32>();
+	P.reg_cap = b_regcap.as<u32>(); P.reg_off = b_regoff.as<u64>(); P.n_rec = b_nrec.as<u32>();
+	P.out_words = b_outwords.as<u32>(); P.out_off = b_outoff.as<u64>();
+	P.wm_cap = wm_cap;
+
+	// ---- stage 1: encode + seed
+	RT_THREADS(body_encode, P, (int64_t)blob_len);
+	RT_THREADS_TID(body_seed, P, (int64_t)n_reads);
+	uint64_t T = rt_scan_u32(P.n_seed, P.seed_off, n_reads);
+	P.n_seed_total = T;
+	{
+		size_t Tn = (size_t)T + 1;
+		ok = b_rbeg.ensure(Tn * 8) && b_S.ensure(Tn * sizeof(Seed)) && b_C.ensure(Tn * sizeof(ChainW)) && b_ord.ensure(Tn * 4) && b_tmp32.ensure(Tn * 4)
+		     && b_ck.ensure(Tn * sizeof(ChainK)) && b_ks.ensure(Tn * sizeof(Seed)) && b_srt.ensure(Tn * 8) && b_regtmp.ensure(Tn * sizeof(Reg));
+		if (!ok) { last_error = "device allocation failed (seed pools)"; return nullptr; }
+	}
+	P.sd_rbeg = b_rbeg.as<i64>(); P.S = b_S.as<Seed>(); P.C = b_C.as<ChainW>(); P.ord = b_ord.as<u32>(); P.tmp32 = b_tmp32.as<u32>();
+	P.ck = b_ck.as<ChainK>(); P.ks = b_ks.as<Seed>(); P.srt = b_srt.as<u64>(); P.regs_tmp = b_regtmp.as<Reg>();
+	// ---- stage 2: SA lookups, chaining
+	RT_THREADS(body_sal, P, (int64_t)T);
+	RT_THREADS(body_chain, P, (int64_t)n_reads);
+	// ---- warp scratch
+	{
+		const int L = max_len > 0 ? max_len : 1;
+		P.ws_z_cap = (size_t)(L + 1) * (size_t)(2 * L + 4 * opt.w + 64);
+		P.ws_cigar_cap = 3 * L + 4 * opt.w + 64;
+		P.ws_md_cap = 4 * L + 8 * opt.w + 128;
+		P.ws_xa_cap = 8192;
+		ok = b_wsz.ensure((size_t)wslots * P.ws_z_cap) && b_wscig.ensure((size_t)wslots * P.ws_cigar_cap * 4) && b_wsmd.ensure((size_t)wslots * P.ws_md_cap) && b_wsxa.ensure((size_t)wslots * P.ws_xa_cap);
+		if (!ok) { last_error = "device allocation failed (warp scratch)"; return nullptr; }
+		P.ws_z = b_wsz.as<u8>(); P.ws_cigar = b_wscig.as<u32>(); P.ws_md = b_wsmd.as<char>(); P.ws_xa = b_wsxa.as<char>();
+		P.ws_brow = nullptr; P.ws_brow_cap = 0;
+	}
+	// ---- stage 3: extension + de-duplication
+	RT_WARPS(wbody_extend, P, (int64_t)n_reads);
+	// ---- paired-end: insert-size statistics (the one batch-global step; host)
+	for (int d = 0; d < 4; ++d) { memset(&P.pes[d], 0, sizeof(PeStat)); P.pes[d].failed = 1; }
+	if (pe) {
+		if (pes0) memcpy(P.pes, pes0, 4 * sizeof(PeStat));
+		else {
+			if (!b_cand.ensure((size_t)(n_units + 1) * 8)) { last_error = "device allocation failed"; return nullptr; }
+			P.pe_cand = b_cand.as<i64>();
+			RT_THREADS(body_pe_cand, P, (int64_t)n_units);
+			std::vector<int64_t> cand((size_t)n_units);
+			rt_d2h(cand.data(), P.pe_cand, (size_t)n_units * 8);
+			host_mem_pestat(opt, cand.data(), n_units, P.pes);
+		}
+		std::vector<double> tab; int64_t off[4];
+		if (!host_pair_table(opt, P.pes, tab, off)) { last_error = "insert-size range too wide to tabulate"; return nullptr; }
+		if (!b_pairtab.ensure(tab.size() * 8 + 8)) { last_error = "device allocation failed"; return nullptr; }
+		if (!tab.empty()) rt_h2d(b_pairtab.p, tab.data(), tab.size() * 8);
+		P.pair_tab = b_pairtab.as<double>();
+		int max_win = 0;
+		for (int d = 0; d < 4; ++d) { P.pair_tab_off[d] = off[d]; if (!P.pes[d].failed) { int wd = P.pes[d].high - P.pes[d].low + 1; if (wd > max_win) max_win = wd; } }
+		P.ws_brow_cap = max_win + max_len + 64;
+		if (!b_wsbrow.ensure((size_t)wslots * P.ws_brow_cap * 8)) { last_error = "device allocation failed"; return nullptr; }
+		P.ws_brow = b_wsbrow.as<u64>();
+	}
+	// ---- region capacity, offsets, compaction
+	RT_THREADS(body_reg_cap, P, (int64_t)n_reads);
+	uint64_t R = rt_scan_u32(P.reg_cap, P.reg_off, n_reads);
+	{
+		size_t Rn = (size_t)R + 2;
+		ok = b_regs.ensure(Rn * sizeof(Reg)) && b_snap.ensure(Rn * sizeof(Reg)) && b_ztmp.ensure(Rn * 4) && b_pairv.ensure(Rn * sizeof(Pair64)) && b_recs.ensure(Rn * sizeof(AlnRec));
+		P.var_cap = (u32)std::min<uint64_t>((uint64_t)0xfffffff0u, (uint64_t)R * 24 + (uint64_t)n_reads * 8 + 4096);
+		ok = ok && b_var.ensure((size_t)P.var_cap * 4);
+		if (!ok) { last_error = "device allocation failed (region pools)"; return nullptr; }
+	}
+	P.regs = b_regs.as<Reg>(); P.snap = b_snap.as<Reg>(); P.ztmp = b_ztmp.as<u32>(); P.pairv = b_pairv.as<Pair64>(); P.recs = b_recs.as<AlnRec>(); P.var = b_var.as<u32>();
+	RT_THREADS(body_compact, P, (int64_t)n_reads);
+	// ---- finalize
+	if (pe) RT_WARPS(wbody_final_pe, P, (int64_t)n_units);
+	else RT_WARPS(wbody_final_se, P, (int64_t)n_reads);
+	// ---- output stream
+	RT_THREADS(body_out_size, P, (int64_t)n_reads);
+	uint64_t W = rt_scan_u32(P.out_words, P.out_off, n_reads);
+	if (!b_out.ensure((size_t)W * 4 + 16)) { last_error = "device allocation failed (output)"; return nullptr; }
+	P.out = b_out.as<u32>();
+	RT_THREADS(body_out_write, P, (int64_t)n_reads);
+	uint32_t misc[32];
+	rt_d2h(misc, b_misc.p, sizeof(misc));
+	memcpy(&last_counters, misc + 8, sizeof(Counters));
+	if (misc[0]) {
+		char buf[128]; snprintf(buf, sizeof buf, "device-side capacity/limit error flags 0x%x", misc[0]);
+		last_error = buf;
+		return nullptr;
+	}
+	void* res = malloc((size_t)W * 4 + 4);
+	if (!res) { last_error = "host allocation failed"; return nullptr; }
+	rt_d2h(res, P.out, (size_t)W * 4);
+	*out_size = (size_t)W * 4;
+	return res;
+}
+
+} // namespace b200

@@ -1,0 +1,259 @@
+// kernels.cuh -- the kernels of one createAlignments batch (bodies; the launch wrappers are in engine.cu).
+//
+// Stage order (reference entry /root/reference/src/main/c/jnibwa.c:197-235):
+//   encode  -> seed (SMEM, 3 rounds) -> [scan] -> sal (SA lookups) -> chain (+filter) -> extend (+dedup)
+//   -> [PE: pestat candidates -> host mem_pestat] -> capacity/scan/compact -> finalize (SE | PE) -> size/scan -> write
+// Thread kernels take one work item per thread; warp kernels one per warp.
+#pragma once
+#include "fm.cuh"
+#include "chain.cuh"
+#include "finalize.cuh"
+
+struct BatchParams {
+	DevIndex x;
+	MemOpt opt;
+	// reads
+	int n_reads;            // reads in the call
+	int n_units;            // reads (SE) or pairs (PE)
+	const u8* blob;         // raw bytes of the request (after the u32 count)
+	u8* seq;                // nt4 codes, same offsets as blob
+	const u64* seq_off;     // n_reads+1 byte offsets (each read followed by its NUL)
+	u64 blob_len;
+	// seeding
+	Intv* intv; int intv_cap; u32* n_intv; u32* n_seed; // per read
+	Intv* smem_scratch; int smem_cap;                  // per thread: 2*smem_cap entries
+	u64* seed_off;          // n_reads+1 (exclusive scan of n_seed)
+	u64 n_seed_total;
+	i64* sd_rbeg;           // [T]
+	// chaining pools, one slot per lookup
+	Seed* S; ChainW* C; u32* ord; u32* tmp32; ChainK* ck; Seed* ks; u64* srt; Reg* regs_tmp;
+	u32* n_ck; u32* n_ks; u32* n_reg;   // per read
+	// final regions
+	u32* reg_cap; u64* reg_off; Reg* regs; Reg* snap; u32* ztmp; Pair64* pairv; AlnRec* recs; u32* n_rec;
+	i64* pe_cand;           // per pair
+	PeStat pes[4];
+	const double* pair_tab; i64 pair_tab_off[4];
+	// output
+	u32* var; u32 var_cap; u32* var_cursor;
+	u32* out_words; u64* out_off; u32* out;
+	const char* ctg_names; const u32* ctg_name_off;
+	// warp scratch (per resident warp)
+	u8* ws_z; size_t ws_z_cap; u32* ws_cigar; int ws_cigar_cap; char* ws_md; int ws_md_cap; char* ws_xa; int ws_xa_cap; u64* ws_brow; int ws_brow_cap;
+	int wm_cap;             // per-warp DP column capacity
+	u32* err; Counters* cnt; u32* work_counter;
+};
+
+// ---- encode: ASCII -> nt4 (bytes already < 4 are taken as codes; hazard H12) --------------------
+DEV u8 nt4_of(u8 c)
+{
+	if (c < 4) return c;
+	switch (c) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; case '-': return 5; default: return 4; }
+}
+DEV void body_encode(const BatchParams& P, i64 i) { P.seq[i] = nt4_of(P.blob[i]); }
+
+// ---- seed: one thread per read -------------------------------------------------------------------
+DEV void body_seed(const BatchParams& P, i64 r, i64 tid)
+{
+	const u8* seq = P.seq + P.seq_off[r];
+	int len = (int)(P.seq_off[r + 1] - P.seq_off[r] - 1);
+	IntvOut o; o.v = P.intv + (size_t)r * P.intv_cap; o.n = 0; o.cap = P.intv_cap; o.overflow = false;
+	u32 ns = 0;
+	if (len >= P.opt.min_seed_len) {
+		if (len > P.smem_cap) { atomic_or_u32(P.err, ERR_QLEN_OVERFLOW); }
+		else {
+			SmemScratch sc; sc.a = P.smem_scratch + (size_t)tid * 2 * P.smem_cap; sc.b = sc.a + P.smem_cap; sc.cap = P.smem_cap;
+			fm_collect_intv(P.x, P.opt, len, seq, sc, o);
+			if (o.overflow) atomic_or_u32(P.err, ERR_INTV_OVERFLOW);
+			for (int i = 0; i < o.n; ++i) ns += (u32)(o.v[i].size < (u64)P.opt.max_occ ? o.v[i].size : (u64)P.opt.max_occ);
+		}
+	}
+	P.n_intv[r] = (u32)o.n;
+	P.n_seed[r] = ns;
+}
+
+// ---- sal: one thread per lookup ------------------------------------------------------------------
+DEV void body_sal(const BatchParams& P, i64 t)
+{
+	// read owning slot t: last r with seed_off[r] <= t
+	i64 lo = 0, hi = P.n_reads;
+	while (hi - lo > 1) { i64 mid = (lo + hi) >> 1; if (P.seed_off[mid] <= (u64)t) lo = mid; else hi = mid; }
+	i64 r = lo;
+	u64 rel = (u64)t - P.seed_off[r];
+	const Intv* iv = P.intv + (size_t)r * P.intv_cap;
+	int n = (int)P.n_intv[r];
+	for (int i = 0; i < n; ++i) {
+		u64 c = iv[i].size < (u64)P.opt.max_occ ? iv[i].size : (u64)P.opt.max_occ;
+		if (rel < c) {
+			u64 step = iv[i].size > (u64)P.opt.max_occ ? iv[i].size / (u64)P.opt.max_occ : 1;
+			P.sd_rbeg[t] = (i64)fm_sa(P.x, iv[i].x0 + rel * step);
+			return;
+		}
+		rel -= c;
+	}
+}
+
+// ---- chain: one thread per read ------------------------------------------------------------------
+DEV void body_chain(const BatchParams& P, i64 r)
+{
+	u64 t0 = P.seed_off[r];
+	int len = (int)(P.seq_off[r + 1] - P.seq_off[r] - 1);
+	ChainStageIO io;
+	io.intv = P.intv + (size_t)r * P.intv_cap; io.n_intv = (int)P.n_intv[r];
+	io.sd_rbeg = P.sd_rbeg + t0;
+	io.S = P.S + t0; io.C = P.C + t0; io.ord = P.ord + t0; io.tmp = P.tmp32 + t0; io.ck = P.ck + t0; io.ks = P.ks + t0;
+	int nks = 0;
+	int nck = P.seed_off[r + 1] > t0 ? chain_read(P.x, P.opt, len, io, &nks) : 0;
+	P.n_ck[r] = (u32)nck; P.n_ks[r] = (u32)nks;
+}
+
+DEV void make_warp_ctx(const BatchParams& P, i64 warp_slot, u8* smem, WarpMem& wm, WarpScratch& ws)
+{
+	int cap = P.wm_cap;
+	i32* p = (i32*)smem;
+	wm.H = p; wm.E = p + (cap + 2); wm.H2 = p + 2 * (cap + 2); wm.Hm = p + 3 * (cap + 2); wm.fend = p + 4 * (cap + 2);
+	wm.q = (u8*)(p + 4 * (cap + 2) + 16);
+	wm.cap = cap;
+	ws.z = P.ws_z + (size_t)warp_slot * P.ws_z_cap; ws.z_cap = P.ws_z_cap;
+	ws.cigar = P.ws_cigar + (size_t)warp_slot * P.ws_cigar_cap; ws.cigar_cap = P.ws_cigar_cap;
+	ws.md = P.ws_md + (size_t)warp_slot * P.ws_md_cap; ws.md_cap = P.ws_md_cap;
+	ws.xa = P.ws_xa + (size_t)warp_slot * P.ws_xa_cap; ws.xa_cap = P.ws_xa_cap;
+	ws.brow = P.ws_brow + (size_t)warp_slot * P.ws_brow_cap; ws.brow_cap = P.ws_brow_cap;
+	ws.err = P.err;
+}
+DEV size_t warp_smem_bytes(int cap) { return (size_t)(4 * (cap + 2) + 16) * 4 + (size_t)((cap + 2 + 15) & ~15); }
+
+// ---- extend: one warp per read -------------------------------------------------------------------
+DEV void wbody_extend(const BatchParams& P, i64 r, WarpMem& wm, WarpScratch& ws)
+{
+	LANE_DECL;
+	u64 t0 = P.seed_off[r];
+	int len = (int)(P.seq_off[r + 1] - P.seq_off[r] - 1);
+	const u8* seq = P.seq + P.seq_off[r];
+	int nck = (int)P.n_ck[r], n_av = 0, av_cap = (int)P.n_ks[r];
+	Reg* av = P.regs_tmp + t0;
+	if (len > wm.cap) { if (nck) { ONE_LANE { atomic_or_u32(P.err, ERR_QLEN_OVERFLOW); } } nck = 0; }
+	for (int c = 0; c < nck; ++c) {
+		const ChainK ck = P.ck[t0 + c];
+		warp_chain2aln(P.x, P.opt, wm, ws, P.cnt, len, seq, ck, P.ks + t0 + ck.seed_start, P.srt + t0, av, &n_av, av_cap);
+	}
+	n_av = warp_sort_dedup_patch(P.x, P.opt, wm, ws, P.cnt, seq, n_av, av);
+	ONE_LANE { P.n_reg[r] = (u32)n_av; }
+}
+
+// ---- PE: insert-size candidate of a pair (thread per pair) and region capacity per read -----------
+DEV void body_pe_cand(const BatchParams& P, i64 pr)
+{
+	i64 r0 = pr << 1, r1 = r0 + 1;
+	P.pe_cand[pr] = pestat_candidate(P.x, P.opt, (int)P.n_reg[r0], P.regs_tmp + P.seed_off[r0], (int)P.n_reg[r1], P.regs_tmp + P.seed_off[r1]);
+}
+
+DEV void body_reg_cap(const BatchParams& P, i64 r)
+{
+	u32 cap = P.n_reg[r];
+	if ((P.opt.flag & MEM_F_PE) && !(P.opt.flag & MEM_F_NO_RESCUE) && (r | 1) < P.n_reads) {
+		i64 m = r ^ 1; // rescues launched from the mate's hits land in this read's list
+		int n_ok = 0;
+		for (int d = 0; d < 4; ++d) n_ok += P.pes[d].failed ? 0 : 1;
+		const Reg* a = P.regs_tmp + P.seed_off[m];
+		int nm = (int)P.n_reg[m], nb = 0;
+		for (int j = 0; j < nm; ++j) if (a[j].score >= a[0].score - P.opt.pen_unpaired) ++nb;
+		nb = nb < P.opt.max_matesw ? nb : P.opt.max_matesw;
+		cap += (u32)(nb * n_ok);
+	}
+	P.reg_cap[r] = cap > 0 ? cap : 1;
+}
+
+DEV void body_compact(const BatchParams& P, i64 r)
+{
+	const Reg* s = P.regs_tmp + P.seed_off[r];
+	Reg* d = P.regs + P.reg_off[r];
+	int n = (int)P.n_reg[r];
+	for (int i = 0; i < n; ++i) d[i] = s[i];
+}
+
+DEV void make_final_ctx(const BatchParams& P, WarpMem& wm, WarpScratch& ws, FinalCtx& f)
+{
+	f.x = &P.x; f.opt = &P.opt; f.wm = &wm; f.ws = &ws; f.cnt = P.cnt;
+	f.var = P.var; f.var_cap = P.var_cap; f.var_cursor = P.var_cursor;
+	f.ctg_names = P.ctg_names; f.ctg_name_off = P.ctg_name_off;
+	f.pes = P.pes; f.pair_tab = P.pair_tab; f.pair_tab_off = P.pair_tab_off;
+}
+
+// ---- finalize, single-end: one warp per read ------------------------------------------------------
+DEV void wbody_final_se(const BatchParams& P, i64 r, WarpMem& wm, WarpScratch& ws)
+{
+	LANE_DECL;
+	FinalCtx f; make_final_ctx(P, wm, ws, f);
+	int len = (int)(P.seq_off[r + 1] - P.seq_off[r] - 1);
+	const u8* seq = P.seq + P.seq_off[r];
+	Reg* a = P.regs + P.reg_off[r];
+	int n = (int)P.n_reg[r];
+	warp_mark_primary_se(P.opt, n, a, r, P.ztmp + P.reg_off[r]); // id = index within the call (hazard H2)
+	if (P.opt.flag & MEM_F_PRIMARY5) warp_reorder_primary5(P.opt.T, n, a);
+	int nr = warp_reg2sam(f, len, seq, n, a, 0, nullptr, P.recs + P.reg_off[r], (int)P.reg_cap[r]);
+	ONE_LANE { P.n_rec[r] = (u32)nr; }
+}
+
+// ---- finalize, paired-end: one warp per pair ------------------------------------------------------
+DEV void wbody_final_pe(const BatchParams& P, i64 pr, WarpMem& wm, WarpScratch& ws)
+{
+	LANE_DECL;
+	FinalCtx f; make_final_ctx(P, wm, ws, f);
+	PairIO io;
+	for (int e = 0; e < 2; ++e) {
+		i64 r = (pr << 1) + e;
+		io.l_seq[e] = (int)(P.seq_off[r + 1] - P.seq_off[r] - 1);
+		io.seq[e] = P.seq + P.seq_off[r];
+		io.a[e] = P.regs + P.reg_off[r]; io.n[e] = (int)P.n_reg[r]; io.cap[e] = (int)P.reg_cap[r];
+		io.snap[e] = P.snap + P.reg_off[r];
+		io.ztmp[e] = P.ztmp + P.reg_off[r];
+		io.out[e] = P.recs + P.reg_off[r]; io.out_cap[e] = (int)P.reg_cap[r]; io.n_out[e] = 0;
+	}
+	io.v = P.pairv + P.reg_off[pr << 1];
+	warp_sam_pe(f, (u64)pr, io);
+	ONE_LANE { P.n_rec[pr << 1] = (u32)io.n_out[0]; P.n_rec[(pr << 1) + 1] = (u32)io.n_out[1]; }
+}
+
+// ---- output stream (fmt_BAMish, jnibwa.c:43-97): size per read, then write --------------------------
+DEV u32 rec_words(const AlnRec& a)
+{
+	u32 n = 1;
+	if (!(a.flag & 0x4)) n += 8 + (u32)a.n_cigar + (u32)((a.md_len + 3) >> 2) + (u32)((a.xa_len + 3) >> 2);
+	if ((a.flag & 0x9) == 1) n += 3;
+	return n;
+}
+
+DEV void body_out_size(const BatchParams& P, i64 r)
+{
+	if ((P.opt.flag & MEM_F_PE) && r >= ((i64)P.n_units << 1)) { P.out_words[r] = 0; return; } // odd trailing read (hazard H11)
+	u32 n = 1;
+	const AlnRec* a = P.recs + P.reg_off[r];
+	for (u32 k = 0; k < P.n_rec[r]; ++k) n += rec_words(a[k]);
+	P.out_words[r] = n;
+}
+
+DEV void body_out_write(const BatchParams& P, i64 r)
+{
+	if (P.out_words[r] == 0) return;
+	u32* o = P.out + P.out_off[r];
+	const AlnRec* a = P.recs + P.reg_off[r];
+	u32 nr = P.n_rec[r];
+	*o++ = nr;
+	for (u32 k = 0; k < nr; ++k) {
+		const AlnRec& p = a[k];
+		u32 fm = (u32)p.flag;
+		if (p.flag & 0x10000) fm |= 0x100;
+		*o++ = (fm << 16) | (p.mapq & 0xff);
+		if (!(p.flag & 0x4)) {
+			*o++ = (u32)p.rid; *o++ = (u32)p.pos; *o++ = (u32)p.NM; *o++ = (u32)p.score; *o++ = (u32)p.sub; *o++ = (u32)p.n_cigar;
+			const u32* v = P.var + p.var_off;
+			for (int c = 0; c < p.n_cigar; ++c) { u32 lo = v[c]; if ((lo & 0xf) > 2) ++lo; *o++ = lo; } // MIDSH -> BAM numbering
+			*o++ = (u32)p.md_len;
+			for (int c = 0; c < (p.md_len + 3) >> 2; ++c) *o++ = v[p.n_cigar + c];
+			*o++ = (u32)p.xa_len;
+			const u32* xv = P.var + p.xa_off;
+			for (int c = 0; c < (p.xa_len + 3) >> 2; ++c) *o++ = xv[c];
+		}
+		if ((p.flag & 0x9) == 1) { *o++ = (u32)p.m_rid; *o++ = (u32)p.m_pos; *o++ = (u32)p.tlen; }
+	}
+}

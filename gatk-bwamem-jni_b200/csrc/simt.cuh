@@ -1,0 +1,88 @@
+// simt.cuh -- thin SIMT vocabulary used by every kernel of the engine.
+//
+// Product build (nvcc, sm_100a): the macros below are the CUDA built-ins; a
+// "warp variable" is one register per lane and the collectives are shuffles /
+// ballots / redux.  This is the only configuration that is ever shipped or
+// loaded by the package.
+//
+// Kernel-debug build (-DB200_SIM, host g++; used ONLY by tests/cudasim to run
+// the very same kernel source under gdb/ASan on the CPU-only dev box, never
+// built into libbwa_b200.so and never reachable from the package): a warp
+// variable is an array of 32 values, FOR_LANES is a loop, and collectives are
+// loops over that array.  Warp kernels are then executed once per warp and
+// thread kernels once per thread by tests/cudasim's launcher.
+#pragma once
+#include <cstdint>
+#include <cstring>
+
+typedef uint64_t u64;
+typedef int64_t i64;
+typedef uint32_t u32;
+typedef int32_t i32;
+typedef uint16_t u16;
+typedef uint8_t u8;
+typedef int8_t i8;
+
+#ifndef B200_SIM
+// ------------------------------------------------------------------ CUDA
+#include <cuda_runtime.h>
+#define DEV __device__ __forceinline__
+#define DEVNI __device__ __noinline__
+#define DEVM __device__ __forceinline__
+#define KERNEL __global__
+#define FULLMASK 0xffffffffu
+#define WV(T, name) T name
+#define L_(name) name
+#define FOR_LANES
+#define LANE_DECL const int lane = (int)(threadIdx.x & 31)
+#define ONE_LANE __syncwarp(); if (lane == 0)      /* pre-synchronised single-lane write (may overwrite data other lanes just read) */
+#define ONE_LANE_NOSYNC if (lane == 0)            /* append-only single-lane write */
+#define WARP_SYNC() __syncwarp()
+
+template <class T> DEV T ldg(const T* p) { return __ldg(p); }
+DEV int popc64(u64 x) { return __popcll(x); }
+template <class T> DEV void wv_shfl_up(T& dst, const T& src, int d) { dst = __shfl_up_sync(FULLMASK, src, d); }
+template <class T> DEV void wv_shfl_idx(T& dst, const T& src, int idx) { dst = __shfl_sync(FULLMASK, src, idx); }
+DEV int wv_reduce_max(const int& v) { return __reduce_max_sync(FULLMASK, v); }
+DEV int wv_reduce_min(const int& v) { return __reduce_min_sync(FULLMASK, v); }
+DEV u32 wv_ballot(const bool& p) { return __ballot_sync(FULLMASK, p); }
+template <class T> DEV T wv_get(const T& v, int l) { return __shfl_sync(FULLMASK, v, l); }
+DEV u64 atomic_add_u64(u64* p, u64 v) { return (u64)atomicAdd((unsigned long long*)p, (unsigned long long)v); }
+DEV u32 atomic_add_u32(u32* p, u32 v) { return atomicAdd(p, v); }
+DEV u32 atomic_or_u32(u32* p, u32 v) { return atomicOr(p, v); }
+DEV u32 atomic_max_u32(u32* p, u32 v) { return atomicMax(p, v); }
+#else
+// ------------------------------------------------------------------ host kernel-debug harness (tests/cudasim only)
+#include <algorithm>
+#define DEV static inline
+#define DEVNI static
+#define DEVM inline
+#define KERNEL static
+#define WV(T, name) T name[32]
+#define L_(name) name[lane]
+#define FOR_LANES for (int lane = 0; lane < 32; ++lane)
+#define LANE_DECL const int lane0_unused_ = 0; (void)lane0_unused_
+#define ONE_LANE
+#define ONE_LANE_NOSYNC
+#define WARP_SYNC()
+
+struct uint4 { u32 x, y, z, w; };
+template <class T> DEV T ldg(const T* p) { return *p; }
+DEV int popc64(u64 x) { return __builtin_popcountll(x); }
+template <class T> DEV void wv_shfl_up(T (&dst)[32], const T (&src)[32], int d) { T t[32]; for (int l = 0; l < 32; ++l) t[l] = l >= d ? src[l - d] : src[l]; for (int l = 0; l < 32; ++l) dst[l] = t[l]; }
+template <class T> DEV void wv_shfl_idx(T (&dst)[32], const T (&src)[32], int idx) { T t = src[idx]; for (int l = 0; l < 32; ++l) dst[l] = t; }
+DEV int wv_reduce_max(const int (&v)[32]) { int m = v[0]; for (int l = 1; l < 32; ++l) m = v[l] > m ? v[l] : m; return m; }
+DEV int wv_reduce_min(const int (&v)[32]) { int m = v[0]; for (int l = 1; l < 32; ++l) m = v[l] < m ? v[l] : m; return m; }
+DEV u32 wv_ballot(const bool (&p)[32]) { u32 m = 0; for (int l = 0; l < 32; ++l) m |= (u32)(p[l] ? 1u : 0u) << l; return m; }
+template <class T> DEV T wv_get(const T (&v)[32], int l) { return v[l]; }
+DEV u64 atomic_add_u64(u64* p, u64 v) { u64 o = *p; *p += v; return o; }
+DEV u32 atomic_add_u32(u32* p, u32 v) { u32 o = *p; *p += v; return o; }
+DEV u32 atomic_or_u32(u32* p, u32 v) { u32 o = *p; *p |= v; return o; }
+DEV u32 atomic_max_u32(u32* p, u32 v) { u32 o = *p; if (v > o) *p = v; return o; }
+DEV int __ffs(u32 x) { return x ? __builtin_ctz(x) + 1 : 0; }
+DEV int __clz(u32 x) { return x ? __builtin_clz(x) : 32; }
+#endif
+
+template <class T> DEV T imax(T a, T b) { return a > b ? a : b; }
+template <class T> DEV T imin(T a, T b) { return a < b ? a : b; }
+DEV int iabs(int a) { return a < 0 ? -a : a; }

@@ -1,0 +1,51 @@
+// sim_engine.cpp -- KERNEL-DEBUG HARNESS (test tooling, never shipped, never loaded by the package).
+//
+// Compiles the engine's kernel source (gatk-bwamem-jni_b200/csrc/*.cuh) and its host orchestration
+// (engine_impl.inl) with -DB200_SIM for the host, so that the exact kernel logic can be executed under
+// gdb / ASan / UBSan on the CPU-only development box and compared with the oracle before GPU time is
+// spent.  A warp variable becomes an array of 32 lanes and collectives become loops (see simt.cuh).
+// The product library libbwa_b200.so is built by nvcc only and contains none of this.
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#define B200_SIM 1
+#include "simt.cuh"
+
+static void* rt_malloc(size_t n) { return calloc(1, n ? n : 1); }
+static void rt_free(void* p) { free(p); }
+static void rt_h2d(void* d, const void* s, size_t n) { memcpy(d, s, n); }
+static void rt_d2h(void* d, const void* s, size_t n) { memcpy(d, s, n); }
+static void rt_memset(void* d, int v, size_t n) { memset(d, v, n); }
+static void rt_sync() {}
+static int64_t rt_thread_slots() { return 1; }
+static int64_t rt_warp_slots() { return 1; }
+static uint64_t rt_scan_u32(const uint32_t* in, uint64_t* out, uint64_t n) { uint64_t s = 0; for (uint64_t i = 0; i < n; ++i) { out[i] = s; s += in[i]; } out[n] = s; return s; }
+
+#include "kernels.cuh"
+
+#define RT_THREADS(body, P, n) do { for (int64_t i_ = 0; i_ < (int64_t)(n); ++i_) body(P, i_); } while (0)
+#define RT_THREADS_TID(body, P, n) do { for (int64_t i_ = 0; i_ < (int64_t)(n); ++i_) body(P, i_, 0); } while (0)
+#define RT_WARPS(wbody, P, n) do { \
+	std::vector<uint8_t> sm_(warp_smem_bytes((P).wm_cap) + 64); \
+	WarpMem wm_; WarpScratch ws_; make_warp_ctx(P, 0, sm_.data(), wm_, ws_); \
+	for (int64_t i_ = 0; i_ < (int64_t)(n); ++i_) wbody(P, i_, wm_, ws_); } while (0)
+
+#include "engine_impl.inl"
+
+using namespace b200;
+
+extern "C" {
+void* sim_openIndex(int fd) { Engine* e = new Engine(); if (!e->open_from_fd(fd)) { fprintf(stderr, "[sim] openIndex: %s\n", e->last_error.c_str()); e->close_all(); delete e; return nullptr; } return e; }
+int sim_destroyIndex(void* h) { Engine* e = (Engine*)h; e->close_all(); delete e; return 0; }
+void* sim_createAlignments(void* h, void* opt, void* pes, char* blob, size_t* size)
+{
+	Engine* e = (Engine*)h;
+	void* r = e->align((const MemOpt*)opt, (const PeStat*)pes, blob, size);
+	if (!r) fprintf(stderr, "[sim] createAlignments: %s\n", e->last_error.c_str());
+	return r;
+}
+void sim_free(void* p) { free(p); }
+void sim_last_counters(void* h, uint64_t* out) { memcpy(out, &((Engine*)h)->last_counters, sizeof(Counters)); }
+}
