@@ -79,7 +79,7 @@ class NativeLib:
     def __init__(self, path: str, prefix: str = "jnibwa_", opt_init: str = "mem_opt_init",
                  free: str = "jnibwa_free"):
         self.path = path
-        self.dll = ctypes.CDLL(path, mode=ctypes.RTLD_GLOBAL)
+        self.dll = ctypes.CDLL(path)  # RTLD_LOCAL: several native libraries may coexist in one process
         d = self.dll
         self.openIndex = getattr(d, prefix + "openIndex")
         self.openIndex.restype = ctypes.c_void_p

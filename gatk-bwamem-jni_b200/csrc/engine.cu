@@ -1,0 +1,210 @@
+// engine.cu -- the product: CUDA runtime binding of the engine (sm_100a) and its C-ABI.
+//
+// Exports the C entry points of /root/reference/src/main/c/jnibwa.h:11-16 with identical signatures
+// (declared, with the reference line each replaces, in include/bwamem_b200.h), mem_opt_init (called by
+// …BwaMemIndex.c:91), the allocator counterpart of destroyByteBuffer (…BwaMemIndex.c:157-160) and a few
+// b200_* instrumentation calls used by bench.py.  No CPU fallback: every call that needs the device fails
+// (NULL / 0) when no CUDA device is usable.
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+
+#include "simt.cuh"
+
+// ---- runtime vocabulary expected by engine_impl.inl ------------------------------------------------
+static thread_local cudaError_t g_last_cuda = cudaSuccess;
+static inline bool cu_ok(cudaError_t e, const char* what)
+{
+	if (e != cudaSuccess) { g_last_cuda = e; fprintf(stderr, "[bwamem-b200] CUDA error in %s: %s\n", what, cudaGetErrorString(e)); return false; }
+	return true;
+}
+static cudaStream_t g_stream = nullptr; // one stream per process (one process per GPU)
+static int g_sm_count = 0;
+static cudaStream_t rt_stream()
+{
+	if (!g_stream) { cu_ok(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking), "cudaStreamCreate"); }
+	return g_stream;
+}
+static int rt_sm_count()
+{
+	if (!g_sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev); if (g_sm_count <= 0) g_sm_count = 148; }
+	return g_sm_count;
+}
+static void* rt_malloc(size_t n) { void* p = nullptr; if (!cu_ok(cudaMalloc(&p, n ? n : 1), "cudaMalloc")) return nullptr; return p; }
+static void rt_free(void* p) { cudaFree(p); }
+static void rt_h2d(void* d, const void* s, size_t n) { if (n) cu_ok(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, rt_stream()), "h2d"); }
+static void rt_d2h(void* d, const void* s, size_t n) { if (n) { cu_ok(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, rt_stream()), "d2h"); cu_ok(cudaStreamSynchronize(rt_stream()), "d2h sync"); } }
+static void rt_memset(void* d, int v, size_t n) { cu_ok(cudaMemsetAsync(d, v, n, rt_stream()), "memset"); }
+static void rt_sync() { cu_ok(cudaStreamSynchronize(rt_stream()), "sync"); }
+
+#define THREADS_PER_BLOCK 128
+#define WARPS_PER_BLOCK 4
+#define SEED_BLOCKS_PER_SM 8
+#define WARP_BLOCKS_PER_SM 8
+static int64_t rt_thread_slots() { return (int64_t)rt_sm_count() * SEED_BLOCKS_PER_SM * THREADS_PER_BLOCK; }
+static int64_t rt_warp_slots() { return (int64_t)rt_sm_count() * WARP_BLOCKS_PER_SM * WARPS_PER_BLOCK; }
+
+#include "kernels.cuh"
+
+// exclusive scan of u32 counts into u64 offsets (out[n] = total); returns the total
+static void* g_scan_tmp = nullptr; static size_t g_scan_tmp_bytes = 0;
+struct U32ToU64 { __host__ __device__ u64 operator()(const u32& v) const { return (u64)v; } };
+__global__ void k_scan_close(const u32* in, u64* out, u64 n) { out[n] = n ? out[n - 1] + in[n - 1] : 0; }
+static uint64_t rt_scan_u32(const uint32_t* in, uint64_t* out, uint64_t n)
+{
+	if (n) {
+		cub::TransformInputIterator<u64, U32ToU64, const u32*> it(in, U32ToU64());
+		size_t need = 0;
+		cub::DeviceScan::ExclusiveSum(nullptr, need, it, out, (int64_t)n, rt_stream());
+		if (need > g_scan_tmp_bytes) { if (g_scan_tmp) cudaFree(g_scan_tmp); cudaMalloc(&g_scan_tmp, need + 1024); g_scan_tmp_bytes = need + 1024; }
+		cub::DeviceScan::ExclusiveSum(g_scan_tmp, need, it, out, (int64_t)n, rt_stream());
+	}
+	k_scan_close<<<1, 1, 0, rt_stream()>>>(in, out, n);
+	uint64_t total = 0;
+	rt_d2h(&total, out + n, 8);
+	return total;
+}
+
+// ---- launchers ---------------------------------------------------------------------------------------
+// Thread kernels: grid-stride over work items.  Warp kernels: one warp per item, items handed out by an
+// atomic counter so that long items (repetitive reads) do not stall a statically assigned neighbour.
+#define DEF_THREAD_KERNEL(body) \
+	__global__ void __launch_bounds__(THREADS_PER_BLOCK) k_##body(const __grid_constant__ BatchParams P, i64 n) { \
+		for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) body(P, i); }
+#define DEF_THREAD_TID_KERNEL(body) \
+	__global__ void __launch_bounds__(THREADS_PER_BLOCK) k_##body(const __grid_constant__ BatchParams P, i64 n) { \
+		const i64 tid = (i64)blockIdx.x * blockDim.x + threadIdx.x; \
+		for (i64 i = tid; i < n; i += (i64)gridDim.x * blockDim.x) body(P, i, tid); }
+#define DEF_WARP_KERNEL(wbody) \
+	__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_##wbody(const __grid_constant__ BatchParams P, i64 n, u32* counter) { \
+		extern __shared__ __align__(16) u8 smem_[]; \
+		const int wib = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31); \
+		const i64 slot = (i64)blockIdx.x * WARPS_PER_BLOCK + wib; \
+		WarpMem wm; WarpScratch ws; \
+		make_warp_ctx(P, slot, smem_ + (size_t)wib * ((warp_smem_bytes(P.wm_cap) + 15) & ~(size_t)15), wm, ws); \
+		for (;;) { \
+			u32 item = 0; \
+			if (lane == 0) item = atomicAdd(counter, 1u); \
+			item = __shfl_sync(FULLMASK, item, 0); \
+			if ((i64)item >= n) break; \
+			wbody(P, (i64)item, wm, ws); \
+			__syncwarp(); \
+		} }
+
+DEF_THREAD_KERNEL(body_encode)
+DEF_THREAD_TID_KERNEL(body_seed)
+DEF_THREAD_KERNEL(body_sal)
+DEF_THREAD_KERNEL(body_chain)
+DEF_THREAD_KERNEL(body_pe_cand)
+DEF_THREAD_KERNEL(body_reg_cap)
+DEF_THREAD_KERNEL(body_compact)
+DEF_THREAD_KERNEL(body_out_size)
+DEF_THREAD_KERNEL(body_out_write)
+DEF_WARP_KERNEL(wbody_extend)
+DEF_WARP_KERNEL(wbody_final_se)
+DEF_WARP_KERNEL(wbody_final_pe)
+
+static u32* g_counters = nullptr; static int g_counter_next = 0;
+static u32* next_counter()
+{
+	if (!g_counters) { cudaMalloc(&g_counters, 64 * sizeof(u32)); }
+	u32* c = g_counters + (g_counter_next++ & 63);
+	cudaMemsetAsync(c, 0, sizeof(u32), rt_stream());
+	return c;
+}
+
+struct StageTimer { // CUDA events on the launching stream around every stage of the last batch
+	static const int MAXS = 16;
+	cudaEvent_t ev[MAXS + 1]; const char* name[MAXS]; int n = 0; bool init = false;
+	void begin() { if (!init) { for (auto& e : ev) cudaEventCreate(&e); init = true; } n = 0; cudaEventRecord(ev[0], rt_stream()); }
+	void mark(const char* nm) { if (n < MAXS) { name[n] = nm; ++n; cudaEventRecord(ev[n], rt_stream()); } }
+};
+static StageTimer g_timer;
+static int g_launches = 0;
+
+#define RT_THREADS(body, P, n) do { i64 n_ = (i64)(n); if (n_ > 0) { \
+	i64 nb_ = (n_ + THREADS_PER_BLOCK - 1) / THREADS_PER_BLOCK; i64 cap_ = (i64)rt_sm_count() * 16; if (nb_ > cap_) nb_ = cap_; \
+	k_##body<<<(unsigned)nb_, THREADS_PER_BLOCK, 0, rt_stream()>>>(P, n_); ++g_launches; } g_timer.mark(#body); } while (0)
+#define RT_THREADS_TID(body, P, n) do { i64 n_ = (i64)(n); if (n_ > 0) { \
+	i64 nb_ = (n_ + THREADS_PER_BLOCK - 1) / THREADS_PER_BLOCK; i64 cap_ = (i64)rt_sm_count() * SEED_BLOCKS_PER_SM; if (nb_ > cap_) nb_ = cap_; \
+	k_##body<<<(unsigned)nb_, THREADS_PER_BLOCK, 0, rt_stream()>>>(P, n_); ++g_launches; } g_timer.mark(#body); } while (0)
+#define RT_WARPS(wbody, P, n) do { i64 n_ = (i64)(n); if (n_ > 0) { \
+	size_t sm_ = ((warp_smem_bytes((P).wm_cap) + 15) & ~(size_t)15) * WARPS_PER_BLOCK; \
+	i64 nb_ = (n_ + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK; i64 cap_ = (i64)rt_sm_count() * WARP_BLOCKS_PER_SM; if (nb_ > cap_) nb_ = cap_; \
+	cudaFuncSetAttribute(k_##wbody, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_); \
+	k_##wbody<<<(unsigned)nb_, WARPS_PER_BLOCK * 32, sm_, rt_stream()>>>(P, n_, next_counter()); ++g_launches; } g_timer.mark(#wbody); } while (0)
+
+#include "engine_impl.inl"
+
+using namespace b200;
+
+// ---- C-ABI (include/bwamem_b200.h) ---------------------------------------------------------------------
+extern "C" {
+
+void* jnibwa_openIndex(int fd)
+{
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+		fprintf(stderr, "[bwamem-b200] no CUDA device: this engine has no CPU fallback\n");
+		if (fd >= 0) close(fd);
+		return nullptr;
+	}
+	Engine* e = new Engine();
+	if (!e->open_from_fd(fd)) { fprintf(stderr, "[bwamem-b200] openIndex: %s\n", e->last_error.c_str()); e->close_all(); delete e; return nullptr; }
+	return e;
+}
+
+int jnibwa_destroyIndex(void* h)
+{
+	if (!h) return 0;
+	Engine* e = (Engine*)h;
+	e->close_all();
+	delete e;
+	return 0;
+}
+
+void* jnibwa_getRefContigNames(void* h, size_t* size) { return h ? contig_names_blob(((Engine*)h)->img, size) : nullptr; }
+
+void* jnibwa_createAlignments(void* h, void* opt, void* pes, char* seqs, size_t* size)
+{
+	if (!h || !opt || !seqs || !size) return nullptr;
+	Engine* e = (Engine*)h;
+	g_last_cuda = cudaSuccess;
+	g_timer.begin();
+	g_launches = 0;
+	void* r = e->align((const MemOpt*)opt, (const PeStat*)pes, seqs, size);
+	e->n_launches = g_launches;
+	if (r && (g_last_cuda != cudaSuccess || cudaGetLastError() != cudaSuccess)) { free(r); r = nullptr; e->last_error = "CUDA error during the batch"; }
+	if (!r) fprintf(stderr, "[bwamem-b200] createAlignments: %s\n", e->last_error.c_str());
+	return r;
+}
+
+void* mem_opt_init(void) { return default_options(); }
+void jnibwa_free(void* p) { free(p); }
+const char* jnibwa_getVersion(void) { return "bwamem-b200 0.1 (sm_100a; bwa-mem semantics of lh3/bwa cb95061)"; }
+
+// ---- instrumentation for bench.py ------------------------------------------------------------------
+int b200_setDevice(int dev) { return cudaSetDevice(dev) == cudaSuccess ? 0 : 1; }
+const char* b200_lastError(void* h) { return h ? ((Engine*)h)->last_error.c_str() : ""; }
+// copies up to cap stage times (ms) of the last batch; names[i] points at static strings; returns the stage count
+int b200_lastStageTimes(void* h, float* ms, const char** names, int cap)
+{
+	(void)h;
+	int n = g_timer.n < cap ? g_timer.n : cap;
+	for (int i = 0; i < n; ++i) { float t = 0; cudaEventElapsedTime(&t, g_timer.ev[i], g_timer.ev[i + 1]); ms[i] = t; names[i] = g_timer.name[i]; }
+	return n;
+}
+// counters: cells_ext, cells_glb, cells_msw, n_ext, n_glb, n_msw, n_seed_lookups, n_launches
+void b200_lastCounters(void* h, uint64_t* out)
+{
+	Engine* e = (Engine*)h;
+	memcpy(out, &e->last_counters, sizeof(Counters));
+	out[6] = e->last_n_seed;
+	out[7] = (uint64_t)e->n_launches;
+}
+
+} // extern "C"

@@ -70,6 +70,39 @@ struct DBuf { // growable device buffer
 
 #define LOG_TAB_N 65536
 
+// mem_opt_init of un-vendored lh3/bwa (called at …BwaMemIndex.c:91); defaults per SURVEY.md App. B.1.
+// The block is malloc'd: Java releases it through destroyByteBuffer == free (…BwaMemIndex.c:157-160).
+inline MemOpt* default_options()
+{
+	MemOpt* o = (MemOpt*)calloc(1, sizeof(MemOpt));
+	if (!o) return nullptr;
+	o->a = 1; o->b = 4; o->o_del = o->o_ins = 6; o->e_del = o->e_ins = 1; o->w = 100; o->T = 30; o->zdrop = 100;
+	o->pen_unpaired = 17; o->pen_clip5 = o->pen_clip3 = 5; o->max_mem_intv = 20; o->min_seed_len = 19; o->split_width = 10;
+	o->max_occ = 500; o->max_chain_gap = 10000; o->max_ins = 10000; o->mask_level = 0.50f; o->drop_ratio = 0.50f;
+	o->XA_drop_ratio = 0.80f; o->split_factor = 1.5f; o->chunk_size = 10000000; o->n_threads = 1; o->max_XA_hits = 5;
+	o->max_XA_hits_alt = 200; o->max_matesw = 50; o->mask_level_redun = 0.95f; o->min_chain_weight = 0;
+	o->max_chain_extend = 1 << 30; o->mapQ_coef_len = 50; o->mapQ_coef_fac = (int)log((double)o->mapQ_coef_len);
+	int k = 0;
+	for (int i = 0; i < 4; ++i) { for (int j = 0; j < 4; ++j) o->mat[k++] = i == j ? (i8)o->a : (i8)-o->b; o->mat[k++] = -1; }
+	for (int j = 0; j < 5; ++j) o->mat[k++] = -1;
+	return o;
+}
+
+// jnibwa_getRefContigNames (jnibwa.c:174-195): i32 n, then { i32 len, bytes } per contig, no NULs
+inline void* contig_names_blob(const ImageView& img, size_t* size)
+{
+	size_t sz = 4 + 4 * (size_t)img.n_seqs;
+	for (auto& c : img.contigs) sz += c.name.size();
+	char* buf = (char*)malloc(sz);
+	if (!buf) return nullptr;
+	int32_t n = img.n_seqs;
+	memcpy(buf, &n, 4);
+	char* p = buf + 4;
+	for (auto& c : img.contigs) { int32_t l = (int32_t)c.name.size(); memcpy(p, &l, 4); p += 4; memcpy(p, c.name.data(), (size_t)l); p += l; }
+	*size = sz;
+	return buf;
+}
+
 struct Engine {
 	// host view of the image
 	void* map = nullptr; size_t map_len = 0;
@@ -82,7 +115,7 @@ struct Engine {
 	DBuf b_blob, b_seq, b_seqoff, b_intv, b_nintv, b_nseed, b_smem, b_seedoff, b_rbeg, b_S, b_C, b_ord, b_tmp32, b_ck, b_ks, b_srt, b_regtmp,
 	     b_nck, b_nks, b_nreg, b_regcap, b_regoff, b_regs, b_snap, b_ztmp, b_pairv, b_recs, b_nrec, b_cand, b_pairtab, b_var, b_misc,
 	     b_outwords, b_outoff, b_out, b_wsz, b_wscig, b_wsmd, b_wsxa, b_wsbrow;
-	Counters last_counters; double last_ms[12];
+	Counters last_counters; uint64_t last_n_seed = 0; int n_launches = 0;
 	std::string last_error;
 
 	bool open_from_fd(int fd);
@@ -213,7 +246,7 @@ inline void* Engine::align(const MemOpt* opt_in, const PeStat* pes0, char* blob_
 	RT_THREADS(body_encode, P, (int64_t)blob_len);
 	RT_THREADS_TID(body_seed, P, (int64_t)n_reads);
 	uint64_t T = rt_scan_u32(P.n_seed, P.seed_off, n_reads);
-	P.n_seed_total = T;
+	P.n_seed_total = T; last_n_seed = T;
 	{
 		size_t Tn = (size_t)T + 1;
 		ok = b_rbeg.ensure(Tn * 8) && b_S.ensure(Tn * sizeof(Seed)) && b_C.ensure(Tn * sizeof(ChainW)) && b_ord.ensure(Tn * 4) && b_tmp32.ensure(Tn * 4)

@@ -120,7 +120,7 @@ DEV void make_warp_ctx(const BatchParams& P, i64 warp_slot, u8* smem, WarpMem& w
 	ws.brow = P.ws_brow + (size_t)warp_slot * P.ws_brow_cap; ws.brow_cap = P.ws_brow_cap;
 	ws.err = P.err;
 }
-DEV size_t warp_smem_bytes(int cap) { return (size_t)(4 * (cap + 2) + 16) * 4 + (size_t)((cap + 2 + 15) & ~15); }
+HOSTDEV size_t warp_smem_bytes(int cap) { return (size_t)(4 * (cap + 2) + 16) * 4 + (size_t)((cap + 2 + 15) & ~15); }
 
 // ---- extend: one warp per read -------------------------------------------------------------------
 DEV void wbody_extend(const BatchParams& P, i64 r, WarpMem& wm, WarpScratch& ws)

@@ -28,6 +28,7 @@ typedef int8_t i8;
 #include <cuda_runtime.h>
 #define DEV __device__ __forceinline__
 #define DEVNI __device__ __noinline__
+#define HOSTDEV __host__ __device__ __forceinline__
 #define DEVM __device__ __forceinline__
 #define KERNEL __global__
 #define FULLMASK 0xffffffffu
@@ -56,6 +57,7 @@ DEV u32 atomic_max_u32(u32* p, u32 v) { return atomicMax(p, v); }
 #include <algorithm>
 #define DEV static inline
 #define DEVNI static
+#define HOSTDEV static inline
 #define DEVM inline
 #define KERNEL static
 #define WV(T, name) T name[32]

@@ -1,0 +1,130 @@
+"""Shared helpers of the test-suite: library handles (oracle = checker, engine = product, sim = kernel-debug
+harness), the rotavirus fixture of the reference (tests/golden/rotavirus, copied from
+/root/reference/src/test/resources by tests/golden/make_golden.py) and seeded synthetic datasets."""
+from __future__ import annotations
+
+import ctypes
+import importlib.util
+import os
+import subprocess
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG_DIR = os.path.join(ROOT, "gatk-bwamem-jni_b200")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+WORK = os.path.join(ROOT, "tests", "_work")
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+
+def _load_pkg():
+    """The package directory name contains '-', so it is loaded by path under the name bwamem_b200."""
+    name = "bwamem_b200"
+    if name in sys.modules:
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, os.path.join(PKG_DIR, "__init__.py"),
+                                                  submodule_search_locations=[PKG_DIR])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+pkg = _load_pkg()
+bwa = pkg.bwa
+import simdata  # noqa: E402  (tools/)
+
+ORACLE_SO = os.path.join(ROOT, "oracle", "liborc.so")
+SIM_SO = os.path.join(ROOT, "tests", "cudasim", "libsim.so")
+ENGINE_SO = os.path.join(PKG_DIR, "lib", "libbwa_b200.so")
+
+
+def build_oracle():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+
+
+def build_sim():
+    src = os.path.join(ROOT, "tests", "cudasim", "sim_engine.cpp")
+    csrc = os.path.join(PKG_DIR, "csrc")
+    newest = max([os.path.getmtime(src)] + [os.path.getmtime(os.path.join(csrc, f)) for f in os.listdir(csrc)])
+    if os.path.exists(SIM_SO) and os.path.getmtime(SIM_SO) >= newest:
+        return
+    subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-Wl,-Bsymbolic", "-Wno-unknown-pragmas", "-I", csrc,
+                           "-o", SIM_SO, src])
+
+
+_libs = {}
+
+
+def oracle_lib():
+    if "orc" not in _libs:
+        build_oracle()
+        _libs["orc"] = bwa.NativeLib(ORACLE_SO, prefix="orc_", opt_init="orc_opt_init", free="orc_free")
+    return _libs["orc"]
+
+
+def sim_lib():
+    if "sim" not in _libs:
+        build_sim()
+        _libs["sim"] = bwa.NativeLib(SIM_SO, prefix="sim_", opt_init="sim_opt_init", free="sim_free")
+    return _libs["sim"]
+
+
+def engine_lib():
+    if "eng" not in _libs:
+        _libs["eng"] = bwa.NativeLib(ENGINE_SO)
+    return _libs["eng"]
+
+
+def workdir():
+    os.makedirs(WORK, exist_ok=True)
+    return WORK
+
+
+def fixture_image() -> str:
+    """tests/_work/rotavirus.img built from the checked-in bwa index files of the reference fixture."""
+    path = os.path.join(workdir(), "rotavirus.img")
+    if not os.path.exists(path):
+        rc = simdata.idxlib().jnibwa_createIndexFile(os.path.join(GOLDEN, "rotavirus", "ref.fa").encode(), path.encode())
+        assert rc == 0
+    return path
+
+
+def synth_image(tag: str, seed: int, lens, **kw):
+    """(genome, image path) of a seeded synthetic genome, cached in tests/_work."""
+    g = simdata.make_genome(seed, lens, **kw)
+    path = os.path.join(workdir(), f"{tag}.img")
+    if not os.path.exists(path):
+        simdata.build_image(g, path)
+    return g, path
+
+
+def run_blob(lib, img_path: str, blob: bytearray, flag: int = 0, stats=None, setup=None) -> bytes:
+    """One createAlignments call through the Java-API mirror; returns the raw int32 stream."""
+    idx = bwa.BwaMemIndex(img_path, lib=lib)
+    try:
+        al = bwa.BwaMemAligner(idx)
+        if flag:
+            al.setFlagOption(al.getFlagOption() | flag)
+        if setup:
+            setup(al)
+        al.pairEndStats = stats
+        out = idx.doAlignment(bytearray(blob), al._opts_addr, al.pairEndStats)
+        al.close()
+        return out
+    finally:
+        idx.close()
+
+
+def first_diff(a: bytes, b: bytes, blob: bytes, paired: bool):
+    """Human-readable description of the first read whose records differ."""
+    n = int.from_bytes(blob[:4], "little")
+    if paired:
+        n -= n & 1
+    ra = bwa.decode_alignments(a, n) if a is not None else None
+    rb = bwa.decode_alignments(b, n)
+    reads = simdata.split_blob(bytes(blob))
+    for i in range(n):
+        if ra[i] != rb[i]:
+            return f"read {i} ({reads[i].decode('latin-1')}):\n  A={ra[i]}\n  B={rb[i]}"
+    return "streams differ but decoded records are equal"

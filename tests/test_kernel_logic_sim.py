@@ -1,0 +1,38 @@
+"""CPU: the engine's kernel source (csrc/*.cuh) compiled by the kernel-debug harness (tests/cudasim, -DB200_SIM:
+warp variables become 32-lane arrays, collectives become loops) against the oracle.  This exercises the host
+orchestration (engine_impl.inl), every device function's logic and the record encoder without a GPU; the real
+parity gate is tests/test_parity_gpu.py on the B200."""
+import pytest
+
+from common import first_diff, oracle_lib, run_blob, sim_lib, simdata, synth_image
+from test_oracle_kat import run_kat
+
+
+def test_sim_known_answers():
+    run_kat(sim_lib())
+
+
+@pytest.fixture(scope="module")
+def small_genome():
+    return synth_image("g200k", 7, [120000, 60000, 20000], repeat_frac=0.08, tandem_frac=0.01, n_segdup=3)
+
+
+CASES = [
+    ("se150", dict(seed=11, n_units=400, read_len=150, paired=False), 0),
+    ("pe150", dict(seed=12, n_units=300, read_len=150, paired=True), 2),
+    ("pe250_noisy", dict(seed=13, n_units=100, read_len=250, paired=True, ins_mean=550, ins_std=80, err_rate=0.05,
+                         mut_rate=0.01, indel_frac=0.5), 2),
+    ("pe_chimeric_repeats_n", dict(seed=14, n_units=200, read_len=150, paired=True, chimeric_frac=0.1,
+                                   repeat_read_frac=0.2, n_rate=0.002), 2),
+    ("se_all_flag", dict(seed=15, n_units=200, read_len=150, paired=False, chimeric_frac=0.2, repeat_read_frac=0.3), 8),
+]
+
+
+@pytest.mark.parametrize("name,kw,flag", CASES, ids=[c[0] for c in CASES])
+def test_sim_matches_oracle(small_genome, name, kw, flag):
+    g, img = small_genome
+    kw = dict(kw)
+    blob, _ = simdata.make_reads(g, kw.pop("seed"), kw.pop("n_units"), kw.pop("read_len"), kw.pop("paired"), **kw)
+    a = run_blob(oracle_lib(), img, blob, flag)
+    b = run_blob(sim_lib(), img, blob, flag)
+    assert a == b, first_diff(a, b, blob, bool(flag & 2))

@@ -1,0 +1,106 @@
+"""GPU: the CUDA engine through its C-ABI (jnibwa_createAlignments) against the CPU oracle on the same inputs,
+options and batch boundaries.  Bar: the int32 record stream is byte-identical (flag, refId, pos, CIGAR, MAPQ, NM,
+MD, AS, XS, XA, mate fields)."""
+import pytest
+
+from common import bwa, engine_lib, first_diff, oracle_lib, run_blob, simdata, synth_image
+from test_oracle_kat import run_kat
+
+pytestmark = pytest.mark.gpu
+
+
+def test_engine_known_answers():
+    run_kat(engine_lib())
+
+
+@pytest.fixture(scope="module")
+def small_genome():
+    return synth_image("g200k", 7, [120000, 60000, 20000], repeat_frac=0.08, tandem_frac=0.01, n_segdup=3)
+
+
+@pytest.fixture(scope="module")
+def mid_genome():
+    return synth_image("g5m", 21, [3000000, 1500000, 500000], repeat_frac=0.05, tandem_frac=0.01, n_segdup=10)
+
+
+CASES = [
+    ("se150", dict(seed=11, n_units=4000, read_len=150, paired=False), 0, None),
+    ("pe150", dict(seed=12, n_units=3000, read_len=150, paired=True), 2, None),
+    ("pe250_noisy", dict(seed=13, n_units=1000, read_len=250, paired=True, ins_mean=550, ins_std=80, err_rate=0.05,
+                         mut_rate=0.01, indel_frac=0.5), 2, None),
+    ("pe_chimeric_repeats_n", dict(seed=14, n_units=2000, read_len=150, paired=True, chimeric_frac=0.1,
+                                   repeat_read_frac=0.2, n_rate=0.002), 2, None),
+    ("se_all_flag", dict(seed=15, n_units=2000, read_len=150, paired=False, chimeric_frac=0.2, repeat_read_frac=0.3), 8, None),
+    ("pe_given_stats", dict(seed=16, n_units=1000, read_len=150, paired=True), 2, (400.0, 50.0, 200, 600)),
+    ("pe_no_infer", dict(seed=17, n_units=1000, read_len=150, paired=True), 2, "failed"),
+    ("pe_no_rescue_primary5", dict(seed=18, n_units=1000, read_len=150, paired=True, chimeric_frac=0.2), 2 | 0x20 | 0x800, None),
+    ("se_short_and_ragged", dict(seed=19, n_units=500, read_len=36, paired=False), 0, None),
+]
+
+
+def _stats(s):
+    if s is None:
+        return None
+    if s == "failed":
+        return bwa.BwaMemPairEndStats.DO_NOT_INFER
+    return bwa.BwaMemPairEndStats.of(*s)
+
+
+@pytest.mark.parametrize("name,kw,flag,stats", CASES, ids=[c[0] for c in CASES])
+def test_engine_matches_oracle_small(small_genome, name, kw, flag, stats):
+    g, img = small_genome
+    kw = dict(kw)
+    blob, _ = simdata.make_reads(g, kw.pop("seed"), kw.pop("n_units"), kw.pop("read_len"), kw.pop("paired"), **kw)
+    a = run_blob(oracle_lib(), img, blob, flag, _stats(stats))
+    b = run_blob(engine_lib(), img, blob, flag, _stats(stats))
+    assert a == b, first_diff(a, b, blob, bool(flag & 2))
+
+
+def test_edge_inputs(small_genome):
+    g, img = small_genome
+    reads = [b"", b"A", b"ACGT" * 5, b"N" * 150, b"ACGTNNNNACGT" * 10, b"acgtacgtnn" * 15]
+    base, _ = simdata.make_reads(g, 30, 20, 150, False)
+    reads += simdata.split_blob(bytes(base))
+    reads.append(reads[-1][:100] + b"N" + reads[-1][101:])
+    blob = bwa.pack_sequences(reads)
+    for flag in (0, 2):  # odd read count in PE mode: the trailing read yields nothing (hazard H11)
+        a = run_blob(oracle_lib(), img, blob, flag)
+        b = run_blob(engine_lib(), img, blob, flag)
+        assert a == b, first_diff(a, b, blob, bool(flag & 2))
+    empty = bwa.pack_sequences([])
+    assert run_blob(engine_lib(), img, empty) == run_blob(oracle_lib(), img, empty)
+
+
+def test_intractg_options(small_genome):
+    """hazard H1: setIntraCtgOptions changes a/b/gap-open but not the scoring matrix."""
+    g, img = small_genome
+    blob, _ = simdata.make_reads(g, 31, 500, 250, False, err_rate=0.03)
+    setup = lambda al: al.setIntraCtgOptions()
+    a = run_blob(oracle_lib(), img, blob, 0, None, setup)
+    b = run_blob(engine_lib(), img, blob, 0, None, setup)
+    assert a == b, first_diff(a, b, blob, False)
+
+
+@pytest.mark.parametrize("paired", [False, True], ids=["se", "pe"])
+def test_engine_matches_oracle_mid(mid_genome, paired):
+    g, img = mid_genome
+    blob, _ = simdata.make_reads(g, 41 + paired, 20000, 150, paired)
+    flag = 2 if paired else 0
+
+    def setup(al):
+        al.setNThreadsOption(8)
+    a = run_blob(oracle_lib(), img, blob, flag, None, setup)
+    b = run_blob(engine_lib(), img, blob, flag, None, setup)
+    assert a == b, first_diff(a, b, blob, paired)
+
+
+def test_repeat_calls_are_deterministic(small_genome):
+    g, img = small_genome
+    blob, _ = simdata.make_reads(g, 50, 2000, 150, True)
+    idx = bwa.BwaMemIndex(img, lib=engine_lib())
+    al = bwa.BwaMemAligner(idx)
+    al.alignPairs()
+    outs = [idx.doAlignment(bytearray(blob), al._opts_addr, None) for _ in range(3)]
+    assert outs[0] == outs[1] == outs[2]
+    al.close()
+    idx.close()
