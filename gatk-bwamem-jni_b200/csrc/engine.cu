@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <unistd.h>
 #include <cuda_runtime.h>
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
@@ -48,6 +49,10 @@ static void rt_sync() { cu_ok(cudaStreamSynchronize(rt_stream()), "sync"); }
 static int64_t rt_thread_slots() { return (int64_t)rt_sm_count() * SEED_BLOCKS_PER_SM * THREADS_PER_BLOCK; }
 static int64_t rt_warp_slots() { return (int64_t)rt_sm_count() * WARP_BLOCKS_PER_SM * WARPS_PER_BLOCK; }
 
+#ifdef B200_DEBUG_CKPT
+__device__ volatile unsigned* g_ckpt = nullptr;
+static unsigned* g_ckpt_host = nullptr;
+#endif
 #include "kernels.cuh"
 
 // exclusive scan of u32 counts into u64 offsets (out[n] = total); returns the total
@@ -120,8 +125,27 @@ static u32* next_counter()
 struct StageTimer { // CUDA events on the launching stream around every stage of the last batch
 	static const int MAXS = 16;
 	cudaEvent_t ev[MAXS + 1]; const char* name[MAXS]; int n = 0; bool init = false;
-	void begin() { if (!init) { for (auto& e : ev) cudaEventCreate(&e); init = true; } n = 0; cudaEventRecord(ev[0], rt_stream()); }
-	void mark(const char* nm) { if (n < MAXS) { name[n] = nm; ++n; cudaEventRecord(ev[n], rt_stream()); } }
+	void begin() {
+#ifdef B200_DEBUG_CKPT
+		if (!g_ckpt_host) { cudaHostAlloc(&g_ckpt_host, 1024, cudaHostAllocMapped); memset(g_ckpt_host, 0, 1024); unsigned* d = nullptr; cudaHostGetDevicePointer(&d, g_ckpt_host, 0); cudaMemcpyToSymbol(g_ckpt, &d, sizeof(d)); }
+#endif
+		if (!init) { for (auto& e : ev) cudaEventCreate(&e); init = true; } n = 0; cudaEventRecord(ev[0], rt_stream()); }
+	void mark(const char* nm)
+	{
+		if (n < MAXS) { name[n] = nm; ++n; cudaEventRecord(ev[n], rt_stream()); }
+		static const bool trace = getenv("B200_TRACE") != nullptr; // development aid: synchronise and report after every stage
+		if (trace) {
+#ifdef B200_DEBUG_CKPT
+			for (int t = 0; t < 100 && cudaStreamQuery(rt_stream()) == cudaErrorNotReady; ++t) usleep(100000);
+			if (cudaStreamQuery(rt_stream()) == cudaErrorNotReady) {
+				fprintf(stderr, "[bwamem-b200] stage %s HUNG; checkpoints (warp: code val):", nm);
+				for (int w = 0; w < 16; ++w) fprintf(stderr, " %d:%u/%u", w, g_ckpt_host[2 * w], g_ckpt_host[2 * w + 1]);
+				fprintf(stderr, "\n"); fflush(stderr); _exit(3);
+			}
+#endif
+			cudaError_t e = cudaStreamSynchronize(rt_stream()); fprintf(stderr, "[bwamem-b200] stage %s: %s\n", nm, cudaGetErrorString(e)); fflush(stderr);
+		}
+	}
 };
 static StageTimer g_timer;
 static int g_launches = 0;

@@ -94,6 +94,7 @@ DEVNI bool warp_gen_cigar2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, Wa
 		*score = warp_global2(x, opt, wm, l_query, (int)rlen, ta, w, ws.z, want_cigar ? ws.cigar : nullptr, &nc, cnt ? &cnt->cells_glb : nullptr);
 		if (cnt) { ONE_LANE { atomic_add_u64(&cnt->n_glb, 1); } }
 	}
+	DBGP(400, nc);
 	if (want_cigar) {
 		// MD / NM: sequential walk (warp-uniform), text written by one lane
 		int xq = 0, y = 0, u = 0, n_mm = 0, n_gap = 0, ml = 0;
@@ -101,7 +102,7 @@ DEVNI bool warp_gen_cigar2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, Wa
 		char* md = ws.md;
 		const int cap = ws.md_cap - 16;
 		bool ovf = false;
-#define MD_PUTC(ch) do { if (ml < cap) { ONE_LANE_NOSYNC { md[ml] = (char)(ch); } ++ml; } else ovf = true; } while (0)
+#define MD_PUTC(ch) do { const char c_ = (char)(ch); /* evaluated by every lane: the argument may have side effects */ if (ml < cap) { ONE_LANE_NOSYNC { md[ml] = c_; } ++ml; } else ovf = true; } while (0)
 #define MD_PUTNUM(v) do { int v_ = (v); char b_[12]; int n_ = 0; do { b_[n_++] = (char)('0' + v_ % 10); v_ /= 10; } while (v_); while (n_) MD_PUTC(b_[--n_]); } while (0)
 		for (int k = 0; k < nc; ++k) {
 			u32 cg = ws.cigar[k];

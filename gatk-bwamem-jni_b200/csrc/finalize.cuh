@@ -160,7 +160,9 @@ DEVNI Aln warp_reg2aln(FinalCtx& f, int l_query, const u8* query, const Reg* ar)
 	int i = 0, score = 0, last_sc = -(1 << 30), NM = -1, nc = 0, ml = 0;
 	do {
 		w2 = w2 < opt.w << 2 ? w2 : opt.w << 2;
+		DBGP(300, w2);
 		warp_gen_cigar2(x, opt, *f.wm, *f.ws, f.cnt, w2, qe - qb, query + qb, rb, re, &score, true, &nc, &NM, &ml);
+		DBGP(301, score);
 		if (score == last_sc || w2 == opt.w << 2) break;
 		last_sc = score;
 		w2 <<= 1;
@@ -277,7 +279,7 @@ DEVNI int warp_gen_xa(FinalCtx& f, int l_query, const u8* query, int n, const Re
 	if (cnt == 0 || cnt > opt.max_XA_hits_alt || cnt > opt.max_XA_hits) return 0; // (no ALT contigs: has_alt is always false)
 	char* xa = f.ws->xa; const int cap = f.ws->xa_cap - 32;
 	int xl = 0; bool ovf = false;
-#define XA_PUTC(ch) do { if (xl < cap) { ONE_LANE_NOSYNC { xa[xl] = (char)(ch); } ++xl; } else ovf = true; } while (0)
+#define XA_PUTC(ch) do { const char c_ = (char)(ch); if (xl < cap) { ONE_LANE_NOSYNC { xa[xl] = c_; } ++xl; } else ovf = true; } while (0)
 #define XA_PUTNUM(v) do { long v_ = (long)(v); char b_[24]; int n_ = 0; if (v_ < 0) { XA_PUTC('-'); v_ = -v_; } do { b_[n_++] = (char)('0' + v_ % 10); v_ /= 10; } while (v_); while (n_) XA_PUTC(b_[--n_]); } while (0)
 	for (int i = 0; i < n; ++i) {
 		if (get_pri_idx(ratio, a, i) != pri) continue;
@@ -317,14 +319,18 @@ DEVNI int warp_reg2sam(FinalCtx& f, int l_seq, const u8* seq, int n, const Reg* 
 		if (p.secondary >= 0 && p.secondary < 0x7fffffff && (float)p.score < (float)a[p.secondary].score * opt.drop_ratio) continue;
 		if (l >= out_cap) { ONE_LANE { atomic_or_u32(f.ws->err, ERR_REG_OVERFLOW); } break; }
 		u32 xa_off = 0; int xa_len = 0;
+		DBGP(200, k);
 		if (!(opt.flag & MEM_F_ALL)) xa_len = warp_gen_xa(f, l_seq, seq, n, a, k, &xa_off);
+		DBGP(201, k);
 		Aln q = warp_reg2aln(f, l_seq, seq, &a[k]);
+		DBGP(202, k);
 		q.flag |= extra_flag;
 		if (p.secondary >= 0) q.sub = -1;
 		if (l && p.secondary < 0) q.flag |= (opt.flag & MEM_F_NO_MULTI) ? 0x10000 : 0x800;
 		if (l && !p.is_alt && q.mapq > mapq0) q.mapq = mapq0;
 		if (l == 0) mapq0 = q.mapq;
 		warp_emit(f, q, m, xa_off, xa_len, &out[l]);
+		DBGP(203, k);
 		++l;
 	}
 	if (l == 0) {

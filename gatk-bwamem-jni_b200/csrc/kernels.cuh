@@ -188,7 +188,9 @@ DEV void wbody_final_se(const BatchParams& P, i64 r, WarpMem& wm, WarpScratch& w
 	const u8* seq = P.seq + P.seq_off[r];
 	Reg* a = P.regs + P.reg_off[r];
 	int n = (int)P.n_reg[r];
+	DBGP(100, n);
 	warp_mark_primary_se(P.opt, n, a, r, P.ztmp + P.reg_off[r]); // id = index within the call (hazard H2)
+	DBGP(101, r);
 	if (P.opt.flag & MEM_F_PRIMARY5) warp_reorder_primary5(P.opt.T, n, a);
 	int nr = warp_reg2sam(f, len, seq, n, a, 0, nullptr, P.recs + P.reg_off[r], (int)P.reg_cap[r]);
 	ONE_LANE { P.n_rec[r] = (u32)nr; }

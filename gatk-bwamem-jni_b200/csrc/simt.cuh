@@ -85,6 +85,15 @@ DEV int __ffs(u32 x) { return x ? __builtin_ctz(x) + 1 : 0; }
 DEV int __clz(u32 x) { return x ? __builtin_clz(x) : 32; }
 #endif
 
+// Development aid (-DB200_DEBUG_CKPT builds only): lane 0 of every warp posts its last checkpoint into host-mapped
+// memory so that a hung kernel can be located from the host (engine.cu, B200_TRACE).
+#if defined(B200_DEBUG_CKPT) && !defined(B200_SIM)
+extern __device__ volatile unsigned* g_ckpt;
+#define DBGP(code, val) do { if ((threadIdx.x & 31) == 0 && g_ckpt) { unsigned w_ = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; if (w_ < 64) { g_ckpt[2 * w_] = (unsigned)(code); g_ckpt[2 * w_ + 1] = (unsigned)(val); __threadfence_system(); } } } while (0)
+#else
+#define DBGP(code, val) do {} while (0)
+#endif
+
 template <class T> DEV T imax(T a, T b) { return a > b ? a : b; }
 template <class T> DEV T imin(T a, T b) { return a < b ? a : b; }
 DEV int iabs(int a) { return a < 0 ? -a : a; }

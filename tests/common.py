@@ -36,7 +36,7 @@ import simdata  # noqa: E402  (tools/)
 
 ORACLE_SO = os.path.join(ROOT, "oracle", "liborc.so")
 SIM_SO = os.path.join(ROOT, "tests", "cudasim", "libsim.so")
-ENGINE_SO = os.path.join(PKG_DIR, "lib", "libbwa_b200.so")
+ENGINE_SO = os.environ.get("LIBBWA_PATH") or os.path.join(PKG_DIR, "lib", "libbwa_b200.so")
 
 
 def build_oracle():

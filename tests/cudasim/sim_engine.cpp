@@ -13,7 +13,7 @@
 #define B200_SIM 1
 #include "simt.cuh"
 
-static void* rt_malloc(size_t n) { return calloc(1, n ? n : 1); }
+static void* rt_malloc(size_t n) { void* p = malloc(n ? n : 1); if (p) memset(p, 0xA5, n ? n : 1); return p; } // poisoned like cudaMalloc (not zeroed)
 static void rt_free(void* p) { free(p); }
 static void rt_h2d(void* d, const void* s, size_t n) { memcpy(d, s, n); }
 static void rt_d2h(void* d, const void* s, size_t n) { memcpy(d, s, n); }

@@ -1,0 +1,45 @@
+"""Development aid: runs increasingly large batches on the GPU with per-stage timings, logging as it goes."""
+import ctypes, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from common import *
+
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+LOG = open(os.path.join(ROOT, "gpurun_out", "diag.log"), "a")
+def log(*a):
+    s = " ".join(str(x) for x in a)
+    print(s, flush=True); LOG.write(s + "\n"); LOG.flush()
+
+def stage_times(lib, idx):
+    ms = (ctypes.c_float * 32)(); names = (ctypes.c_char_p * 32)()
+    lib.dll.b200_lastStageTimes.restype = ctypes.c_int
+    n = lib.dll.b200_lastStageTimes(ctypes.c_void_p(idx._addr), ms, names, 32)
+    return [(names[i].decode(), round(ms[i], 3)) for i in range(n)]
+
+def run(tag, img, blob, flag=0, check=True):
+    eng = engine_lib()
+    idx = bwa.BwaMemIndex(img, lib=eng)
+    al = bwa.BwaMemAligner(idx)
+    al.setFlagOption(flag)
+    log(tag, "start")
+    t = time.time()
+    out = idx.doAlignment(bytearray(blob), al._opts_addr, None)
+    dt = time.time() - t
+    log(tag, f"gpu call {dt:.3f}s", stage_times(eng, idx))
+    al.close(); idx.close()
+    if check:
+        def setup(a): a.setNThreadsOption(16)
+        want = run_blob(oracle_lib(), img, blob, flag, None, setup)
+        log(tag, "PARITY", "OK" if want == out else "DIFF " + first_diff(want, out, blob, bool(flag & 2))[:2000])
+
+if __name__ == "__main__":
+    sizes = [int(x) for x in sys.argv[1:]] or [4, 100, 2000]
+    img = fixture_image()
+    blob = bwa.pack_sequences([b"GGCTTTTAATGCTTTTCAGTGGTTGCTGCTCAAGATGGAGTCTACTCAGCAGATGGTAAGCTCTATTATT"] * 2)
+    run("kat", img, blob)
+    g, img = synth_image("g200k", 7, [120000, 60000, 20000], repeat_frac=0.08, tandem_frac=0.01, n_segdup=3)
+    for n in sizes:
+        blob, _ = simdata.make_reads(g, 11, n, 150, False)
+        run(f"se{n}", img, blob)
+        blob, _ = simdata.make_reads(g, 12, n, 150, True)
+        run(f"pe{n}", img, blob, 2)
