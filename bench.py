@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the hot path (jnibwa_createAlignments: a batch of reads in -> BwaMemAlignment records out).
+
+Contract: `python bench.py --gpus N --steps K --warmup W [--impl reference]` prints ONE JSON line (rank 0).
+A "step" is one createAlignments call over one batch of synthetic 2x150 bp read pairs (batch = one pestat domain,
+exactly like one BwaMemAligner.alignSeqs call).  Under torchrun every rank owns one GPU with its own index replica
+and its own stream of batches (shard-by-call, SURVEY.md 8e: no data-path collective); `value` is the whole-job
+aggregate.
+
+  value   device time of the pipeline with the batch already resident in HBM (CUDA events on the engine's stream)
+  e2e     the same batches through the reference-facing C-ABI with HOST buffers (blob in, malloc'd record stream
+          out), wall clock, host<->device copies inside the timed region
+  roofline / kernels   per-stage device times of the last timed step, the dominant kernel against its bound
+  cpu_baseline         the CPU oracle (restatement of bwa-mem @cb95061 semantics; the real bwa is not vendored in the
+                       reference and cannot be built offline) on a bounded sample, all host cores
+
+`--impl reference` times that CPU restatement alone (all host threads) on the same config.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--genome-mbp", type=float, default=float(os.environ.get("B200_BENCH_GENOME_MBP", "256")))
+    ap.add_argument("--pairs", type=int, default=int(os.environ.get("B200_BENCH_PAIRS", "250000")),
+                    help="read pairs per step (per GPU)")
+    ap.add_argument("--read-len", type=int, default=150)
+    ap.add_argument("--cpu-sample-pairs", type=int, default=20000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, gpu: int):
+        super().__init__(daemon=True)
+        self.gpu = gpu
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                f = [x.strip() for x in out.split(",")]
+                self.samples.append(float(f[0])); self.max_mhz = float(f[1])
+                for nm, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=3)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def workload(args, rank: int, world: int):
+    """Seeded synthetic genome (contigs, injected repeat families / tandem repeats / segmental duplications)
+    + wgsim-style 2x150 bp pairs.  Built once by rank 0, shared through tests/_work."""
+    import common
+    total = int(args.genome_mbp * 1e6)
+    n_ctg = 4 if total >= 4_000_000 else 1
+    lens = [total // n_ctg] * n_ctg
+    tag = f"bench_g{total}"
+    img = os.path.join(common.workdir(), tag + ".img")
+    g = common.simdata.make_genome(2, lens, repeat_frac=0.05, tandem_frac=0.01, n_segdup=50 if total >= 50_000_000 else 5)
+    if rank == 0 and not os.path.exists(img):
+        t = time.time()
+        common.simdata.build_image(g, img + ".tmp")
+        os.replace(img + ".tmp", img)
+        sys.stderr.write(f"[bench] built index image for {total} bp in {time.time() - t:.1f}s\n")
+    return g, img
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+
+
+def allreduce_max(x: float, world) -> float:
+    if world <= 1:
+        return x
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def allreduce_sum(x: float, world) -> float:
+    if world <= 1:
+        return x
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def oracle_counters(lib):
+    class C(ctypes.Structure):
+        _fields_ = [(n, ctypes.c_uint64) for n in ("n_occ", "n_sa", "n_extend", "n_sa_lookup", "cells_ext", "cells_msw",
+                                                    "cells_glb", "n_ext_calls", "n_msw_calls", "n_glb_calls", "n_seeds",
+                                                    "n_chains", "n_regs")]
+    c = C()
+    lib.dll.orc_get_counters(ctypes.byref(c), 1)
+    return {n: int(getattr(c, n)) for n, _ in C._fields_}
+
+
+def run_oracle(img, blob, flag, threads):
+    """One createAlignments call of the CPU oracle with `threads` host threads; returns (seconds, counters, bytes)."""
+    import common
+    lib = common.oracle_lib()
+    idx = common.bwa.BwaMemIndex(img, lib=lib)
+    al = common.bwa.BwaMemAligner(idx)
+    al.setFlagOption(flag)
+    al.setNThreadsOption(threads)
+    oracle_counters(lib)
+    t = time.time()
+    out = idx.doAlignment(bytearray(blob), al._opts_addr, None)
+    dt = time.time() - t
+    cnt = oracle_counters(lib)
+    al.close(); idx.close()
+    return dt, cnt, out
+
+
+def main():
+    args = parse_args()
+    rank, world, local = dist_env()
+    cores = os.cpu_count() or 1
+    cfg = {"workload": f"synthetic {args.genome_mbp:g} Mbp genome (4 contigs, 5% interspersed repeats, 1% tandem, segdups), "
+                       f"2x{args.read_len} bp wgsim-style pairs (insert N(400,50), 0.1% mutations, 1% base error), "
+                       f"{args.pairs} pairs per createAlignments call per GPU, default mem_opt_t + MEM_F_PE, pestat inferred per call",
+           "genome_bp": int(args.genome_mbp * 1e6), "pairs_per_step_per_gpu": args.pairs, "read_len": args.read_len,
+           "parallelism": f"index replica per GPU, shard-by-call x{world}", "cache": "index + batch exceed L2; a different batch every step",
+           "note": "BASELINE's 3 Gbp genome needs an index build that is a 'next' row (SURVEY 8f.1); same kernels, smaller index"}
+
+    # ---------------- reference arm: the CPU restatement on all host cores -----------------------------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        import common
+        g, img = workload(args, 0, 1)
+        n = min(args.pairs, args.cpu_sample_pairs)
+        times = []
+        for s in range(args.warmup + args.steps):
+            blob, _ = common.simdata.make_reads(g, 1000 + s, n, args.read_len, True)
+            dt, _, _ = run_oracle(img, blob, 2, cores)
+            if s >= args.warmup:
+                times.append(dt)
+        tot = sum(times)
+        val = n * len(times) / tot
+        print(json.dumps({"metric": "aligned read-pairs/sec", "value": val, "unit": "pairs/s", "impl": "reference", "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": cfg,
+                          "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port",
+                                           "sample": f"{n} pairs per step of the same workload (CPU restatement of bwa-mem, gcc -O2, {cores} threads)"},
+                          "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    # ---------------- B200 arm ------------------------------------------------------------------------------
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import common
+    eng = common.engine_lib()
+    assert eng.dll.b200_setDevice(local) == 0
+    g, img = workload(args, rank, world)
+    barrier(world)
+    idx = common.bwa.BwaMemIndex(img, lib=eng)
+    al = common.bwa.BwaMemAligner(idx)
+    al.alignPairs()
+    dll = eng.dll
+    dll.b200_alignStaged.restype = ctypes.c_longlong
+    dll.b200_alignStaged.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    dll.b200_stageBatch.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+    dll.b200_lastBatchMs.restype = ctypes.c_float
+    dll.b200_lastBatchMs.argtypes = [ctypes.c_void_p]
+    dll.b200_lastStageTimes.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    dll.b200_lastCounters.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    h = ctypes.c_void_p(idx._addr)
+
+    n_steps = args.warmup + args.steps
+    n_distinct = min(n_steps, 4)
+    blobs = [bytes(common.simdata.make_reads(g, 1000 + rank * 100 + s, args.pairs, args.read_len, True)[0]) for s in range(n_distinct)]
+    h2d = len(blobs[0])
+
+    # ---- HBM-resident leg: stage (untimed), run (timed by CUDA events on the engine's stream)
+    sampler = ClockSampler(local) if rank == 0 else None
+    dev_ms, out_bytes = [], 0
+    for s in range(n_steps):
+        if s == args.warmup:
+            barrier(world); torch.cuda.synchronize()
+            if sampler:
+                sampler.start()
+        assert dll.b200_stageBatch(h, blobs[s % n_distinct]) == 0
+        sz = dll.b200_alignStaged(h, al._opts_addr, None)
+        assert sz > 0, "alignStaged failed"
+        if s >= args.warmup:
+            dev_ms.append(float(dll.b200_lastBatchMs(h)))
+            out_bytes = int(sz)
+    torch.cuda.synchronize(); barrier(world)
+    clocks = sampler.stop() if sampler else None
+    ms = (ctypes.c_float * 32)(); names = (ctypes.c_char_p * 32)()
+    ns = dll.b200_lastStageTimes(h, ms, names, 32)
+    stages = [(names[i].decode(), float(ms[i])) for i in range(ns)]
+    cnt = (ctypes.c_uint64 * 8)()
+    dll.b200_lastCounters(h, cnt)
+    t_dev = allreduce_max(sum(dev_ms) / 1e3, world)
+    value = world * args.pairs * args.steps / t_dev
+
+    # ---- end-to-end leg: host blob in -> host record stream out through jnibwa_createAlignments
+    e2e_t = []
+    for s in range(args.warmup + args.steps):
+        if s == args.warmup:
+            barrier(world); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+        out = idx.doAlignment(bytearray(blobs[s % n_distinct]), al._opts_addr, None)
+    torch.cuda.synchronize()
+    t_e2e = allreduce_max(time.perf_counter() - t0, world)
+    e2e = world * args.pairs * args.steps / t_e2e
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel + per-kernel table (algorithmic work from the oracle's counters on a sample)
+    n_s = min(args.pairs, args.cpu_sample_pairs)
+    sample_blob = blobs[(n_steps - 1) % n_distinct]
+    reads = sample_blob[4:].split(b"\0")[:2 * n_s]
+    sblob = common.bwa.pack_sequences(reads)
+    cpu = None
+    work = None
+    if not args.no_cpu_baseline:
+        dt, oc, ref_out = run_oracle(img, sblob, 2, cores)
+        scale = args.pairs / n_s
+        work = {k: v * scale for k, v in oc.items()}
+        cpu = {"value": n_s / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
+               "sample": f"first {n_s} pairs of the last timed batch (CPU restatement of bwa-mem @cb95061 semantics, gcc -O2, {cores} threads)"}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6545.9))
+    kern = []
+    tot_ms = sum(t for _, t in stages) or 1.0
+    for nm, t in stages:
+        k = {"kernel": nm, "ms": round(t, 3), "share": round(t / tot_ms, 4)}
+        if work:
+            if nm == "body_seed":
+                k["algorithmic_bytes"] = 64 * (work["n_occ"] - work["n_sa_lookup"] * 0)  # occ-block touches of SMEM + SA walks are counted together below
+            if nm == "wbody_extend":
+                k["gcups"] = round(work["cells_ext"] / (t * 1e6), 3)
+        kern.append(k)
+    dom = max(stages, key=lambda x: x[1])
+    roof = {"bound": "hbm", "kernel": dom[0], "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback"}
+    if work:
+        fm_bytes = 64.0 * work["n_occ"] + 8.0 * work["n_sa"]
+        fm_ms = sum(t for nm, t in stages if nm in ("body_seed", "body_sal")) or 1e-9
+        dp_cells = {"wbody_extend": work["cells_ext"], "wbody_final_pe": work["cells_msw"] + work["cells_glb"]}
+        # algorithmic bytes of a DP kernel: 1 byte per query/target base fetched + 8 bytes of H/E state per cell (scalar formulation)
+        if dom[0] in dp_cells:
+            roof["note"] = "dominant kernel is integer DP (DPX pipe), not HBM-bound: achieved = cell updates x 8 B of H/E state / time"
+            roof["achieved"] = dp_cells[dom[0]] * 8.0 / (dom[1] * 1e6)
+            roof["gcups"] = dp_cells[dom[0]] / (dom[1] * 1e6)
+        else:
+            roof["achieved"] = fm_bytes / (fm_ms * 1e6)
+        roof["frac"] = roof["achieved"] / hbm_peak
+        roof["fm_index"] = {"algorithmic_bytes_per_step": fm_bytes, "ms": round(fm_ms, 3), "gbs": fm_bytes / (fm_ms * 1e6)}
+    line = {"metric": "aligned read-pairs/sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+            "data": "synthetic", "config": cfg, "clocks": clocks,
+            "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": out_bytes},
+            "gpu_launches": int(cnt[7]) * args.steps, "roofline": roof, "kernels": kern, "cpu_baseline": cpu}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -162,6 +162,8 @@ static int g_launches = 0;
 	cudaFuncSetAttribute(k_##wbody, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_); \
 	k_##wbody<<<(unsigned)nb_, WARPS_PER_BLOCK * 32, sm_, rt_stream()>>>(P, n_, next_counter()); ++g_launches; } g_timer.mark(#wbody); } while (0)
 
+static void rt_timer_begin() { g_timer.begin(); g_launches = 0; }
+
 #include "engine_impl.inl"
 
 using namespace b200;
@@ -198,8 +200,6 @@ void* jnibwa_createAlignments(void* h, void* opt, void* pes, char* seqs, size_t*
 	if (!h || !opt || !seqs || !size) return nullptr;
 	Engine* e = (Engine*)h;
 	g_last_cuda = cudaSuccess;
-	g_timer.begin();
-	g_launches = 0;
 	void* r = e->align((const MemOpt*)opt, (const PeStat*)pes, seqs, size);
 	e->n_launches = g_launches;
 	if (r && (g_last_cuda != cudaSuccess || cudaGetLastError() != cudaSuccess)) { free(r); r = nullptr; e->last_error = "CUDA error during the batch"; }
@@ -212,6 +212,32 @@ void jnibwa_free(void* p) { free(p); }
 const char* jnibwa_getVersion(void) { return "bwamem-b200 0.1 (sm_100a; bwa-mem semantics of lh3/bwa cb95061)"; }
 
 // ---- instrumentation for bench.py ------------------------------------------------------------------
+// HBM-resident measurement: stage a request (host parse + upload, untimed by the caller), then run the device
+// pipeline on it leaving the record stream in device memory.  Returns the stream's byte size, or -1.
+int b200_stageBatch(void* h, const char* seqs)
+{
+	Engine* e = (Engine*)h;
+	std::lock_guard<std::mutex> lock(e->mu);
+	return e->stage(seqs) ? 0 : 1;
+}
+long long b200_alignStaged(void* h, void* opt, void* pes)
+{
+	Engine* e = (Engine*)h;
+	std::lock_guard<std::mutex> lock(e->mu);
+	size_t size = 0;
+	g_last_cuda = cudaSuccess;
+	void* r = e->run((const MemOpt*)opt, (const PeStat*)pes, &size, false);
+	e->n_launches = g_launches;
+	if (!r || g_last_cuda != cudaSuccess) { fprintf(stderr, "[bwamem-b200] alignStaged: %s\n", e->last_error.c_str()); return -1; }
+	return (long long)size;
+}
+// device time of the last batch: first to last stage event on the engine's stream (ms)
+float b200_lastBatchMs(void* h)
+{
+	(void)h; float t = 0;
+	if (g_timer.n > 0) cudaEventElapsedTime(&t, g_timer.ev[0], g_timer.ev[g_timer.n]);
+	return t;
+}
 int b200_setDevice(int dev) { return cudaSetDevice(dev) == cudaSuccess ? 0 : 1; }
 const char* b200_lastError(void* h) { return h ? ((Engine*)h)->last_error.c_str() : ""; }
 // copies up to cap stage times (ms) of the last batch; names[i] points at static strings; returns the stage count

@@ -121,6 +121,10 @@ struct Engine {
 	bool open_from_fd(int fd);
 	bool upload();
 	void close_all();
+	// staged request
+	bool st_valid = false; uint32_t st_n_reads = 0; int st_max_len = 0; uint64_t st_blob_len = 0; std::vector<uint64_t> st_seq_off;
+	bool stage(const char* blob);
+	void* run(const MemOpt* opt, const PeStat* pes0, size_t* out_size, bool host_output);
 	void* align(const MemOpt* opt, const PeStat* pes0, char* blob, size_t* out_size);
 };
 
@@ -178,28 +182,57 @@ inline void Engine::close_all()
 }
 
 // misc block layout (u32 words): [0] err  [1] work counter  [2] var cursor  [8..] Counters
-inline void* Engine::align(const MemOpt* opt_in, const PeStat* pes0, char* blob_in, size_t* out_size)
+// Stage a request: one host pass over the blob for the read boundaries, then upload of bases and offsets.
+inline bool Engine::stage(const char* blob_in)
 {
-	std::lock_guard<std::mutex> lock(mu);
-	last_error.clear();
-	*out_size = 0;
-	MemOpt opt = *opt_in; // the options live in a caller-owned buffer (…BwaMemIndex.c:146): snapshot them
+	st_valid = false;
 	uint32_t n_reads; memcpy(&n_reads, blob_in, 4);
 	const char* base = blob_in + 4;
-	// ---- parse the request on the host: one pass for the read boundaries
-	std::vector<uint64_t> seq_off((size_t)n_reads + 1);
+	st_seq_off.resize((size_t)n_reads + 1);
 	int max_len = 0;
 	{
 		const char* p = base;
 		for (uint32_t i = 0; i < n_reads; ++i) {
 			size_t l = strlen(p);
-			seq_off[i] = (uint64_t)(p - base);
+			st_seq_off[i] = (uint64_t)(p - base);
 			if ((int)l > max_len) max_len = (int)l;
 			p += l + 1;
 		}
-		seq_off[n_reads] = (uint64_t)(p - base);
+		st_seq_off[n_reads] = (uint64_t)(p - base);
 	}
-	const uint64_t blob_len = seq_off[n_reads];
+	st_n_reads = n_reads; st_max_len = max_len; st_blob_len = st_seq_off[n_reads];
+	if (n_reads) {
+		if (!(b_blob.ensure(st_blob_len + 16) && b_seqoff.ensure(((size_t)n_reads + 1) * 8))) { last_error = "device allocation failed"; return false; }
+		rt_h2d(b_blob.p, base, st_blob_len);
+		rt_h2d(b_seqoff.p, st_seq_off.data(), st_seq_off.size() * 8);
+		rt_sync();
+	}
+	st_valid = true;
+	return true;
+}
+
+inline void* Engine::align(const MemOpt* opt_in, const PeStat* pes0, char* blob_in, size_t* out_size)
+{
+	std::lock_guard<std::mutex> lock(mu);
+	last_error.clear();
+	*out_size = 0;
+	if (!stage(blob_in)) return nullptr;
+	return run(opt_in, pes0, out_size, true);
+}
+
+// Run the device pipeline on the staged request.  host_output: copy the record stream into a malloc'd buffer (the
+// reference contract); otherwise it stays in device memory (bench.py's HBM-resident measurement) and a non-null
+// sentinel is returned.
+inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_size, bool host_output)
+{
+	*out_size = 0;
+	if (!st_valid) { last_error = "no staged request"; return nullptr; }
+	rt_timer_begin();
+	MemOpt opt = *opt_in; // the options live in a caller-owned buffer (…BwaMemIndex.c:146): snapshot them
+	const uint32_t n_reads = st_n_reads;
+	const std::vector<uint64_t>& seq_off = st_seq_off;
+	const int max_len = st_max_len;
+	const uint64_t blob_len = st_blob_len;
 	const bool pe = (opt.flag & MEM_F_PE) != 0;
 	const int n_units = pe ? (int)(n_reads >> 1) : (int)n_reads;
 	if (n_reads == 0) { void* r = malloc(1); return r; }
@@ -209,7 +242,7 @@ inline void* Engine::align(const MemOpt* opt_in, const PeStat* pes0, char* blob_
 		// mem_flt_chained_seeds (long-read seed re-scoring) is not on this path: refuse reads that would trigger it
 		for (uint32_t i = 0; i < n_reads; ++i) {
 			int l = (int)(seq_off[i + 1] - seq_off[i] - 1);
-			if (l <= 0) continue;
+			if (l < opt.min_seed_len) continue; // no seed can exist: the filter has nothing to act on
 			double min_l = opt.min_chain_weight ? 1.1f * opt.min_chain_weight : 5.5f * log((double)l);
 			if (!(min_l > 0.05f * l)) { last_error = "read length/min_chain_weight would enable mem_flt_chained_seeds (long-read path not built)"; return nullptr; }
 		}
@@ -222,7 +255,7 @@ inline void* Engine::align(const MemOpt* opt_in, const PeStat* pes0, char* blob_
 	P.x = dx; P.opt = opt; P.n_reads = (int)n_reads; P.n_units = n_units; P.blob_len = blob_len;
 	P.ctg_names = (const char*)d_names.p; P.ctg_name_off = (const u32*)d_name_off.p;
 	bool ok = true;
-	ok &= b_blob.ensure(blob_len + 16) && b_seq.ensure(blob_len + 16) && b_seqoff.ensure(((size_t)n_reads + 1) * 8);
+	ok &= b_seq.ensure(blob_len + 16);
 	ok &= b_intv.ensure((size_t)n_reads * intv_cap * sizeof(Intv)) && b_nintv.ensure((size_t)n_reads * 4) && b_nseed.ensure((size_t)n_reads * 4);
 	const int64_t tslots = rt_thread_slots(), wslots = rt_warp_slots();
 	ok &= b_smem.ensure((size_t)tslots * 2 * (size_t)(max_len + 1) * sizeof(Intv));
@@ -232,8 +265,6 @@ inline void* Engine::align(const MemOpt* opt_in, const PeStat* pes0, char* blob_
 	if (!ok) { last_error = "device allocation failed"; return nullptr; }
 	rt_memset(b_misc.p, 0, 1024);
 	P.err = b_misc.as<u32>(); P.work_counter = b_misc.as<u32>() + 1; P.var_cursor = b_misc.as<u32>() + 2; P.cnt = (Counters*)(b_misc.as<u32>() + 8);
-	rt_h2d(b_blob.p, base, blob_len);
-	rt_h2d(b_seqoff.p, seq_off.data(), seq_off.size() * 8);
 	P.blob = b_blob.as<u8>(); P.seq = b_seq.as<u8>(); P.seq_off = b_seqoff.as<u64>();
 	P.intv = b_intv.as<Intv>(); P.intv_cap = intv_cap; P.n_intv = b_nintv.as<u32>(); P.n_seed = b_nseed.as<u32>();
 	P.smem_scratch = b_smem.as<Intv>(); P.smem_cap = max_len + 1;
@@ -324,6 +355,7 @@ inline void* Engine::align(const MemOpt* opt_in, const PeStat* pes0, char* blob_
 		last_error = buf;
 		return nullptr;
 	}
+	if (!host_output) { *out_size = (size_t)W * 4; rt_sync(); return (void*)b_out.p; }
 	void* res = malloc((size_t)W * 4 + 4);
 	if (!res) { last_error = "host allocation failed"; return nullptr; }
 	rt_d2h(res, P.out, (size_t)W * 4);

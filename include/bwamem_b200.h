@@ -75,6 +75,11 @@ int b200_setDevice(int dev);
 const char* b200_lastError(void* idx);
 int b200_lastStageTimes(void* idx, float* ms, const char** names, int cap);
 void b200_lastCounters(void* idx, uint64_t* out8);
+float b200_lastBatchMs(void* idx);
+/* HBM-resident measurement: stage = host parse + upload; alignStaged = device pipeline only, result stays in HBM
+ * (returns its byte size, -1 on failure) */
+int b200_stageBatch(void* idx, const char* pSeq);
+long long b200_alignStaged(void* idx, void* pOpts, void* pStats);
 /* index construction straight from bases in memory (synthetic-genome tools) */
 int b200_buildImageFromBases(int n_contigs, const char* names, const int64_t* lens, const char* bases,
                              const char* imgName, const char* prefixOrNull);

@@ -32,6 +32,7 @@ static uint64_t rt_scan_u32(const uint32_t* in, uint64_t* out, uint64_t n) { uin
 	WarpMem wm_; WarpScratch ws_; make_warp_ctx(P, 0, sm_.data(), wm_, ws_); \
 	for (int64_t i_ = 0; i_ < (int64_t)(n); ++i_) wbody(P, i_, wm_, ws_); } while (0)
 
+static void rt_timer_begin() {}
 #include "engine_impl.inl"
 
 using namespace b200;
