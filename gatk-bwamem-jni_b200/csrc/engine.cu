@@ -96,7 +96,7 @@ static uint64_t rt_scan_u32(const uint32_t* in, uint64_t* out, uint64_t n)
 			if (lane == 0) item = atomicAdd(counter, 1u); \
 			item = __shfl_sync(FULLMASK, item, 0); \
 			if ((i64)item >= n) break; \
-			wbody(P, (i64)item, wm, ws); \
+			wbody<32>(P, (i64)item, wm, ws); \
 			__syncwarp(); \
 		} }
 

@@ -54,6 +54,7 @@ DEV int ref_clip_window(const DevIndex& x, i64& beg, i64 mid, i64& end)
 // bwa_gen_cigar2.  query points at the nt4 codes of the read segment [0,l_query) in global memory.
 // want_cigar: write cigar words to ws.cigar and the MD text to ws.md (NUL-terminated), set *n_cigar, *NM, *md_len.
 // Returns false when the request is rejected (empty / straddling the strand junction).
+template <int W>
 DEVNI bool warp_gen_cigar2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, WarpScratch& ws, Counters* cnt, int w_,
                            int l_query, const u8* query, i64 rb, i64 re, int* score, bool want_cigar, int* n_cigar, int* NM, int* md_len)
 {
@@ -67,14 +68,14 @@ DEVNI bool warp_gen_cigar2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, Wa
 	const bool rev = rb >= l_pac; // reverse (not complement) both sequences so that indels left-align on the forward strand
 	TAcc ta; ta.piv = -1;
 	if (rev) { ta.base = re - 1; ta.stride = -1; } else { ta.base = rb; ta.stride = 1; }
-	FOR_LANES { for (int j = lane; j < l_query; j += 32) wm.q[j] = rev ? query[l_query - 1 - j] : query[j]; }
+	FOR_LANES { for (int j = lane; j < l_query; j += W) wm.q[j] = rev ? query[l_query - 1 - j] : query[j]; }
 	WARP_SYNC();
 	int nc = 0;
 	if (l_query == rlen && w_ == 0) { // ungapped: one M run, score by direct summation
 		WV(int, part);
-		FOR_LANES { int s = 0; for (int j = lane; j < l_query; j += 32) s += (int)opt.mat[ref_base2(x, tacc_pos(ta, j)) * 5 + wm.q[j]]; L_(part) = s; }
+		FOR_LANES { int s = 0; for (int j = lane; j < l_query; j += W) s += (int)opt.mat[ref_base2(x, tacc_pos(ta, j)) * 5 + wm.q[j]]; L_(part) = s; }
 		int tot = 0;
-		for (int l = 0; l < 32; ++l) tot += wv_get(part, l);
+		for (int l = 0; l < W; ++l) tot += wv_get(part, l);
 		*score = tot;
 		if (want_cigar) { ONE_LANE { ws.cigar[0] = (u32)l_query << 4; } nc = 1; WARP_SYNC(); }
 	} else {
@@ -91,7 +92,7 @@ DEVNI bool warp_gen_cigar2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, Wa
 			int n_col = l_query < 2 * w + 1 ? l_query : 2 * w + 1;
 			if ((size_t)n_col * (size_t)rlen > ws.z_cap) { ONE_LANE { atomic_or_u32(ws.err, ERR_Z_OVERFLOW); } return false; }
 		}
-		*score = warp_global2(x, opt, wm, l_query, (int)rlen, ta, w, ws.z, want_cigar ? ws.cigar : nullptr, &nc, cnt ? &cnt->cells_glb : nullptr);
+		*score = warp_global2<W>(x, opt, wm, l_query, (int)rlen, ta, w, ws.z, want_cigar ? ws.cigar : nullptr, &nc, cnt ? &cnt->cells_glb : nullptr);
 		if (cnt) { ONE_LANE { atomic_add_u64(&cnt->n_glb, 1); } }
 	}
 	DBGP(400, nc);
@@ -132,6 +133,7 @@ DEVNI bool warp_gen_cigar2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, Wa
 	return true;
 }
 
+template <int W>
 DEV int patch_reg(const DevIndex& x, const MemOpt& opt, WarpMem& wm, WarpScratch& ws, Counters* cnt, const u8* query, const Reg& a, const Reg& b, int* w_out)
 {
 	if (query == nullptr) return 0;
@@ -146,7 +148,7 @@ DEV int patch_reg(const DevIndex& x, const MemOpt& opt, WarpMem& wm, WarpScratch
 	w += a.w + b.w;
 	w = w < opt.w << 2 ? w : opt.w << 2;
 	int score = 0;
-	warp_gen_cigar2(x, opt, wm, ws, cnt, w, b.qe - a.qb, query + a.qb, a.rb, b.re, &score, false, nullptr, nullptr, nullptr);
+	warp_gen_cigar2<W>(x, opt, wm, ws, cnt, w, b.qe - a.qb, query + a.qb, a.rb, b.re, &score, false, nullptr, nullptr, nullptr);
 	int q_s = (int)((double)(b.qe - a.qb) / (double)((b.qe - b.qb) + (a.qe - a.qb)) * (double)(b.score + a.score) + .499);
 	int r_s = (int)((double)(b.re - a.rb) / (double)((b.re - b.rb) + (a.re - a.rb)) * (double)(b.score + a.score) + .499);
 	if ((double)score / (double)(q_s > r_s ? q_s : r_s) < (double)0.90f) return 0;
@@ -160,12 +162,13 @@ struct RegLtScore { DEVM bool operator()(const Reg& a, const Reg& b) const { ret
 struct RegLtHash { DEVM bool operator()(const Reg& a, const Reg& b) const { return a.score > b.score || (a.score == b.score && (a.is_alt < b.is_alt || (a.is_alt == b.is_alt && a.hash < b.hash))); } };
 
 #ifndef B200_SIM
-#define LANE0_ONLY __syncwarp(); if (lane == 0)
+#define LANE0_ONLY wsync_<W>(); if (lane == 0)
 #else
 #define LANE0_ONLY
 #endif
 
 // mem_sort_dedup_patch; query == nullptr disables patching (the mate-rescue call sites)
+template <int W>
 DEVNI int warp_sort_dedup_patch(const DevIndex& x, const MemOpt& opt, WarpMem& wm, WarpScratch& ws, Counters* cnt, const u8* query, int n, Reg* a)
 {
 	LANE_DECL;
@@ -187,7 +190,7 @@ DEVNI int warp_sort_dedup_patch(const DevIndex& x, const MemOpt& opt, WarpMem& w
 			if ((float)or_ > opt.mask_level_redun * (float)mr && (float)oq > opt.mask_level_redun * (float)mq) {
 				if (p.score < q.score) { p.qe = p.qb; p_dirty = true; break; }
 				else { ONE_LANE { a[j].qe = a[j].qb; } WARP_SYNC(); }
-			} else if (q.rb < p.rb && (score = patch_reg(x, opt, wm, ws, cnt, query, q, p, &w)) > 0) {
+			} else if (q.rb < p.rb && (score = patch_reg<W>(x, opt, wm, ws, cnt, query, q, p, &w)) > 0) {
 				p.n_comp += q.n_comp + 1;
 				p.seedcov = p.seedcov > q.seedcov ? p.seedcov : q.seedcov;
 				p.sub = p.sub > q.sub ? p.sub : q.sub;
@@ -217,6 +220,7 @@ DEVNI int warp_sort_dedup_patch(const DevIndex& x, const MemOpt& opt, WarpMem& w
 }
 
 // mem_chain2aln for one chain; av[0..*n_av) accumulates the regions of the read
+template <int W>
 DEVNI void warp_chain2aln(const DevIndex& x, const MemOpt& opt, WarpMem& wm, WarpScratch& ws, Counters* cnt, int l_query, const u8* query,
                           const ChainK& c, const Seed* seeds, u64* srt, Reg* av, int* n_av, int av_cap)
 {
@@ -274,7 +278,7 @@ DEVNI void warp_chain2aln(const DevIndex& x, const MemOpt& opt, WarpMem& wm, War
 		int aw0 = opt.w, aw1 = opt.w;
 		a.w = opt.w; a.score = a.truesc = -1; a.rid = c.rid;
 		if (s.qbeg) { // left extension: both sequences reversed
-			FOR_LANES { for (int j = lane; j < s.qbeg; j += 32) wm.q[j] = query[s.qbeg - 1 - j]; }
+			FOR_LANES { for (int j = lane; j < s.qbeg; j += W) wm.q[j] = query[s.qbeg - 1 - j]; }
 			WARP_SYNC();
 			TAcc ta; ta.base = s.rbeg - 1; ta.stride = -1; ta.piv = -1;
 			int tlen = (int)(s.rbeg - rmax0);
@@ -282,7 +286,7 @@ DEVNI void warp_chain2aln(const DevIndex& x, const MemOpt& opt, WarpMem& wm, War
 			for (int t = 0; t < 2; ++t) {
 				int prev = a.score;
 				aw0 = opt.w << t;
-				warp_extend2(x, opt, wm, s.qbeg, tlen, ta, aw0, opt.pen_clip5, opt.zdrop, s.len * opt.a, er, cnt ? &cnt->cells_ext : nullptr);
+				warp_extend2<W>(x, opt, wm, s.qbeg, tlen, ta, aw0, opt.pen_clip5, opt.zdrop, s.len * opt.a, er, cnt ? &cnt->cells_ext : nullptr);
 				if (cnt) { ONE_LANE { atomic_add_u64(&cnt->n_ext, 1); } }
 				a.score = er.score;
 				if (a.score == prev || er.max_off < (aw0 >> 1) + (aw0 >> 2)) break;
@@ -293,7 +297,7 @@ DEVNI void warp_chain2aln(const DevIndex& x, const MemOpt& opt, WarpMem& wm, War
 		if (s.qbeg + s.len != l_query) { // right extension
 			int qe = s.qbeg + s.len, sc0 = a.score;
 			i64 re = s.rbeg + s.len;
-			FOR_LANES { for (int j = lane; j < l_query - qe; j += 32) wm.q[j] = query[qe + j]; }
+			FOR_LANES { for (int j = lane; j < l_query - qe; j += W) wm.q[j] = query[qe + j]; }
 			WARP_SYNC();
 			TAcc ta; ta.base = re; ta.stride = 1; ta.piv = -1;
 			int tlen = (int)(rmax1 - re);
@@ -301,7 +305,7 @@ DEVNI void warp_chain2aln(const DevIndex& x, const MemOpt& opt, WarpMem& wm, War
 			for (int t = 0; t < 2; ++t) {
 				int prev = a.score;
 				aw1 = opt.w << t;
-				warp_extend2(x, opt, wm, l_query - qe, tlen, ta, aw1, opt.pen_clip3, opt.zdrop, sc0, er, cnt ? &cnt->cells_ext : nullptr);
+				warp_extend2<W>(x, opt, wm, l_query - qe, tlen, ta, aw1, opt.pen_clip3, opt.zdrop, sc0, er, cnt ? &cnt->cells_ext : nullptr);
 				if (cnt) { ONE_LANE { atomic_add_u64(&cnt->n_ext, 1); } }
 				a.score = er.score;
 				if (a.score == prev || er.max_off < (aw1 >> 1) + (aw1 >> 2)) break;

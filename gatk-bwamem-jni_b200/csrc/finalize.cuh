@@ -16,6 +16,7 @@ struct FinalCtx {
 	const double* pair_tab; const i64* pair_tab_off; // per-orientation pairing term for dist in [low,high] (hazard H5)
 };
 
+template <int W>
 DEV u32 var_alloc(FinalCtx& f, u32 n_words)
 {
 	LANE_DECL;
@@ -59,6 +60,7 @@ DEV void mark_primary_core(const MemOpt& opt, int n, Reg* a, u32* z)
 }
 
 // returns n_pri (== n: ALT contigs are refused at index open)
+template <int W>
 DEVNI int warp_mark_primary_se(const MemOpt& opt, int n, Reg* a, i64 id, u32* ztmp)
 {
 	LANE_DECL;
@@ -73,6 +75,7 @@ DEVNI int warp_mark_primary_se(const MemOpt& opt, int n, Reg* a, i64 id, u32* zt
 	return n;
 }
 
+template <int W>
 DEVNI void warp_reorder_primary5(int T, int n, Reg* a)
 {
 	LANE_DECL;
@@ -143,6 +146,7 @@ DEV int infer_bw(int l1, int l2, int score, int a, int q, int r)
 
 // mem_reg2aln; ar == nullptr gives the unmapped record.  CIGAR (clips added, edge deletion squeezed) is left in
 // ws.cigar[0..n_cigar) and the MD text in ws.md[0..md_len).
+template <int W>
 DEVNI Aln warp_reg2aln(FinalCtx& f, int l_query, const u8* query, const Reg* ar)
 {
 	LANE_DECL;
@@ -161,7 +165,7 @@ DEVNI Aln warp_reg2aln(FinalCtx& f, int l_query, const u8* query, const Reg* ar)
 	do {
 		w2 = w2 < opt.w << 2 ? w2 : opt.w << 2;
 		DBGP(300, w2);
-		warp_gen_cigar2(x, opt, *f.wm, *f.ws, f.cnt, w2, qe - qb, query + qb, rb, re, &score, true, &nc, &NM, &ml);
+		warp_gen_cigar2<W>(x, opt, *f.wm, *f.ws, f.cnt, w2, qe - qb, query + qb, rb, re, &score, true, &nc, &NM, &ml);
 		DBGP(301, score);
 		if (score == last_sc || w2 == opt.w << 2) break;
 		last_sc = score;
@@ -208,6 +212,7 @@ DEV MateDesc mate_of(const Aln& a, const u32* cg)
 
 // Copies the payload of `a` (ws.cigar / ws.md) into the var pool, applies the flag finalisation bwa performs on
 // copies before the formatter hook (B.14) and writes the output record.
+template <int W>
 DEVNI void warp_emit(FinalCtx& f, const Aln& a_in, const MateDesc* mate, u32 xa_off, int xa_len, AlnRec* out)
 {
 	LANE_DECL;
@@ -230,13 +235,13 @@ DEVNI void warp_emit(FinalCtx& f, const Aln& a_in, const MateDesc* mate, u32 xa_
 		r.rid = p.rid; r.pos = (i32)p.pos; r.NM = p.NM; r.score = p.score; r.sub = p.sub; r.n_cigar = n_cigar;
 		r.md_len = n_cigar ? p.md_len : 0;
 		u32 n_words = (u32)n_cigar + (u32)((r.md_len + 3) >> 2);
-		u32 off = n_words ? var_alloc(f, n_words) : 0;
+		u32 off = n_words ? var_alloc<W>(f, n_words) : 0;
 		if (off == 0xffffffffu) { off = 0; r.n_cigar = 0; r.md_len = 0; n_cigar = 0; }
 		r.var_off = off;
 		FOR_LANES {
-			for (int k = lane; k < n_cigar; k += 32) f.var[off + k] = f.ws->cigar[k];
+			for (int k = lane; k < n_cigar; k += W) f.var[off + k] = f.ws->cigar[k];
 			int mdw = (r.md_len + 3) >> 2;
-			for (int k = lane; k < mdw; k += 32) {
+			for (int k = lane; k < mdw; k += W) {
 				u32 wd = 0;
 				for (int b = 0; b < 4; ++b) { int ci = k * 4 + b; if (ci < r.md_len) wd |= (u32)(u8)f.ws->md[ci] << (8 * b); }
 				f.var[off + n_cigar + k] = wd;
@@ -268,6 +273,7 @@ DEV int get_pri_idx(double XA_drop_ratio, const Reg* a, int i)
 
 // XA text of primary index `pri` (mem_gen_alt restricted to one primary); returns the byte length, payload copied to
 // the var pool at *xa_off.  Uses ws.cigar / ws.md as scratch (call before the record's own warp_reg2aln).
+template <int W>
 DEVNI int warp_gen_xa(FinalCtx& f, int l_query, const u8* query, int n, const Reg* a, int pri, u32* xa_off)
 {
 	LANE_DECL;
@@ -283,7 +289,7 @@ DEVNI int warp_gen_xa(FinalCtx& f, int l_query, const u8* query, int n, const Re
 #define XA_PUTNUM(v) do { long v_ = (long)(v); char b_[24]; int n_ = 0; if (v_ < 0) { XA_PUTC('-'); v_ = -v_; } do { b_[n_++] = (char)('0' + v_ % 10); v_ /= 10; } while (v_); while (n_) XA_PUTC(b_[--n_]); } while (0)
 	for (int i = 0; i < n; ++i) {
 		if (get_pri_idx(ratio, a, i) != pri) continue;
-		Aln t = warp_reg2aln(f, l_query, query, &a[i]);
+		Aln t = warp_reg2aln<W>(f, l_query, query, &a[i]);
 		const char* nm = f.ctg_names + f.ctg_name_off[t.rid];
 		for (int k = 0; nm[k]; ++k) XA_PUTC(nm[k]);
 		XA_PUTC(','); XA_PUTC("+-"[t.is_rev]); XA_PUTNUM(t.pos + 1); XA_PUTC(',');
@@ -293,10 +299,10 @@ DEVNI int warp_gen_xa(FinalCtx& f, int l_query, const u8* query, int n, const Re
 	WARP_SYNC();
 	if (ovf) { ONE_LANE { atomic_or_u32(f.ws->err, ERR_XA_OVERFLOW); } return 0; }
 	u32 n_words = (u32)((xl + 3) >> 2);
-	u32 off = var_alloc(f, n_words);
+	u32 off = var_alloc<W>(f, n_words);
 	if (off == 0xffffffffu) return 0;
 	FOR_LANES {
-		for (int k = lane; k < (int)n_words; k += 32) {
+		for (int k = lane; k < (int)n_words; k += W) {
 			u32 wd = 0;
 			for (int b = 0; b < 4; ++b) { int ci = k * 4 + b; if (ci < xl) wd |= (u32)(u8)xa[ci] << (8 * b); }
 			f.var[off + k] = wd;
@@ -307,6 +313,7 @@ DEVNI int warp_gen_xa(FinalCtx& f, int l_query, const u8* query, int n, const Re
 }
 
 // ---- SE emission (mem_reg2sam, B.14).  Returns the number of records written to out[]. ----------
+template <int W>
 DEVNI int warp_reg2sam(FinalCtx& f, int l_seq, const u8* seq, int n, const Reg* a, int extra_flag, const MateDesc* m, AlnRec* out, int out_cap)
 {
 	LANE_DECL;
@@ -320,23 +327,23 @@ DEVNI int warp_reg2sam(FinalCtx& f, int l_seq, const u8* seq, int n, const Reg* 
 		if (l >= out_cap) { ONE_LANE { atomic_or_u32(f.ws->err, ERR_REG_OVERFLOW); } break; }
 		u32 xa_off = 0; int xa_len = 0;
 		DBGP(200, k);
-		if (!(opt.flag & MEM_F_ALL)) xa_len = warp_gen_xa(f, l_seq, seq, n, a, k, &xa_off);
+		if (!(opt.flag & MEM_F_ALL)) xa_len = warp_gen_xa<W>(f, l_seq, seq, n, a, k, &xa_off);
 		DBGP(201, k);
-		Aln q = warp_reg2aln(f, l_seq, seq, &a[k]);
+		Aln q = warp_reg2aln<W>(f, l_seq, seq, &a[k]);
 		DBGP(202, k);
 		q.flag |= extra_flag;
 		if (p.secondary >= 0) q.sub = -1;
 		if (l && p.secondary < 0) q.flag |= (opt.flag & MEM_F_NO_MULTI) ? 0x10000 : 0x800;
 		if (l && !p.is_alt && q.mapq > mapq0) q.mapq = mapq0;
 		if (l == 0) mapq0 = q.mapq;
-		warp_emit(f, q, m, xa_off, xa_len, &out[l]);
+		warp_emit<W>(f, q, m, xa_off, xa_len, &out[l]);
 		DBGP(203, k);
 		++l;
 	}
 	if (l == 0) {
-		Aln t = warp_reg2aln(f, l_seq, seq, nullptr);
+		Aln t = warp_reg2aln<W>(f, l_seq, seq, nullptr);
 		t.flag |= extra_flag;
-		warp_emit(f, t, m, 0, 0, &out[0]);
+		warp_emit<W>(f, t, m, 0, 0, &out[0]);
 		l = 1;
 	}
 	return l;
@@ -379,6 +386,7 @@ DEV i64 pestat_candidate(const DevIndex& x, const MemOpt& opt, int n0, const Reg
 }
 
 // mate rescue (B.8).  a: snapshot hit of one end; ms: mate read codes; ma[0..*n_ma): the mate's live region list.
+template <int W>
 DEVNI int warp_matesw(FinalCtx& f, const Reg& a, int l_ms, const u8* ms, Reg* ma, int* n_ma, int ma_cap)
 {
 	LANE_DECL;
@@ -417,7 +425,7 @@ DEVNI int warp_matesw(FinalCtx& f, const Reg& a, int l_ms, const u8* ms, Reg* ma
 			if (tlen > f.ws->brow_cap) { ONE_LANE { atomic_or_u32(f.ws->err, ERR_BROW_OVERFLOW); } return n; }
 			// forward pass: query = mate (reverse-complemented when is_rev), padded with code 5
 			FOR_LANES {
-				for (int j = lane; j < plen; j += 32) {
+				for (int j = lane; j < plen; j += W) {
 					u8 c = 5;
 					if (j < l_ms) { if (is_rev) { u8 b = ms[l_ms - 1 - j]; c = b < 4 ? (u8)(3 - b) : (u8)4; } else c = ms[j]; }
 					wm.q[j] = c;
@@ -425,14 +433,14 @@ DEVNI int warp_matesw(FinalCtx& f, const Reg& a, int l_ms, const u8* ms, Reg* ma
 			}
 			WARP_SYNC();
 			TAcc ta; ta.base = rb; ta.stride = 1; ta.piv = -1;
-			SwFwd fw = warp_sw_striped(x, opt, wm, lanes_simd, is_u8, l_ms, tlen, ta, xtra, f.ws->brow, f.cnt ? &f.cnt->cells_msw : nullptr);
+			SwFwd fw = warp_sw_striped<W>(x, opt, wm, lanes_simd, is_u8, l_ms, tlen, ta, xtra, f.ws->brow, f.cnt ? &f.cnt->cells_msw : nullptr);
 			if (f.cnt) { ONE_LANE { atomic_add_u64(&f.cnt->n_msw, 1); } }
 			int qb_ = -1, tb_ = -1;
 			if (!(fw.score < (xtra & 0xffff))) { // XSUBO: the start is only searched for scores above the threshold
 				int ql2 = fw.qe + 1;
 				int slen2 = (ql2 + lanes_simd - 1) / lanes_simd, plen2 = slen2 * lanes_simd;
 				FOR_LANES {
-					for (int j = lane; j < plen2; j += 32) {
+					for (int j = lane; j < plen2; j += W) {
 						u8 c = 5;
 						if (j < ql2) { int jj = fw.qe - j; if (is_rev) { u8 b = ms[l_ms - 1 - jj]; c = b < 4 ? (u8)(3 - b) : (u8)4; } else c = ms[jj]; }
 						wm.q[j] = c;
@@ -440,7 +448,7 @@ DEVNI int warp_matesw(FinalCtx& f, const Reg& a, int l_ms, const u8* ms, Reg* ma
 				}
 				WARP_SYNC();
 				TAcc tr; tr.base = rb; tr.stride = 1; tr.piv = fw.te; // target prefix [0,te] reversed, the rest untouched
-				SwFwd rv = warp_sw_striped(x, opt, wm, lanes_simd, is_u8, ql2, tlen, tr, KSW_XSTOP | fw.score, f.ws->brow, f.cnt ? &f.cnt->cells_msw : nullptr);
+				SwFwd rv = warp_sw_striped<W>(x, opt, wm, lanes_simd, is_u8, ql2, tlen, tr, KSW_XSTOP | fw.score, f.ws->brow, f.cnt ? &f.cnt->cells_msw : nullptr);
 				if (fw.score == rv.score) { tb_ = fw.te - rv.te; qb_ = fw.qe - rv.qe; }
 			}
 			if (fw.score >= opt.min_seed_len && qb_ >= 0) {
@@ -466,7 +474,7 @@ DEVNI int warp_matesw(FinalCtx& f, const Reg& a, int l_ms, const u8* ms, Reg* ma
 			}
 			++n;
 		}
-		if (n) nm = warp_sort_dedup_patch(x, opt, wm, *f.ws, f.cnt, nullptr, nm, ma);
+		if (n) nm = warp_sort_dedup_patch<W>(x, opt, wm, *f.ws, f.cnt, nullptr, nm, ma);
 	}
 	*n_ma = nm;
 	return n;
@@ -477,6 +485,7 @@ struct Pair64Lt { DEVM bool operator()(const Pair64& a, const Pair64& b) const {
 
 // mem_pair (B.13).  v: scratch for n_pri[0]+n_pri[1] keys.  The candidate list u is never materialised: the best,
 // the runner-up and the n_sub count are obtained by enumerating the candidates twice.
+template <int W>
 DEVNI int warp_mem_pair(FinalCtx& f, const Reg* a0, const Reg* a1, const int n_pri[2], int id, int* sub, int* n_sub, int z[2], Pair64* v)
 {
 	LANE_DECL;
@@ -563,6 +572,7 @@ struct PairIO {
 };
 
 // mem_sam_pe (B.13)
+template <int W>
 DEVNI void warp_sam_pe(FinalCtx& f, u64 id, PairIO& io)
 {
 	LANE_DECL;
@@ -580,16 +590,16 @@ DEVNI void warp_sam_pe(FinalCtx& f, u64 id, PairIO& io)
 		for (int i = 0; i < 2; ++i)
 			for (int j = 0; j < nb[i] && j < opt.max_matesw; ++j) {
 				const Reg s = io.snap[i][j];
-				warp_matesw(f, s, io.l_seq[!i], io.seq[!i], io.a[!i], &io.n[!i], io.cap[!i]);
+				warp_matesw<W>(f, s, io.l_seq[!i], io.seq[!i], io.a[!i], &io.n[!i], io.cap[!i]);
 			}
 	}
-	n_pri[0] = warp_mark_primary_se(opt, io.n[0], io.a[0], (i64)(id << 1 | 0), io.ztmp[0]);
-	n_pri[1] = warp_mark_primary_se(opt, io.n[1], io.a[1], (i64)(id << 1 | 1), io.ztmp[1]);
-	if (opt.flag & MEM_F_PRIMARY5) { warp_reorder_primary5(opt.T, io.n[0], io.a[0]); warp_reorder_primary5(opt.T, io.n[1], io.a[1]); }
+	n_pri[0] = warp_mark_primary_se<W>(opt, io.n[0], io.a[0], (i64)(id << 1 | 0), io.ztmp[0]);
+	n_pri[1] = warp_mark_primary_se<W>(opt, io.n[1], io.a[1], (i64)(id << 1 | 1), io.ztmp[1]);
+	if (opt.flag & MEM_F_PRIMARY5) { warp_reorder_primary5<W>(opt.T, io.n[0], io.a[0]); warp_reorder_primary5<W>(opt.T, io.n[1], io.a[1]); }
 	bool paired_path = false;
 	int o = 0, subo = 0, n_sub = 0;
 	if (!(opt.flag & MEM_F_NOPAIRING) && n_pri[0] && n_pri[1]) {
-		o = warp_mem_pair(f, io.a[0], io.a[1], n_pri, (int)id, &subo, &n_sub, z, io.v);
+		o = warp_mem_pair<W>(f, io.a[0], io.a[1], n_pri, (int)id, &subo, &n_sub, z, io.v);
 		if (o > 0) {
 			bool is_multi = false;
 			for (int i = 0; i < 2; ++i) {
@@ -645,15 +655,15 @@ DEVNI void warp_sam_pe(FinalCtx& f, u64 id, PairIO& io)
 		u32 xa_off[2] = { 0, 0 }; int xa_len[2] = { 0, 0 };
 		MateDesc md[2];
 		for (int i = 0; i < 2; ++i) { // mate descriptors need pos/is_rev/ref_len of both ends first
-			Aln h = warp_reg2aln(f, io.l_seq[i], io.seq[i], &io.a[i][z[i]]);
+			Aln h = warp_reg2aln<W>(f, io.l_seq[i], io.seq[i], &io.a[i][z[i]]);
 			md[i] = mate_of(h, f.ws->cigar);
 		}
 		for (int i = 0; i < 2; ++i) {
-			if (!(opt.flag & MEM_F_ALL)) xa_len[i] = warp_gen_xa(f, io.l_seq[i], io.seq[i], io.n[i], io.a[i], z[i], &xa_off[i]);
-			Aln h = warp_reg2aln(f, io.l_seq[i], io.seq[i], &io.a[i][z[i]]);
+			if (!(opt.flag & MEM_F_ALL)) xa_len[i] = warp_gen_xa<W>(f, io.l_seq[i], io.seq[i], io.n[i], io.a[i], z[i], &xa_off[i]);
+			Aln h = warp_reg2aln<W>(f, io.l_seq[i], io.seq[i], &io.a[i][z[i]]);
 			h.mapq = (u32)q_se[i];
 			h.flag |= 0x40 << i | extra_flag;
-			warp_emit(f, h, &md[!i], xa_off[i], xa_len[i], &io.out[i][0]);
+			warp_emit<W>(f, h, &md[!i], xa_off[i], xa_len[i], &io.out[i][0]);
 			io.n_out[i] = 1;
 		}
 		return;
@@ -663,7 +673,7 @@ DEVNI void warp_sam_pe(FinalCtx& f, u64 id, PairIO& io)
 	for (int i = 0; i < 2; ++i) {
 		int which = -1;
 		if (io.n[i]) { if (io.a[i][0].score >= opt.T) which = 0; } // (the ALT alternative n_pri < n never applies)
-		Aln t = warp_reg2aln(f, io.l_seq[i], io.seq[i], which >= 0 ? &io.a[i][which] : nullptr);
+		Aln t = warp_reg2aln<W>(f, io.l_seq[i], io.seq[i], which >= 0 ? &io.a[i][which] : nullptr);
 		h[i] = mate_of(t, f.ws->cigar);
 	}
 	if (!(opt.flag & MEM_F_NOPAIRING) && h[0].rid == h[1].rid && h[0].rid >= 0) {
@@ -671,6 +681,6 @@ DEVNI void warp_sam_pe(FinalCtx& f, u64 id, PairIO& io)
 		int d = infer_dir(x.l_pac, io.a[0][0].rb, io.a[1][0].rb, &dist);
 		if (!pes[d].failed && dist >= pes[d].low && dist <= pes[d].high) extra_flag |= 2;
 	}
-	io.n_out[0] = warp_reg2sam(f, io.l_seq[0], io.seq[0], io.n[0], io.a[0], 0x41 | extra_flag, &h[1], io.out[0], io.out_cap[0]);
-	io.n_out[1] = warp_reg2sam(f, io.l_seq[1], io.seq[1], io.n[1], io.a[1], 0x81 | extra_flag, &h[0], io.out[1], io.out_cap[1]);
+	io.n_out[0] = warp_reg2sam<W>(f, io.l_seq[0], io.seq[0], io.n[0], io.a[0], 0x41 | extra_flag, &h[1], io.out[0], io.out_cap[0]);
+	io.n_out[1] = warp_reg2sam<W>(f, io.l_seq[1], io.seq[1], io.n[1], io.a[1], 0x81 | extra_flag, &h[0], io.out[1], io.out_cap[1]);
 }

@@ -123,6 +123,7 @@ DEV void make_warp_ctx(const BatchParams& P, i64 warp_slot, u8* smem, WarpMem& w
 HOSTDEV size_t warp_smem_bytes(int cap) { return (size_t)(4 * (cap + 2) + 16) * 4 + (size_t)((cap + 2 + 15) & ~15); }
 
 // ---- extend: one warp per read -------------------------------------------------------------------
+template <int W>
 DEV void wbody_extend(const BatchParams& P, i64 r, WarpMem& wm, WarpScratch& ws)
 {
 	LANE_DECL;
@@ -134,9 +135,9 @@ DEV void wbody_extend(const BatchParams& P, i64 r, WarpMem& wm, WarpScratch& ws)
 	if (len > wm.cap) { if (nck) { ONE_LANE { atomic_or_u32(P.err, ERR_QLEN_OVERFLOW); } } nck = 0; }
 	for (int c = 0; c < nck; ++c) {
 		const ChainK ck = P.ck[t0 + c];
-		warp_chain2aln(P.x, P.opt, wm, ws, P.cnt, len, seq, ck, P.ks + t0 + ck.seed_start, P.srt + t0, av, &n_av, av_cap);
+		warp_chain2aln<W>(P.x, P.opt, wm, ws, P.cnt, len, seq, ck, P.ks + t0 + ck.seed_start, P.srt + t0, av, &n_av, av_cap);
 	}
-	n_av = warp_sort_dedup_patch(P.x, P.opt, wm, ws, P.cnt, seq, n_av, av);
+	n_av = warp_sort_dedup_patch<W>(P.x, P.opt, wm, ws, P.cnt, seq, n_av, av);
 	ONE_LANE { P.n_reg[r] = (u32)n_av; }
 }
 
@@ -180,6 +181,7 @@ DEV void make_final_ctx(const BatchParams& P, WarpMem& wm, WarpScratch& ws, Fina
 }
 
 // ---- finalize, single-end: one warp per read ------------------------------------------------------
+template <int W>
 DEV void wbody_final_se(const BatchParams& P, i64 r, WarpMem& wm, WarpScratch& ws)
 {
 	LANE_DECL;
@@ -189,14 +191,15 @@ DEV void wbody_final_se(const BatchParams& P, i64 r, WarpMem& wm, WarpScratch& w
 	Reg* a = P.regs + P.reg_off[r];
 	int n = (int)P.n_reg[r];
 	DBGP(100, n);
-	warp_mark_primary_se(P.opt, n, a, r, P.ztmp + P.reg_off[r]); // id = index within the call (hazard H2)
+	warp_mark_primary_se<W>(P.opt, n, a, r, P.ztmp + P.reg_off[r]); // id = index within the call (hazard H2)
 	DBGP(101, r);
-	if (P.opt.flag & MEM_F_PRIMARY5) warp_reorder_primary5(P.opt.T, n, a);
-	int nr = warp_reg2sam(f, len, seq, n, a, 0, nullptr, P.recs + P.reg_off[r], (int)P.reg_cap[r]);
+	if (P.opt.flag & MEM_F_PRIMARY5) warp_reorder_primary5<W>(P.opt.T, n, a);
+	int nr = warp_reg2sam<W>(f, len, seq, n, a, 0, nullptr, P.recs + P.reg_off[r], (int)P.reg_cap[r]);
 	ONE_LANE { P.n_rec[r] = (u32)nr; }
 }
 
 // ---- finalize, paired-end: one warp per pair ------------------------------------------------------
+template <int W>
 DEV void wbody_final_pe(const BatchParams& P, i64 pr, WarpMem& wm, WarpScratch& ws)
 {
 	LANE_DECL;
@@ -212,7 +215,7 @@ DEV void wbody_final_pe(const BatchParams& P, i64 pr, WarpMem& wm, WarpScratch& 
 		io.out[e] = P.recs + P.reg_off[r]; io.out_cap[e] = (int)P.reg_cap[r]; io.n_out[e] = 0;
 	}
 	io.v = P.pairv + P.reg_off[pr << 1];
-	warp_sam_pe(f, (u64)pr, io);
+	warp_sam_pe<W>(f, (u64)pr, io);
 	ONE_LANE { P.n_rec[pr << 1] = (u32)io.n_out[0]; P.n_rec[(pr << 1) + 1] = (u32)io.n_out[1]; }
 }
 

@@ -44,11 +44,12 @@ struct ExtResult { int score, qle, tle, gtle, gscore, max_off; };
 
 // inclusive max-scan over the 32 lanes
 #define WV_SCAN_MAX(pm) do { \
-	for (int d_ = 1; d_ < 32; d_ <<= 1) { \
+	for (int d_ = 1; d_ < W; d_ <<= 1) { \
 		WV(int, t_); wv_shfl_up(t_, pm, d_); \
 		FOR_LANES { if (lane >= d_) L_(pm) = imax(L_(pm), L_(t_)); } \
 	} } while (0)
 
+template <int W>
 DEVNI void warp_extend2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, int qlen, int tlen, TAcc ta,
                         int w, int end_bonus, int zdrop, int h0, ExtResult& res, u64* cell_counter)
 {
@@ -58,7 +59,7 @@ DEVNI void warp_extend2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, int q
 	i32* H = wm.H; i32* E = wm.E;
 	// first row: H[0]=h0, H[1]=h0-oe_ins, then decay by e_ins while positive
 	FOR_LANES {
-		for (int j = lane; j <= qlen; j += 32) {
+		for (int j = lane; j <= qlen; j += W) {
 			int v;
 			if (j == 0) v = h0;
 			else { v = h0 - oe_ins - (j - 1) * e_ins; if (v < 0) v = 0; }
@@ -80,15 +81,15 @@ DEVNI void warp_extend2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, int q
 	WV(int, tch);
 	FOR_LANES { L_(tch) = 0; }
 	for (int i = 0; i < tlen; ++i) {
-		if ((i & 31) == 0) { FOR_LANES { int ii = i + lane; L_(tch) = ii < tlen ? ref_base2(x, tacc_pos(ta, ii)) : 0; } }
-		const int tb = wv_get(tch, i & 31);
+		if ((i & (W - 1)) == 0) { FOR_LANES { int ii = i + lane; L_(tch) = ii < tlen ? ref_base2(x, tacc_pos(ta, ii)) : 0; } }
+		const int tb = wv_get(tch, i & (W - 1));
 		if (beg < i - w) beg = i - w;
 		if (end > i + w + 1) end = i + w + 1;
 		if (end > qlen) end = qlen;
 		int h1c, fcar = 0, m = 0, mj = -1, nzfirst = -1, nzlast = -1;
 		if (beg == 0) { h1c = h0 - (o_del + e_del * (i + 1)); if (h1c < 0) h1c = 0; } else h1c = 0;
 		if (end > beg) cells += (u64)(end - beg);
-		for (int j0 = beg; j0 < end; j0 += 32) {
+		for (int j0 = beg; j0 < end; j0 += W) {
 			WV(int, M); WV(int, e); WV(int, pm); WV(bool, act);
 			FOR_LANES {
 				int j = j0 + lane;
@@ -130,7 +131,7 @@ DEVNI void warp_extend2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, int q
 			u32 bmax = wv_ballot(ismax), bnz = wv_ballot(nz);
 			if (cmx >= m) { m = cmx; mj = j0 + 31 - __clz(bmax); }
 			if (bnz) { if (nzfirst < 0) nzfirst = j0 + __ffs(bnz) - 1; nzlast = j0 + 31 - __clz(bnz); }
-			int la = end - 1 - j0; la = la < 31 ? la : 31;
+			int la = end - 1 - j0; la = la < W - 1 ? la : W - 1;
 			fcar = wv_get(fout, la); h1c = wv_get(h, la);
 		}
 		ONE_LANE { H[end] = h1c; E[end] = 0; }
@@ -154,6 +155,7 @@ DEVNI void warp_extend2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, int q
 
 // Banded global alignment.  z (traceback bytes, n_col per target row) and cigar live in per-warp global scratch.
 // Returns the score; *n_cigar_out = 0 when no traceback was requested (cigar == nullptr).
+template <int W>
 DEVNI int warp_global2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, int qlen, int tlen, TAcc ta, int w,
                        u8* z, u32* cigar, int* n_cigar_out, u64* cell_counter)
 {
@@ -165,7 +167,7 @@ DEVNI int warp_global2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, int ql
 	const bool bt = cigar != nullptr;
 	if (n_cigar_out) *n_cigar_out = 0;
 	FOR_LANES {
-		for (int j = lane; j <= qlen; j += 32) {
+		for (int j = lane; j <= qlen; j += W) {
 			int v = j == 0 ? 0 : (j <= w ? -(o_ins + e_ins * j) : KSW_NEG_INF);
 			H[j] = v; E[j] = KSW_NEG_INF;
 		}
@@ -175,14 +177,14 @@ DEVNI int warp_global2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, int ql
 	WV(int, tch);
 	FOR_LANES { L_(tch) = 0; }
 	for (int i = 0; i < tlen; ++i) {
-		if ((i & 31) == 0) { FOR_LANES { int ii = i + lane; L_(tch) = ii < tlen ? ref_base2(x, tacc_pos(ta, ii)) : 0; } }
-		const int tb = wv_get(tch, i & 31);
+		if ((i & (W - 1)) == 0) { FOR_LANES { int ii = i + lane; L_(tch) = ii < tlen ? ref_base2(x, tacc_pos(ta, ii)) : 0; } }
+		const int tb = wv_get(tch, i & (W - 1));
 		int beg = i > w ? i - w : 0;
 		int end = i + w + 1 < qlen ? i + w + 1 : qlen;
 		int h1c = beg == 0 ? -(o_del + e_del * (i + 1)) : KSW_NEG_INF;
 		int fcar = KSW_NEG_INF;
 		if (end > beg) cells += (u64)(end - beg);
-		for (int j0 = beg; j0 < end; j0 += 32) {
+		for (int j0 = beg; j0 < end; j0 += W) {
 			WV(int, M); WV(int, e); WV(int, pm); WV(bool, act);
 			FOR_LANES {
 				int j = j0 + lane;
@@ -221,7 +223,7 @@ DEVNI int warp_global2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, int ql
 					if (bt) z[(size_t)i * n_col + (j - beg)] = (u8)d;
 				}
 			}
-			int la = end - 1 - j0; la = la < 31 ? la : 31;
+			int la = end - 1 - j0; la = la < W - 1 ? la : W - 1;
 			fcar = wv_get(fout, la); h1c = wv_get(h, la);
 		}
 		ONE_LANE { H[end] = h1c; E[end] = KSW_NEG_INF; }
@@ -259,6 +261,7 @@ struct SwFwd { int score, te, qe, score2, te2; };
 
 // wm.q must hold the query in DP orientation for columns [0,qlen) ; columns [qlen,plen) are padding.
 // brow: per-warp global scratch for the (row maximum,row) list, capacity >= tlen.
+template <int W>
 DEVNI SwFwd warp_sw_striped(const DevIndex& x, const MemOpt& opt, WarpMem& wm, int lanes_simd, bool is_u8, int qlen, int tlen, TAcc ta,
                             int xtra, u64* brow, u64* cell_counter)
 {
@@ -273,18 +276,18 @@ DEVNI SwFwd warp_sw_striped(const DevIndex& x, const MemOpt& opt, WarpMem& wm, i
 	const int minsc = (xtra & KSW_XSUBO) ? (xtra & 0xffff) : 0x10000;
 	const int endsc = (xtra & KSW_XSTOP) ? (xtra & 0xffff) : 0x10000;
 	i32* H0 = wm.H; i32* H1 = wm.H2; i32* E = wm.E; i32* Hm = wm.Hm;
-	FOR_LANES { for (int q = lane; q < plen; q += 32) { H0[q] = 0; H1[q] = 0; E[q] = 0; Hm[q] = 0; } }
+	FOR_LANES { for (int q = lane; q < plen; q += W) { H0[q] = 0; H1[q] = 0; E[q] = 0; Hm[q] = 0; } }
 	WARP_SYNC();
 	int gmax = 0, te = -1, n_b = 0;
 	u64 cells = 0;
 	WV(int, tch);
 	FOR_LANES { L_(tch) = 0; }
 	for (int i = 0; i < tlen; ++i) {
-		if ((i & 31) == 0) { FOR_LANES { int ii = i + lane; L_(tch) = ii < tlen ? ref_base2(x, tacc_pos(ta, ii)) : 0; } }
-		const int tb = wv_get(tch, i & 31);
+		if ((i & (W - 1)) == 0) { FOR_LANES { int ii = i + lane; L_(tch) = ii < tlen ? ref_base2(x, tacc_pos(ta, ii)) : 0; } }
+		const int tb = wv_get(tch, i & (W - 1));
 		int imx = 0, fcar = 0;
 		cells += (u64)qlen;
-		for (int q0 = 0; q0 < plen; q0 += 32) { // pass 1
+		for (int q0 = 0; q0 < plen; q0 += W) { // pass 1
 			WV(int, hd); WV(int, e); WV(int, pm); WV(bool, act); WV(int, head);
 			FOR_LANES {
 				int q = q0 + lane;
@@ -304,7 +307,7 @@ DEVNI SwFwd warp_sw_striped(const DevIndex& x, const MemOpt& opt, WarpMem& wm, i
 				L_(head) = (qq - qq % slen) - q0; // lane index of this column's segment head (may be < 0)
 			}
 			// segmented inclusive max-scan: a lane only takes values from lanes of its own segment
-			for (int d_ = 1; d_ < 32; d_ <<= 1) {
+			for (int d_ = 1; d_ < W; d_ <<= 1) {
 				WV(int, t_); wv_shfl_up(t_, pm, d_);
 				FOR_LANES { if (lane >= d_ && lane - d_ >= L_(head)) L_(pm) = imax(L_(pm), L_(t_)); }
 			}
@@ -343,13 +346,13 @@ DEVNI SwFwd warp_sw_striped(const DevIndex& x, const MemOpt& opt, WarpMem& wm, i
 				WV(int, fl);
 				FOR_LANES { int fi = lane == 0 ? fcar : L_(fin); if (lane == L_(head)) fi = 0; if (fi < 0) fi = 0;
 					int fo = fi - e_ins; if (fo < 0) fo = 0; int t2 = L_(h) - oe_ins; if (t2 < 0) t2 = 0; L_(fl) = fo > t2 ? fo : t2; }
-				int la = plen - 1 - q0; la = la < 31 ? la : 31;
+				int la = plen - 1 - q0; la = la < W - 1 ? la : W - 1;
 				fcar = wv_get(fl, la);
 			}
 		}
 		WARP_SYNC();
 		// pass 2: F carried out of earlier segments
-		for (int q0 = 0; q0 < plen; q0 += 32) {
+		for (int q0 = 0; q0 < plen; q0 += W) {
 			FOR_LANES {
 				int q = q0 + lane;
 				if (q < plen) {
@@ -367,7 +370,7 @@ DEVNI SwFwd warp_sw_striped(const DevIndex& x, const MemOpt& opt, WarpMem& wm, i
 		bool stop = false;
 		if (imx > gmax) {
 			gmax = imx; te = i;
-			FOR_LANES { for (int q = lane; q < plen; q += 32) Hm[q] = H1[q]; }
+			FOR_LANES { for (int q = lane; q < plen; q += W) Hm[q] = H1[q]; }
 			if (is_u8) { if (gmax + shift >= 255 || gmax >= endsc) stop = true; }
 			else if (gmax >= endsc) stop = true;
 		}
@@ -380,10 +383,10 @@ DEVNI SwFwd warp_sw_striped(const DevIndex& x, const MemOpt& opt, WarpMem& wm, i
 	if (!is_u8 || r.score != 255) {
 		// smallest query column holding the maximum of the snapshot row
 		WV(int, best);
-		FOR_LANES { int b = -1; for (int q = lane; q < plen; q += 32) b = Hm[q] > b ? Hm[q] : b; L_(best) = b; }
+		FOR_LANES { int b = -1; for (int q = lane; q < plen; q += W) b = Hm[q] > b ? Hm[q] : b; L_(best) = b; }
 		int mxv = wv_reduce_max(best);
 		WV(int, qmin);
-		FOR_LANES { int qq = 0x7fffffff; for (int q = lane; q < plen; q += 32) if (Hm[q] == mxv) { qq = q; break; } L_(qmin) = qq; }
+		FOR_LANES { int qq = 0x7fffffff; for (int q = lane; q < plen; q += W) if (Hm[q] == mxv) { qq = q; break; } L_(qmin) = qq; }
 		r.qe = wv_reduce_min(qmin);
 		if (n_b > 0) {
 			int d = (r.score + mmax - 1) / mmax, low = te - d, high = te + d;

@@ -35,19 +35,27 @@ typedef int8_t i8;
 #define WV(T, name) T name
 #define L_(name) name
 #define FOR_LANES
-#define LANE_DECL const int lane = (int)(threadIdx.x & 31)
-#define ONE_LANE __syncwarp(); if (lane == 0)      /* pre-synchronised single-lane write (may overwrite data other lanes just read) */
+// Every lane-aware device function is a template on W, the number of lanes that cooperate on one work item:
+// W = 32 (a warp per item: shuffles, ballots, __syncwarp) or W = 1 (a thread per item: collectives are identities).
+template <int W> __device__ __forceinline__ int lane_id_() { return W == 32 ? (int)(threadIdx.x & 31) : 0; }
+template <int W> __device__ __forceinline__ void wsync_() { if (W == 32) __syncwarp(); }
+#define LANE_DECL const int lane = lane_id_<W>()
+#define ONE_LANE wsync_<W>(); if (lane == 0)       /* pre-synchronised single-lane write (may overwrite data other lanes just read) */
 #define ONE_LANE_NOSYNC if (lane == 0)            /* append-only single-lane write */
-#define WARP_SYNC() __syncwarp()
+#define WARP_SYNC() wsync_<W>()
 
 template <class T> DEV T ldg(const T* p) { return __ldg(p); }
 DEV int popc64(u64 x) { return __popcll(x); }
-template <class T> DEV void wv_shfl_up(T& dst, const T& src, int d) { dst = __shfl_up_sync(FULLMASK, src, d); }
-template <class T> DEV void wv_shfl_idx(T& dst, const T& src, int idx) { dst = __shfl_sync(FULLMASK, src, idx); }
-DEV int wv_reduce_max(const int& v) { return __reduce_max_sync(FULLMASK, v); }
-DEV int wv_reduce_min(const int& v) { return __reduce_min_sync(FULLMASK, v); }
-DEV u32 wv_ballot(const bool& p) { return __ballot_sync(FULLMASK, p); }
-template <class T> DEV T wv_get(const T& v, int l) { return __shfl_sync(FULLMASK, v, l); }
+template <int W, class T> DEV void wv_shfl_up_(T& dst, const T& src, int d) { if (W == 32) dst = __shfl_up_sync(FULLMASK, src, d); else dst = src; }
+template <int W> DEV int wv_reduce_max_(const int& v) { return W == 32 ? __reduce_max_sync(FULLMASK, v) : v; }
+template <int W> DEV int wv_reduce_min_(const int& v) { return W == 32 ? __reduce_min_sync(FULLMASK, v) : v; }
+template <int W> DEV u32 wv_ballot_(const bool& p) { return W == 32 ? __ballot_sync(FULLMASK, p) : (p ? 1u : 0u); }
+template <int W, class T> DEV T wv_get_(const T& v, int l) { return W == 32 ? __shfl_sync(FULLMASK, v, l) : v; }
+#define wv_shfl_up(dst, src, d) wv_shfl_up_<W>(dst, src, d)
+#define wv_reduce_max(v) wv_reduce_max_<W>(v)
+#define wv_reduce_min(v) wv_reduce_min_<W>(v)
+#define wv_ballot(p) wv_ballot_<W>(p)
+#define wv_get(v, l) wv_get_<W>(v, l)
 DEV u64 atomic_add_u64(u64* p, u64 v) { return (u64)atomicAdd((unsigned long long*)p, (unsigned long long)v); }
 DEV u32 atomic_add_u32(u32* p, u32 v) { return atomicAdd(p, v); }
 DEV u32 atomic_or_u32(u32* p, u32 v) { return atomicOr(p, v); }
@@ -62,7 +70,7 @@ DEV u32 atomic_max_u32(u32* p, u32 v) { return atomicMax(p, v); }
 #define KERNEL static
 #define WV(T, name) T name[32]
 #define L_(name) name[lane]
-#define FOR_LANES for (int lane = 0; lane < 32; ++lane)
+#define FOR_LANES for (int lane = 0; lane < W; ++lane)
 #define LANE_DECL const int lane0_unused_ = 0; (void)lane0_unused_
 #define ONE_LANE
 #define ONE_LANE_NOSYNC
@@ -71,12 +79,16 @@ DEV u32 atomic_max_u32(u32* p, u32 v) { return atomicMax(p, v); }
 struct uint4 { u32 x, y, z, w; };
 template <class T> DEV T ldg(const T* p) { return *p; }
 DEV int popc64(u64 x) { return __builtin_popcountll(x); }
-template <class T> DEV void wv_shfl_up(T (&dst)[32], const T (&src)[32], int d) { T t[32]; for (int l = 0; l < 32; ++l) t[l] = l >= d ? src[l - d] : src[l]; for (int l = 0; l < 32; ++l) dst[l] = t[l]; }
-template <class T> DEV void wv_shfl_idx(T (&dst)[32], const T (&src)[32], int idx) { T t = src[idx]; for (int l = 0; l < 32; ++l) dst[l] = t; }
-DEV int wv_reduce_max(const int (&v)[32]) { int m = v[0]; for (int l = 1; l < 32; ++l) m = v[l] > m ? v[l] : m; return m; }
-DEV int wv_reduce_min(const int (&v)[32]) { int m = v[0]; for (int l = 1; l < 32; ++l) m = v[l] < m ? v[l] : m; return m; }
-DEV u32 wv_ballot(const bool (&p)[32]) { u32 m = 0; for (int l = 0; l < 32; ++l) m |= (u32)(p[l] ? 1u : 0u) << l; return m; }
-template <class T> DEV T wv_get(const T (&v)[32], int l) { return v[l]; }
+template <int W, class T> DEV void wv_shfl_up_(T (&dst)[32], const T (&src)[32], int d) { T t[32]; for (int l = 0; l < W; ++l) t[l] = l >= d ? src[l - d] : src[l]; for (int l = 0; l < W; ++l) dst[l] = t[l]; }
+template <int W> DEV int wv_reduce_max_(const int (&v)[32]) { int m = v[0]; for (int l = 1; l < W; ++l) m = v[l] > m ? v[l] : m; return m; }
+template <int W> DEV int wv_reduce_min_(const int (&v)[32]) { int m = v[0]; for (int l = 1; l < W; ++l) m = v[l] < m ? v[l] : m; return m; }
+template <int W> DEV u32 wv_ballot_(const bool (&p)[32]) { u32 m = 0; for (int l = 0; l < W; ++l) m |= (u32)(p[l] ? 1u : 0u) << l; return m; }
+template <int W, class T> DEV T wv_get_(const T (&v)[32], int l) { return v[l]; }
+#define wv_shfl_up(dst, src, d) wv_shfl_up_<W>(dst, src, d)
+#define wv_reduce_max(v) wv_reduce_max_<W>(v)
+#define wv_reduce_min(v) wv_reduce_min_<W>(v)
+#define wv_ballot(p) wv_ballot_<W>(p)
+#define wv_get(v, l) wv_get_<W>(v, l)
 DEV u64 atomic_add_u64(u64* p, u64 v) { u64 o = *p; *p += v; return o; }
 DEV u32 atomic_add_u32(u32* p, u32 v) { u32 o = *p; *p += v; return o; }
 DEV u32 atomic_or_u32(u32* p, u32 v) { u32 o = *p; *p |= v; return o; }
