@@ -100,6 +100,24 @@ static uint64_t rt_scan_u32(const uint32_t* in, uint64_t* out, uint64_t n)
 			__syncwarp(); \
 		} }
 
+// warp kernel whose item count lives in device memory (written by the preceding kernel of the same stream)
+#define DEF_WARP_KERNEL_DEVN(wbody) \
+	__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_##wbody(const __grid_constant__ BatchParams P, const u32* n_ptr, u32* counter) { \
+		extern __shared__ __align__(16) u8 smem_[]; \
+		const int wib = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31); \
+		const i64 slot = (i64)blockIdx.x * WARPS_PER_BLOCK + wib; \
+		const i64 n = (i64)*n_ptr; \
+		WarpMem wm; WarpScratch ws; \
+		make_warp_ctx(P, slot, smem_ + (size_t)wib * ((warp_smem_bytes(P.wm_cap) + 15) & ~(size_t)15), wm, ws); \
+		for (;;) { \
+			u32 item = 0; \
+			if (lane == 0) item = atomicAdd(counter, 1u); \
+			item = __shfl_sync(FULLMASK, item, 0); \
+			if ((i64)item >= n) break; \
+			wbody<32>(P, (i64)item, wm, ws); \
+			__syncwarp(); \
+		} }
+
 DEF_THREAD_KERNEL(body_encode)
 DEF_THREAD_TID_KERNEL(body_seed)
 DEF_THREAD_KERNEL(body_sal)
@@ -109,9 +127,16 @@ DEF_THREAD_KERNEL(body_reg_cap)
 DEF_THREAD_KERNEL(body_compact)
 DEF_THREAD_KERNEL(body_out_size)
 DEF_THREAD_KERNEL(body_out_write)
+DEF_THREAD_KERNEL(body_rescue_snap)
+DEF_THREAD_KERNEL(body_rescue_gen)
+DEF_THREAD_KERNEL(body_rescue_apply)
+DEF_WARP_KERNEL_DEVN(wbody_rescue_sw)
 DEF_WARP_KERNEL(wbody_extend)
-DEF_WARP_KERNEL(wbody_final_se)
-DEF_WARP_KERNEL(wbody_final_pe)
+DEF_THREAD_KERNEL(body_save_regs)
+DEF_THREAD_TID_KERNEL(body_final_pe_t)
+DEF_THREAD_TID_KERNEL(body_final_se_t)
+DEF_WARP_KERNEL_DEVN(wbody_final_pe_redo)
+DEF_WARP_KERNEL_DEVN(wbody_final_se_redo)
 
 static u32* g_counters = nullptr; static int g_counter_next = 0;
 static u32* next_counter()
@@ -123,7 +148,7 @@ static u32* next_counter()
 }
 
 struct StageTimer { // CUDA events on the launching stream around every stage of the last batch
-	static const int MAXS = 16;
+	static const int MAXS = 512;
 	cudaEvent_t ev[MAXS + 1]; const char* name[MAXS]; int n = 0; bool init = false;
 	void begin() {
 #ifdef B200_DEBUG_CKPT
@@ -161,6 +186,12 @@ static int g_launches = 0;
 	i64 nb_ = (n_ + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK; i64 cap_ = (i64)rt_sm_count() * WARP_BLOCKS_PER_SM; if (nb_ > cap_) nb_ = cap_; \
 	cudaFuncSetAttribute(k_##wbody, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_); \
 	k_##wbody<<<(unsigned)nb_, WARPS_PER_BLOCK * 32, sm_, rt_stream()>>>(P, n_, next_counter()); ++g_launches; } g_timer.mark(#wbody); } while (0)
+
+#define RT_WARPS_DEVN(wbody, P, n_ptr, n_max) do { \
+	size_t sm_ = ((warp_smem_bytes((P).wm_cap) + 15) & ~(size_t)15) * WARPS_PER_BLOCK; \
+	i64 nb_ = (i64)rt_sm_count() * WARP_BLOCKS_PER_SM; \
+	cudaFuncSetAttribute(k_##wbody, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_); \
+	k_##wbody<<<(unsigned)nb_, WARPS_PER_BLOCK * 32, sm_, rt_stream()>>>(P, n_ptr, next_counter()); ++g_launches; g_timer.mark(#wbody); } while (0)
 
 static void rt_timer_begin() { g_timer.begin(); g_launches = 0; }
 
@@ -244,8 +275,14 @@ const char* b200_lastError(void* h) { return h ? ((Engine*)h)->last_error.c_str(
 int b200_lastStageTimes(void* h, float* ms, const char** names, int cap)
 {
 	(void)h;
-	int n = g_timer.n < cap ? g_timer.n : cap;
-	for (int i = 0; i < n; ++i) { float t = 0; cudaEventElapsedTime(&t, g_timer.ev[i], g_timer.ev[i + 1]); ms[i] = t; names[i] = g_timer.name[i]; }
+	int n = 0; // aggregated by stage name, in order of first appearance
+	for (int i = 0; i < g_timer.n; ++i) {
+		float t = 0; cudaEventElapsedTime(&t, g_timer.ev[i], g_timer.ev[i + 1]);
+		int j = 0;
+		for (; j < n; ++j) if (strcmp(names[j], g_timer.name[i]) == 0) break;
+		if (j == n) { if (n >= cap) continue; names[n] = g_timer.name[i]; ms[n] = 0; ++n; }
+		ms[j] += t;
+	}
 	return n;
 }
 // counters: cells_ext, cells_glb, cells_msw, n_ext, n_glb, n_msw, n_seed_lookups, n_launches

@@ -114,7 +114,7 @@ struct Engine {
 	// batch workspace
 	DBuf b_blob, b_seq, b_seqoff, b_intv, b_nintv, b_nseed, b_smem, b_seedoff, b_rbeg, b_S, b_C, b_ord, b_tmp32, b_ck, b_ks, b_srt, b_regtmp,
 	     b_nck, b_nks, b_nreg, b_regcap, b_regoff, b_regs, b_snap, b_ztmp, b_pairv, b_recs, b_nrec, b_cand, b_pairtab, b_var, b_misc,
-	     b_outwords, b_outoff, b_out, b_wsz, b_wscig, b_wsmd, b_wsxa, b_wsbrow;
+	     b_outwords, b_outoff, b_out, b_wsz, b_wscig, b_wsmd, b_wsxa, b_wsbrow, b_nb, b_swtask, b_swstate, b_swlist, b_tbuf, b_redo;
 	Counters last_counters; uint64_t last_n_seed = 0; int n_launches = 0;
 	std::string last_error;
 
@@ -175,13 +175,13 @@ inline void Engine::close_all()
 	DBuf* all[] = { &d_bwt, &d_sa, &d_pac, &d_ctg, &d_log, &d_names, &d_name_off, &b_blob, &b_seq, &b_seqoff, &b_intv, &b_nintv, &b_nseed, &b_smem,
 	                &b_seedoff, &b_rbeg, &b_S, &b_C, &b_ord, &b_tmp32, &b_ck, &b_ks, &b_srt, &b_regtmp, &b_nck, &b_nks, &b_nreg, &b_regcap, &b_regoff,
 	                &b_regs, &b_snap, &b_ztmp, &b_pairv, &b_recs, &b_nrec, &b_cand, &b_pairtab, &b_var, &b_misc, &b_outwords, &b_outoff, &b_out,
-	                &b_wsz, &b_wscig, &b_wsmd, &b_wsxa, &b_wsbrow };
+	                &b_wsz, &b_wscig, &b_wsmd, &b_wsxa, &b_wsbrow, &b_nb, &b_swtask, &b_swstate, &b_swlist, &b_tbuf, &b_redo };
 	for (DBuf* b : all) b->release();
 	if (map) munmap(map, map_len);
 	map = nullptr;
 }
 
-// misc block layout (u32 words): [0] err  [1] work counter  [2] var cursor  [8..] Counters
+// misc block layout (u32 words): [0] err  [1] work counter  [2] var cursor  [3] rescue task count  [4] max nb  [5] redo count  [8..] Counters
 // Stage a request: one host pass over the blob for the read boundaries, then upload of bases and offsets.
 inline bool Engine::stage(const char* blob_in)
 {
@@ -338,9 +338,38 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 	}
 	P.regs = b_regs.as<Reg>(); P.snap = b_snap.as<Reg>(); P.ztmp = b_ztmp.as<u32>(); P.pairv = b_pairv.as<Pair64>(); P.recs = b_recs.as<AlnRec>(); P.var = b_var.as<u32>();
 	RT_THREADS(body_compact, P, (int64_t)n_reads);
-	// ---- finalize
-	if (pe) RT_WARPS(wbody_final_pe, P, (int64_t)n_units);
-	else RT_WARPS(wbody_final_se, P, (int64_t)n_reads);
+	// ---- mate rescue as a task pipeline (rescue.cuh): snapshot, then rounds of gen -> sw -> apply
+	if (pe && !(opt.flag & MEM_F_NO_RESCUE)) {
+		size_t nr = (size_t)n_reads + 2;
+		ok = b_nb.ensure(nr * 4) && b_swtask.ensure(nr * 4 * sizeof(SwTask)) && b_swstate.ensure(nr * 4) && b_swlist.ensure(nr * 4 * 4);
+		if (!ok) { last_error = "device allocation failed (rescue pools)"; return nullptr; }
+		P.nb = b_nb.as<u32>(); P.sw_tasks = b_swtask.as<SwTask>(); P.sw_state = b_swstate.as<u8>(); P.sw_list = b_swlist.as<u32>();
+		P.sw_n_list = b_misc.as<u32>() + 3; P.max_nb = b_misc.as<u32>() + 4;
+		RT_THREADS(body_rescue_snap, P, (int64_t)n_reads);
+		uint32_t max_nb = 0;
+		rt_d2h(&max_nb, P.max_nb, 4);
+		int rounds = (int)max_nb < opt.max_matesw ? (int)max_nb : opt.max_matesw;
+		for (int k = 0; k < rounds; ++k) {
+			P.round = k;
+			rt_memset(P.sw_n_list, 0, 4);
+			RT_THREADS(body_rescue_gen, P, (int64_t)n_reads);
+			RT_WARPS_DEVN(wbody_rescue_sw, P, P.sw_n_list, (int64_t)n_reads * 4);
+			RT_THREADS(body_rescue_apply, P, (int64_t)n_reads);
+		}
+		P.rescued = 1;
+	}
+	// ---- finalize: a thread per read / pair; items that exceed the thread-level scratch are redone by a warp
+	{
+		P.t_z_cap = 8192; P.t_cigar_cap = 48; P.t_md_cap = 192; P.t_xa_cap = 1024;
+		if (getenv("B200_TEST_TINY_SCRATCH")) { P.t_z_cap = 1024; P.t_cigar_cap = 6; P.t_md_cap = 24; P.t_xa_cap = 80; } // tests: force hand-overs
+		P.t_stride = thread_scratch_bytes(P.wm_cap, P.t_z_cap, P.t_cigar_cap, P.t_md_cap, P.t_xa_cap);
+		ok = b_tbuf.ensure((size_t)tslots * P.t_stride) && b_redo.ensure(((size_t)n_reads + 1) * 4);
+		if (!ok) { last_error = "device allocation failed (thread scratch)"; return nullptr; }
+		P.t_buf = b_tbuf.as<u8>(); P.redo_list = b_redo.as<u32>(); P.n_redo = b_misc.as<u32>() + 5;
+		RT_THREADS(body_save_regs, P, (int64_t)n_reads);
+		if (pe) { RT_THREADS_TID(body_final_pe_t, P, (int64_t)n_units); RT_WARPS_DEVN(wbody_final_pe_redo, P, P.n_redo, (int64_t)n_units); }
+		else { RT_THREADS_TID(body_final_se_t, P, (int64_t)n_reads); RT_WARPS_DEVN(wbody_final_se_redo, P, P.n_redo, (int64_t)n_reads); }
+	}
 	// ---- output stream
 	RT_THREADS(body_out_size, P, (int64_t)n_reads);
 	uint64_t W = rt_scan_u32(P.out_words, P.out_off, n_reads);

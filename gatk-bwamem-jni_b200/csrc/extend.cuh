@@ -17,15 +17,6 @@ struct WarpScratch { // per-warp global scratch
 	u32* err; // engine-wide error flags
 };
 
-#define ERR_Z_OVERFLOW     1u
-#define ERR_CIGAR_OVERFLOW 2u
-#define ERR_MD_OVERFLOW    4u
-#define ERR_XA_OVERFLOW    8u
-#define ERR_BROW_OVERFLOW  16u
-#define ERR_VAR_OVERFLOW   32u
-#define ERR_REG_OVERFLOW   64u
-#define ERR_INTV_OVERFLOW  128u
-#define ERR_QLEN_OVERFLOW  256u
 
 struct Counters { u64 cells_ext, cells_glb, cells_msw, n_ext, n_glb, n_msw; };
 
@@ -92,7 +83,7 @@ DEVNI bool warp_gen_cigar2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, Wa
 			int n_col = l_query < 2 * w + 1 ? l_query : 2 * w + 1;
 			if ((size_t)n_col * (size_t)rlen > ws.z_cap) { ONE_LANE { atomic_or_u32(ws.err, ERR_Z_OVERFLOW); } return false; }
 		}
-		*score = warp_global2<W>(x, opt, wm, l_query, (int)rlen, ta, w, ws.z, want_cigar ? ws.cigar : nullptr, &nc, cnt ? &cnt->cells_glb : nullptr);
+		*score = warp_global2<W>(x, opt, wm, l_query, (int)rlen, ta, w, ws.z, want_cigar ? ws.cigar : nullptr, ws.cigar_cap, ws.err, &nc, cnt ? &cnt->cells_glb : nullptr);
 		if (cnt) { ONE_LANE { atomic_add_u64(&cnt->n_glb, 1); } }
 	}
 	DBGP(400, nc);

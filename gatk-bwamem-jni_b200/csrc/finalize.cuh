@@ -14,6 +14,7 @@ struct FinalCtx {
 	const char* ctg_names; const u32* ctg_name_off; // contig names blob + offsets (n_seqs+1)
 	const PeStat* pes;                // 4 orientations
 	const double* pair_tab; const i64* pair_tab_off; // per-orientation pairing term for dist in [low,high] (hazard H5)
+	bool rescued;                     // mate rescue already performed by the task pipeline (rescue.cuh)
 };
 
 template <int W>
@@ -578,7 +579,7 @@ DEVNI void warp_sam_pe(FinalCtx& f, u64 id, PairIO& io)
 	LANE_DECL;
 	const DevIndex& x = *f.x; const MemOpt& opt = *f.opt; const PeStat* pes = f.pes;
 	int z[2] = { 0, 0 }, n_pri[2], extra_flag = 1;
-	if (!(opt.flag & MEM_F_NO_RESCUE)) {
+	if (!(opt.flag & MEM_F_NO_RESCUE) && !f.rescued) {
 		int nb[2];
 		for (int i = 0; i < 2; ++i) {
 			int m = 0;

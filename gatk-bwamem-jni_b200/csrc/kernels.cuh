@@ -8,6 +8,7 @@
 #include "fm.cuh"
 #include "chain.cuh"
 #include "finalize.cuh"
+#include "rescue.cuh"
 
 struct BatchParams {
 	DevIndex x;
@@ -31,6 +32,8 @@ struct BatchParams {
 	// final regions
 	u32* reg_cap; u64* reg_off; Reg* regs; Reg* snap; u32* ztmp; Pair64* pairv; AlnRec* recs; u32* n_rec;
 	i64* pe_cand;           // per pair
+	// mate rescue (rescue.cuh)
+	u32* nb; SwTask* sw_tasks; u8* sw_state; u32* sw_list; u32* sw_n_list; u32* max_nb; int round; int rescued;
 	PeStat pes[4];
 	const double* pair_tab; i64 pair_tab_off[4];
 	// output
@@ -40,6 +43,9 @@ struct BatchParams {
 	// warp scratch (per resident warp)
 	u8* ws_z; size_t ws_z_cap; u32* ws_cigar; int ws_cigar_cap; char* ws_md; int ws_md_cap; char* ws_xa; int ws_xa_cap; u64* ws_brow; int ws_brow_cap;
 	int wm_cap;             // per-warp DP column capacity
+	// thread scratch (per resident thread of the thread-per-item kernels): DP rows, traceback, cigar, MD, XA
+	u8* t_buf; size_t t_stride; int t_z_cap, t_cigar_cap, t_md_cap, t_xa_cap;
+	u32* redo_list; u32* n_redo; // items a thread-level kernel handed over to the warp-level kernel
 	u32* err; Counters* cnt; u32* work_counter;
 };
 
@@ -172,8 +178,35 @@ DEV void body_compact(const BatchParams& P, i64 r)
 	for (int i = 0; i < n; ++i) d[i] = s[i];
 }
 
+DEV RescueIO make_rescue_io(const BatchParams& P)
+{
+	RescueIO io;
+	io.seq_off = P.seq_off; io.seq = P.seq; io.reg_off = P.reg_off; io.reg_cap = P.reg_cap; io.regs = P.regs; io.n_reg = P.n_reg;
+	io.snap = P.snap; io.nb = P.nb; io.tasks = P.sw_tasks; io.state = P.sw_state; io.list = P.sw_list; io.n_list = P.sw_n_list;
+	io.max_nb = P.max_nb; io.n_reads = P.n_units << 1; io.round = P.round;
+	return io;
+}
+DEV void body_rescue_snap(const BatchParams& P, i64 r) { RescueIO io = make_rescue_io(P); rescue_snap(P.opt, io, r); }
+DEV void body_rescue_gen(const BatchParams& P, i64 r) { if (r >= ((i64)P.n_units << 1)) return; RescueIO io = make_rescue_io(P); rescue_gen(P.x, P.opt, P.pes, io, r); }
+DEV void body_rescue_apply(const BatchParams& P, i64 r)
+{
+	if (r >= ((i64)P.n_units << 1)) return;
+	RescueIO io = make_rescue_io(P);
+	WarpMem wm; memset(&wm, 0, sizeof(wm));
+	WarpScratch ws; memset(&ws, 0, sizeof(ws)); ws.err = P.err;
+	rescue_apply<1>(P.x, P.opt, wm, ws, io, r);
+}
+// one warp per alignment task; `item` indexes the compact task list of the round
+template <int W>
+DEV void wbody_rescue_sw(const BatchParams& P, i64 item, WarpMem& wm, WarpScratch& ws)
+{
+	RescueIO io = make_rescue_io(P);
+	rescue_sw<W>(P.x, P.opt, wm, ws, P.cnt, io, P.sw_list[item]);
+}
+
 DEV void make_final_ctx(const BatchParams& P, WarpMem& wm, WarpScratch& ws, FinalCtx& f)
 {
+	f.rescued = P.rescued != 0;
 	f.x = &P.x; f.opt = &P.opt; f.wm = &wm; f.ws = &ws; f.cnt = P.cnt;
 	f.var = P.var; f.var_cap = P.var_cap; f.var_cursor = P.var_cursor;
 	f.ctg_names = P.ctg_names; f.ctg_name_off = P.ctg_name_off;
@@ -217,6 +250,73 @@ DEV void wbody_final_pe(const BatchParams& P, i64 pr, WarpMem& wm, WarpScratch& 
 	io.v = P.pairv + P.reg_off[pr << 1];
 	warp_sam_pe<W>(f, (u64)pr, io);
 	ONE_LANE { P.n_rec[pr << 1] = (u32)io.n_out[0]; P.n_rec[(pr << 1) + 1] = (u32)io.n_out[1]; }
+}
+
+// ---- thread-per-item variants (W = 1) with hand-over of oversized items to the warp-level kernels -------------
+HOSTDEV size_t thread_scratch_bytes(int wm_cap, int z_cap, int cigar_cap, int md_cap, int xa_cap)
+{
+	size_t n = (size_t)(2 * (wm_cap + 2)) * 4 + (size_t)((wm_cap + 2 + 15) & ~15) + (size_t)((z_cap + 15) & ~15) + (size_t)cigar_cap * 4 + (size_t)((md_cap + 15) & ~15) + (size_t)((xa_cap + 15) & ~15);
+	return (n + 127) & ~(size_t)127;
+}
+DEV void make_thread_ctx(const BatchParams& P, i64 tid, WarpMem& wm, WarpScratch& ws, u32* lerr)
+{
+	const int cap = P.wm_cap;
+	u8* b = P.t_buf + (size_t)tid * P.t_stride;
+	i32* p = (i32*)b;
+	wm.H = p; wm.E = p + (cap + 2); wm.H2 = nullptr; wm.Hm = nullptr; wm.fend = nullptr;
+	b += (size_t)(2 * (cap + 2)) * 4;
+	wm.q = b; b += (cap + 2 + 15) & ~15;
+	wm.cap = cap;
+	ws.z = b; ws.z_cap = (size_t)P.t_z_cap; b += (P.t_z_cap + 15) & ~15;
+	ws.cigar = (u32*)b; ws.cigar_cap = P.t_cigar_cap; b += (size_t)P.t_cigar_cap * 4;
+	ws.md = (char*)b; ws.md_cap = P.t_md_cap; b += (P.t_md_cap + 15) & ~15;
+	ws.xa = (char*)b; ws.xa_cap = P.t_xa_cap;
+	ws.brow = nullptr; ws.brow_cap = 0;
+	ws.err = lerr; // limits hit here are not errors: the item is redone by a warp with the large scratch
+}
+DEV void body_save_regs(const BatchParams& P, i64 r)
+{
+	const Reg* s = P.regs + P.reg_off[r]; Reg* d = P.snap + P.reg_off[r];
+	int n = (int)P.n_reg[r];
+	for (int i = 0; i < n; ++i) d[i] = s[i];
+}
+DEV void restore_regs(const BatchParams& P, i64 r, int lane, int W)
+{
+	const Reg* s = P.snap + P.reg_off[r]; Reg* d = P.regs + P.reg_off[r];
+	int n = (int)P.n_reg[r];
+	for (int i = lane; i < n; i += W) d[i] = s[i];
+}
+DEV void body_final_pe_t(const BatchParams& P, i64 pr, i64 tid)
+{
+	u32 lerr = 0;
+	WarpMem wm; WarpScratch ws; make_thread_ctx(P, tid, wm, ws, &lerr);
+	wbody_final_pe<1>(P, pr, wm, ws);
+	if (lerr) { u32 slot = atomic_add_u32(P.n_redo, 1u); P.redo_list[slot] = (u32)pr; }
+}
+DEV void body_final_se_t(const BatchParams& P, i64 r, i64 tid)
+{
+	u32 lerr = 0;
+	WarpMem wm; WarpScratch ws; make_thread_ctx(P, tid, wm, ws, &lerr);
+	wbody_final_se<1>(P, r, wm, ws);
+	if (lerr) { u32 slot = atomic_add_u32(P.n_redo, 1u); P.redo_list[slot] = (u32)r; }
+}
+template <int W>
+DEV void wbody_final_pe_redo(const BatchParams& P, i64 item, WarpMem& wm, WarpScratch& ws)
+{
+	LANE_DECL;
+	const i64 pr = (i64)P.redo_list[item];
+	FOR_LANES { restore_regs(P, pr << 1, lane, W); restore_regs(P, (pr << 1) + 1, lane, W); }
+	WARP_SYNC();
+	wbody_final_pe<W>(P, pr, wm, ws);
+}
+template <int W>
+DEV void wbody_final_se_redo(const BatchParams& P, i64 item, WarpMem& wm, WarpScratch& ws)
+{
+	LANE_DECL;
+	const i64 r = (i64)P.redo_list[item];
+	FOR_LANES { restore_regs(P, r, lane, W); }
+	WARP_SYNC();
+	wbody_final_se<W>(P, r, wm, ws);
 }
 
 // ---- output stream (fmt_BAMish, jnibwa.c:43-97): size per read, then write --------------------------

@@ -157,7 +157,7 @@ DEVNI void warp_extend2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, int q
 // Returns the score; *n_cigar_out = 0 when no traceback was requested (cigar == nullptr).
 template <int W>
 DEVNI int warp_global2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, int qlen, int tlen, TAcc ta, int w,
-                       u8* z, u32* cigar, int* n_cigar_out, u64* cell_counter)
+                       u8* z, u32* cigar, int cigar_cap, u32* err, int* n_cigar_out, u64* cell_counter)
 {
 	LANE_DECL;
 	const int o_del = opt.o_del, e_del = opt.e_del, o_ins = opt.o_ins, e_ins = opt.e_ins;
@@ -231,7 +231,9 @@ DEVNI int warp_global2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, int ql
 	}
 	int score = H[qlen];
 	if (bt) {
-		// traceback: sequential, warp-uniform
+		// traceback: sequential, warp-uniform; the op list is bounded by cigar_cap (overflow is reported, never written)
+#define CG_PUT() do { if (n_cigar < cigar_cap) { ONE_LANE { cigar[n_cigar] = cur_len << 4 | cur_op; } } else cg_ovf = true; ++n_cigar; } while (0)
+		bool cg_ovf = false;
 		int n_cigar = 0, which = 0, i = tlen - 1, k = (i + w + 1 < qlen ? i + w + 1 : qlen) - 1;
 		u32 cur_op = 0xffffffffu, cur_len = 0;
 		// ops are produced back to front; emitted reversed at the end
@@ -242,15 +244,17 @@ DEVNI int warp_global2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, int ql
 			else if (which == 1) { op = 2; --i; }
 			else { op = 1; --k; }
 			if (op == cur_op) ++cur_len;
-			else { if (cur_op != 0xffffffffu) { ONE_LANE { cigar[n_cigar] = cur_len << 4 | cur_op; } ++n_cigar; } cur_op = op; cur_len = 1; }
+			else { if (cur_op != 0xffffffffu) { CG_PUT(); } cur_op = op; cur_len = 1; }
 		}
-		if (i >= 0) { if (cur_op == 2) cur_len += (u32)(i + 1); else { if (cur_op != 0xffffffffu) { ONE_LANE { cigar[n_cigar] = cur_len << 4 | cur_op; } ++n_cigar; } cur_op = 2; cur_len = (u32)(i + 1); } }
-		if (k >= 0) { if (cur_op == 1) cur_len += (u32)(k + 1); else { if (cur_op != 0xffffffffu) { ONE_LANE { cigar[n_cigar] = cur_len << 4 | cur_op; } ++n_cigar; } cur_op = 1; cur_len = (u32)(k + 1); } }
-		if (cur_op != 0xffffffffu) { ONE_LANE { cigar[n_cigar] = cur_len << 4 | cur_op; } ++n_cigar; }
+		if (i >= 0) { if (cur_op == 2) cur_len += (u32)(i + 1); else { if (cur_op != 0xffffffffu) { CG_PUT(); } cur_op = 2; cur_len = (u32)(i + 1); } }
+		if (k >= 0) { if (cur_op == 1) cur_len += (u32)(k + 1); else { if (cur_op != 0xffffffffu) { CG_PUT(); } cur_op = 1; cur_len = (u32)(k + 1); } }
+		if (cur_op != 0xffffffffu) { CG_PUT(); }
 		WARP_SYNC();
-		ONE_LANE { for (int a = 0; a < n_cigar >> 1; ++a) { u32 t = cigar[a]; cigar[a] = cigar[n_cigar - 1 - a]; cigar[n_cigar - 1 - a] = t; } }
+		if (!cg_ovf) { ONE_LANE { for (int a = 0; a < n_cigar >> 1; ++a) { u32 t = cigar[a]; cigar[a] = cigar[n_cigar - 1 - a]; cigar[n_cigar - 1 - a] = t; } } }
 		WARP_SYNC();
+		if (cg_ovf) { ONE_LANE { atomic_or_u32(err, ERR_CIGAR_OVERFLOW); } n_cigar = 0; }
 		*n_cigar_out = n_cigar;
+#undef CG_PUT
 	}
 	if (cell_counter) { ONE_LANE { atomic_add_u64(cell_counter, cells); } }
 	return score;

@@ -29,6 +29,17 @@ static_assert(sizeof(PeStat) == 32, "mem_pestat_t layout");
 #define MEM_F_NO_RESCUE 0x20
 #define MEM_F_PRIMARY5  0x800
 
+// ---- capacity / limit flags raised by device code (any flag fails the batch, or re-routes a thread-level item to the warp path)
+#define ERR_Z_OVERFLOW     1u
+#define ERR_CIGAR_OVERFLOW 2u
+#define ERR_MD_OVERFLOW    4u
+#define ERR_XA_OVERFLOW    8u
+#define ERR_BROW_OVERFLOW  16u
+#define ERR_VAR_OVERFLOW   32u
+#define ERR_REG_OVERFLOW   64u
+#define ERR_INTV_OVERFLOW  128u
+#define ERR_QLEN_OVERFLOW  256u
+
 // ---- index resident in HBM --------------------------------------------------------------------
 struct DevIndex {
 	u64 primary, L2[5], seq_len;

@@ -33,6 +33,10 @@ static uint64_t rt_scan_u32(const uint32_t* in, uint64_t* out, uint64_t n) { uin
 	for (int64_t i_ = 0; i_ < (int64_t)(n); ++i_) wbody<32>(P, i_, wm_, ws_); } while (0)
 
 static void rt_timer_begin() {}
+#define RT_WARPS_DEVN(wbody, P, n_ptr, n_max) do { \
+	std::vector<uint8_t> sm_(warp_smem_bytes((P).wm_cap) + 64); \
+	WarpMem wm_; WarpScratch ws_; make_warp_ctx(P, 0, sm_.data(), wm_, ws_); \
+	for (int64_t i_ = 0; i_ < (int64_t)*(n_ptr); ++i_) wbody<32>(P, i_, wm_, ws_); } while (0)
 #include "engine_impl.inl"
 
 using namespace b200;
