@@ -131,7 +131,8 @@ DEF_THREAD_KERNEL(body_rescue_snap)
 DEF_THREAD_KERNEL(body_rescue_gen)
 DEF_THREAD_KERNEL(body_rescue_apply)
 DEF_WARP_KERNEL_DEVN(wbody_rescue_sw)
-DEF_WARP_KERNEL(wbody_extend)
+DEF_THREAD_TID_KERNEL(body_extend_t)
+DEF_WARP_KERNEL_DEVN(wbody_extend_heavy)
 DEF_THREAD_KERNEL(body_save_regs)
 DEF_THREAD_TID_KERNEL(body_final_pe_t)
 DEF_THREAD_TID_KERNEL(body_final_se_t)

@@ -114,7 +114,7 @@ struct Engine {
 	// batch workspace
 	DBuf b_blob, b_seq, b_seqoff, b_intv, b_nintv, b_nseed, b_smem, b_seedoff, b_rbeg, b_S, b_C, b_ord, b_tmp32, b_ck, b_ks, b_srt, b_regtmp,
 	     b_nck, b_nks, b_nreg, b_regcap, b_regoff, b_regs, b_snap, b_ztmp, b_pairv, b_recs, b_nrec, b_cand, b_pairtab, b_var, b_misc,
-	     b_outwords, b_outoff, b_out, b_wsz, b_wscig, b_wsmd, b_wsxa, b_wsbrow, b_nb, b_swtask, b_swstate, b_swlist, b_tbuf, b_redo;
+	     b_outwords, b_outoff, b_out, b_wsz, b_wscig, b_wsmd, b_wsxa, b_wsbrow, b_nb, b_swtask, b_swstate, b_swlist, b_tbuf, b_redo, b_heavy;
 	Counters last_counters; uint64_t last_n_seed = 0; int n_launches = 0;
 	std::string last_error;
 
@@ -175,13 +175,13 @@ inline void Engine::close_all()
 	DBuf* all[] = { &d_bwt, &d_sa, &d_pac, &d_ctg, &d_log, &d_names, &d_name_off, &b_blob, &b_seq, &b_seqoff, &b_intv, &b_nintv, &b_nseed, &b_smem,
 	                &b_seedoff, &b_rbeg, &b_S, &b_C, &b_ord, &b_tmp32, &b_ck, &b_ks, &b_srt, &b_regtmp, &b_nck, &b_nks, &b_nreg, &b_regcap, &b_regoff,
 	                &b_regs, &b_snap, &b_ztmp, &b_pairv, &b_recs, &b_nrec, &b_cand, &b_pairtab, &b_var, &b_misc, &b_outwords, &b_outoff, &b_out,
-	                &b_wsz, &b_wscig, &b_wsmd, &b_wsxa, &b_wsbrow, &b_nb, &b_swtask, &b_swstate, &b_swlist, &b_tbuf, &b_redo };
+	                &b_wsz, &b_wscig, &b_wsmd, &b_wsxa, &b_wsbrow, &b_nb, &b_swtask, &b_swstate, &b_swlist, &b_tbuf, &b_redo, &b_heavy };
 	for (DBuf* b : all) b->release();
 	if (map) munmap(map, map_len);
 	map = nullptr;
 }
 
-// misc block layout (u32 words): [0] err  [1] work counter  [2] var cursor  [3] rescue task count  [4] max nb  [5] redo count  [8..] Counters
+// misc block layout (u32 words): [0] err  [1] work counter  [2] var cursor  [3] rescue task count  [4] max nb  [5] redo count  [6] heavy-read count  [8..] Counters
 // Stage a request: one host pass over the blob for the read boundaries, then upload of bases and offsets.
 inline bool Engine::stage(const char* blob_in)
 {
@@ -301,8 +301,22 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 		P.ws_z = b_wsz.as<u8>(); P.ws_cigar = b_wscig.as<u32>(); P.ws_md = b_wsmd.as<char>(); P.ws_xa = b_wsxa.as<char>();
 		P.ws_brow = nullptr; P.ws_brow_cap = 0;
 	}
-	// ---- stage 3: extension + de-duplication
-	RT_WARPS(wbody_extend, P, (int64_t)n_reads);
+	// ---- thread scratch for the thread-per-item kernels (extension, finalize) and the hand-over lists
+	{
+		P.t_z_cap = 8192; P.t_cigar_cap = 48; P.t_md_cap = 192; P.t_xa_cap = 1024;
+		if (getenv("B200_TEST_TINY_SCRATCH")) { P.t_z_cap = 1024; P.t_cigar_cap = 6; P.t_md_cap = 24; P.t_xa_cap = 80; } // tests: force hand-overs
+		P.t_stride = thread_scratch_bytes(P.wm_cap, P.t_z_cap, P.t_cigar_cap, P.t_md_cap, P.t_xa_cap);
+		ok = b_tbuf.ensure((size_t)tslots * P.t_stride) && b_redo.ensure(((size_t)n_reads + 1) * 4) && b_heavy.ensure(((size_t)n_reads + 1) * 4);
+		if (!ok) { last_error = "device allocation failed (thread scratch)"; return nullptr; }
+		P.t_buf = b_tbuf.as<u8>(); P.redo_list = b_redo.as<u32>(); P.n_redo = b_misc.as<u32>() + 5;
+		P.heavy_list = b_heavy.as<u32>(); P.n_heavy = b_misc.as<u32>() + 6;
+		P.light_max_seeds = 12; P.light_max_chains = 4;
+		if (getenv("B200_TEST_ALL_HEAVY")) P.light_max_seeds = -1;
+		if (getenv("B200_TEST_ALL_LIGHT")) { P.light_max_seeds = 1 << 30; P.light_max_chains = 1 << 30; }
+	}
+	// ---- stage 3: extension + de-duplication (thread per light read, warp per heavy read)
+	RT_THREADS_TID(body_extend_t, P, (int64_t)n_reads);
+	RT_WARPS_DEVN(wbody_extend_heavy, P, P.n_heavy, (int64_t)n_reads);
 	// ---- paired-end: insert-size statistics (the one batch-global step; host)
 	for (int d = 0; d < 4; ++d) { memset(&P.pes[d], 0, sizeof(PeStat)); P.pes[d].failed = 1; }
 	if (pe) {
@@ -360,12 +374,6 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 	}
 	// ---- finalize: a thread per read / pair; items that exceed the thread-level scratch are redone by a warp
 	{
-		P.t_z_cap = 8192; P.t_cigar_cap = 48; P.t_md_cap = 192; P.t_xa_cap = 1024;
-		if (getenv("B200_TEST_TINY_SCRATCH")) { P.t_z_cap = 1024; P.t_cigar_cap = 6; P.t_md_cap = 24; P.t_xa_cap = 80; } // tests: force hand-overs
-		P.t_stride = thread_scratch_bytes(P.wm_cap, P.t_z_cap, P.t_cigar_cap, P.t_md_cap, P.t_xa_cap);
-		ok = b_tbuf.ensure((size_t)tslots * P.t_stride) && b_redo.ensure(((size_t)n_reads + 1) * 4);
-		if (!ok) { last_error = "device allocation failed (thread scratch)"; return nullptr; }
-		P.t_buf = b_tbuf.as<u8>(); P.redo_list = b_redo.as<u32>(); P.n_redo = b_misc.as<u32>() + 5;
 		RT_THREADS(body_save_regs, P, (int64_t)n_reads);
 		if (pe) { RT_THREADS_TID(body_final_pe_t, P, (int64_t)n_units); RT_WARPS_DEVN(wbody_final_pe_redo, P, P.n_redo, (int64_t)n_units); }
 		else { RT_THREADS_TID(body_final_se_t, P, (int64_t)n_reads); RT_WARPS_DEVN(wbody_final_se_redo, P, P.n_redo, (int64_t)n_reads); }

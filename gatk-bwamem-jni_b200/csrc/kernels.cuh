@@ -46,6 +46,7 @@ struct BatchParams {
 	// thread scratch (per resident thread of the thread-per-item kernels): DP rows, traceback, cigar, MD, XA
 	u8* t_buf; size_t t_stride; int t_z_cap, t_cigar_cap, t_md_cap, t_xa_cap;
 	u32* redo_list; u32* n_redo; // items a thread-level kernel handed over to the warp-level kernel
+	u32* heavy_list; u32* n_heavy; int light_max_seeds, light_max_chains; // extension: reads with many seeds go to the warp-level kernel
 	u32* err; Counters* cnt; u32* work_counter;
 };
 
@@ -274,6 +275,21 @@ DEV void make_thread_ctx(const BatchParams& P, i64 tid, WarpMem& wm, WarpScratch
 	ws.brow = nullptr; ws.brow_cap = 0;
 	ws.err = lerr; // limits hit here are not errors: the item is redone by a warp with the large scratch
 }
+// extension, thread per read: reads with few kept seeds are extended by one thread (scalar DP rows in the thread's
+// scratch); the others are queued for the warp-per-read kernel
+DEV void body_extend_t(const BatchParams& P, i64 r, i64 tid)
+{
+	const int nck = (int)P.n_ck[r], nks = (int)P.n_ks[r];
+	if (nck == 0) { P.n_reg[r] = 0; return; }
+	if (nks > P.light_max_seeds || nck > P.light_max_chains) { u32 slot = atomic_add_u32(P.n_heavy, 1u); P.heavy_list[slot] = (u32)r; return; }
+	u32 lerr = 0;
+	WarpMem wm; WarpScratch ws; make_thread_ctx(P, tid, wm, ws, &lerr);
+	ws.err = P.err; // nothing here is re-routable: limits are real errors
+	wbody_extend<1>(P, r, wm, ws);
+}
+template <int W>
+DEV void wbody_extend_heavy(const BatchParams& P, i64 item, WarpMem& wm, WarpScratch& ws) { wbody_extend<W>(P, (i64)P.heavy_list[item], wm, ws); }
+
 DEV void body_save_regs(const BatchParams& P, i64 r)
 {
 	const Reg* s = P.regs + P.reg_off[r]; Reg* d = P.snap + P.reg_off[r];

@@ -49,10 +49,153 @@ struct ExtResult { int score, qle, tle, gtle, gscore, max_off; };
 		FOR_LANES { if (lane >= d_) L_(pm) = imax(L_(pm), L_(t_)); } \
 	} } while (0)
 
+
+// ---- thread-per-task formulations (W = 1): the scalar recurrences, one cell at a time ------------------------
+DEVNI void thread_extend2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, int qlen, int tlen, TAcc ta,
+                          int w, int end_bonus, int zdrop, int h0, ExtResult& res, u64* cell_counter)
+{
+	const int o_del = opt.o_del, e_del = opt.e_del, o_ins = opt.o_ins, e_ins = opt.e_ins;
+	const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
+	i32* H = wm.H; i32* E = wm.E; const u8* q = wm.q;
+	H[0] = h0; E[0] = 0;
+	{
+		int v = h0 > oe_ins ? h0 - oe_ins : 0;
+		if (qlen >= 1) { H[1] = v; E[1] = 0; }
+		int j;
+		for (j = 2; j <= qlen && H[j - 1] > e_ins; ++j) { H[j] = H[j - 1] - e_ins; E[j] = 0; }
+		for (; j <= qlen; ++j) { H[j] = 0; E[j] = 0; }
+	}
+	int mx = 0;
+	for (int k = 0; k < 25; ++k) mx = mx > opt.mat[k] ? mx : (int)opt.mat[k];
+	int max_ins = (int)((double)(qlen * mx + end_bonus - o_ins) / e_ins + 1.); max_ins = max_ins > 1 ? max_ins : 1;
+	w = w < max_ins ? w : max_ins;
+	int max_del = (int)((double)(qlen * mx + end_bonus - o_del) / e_del + 1.); max_del = max_del > 1 ? max_del : 1;
+	w = w < max_del ? w : max_del;
+	int max = h0, max_i = -1, max_j = -1, max_ie = -1, gscore = -1, max_off = 0, beg = 0, end = qlen;
+	u64 cells = 0;
+	for (int i = 0; i < tlen; ++i) {
+		int f = 0, h1, m = 0, mj = -1, j;
+		const int tb = ref_base2(x, tacc_pos(ta, i));
+		u64 rowpack = 0;
+		for (int c = 0; c < 5; ++c) rowpack |= (u64)(u8)opt.mat[tb * 5 + c] << (8 * c);
+		if (beg < i - w) beg = i - w;
+		if (end > i + w + 1) end = i + w + 1;
+		if (end > qlen) end = qlen;
+		if (beg == 0) { h1 = h0 - (o_del + e_del * (i + 1)); if (h1 < 0) h1 = 0; } else h1 = 0;
+		if (end > beg) cells += (u64)(end - beg);
+		for (j = beg; j < end; ++j) {
+			int h, M = H[j], e = E[j], t;
+			H[j] = h1;
+			M = M ? M + (int)(i8)(rowpack >> (8 * q[j])) : 0;
+			h = M > e ? M : e;
+			h = h > f ? h : f;
+			h1 = h;
+			mj = m > h ? mj : j;
+			m = m > h ? m : h;
+			t = M - oe_del; t = t > 0 ? t : 0;
+			e -= e_del; e = e > t ? e : t;
+			E[j] = e;
+			t = M - oe_ins; t = t > 0 ? t : 0;
+			f -= e_ins; f = f > t ? f : t;
+		}
+		H[end] = h1; E[end] = 0;
+		if (j == qlen) { max_ie = gscore > h1 ? max_ie : i; gscore = gscore > h1 ? gscore : h1; }
+		if (m == 0) break;
+		if (m > max) { max = m; max_i = i; max_j = mj; int off = iabs(mj - i); max_off = max_off > off ? max_off : off; }
+		else if (zdrop > 0) {
+			if (i - max_i > mj - max_j) { if (max - m - ((i - max_i) - (mj - max_j)) * e_del > zdrop) break; }
+			else { if (max - m - ((mj - max_j) - (i - max_i)) * e_ins > zdrop) break; }
+		}
+		for (j = beg; j < end && H[j] == 0 && E[j] == 0; ++j) {}
+		beg = j;
+		for (j = end; j >= beg && H[j] == 0 && E[j] == 0; --j) {}
+		end = j + 2 < qlen ? j + 2 : qlen;
+	}
+	res.score = max; res.qle = max_j + 1; res.tle = max_i + 1; res.gtle = max_ie + 1; res.gscore = gscore; res.max_off = max_off;
+	if (cell_counter) atomic_add_u64(cell_counter, cells);
+}
+
+DEVNI int thread_global2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, int qlen, int tlen, TAcc ta, int w,
+                         u8* z, u32* cigar, int cigar_cap, u32* err, int* n_cigar_out, u64* cell_counter)
+{
+	const int o_del = opt.o_del, e_del = opt.e_del, o_ins = opt.o_ins, e_ins = opt.e_ins;
+	const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
+	i32* H = wm.H; i32* E = wm.E; const u8* q = wm.q;
+	const int n_col = qlen < 2 * w + 1 ? qlen : 2 * w + 1;
+	const bool bt = cigar != nullptr;
+	if (n_cigar_out) *n_cigar_out = 0;
+	{
+		int j;
+		H[0] = 0; E[0] = KSW_NEG_INF;
+		for (j = 1; j <= qlen && j <= w; ++j) { H[j] = -(o_ins + e_ins * j); E[j] = KSW_NEG_INF; }
+		for (; j <= qlen; ++j) { H[j] = KSW_NEG_INF; E[j] = KSW_NEG_INF; }
+	}
+	u64 cells = 0;
+	for (int i = 0; i < tlen; ++i) {
+		const int tb = ref_base2(x, tacc_pos(ta, i));
+		u64 rowpack = 0;
+		for (int c = 0; c < 5; ++c) rowpack |= (u64)(u8)opt.mat[tb * 5 + c] << (8 * c);
+		int f = KSW_NEG_INF, h1, t;
+		const int beg = i > w ? i - w : 0;
+		const int end = i + w + 1 < qlen ? i + w + 1 : qlen;
+		h1 = beg == 0 ? -(o_del + e_del * (i + 1)) : KSW_NEG_INF;
+		if (end > beg) cells += (u64)(end - beg);
+		u8* zi = bt ? z + (size_t)i * n_col : nullptr;
+		for (int j = beg; j < end; ++j) {
+			int h, m = H[j], e = E[j];
+			u8 d;
+			H[j] = h1;
+			m += (int)(i8)(rowpack >> (8 * q[j]));
+			d = m >= e ? 0 : 1;
+			h = m >= e ? m : e;
+			d = h >= f ? d : 2;
+			h = h >= f ? h : f;
+			h1 = h;
+			t = m - oe_del;
+			e -= e_del;
+			d |= e > t ? 1 << 2 : 0;
+			e = e > t ? e : t;
+			E[j] = e;
+			t = m - oe_ins;
+			f -= e_ins;
+			d |= f > t ? 2 << 4 : 0;
+			f = f > t ? f : t;
+			if (zi) zi[j - beg] = d;
+		}
+		H[end] = h1; E[end] = KSW_NEG_INF;
+	}
+	const int score = H[qlen];
+	if (bt) {
+		bool cg_ovf = false;
+		int n_cigar = 0, which = 0, i = tlen - 1, k = (i + w + 1 < qlen ? i + w + 1 : qlen) - 1;
+		u32 cur_op = 0xffffffffu, cur_len = 0;
+#define CG_PUT1() do { if (n_cigar < cigar_cap) cigar[n_cigar] = cur_len << 4 | cur_op; else cg_ovf = true; ++n_cigar; } while (0)
+		while (i >= 0 && k >= 0) {
+			which = z[(size_t)i * n_col + (k - (i > w ? i - w : 0))] >> (which << 1) & 3;
+			u32 op;
+			if (which == 0) { op = 0; --i; --k; }
+			else if (which == 1) { op = 2; --i; }
+			else { op = 1; --k; }
+			if (op == cur_op) ++cur_len;
+			else { if (cur_op != 0xffffffffu) { CG_PUT1(); } cur_op = op; cur_len = 1; }
+		}
+		if (i >= 0) { if (cur_op == 2) cur_len += (u32)(i + 1); else { if (cur_op != 0xffffffffu) { CG_PUT1(); } cur_op = 2; cur_len = (u32)(i + 1); } }
+		if (k >= 0) { if (cur_op == 1) cur_len += (u32)(k + 1); else { if (cur_op != 0xffffffffu) { CG_PUT1(); } cur_op = 1; cur_len = (u32)(k + 1); } }
+		if (cur_op != 0xffffffffu) { CG_PUT1(); }
+#undef CG_PUT1
+		if (cg_ovf) { atomic_or_u32(err, ERR_CIGAR_OVERFLOW); n_cigar = 0; }
+		else for (int a = 0; a < n_cigar >> 1; ++a) { u32 t = cigar[a]; cigar[a] = cigar[n_cigar - 1 - a]; cigar[n_cigar - 1 - a] = t; }
+		*n_cigar_out = n_cigar;
+	}
+	if (cell_counter) atomic_add_u64(cell_counter, cells);
+	return score;
+}
+
 template <int W>
 DEVNI void warp_extend2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, int qlen, int tlen, TAcc ta,
                         int w, int end_bonus, int zdrop, int h0, ExtResult& res, u64* cell_counter)
 {
+	if (W == 1) { thread_extend2(x, opt, wm, qlen, tlen, ta, w, end_bonus, zdrop, h0, res, cell_counter); return; }
 	LANE_DECL;
 	const int o_del = opt.o_del, e_del = opt.e_del, o_ins = opt.o_ins, e_ins = opt.e_ins;
 	const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
@@ -159,6 +302,7 @@ template <int W>
 DEVNI int warp_global2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, int qlen, int tlen, TAcc ta, int w,
                        u8* z, u32* cigar, int cigar_cap, u32* err, int* n_cigar_out, u64* cell_counter)
 {
+	if (W == 1) return thread_global2(x, opt, wm, qlen, tlen, ta, w, z, cigar, cigar_cap, err, n_cigar_out, cell_counter);
 	LANE_DECL;
 	const int o_del = opt.o_del, e_del = opt.e_del, o_ins = opt.o_ins, e_ins = opt.e_ins;
 	const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
