@@ -131,6 +131,7 @@ DEF_THREAD_KERNEL(body_rescue_snap)
 DEF_THREAD_KERNEL(body_rescue_gen)
 DEF_THREAD_KERNEL(body_rescue_apply)
 DEF_WARP_KERNEL_DEVN(wbody_rescue_sw)
+DEF_WARP_KERNEL(wbody_extend)
 DEF_THREAD_TID_KERNEL(body_extend_t)
 DEF_WARP_KERNEL_DEVN(wbody_extend_heavy)
 DEF_THREAD_KERNEL(body_save_regs)

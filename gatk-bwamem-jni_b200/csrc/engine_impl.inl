@@ -315,8 +315,10 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 		if (getenv("B200_TEST_ALL_LIGHT")) { P.light_max_seeds = 1 << 30; P.light_max_chains = 1 << 30; }
 	}
 	// ---- stage 3: extension + de-duplication (thread per light read, warp per heavy read)
-	RT_THREADS_TID(body_extend_t, P, (int64_t)n_reads);
-	RT_WARPS_DEVN(wbody_extend_heavy, P, P.n_heavy, (int64_t)n_reads);
+	if (getenv("B200_THREAD_EXTEND")) { // experimental: thread per light read (global-memory DP rows are slow; kept for tests)
+		RT_THREADS_TID(body_extend_t, P, (int64_t)n_reads);
+		RT_WARPS_DEVN(wbody_extend_heavy, P, P.n_heavy, (int64_t)n_reads);
+	} else RT_WARPS(wbody_extend, P, (int64_t)n_reads);
 	// ---- paired-end: insert-size statistics (the one batch-global step; host)
 	for (int d = 0; d < 4; ++d) { memset(&P.pes[d], 0, sizeof(PeStat)); P.pes[d].failed = 1; }
 	if (pe) {

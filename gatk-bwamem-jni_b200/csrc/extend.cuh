@@ -59,6 +59,10 @@ DEVNI bool warp_gen_cigar2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, Wa
 	const bool rev = rb >= l_pac; // reverse (not complement) both sequences so that indels left-align on the forward strand
 	TAcc ta; ta.piv = -1;
 	if (rev) { ta.base = re - 1; ta.stride = -1; } else { ta.base = rb; ta.stride = 1; }
+	if (W == 1 && !(l_query == rlen && w_ == 0)) { // thread-level callers hand banded DP over to a warp (see kernels.cuh)
+		atomic_or_u32(ws.err, ERR_NEED_WARP);
+		return false;
+	}
 	FOR_LANES { for (int j = lane; j < l_query; j += W) wm.q[j] = rev ? query[l_query - 1 - j] : query[j]; }
 	WARP_SYNC();
 	int nc = 0;

@@ -284,8 +284,9 @@ DEV void body_extend_t(const BatchParams& P, i64 r, i64 tid)
 	if (nks > P.light_max_seeds || nck > P.light_max_chains) { u32 slot = atomic_add_u32(P.n_heavy, 1u); P.heavy_list[slot] = (u32)r; return; }
 	u32 lerr = 0;
 	WarpMem wm; WarpScratch ws; make_thread_ctx(P, tid, wm, ws, &lerr);
-	ws.err = P.err; // nothing here is re-routable: limits are real errors
-	wbody_extend<1>(P, r, wm, ws);
+	wbody_extend<1>(P, r, wm, ws); // writes only this read's output slots, so a hand-over simply recomputes them
+	if (lerr & ERR_NEED_WARP) { u32 slot = atomic_add_u32(P.n_heavy, 1u); P.heavy_list[slot] = (u32)r; }
+	else if (lerr) atomic_or_u32(P.err, lerr);
 }
 template <int W>
 DEV void wbody_extend_heavy(const BatchParams& P, i64 item, WarpMem& wm, WarpScratch& ws) { wbody_extend<W>(P, (i64)P.heavy_list[item], wm, ws); }

@@ -39,6 +39,7 @@ static_assert(sizeof(PeStat) == 32, "mem_pestat_t layout");
 #define ERR_REG_OVERFLOW   64u
 #define ERR_INTV_OVERFLOW  128u
 #define ERR_QLEN_OVERFLOW  256u
+#define ERR_NEED_WARP      512u  // not an error: a thread-level item asks for the warp-level kernel
 
 // ---- index resident in HBM --------------------------------------------------------------------
 struct DevIndex {

@@ -22,9 +22,10 @@ def run(tag, img, blob, flag=0, check=True):
     al = bwa.BwaMemAligner(idx)
     al.setFlagOption(flag)
     log(tag, "start")
-    t = time.time()
-    out = idx.doAlignment(bytearray(blob), al._opts_addr, None)
-    dt = time.time() - t
+    for rep in range(2):  # the second call shows steady-state times (buffers grown, local-memory pool sized)
+        t = time.time()
+        out = idx.doAlignment(bytearray(blob), al._opts_addr, None)
+        dt = time.time() - t
     log(tag, f"gpu call {dt:.3f}s", stage_times(eng, idx))
     al.close(); idx.close()
     if check:
