@@ -12,6 +12,7 @@
 #include <unistd.h>
 #include <cuda_runtime.h>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
 
 #include "simt.cuh"
@@ -74,6 +75,15 @@ static uint64_t rt_scan_u32(const uint32_t* in, uint64_t* out, uint64_t n)
 	return total;
 }
 
+static void rt_sort_u64(const uint64_t* in, uint64_t* out, uint64_t n)
+{
+	if (!n) return;
+	size_t need = 0;
+	cub::DeviceRadixSort::SortKeys(nullptr, need, in, out, (int64_t)n, 0, 64, rt_stream());
+	if (need > g_scan_tmp_bytes) { if (g_scan_tmp) cudaFree(g_scan_tmp); cudaMalloc(&g_scan_tmp, need + 1024); g_scan_tmp_bytes = need + 1024; }
+	cub::DeviceRadixSort::SortKeys(g_scan_tmp, need, in, out, (int64_t)n, 0, 64, rt_stream());
+}
+
 // ---- launchers ---------------------------------------------------------------------------------------
 // Thread kernels: grid-stride over work items.  Warp kernels: one warp per item, items handed out by an
 // atomic counter so that long items (repetitive reads) do not stall a statically assigned neighbour.
@@ -130,6 +140,8 @@ DEF_THREAD_KERNEL(body_out_write)
 DEF_THREAD_KERNEL(body_rescue_snap)
 DEF_THREAD_KERNEL(body_rescue_gen)
 DEF_THREAD_KERNEL(body_rescue_apply)
+DEF_THREAD_KERNEL(body_rescue_gen_multi)
+DEF_THREAD_KERNEL(body_rescue_apply_multi)
 DEF_WARP_KERNEL_DEVN(wbody_rescue_sw)
 DEF_WARP_KERNEL(wbody_extend)
 DEF_THREAD_TID_KERNEL(body_extend_t)
@@ -183,6 +195,12 @@ static int g_launches = 0;
 #define RT_THREADS_TID(body, P, n) do { i64 n_ = (i64)(n); if (n_ > 0) { \
 	i64 nb_ = (n_ + THREADS_PER_BLOCK - 1) / THREADS_PER_BLOCK; i64 cap_ = (i64)rt_sm_count() * SEED_BLOCKS_PER_SM; if (nb_ > cap_) nb_ = cap_; \
 	k_##body<<<(unsigned)nb_, THREADS_PER_BLOCK, 0, rt_stream()>>>(P, n_); ++g_launches; } g_timer.mark(#body); } while (0)
+// thread kernels whose threads use the shared-memory rings (make_thread_ctx)
+#define RT_THREADS_TID_RING(body, P, n) do { i64 n_ = (i64)(n); if (n_ > 0) { \
+	i64 nb_ = (n_ + THREADS_PER_BLOCK - 1) / THREADS_PER_BLOCK; i64 cap_ = (i64)rt_sm_count() * SEED_BLOCKS_PER_SM; if (nb_ > cap_) nb_ = cap_; \
+	static bool attr_##body = false; size_t tsm_ = thread_block_smem_bytes(THREADS_PER_BLOCK); \
+	if (!attr_##body) { cudaFuncSetAttribute(k_##body, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm_); attr_##body = true; } \
+	k_##body<<<(unsigned)nb_, THREADS_PER_BLOCK, tsm_, rt_stream()>>>(P, n_); ++g_launches; } g_timer.mark(#body); } while (0)
 #define RT_WARPS(wbody, P, n) do { i64 n_ = (i64)(n); if (n_ > 0) { \
 	size_t sm_ = ((warp_smem_bytes((P).wm_cap) + 15) & ~(size_t)15) * WARPS_PER_BLOCK; \
 	i64 nb_ = (n_ + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK; i64 cap_ = (i64)rt_sm_count() * WARP_BLOCKS_PER_SM; if (nb_ > cap_) nb_ = cap_; \

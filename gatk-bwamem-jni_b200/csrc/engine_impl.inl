@@ -114,7 +114,7 @@ struct Engine {
 	// batch workspace
 	DBuf b_blob, b_seq, b_seqoff, b_intv, b_nintv, b_nseed, b_smem, b_seedoff, b_rbeg, b_S, b_C, b_ord, b_tmp32, b_ck, b_ks, b_srt, b_regtmp,
 	     b_nck, b_nks, b_nreg, b_regcap, b_regoff, b_regs, b_snap, b_ztmp, b_pairv, b_recs, b_nrec, b_cand, b_pairtab, b_var, b_misc,
-	     b_outwords, b_outoff, b_out, b_wsz, b_wscig, b_wsmd, b_wsxa, b_wsbrow, b_nb, b_swtask, b_swstate, b_swlist, b_tbuf, b_redo, b_heavy;
+	     b_outwords, b_outoff, b_out, b_wsz, b_wscig, b_wsmd, b_wsxa, b_wsbrow, b_nb, b_swtask, b_swstate, b_swlist, b_tbuf, b_redo, b_heavy, b_multi, b_cand2;
 	Counters last_counters; uint64_t last_n_seed = 0; int n_launches = 0;
 	std::string last_error;
 
@@ -175,13 +175,13 @@ inline void Engine::close_all()
 	DBuf* all[] = { &d_bwt, &d_sa, &d_pac, &d_ctg, &d_log, &d_names, &d_name_off, &b_blob, &b_seq, &b_seqoff, &b_intv, &b_nintv, &b_nseed, &b_smem,
 	                &b_seedoff, &b_rbeg, &b_S, &b_C, &b_ord, &b_tmp32, &b_ck, &b_ks, &b_srt, &b_regtmp, &b_nck, &b_nks, &b_nreg, &b_regcap, &b_regoff,
 	                &b_regs, &b_snap, &b_ztmp, &b_pairv, &b_recs, &b_nrec, &b_cand, &b_pairtab, &b_var, &b_misc, &b_outwords, &b_outoff, &b_out,
-	                &b_wsz, &b_wscig, &b_wsmd, &b_wsxa, &b_wsbrow, &b_nb, &b_swtask, &b_swstate, &b_swlist, &b_tbuf, &b_redo, &b_heavy };
+	                &b_wsz, &b_wscig, &b_wsmd, &b_wsxa, &b_wsbrow, &b_nb, &b_swtask, &b_swstate, &b_swlist, &b_tbuf, &b_redo, &b_heavy, &b_multi, &b_cand2 };
 	for (DBuf* b : all) b->release();
 	if (map) munmap(map, map_len);
 	map = nullptr;
 }
 
-// misc block layout (u32 words): [0] err  [1] work counter  [2] var cursor  [3] rescue task count  [4] max nb  [5] redo count  [6] heavy-read count  [8..] Counters
+// misc block layout (u32 words): [0] err  [1] work counter  [2] var cursor  [3] rescue task count  [4] max nb  [5] redo count  [6] heavy-read count  [7] multi-hit read count  [8..] Counters
 // Stage a request: one host pass over the blob for the read boundaries, then upload of bases and offsets.
 inline bool Engine::stage(const char* blob_in)
 {
@@ -316,7 +316,7 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 	}
 	// ---- stage 3: extension + de-duplication (thread per light read, warp per heavy read)
 	if (getenv("B200_THREAD_EXTEND")) { // experimental: thread per light read (global-memory DP rows are slow; kept for tests)
-		RT_THREADS_TID(body_extend_t, P, (int64_t)n_reads);
+		RT_THREADS_TID_RING(body_extend_t, P, (int64_t)n_reads);
 		RT_WARPS_DEVN(wbody_extend_heavy, P, P.n_heavy, (int64_t)n_reads);
 	} else RT_WARPS(wbody_extend, P, (int64_t)n_reads);
 	// ---- paired-end: insert-size statistics (the one batch-global step; host)
@@ -327,9 +327,12 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 			if (!b_cand.ensure((size_t)(n_units + 1) * 8)) { last_error = "device allocation failed"; return nullptr; }
 			P.pe_cand = b_cand.as<i64>();
 			RT_THREADS(body_pe_cand, P, (int64_t)n_units);
+			// sorted on the device (keys dir<<48 | isize; -1 = no candidate sorts last as unsigned), summed on the host
+			if (!b_cand2.ensure((size_t)(n_units + 1) * 8)) { last_error = "device allocation failed"; return nullptr; }
+			rt_sort_u64((const uint64_t*)P.pe_cand, b_cand2.as<uint64_t>(), (uint64_t)n_units);
 			std::vector<int64_t> cand((size_t)n_units);
-			rt_d2h(cand.data(), P.pe_cand, (size_t)n_units * 8);
-			host_mem_pestat(opt, cand.data(), n_units, P.pes);
+			rt_d2h(cand.data(), b_cand2.p, (size_t)n_units * 8);
+			host_mem_pestat(opt, cand.data(), n_units, P.pes, true);
 		}
 		std::vector<double> tab; int64_t off[4];
 		if (!host_pair_table(opt, P.pes, tab, off)) { last_error = "insert-size range too wide to tabulate"; return nullptr; }
@@ -360,25 +363,28 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 		ok = b_nb.ensure(nr * 4) && b_swtask.ensure(nr * 4 * sizeof(SwTask)) && b_swstate.ensure(nr * 4) && b_swlist.ensure(nr * 4 * 4);
 		if (!ok) { last_error = "device allocation failed (rescue pools)"; return nullptr; }
 		P.nb = b_nb.as<u32>(); P.sw_tasks = b_swtask.as<SwTask>(); P.sw_state = b_swstate.as<u8>(); P.sw_list = b_swlist.as<u32>();
-		P.sw_n_list = b_misc.as<u32>() + 3; P.max_nb = b_misc.as<u32>() + 4;
+		P.sw_n_list = b_misc.as<u32>() + 3; P.max_nb = b_misc.as<u32>() + 4; P.n_multi = b_misc.as<u32>() + 7;
+		if (!b_multi.ensure(nr * 4)) { last_error = "device allocation failed (rescue pools)"; return nullptr; }
+		P.multi = b_multi.as<u32>();
 		RT_THREADS(body_rescue_snap, P, (int64_t)n_reads);
-		uint32_t max_nb = 0;
-		rt_d2h(&max_nb, P.max_nb, 4);
+		uint32_t hdr[8];
+		rt_d2h(hdr, b_misc.as<u32>(), sizeof(hdr));
+		const uint32_t max_nb = hdr[4], n_multi = hdr[7];
 		int rounds = (int)max_nb < opt.max_matesw ? (int)max_nb : opt.max_matesw;
 		for (int k = 0; k < rounds; ++k) {
 			P.round = k;
 			rt_memset(P.sw_n_list, 0, 4);
-			RT_THREADS(body_rescue_gen, P, (int64_t)n_reads);
+			if (k == 0) RT_THREADS(body_rescue_gen, P, (int64_t)n_reads); else RT_THREADS(body_rescue_gen_multi, P, (int64_t)n_multi);
 			RT_WARPS_DEVN(wbody_rescue_sw, P, P.sw_n_list, (int64_t)n_reads * 4);
-			RT_THREADS(body_rescue_apply, P, (int64_t)n_reads);
+			if (k == 0) RT_THREADS(body_rescue_apply, P, (int64_t)n_reads); else RT_THREADS(body_rescue_apply_multi, P, (int64_t)n_multi);
 		}
 		P.rescued = 1;
 	}
 	// ---- finalize: a thread per read / pair; items that exceed the thread-level scratch are redone by a warp
 	{
 		RT_THREADS(body_save_regs, P, (int64_t)n_reads);
-		if (pe) { RT_THREADS_TID(body_final_pe_t, P, (int64_t)n_units); RT_WARPS_DEVN(wbody_final_pe_redo, P, P.n_redo, (int64_t)n_units); }
-		else { RT_THREADS_TID(body_final_se_t, P, (int64_t)n_reads); RT_WARPS_DEVN(wbody_final_se_redo, P, P.n_redo, (int64_t)n_reads); }
+		if (pe) { RT_THREADS_TID_RING(body_final_pe_t, P, (int64_t)n_units); RT_WARPS_DEVN(wbody_final_pe_redo, P, P.n_redo, (int64_t)n_units); }
+		else { RT_THREADS_TID_RING(body_final_se_t, P, (int64_t)n_reads); RT_WARPS_DEVN(wbody_final_se_redo, P, P.n_redo, (int64_t)n_reads); }
 	}
 	// ---- output stream
 	RT_THREADS(body_out_size, P, (int64_t)n_reads);

@@ -59,10 +59,6 @@ DEVNI bool warp_gen_cigar2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, Wa
 	const bool rev = rb >= l_pac; // reverse (not complement) both sequences so that indels left-align on the forward strand
 	TAcc ta; ta.piv = -1;
 	if (rev) { ta.base = re - 1; ta.stride = -1; } else { ta.base = rb; ta.stride = 1; }
-	if (W == 1 && !(l_query == rlen && w_ == 0)) { // thread-level callers hand banded DP over to a warp (see kernels.cuh)
-		atomic_or_u32(ws.err, ERR_NEED_WARP);
-		return false;
-	}
 	FOR_LANES { for (int j = lane; j < l_query; j += W) wm.q[j] = rev ? query[l_query - 1 - j] : query[j]; }
 	WARP_SYNC();
 	int nc = 0;
@@ -86,6 +82,10 @@ DEVNI bool warp_gen_cigar2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, Wa
 		if (want_cigar) {
 			int n_col = l_query < 2 * w + 1 ? l_query : 2 * w + 1;
 			if ((size_t)n_col * (size_t)rlen > ws.z_cap) { ONE_LANE { atomic_or_u32(ws.err, ERR_Z_OVERFLOW); } return false; }
+		}
+		if (W == 1 && (wm.ringH == nullptr || 2 * w + 2 > wm.ring_n)) { // band too wide for the thread's ring: a warp takes the item
+			atomic_or_u32(ws.err, ERR_NEED_WARP);
+			return false;
 		}
 		*score = warp_global2<W>(x, opt, wm, l_query, (int)rlen, ta, w, ws.z, want_cigar ? ws.cigar : nullptr, ws.cigar_cap, ws.err, &nc, cnt ? &cnt->cells_glb : nullptr);
 		if (cnt) { ONE_LANE { atomic_add_u64(&cnt->n_glb, 1); } }

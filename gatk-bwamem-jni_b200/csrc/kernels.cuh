@@ -33,7 +33,7 @@ struct BatchParams {
 	u32* reg_cap; u64* reg_off; Reg* regs; Reg* snap; u32* ztmp; Pair64* pairv; AlnRec* recs; u32* n_rec;
 	i64* pe_cand;           // per pair
 	// mate rescue (rescue.cuh)
-	u32* nb; SwTask* sw_tasks; u8* sw_state; u32* sw_list; u32* sw_n_list; u32* max_nb; int round; int rescued;
+	u32* nb; SwTask* sw_tasks; u8* sw_state; u32* sw_list; u32* sw_n_list; u32* max_nb; u32* multi; u32* n_multi; int round; int rescued;
 	PeStat pes[4];
 	const double* pair_tab; i64 pair_tab_off[4];
 	// output
@@ -118,6 +118,7 @@ DEV void make_warp_ctx(const BatchParams& P, i64 warp_slot, u8* smem, WarpMem& w
 	int cap = P.wm_cap;
 	i32* p = (i32*)smem;
 	wm.H = p; wm.E = p + (cap + 2); wm.H2 = p + 2 * (cap + 2); wm.Hm = p + 3 * (cap + 2); wm.fend = p + 4 * (cap + 2);
+	wm.ringH = nullptr; wm.ringE = nullptr; wm.ring_n = 0; wm.ring_stride = 0;
 	wm.q = (u8*)(p + 4 * (cap + 2) + 16);
 	wm.cap = cap;
 	ws.z = P.ws_z + (size_t)warp_slot * P.ws_z_cap; ws.z_cap = P.ws_z_cap;
@@ -184,11 +185,15 @@ DEV RescueIO make_rescue_io(const BatchParams& P)
 	RescueIO io;
 	io.seq_off = P.seq_off; io.seq = P.seq; io.reg_off = P.reg_off; io.reg_cap = P.reg_cap; io.regs = P.regs; io.n_reg = P.n_reg;
 	io.snap = P.snap; io.nb = P.nb; io.tasks = P.sw_tasks; io.state = P.sw_state; io.list = P.sw_list; io.n_list = P.sw_n_list;
-	io.max_nb = P.max_nb; io.n_reads = P.n_units << 1; io.round = P.round;
+	io.max_nb = P.max_nb; io.multi = P.multi; io.n_multi = P.n_multi; io.n_reads = P.n_units << 1; io.round = P.round;
 	return io;
 }
 DEV void body_rescue_snap(const BatchParams& P, i64 r) { RescueIO io = make_rescue_io(P); rescue_snap(P.opt, io, r); }
 DEV void body_rescue_gen(const BatchParams& P, i64 r) { if (r >= ((i64)P.n_units << 1)) return; RescueIO io = make_rescue_io(P); rescue_gen(P.x, P.opt, P.pes, io, r); }
+// rounds >= 1 visit only the reads with several rescuing hits (compact list built by the snapshot kernel)
+DEV void body_rescue_gen_multi(const BatchParams& P, i64 i) { if (i < (i64)*P.n_multi) body_rescue_gen(P, (i64)P.multi[i]); }
+DEV void body_rescue_apply(const BatchParams& P, i64 r);
+DEV void body_rescue_apply_multi(const BatchParams& P, i64 i) { if (i < (i64)*P.n_multi) body_rescue_apply(P, (i64)P.multi[i]); }
 DEV void body_rescue_apply(const BatchParams& P, i64 r)
 {
 	if (r >= ((i64)P.n_units << 1)) return;
@@ -259,6 +264,11 @@ HOSTDEV size_t thread_scratch_bytes(int wm_cap, int z_cap, int cigar_cap, int md
 	size_t n = (size_t)(2 * (wm_cap + 2)) * 4 + (size_t)((wm_cap + 2 + 15) & ~15) + (size_t)((z_cap + 15) & ~15) + (size_t)cigar_cap * 4 + (size_t)((md_cap + 15) & ~15) + (size_t)((xa_cap + 15) & ~15);
 	return (n + 127) & ~(size_t)127;
 }
+#ifdef B200_SIM
+static i32 g_sim_ring[2 * THREAD_RING_N];
+#endif
+// shared memory of a thread-level block: two rings of THREAD_RING_N i32 per thread
+HOSTDEV size_t thread_block_smem_bytes(int block_threads) { return (size_t)block_threads * THREAD_RING_N * 2 * 4; }
 DEV void make_thread_ctx(const BatchParams& P, i64 tid, WarpMem& wm, WarpScratch& ws, u32* lerr)
 {
 	const int cap = P.wm_cap;
@@ -268,6 +278,16 @@ DEV void make_thread_ctx(const BatchParams& P, i64 tid, WarpMem& wm, WarpScratch
 	b += (size_t)(2 * (cap + 2)) * 4;
 	wm.q = b; b += (cap + 2 + 15) & ~15;
 	wm.cap = cap;
+#ifdef B200_SIM
+	wm.ringH = g_sim_ring; wm.ringE = g_sim_ring + THREAD_RING_N; wm.ring_n = THREAD_RING_N; wm.ring_stride = 1;
+#else
+	{
+		extern __shared__ __align__(16) u8 tsm_[];
+		i32* r = (i32*)tsm_;
+		wm.ringH = r + threadIdx.x; wm.ringE = r + (size_t)blockDim.x * THREAD_RING_N + threadIdx.x;
+		wm.ring_n = THREAD_RING_N; wm.ring_stride = (int)blockDim.x;
+	}
+#endif
 	ws.z = b; ws.z_cap = (size_t)P.t_z_cap; b += (P.t_z_cap + 15) & ~15;
 	ws.cigar = (u32*)b; ws.cigar_cap = P.t_cigar_cap; b += (size_t)P.t_cigar_cap * 4;
 	ws.md = (char*)b; ws.md_cap = P.t_md_cap; b += (P.t_md_cap + 15) & ~15;

@@ -34,7 +34,11 @@ struct WarpMem {
 	u8* q;     // [cap+2]   query codes in DP orientation (5 = padding column)
 	i32* fend; // [16]
 	int cap;
+	// thread-level kernels (W = 1): ring buffers for the banded global alignment, in shared memory, one slot column per
+	// thread (element k of this thread's ring is ring?[k * ring_stride]; stride = block size keeps every access on bank tid % 32)
+	i32* ringH; i32* ringE; int ring_n; int ring_stride;
 };
+#define THREAD_RING_N 64
 
 // target accessor over the doubled reference text
 struct TAcc { i64 base; int stride; int piv; };
@@ -120,15 +124,22 @@ DEVNI int thread_global2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, int 
 {
 	const int o_del = opt.o_del, e_del = opt.e_del, o_ins = opt.o_ins, e_ins = opt.e_ins;
 	const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
-	i32* H = wm.H; i32* E = wm.E; const u8* q = wm.q;
+	const u8* q = wm.q;
+	// H/E rows: a ring of ring_n >= 2w+2 column slots when the caller provides one (a row touches columns
+	// [i-w, i+w+1] only and every column entering the band was written as H[end] by the row before), else the full rows
+	const bool ring = wm.ringH != nullptr && 2 * w + 2 <= wm.ring_n;
+	i32* H = ring ? wm.ringH : wm.H; i32* E = ring ? wm.ringE : wm.E;
+	const int rmask = ring ? wm.ring_n - 1 : -1, rstride = ring ? wm.ring_stride : 1;
+#define HX(j) (((j) & rmask) * rstride)
 	const int n_col = qlen < 2 * w + 1 ? qlen : 2 * w + 1;
 	const bool bt = cigar != nullptr;
 	if (n_cigar_out) *n_cigar_out = 0;
 	{
 		int j;
-		H[0] = 0; E[0] = KSW_NEG_INF;
-		for (j = 1; j <= qlen && j <= w; ++j) { H[j] = -(o_ins + e_ins * j); E[j] = KSW_NEG_INF; }
-		for (; j <= qlen; ++j) { H[j] = KSW_NEG_INF; E[j] = KSW_NEG_INF; }
+		H[HX(0)] = 0; E[HX(0)] = KSW_NEG_INF;
+		for (j = 1; j <= qlen && j <= w; ++j) { H[HX(j)] = -(o_ins + e_ins * j); E[HX(j)] = KSW_NEG_INF; }
+		if (!ring) for (; j <= qlen; ++j) { H[j] = KSW_NEG_INF; E[j] = KSW_NEG_INF; }
+		else if (j <= qlen) { H[HX(j)] = KSW_NEG_INF; E[HX(j)] = KSW_NEG_INF; } // column w+1: only ever read after row 0 overwrote it
 	}
 	u64 cells = 0;
 	for (int i = 0; i < tlen; ++i) {
@@ -142,9 +153,10 @@ DEVNI int thread_global2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, int 
 		if (end > beg) cells += (u64)(end - beg);
 		u8* zi = bt ? z + (size_t)i * n_col : nullptr;
 		for (int j = beg; j < end; ++j) {
-			int h, m = H[j], e = E[j];
+			const int jx = HX(j);
+			int h, m = H[jx], e = E[jx];
 			u8 d;
-			H[j] = h1;
+			H[jx] = h1;
 			m += (int)(i8)(rowpack >> (8 * q[j]));
 			d = m >= e ? 0 : 1;
 			h = m >= e ? m : e;
@@ -155,16 +167,17 @@ DEVNI int thread_global2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, int 
 			e -= e_del;
 			d |= e > t ? 1 << 2 : 0;
 			e = e > t ? e : t;
-			E[j] = e;
+			E[jx] = e;
 			t = m - oe_ins;
 			f -= e_ins;
 			d |= f > t ? 2 << 4 : 0;
 			f = f > t ? f : t;
 			if (zi) zi[j - beg] = d;
 		}
-		H[end] = h1; E[end] = KSW_NEG_INF;
+		H[HX(end)] = h1; E[HX(end)] = KSW_NEG_INF;
 	}
-	const int score = H[qlen];
+	const int score = H[HX(qlen)];
+#undef HX
 	if (bt) {
 		bool cg_ovf = false;
 		int n_cigar = 0, which = 0, i = tlen - 1, k = (i + w + 1 < qlen ? i + w + 1 : qlen) - 1;

@@ -12,7 +12,7 @@
 
 namespace b200 {
 
-inline void host_mem_pestat(const MemOpt& opt, const int64_t* cand, int64_t n_pairs, PeStat pes[4])
+inline void host_mem_pestat(const MemOpt& opt, const int64_t* cand, int64_t n_pairs, PeStat pes[4], bool presorted = false)
 {
 	std::vector<uint64_t> isize[4];
 	memset(pes, 0, 4 * sizeof(PeStat));
@@ -25,7 +25,7 @@ inline void host_mem_pestat(const MemOpt& opt, const int64_t* cand, int64_t n_pa
 		PeStat* r = &pes[d];
 		std::vector<uint64_t>& q = isize[d];
 		if (q.size() < 10) { r->failed = 1; continue; }
-		std::sort(q.begin(), q.end()); // integers: every correct sort yields the same array
+		if (!presorted) std::sort(q.begin(), q.end()); // integers: every correct sort yields the same array
 		size_t n = q.size();
 		int p25 = (int)q[(int)(.25 * n + .499)];
 		int p75 = (int)q[(int)(.75 * n + .499)];

@@ -204,6 +204,7 @@ struct RescueIO {
 	const u64* seq_off; const u8* seq; const u64* reg_off; const u32* reg_cap;
 	Reg* regs; u32* n_reg; Reg* snap; u32* nb;
 	SwTask* tasks; u8* state; u32* list; u32* n_list; u32* max_nb;
+	u32* multi; u32* n_multi; // reads with more than one rescuing hit (the only ones that take part in rounds >= 1)
 	int n_reads; int round;
 };
 
@@ -217,6 +218,7 @@ DEV void rescue_snap(const MemOpt& opt, const RescueIO& io, i64 r)
 	if (m > opt.max_matesw) m = opt.max_matesw;
 	io.nb[r] = (u32)m;
 	if (m) atomic_max_u32(io.max_nb, (u32)m);
+	if (m > 1) { u32 slot = atomic_add_u32(io.n_multi, 1u); io.multi[slot] = (u32)r; }
 }
 
 // ---- gen: the skip test and the windows of mem_matesw for hit `round` of read r -----------------------

@@ -21,12 +21,14 @@ static void rt_memset(void* d, int v, size_t n) { memset(d, v, n); }
 static void rt_sync() {}
 static int64_t rt_thread_slots() { return 1; }
 static int64_t rt_warp_slots() { return 1; }
+static void rt_sort_u64(const uint64_t* in, uint64_t* out, uint64_t n) { memcpy(out, in, n * 8); std::sort(out, out + n); }
 static uint64_t rt_scan_u32(const uint32_t* in, uint64_t* out, uint64_t n) { uint64_t s = 0; for (uint64_t i = 0; i < n; ++i) { out[i] = s; s += in[i]; } out[n] = s; return s; }
 
 #include "kernels.cuh"
 
 #define RT_THREADS(body, P, n) do { for (int64_t i_ = 0; i_ < (int64_t)(n); ++i_) body(P, i_); } while (0)
 #define RT_THREADS_TID(body, P, n) do { for (int64_t i_ = 0; i_ < (int64_t)(n); ++i_) body(P, i_, 0); } while (0)
+#define RT_THREADS_TID_RING(body, P, n) RT_THREADS_TID(body, P, n)
 #define RT_WARPS(wbody, P, n) do { \
 	std::vector<uint8_t> sm_(warp_smem_bytes((P).wm_cap) + 64); \
 	WarpMem wm_; WarpScratch ws_; make_warp_ctx(P, 0, sm_.data(), wm_, ws_); \
