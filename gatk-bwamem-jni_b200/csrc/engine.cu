@@ -198,8 +198,8 @@ static int g_launches = 0;
 // thread kernels whose threads use the shared-memory rings (make_thread_ctx)
 #define RT_THREADS_TID_RING(body, P, n) do { i64 n_ = (i64)(n); if (n_ > 0) { \
 	i64 nb_ = (n_ + THREADS_PER_BLOCK - 1) / THREADS_PER_BLOCK; i64 cap_ = (i64)rt_sm_count() * SEED_BLOCKS_PER_SM; if (nb_ > cap_) nb_ = cap_; \
-	static bool attr_##body = false; size_t tsm_ = thread_block_smem_bytes(THREADS_PER_BLOCK); \
-	if (!attr_##body) { cudaFuncSetAttribute(k_##body, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm_); attr_##body = true; } \
+	size_t tsm_ = thread_block_smem_bytes(THREADS_PER_BLOCK, (P).wm_cap); \
+	cudaFuncSetAttribute(k_##body, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm_); \
 	k_##body<<<(unsigned)nb_, THREADS_PER_BLOCK, tsm_, rt_stream()>>>(P, n_); ++g_launches; } g_timer.mark(#body); } while (0)
 #define RT_WARPS(wbody, P, n) do { i64 n_ = (i64)(n); if (n_ > 0) { \
 	size_t sm_ = ((warp_smem_bytes((P).wm_cap) + 15) & ~(size_t)15) * WARPS_PER_BLOCK; \

@@ -59,12 +59,12 @@ DEVNI bool warp_gen_cigar2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, Wa
 	const bool rev = rb >= l_pac; // reverse (not complement) both sequences so that indels left-align on the forward strand
 	TAcc ta; ta.piv = -1;
 	if (rev) { ta.base = re - 1; ta.stride = -1; } else { ta.base = rb; ta.stride = 1; }
-	FOR_LANES { for (int j = lane; j < l_query; j += W) wm.q[j] = rev ? query[l_query - 1 - j] : query[j]; }
+	FOR_LANES { for (int j = lane; j < l_query; j += W) WQ(wm, j) = rev ? query[l_query - 1 - j] : query[j]; }
 	WARP_SYNC();
 	int nc = 0;
 	if (l_query == rlen && w_ == 0) { // ungapped: one M run, score by direct summation
 		WV(int, part);
-		FOR_LANES { int s = 0; for (int j = lane; j < l_query; j += W) s += (int)opt.mat[ref_base2(x, tacc_pos(ta, j)) * 5 + wm.q[j]]; L_(part) = s; }
+		FOR_LANES { int s = 0; for (int j = lane; j < l_query; j += W) s += (int)opt.mat[ref_base2(x, tacc_pos(ta, j)) * 5 + WQ(wm, j)]; L_(part) = s; }
 		int tot = 0;
 		for (int l = 0; l < W; ++l) tot += wv_get(part, l);
 		*score = tot;
@@ -81,7 +81,7 @@ DEVNI bool warp_gen_cigar2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, Wa
 		w = w > min_w ? w : min_w;
 		if (want_cigar) {
 			int n_col = l_query < 2 * w + 1 ? l_query : 2 * w + 1;
-			if ((size_t)n_col * (size_t)rlen > ws.z_cap) { ONE_LANE { atomic_or_u32(ws.err, ERR_Z_OVERFLOW); } return false; }
+			if ((size_t)(W == 1 ? ((n_col + 3) & ~3) : n_col) * (size_t)rlen > ws.z_cap) { ONE_LANE { atomic_or_u32(ws.err, ERR_Z_OVERFLOW); } return false; }
 		}
 		if (W == 1 && (wm.ringH == nullptr || 2 * w + 2 > wm.ring_n)) { // band too wide for the thread's ring: a warp takes the item
 			atomic_or_u32(ws.err, ERR_NEED_WARP);
@@ -106,7 +106,7 @@ DEVNI bool warp_gen_cigar2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, Wa
 			if (op == 0) {
 				for (int i = 0; i < len; ++i) {
 					int rbs = ref_base2(x, tacc_pos(ta, y + i));
-					if ((int)wm.q[xq + i] != rbs) { MD_PUTNUM(u); MD_PUTC(int2base[rbs]); ++n_mm; u = 0; }
+					if ((int)WQ(wm, xq + i) != rbs) { MD_PUTNUM(u); MD_PUTC(int2base[rbs]); ++n_mm; u = 0; }
 					else ++u;
 				}
 				xq += len; y += len;
@@ -273,7 +273,7 @@ DEVNI void warp_chain2aln(const DevIndex& x, const MemOpt& opt, WarpMem& wm, War
 		int aw0 = opt.w, aw1 = opt.w;
 		a.w = opt.w; a.score = a.truesc = -1; a.rid = c.rid;
 		if (s.qbeg) { // left extension: both sequences reversed
-			FOR_LANES { for (int j = lane; j < s.qbeg; j += W) wm.q[j] = query[s.qbeg - 1 - j]; }
+			FOR_LANES { for (int j = lane; j < s.qbeg; j += W) WQ(wm, j) = query[s.qbeg - 1 - j]; }
 			WARP_SYNC();
 			TAcc ta; ta.base = s.rbeg - 1; ta.stride = -1; ta.piv = -1;
 			int tlen = (int)(s.rbeg - rmax0);
@@ -292,7 +292,7 @@ DEVNI void warp_chain2aln(const DevIndex& x, const MemOpt& opt, WarpMem& wm, War
 		if (s.qbeg + s.len != l_query) { // right extension
 			int qe = s.qbeg + s.len, sc0 = a.score;
 			i64 re = s.rbeg + s.len;
-			FOR_LANES { for (int j = lane; j < l_query - qe; j += W) wm.q[j] = query[qe + j]; }
+			FOR_LANES { for (int j = lane; j < l_query - qe; j += W) WQ(wm, j) = query[qe + j]; }
 			WARP_SYNC();
 			TAcc ta; ta.base = re; ta.stride = 1; ta.piv = -1;
 			int tlen = (int)(rmax1 - re);

@@ -429,7 +429,7 @@ DEVNI int warp_matesw(FinalCtx& f, const Reg& a, int l_ms, const u8* ms, Reg* ma
 				for (int j = lane; j < plen; j += W) {
 					u8 c = 5;
 					if (j < l_ms) { if (is_rev) { u8 b = ms[l_ms - 1 - j]; c = b < 4 ? (u8)(3 - b) : (u8)4; } else c = ms[j]; }
-					wm.q[j] = c;
+					WQ(wm, j) = c;
 				}
 			}
 			WARP_SYNC();
@@ -444,7 +444,7 @@ DEVNI int warp_matesw(FinalCtx& f, const Reg& a, int l_ms, const u8* ms, Reg* ma
 					for (int j = lane; j < plen2; j += W) {
 						u8 c = 5;
 						if (j < ql2) { int jj = fw.qe - j; if (is_rev) { u8 b = ms[l_ms - 1 - jj]; c = b < 4 ? (u8)(3 - b) : (u8)4; } else c = ms[jj]; }
-						wm.q[j] = c;
+						WQ(wm, j) = c;
 					}
 				}
 				WARP_SYNC();

@@ -95,128 +95,171 @@ struct SmemScratch { Intv* a; Intv* b; int cap; };
 struct IntvOut { Intv* v; int n, cap; bool overflow; };
 DEV void out_push(IntvOut& o, const Intv& t) { if (o.n < o.cap) o.v[o.n++] = t; else o.overflow = true; }
 
-// bwt_smem1a with max_intv = 0 (App. B.3).  Emits SMEMs (ascending begin) at o.v[o.n..]; returns the next start.
-DEV int fm_smem1(const DevIndex& x, int len, const u8* q, int start, u64 min_intv, SmemScratch& sc, IntvOut& o, int min_seed_len)
+// mem_collect_intv (bwt_smem1a with max_intv = 0 for rounds 1 and 2, bwt_seed_strategy1 for round 3; App. B.3) as ONE
+// loop with ONE fm_extend call site.  The three rounds and the forward / backward phases of SMEM discovery are states
+// of a small machine: each trip of the loop first advances the machine, without touching the index, to the next
+// interval that has to be extended (cheap, lane-divergent bookkeeping), then all lanes of the warp meet at the same
+// fm_extend (two occurrence-block fetches, the expensive part) and consume its result.  With nested per-phase loops the
+// lanes of a warp sit in different loops and the block fetches serialise (measured: 8 of 32 lanes active); with a
+// single call site they issue together.  The interval lists it produces are those of the nested-loop formulation.
+enum { SM_NEXT_R1, SM_FWD, SM_BWD_ROW, SM_BWD_ITEM, SM_NEXT_R2, SM_NEXT_R3, SM_S3, SM_DONE };
+enum { SMX_NONE, SMX_FWD, SMX_BWD, SMX_S3 };
+
+DEV void intv_set(Intv& t, const BiIntv& b, u32 beg, u32 end) { t.x0 = b.x0; t.x1 = b.x1; t.size = b.size; t.beg = beg; t.end = end; }
+
+DEV void fm_collect_intv(const DevIndex& x, const MemOpt& opt, int len, const u8* q, SmemScratch& sc, IntvOut& o)
 {
-	if (q[start] > 3) return start + 1;
-	if (min_intv < 1) min_intv = 1;
+	const int split_len = (int)(opt.min_seed_len * opt.split_factor + .499);
+	const int min_seed_len = opt.min_seed_len;
+	o.n = 0; o.overflow = false;
+	int st = SM_NEXT_R1, round = 1, pend = SMX_NONE;
+	int xx = 0;                 // rounds 1 and 3: next start position
+	int k2 = 0, old_n = 0;      // round 2: cursor over the round-1 SMEMs
+	// one SMEM search (bwt_smem1a) in flight
+	int start = 0, i = 0, ret = 0, c = -1, j = 0, first_out = 0;
+	u64 min_intv = 1, last_size = 0;
+	BiIntv ik, ext; u32 ik_end = 0;
 	Intv* prev = sc.a; Intv* curr = sc.b;
-	int n_prev, n_curr = 0, i, ret;
-	BiIntv ik, ok[4];
-	u32 ik_end = (u32)(start + 1);
-	fm_set_intv(x, q[start], ik);
-	for (i = start + 1; i < len; ++i) { // forward phase: record the interval at every change of size
-		if (q[i] < 4) {
-			int c = 3 - q[i];
-			fm_extend(x, ik, ok, 0);
-			if (ok[c].size != ik.size) {
-				if (n_curr < sc.cap) { Intv t; t.x0 = ik.x0; t.x1 = ik.x1; t.size = ik.size; t.beg = 0; t.end = ik_end; curr[n_curr++] = t; } else o.overflow = true;
-				if (ok[c].size < min_intv) break;
-			}
-			ik = ok[c]; ik_end = (u32)(i + 1);
-		} else {
-			if (n_curr < sc.cap) { Intv t; t.x0 = ik.x0; t.x1 = ik.x1; t.size = ik.size; t.beg = 0; t.end = ik_end; curr[n_curr++] = t; } else o.overflow = true;
-			break;
-		}
-	}
-	if (i == len) { if (n_curr < sc.cap) { Intv t; t.x0 = ik.x0; t.x1 = ik.x1; t.size = ik.size; t.beg = 0; t.end = ik_end; curr[n_curr++] = t; } else o.overflow = true; }
-	for (int j = 0; j < n_curr >> 1; ++j) { Intv t = curr[j]; curr[j] = curr[n_curr - 1 - j]; curr[n_curr - 1 - j] = t; } // longest match first
-	ret = (int)curr[0].end;
-	{ Intv* t = curr; curr = prev; prev = t; n_prev = n_curr; }
-	int first_out = o.n;
+	int n_prev = 0, n_curr = 0;
 	u32 last_beg = 0; bool have_out = false;
-	for (i = start - 1; i >= -1; --i) { // backward phase
-		int c = i < 0 ? -1 : (q[i] < 4 ? (int)q[i] : -1);
-		n_curr = 0;
-		u64 last_size = 0;
-		for (int j = 0; j < n_prev; ++j) {
-			Intv p = prev[j];
-			bool can = false;
-			if (c >= 0) {
-				BiIntv pk; pk.x0 = p.x0; pk.x1 = p.x1; pk.size = p.size;
-				fm_extend(x, pk, ok, 1);
-				can = ok[c].size >= min_intv;
+	Intv pcur; // backward phase: the candidate being extended
+	BiIntv ok[4];
+	ik.x0 = ik.x1 = ik.size = 0; ext = ik;
+	memset(&pcur, 0, sizeof(pcur));
+#define SM_PUSH_CURR(bi, e) do { if (n_curr < sc.cap) { intv_set(curr[n_curr], bi, 0, e); ++n_curr; } else o.overflow = true; } while (0)
+	for (;;) {
+		// ---- advance to the next extension (or to the end of the read)
+		while (pend == SMX_NONE && st != SM_DONE) {
+			switch (st) {
+			case SM_NEXT_R1:
+				while (xx < len && q[xx] > 3) ++xx;
+				if (xx >= len) { old_n = o.n; k2 = 0; round = 2; st = SM_NEXT_R2; break; }
+				start = xx; min_intv = 1;
+				fm_set_intv(x, q[start], ik); ik_end = (u32)(start + 1); n_curr = 0; i = start + 1; prev = sc.a; curr = sc.b;
+				st = SM_FWD;
+				break;
+			case SM_NEXT_R2: {
+				bool go = false;
+				while (k2 < old_n) {
+					const Intv p = o.v[k2];
+					if ((int)(p.end - p.beg) < split_len || p.size > (u64)opt.split_width) { ++k2; continue; }
+					start = (int)((p.beg + p.end) >> 1); min_intv = p.size + 1;
+					go = true;
+					break;
+				}
+				if (!go) { xx = 0; round = 3; st = opt.max_mem_intv > 0 ? SM_NEXT_R3 : SM_DONE; break; }
+				if (q[start] > 3) { ++k2; break; } // (an SMEM never holds an ambiguous base; kept for fidelity)
+				fm_set_intv(x, q[start], ik); ik_end = (u32)(start + 1); n_curr = 0; i = start + 1; prev = sc.a; curr = sc.b;
+				st = SM_FWD;
+				break; }
+			case SM_FWD: // forward phase: record the interval at every change of size
+				if (i < len && q[i] < 4) { ext = ik; pend = SMX_FWD; break; }
+				SM_PUSH_CURR(ik, ik_end); // i == len, or an ambiguous base ends the match
+				goto end_forward;
+			end_forward:
+				for (int a = 0; a < n_curr >> 1; ++a) { Intv t = curr[a]; curr[a] = curr[n_curr - 1 - a]; curr[n_curr - 1 - a] = t; } // longest match first
+				ret = (int)curr[0].end;
+				{ Intv* t = curr; curr = prev; prev = t; n_prev = n_curr; }
+				first_out = o.n; have_out = false; last_beg = 0;
+				i = start - 1;
+				st = SM_BWD_ROW;
+				break;
+			case SM_BWD_ROW:
+				if (i < -1) goto end_backward;
+				c = i < 0 ? -1 : (q[i] < 4 ? (int)q[i] : -1);
+				n_curr = 0; last_size = 0; j = 0;
+				st = SM_BWD_ITEM;
+				break;
+			case SM_BWD_ITEM:
+				if (j == n_prev) { // row finished
+					if (n_curr == 0) goto end_backward;
+					{ Intv* t = curr; curr = prev; prev = t; n_prev = n_curr; }
+					--i;
+					st = SM_BWD_ROW;
+					break;
+				}
+				pcur = prev[j];
+				if (c >= 0) { ext.x0 = pcur.x0; ext.x1 = pcur.x1; ext.size = pcur.size; pend = SMX_BWD; break; }
+				// no base to extend with: the candidate cannot grow
+				if (n_curr == 0 && (!have_out || (u32)(i + 1) < last_beg)) {
+					Intv t = pcur; t.beg = (u32)(i + 1);
+					have_out = true; last_beg = t.beg;
+					out_push(o, t);
+				}
+				++j;
+				break;
+			end_backward: {
+				for (int a = first_out, b = o.n - 1; a < b; ++a, --b) { Intv t = o.v[a]; o.v[a] = o.v[b]; o.v[b] = t; } // ascending begin
+				int w = first_out;
+				for (int a = first_out; a < o.n; ++a) if ((int)(o.v[a].end - o.v[a].beg) >= min_seed_len) o.v[w++] = o.v[a];
+				o.n = w;
+				if (round == 1) { xx = ret; st = SM_NEXT_R1; } else { ++k2; st = SM_NEXT_R2; }
+				break; }
+			case SM_NEXT_R3:
+				while (xx < len && q[xx] > 3) ++xx;
+				if (xx >= len) { st = SM_DONE; break; }
+				start = xx;
+				fm_set_intv(x, q[start], ik); i = start + 1;
+				st = SM_S3;
+				break;
+			case SM_S3: // bwt_seed_strategy1: shortest forward match of >= min_seed_len+1 bases with < max_mem_intv occurrences
+				if (i >= len) { xx = len; st = SM_NEXT_R3; break; }
+				if (q[i] > 3) { xx = i + 1; st = SM_NEXT_R3; break; }
+				ext = ik; pend = SMX_S3;
+				break;
+			default: st = SM_DONE; break;
 			}
-			if (!can) {
-				if (n_curr == 0) {
-					if (!have_out || (u32)(i + 1) < last_beg) {
-						Intv t = p; t.beg = (u32)(i + 1);
-						have_out = true; last_beg = t.beg;
-						out_push(o, t);
-					}
+		}
+		if (st == SM_DONE && pend == SMX_NONE) break;
+		// ---- the one place where the index is read
+		fm_extend(x, ext, ok, pend == SMX_BWD ? 1 : 0);
+		// ---- consume
+		if (pend == SMX_FWD) {
+			const int cc = 3 - q[i];
+			bool stop = false;
+			if (ok[cc].size != ik.size) {
+				SM_PUSH_CURR(ik, ik_end);
+				if (ok[cc].size < min_intv) stop = true;
+			}
+			if (!stop) { ik = ok[cc]; ik_end = (u32)(i + 1); ++i; st = SM_FWD; }
+			else { // same epilogue as the other forward exits (no second push: the loop ended before i == len)
+				for (int a = 0; a < n_curr >> 1; ++a) { Intv t = curr[a]; curr[a] = curr[n_curr - 1 - a]; curr[n_curr - 1 - a] = t; }
+				ret = (int)curr[0].end;
+				{ Intv* t = curr; curr = prev; prev = t; n_prev = n_curr; }
+				first_out = o.n; have_out = false; last_beg = 0;
+				i = start - 1;
+				st = SM_BWD_ROW;
+			}
+		} else if (pend == SMX_BWD) {
+			if (ok[c].size < min_intv) {
+				if (n_curr == 0 && (!have_out || (u32)(i + 1) < last_beg)) {
+					Intv t = pcur; t.beg = (u32)(i + 1);
+					have_out = true; last_beg = t.beg;
+					out_push(o, t);
 				}
 			} else if (n_curr == 0 || ok[c].size != last_size) {
-				Intv t; t.x0 = ok[c].x0; t.x1 = ok[c].x1; t.size = ok[c].size; t.beg = 0; t.end = p.end;
-				curr[n_curr++] = t; last_size = t.size; // n_curr <= n_prev <= cap
+				intv_set(curr[n_curr], ok[c], 0, pcur.end); ++n_curr; last_size = ok[c].size; // n_curr <= n_prev <= cap
 			}
+			++j;
+			st = SM_BWD_ITEM;
+		} else { // SMX_S3
+			const int cc = 3 - q[i];
+			if (ok[cc].size < opt.max_mem_intv && i - start >= min_seed_len) {
+				if (ok[cc].size > 0) { Intv m; intv_set(m, ok[cc], (u32)start, (u32)(i + 1)); out_push(o, m); }
+				xx = i + 1; st = SM_NEXT_R3;
+			} else { ik = ok[cc]; ++i; st = SM_S3; }
 		}
-		if (n_curr == 0) break;
-		{ Intv* t = curr; curr = prev; prev = t; n_prev = n_curr; }
+		pend = SMX_NONE;
 	}
-	// emitted in descending begin -> reverse, then keep only seeds of at least min_seed_len
-	for (int a = first_out, b = o.n - 1; a < b; ++a, --b) { Intv t = o.v[a]; o.v[a] = o.v[b]; o.v[b] = t; }
-	int w = first_out;
-	for (int a = first_out; a < o.n; ++a)
-		if ((int)(o.v[a].end - o.v[a].beg) >= min_seed_len) o.v[w++] = o.v[a];
-	o.n = w;
-	return ret;
-}
-
-// bwt_seed_strategy1 (round 3)
-DEV int fm_seed_strategy1(const DevIndex& x, int len, const u8* q, int start, int min_len, u64 max_intv, Intv& mem)
-{
-	BiIntv ik, ok[4];
-	mem.size = 0; mem.x0 = mem.x1 = 0; mem.beg = mem.end = 0;
-	if (q[start] > 3) return start + 1;
-	fm_set_intv(x, q[start], ik);
-	for (int i = start + 1; i < len; ++i) {
-		if (q[i] < 4) {
-			int c = 3 - q[i];
-			fm_extend(x, ik, ok, 0);
-			if (ok[c].size < max_intv && i - start >= min_len) {
-				mem.x0 = ok[c].x0; mem.x1 = ok[c].x1; mem.size = ok[c].size; mem.beg = (u32)start; mem.end = (u32)(i + 1);
-				return i + 1;
-			}
-			ik = ok[c];
-		} else return i + 1;
-	}
-	return len;
-}
-
-// mem_collect_intv: three rounds, then ordered by (beg, end).  Equal keys are identical intervals, so the
-// sort algorithm is unobservable here (unlike hazard H4 sorts) and a plain insertion sort is used.
-DEV void fm_collect_intv(const DevIndex& x, const MemOpt& opt, int len, const u8* seq, SmemScratch& sc, IntvOut& o)
-{
-	int start = 0;
-	int split_len = (int)(opt.min_seed_len * opt.split_factor + .499);
-	o.n = 0; o.overflow = false;
-	while (start < len) {
-		if (seq[start] < 4) start = fm_smem1(x, len, seq, start, 1, sc, o, opt.min_seed_len);
-		else ++start;
-	}
-	int old_n = o.n;
-	for (int k = 0; k < old_n; ++k) {
-		Intv p = o.v[k];
-		int beg = (int)p.beg, end = (int)p.end;
-		if (end - beg < split_len || p.size > (u64)opt.split_width) continue;
-		fm_smem1(x, len, seq, (beg + end) >> 1, p.size + 1, sc, o, opt.min_seed_len);
-	}
-	if (opt.max_mem_intv > 0) {
-		start = 0;
-		while (start < len) {
-			if (seq[start] < 4) {
-				Intv m;
-				start = fm_seed_strategy1(x, len, seq, start, opt.min_seed_len, opt.max_mem_intv, m);
-				if (m.size > 0) out_push(o, m);
-			} else ++start;
-		}
-	}
-	for (int i = 1; i < o.n; ++i) {
-		Intv t = o.v[i];
+#undef SM_PUSH_CURR
+	// ordered by (beg, end).  Equal keys are identical intervals, so the sort algorithm is unobservable here (unlike
+	// the hazard-H4 sorts) and a plain insertion sort is used.
+	for (int a = 1; a < o.n; ++a) {
+		Intv t = o.v[a];
 		u64 key = (u64)t.beg << 32 | t.end;
-		int j = i - 1;
-		while (j >= 0 && ((u64)o.v[j].beg << 32 | o.v[j].end) > key) { o.v[j + 1] = o.v[j]; --j; }
-		o.v[j + 1] = t;
+		int b = a - 1;
+		while (b >= 0 && ((u64)o.v[b].beg << 32 | o.v[b].end) > key) { o.v[b + 1] = o.v[b]; --b; }
+		o.v[b + 1] = t;
 	}
 }
 

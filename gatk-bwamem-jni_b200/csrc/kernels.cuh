@@ -119,7 +119,7 @@ DEV void make_warp_ctx(const BatchParams& P, i64 warp_slot, u8* smem, WarpMem& w
 	i32* p = (i32*)smem;
 	wm.H = p; wm.E = p + (cap + 2); wm.H2 = p + 2 * (cap + 2); wm.Hm = p + 3 * (cap + 2); wm.fend = p + 4 * (cap + 2);
 	wm.ringH = nullptr; wm.ringE = nullptr; wm.ring_n = 0; wm.ring_stride = 0;
-	wm.q = (u8*)(p + 4 * (cap + 2) + 16);
+	wm.q = (u8*)(p + 4 * (cap + 2) + 16); wm.q_stride = 1;
 	wm.cap = cap;
 	ws.z = P.ws_z + (size_t)warp_slot * P.ws_z_cap; ws.z_cap = P.ws_z_cap;
 	ws.cigar = P.ws_cigar + (size_t)warp_slot * P.ws_cigar_cap; ws.cigar_cap = P.ws_cigar_cap;
@@ -268,7 +268,7 @@ HOSTDEV size_t thread_scratch_bytes(int wm_cap, int z_cap, int cigar_cap, int md
 static i32 g_sim_ring[2 * THREAD_RING_N];
 #endif
 // shared memory of a thread-level block: two rings of THREAD_RING_N i32 per thread
-HOSTDEV size_t thread_block_smem_bytes(int block_threads) { return (size_t)block_threads * THREAD_RING_N * 2 * 4; }
+HOSTDEV size_t thread_block_smem_bytes(int block_threads, int wm_cap) { return (size_t)block_threads * (THREAD_RING_N * 2 * 4 + (size_t)((wm_cap + 2 + 3) & ~3)); }
 DEV void make_thread_ctx(const BatchParams& P, i64 tid, WarpMem& wm, WarpScratch& ws, u32* lerr)
 {
 	const int cap = P.wm_cap;
@@ -276,7 +276,7 @@ DEV void make_thread_ctx(const BatchParams& P, i64 tid, WarpMem& wm, WarpScratch
 	i32* p = (i32*)b;
 	wm.H = p; wm.E = p + (cap + 2); wm.H2 = nullptr; wm.Hm = nullptr; wm.fend = nullptr;
 	b += (size_t)(2 * (cap + 2)) * 4;
-	wm.q = b; b += (cap + 2 + 15) & ~15;
+	wm.q = b; wm.q_stride = 1; b += (cap + 2 + 15) & ~15;
 	wm.cap = cap;
 #ifdef B200_SIM
 	wm.ringH = g_sim_ring; wm.ringE = g_sim_ring + THREAD_RING_N; wm.ring_n = THREAD_RING_N; wm.ring_stride = 1;
@@ -286,6 +286,7 @@ DEV void make_thread_ctx(const BatchParams& P, i64 tid, WarpMem& wm, WarpScratch
 		i32* r = (i32*)tsm_;
 		wm.ringH = r + threadIdx.x; wm.ringE = r + (size_t)blockDim.x * THREAD_RING_N + threadIdx.x;
 		wm.ring_n = THREAD_RING_N; wm.ring_stride = (int)blockDim.x;
+		wm.q = tsm_ + (size_t)blockDim.x * THREAD_RING_N * 8 + threadIdx.x; wm.q_stride = (int)blockDim.x; // query row, interleaved like the rings
 	}
 #endif
 	ws.z = b; ws.z_cap = (size_t)P.t_z_cap; b += (P.t_z_cap + 15) & ~15;

@@ -31,7 +31,8 @@ struct WarpMem {
 	i32* E;    // [cap+2]
 	i32* H2;   // [cap+2]   (align2: second H row)
 	i32* Hm;   // [cap+2]   (align2: snapshot of the best row)
-	u8* q;     // [cap+2]   query codes in DP orientation (5 = padding column)
+	u8* q;     // [cap+2]   query codes in DP orientation (5 = padding column); element j is q[j * q_stride] (WQ)
+	int q_stride; // 1 for a warp's private row; the block size when threads of a block interleave their rows in shared memory
 	i32* fend; // [16]
 	int cap;
 	// thread-level kernels (W = 1): ring buffers for the banded global alignment, in shared memory, one slot column per
@@ -39,6 +40,7 @@ struct WarpMem {
 	i32* ringH; i32* ringE; int ring_n; int ring_stride;
 };
 #define THREAD_RING_N 64
+#define WQ(wm_, j_) (wm_).q[(size_t)(j_) * (wm_).q_stride]
 
 // target accessor over the doubled reference text
 struct TAcc { i64 base; int stride; int piv; };
@@ -60,7 +62,7 @@ DEVNI void thread_extend2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, int
 {
 	const int o_del = opt.o_del, e_del = opt.e_del, o_ins = opt.o_ins, e_ins = opt.e_ins;
 	const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
-	i32* H = wm.H; i32* E = wm.E; const u8* q = wm.q;
+	i32* H = wm.H; i32* E = wm.E; const u8* q = wm.q; const size_t qs = (size_t)wm.q_stride;
 	H[0] = h0; E[0] = 0;
 	{
 		int v = h0 > oe_ins ? h0 - oe_ins : 0;
@@ -90,7 +92,7 @@ DEVNI void thread_extend2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, int
 		for (j = beg; j < end; ++j) {
 			int h, M = H[j], e = E[j], t;
 			H[j] = h1;
-			M = M ? M + (int)(i8)(rowpack >> (8 * q[j])) : 0;
+			M = M ? M + (int)(i8)(rowpack >> (8 * q[j * qs])) : 0;
 			h = M > e ? M : e;
 			h = h > f ? h : f;
 			h1 = h;
@@ -124,7 +126,7 @@ DEVNI int thread_global2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, int 
 {
 	const int o_del = opt.o_del, e_del = opt.e_del, o_ins = opt.o_ins, e_ins = opt.e_ins;
 	const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
-	const u8* q = wm.q;
+	const u8* q = wm.q; const size_t qs = (size_t)wm.q_stride;
 	// H/E rows: a ring of ring_n >= 2w+2 column slots when the caller provides one (a row touches columns
 	// [i-w, i+w+1] only and every column entering the band was written as H[end] by the row before), else the full rows
 	const bool ring = wm.ringH != nullptr && 2 * w + 2 <= wm.ring_n;
@@ -132,6 +134,7 @@ DEVNI int thread_global2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, int 
 	const int rmask = ring ? wm.ring_n - 1 : -1, rstride = ring ? wm.ring_stride : 1;
 #define HX(j) (((j) & rmask) * rstride)
 	const int n_col = qlen < 2 * w + 1 ? qlen : 2 * w + 1;
+	const int zs = (n_col + 3) & ~3; // traceback row stride: whole 32-bit words, so four cells go out per store
 	const bool bt = cigar != nullptr;
 	if (n_cigar_out) *n_cigar_out = 0;
 	{
@@ -151,13 +154,14 @@ DEVNI int thread_global2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, int 
 		const int end = i + w + 1 < qlen ? i + w + 1 : qlen;
 		h1 = beg == 0 ? -(o_del + e_del * (i + 1)) : KSW_NEG_INF;
 		if (end > beg) cells += (u64)(end - beg);
-		u8* zi = bt ? z + (size_t)i * n_col : nullptr;
+		u32* zi = bt ? (u32*)(z + (size_t)i * zs) : nullptr;
+		u32 zw = 0;
 		for (int j = beg; j < end; ++j) {
 			const int jx = HX(j);
 			int h, m = H[jx], e = E[jx];
 			u8 d;
 			H[jx] = h1;
-			m += (int)(i8)(rowpack >> (8 * q[j]));
+			m += (int)(i8)(rowpack >> (8 * q[j * qs]));
 			d = m >= e ? 0 : 1;
 			h = m >= e ? m : e;
 			d = h >= f ? d : 2;
@@ -172,7 +176,11 @@ DEVNI int thread_global2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, int 
 			f -= e_ins;
 			d |= f > t ? 2 << 4 : 0;
 			f = f > t ? f : t;
-			if (zi) zi[j - beg] = d;
+			if (zi) {
+				const int k = j - beg;
+				zw |= (u32)d << ((k & 3) << 3);
+				if ((k & 3) == 3 || j == end - 1) { zi[k >> 2] = zw; zw = 0; }
+			}
 		}
 		H[HX(end)] = h1; E[HX(end)] = KSW_NEG_INF;
 	}
@@ -184,7 +192,7 @@ DEVNI int thread_global2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, int 
 		u32 cur_op = 0xffffffffu, cur_len = 0;
 #define CG_PUT1() do { if (n_cigar < cigar_cap) cigar[n_cigar] = cur_len << 4 | cur_op; else cg_ovf = true; ++n_cigar; } while (0)
 		while (i >= 0 && k >= 0) {
-			which = z[(size_t)i * n_col + (k - (i > w ? i - w : 0))] >> (which << 1) & 3;
+			which = z[(size_t)i * zs + (k - (i > w ? i - w : 0))] >> (which << 1) & 3;
 			u32 op;
 			if (which == 0) { op = 0; --i; --k; }
 			else if (which == 1) { op = 2; --i; }
@@ -252,7 +260,7 @@ DEVNI void warp_extend2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, int q
 				L_(act) = j < end;
 				int hold = L_(act) ? H[j] : 0;
 				L_(e) = L_(act) ? E[j] : 0;
-				int mm = hold ? hold + (int)opt.mat[tb * 5 + wm.q[L_(act) ? j : 0]] : 0;
+				int mm = hold ? hold + (int)opt.mat[tb * 5 + WQ(wm, L_(act) ? j : 0)] : 0;
 				L_(M) = mm;
 				int g = mm - oe_ins; g = g > 0 ? g : 0;
 				L_(pm) = L_(act) ? g + lane * e_ins : KSW_NEG_INF;
@@ -348,7 +356,7 @@ DEVNI int warp_global2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, int ql
 				L_(act) = j < end;
 				int hold = L_(act) ? H[j] : KSW_NEG_INF;
 				L_(e) = L_(act) ? E[j] : KSW_NEG_INF;
-				int mm = hold + (int)opt.mat[tb * 5 + wm.q[L_(act) ? j : 0]];
+				int mm = hold + (int)opt.mat[tb * 5 + WQ(wm, L_(act) ? j : 0)];
 				L_(M) = mm;
 				L_(pm) = L_(act) ? (mm - oe_ins) + lane * e_ins : 2 * KSW_NEG_INF + 1;
 			}
@@ -454,7 +462,7 @@ DEVNI SwFwd warp_sw_striped(const DevIndex& x, const MemOpt& opt, WarpMem& wm, i
 				int q = q0 + lane;
 				L_(act) = q < plen;
 				int qq = L_(act) ? q : 0;
-				int code = wm.q[qq];
+				int code = WQ(wm, qq);
 				int s = code < 5 ? (int)opt.mat[tb * 5 + code] : 0;
 				int hh = qq > 0 ? H0[qq - 1] : 0;
 				if (is_u8) { hh = hh + s + shift; if (hh > 255) hh = 255; hh -= shift; if (hh < 0) hh = 0; }

@@ -119,15 +119,21 @@ DEVNI SwFwd warp_sw_fast(const DevIndex& x, const MemOpt& opt, int lanes_simd, b
 			int u = fl + (s.qs + s.qn) * e_ins;
 			L_(useg) = u; L_(ufull) = u;
 		}
-		// full scan: F leaving every earlier lane, as seen at a common origin
-		WV_SCAN_MAX(ufull);
+		// A lane whose outgoing F is 0 cannot raise any later column (carries are floored at 0), so the two scans
+		// are skipped on rows where no lane has one -- the common case away from the true alignment.
+		WV(bool, has_out);
+		FOR_LANES { L_(has_out) = L_(lout) > 0; }
 		WV(int, cfull); WV(int, cseg);
-		wv_shfl_up(cfull, ufull, 1);
-		FOR_LANES { L_(cseg) = KSW_NEG_INF; }
-		for (int d = 1; d < k; ++d) {
-			WV(int, t_); wv_shfl_up(t_, useg, d);
-			FOR_LANES { if (L_(st).sub >= d && lane >= d) L_(cseg) = imax(L_(cseg), L_(t_)); }
-		}
+		if (wv_ballot(has_out) != 0u) {
+			// full scan: F leaving every earlier lane, as seen at a common origin
+			WV_SCAN_MAX(ufull);
+			wv_shfl_up(cfull, ufull, 1);
+			FOR_LANES { L_(cseg) = KSW_NEG_INF; }
+			for (int d = 1; d < k; ++d) {
+				WV(int, t_); wv_shfl_up(t_, useg, d);
+				FOR_LANES { if (L_(st).sub >= d && lane >= d) L_(cseg) = imax(L_(cseg), L_(t_)); }
+			}
+		} else { FOR_LANES { L_(cfull) = KSW_NEG_INF; L_(cseg) = KSW_NEG_INF; } }
 		WV(int, lmax);
 		FOR_LANES {
 			SwLane& s = L_(st);
@@ -288,7 +294,7 @@ DEVNI void rescue_sw(const DevIndex& x, const MemOpt& opt, WarpMem& wm, WarpScra
 		int slen = (l_ms + lanes_simd - 1) / lanes_simd, plen = slen * lanes_simd;
 		if (plen > wm.cap) { ONE_LANE { atomic_or_u32(ws.err, ERR_QLEN_OVERFLOW); } return; }
 		if (tlen > ws.brow_cap) { ONE_LANE { atomic_or_u32(ws.err, ERR_BROW_OVERFLOW); } return; }
-		FOR_LANES { for (int j = lane; j < plen; j += W) { u8 c = 5; if (j < l_ms) { if (t.is_rev) { u8 b = ms[l_ms - 1 - j]; c = b < 4 ? (u8)(3 - b) : (u8)4; } else c = ms[j]; } wm.q[j] = c; } }
+		FOR_LANES { for (int j = lane; j < plen; j += W) { u8 c = 5; if (j < l_ms) { if (t.is_rev) { u8 b = ms[l_ms - 1 - j]; c = b < 4 ? (u8)(3 - b) : (u8)4; } else c = ms[j]; } WQ(wm, j) = c; } }
 		WARP_SYNC();
 		fw = warp_sw_striped<W>(x, opt, wm, lanes_simd, is_u8, l_ms, tlen, ta, xtra, ws.brow, cnt ? &cnt->cells_msw : nullptr);
 	}
@@ -302,7 +308,7 @@ DEVNI void rescue_sw(const DevIndex& x, const MemOpt& opt, WarpMem& wm, WarpScra
 		} else {
 			int slen2 = (ql2 + lanes_simd - 1) / lanes_simd, plen2 = slen2 * lanes_simd;
 			if (plen2 > wm.cap) { ONE_LANE { atomic_or_u32(ws.err, ERR_QLEN_OVERFLOW); } return; }
-			FOR_LANES { for (int j = lane; j < plen2; j += W) { u8 c = 5; if (j < ql2) { int jj = fw.qe - j; if (t.is_rev) { u8 b = ms[l_ms - 1 - jj]; c = b < 4 ? (u8)(3 - b) : (u8)4; } else c = ms[jj]; } wm.q[j] = c; } }
+			FOR_LANES { for (int j = lane; j < plen2; j += W) { u8 c = 5; if (j < ql2) { int jj = fw.qe - j; if (t.is_rev) { u8 b = ms[l_ms - 1 - jj]; c = b < 4 ? (u8)(3 - b) : (u8)4; } else c = ms[jj]; } WQ(wm, j) = c; } }
 			WARP_SYNC();
 			rv = warp_sw_striped<W>(x, opt, wm, lanes_simd, is_u8, ql2, tlen, tr, KSW_XSTOP | fw.score, ws.brow, cnt ? &cnt->cells_msw : nullptr);
 		}
