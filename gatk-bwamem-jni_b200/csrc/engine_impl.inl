@@ -258,7 +258,7 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 	ok &= b_seq.ensure(blob_len + 16);
 	ok &= b_intv.ensure((size_t)n_reads * intv_cap * sizeof(Intv)) && b_nintv.ensure((size_t)n_reads * 4) && b_nseed.ensure((size_t)n_reads * 4);
 	const int64_t tslots = rt_thread_slots(), wslots = rt_warp_slots();
-	ok &= b_smem.ensure((size_t)tslots * 2 * (size_t)(max_len + 1) * sizeof(Intv));
+	ok &= b_smem.ensure((size_t)tslots * (size_t)(max_len + 1) * sizeof(Intv));
 	ok &= b_seedoff.ensure(((size_t)n_reads + 1) * 8) && b_nck.ensure((size_t)n_reads * 4) && b_nks.ensure((size_t)n_reads * 4) && b_nreg.ensure((size_t)n_reads * 4);
 	ok &= b_regcap.ensure((size_t)n_reads * 4) && b_regoff.ensure(((size_t)n_reads + 1) * 8) && b_nrec.ensure((size_t)n_reads * 4);
 	ok &= b_outwords.ensure((size_t)n_reads * 4) && b_outoff.ensure(((size_t)n_reads + 1) * 8) && b_misc.ensure(1024);
@@ -268,6 +268,7 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 	P.blob = b_blob.as<u8>(); P.seq = b_seq.as<u8>(); P.seq_off = b_seqoff.as<u64>();
 	P.intv = b_intv.as<Intv>(); P.intv_cap = intv_cap; P.n_intv = b_nintv.as<u32>(); P.n_seed = b_nseed.as<u32>();
 	P.smem_scratch = b_smem.as<Intv>(); P.smem_cap = max_len + 1;
+	P.seed_shared = (max_len <= 255 && img.seq_len < (1ULL << 40)) ? 1 : 0;
 	P.seed_off = b_seedoff.as<u64>(); P.n_ck = b_nck.as<u32>(); P.n_ks = b_nks.as<u32>(); P.n_reg = b_nreg.as<u32>();
 	P.reg_cap = b_regcap.as<u32>(); P.reg_off = b_regoff.as<u64>(); P.n_rec = b_nrec.as<u32>();
 	P.out_words = b_outwords.as<u32>(); P.out_off = b_outoff.as<u64>();
@@ -275,7 +276,7 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 
 	// ---- stage 1: encode + seed
 	RT_THREADS(body_encode, P, (int64_t)blob_len);
-	RT_THREADS_TID(body_seed, P, (int64_t)n_reads);
+	RT_THREADS_SEED(body_seed, P, (int64_t)n_reads, max_len);
 	uint64_t T = rt_scan_u32(P.n_seed, P.seed_off, n_reads);
 	P.n_seed_total = T; last_n_seed = T;
 	{

@@ -21,26 +21,24 @@ DEV OccBlock load_block(const DevIndex& x, u64 blk)
 	return b;
 }
 
-// counts of C, G, T among the first n (1..32) symbols of a 32-symbol word (first symbol in the top bits)
-DEV void count32(u64 y, int n, u32& cC, u32& cG, u32& cT)
-{
-	if (n < 32) y &= ~((1ull << ((32 - n) << 1)) - 1); // masked fields read as A and are never counted below
-	u64 lo = y & 0x5555555555555555ull, hi = (y >> 1) & 0x5555555555555555ull;
-	u32 t = (u32)popc64(lo & hi);
-	cT += t; cC += (u32)popc64(lo) - t; cG += (u32)popc64(hi) - t;
-}
-
-// occ of A,C,G,T in packed-BWT positions [0, kk] given the block that contains kk
+// Occurrences of A,C,G,T in packed-BWT positions [0, kk] given the block that holds kk.  Branch-free: every lane runs
+// the same twelve population counts whatever its offset in the block, so the lanes of a warp stay together (the
+// data-dependent "how many words to count" branches of a word-at-a-time formulation split a warp four ways).
+// Symbols past the offset are masked to 00 (= A) and never counted; A is what remains of n.
 DEV void occ4_in_block(const OccBlock& b, u64 kk, u64 cnt[4])
 {
-	int n = (int)(kk & 127) + 1;
-	u32 cC = 0, cG = 0, cT = 0;
-	u64 y0 = (u64)b.s0.x << 32 | b.s0.y, y1 = (u64)b.s0.z << 32 | b.s0.w;
-	u64 y2 = (u64)b.s1.x << 32 | b.s1.y, y3 = (u64)b.s1.z << 32 | b.s1.w;
-	count32(y0, n < 32 ? n : 32, cC, cG, cT);
-	if (n > 32) count32(y1, n < 64 ? n - 32 : 32, cC, cG, cT);
-	if (n > 64) count32(y2, n < 96 ? n - 64 : 32, cC, cG, cT);
-	if (n > 96) count32(y3, n - 96, cC, cG, cT);
+	const int n = (int)(kk & 127) + 1; // 1..128 symbols of this block
+	const u64 y[4] = { (u64)b.s0.x << 32 | b.s0.y, (u64)b.s0.z << 32 | b.s0.w, (u64)b.s1.x << 32 | b.s1.y, (u64)b.s1.z << 32 | b.s1.w };
+	u32 sLo = 0, sHi = 0, sT = 0;
+#pragma unroll
+	for (int w = 0; w < 4; ++w) {
+		int nn = n - 32 * w; nn = nn < 0 ? 0 : (nn > 32 ? 32 : nn);
+		const u64 mask = nn == 0 ? 0ull : (~0ull << ((32 - nn) << 1)); // first symbol sits in the top bits
+		const u64 v = y[w] & mask;
+		const u64 lo = v & 0x5555555555555555ull, hi = (v >> 1) & 0x5555555555555555ull;
+		sLo += (u32)popc64(lo); sHi += (u32)popc64(hi); sT += (u32)popc64(lo & hi);
+	}
+	const u32 cC = sLo - sT, cG = sHi - sT, cT = sT;
 	cnt[0] = ((u64)b.c01.x | (u64)b.c01.y << 32) + (u64)((u32)n - cC - cG - cT);
 	cnt[1] = ((u64)b.c01.z | (u64)b.c01.w << 32) + cC;
 	cnt[2] = ((u64)b.c23.x | (u64)b.c23.y << 32) + cG;
@@ -64,13 +62,17 @@ DEV void fm_extend(const DevIndex& x, const BiIntv& ik, BiIntv ok[4], int is_bac
 	u64 tk[4], tl[4];
 	u64 a0 = is_back ? ik.x0 : ik.x1, oth = is_back ? ik.x1 : ik.x0, s = ik.size;
 	u64 k = a0 - 1, l = a0 - 1 + s;
-	if (k != ~0ull && l != ~0ull) {
-		u64 k_ = k - (k >= x.primary), l_ = l - (l >= x.primary);
+	{ // both bounds, without branches: a bound of (u64)-1 (empty prefix) reads block 0 and is zeroed afterwards; when both
+	  // bounds fall in one block the second fetch is an L1 hit (bwt_2occ4's single touch, algorithmically)
+		const bool kz = k == ~0ull, lz = l == ~0ull;
+		const u64 k_ = kz ? 0 : k - (k >= x.primary), l_ = lz ? 0 : l - (l >= x.primary);
 		OccBlock bk = load_block(x, k_ >> 7);
+		OccBlock bl = load_block(x, l_ >> 7);
 		occ4_in_block(bk, k_, tk);
-		if ((l_ >> 7) == (k_ >> 7)) occ4_in_block(bk, l_, tl); // both bounds in one block: one touch (bwt_2occ4)
-		else { OccBlock bl = load_block(x, l_ >> 7); occ4_in_block(bl, l_, tl); }
-	} else { occ4(x, k, tk); occ4(x, l, tl); }
+		occ4_in_block(bl, l_, tl);
+		if (kz) { tk[0] = tk[1] = tk[2] = tk[3] = 0; }
+		if (lz) { tl[0] = tl[1] = tl[2] = tl[3] = 0; }
+	}
 #pragma unroll
 	for (int c = 0; c < 4; ++c) {
 		u64 v = x.L2[c] + 1 + tk[c];
@@ -89,53 +91,87 @@ DEV void fm_set_intv(const DevIndex& x, int c, BiIntv& ik)
 }
 
 // ---- SMEM discovery -----------------------------------------------------------------------------
-// Scratch lists of one read (thread-private): candidate intervals carry the query end in `end`.
-struct SmemScratch { Intv* a; Intv* b; int cap; };
-
+// Working set of one read (one thread): the candidate list of the SMEM search in flight and the read's base codes.
+// Both live in shared memory, interleaved over the threads of the block (element k of this thread's row is at
+// k * stride, so every access stays on bank tid % 32); candidates beyond `lcap` spill to the thread's slice of a
+// global pool.  A candidate is packed in 16 bytes: the low words of x0, x1 and size, then one byte each of their bits
+// 32..39 and the query end -- enough for |T| < 2^40 and reads of <= 255 bases (longer reads keep everything global).
+struct SeedWork {
+	uint4* L; int lstride, lcap;   // shared candidate list (packed); lcap = 0 -> global only
+	Intv* G; int gcap;             // global spill of the list, entries [lcap, lcap + gcap)
+	u8* qs; int qstride;           // shared copy of the read (nullptr -> read through q)
+};
 struct IntvOut { Intv* v; int n, cap; bool overflow; };
 DEV void out_push(IntvOut& o, const Intv& t) { if (o.n < o.cap) o.v[o.n++] = t; else o.overflow = true; }
+
+DEV void cand_set(const SeedWork& w, int k, const BiIntv& b, u32 end)
+{
+	if (k < w.lcap) {
+		uint4 e;
+		e.x = (u32)b.x0; e.y = (u32)b.x1; e.z = (u32)b.size;
+		e.w = (u32)(b.x0 >> 32 & 0xff) | (u32)(b.x1 >> 32 & 0xff) << 8 | (u32)(b.size >> 32 & 0xff) << 16 | end << 24;
+		w.L[(size_t)k * w.lstride] = e;
+	} else { Intv& t = w.G[k - w.lcap]; t.x0 = b.x0; t.x1 = b.x1; t.size = b.size; t.beg = 0; t.end = end; }
+}
+DEV void cand_get(const SeedWork& w, int k, BiIntv& b, u32& end)
+{
+	if (k < w.lcap) {
+		const uint4 e = w.L[(size_t)k * w.lstride];
+		b.x0 = (u64)e.x | (u64)(e.w & 0xff) << 32; b.x1 = (u64)e.y | (u64)(e.w >> 8 & 0xff) << 32; b.size = (u64)e.z | (u64)(e.w >> 16 & 0xff) << 32;
+		end = e.w >> 24;
+	} else { const Intv& t = w.G[k - w.lcap]; b.x0 = t.x0; b.x1 = t.x1; b.size = t.size; end = t.end; }
+}
 
 // mem_collect_intv (bwt_smem1a with max_intv = 0 for rounds 1 and 2, bwt_seed_strategy1 for round 3; App. B.3) as ONE
 // loop with ONE fm_extend call site.  The three rounds and the forward / backward phases of SMEM discovery are states
 // of a small machine: each trip of the loop first advances the machine, without touching the index, to the next
-// interval that has to be extended (cheap, lane-divergent bookkeeping), then all lanes of the warp meet at the same
-// fm_extend (two occurrence-block fetches, the expensive part) and consume its result.  With nested per-phase loops the
-// lanes of a warp sit in different loops and the block fetches serialise (measured: 8 of 32 lanes active); with a
-// single call site they issue together.  The interval lists it produces are those of the nested-loop formulation.
+// interval that has to be extended (lane-divergent bookkeeping on shared memory and registers), then all lanes of the
+// warp meet at the same fm_extend (two occurrence-block fetches, the expensive part) and consume its result.
+// The backward phase compacts the candidate list in place: row i reads candidate j and writes at most j survivors, so
+// the "previous" and "current" lists of the textbook formulation share one array.
 enum { SM_NEXT_R1, SM_FWD, SM_BWD_ROW, SM_BWD_ITEM, SM_NEXT_R2, SM_NEXT_R3, SM_S3, SM_DONE };
 enum { SMX_NONE, SMX_FWD, SMX_BWD, SMX_S3 };
 
 DEV void intv_set(Intv& t, const BiIntv& b, u32 beg, u32 end) { t.x0 = b.x0; t.x1 = b.x1; t.size = b.size; t.beg = beg; t.end = end; }
 
-DEV void fm_collect_intv(const DevIndex& x, const MemOpt& opt, int len, const u8* q, SmemScratch& sc, IntvOut& o)
+DEV void fm_collect_intv(const DevIndex& x, const MemOpt& opt, int len, const u8* qg, const SeedWork& wk, IntvOut& o)
 {
 	const int split_len = (int)(opt.min_seed_len * opt.split_factor + .499);
 	const int min_seed_len = opt.min_seed_len;
+	const int lcap_all = wk.lcap + wk.gcap;
 	o.n = 0; o.overflow = false;
+	// the read's codes: shared copy when provided
+	const u8* q = qg; size_t qst = 1;
+	if (wk.qs) { for (int t = 0; t < len; ++t) wk.qs[(size_t)t * wk.qstride] = qg[t]; q = wk.qs; qst = (size_t)wk.qstride; }
+#define Q(i_) q[(size_t)(i_) * qst]
 	int st = SM_NEXT_R1, round = 1, pend = SMX_NONE;
 	int xx = 0;                 // rounds 1 and 3: next start position
 	int k2 = 0, old_n = 0;      // round 2: cursor over the round-1 SMEMs
-	// one SMEM search (bwt_smem1a) in flight
 	int start = 0, i = 0, ret = 0, c = -1, j = 0, first_out = 0;
 	u64 min_intv = 1, last_size = 0;
-	BiIntv ik, ext; u32 ik_end = 0;
-	Intv* prev = sc.a; Intv* curr = sc.b;
+	BiIntv ik, ext, pcur; u32 ik_end = 0, pcur_end = 0;
 	int n_prev = 0, n_curr = 0;
 	u32 last_beg = 0; bool have_out = false;
-	Intv pcur; // backward phase: the candidate being extended
 	BiIntv ok[4];
-	ik.x0 = ik.x1 = ik.size = 0; ext = ik;
-	memset(&pcur, 0, sizeof(pcur));
-#define SM_PUSH_CURR(bi, e) do { if (n_curr < sc.cap) { intv_set(curr[n_curr], bi, 0, e); ++n_curr; } else o.overflow = true; } while (0)
+	ik.x0 = ik.x1 = ik.size = 0; ext = ik; pcur = ik;
+#define SM_PUSH(bi, e) do { if (n_curr < lcap_all) { cand_set(wk, n_curr, bi, e); ++n_curr; } else o.overflow = true; } while (0)
+#define SM_END_FORWARD() do { \
+		for (int a_ = 0; a_ < n_curr >> 1; ++a_) { /* longest match first */ \
+			BiIntv t0_, t1_; u32 e0_, e1_; cand_get(wk, a_, t0_, e0_); cand_get(wk, n_curr - 1 - a_, t1_, e1_); \
+			cand_set(wk, a_, t1_, e1_); cand_set(wk, n_curr - 1 - a_, t0_, e0_); } \
+		{ BiIntv t0_; u32 e0_ = 0; if (n_curr > 0) cand_get(wk, 0, t0_, e0_); ret = (int)e0_; } \
+		n_prev = n_curr; first_out = o.n; have_out = false; last_beg = 0; i = start - 1; st = SM_BWD_ROW; } while (0)
+#define SM_EMIT_PCUR() do { if (n_curr == 0 && (!have_out || (u32)(i + 1) < last_beg)) { \
+		Intv t_; intv_set(t_, pcur, (u32)(i + 1), pcur_end); have_out = true; last_beg = t_.beg; out_push(o, t_); } } while (0)
 	for (;;) {
 		// ---- advance to the next extension (or to the end of the read)
 		while (pend == SMX_NONE && st != SM_DONE) {
 			switch (st) {
 			case SM_NEXT_R1:
-				while (xx < len && q[xx] > 3) ++xx;
+				while (xx < len && Q(xx) > 3) ++xx;
 				if (xx >= len) { old_n = o.n; k2 = 0; round = 2; st = SM_NEXT_R2; break; }
 				start = xx; min_intv = 1;
-				fm_set_intv(x, q[start], ik); ik_end = (u32)(start + 1); n_curr = 0; i = start + 1; prev = sc.a; curr = sc.b;
+				fm_set_intv(x, Q(start), ik); ik_end = (u32)(start + 1); n_curr = 0; i = start + 1;
 				st = SM_FWD;
 				break;
 			case SM_NEXT_R2: {
@@ -148,44 +184,32 @@ DEV void fm_collect_intv(const DevIndex& x, const MemOpt& opt, int len, const u8
 					break;
 				}
 				if (!go) { xx = 0; round = 3; st = opt.max_mem_intv > 0 ? SM_NEXT_R3 : SM_DONE; break; }
-				if (q[start] > 3) { ++k2; break; } // (an SMEM never holds an ambiguous base; kept for fidelity)
-				fm_set_intv(x, q[start], ik); ik_end = (u32)(start + 1); n_curr = 0; i = start + 1; prev = sc.a; curr = sc.b;
+				if (Q(start) > 3) { ++k2; break; } // (an SMEM never holds an ambiguous base; kept for fidelity)
+				fm_set_intv(x, Q(start), ik); ik_end = (u32)(start + 1); n_curr = 0; i = start + 1;
 				st = SM_FWD;
 				break; }
 			case SM_FWD: // forward phase: record the interval at every change of size
-				if (i < len && q[i] < 4) { ext = ik; pend = SMX_FWD; break; }
-				SM_PUSH_CURR(ik, ik_end); // i == len, or an ambiguous base ends the match
-				goto end_forward;
-			end_forward:
-				for (int a = 0; a < n_curr >> 1; ++a) { Intv t = curr[a]; curr[a] = curr[n_curr - 1 - a]; curr[n_curr - 1 - a] = t; } // longest match first
-				ret = (int)curr[0].end;
-				{ Intv* t = curr; curr = prev; prev = t; n_prev = n_curr; }
-				first_out = o.n; have_out = false; last_beg = 0;
-				i = start - 1;
-				st = SM_BWD_ROW;
+				if (i < len && Q(i) < 4) { ext = ik; pend = SMX_FWD; break; }
+				SM_PUSH(ik, ik_end); // i == len, or an ambiguous base ends the match
+				SM_END_FORWARD();
 				break;
 			case SM_BWD_ROW:
 				if (i < -1) goto end_backward;
-				c = i < 0 ? -1 : (q[i] < 4 ? (int)q[i] : -1);
+				c = i < 0 ? -1 : (Q(i) < 4 ? (int)Q(i) : -1);
 				n_curr = 0; last_size = 0; j = 0;
 				st = SM_BWD_ITEM;
 				break;
 			case SM_BWD_ITEM:
 				if (j == n_prev) { // row finished
 					if (n_curr == 0) goto end_backward;
-					{ Intv* t = curr; curr = prev; prev = t; n_prev = n_curr; }
+					n_prev = n_curr;
 					--i;
 					st = SM_BWD_ROW;
 					break;
 				}
-				pcur = prev[j];
-				if (c >= 0) { ext.x0 = pcur.x0; ext.x1 = pcur.x1; ext.size = pcur.size; pend = SMX_BWD; break; }
-				// no base to extend with: the candidate cannot grow
-				if (n_curr == 0 && (!have_out || (u32)(i + 1) < last_beg)) {
-					Intv t = pcur; t.beg = (u32)(i + 1);
-					have_out = true; last_beg = t.beg;
-					out_push(o, t);
-				}
+				cand_get(wk, j, pcur, pcur_end);
+				if (c >= 0) { ext = pcur; pend = SMX_BWD; break; }
+				SM_EMIT_PCUR(); // no base to extend with: the candidate cannot grow
 				++j;
 				break;
 			end_backward: {
@@ -196,15 +220,15 @@ DEV void fm_collect_intv(const DevIndex& x, const MemOpt& opt, int len, const u8
 				if (round == 1) { xx = ret; st = SM_NEXT_R1; } else { ++k2; st = SM_NEXT_R2; }
 				break; }
 			case SM_NEXT_R3:
-				while (xx < len && q[xx] > 3) ++xx;
+				while (xx < len && Q(xx) > 3) ++xx;
 				if (xx >= len) { st = SM_DONE; break; }
 				start = xx;
-				fm_set_intv(x, q[start], ik); i = start + 1;
+				fm_set_intv(x, Q(start), ik); i = start + 1;
 				st = SM_S3;
 				break;
 			case SM_S3: // bwt_seed_strategy1: shortest forward match of >= min_seed_len+1 bases with < max_mem_intv occurrences
 				if (i >= len) { xx = len; st = SM_NEXT_R3; break; }
-				if (q[i] > 3) { xx = i + 1; st = SM_NEXT_R3; break; }
+				if (Q(i) > 3) { xx = i + 1; st = SM_NEXT_R3; break; }
 				ext = ik; pend = SMX_S3;
 				break;
 			default: st = SM_DONE; break;
@@ -215,35 +239,21 @@ DEV void fm_collect_intv(const DevIndex& x, const MemOpt& opt, int len, const u8
 		fm_extend(x, ext, ok, pend == SMX_BWD ? 1 : 0);
 		// ---- consume
 		if (pend == SMX_FWD) {
-			const int cc = 3 - q[i];
+			const int cc = 3 - Q(i);
 			bool stop = false;
 			if (ok[cc].size != ik.size) {
-				SM_PUSH_CURR(ik, ik_end);
+				SM_PUSH(ik, ik_end);
 				if (ok[cc].size < min_intv) stop = true;
 			}
 			if (!stop) { ik = ok[cc]; ik_end = (u32)(i + 1); ++i; st = SM_FWD; }
-			else { // same epilogue as the other forward exits (no second push: the loop ended before i == len)
-				for (int a = 0; a < n_curr >> 1; ++a) { Intv t = curr[a]; curr[a] = curr[n_curr - 1 - a]; curr[n_curr - 1 - a] = t; }
-				ret = (int)curr[0].end;
-				{ Intv* t = curr; curr = prev; prev = t; n_prev = n_curr; }
-				first_out = o.n; have_out = false; last_beg = 0;
-				i = start - 1;
-				st = SM_BWD_ROW;
-			}
+			else SM_END_FORWARD(); // (no second push: the scan ended before i == len)
 		} else if (pend == SMX_BWD) {
-			if (ok[c].size < min_intv) {
-				if (n_curr == 0 && (!have_out || (u32)(i + 1) < last_beg)) {
-					Intv t = pcur; t.beg = (u32)(i + 1);
-					have_out = true; last_beg = t.beg;
-					out_push(o, t);
-				}
-			} else if (n_curr == 0 || ok[c].size != last_size) {
-				intv_set(curr[n_curr], ok[c], 0, pcur.end); ++n_curr; last_size = ok[c].size; // n_curr <= n_prev <= cap
-			}
+			if (ok[c].size < min_intv) SM_EMIT_PCUR();
+			else if (n_curr == 0 || ok[c].size != last_size) { cand_set(wk, n_curr, ok[c], pcur_end); ++n_curr; last_size = ok[c].size; } // n_curr <= j
 			++j;
 			st = SM_BWD_ITEM;
 		} else { // SMX_S3
-			const int cc = 3 - q[i];
+			const int cc = 3 - Q(i);
 			if (ok[cc].size < opt.max_mem_intv && i - start >= min_seed_len) {
 				if (ok[cc].size > 0) { Intv m; intv_set(m, ok[cc], (u32)start, (u32)(i + 1)); out_push(o, m); }
 				xx = i + 1; st = SM_NEXT_R3;
@@ -251,7 +261,10 @@ DEV void fm_collect_intv(const DevIndex& x, const MemOpt& opt, int len, const u8
 		}
 		pend = SMX_NONE;
 	}
-#undef SM_PUSH_CURR
+#undef SM_PUSH
+#undef SM_END_FORWARD
+#undef SM_EMIT_PCUR
+#undef Q
 	// ordered by (beg, end).  Equal keys are identical intervals, so the sort algorithm is unobservable here (unlike
 	// the hazard-H4 sorts) and a plain insertion sort is used.
 	for (int a = 1; a < o.n; ++a) {

@@ -22,7 +22,8 @@ struct BatchParams {
 	u64 blob_len;
 	// seeding
 	Intv* intv; int intv_cap; u32* n_intv; u32* n_seed; // per read
-	Intv* smem_scratch; int smem_cap;                  // per thread: 2*smem_cap entries
+	Intv* smem_scratch; int smem_cap;                  // per thread: smem_cap spill entries of the candidate list
+	int seed_shared;                                    // candidate list + read codes in shared memory (fm.cuh SeedWork)
 	u64* seed_off;          // n_reads+1 (exclusive scan of n_seed)
 	u64 n_seed_total;
 	i64* sd_rbeg;           // [T]
@@ -59,6 +60,11 @@ DEV u8 nt4_of(u8 c)
 DEV void body_encode(const BatchParams& P, i64 i) { P.seq[i] = nt4_of(P.blob[i]); }
 
 // ---- seed: one thread per read -------------------------------------------------------------------
+#define SEED_LCAP 16   // candidates per thread kept in shared memory (16 bytes each); the rest spill to the global pool
+HOSTDEV size_t seed_block_smem_bytes(int block_threads, int max_len) { return (size_t)block_threads * (SEED_LCAP * 16 + (size_t)((max_len + 1 + 3) & ~3)); }
+#ifdef B200_SIM
+static uint4 g_sim_seed_l[SEED_LCAP];
+#endif
 DEV void body_seed(const BatchParams& P, i64 r, i64 tid)
 {
 	const u8* seq = P.seq + P.seq_off[r];
@@ -68,8 +74,19 @@ DEV void body_seed(const BatchParams& P, i64 r, i64 tid)
 	if (len >= P.opt.min_seed_len) {
 		if (len > P.smem_cap) { atomic_or_u32(P.err, ERR_QLEN_OVERFLOW); }
 		else {
-			SmemScratch sc; sc.a = P.smem_scratch + (size_t)tid * 2 * P.smem_cap; sc.b = sc.a + P.smem_cap; sc.cap = P.smem_cap;
-			fm_collect_intv(P.x, P.opt, len, seq, sc, o);
+			SeedWork wk;
+			wk.G = P.smem_scratch + (size_t)tid * P.smem_cap; wk.gcap = P.smem_cap;
+			wk.L = nullptr; wk.lstride = 0; wk.lcap = 0; wk.qs = nullptr; wk.qstride = 0;
+			if (P.seed_shared) { // packed shared-memory working set (reads of <= 255 bases, |T| < 2^40)
+#ifdef B200_SIM
+				wk.L = g_sim_seed_l; wk.lstride = 1; wk.lcap = SEED_LCAP;
+#else
+				extern __shared__ __align__(16) u8 tsm_[];
+				wk.L = (uint4*)tsm_ + threadIdx.x; wk.lstride = (int)blockDim.x; wk.lcap = SEED_LCAP;
+				wk.qs = tsm_ + (size_t)blockDim.x * SEED_LCAP * 16 + threadIdx.x; wk.qstride = (int)blockDim.x;
+#endif
+			}
+			fm_collect_intv(P.x, P.opt, len, seq, wk, o);
 			if (o.overflow) atomic_or_u32(P.err, ERR_INTV_OVERFLOW);
 			for (int i = 0; i < o.n; ++i) ns += (u32)(o.v[i].size < (u64)P.opt.max_occ ? o.v[i].size : (u64)P.opt.max_occ);
 		}

@@ -29,6 +29,7 @@ static uint64_t rt_scan_u32(const uint32_t* in, uint64_t* out, uint64_t n) { uin
 #define RT_THREADS(body, P, n) do { for (int64_t i_ = 0; i_ < (int64_t)(n); ++i_) body(P, i_); } while (0)
 #define RT_THREADS_TID(body, P, n) do { for (int64_t i_ = 0; i_ < (int64_t)(n); ++i_) body(P, i_, 0); } while (0)
 #define RT_THREADS_TID_RING(body, P, n) RT_THREADS_TID(body, P, n)
+#define RT_THREADS_SEED(body, P, n, max_len) RT_THREADS_TID(body, P, n)
 #define RT_WARPS(wbody, P, n) do { \
 	std::vector<uint8_t> sm_(warp_smem_bytes((P).wm_cap) + 64); \
 	WarpMem wm_; WarpScratch ws_; make_warp_ctx(P, 0, sm_.data(), wm_, ws_); \
