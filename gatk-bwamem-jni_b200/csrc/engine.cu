@@ -94,6 +94,10 @@ static void rt_sort_u64(const uint64_t* in, uint64_t* out, uint64_t n)
 	__global__ void __launch_bounds__(THREADS_PER_BLOCK) k_##body(const __grid_constant__ BatchParams P, i64 n) { \
 		const i64 tid = (i64)blockIdx.x * blockDim.x + threadIdx.x; \
 		for (i64 i = tid; i < n; i += (i64)gridDim.x * blockDim.x) body(P, i, tid); }
+// persistent thread kernel: every thread takes work items from a batch-wide counter inside the body
+#define DEF_THREAD_QUEUE_KERNEL(body) \
+	__global__ void __launch_bounds__(THREADS_PER_BLOCK) k_##body(const __grid_constant__ BatchParams P, i64 n, u32* counter) { \
+		body(P, n, counter, (i64)blockIdx.x * blockDim.x + threadIdx.x); }
 #define DEF_WARP_KERNEL(wbody) \
 	__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_##wbody(const __grid_constant__ BatchParams P, i64 n, u32* counter) { \
 		extern __shared__ __align__(16) u8 smem_[]; \
@@ -139,12 +143,15 @@ DEF_THREAD_KERNEL(body_out_size)
 DEF_THREAD_KERNEL(body_out_write)
 DEF_THREAD_KERNEL(body_rescue_snap)
 DEF_THREAD_KERNEL(body_rescue_gen)
+DEF_THREAD_KERNEL(body_rescue_gen_all)
+DEF_THREAD_KERNEL(body_rescue_apply_all)
+DEF_THREAD_KERNEL(body_rescue_fb_restore)
 DEF_THREAD_KERNEL(body_rescue_apply)
 DEF_THREAD_KERNEL(body_rescue_gen_multi)
 DEF_THREAD_KERNEL(body_rescue_apply_multi)
 DEF_WARP_KERNEL_DEVN(wbody_rescue_sw)
 DEF_WARP_KERNEL(wbody_extend)
-DEF_THREAD_TID_KERNEL(body_extend_t)
+DEF_THREAD_QUEUE_KERNEL(body_extend_q)
 DEF_WARP_KERNEL_DEVN(wbody_extend_heavy)
 DEF_THREAD_KERNEL(body_save_regs)
 DEF_THREAD_TID_KERNEL(body_final_pe_t)
@@ -207,6 +214,13 @@ static int g_launches = 0;
 	size_t tsm_ = thread_block_smem_bytes(THREADS_PER_BLOCK, (P).wm_cap); \
 	cudaFuncSetAttribute(k_##body, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm_); \
 	k_##body<<<(unsigned)nb_, THREADS_PER_BLOCK, tsm_, rt_stream()>>>(P, n_); ++g_launches; } g_timer.mark(#body); } while (0)
+// persistent queue kernels with an explicit dynamic shared-memory size (as many blocks per SM as that size allows)
+#define RT_THREADS_QUEUE_SMEM(body, P, n, bytes) do { i64 n_ = (i64)(n); if (n_ > 0) { \
+	size_t tsm_ = (bytes); \
+	i64 nb_ = (n_ + THREADS_PER_BLOCK - 1) / THREADS_PER_BLOCK; i64 per_sm_ = (i64)((227 * 1024) / (tsm_ + 1024)); if (per_sm_ < 1) per_sm_ = 1; if (per_sm_ > SEED_BLOCKS_PER_SM) per_sm_ = SEED_BLOCKS_PER_SM; \
+	i64 cap_ = (i64)rt_sm_count() * per_sm_; if (nb_ > cap_) nb_ = cap_; \
+	cudaFuncSetAttribute(k_##body, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm_); \
+	k_##body<<<(unsigned)nb_, THREADS_PER_BLOCK, tsm_, rt_stream()>>>(P, n_, next_counter()); ++g_launches; } g_timer.mark(#body); } while (0)
 #define RT_WARPS(wbody, P, n) do { i64 n_ = (i64)(n); if (n_ > 0) { \
 	size_t sm_ = ((warp_smem_bytes((P).wm_cap) + 15) & ~(size_t)15) * WARPS_PER_BLOCK; \
 	i64 nb_ = (n_ + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK; i64 cap_ = (i64)rt_sm_count() * WARP_BLOCKS_PER_SM; if (nb_ > cap_) nb_ = cap_; \

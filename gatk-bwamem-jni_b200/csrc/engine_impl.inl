@@ -9,6 +9,7 @@
 // /root/reference/src/main/c/jnibwa.h:11-16 (definitions at jnibwa.c:154-235).
 
 #include <cmath>
+#include <ctime>
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
@@ -54,6 +55,17 @@ bool ImageView::parse(const uint8_t* m, size_t l)
 	pac = m + k; k += (size_t)(l_pac / 4 + 1);
 	return k == l; // the reference asserts that the walk ends exactly at the file size
 }
+
+// development aid (B200_HOSTPROF=1): wall-clock marks of the host side of one call, printed to stderr
+struct HostProf {
+	bool on = getenv("B200_HOSTPROF") != nullptr;
+	std::vector<std::pair<const char*, double>> marks; double t0 = 0;
+	static double now() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+	void begin() { if (on) { marks.clear(); t0 = now(); } }
+	void mark(const char* nm) { if (on) marks.push_back({ nm, now() }); }
+	void report() { if (!on) return; double p = t0; fprintf(stderr, "[hostprof]"); for (auto& m : marks) { fprintf(stderr, " %s=%.2f", m.first, m.second - p); p = m.second; } fprintf(stderr, " total=%.2f ms\n", p - t0); }
+};
+static HostProf g_hp;
 
 struct DBuf { // growable device buffer
 	void* p = nullptr; size_t cap = 0;
@@ -114,7 +126,7 @@ struct Engine {
 	// batch workspace
 	DBuf b_blob, b_seq, b_seqoff, b_intv, b_nintv, b_nseed, b_smem, b_seedoff, b_rbeg, b_S, b_C, b_ord, b_tmp32, b_ck, b_ks, b_srt, b_regtmp,
 	     b_nck, b_nks, b_nreg, b_regcap, b_regoff, b_regs, b_snap, b_ztmp, b_pairv, b_recs, b_nrec, b_cand, b_pairtab, b_var, b_misc,
-	     b_outwords, b_outoff, b_out, b_wsz, b_wscig, b_wsmd, b_wsxa, b_wsbrow, b_nb, b_swtask, b_swstate, b_swlist, b_tbuf, b_redo, b_heavy, b_multi, b_cand2;
+	     b_outwords, b_outoff, b_out, b_wsz, b_wscig, b_wsmd, b_wsxa, b_wsbrow, b_nb, b_swtask, b_swstate, b_swlist, b_tbuf, b_redo, b_heavy, b_multi, b_cand2, b_specstate, b_spectask, b_nreg0;
 	Counters last_counters; uint64_t last_n_seed = 0; int n_launches = 0;
 	std::string last_error;
 
@@ -175,7 +187,7 @@ inline void Engine::close_all()
 	DBuf* all[] = { &d_bwt, &d_sa, &d_pac, &d_ctg, &d_log, &d_names, &d_name_off, &b_blob, &b_seq, &b_seqoff, &b_intv, &b_nintv, &b_nseed, &b_smem,
 	                &b_seedoff, &b_rbeg, &b_S, &b_C, &b_ord, &b_tmp32, &b_ck, &b_ks, &b_srt, &b_regtmp, &b_nck, &b_nks, &b_nreg, &b_regcap, &b_regoff,
 	                &b_regs, &b_snap, &b_ztmp, &b_pairv, &b_recs, &b_nrec, &b_cand, &b_pairtab, &b_var, &b_misc, &b_outwords, &b_outoff, &b_out,
-	                &b_wsz, &b_wscig, &b_wsmd, &b_wsxa, &b_wsbrow, &b_nb, &b_swtask, &b_swstate, &b_swlist, &b_tbuf, &b_redo, &b_heavy, &b_multi, &b_cand2 };
+	                &b_wsz, &b_wscig, &b_wsmd, &b_wsxa, &b_wsbrow, &b_nb, &b_swtask, &b_swstate, &b_swlist, &b_tbuf, &b_redo, &b_heavy, &b_multi, &b_cand2, &b_specstate, &b_spectask, &b_nreg0 };
 	for (DBuf* b : all) b->release();
 	if (map) munmap(map, map_len);
 	map = nullptr;
@@ -216,8 +228,13 @@ inline void* Engine::align(const MemOpt* opt_in, const PeStat* pes0, char* blob_
 	std::lock_guard<std::mutex> lock(mu);
 	last_error.clear();
 	*out_size = 0;
+	g_hp.begin();
 	if (!stage(blob_in)) return nullptr;
-	return run(opt_in, pes0, out_size, true);
+	g_hp.mark("stage");
+	void* r = run(opt_in, pes0, out_size, true);
+	g_hp.mark("d2h_out");
+	g_hp.report();
+	return r;
 }
 
 // Run the device pipeline on the staged request.  host_output: copy the record stream into a malloc'd buffer (the
@@ -277,7 +294,9 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 	// ---- stage 1: encode + seed
 	RT_THREADS(body_encode, P, (int64_t)blob_len);
 	RT_THREADS_SEED(body_seed, P, (int64_t)n_reads, max_len);
+	g_hp.mark("launch1");
 	uint64_t T = rt_scan_u32(P.n_seed, P.seed_off, n_reads);
+	g_hp.mark("seed_sync");
 	P.n_seed_total = T; last_n_seed = T;
 	{
 		size_t Tn = (size_t)T + 1;
@@ -315,11 +334,25 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 		if (getenv("B200_TEST_ALL_HEAVY")) P.light_max_seeds = -1;
 		if (getenv("B200_TEST_ALL_LIGHT")) { P.light_max_seeds = 1 << 30; P.light_max_chains = 1 << 30; }
 	}
-	// ---- stage 3: extension + de-duplication (thread per light read, warp per heavy read)
-	if (getenv("B200_THREAD_EXTEND")) { // experimental: thread per light read (global-memory DP rows are slow; kept for tests)
-		RT_THREADS_TID_RING(body_extend_t, P, (int64_t)n_reads);
-		RT_WARPS_DEVN(wbody_extend_heavy, P, P.n_heavy, (int64_t)n_reads);
-	} else RT_WARPS(wbody_extend, P, (int64_t)n_reads);
+	// ---- stage 3: extension + de-duplication (thread per light read with shared-memory DP rows, warp per heavy read)
+	if (getenv("B200_WARP_EXTEND")) RT_WARPS(wbody_extend, P, (int64_t)n_reads); // the all-warp formulation, kept for comparison
+	else {
+		int rw = max_len - opt.min_seed_len + 2;
+		if (rw < 2 * THREAD_RING_N) rw = 2 * THREAD_RING_N;
+		const size_t budget = 200 * 1024; // per block of THREADS_PER_BLOCK threads
+		const size_t qb = (size_t)((wm_cap + 2 + 3) & ~3);
+		if ((size_t)THREADS_PER_BLOCK * ((size_t)rw * 4 + qb) > budget) { // long reads: shorter rows, long extensions go to the warp kernel
+			size_t fit = budget / THREADS_PER_BLOCK > qb ? (budget / THREADS_PER_BLOCK - qb) / 4 : 0;
+			rw = fit >= 2 * THREAD_RING_N ? (int)fit : 0;
+		}
+		for (int t = 0; t < 5; ++t) { P.rowpack[t] = 0; for (int c2 = 0; c2 < 5; ++c2) P.rowpack[t] |= (u64)(u8)opt.mat[t * 5 + c2] << (8 * c2); }
+		if (rw == 0) RT_WARPS(wbody_extend, P, (int64_t)n_reads);
+		else {
+			P.t_ext_rw = rw;
+			RT_THREADS_QUEUE_SMEM(body_extend_q, P, (int64_t)n_reads, thread_ext_smem_bytes(THREADS_PER_BLOCK, rw, wm_cap));
+			RT_WARPS_DEVN(wbody_extend_heavy, P, P.n_heavy, (int64_t)n_reads);
+		}
+	}
 	// ---- paired-end: insert-size statistics (the one batch-global step; host)
 	for (int d = 0; d < 4; ++d) { memset(&P.pes[d], 0, sizeof(PeStat)); P.pes[d].failed = 1; }
 	if (pe) {
@@ -333,7 +366,9 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 			rt_sort_u64((const uint64_t*)P.pe_cand, b_cand2.as<uint64_t>(), (uint64_t)n_units);
 			std::vector<int64_t> cand((size_t)n_units);
 			rt_d2h(cand.data(), b_cand2.p, (size_t)n_units * 8);
+			g_hp.mark("extend_sync");
 			host_mem_pestat(opt, cand.data(), n_units, P.pes, true);
+			g_hp.mark("pestat");
 		}
 		std::vector<double> tab; int64_t off[4];
 		if (!host_pair_table(opt, P.pes, tab, off)) { last_error = "insert-size range too wide to tabulate"; return nullptr; }
@@ -349,6 +384,7 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 	// ---- region capacity, offsets, compaction
 	RT_THREADS(body_reg_cap, P, (int64_t)n_reads);
 	uint64_t R = rt_scan_u32(P.reg_cap, P.reg_off, n_reads);
+	g_hp.mark("regcap_sync");
 	{
 		size_t Rn = (size_t)R + 2;
 		ok = b_regs.ensure(Rn * sizeof(Reg)) && b_snap.ensure(Rn * sizeof(Reg)) && b_ztmp.ensure(Rn * 4) && b_pairv.ensure(Rn * sizeof(Pair64)) && b_recs.ensure(Rn * sizeof(AlnRec));
@@ -358,26 +394,36 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 	}
 	P.regs = b_regs.as<Reg>(); P.snap = b_snap.as<Reg>(); P.ztmp = b_ztmp.as<u32>(); P.pairv = b_pairv.as<Pair64>(); P.recs = b_recs.as<AlnRec>(); P.var = b_var.as<u32>();
 	RT_THREADS(body_compact, P, (int64_t)n_reads);
-	// ---- mate rescue as a task pipeline (rescue.cuh): snapshot, then rounds of gen -> sw -> apply
+	// ---- mate rescue as a task pipeline (rescue.cuh): snapshot, ONE speculative gen -> sw -> replay over all rescuing
+	// hits; reads whose replay needs an alignment that was not speculated take the round-by-round kernels (rare)
 	if (pe && !(opt.flag & MEM_F_NO_RESCUE)) {
-		size_t nr = (size_t)n_reads + 2;
-		ok = b_nb.ensure(nr * 4) && b_swtask.ensure(nr * 4 * sizeof(SwTask)) && b_swstate.ensure(nr * 4) && b_swlist.ensure(nr * 4 * 4);
+		size_t nr = (size_t)n_reads + 2, Rn = (size_t)R + 2;
+		ok = b_nb.ensure(nr * 4) && b_swtask.ensure((Rn > nr * 4 ? Rn : nr * 4) * sizeof(SwTask)) && b_swstate.ensure(nr * 4) && b_swlist.ensure(nr * 4 * 4)
+		     && b_multi.ensure(nr * 4) && b_specstate.ensure(Rn * 4) && b_spectask.ensure(Rn * 4 * 4) && b_nreg0.ensure(nr * 4);
 		if (!ok) { last_error = "device allocation failed (rescue pools)"; return nullptr; }
 		P.nb = b_nb.as<u32>(); P.sw_tasks = b_swtask.as<SwTask>(); P.sw_state = b_swstate.as<u8>(); P.sw_list = b_swlist.as<u32>();
 		P.sw_n_list = b_misc.as<u32>() + 3; P.max_nb = b_misc.as<u32>() + 4; P.n_multi = b_misc.as<u32>() + 7;
-		if (!b_multi.ensure(nr * 4)) { last_error = "device allocation failed (rescue pools)"; return nullptr; }
-		P.multi = b_multi.as<u32>();
+		P.multi = b_multi.as<u32>(); P.spec_state = b_specstate.as<u8>(); P.spec_task = b_spectask.as<u32>(); P.n_reg0 = b_nreg0.as<u32>();
+		P.force_fb = getenv("B200_TEST_RESCUE_FALLBACK") ? 1 : 0; // tests: every rescuing read takes the round-by-round path
 		RT_THREADS(body_rescue_snap, P, (int64_t)n_reads);
+		// the task pool holds at most sum(nb * live orientations) <= R entries (that head-room is part of reg_cap)
+		RT_THREADS(body_rescue_gen_all, P, (int64_t)n_reads);
+		RT_WARPS_DEVN(wbody_rescue_sw, P, P.sw_n_list, (int64_t)R);
+		RT_THREADS(body_rescue_apply_all, P, (int64_t)n_reads);
 		uint32_t hdr[8];
 		rt_d2h(hdr, b_misc.as<u32>(), sizeof(hdr));
-		const uint32_t max_nb = hdr[4], n_multi = hdr[7];
-		int rounds = (int)max_nb < opt.max_matesw ? (int)max_nb : opt.max_matesw;
-		for (int k = 0; k < rounds; ++k) {
-			P.round = k;
-			rt_memset(P.sw_n_list, 0, 4);
-			if (k == 0) RT_THREADS(body_rescue_gen, P, (int64_t)n_reads); else RT_THREADS(body_rescue_gen_multi, P, (int64_t)n_multi);
-			RT_WARPS_DEVN(wbody_rescue_sw, P, P.sw_n_list, (int64_t)n_reads * 4);
-			if (k == 0) RT_THREADS(body_rescue_apply, P, (int64_t)n_reads); else RT_THREADS(body_rescue_apply_multi, P, (int64_t)n_multi);
+		const uint32_t max_nb = hdr[4], n_fb = hdr[7];
+		g_hp.mark("rescue_sync");
+		if (n_fb) {
+			RT_THREADS(body_rescue_fb_restore, P, (int64_t)n_fb);
+			int rounds = (int)max_nb < opt.max_matesw ? (int)max_nb : opt.max_matesw;
+			for (int k = 0; k < rounds; ++k) {
+				P.round = k;
+				rt_memset(P.sw_n_list, 0, 4);
+				RT_THREADS(body_rescue_gen_multi, P, (int64_t)n_fb);
+				RT_WARPS_DEVN(wbody_rescue_sw, P, P.sw_n_list, (int64_t)n_reads * 4);
+				RT_THREADS(body_rescue_apply_multi, P, (int64_t)n_fb);
+			}
 		}
 		P.rescued = 1;
 	}
@@ -390,6 +436,7 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 	// ---- output stream
 	RT_THREADS(body_out_size, P, (int64_t)n_reads);
 	uint64_t W = rt_scan_u32(P.out_words, P.out_off, n_reads);
+	g_hp.mark("final_sync");
 	if (!b_out.ensure((size_t)W * 4 + 16)) { last_error = "device allocation failed (output)"; return nullptr; }
 	P.out = b_out.as<u32>();
 	RT_THREADS(body_out_write, P, (int64_t)n_reads);
@@ -402,6 +449,7 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 		return nullptr;
 	}
 	if (!host_output) { *out_size = (size_t)W * 4; rt_sync(); return (void*)b_out.p; }
+	g_hp.mark("write_sync");
 	void* res = malloc((size_t)W * 4 + 4);
 	if (!res) { last_error = "host allocation failed"; return nullptr; }
 	rt_d2h(res, P.out, (size_t)W * 4);

@@ -1,0 +1,289 @@
+// extend_thread.cuh -- seed extension of one read by ONE thread (mem_chain2aln + ksw_extend2 of un-vendored lh3/bwa,
+// SURVEY.md App. B.6 / B.7, behind /root/reference/src/main/c/jnibwa.c:214).
+//
+// Most reads have a handful of kept seeds and two short extensions (~5-7 k DP cells), far too little to keep the 32
+// lanes of a warp busy row by row.  Here every lane owns a read and the warp runs 32 independent scalar DPs:
+//   * the DP row lives in shared memory, one u32 per query column (H in the low half-word, E in the high one; both are
+//     non-negative in ksw_extend2), interleaved over the threads of the block so that column j of every thread sits in
+//     bank tid % 32 -- one conflict-free LDS + STS per cell;
+//   * the read's base codes live in shared memory too (same interleaving); the left extension walks them backwards, the
+//     right extension forwards, so no reversed copy is made;
+//   * the per-read control flow (chains, seeds by score, containment test, left / right extension, band retry) is a
+//     state machine around ONE DP-row site: each trip of the outer loop advances the machine (lane-divergent, cheap)
+//     to the next row that has to be computed, then all lanes compute one row together.  Lanes therefore stay in step
+//     at row granularity no matter how their extensions differ in length;
+//   * reads are not assigned statically: a lane that finishes its read takes the next one from a batch-wide counter
+//     (fetching is one more state of the machine), so no lane idles while a neighbour works through a long read; a
+//     warp vote at the top of every trip is both the exit test and the reconvergence point.
+// Exactness: the row code is the scalar recurrence of ksw_extend2 verbatim (band clamp, [beg,end) shrink, z-drop,
+// tie rules); the only representational change is 16-bit storage, guarded by a bound on the largest reachable score
+// (reads that could exceed it, or do not fit the shared rows, are handed to the warp-per-read kernel).
+#pragma once
+#include "extend.cuh"
+
+struct ThreadExtMem {
+	u32* row; int row_stride; int row_cap;   // DP row: element j at row[j * row_stride], j in [0, row_cap)
+	u8* rd; int rd_stride; int rd_cap;       // read codes: element j at rd[j * rd_stride]
+	const u64* rowpack;                      // [5]: byte c of rowpack[t] = mat[t*5 + c]
+};
+
+enum { TX_FETCH, TX_NEXT_CHAIN, TX_NEXT_SEED, TX_EXT_START, TX_EXT_DONE, TX_RIGHT_CHECK, TX_FINISH_SEED, TX_READ_DONE };
+
+#ifndef B200_SIM
+DEV bool tx_all_done(bool done) { return __all_sync(FULLMASK, done) != 0; }
+#else
+DEV bool tx_all_done(bool done) { return done; }
+#endif
+
+// Extends reads taken from `counter` until the batch is exhausted.  Every lane of the warp must call this (the loop
+// votes with the full mask).  Reads with many kept seeds, and reads that do not fit the thread-level rows, are queued
+// on the heavy list for the warp-per-read kernel.
+DEV void thread_extend_queue(const BatchParams& P, i64 n_reads, u32* counter, const ThreadExtMem& tm, WarpMem& wm, WarpScratch& ws, u32* lerr)
+{
+	const DevIndex& x = P.x; const MemOpt& opt = P.opt; Counters* cnt = P.cnt; u32* err = P.err;
+	const i64 l_pac = x.l_pac;
+	const int o_del = opt.o_del, e_del = opt.e_del, o_ins = opt.o_ins, e_ins = opt.e_ins;
+	const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
+	int mx = 0;
+	for (int k = 0; k < 25; ++k) mx = mx > opt.mat[k] ? mx : (int)opt.mat[k];
+	const size_t RS = (size_t)tm.row_stride, QS = (size_t)tm.rd_stride;
+	// per-read state
+	i64 r = -1; int l_query = 0, nck = 0, av_cap = 0;
+	const u8* query = nullptr; const ChainK* cks = nullptr; const Seed* ks_base = nullptr; u64* srt = nullptr; Reg* av = nullptr;
+
+	int phase = TX_FETCH, n_av = 0;
+	bool in_ext = false, done = false;
+#define TX_TO_WARP() do { u32 slot_ = atomic_add_u32(P.n_heavy, 1u); P.heavy_list[slot_] = (u32)r; phase = TX_FETCH; } while (0)
+	int c = -1, k = -1, cn = 0;
+	const Seed* seeds = nullptr; ChainK ck; ck.n_seeds = 0; ck.seed_start = 0; ck.rid = 0; ck.frac_rep = 0.f;
+	i64 rmax0 = 0, rmax1 = 0;
+	Seed s; s.rbeg = 0; s.qbeg = s.len = s.score = s.next = 0;
+	Reg a; memset(&a, 0, sizeof(Reg));
+	int aw0 = 0, aw1 = 0, side = 0, tr = 0, prev = 0, sc0 = 0;
+	// extension in flight
+	int qlen = 0, tlen = 0, w = 0, end_bonus = 0, h0 = 0, qbase = 0, qdir = 1;
+	i64 tbase = 0; int tdir = 1;
+	int i = 0, beg = 0, end = 0, max = 0, max_i = -1, max_j = -1, max_ie = -1, gscore = -1, max_off = 0;
+	u64 cells = 0, n_ext = 0;
+	u32 pac_word = 0; i64 pac_widx = -1;
+
+	for (;;) {
+		// ---- advance to the next DP row (or to the end of the read)
+		while (!in_ext && !done) {
+			switch (phase) {
+			case TX_FETCH: {
+				r = (i64)atomic_add_u32(counter, 1u);
+				if (r >= n_reads) { done = true; break; }
+				nck = (int)P.n_ck[r];
+				const int nks = (int)P.n_ks[r];
+				if (nck == 0) { P.n_reg[r] = 0; break; }
+				if (nks > P.light_max_seeds || nck > P.light_max_chains) { TX_TO_WARP(); break; }
+				const u64 t0 = P.seed_off[r];
+				l_query = (int)(P.seq_off[r + 1] - P.seq_off[r] - 1);
+				query = P.seq + P.seq_off[r];
+				// 16-bit storage bound: no H/E value exceeds (seed + left + right) scores <= 2 * l_query * mx, plus the clip bonus
+				if (l_query > tm.rd_cap || (i64)2 * l_query * mx + opt.pen_clip5 + opt.pen_clip3 > 60000) { TX_TO_WARP(); break; }
+				cks = P.ck + t0; ks_base = P.ks + t0; srt = P.srt + t0; av = P.regs_tmp + t0; av_cap = nks;
+				for (int j = 0; j < l_query; ++j) tm.rd[(size_t)j * QS] = query[j];
+				c = -1; n_av = 0; *lerr = 0;
+				phase = TX_NEXT_CHAIN;
+				break; }
+			case TX_READ_DONE: { // region de-duplication / patching of the read, then the next read
+				int n2 = warp_sort_dedup_patch<1>(x, opt, wm, ws, cnt, query, n_av, av);
+				if (*lerr & ERR_NEED_WARP) { TX_TO_WARP(); break; } // recomputed from scratch by a warp
+				if (*lerr) atomic_or_u32(err, *lerr);
+				P.n_reg[r] = (u32)n2;
+				phase = TX_FETCH;
+				break; }
+			case TX_NEXT_CHAIN: {
+				++c;
+				if (c >= nck) { phase = TX_READ_DONE; break; }
+				ck = cks[c];
+				cn = (int)ck.n_seeds;
+				if (cn == 0) break;
+				seeds = ks_base + ck.seed_start;
+				rmax0 = l_pac << 1; rmax1 = 0;
+				for (int t = 0; t < cn; ++t) {
+					const Seed& sd = seeds[t];
+					i64 b = sd.rbeg - (sd.qbeg + cal_max_gap(opt, sd.qbeg));
+					i64 e = sd.rbeg + sd.len + ((l_query - sd.qbeg - sd.len) + cal_max_gap(opt, l_query - sd.qbeg - sd.len));
+					rmax0 = rmax0 < b ? rmax0 : b;
+					rmax1 = rmax1 > e ? rmax1 : e;
+				}
+				rmax0 = rmax0 > 0 ? rmax0 : 0;
+				rmax1 = rmax1 < l_pac << 1 ? rmax1 : l_pac << 1;
+				if (rmax0 < l_pac && l_pac < rmax1) { if (seeds[0].rbeg < l_pac) rmax1 = l_pac; else rmax0 = l_pac; }
+				ref_clip_window(x, rmax0, seeds[0].rbeg, rmax1);
+				for (int t = 0; t < cn; ++t) srt[t] = (u64)(u32)seeds[t].score << 32 | (u32)t;
+				ks_introsort<u64, U64Lt>((size_t)cn, srt, U64Lt());
+				k = cn;
+				phase = TX_NEXT_SEED;
+				break; }
+			case TX_NEXT_SEED: {
+				--k;
+				if (k < 0) { phase = TX_NEXT_CHAIN; break; }
+				s = seeds[(u32)srt[k]];
+				int t;
+				for (t = 0; t < n_av; ++t) { // inside an earlier region and close to its diagonal?
+					const Reg& p = av[t];
+					if (s.rbeg < p.rb || s.rbeg + s.len > p.re || s.qbeg < p.qb || s.qbeg + s.len > p.qe) continue;
+					if ((double)(s.len - p.seedlen0) > .1 * (double)l_query) continue;
+					int qd = s.qbeg - p.qb; i64 rd = s.rbeg - p.rb;
+					int max_gap = cal_max_gap(opt, qd < rd ? qd : (int)rd);
+					int ww = max_gap < p.w ? max_gap : p.w;
+					if (qd - rd < ww && rd - qd < ww) break;
+					qd = p.qe - (s.qbeg + s.len); rd = p.re - (s.rbeg + s.len);
+					max_gap = cal_max_gap(opt, qd < rd ? qd : (int)rd);
+					ww = max_gap < p.w ? max_gap : p.w;
+					if (qd - rd < ww && rd - qd < ww) break;
+				}
+				if (t < n_av) { // contained: extend anyway only if an overlapping seed lies on another diagonal
+					for (t = k + 1; t < cn; ++t) {
+						if (srt[t] == 0) continue;
+						const Seed& u = seeds[(u32)srt[t]];
+						if ((double)u.len < (double)s.len * .95) continue;
+						if (s.qbeg <= u.qbeg && s.qbeg + s.len - u.qbeg >= s.len >> 2 && u.qbeg - s.qbeg != u.rbeg - s.rbeg) break;
+						if (u.qbeg <= s.qbeg && u.qbeg + u.len - s.qbeg >= s.len >> 2 && s.qbeg - u.qbeg != s.rbeg - u.rbeg) break;
+					}
+					if (t == cn) { srt[k] = 0; break; }
+				}
+				if (n_av >= av_cap) { atomic_or_u32(err, ERR_REG_OVERFLOW); P.n_reg[r] = 0; phase = TX_FETCH; break; }
+				memset(&a, 0, sizeof(Reg));
+				aw0 = aw1 = opt.w;
+				a.w = opt.w; a.score = a.truesc = -1; a.rid = ck.rid;
+				if (s.qbeg) { // left extension: both sequences walked backwards
+					side = 0; tr = 0;
+					qlen = s.qbeg; qbase = s.qbeg - 1; qdir = -1;
+					tbase = s.rbeg - 1; tdir = -1; tlen = (int)(s.rbeg - rmax0);
+					end_bonus = opt.pen_clip5; h0 = s.len * opt.a;
+					phase = TX_EXT_START;
+				} else { a.score = a.truesc = s.len * opt.a; a.qb = 0; a.rb = s.rbeg; phase = TX_RIGHT_CHECK; }
+				break; }
+			case TX_RIGHT_CHECK:
+				if (s.qbeg + s.len != l_query) {
+					side = 1; tr = 0; sc0 = a.score;
+					const int qe = s.qbeg + s.len;
+					qlen = l_query - qe; qbase = qe; qdir = 1;
+					tbase = s.rbeg + s.len; tdir = 1; tlen = (int)(rmax1 - tbase);
+					end_bonus = opt.pen_clip3; h0 = sc0;
+					phase = TX_EXT_START;
+				} else { a.qe = l_query; a.re = s.rbeg + s.len; phase = TX_FINISH_SEED; }
+				break;
+			case TX_EXT_START: { // one band try of ksw_extend2: first row of H/E, band clamp, running maxima
+				prev = a.score;
+				w = opt.w << tr;
+				if (side == 0) aw0 = w; else aw1 = w;
+				if (qlen + 1 > tm.row_cap) { TX_TO_WARP(); break; }
+				{
+					u32* rw = tm.row;
+					rw[0] = (u32)h0;
+					int v = h0 > oe_ins ? h0 - oe_ins : 0;
+					for (int j = 1; j <= qlen; ++j) { rw[(size_t)j * RS] = (u32)v; v = v > e_ins ? v - e_ins : 0; }
+				}
+				int max_ins = (int)((double)(qlen * mx + end_bonus - o_ins) / e_ins + 1.); max_ins = max_ins > 1 ? max_ins : 1;
+				w = w < max_ins ? w : max_ins;
+				int max_del = (int)((double)(qlen * mx + end_bonus - o_del) / e_del + 1.); max_del = max_del > 1 ? max_del : 1;
+				w = w < max_del ? w : max_del;
+				max = h0; max_i = -1; max_j = -1; max_ie = -1; gscore = -1; max_off = 0; beg = 0; end = qlen; i = 0;
+				++n_ext;
+				if (tlen > 0) in_ext = true; else phase = TX_EXT_DONE;
+				break; }
+			case TX_EXT_DONE: { // consume the result of the try
+				const int score = max, qle = max_j + 1, tle = max_i + 1, gtle = max_ie + 1;
+				const int wt = opt.w << tr;
+				a.score = score;
+				const bool more = !(a.score == prev || max_off < (wt >> 1) + (wt >> 2)) && tr == 0;
+				if (more) { tr = 1; phase = TX_EXT_START; break; }
+				if (side == 0) {
+					if (gscore <= 0 || gscore <= a.score - opt.pen_clip5) { a.qb = s.qbeg - qle; a.rb = s.rbeg - tle; a.truesc = a.score; }
+					else { a.qb = 0; a.rb = s.rbeg - gtle; a.truesc = gscore; }
+					phase = TX_RIGHT_CHECK;
+				} else {
+					const int qe = s.qbeg + s.len; const i64 re = s.rbeg + s.len;
+					if (gscore <= 0 || gscore <= a.score - opt.pen_clip3) { a.qe = qe + qle; a.re = re + tle; a.truesc += a.score - sc0; }
+					else { a.qe = l_query; a.re = re + gtle; a.truesc += gscore - sc0; }
+					phase = TX_FINISH_SEED;
+				}
+				break; }
+			case TX_FINISH_SEED: {
+				a.seedcov = 0;
+				for (int t = 0; t < cn; ++t) {
+					const Seed& u = seeds[t];
+					if (u.qbeg >= a.qb && u.qbeg + u.len <= a.qe && u.rbeg >= a.rb && u.rbeg + u.len <= a.re) a.seedcov += u.len;
+				}
+				a.w = aw0 > aw1 ? aw0 : aw1;
+				a.seedlen0 = s.len;
+				a.frac_rep = ck.frac_rep;
+				av[n_av++] = a;
+				phase = TX_NEXT_SEED;
+				break; }
+			default: done = true; break;
+			}
+		}
+		if (tx_all_done(done)) break; // full-mask vote: exit test and reconvergence point
+		// ---- one DP row (the scalar recurrence of ksw_extend2, verbatim)
+		if (in_ext) {
+			// target base of row i from the 2-bit packed reference (one 32-bit word holds 16 consecutive forward bases)
+			const i64 p = tbase + (i64)tdir * i;
+			const bool rv = p >= l_pac;
+			const i64 fp = rv ? (l_pac << 1) - 1 - p : p;
+			const i64 widx = fp >> 4;
+			if (widx != pac_widx) { pac_word = ldg((const u32*)x.pac + widx); pac_widx = widx; }
+			int tb = (int)((pac_word >> (8 * (int)((fp >> 2) & 3))) >> ((~fp & 3) << 1) & 3);
+			if (rv) tb = 3 - tb;
+			const u64 rp = tm.rowpack[tb];
+			if (beg < i - w) beg = i - w;
+			if (end > i + w + 1) end = i + w + 1;
+			if (end > qlen) end = qlen;
+			int h1, f = 0, m = 0, mj = -1;
+			if (beg == 0) { h1 = h0 - (o_del + e_del * (i + 1)); if (h1 < 0) h1 = 0; } else h1 = 0;
+			if (end > beg) cells += (u64)(end - beg);
+			{
+				u32* rw = tm.row + (size_t)beg * RS;
+				const u8* qp = tm.rd + (size_t)(qbase + qdir * beg) * QS;
+				const ptrdiff_t qstep = (ptrdiff_t)qdir * (ptrdiff_t)QS;
+				for (int j = beg; j < end; ++j) {
+					const u32 he = *rw;
+					int M = (int)(he & 0xffffu), e = (int)(he >> 16);
+					const int sc = (int)(i8)(rp >> (8 * (int)*qp));
+					M = M ? M + sc : 0;
+					int h = M > e ? M : e;
+					h = h > f ? h : f;
+					mj = m > h ? mj : j;
+					m = m > h ? m : h;
+					int t = M - oe_del; t = t > 0 ? t : 0;
+					e -= e_del; e = e > t ? e : t;
+					*rw = (u32)h1 | (u32)e << 16;
+					h1 = h;
+					t = M - oe_ins; t = t > 0 ? t : 0;
+					f -= e_ins; f = f > t ? f : t;
+					rw += RS; qp += qstep;
+				}
+				tm.row[(size_t)end * RS] = (u32)h1; // H[end] = h1, E[end] = 0
+			}
+			bool fin = false;
+			const int jfin = beg < end ? end : beg;
+			if (jfin == qlen) { max_ie = gscore > h1 ? max_ie : i; gscore = gscore > h1 ? gscore : h1; }
+			if (m == 0) fin = true;
+			else {
+				if (m > max) { max = m; max_i = i; max_j = mj; int off = iabs(mj - i); max_off = max_off > off ? max_off : off; }
+				else if (opt.zdrop > 0) {
+					if (i - max_i > mj - max_j) { if (max - m - ((i - max_i) - (mj - max_j)) * e_del > opt.zdrop) fin = true; }
+					else { if (max - m - ((mj - max_j) - (i - max_i)) * e_ins > opt.zdrop) fin = true; }
+				}
+				if (!fin) {
+					int j;
+					for (j = beg; j < end && tm.row[(size_t)j * RS] == 0; ++j) {}
+					beg = j;
+					for (j = end; j >= beg && tm.row[(size_t)j * RS] == 0; --j) {}
+					end = j + 2 < qlen ? j + 2 : qlen;
+					++i;
+					if (i >= tlen) fin = true;
+				}
+			}
+			if (fin) { in_ext = false; phase = TX_EXT_DONE; }
+		}
+	}
+#undef TX_TO_WARP
+	if (cnt) { if (cells) atomic_add_u64(&cnt->cells_ext, cells); if (n_ext) atomic_add_u64(&cnt->n_ext, n_ext); }
+}

@@ -35,6 +35,7 @@ struct BatchParams {
 	i64* pe_cand;           // per pair
 	// mate rescue (rescue.cuh)
 	u32* nb; SwTask* sw_tasks; u8* sw_state; u32* sw_list; u32* sw_n_list; u32* max_nb; u32* multi; u32* n_multi; int round; int rescued;
+	u8* spec_state; u32* spec_task; u32* n_reg0; int force_fb; // speculative rescue (rescue.cuh); multi / n_multi double as the fallback list
 	PeStat pes[4];
 	const double* pair_tab; i64 pair_tab_off[4];
 	// output
@@ -48,8 +49,12 @@ struct BatchParams {
 	u8* t_buf; size_t t_stride; int t_z_cap, t_cigar_cap, t_md_cap, t_xa_cap;
 	u32* redo_list; u32* n_redo; // items a thread-level kernel handed over to the warp-level kernel
 	u32* heavy_list; u32* n_heavy; int light_max_seeds, light_max_chains; // extension: reads with many seeds go to the warp-level kernel
+	int t_ext_rw;           // thread-level extension: shared-memory words per thread (DP row, doubling as the two NW rings)
+	u64 rowpack[5];         // byte c of rowpack[t] = mat[t*5 + c] (score of query code c against target base t)
 	u32* err; Counters* cnt; u32* work_counter;
 };
+
+#include "extend_thread.cuh"
 
 // ---- encode: ASCII -> nt4 (bytes already < 4 are taken as codes; hazard H12) --------------------
 DEV u8 nt4_of(u8 c)
@@ -203,11 +208,31 @@ DEV RescueIO make_rescue_io(const BatchParams& P)
 	io.seq_off = P.seq_off; io.seq = P.seq; io.reg_off = P.reg_off; io.reg_cap = P.reg_cap; io.regs = P.regs; io.n_reg = P.n_reg;
 	io.snap = P.snap; io.nb = P.nb; io.tasks = P.sw_tasks; io.state = P.sw_state; io.list = P.sw_list; io.n_list = P.sw_n_list;
 	io.max_nb = P.max_nb; io.multi = P.multi; io.n_multi = P.n_multi; io.n_reads = P.n_units << 1; io.round = P.round;
+	io.spec_state = P.spec_state; io.spec_task = P.spec_task; io.n_reg0 = P.n_reg0; io.fb_list = P.multi; io.n_fb = P.n_multi; io.force_fb = P.force_fb;
 	return io;
 }
 DEV void body_rescue_snap(const BatchParams& P, i64 r) { RescueIO io = make_rescue_io(P); rescue_snap(P.opt, io, r); }
 DEV void body_rescue_gen(const BatchParams& P, i64 r) { if (r >= ((i64)P.n_units << 1)) return; RescueIO io = make_rescue_io(P); rescue_gen(P.x, P.opt, P.pes, io, r); }
-// rounds >= 1 visit only the reads with several rescuing hits (compact list built by the snapshot kernel)
+DEV void body_rescue_gen_all(const BatchParams& P, i64 r) { if (r >= ((i64)P.n_units << 1)) return; RescueIO io = make_rescue_io(P); rescue_gen_all(P.x, P.opt, P.pes, io, r); }
+// replay of the speculated rescue chain of read r; reads that cannot be replayed are queued for the round-by-round kernels
+DEV void body_rescue_apply_all(const BatchParams& P, i64 r)
+{
+	if (r >= ((i64)P.n_units << 1)) return;
+	RescueIO io = make_rescue_io(P);
+	WarpMem wm; memset(&wm, 0, sizeof(wm));
+	WarpScratch ws; memset(&ws, 0, sizeof(ws)); ws.err = P.err;
+	if (!rescue_apply_all<1>(P.x, P.opt, P.pes, wm, ws, io, r)) { u32 slot = atomic_add_u32(io.n_fb, 1u); io.fb_list[slot] = (u32)r; }
+}
+// round-by-round path: the mate's list of a queued read is put back to its pre-rescue state first
+DEV void body_rescue_fb_restore(const BatchParams& P, i64 i)
+{
+	const i64 r = (i64)P.multi[i], m = r ^ 1;
+	const Reg* s = P.regs_tmp + P.seed_off[m]; Reg* d = P.regs + P.reg_off[m];
+	const int n = (int)P.n_reg0[m];
+	for (int k = 0; k < n; ++k) d[k] = s[k];
+	P.n_reg[m] = (u32)n;
+}
+// the round-by-round kernels visit only the queued reads (compact list)
 DEV void body_rescue_gen_multi(const BatchParams& P, i64 i) { if (i < (i64)*P.n_multi) body_rescue_gen(P, (i64)P.multi[i]); }
 DEV void body_rescue_apply(const BatchParams& P, i64 r);
 DEV void body_rescue_apply_multi(const BatchParams& P, i64 i) { if (i < (i64)*P.n_multi) body_rescue_apply(P, (i64)P.multi[i]); }
@@ -224,7 +249,7 @@ template <int W>
 DEV void wbody_rescue_sw(const BatchParams& P, i64 item, WarpMem& wm, WarpScratch& ws)
 {
 	RescueIO io = make_rescue_io(P);
-	rescue_sw<W>(P.x, P.opt, wm, ws, P.cnt, io, P.sw_list[item]);
+	rescue_sw<W>(P.x, P.opt, wm, ws, P.cnt, io, (u32)item); // tasks are stored compactly: the item is the task index
 }
 
 DEV void make_final_ctx(const BatchParams& P, WarpMem& wm, WarpScratch& ws, FinalCtx& f)
@@ -313,18 +338,36 @@ DEV void make_thread_ctx(const BatchParams& P, i64 tid, WarpMem& wm, WarpScratch
 	ws.brow = nullptr; ws.brow_cap = 0;
 	ws.err = lerr; // limits hit here are not errors: the item is redone by a warp with the large scratch
 }
-// extension, thread per read: reads with few kept seeds are extended by one thread (scalar DP rows in the thread's
-// scratch); the others are queued for the warp-per-read kernel
-DEV void body_extend_t(const BatchParams& P, i64 r, i64 tid)
+// extension, thread per read (extend_thread.cuh): reads with few kept seeds are extended by one thread with its DP row
+// in shared memory; the others, and reads that do not fit the thread-level rows, are queued for the warp-per-read kernel
+HOSTDEV size_t thread_ext_smem_bytes(int block_threads, int rw, int wm_cap) { return (size_t)block_threads * ((size_t)rw * 4 + (size_t)((wm_cap + 2 + 3) & ~3)); }
+#ifdef B200_SIM
+static u32 g_sim_ext_row[4096]; static u8 g_sim_ext_q[4096];
+#endif
+DEV void make_thread_ext_ctx(const BatchParams& P, i64 tid, ThreadExtMem& tm, WarpMem& wm, WarpScratch& ws, u32* lerr)
 {
-	const int nck = (int)P.n_ck[r], nks = (int)P.n_ks[r];
-	if (nck == 0) { P.n_reg[r] = 0; return; }
-	if (nks > P.light_max_seeds || nck > P.light_max_chains) { u32 slot = atomic_add_u32(P.n_heavy, 1u); P.heavy_list[slot] = (u32)r; return; }
+	make_thread_ctx(P, tid, wm, ws, lerr); // global scratch (traceback, cigar, MD) of this thread slot
+#ifdef B200_SIM
+	u32* words = g_sim_ext_row; u8* qrow = g_sim_ext_q; const int st = 1;
+	const int rw = P.t_ext_rw < 4096 ? P.t_ext_rw : 4096;
+#else
+	extern __shared__ __align__(16) u8 tsm_[];
+	const int st = (int)blockDim.x, rw = P.t_ext_rw;
+	u32* words = (u32*)tsm_ + threadIdx.x;
+	u8* qrow = tsm_ + (size_t)st * rw * 4 + threadIdx.x;
+#endif
+	tm.row = words; tm.row_stride = st; tm.row_cap = rw;
+	tm.rd = qrow; tm.rd_stride = st; tm.rd_cap = P.wm_cap + 2;
+	tm.rowpack = P.rowpack;
+	// the banded global alignment of region patching runs after the extensions: its rings and query row reuse the space
+	wm.ringH = (i32*)words; wm.ringE = (i32*)words + (size_t)THREAD_RING_N * st; wm.ring_n = THREAD_RING_N; wm.ring_stride = st;
+	wm.q = qrow; wm.q_stride = st;
+}
+DEV void body_extend_q(const BatchParams& P, i64 n, u32* counter, i64 tid)
+{
 	u32 lerr = 0;
-	WarpMem wm; WarpScratch ws; make_thread_ctx(P, tid, wm, ws, &lerr);
-	wbody_extend<1>(P, r, wm, ws); // writes only this read's output slots, so a hand-over simply recomputes them
-	if (lerr & ERR_NEED_WARP) { u32 slot = atomic_add_u32(P.n_heavy, 1u); P.heavy_list[slot] = (u32)r; }
-	else if (lerr) atomic_or_u32(P.err, lerr);
+	ThreadExtMem tm; WarpMem wm; WarpScratch ws; make_thread_ext_ctx(P, tid, tm, wm, ws, &lerr);
+	thread_extend_queue(P, n, counter, tm, wm, ws, &lerr);
 }
 template <int W>
 DEV void wbody_extend_heavy(const BatchParams& P, i64 item, WarpMem& wm, WarpScratch& ws) { wbody_extend<W>(P, (i64)P.heavy_list[item], wm, ws); }

@@ -11,6 +11,14 @@
 //   The two rescue chains of a pair (hits of end 0 into the list of end 1 and vice versa) never read each other's
 //   output, and the <= 4 alignments of one mem_matesw call are fixed before the first of them runs, so this order
 //   of evaluation yields the same lists as the sequential loop.
+//
+// Speculative form (the default): the alignment of (hit k, orientation d) depends only on the hit, the insert-size
+// statistics and the mate's bases -- not on the mate's list -- so ONE launch aligns the tasks of ALL hits k, chosen by
+// the skip test against the mate's ORIGINAL list (gen_all), and one thread per read then replays the sequential
+// decisions against the live list (apply_all), consuming the precomputed results.  Rescued hits only ever add
+// suppressors, so the speculated set is a superset of the needed one -- except when region de-duplication removed the
+// hit that had suppressed an orientation; replay detects that (a needed orientation with no speculated result) and
+// hands the read to the round-by-round kernels above, which recompute its chain from the restored list.
 #pragma once
 #include "finalize.cuh"
 
@@ -210,12 +218,15 @@ struct RescueIO {
 	const u64* seq_off; const u8* seq; const u64* reg_off; const u32* reg_cap;
 	Reg* regs; u32* n_reg; Reg* snap; u32* nb;
 	SwTask* tasks; u8* state; u32* list; u32* n_list; u32* max_nb;
-	u32* multi; u32* n_multi; // reads with more than one rescuing hit (the only ones that take part in rounds >= 1)
+	u32* multi; u32* n_multi; // the reads that take part in the round-by-round kernels (compact list)
 	int n_reads; int round;
+	// speculative pipeline: per snapshot slot (reg_off[r] + k) and orientation
+	u8* spec_state; u32* spec_task; u32* n_reg0; u32* fb_list; u32* n_fb; int force_fb;
 };
 
 DEV void rescue_snap(const MemOpt& opt, const RescueIO& io, i64 r)
 {
+	io.n_reg0[r] = io.n_reg[r];
 	if ((r | 1) >= io.n_reads) { io.nb[r] = 0; return; } // odd trailing read
 	const Reg* a = io.regs + io.reg_off[r];
 	Reg* b = io.snap + io.reg_off[r];
@@ -224,7 +235,6 @@ DEV void rescue_snap(const MemOpt& opt, const RescueIO& io, i64 r)
 	if (m > opt.max_matesw) m = opt.max_matesw;
 	io.nb[r] = (u32)m;
 	if (m) atomic_max_u32(io.max_nb, (u32)m);
-	if (m > 1) { u32 slot = atomic_add_u32(io.n_multi, 1u); io.multi[slot] = (u32)r; }
 }
 
 // ---- gen: the skip test and the windows of mem_matesw for hit `round` of read r -----------------------
@@ -265,11 +275,60 @@ DEV void rescue_gen(const DevIndex& x, const MemOpt& opt, const PeStat* pes, con
 			SwTask t;
 			t.rb = rb; t.re = re; t.read = (u32)m; t.is_rev = is_rev;
 			t.score = 0; t.te = t.qe = t.score2 = t.te2 = t.tb = t.qb = -1; t.pad_ = 0;
-			io.tasks[(size_t)r * 4 + d] = t;
-			state[d] = SW_RUN;
 			u32 slot = atomic_add_u32(io.n_list, 1u);
-			io.list[slot] = (u32)(r * 4 + d);
+			io.tasks[slot] = t;
+			io.list[(size_t)r * 4 + d] = slot;
+			state[d] = SW_RUN;
 		} else state[d] = SW_NORUN;
+	}
+}
+
+// ---- gen_all: the tasks of every rescuing hit of read r, chosen against the mate's original list -------------
+DEV void rescue_gen_all(const DevIndex& x, const MemOpt& opt, const PeStat* pes, const RescueIO& io, i64 r)
+{
+	const int nb = (int)io.nb[r];
+	if (nb == 0) return;
+	const i64 m = r ^ 1;
+	const Reg* ma = io.regs + io.reg_off[m];
+	const int nm = (int)io.n_reg[m];
+	const int l_ms = (int)(io.seq_off[m + 1] - io.seq_off[m] - 1);
+	const i64 l_pac = x.l_pac;
+	for (int k = 0; k < nb; ++k) {
+		const Reg a = io.snap[io.reg_off[r] + k];
+		int skip[4];
+		for (int d = 0; d < 4; ++d) skip[d] = pes[d].failed ? 1 : 0;
+		for (int i = 0; i < nm; ++i) {
+			i64 dist;
+			int d = infer_dir(l_pac, a.rb, ma[i].rb, &dist);
+			if (dist >= pes[d].low && dist <= pes[d].high) skip[d] = 1;
+		}
+		u8* state = io.spec_state + (io.reg_off[r] + k) * 4;
+		u32* tix = io.spec_task + (io.reg_off[r] + k) * 4;
+		for (int d = 0; d < 4; ++d) {
+			if (skip[d]) { state[d] = SW_SKIP; continue; }
+			int is_rev = (d >> 1) != (d & 1), is_larger = !(d >> 1);
+			i64 rb, re;
+			if (!is_rev) {
+				rb = is_larger ? a.rb + pes[d].low : a.rb - pes[d].high;
+				re = (is_larger ? a.rb + pes[d].high : a.rb - pes[d].low) + l_ms;
+			} else {
+				rb = (is_larger ? a.rb + pes[d].low : a.rb - pes[d].high) - l_ms;
+				re = is_larger ? a.rb + pes[d].high : a.rb - pes[d].low;
+			}
+			if (rb < 0) rb = 0;
+			if (re > l_pac << 1) re = l_pac << 1;
+			int rid = -1;
+			if (rb < re) rid = ref_clip_window(x, rb, (rb + re) >> 1, re);
+			if (a.rid == rid && re - rb >= opt.min_seed_len) {
+				SwTask t;
+				t.rb = rb; t.re = re; t.read = (u32)m; t.is_rev = is_rev;
+				t.score = 0; t.te = t.qe = t.score2 = t.te2 = t.tb = t.qb = -1; t.pad_ = 0;
+				u32 slot = atomic_add_u32(io.n_list, 1u);
+				io.tasks[slot] = t;
+				tix[d] = slot;
+				state[d] = SW_RUN;
+			} else state[d] = SW_NORUN;
+		}
 	}
 }
 
@@ -321,6 +380,31 @@ DEVNI void rescue_sw(const DevIndex& x, const MemOpt& opt, WarpMem& wm, WarpScra
 	WARP_SYNC();
 }
 
+// the hit of one finished alignment task, inserted by score into the mate's list (false: no room)
+DEV bool rescue_insert(const MemOpt& opt, i64 l_pac, const Reg& a, const SwTask& t, int l_ms, Reg* ma, int* n_ma, int ma_cap)
+{
+	if (!(t.score >= opt.min_seed_len && t.qb >= 0)) return true;
+	const int is_rev = t.is_rev;
+	int nm = *n_ma;
+	Reg b;
+	memset(&b, 0, sizeof(Reg));
+	b.rid = a.rid; b.is_alt = a.is_alt;
+	b.qb = is_rev ? l_ms - (t.qe + 1) : t.qb;
+	b.qe = is_rev ? l_ms - t.qb : t.qe + 1;
+	b.rb = is_rev ? (l_pac << 1) - (t.rb + t.te + 1) : t.rb + t.tb;
+	b.re = is_rev ? (l_pac << 1) - (t.rb + t.tb) : t.rb + t.te + 1;
+	b.score = t.score; b.csub = t.score2; b.secondary = -1;
+	b.seedcov = (int)((b.re - b.rb < b.qe - b.qb ? b.re - b.rb : b.qe - b.qb) >> 1);
+	if (nm >= ma_cap) return false;
+	int i, tmp;
+	for (i = 0; i < nm; ++i) if (ma[i].score < b.score) break;
+	tmp = i;
+	for (i = nm; i > tmp; --i) ma[i] = ma[i - 1];
+	ma[tmp] = b;
+	*n_ma = nm + 1;
+	return true;
+}
+
 // ---- apply: insert the hits of one mem_matesw call into the mate's list, de-duplicating as the loop does ----
 template <int W>
 DEV void rescue_apply(const DevIndex& x, const MemOpt& opt, WarpMem& wm, WarpScratch& ws, const RescueIO& io, i64 r)
@@ -338,29 +422,54 @@ DEV void rescue_apply(const DevIndex& x, const MemOpt& opt, WarpMem& wm, WarpScr
 	for (int d = 0; d < 4; ++d) {
 		if (state[d] == SW_SKIP) continue;
 		if (state[d] == SW_RUN) {
-			const SwTask t = io.tasks[(size_t)r * 4 + d];
-			const int is_rev = t.is_rev;
-			if (t.score >= opt.min_seed_len && t.qb >= 0) {
-				Reg b;
-				memset(&b, 0, sizeof(Reg));
-				b.rid = a.rid; b.is_alt = a.is_alt;
-				b.qb = is_rev ? l_ms - (t.qe + 1) : t.qb;
-				b.qe = is_rev ? l_ms - t.qb : t.qe + 1;
-				b.rb = is_rev ? (l_pac << 1) - (t.rb + t.te + 1) : t.rb + t.tb;
-				b.re = is_rev ? (l_pac << 1) - (t.rb + t.tb) : t.rb + t.te + 1;
-				b.score = t.score; b.csub = t.score2; b.secondary = -1;
-				b.seedcov = (int)((b.re - b.rb < b.qe - b.qb ? b.re - b.rb : b.qe - b.qb) >> 1);
-				if (nm >= ma_cap) { atomic_or_u32(ws.err, ERR_REG_OVERFLOW); return; }
-				int i, tmp;
-				for (i = 0; i < nm; ++i) if (ma[i].score < b.score) break;
-				tmp = i;
-				for (i = nm; i > tmp; --i) ma[i] = ma[i - 1];
-				ma[tmp] = b;
-				++nm;
-			}
+			const SwTask t = io.tasks[io.list[(size_t)r * 4 + d]];
+			if (!rescue_insert(opt, l_pac, a, t, l_ms, ma, &nm, ma_cap)) { atomic_or_u32(ws.err, ERR_REG_OVERFLOW); return; }
 			++n;
 		}
 		if (n) nm = warp_sort_dedup_patch<W>(x, opt, wm, ws, nullptr, nullptr, nm, ma);
 	}
 	io.n_reg[m] = (u32)nm;
+}
+
+// ---- apply_all: replay of the whole rescue chain of read r (hits 0 .. nb-1 into the mate's list) from the
+// speculated results.  Returns false when the read has to take the round-by-round path instead.
+template <int W>
+DEV bool rescue_apply_all(const DevIndex& x, const MemOpt& opt, const PeStat* pes, WarpMem& wm, WarpScratch& ws, const RescueIO& io, i64 r)
+{
+	const int nb = (int)io.nb[r];
+	if (nb == 0) return true;
+	const i64 m = r ^ 1;
+	Reg* ma = io.regs + io.reg_off[m];
+	int nm = (int)io.n_reg[m];
+	const int ma_cap = (int)io.reg_cap[m];
+	const int l_ms = (int)(io.seq_off[m + 1] - io.seq_off[m] - 1);
+	const i64 l_pac = x.l_pac;
+	bool ok = true;
+	for (int k = 0; k < nb && ok; ++k) {
+		const Reg a = io.snap[io.reg_off[r] + k];
+		int skip[4];
+		for (int d = 0; d < 4; ++d) skip[d] = pes[d].failed ? 1 : 0;
+		for (int i = 0; i < nm; ++i) {
+			i64 dist;
+			int d = infer_dir(l_pac, a.rb, ma[i].rb, &dist);
+			if (dist >= pes[d].low && dist <= pes[d].high) skip[d] = 1;
+		}
+		if (skip[0] + skip[1] + skip[2] + skip[3] == 4) continue;
+		const u8* state = io.spec_state + (io.reg_off[r] + k) * 4;
+		const u32* tix = io.spec_task + (io.reg_off[r] + k) * 4;
+		for (int d = 0; d < 4; ++d) if (!skip[d] && state[d] == SW_SKIP) ok = false; // needed, not speculated
+		if (!ok) break;
+		int n = 0;
+		for (int d = 0; d < 4; ++d) {
+			if (skip[d]) continue;
+			if (state[d] == SW_RUN) {
+				const SwTask t = io.tasks[tix[d]];
+				if (!rescue_insert(opt, l_pac, a, t, l_ms, ma, &nm, ma_cap)) { atomic_or_u32(ws.err, ERR_REG_OVERFLOW); io.n_reg[m] = (u32)nm; return true; }
+				++n;
+			}
+			if (n) nm = warp_sort_dedup_patch<W>(x, opt, wm, ws, nullptr, nullptr, nm, ma);
+		}
+	}
+	io.n_reg[m] = (u32)nm;
+	return ok && !io.force_fb;
 }

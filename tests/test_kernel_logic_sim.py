@@ -36,3 +36,15 @@ def test_sim_matches_oracle(small_genome, name, kw, flag):
     a = run_blob(oracle_lib(), img, blob, flag)
     b = run_blob(sim_lib(), img, blob, flag)
     assert a == b, first_diff(a, b, blob, bool(flag & 2))
+
+
+def test_sim_rescue_fallback_path(small_genome, monkeypatch):
+    """Mate rescue: every rescuing read is forced from the speculative replay onto the round-by-round kernels
+    (restore of the mate's list included); repeat-heavy reads give chains of several rescuing hits."""
+    g, img = small_genome
+    blob, _ = simdata.make_reads(g, 77, 400, 150, True, repeat_read_frac=0.5, chimeric_frac=0.05)
+    a = run_blob(oracle_lib(), img, blob, 2)
+    assert run_blob(sim_lib(), img, blob, 2) == a
+    monkeypatch.setenv("B200_TEST_RESCUE_FALLBACK", "1")
+    b = run_blob(sim_lib(), img, blob, 2)
+    assert a == b, first_diff(a, b, blob, True)

@@ -94,6 +94,21 @@ def test_engine_matches_oracle_mid(mid_genome, paired):
     assert a == b, first_diff(a, b, blob, paired)
 
 
+@pytest.mark.parametrize("env", [None, "B200_TEST_RESCUE_FALLBACK", "B200_TEST_TINY_SCRATCH", "B200_TEST_ALL_LIGHT", "B200_TEST_ALL_HEAVY", "B200_WARP_EXTEND"],
+                         ids=["default", "rescue_fallback", "tiny_scratch", "extend_all_thread", "extend_all_handover", "extend_all_warp"])
+def test_repeat_heavy_pairs_and_forced_slow_paths(small_genome, monkeypatch, env):
+    """Chains of several rescuing hits per read (repeat-derived reads); the same batch with every rescuing read forced
+    onto the round-by-round rescue kernels, with thread-level scratch so small that items are handed to warps, and with
+    the seed extension forced onto each of its three routes (thread per read, hand-over list, warp per read)."""
+    g, img = small_genome
+    blob, _ = simdata.make_reads(g, 77, 3000, 150, True, repeat_read_frac=0.5, chimeric_frac=0.05, err_rate=0.02, indel_frac=0.3)
+    a = run_blob(oracle_lib(), img, blob, 2)
+    if env:
+        monkeypatch.setenv(env, "1")
+    b = run_blob(engine_lib(), img, blob, 2)
+    assert a == b, first_diff(a, b, blob, True)
+
+
 def test_repeat_calls_are_deterministic(small_genome):
     g, img = small_genome
     blob, _ = simdata.make_reads(g, 50, 2000, 150, True)
