@@ -3,5 +3,5 @@
 The package holds the CUDA engine (csrc/ -> lib/libbwa_b200.so, C-ABI in include/bwamem_b200.h) and the host-side
 mirror of the reference's Java classes (bwa.py).  The directory name contains '-', so load it by path
 (see tests/common.py or __graft_entry__.py) rather than with a plain import statement."""
-from . import bwa
+from . import bwa, shard
 from .bwa import *  # noqa: F401,F403

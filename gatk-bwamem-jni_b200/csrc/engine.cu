@@ -250,6 +250,9 @@ void* jnibwa_openIndex(int fd)
 		if (fd >= 0) close(fd);
 		return nullptr;
 	}
+	if (const char* dv = getenv("BWA_B200_DEVICE")) { // the Java API has no notion of a device
+		if (cudaSetDevice(atoi(dv)) != cudaSuccess) { fprintf(stderr, "[bwamem-b200] BWA_B200_DEVICE=%s is not a usable device\n", dv); if (fd >= 0) close(fd); return nullptr; }
+	}
 	Engine* e = new Engine();
 	if (!e->open_from_fd(fd)) { fprintf(stderr, "[bwamem-b200] openIndex: %s\n", e->last_error.c_str()); e->close_all(); delete e; return nullptr; }
 	return e;

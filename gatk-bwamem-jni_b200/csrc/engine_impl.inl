@@ -331,6 +331,8 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 		P.t_buf = b_tbuf.as<u8>(); P.redo_list = b_redo.as<u32>(); P.n_redo = b_misc.as<u32>() + 5;
 		P.heavy_list = b_heavy.as<u32>(); P.n_heavy = b_misc.as<u32>() + 6;
 		P.light_max_seeds = 12; P.light_max_chains = 4;
+		if (getenv("B200_LIGHT_SEEDS")) P.light_max_seeds = atoi(getenv("B200_LIGHT_SEEDS")); // tuning aids
+		if (getenv("B200_LIGHT_CHAINS")) P.light_max_chains = atoi(getenv("B200_LIGHT_CHAINS"));
 		if (getenv("B200_TEST_ALL_HEAVY")) P.light_max_seeds = -1;
 		if (getenv("B200_TEST_ALL_LIGHT")) { P.light_max_seeds = 1 << 30; P.light_max_chains = 1 << 30; }
 	}
