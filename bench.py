@@ -38,7 +38,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--genome-mbp", type=float, default=float(os.environ.get("B200_BENCH_GENOME_MBP", "256")))
+    ap.add_argument("--genome-mbp", type=float, default=float(os.environ.get("B200_BENCH_GENOME_MBP", "3000")))
     ap.add_argument("--pairs", type=int, default=int(os.environ.get("B200_BENCH_PAIRS", "250000")),
                     help="read pairs per step (per GPU)")
     ap.add_argument("--read-len", type=int, default=150)
@@ -87,21 +87,42 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+def contig_lengths(total: int):
+    """24 contigs of 50-250 Mbp at human scale (deterministic spread); 4 equal contigs below 1 Gbp."""
+    if total < 1_000_000_000:
+        n_ctg = 4 if total >= 4_000_000 else 1
+        return [total // n_ctg] * n_ctg
+    w = [50 + (i * 37) % 201 for i in range(24)]
+    lens = [int(total * x / sum(w)) for x in w]
+    lens[-1] += total - sum(lens)
+    return lens
+
+
 def workload(args, rank: int, world: int):
     """Seeded synthetic genome (contigs, injected repeat families / tandem repeats / segmental duplications)
-    + wgsim-style 2x150 bp pairs.  Built once by rank 0, shared through tests/_work."""
+    + wgsim-style 2x150 bp pairs.  The index image is built once by rank 0 (on the GPU when one is present:
+    csrc/sa_build.cu; the host sorter otherwise) and shared through tests/_work; none of this is timed."""
     import common
     total = int(args.genome_mbp * 1e6)
-    n_ctg = 4 if total >= 4_000_000 else 1
-    lens = [total // n_ctg] * n_ctg
+    lens = contig_lengths(total)
     tag = f"bench_g{total}"
     img = os.path.join(common.workdir(), tag + ".img")
+    t = time.time()
     g = common.simdata.make_genome(2, lens, repeat_frac=0.05, tandem_frac=0.01, n_segdup=50 if total >= 50_000_000 else 5)
+    if rank == 0:
+        sys.stderr.write(f"[bench] generated the {total} bp genome in {time.time() - t:.1f}s\n")
     if rank == 0 and not os.path.exists(img):
         t = time.time()
-        common.simdata.build_image(g, img + ".tmp")
+        dll = None
+        try:
+            import torch
+            if torch.cuda.is_available():
+                dll = common.engine_lib().dll
+        except Exception:
+            dll = None
+        common.simdata.build_image(g, img + ".tmp", dll=dll)
         os.replace(img + ".tmp", img)
-        sys.stderr.write(f"[bench] built index image for {total} bp in {time.time() - t:.1f}s\n")
+        sys.stderr.write(f"[bench] built the index image for {total} bp in {time.time() - t:.1f}s ({'device' if dll else 'host'} suffix sorter)\n")
     return g, img
 
 
@@ -162,12 +183,12 @@ def main():
     args = parse_args()
     rank, world, local = dist_env()
     cores = os.cpu_count() or 1
-    cfg = {"workload": f"synthetic {args.genome_mbp:g} Mbp genome (4 contigs, 5% interspersed repeats, 1% tandem, segdups), "
+    cfg = {"workload": f"synthetic {args.genome_mbp:g} Mbp genome ({len(contig_lengths(int(args.genome_mbp * 1e6)))} contigs, 5% interspersed repeats, 1% tandem, segdups), "
                        f"2x{args.read_len} bp wgsim-style pairs (insert N(400,50), 0.1% mutations, 1% base error), "
                        f"{args.pairs} pairs per createAlignments call per GPU, default mem_opt_t + MEM_F_PE, pestat inferred per call",
            "genome_bp": int(args.genome_mbp * 1e6), "pairs_per_step_per_gpu": args.pairs, "read_len": args.read_len,
            "parallelism": f"index replica per GPU, shard-by-call x{world}", "cache": "index + batch exceed L2; a different batch every step",
-           "note": "BASELINE's 3 Gbp genome needs an index build that is a 'next' row (SURVEY 8f.1); same kernels, smaller index"}
+           "index": "BwaMemIndex image of the genome built on the GPU before the timed region (csrc/sa_build.cu)"}
 
     # ---------------- reference arm: the CPU restatement on all host cores -----------------------------------
     if args.impl == "reference":
@@ -267,8 +288,12 @@ def main():
     sblob = common.bwa.pack_sequences(reads)
     cpu = None
     work = None
+    parity = None
     if not args.no_cpu_baseline:
         dt, oc, ref_out = run_oracle(img, sblob, 2, cores)
+        # the oracle's stream for the sample doubles as a full-scale parity check of the engine (same batch, untimed)
+        eng_out = idx.doAlignment(bytearray(sblob), al._opts_addr, None)
+        parity = {"sample_pairs": n_s, "identical": bool(eng_out == ref_out), "bytes": len(ref_out)}
         scale = args.pairs / n_s
         work = {k: v * scale for k, v in oc.items()}
         cpu = {"value": n_s / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
@@ -309,7 +334,7 @@ def main():
             "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic", "config": cfg, "clocks": clocks,
             "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": out_bytes},
-            "gpu_launches": int(cnt[7]) * args.steps, "roofline": roof, "kernels": kern, "cpu_baseline": cpu}
+            "gpu_launches": int(cnt[7]) * args.steps, "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "parity": parity}
     print(json.dumps(line))
 
 

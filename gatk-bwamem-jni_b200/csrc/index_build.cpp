@@ -190,8 +190,19 @@ static void build_fm_t(const RefSeqs& ref, FmIndex& fm, int n_threads)
 	for (uint64_t r = 32; r <= (uint64_t)n; r += 32) fm.sa[r / 32] = (uint64_t)sa[(size_t)(r - 1)];
 }
 
+// Defined in sa_build.cu when this file is linked into libbwa_b200.so (the CUDA build); absent from the host-only
+// tool library.  BWA_B200_BUILD=host|device forces one sorter; by default the device is used when one is present
+// and the text is large enough to be worth the upload.
+bool build_fm_device(const RefSeqs& ref, FmIndex& fm) __attribute__((weak));
+
 void build_fm(const RefSeqs& ref, FmIndex& fm, int n_threads)
 {
+	const char* mode = getenv("BWA_B200_BUILD");
+	const bool force_host = mode && strcmp(mode, "host") == 0, force_dev = mode && strcmp(mode, "device") == 0;
+	if (build_fm_device && !force_host && (force_dev || ref.l_pac >= (int64_t)8 << 20)) {
+		if (build_fm_device(ref, fm)) return;
+		fprintf(stderr, "[bwamem-b200] index build: device sorter unavailable, using the host sorter\n");
+	}
 	if (2 * ref.l_pac < (int64_t)0xFFFFFFF0LL) build_fm_t<uint32_t>(ref, fm, n_threads);
 	else build_fm_t<uint64_t>(ref, fm, n_threads);
 }

@@ -119,3 +119,21 @@ def test_repeat_calls_are_deterministic(small_genome):
     assert outs[0] == outs[1] == outs[2]
     al.close()
     idx.close()
+
+
+@pytest.mark.parametrize("chunk", [None, "20000"], ids=["one_chunk", "many_chunks_with_splits"])
+def test_device_index_builder_matches_host_builder(tmp_path, monkeypatch, chunk):
+    """csrc/sa_build.cu (GPU suffix sorting) against the host sorter of index_build.cpp: identical image bytes, on a
+    genome with repeat families, tandem repeats and segmental duplications (deep refinement rounds), also with a chunk
+    capacity so small that prefix ranges have to be split."""
+    import os
+    g = simdata.make_genome(5, [300000, 150000, 50000], repeat_frac=0.08, tandem_frac=0.02, n_segdup=4)
+    host = str(tmp_path / "host.img")
+    dev = str(tmp_path / "dev.img")
+    simdata.build_image(g, host)
+    monkeypatch.setenv("BWA_B200_BUILD", "device")
+    if chunk:
+        monkeypatch.setenv("BWA_B200_BUILD_CHUNK", chunk)
+    simdata.build_image(g, dev, dll=engine_lib().dll)
+    assert os.path.getsize(host) == os.path.getsize(dev)
+    assert open(host, "rb").read() == open(dev, "rb").read()

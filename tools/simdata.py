@@ -119,9 +119,15 @@ def split_blob(blob: bytes) -> List[bytes]:
     return parts[:n]
 
 
-def build_image(genome: Genome, img_path: str, prefix: Optional[str] = None) -> None:
+def build_image(genome: Genome, img_path: str, prefix: Optional[str] = None, dll=None) -> None:
+    """dll: a loaded library exporting b200_buildImageFromBases (default: the host-only builder; pass the engine's
+    library to use the device suffix sorter, csrc/sa_build.cu)."""
     names = b"".join(n.encode() + b"\0" for n in genome.names)
-    rc = idxlib().b200_buildImageFromBases(len(genome.lens), names, genome.lens.ctypes.data, genome.bases.ctypes.data,
+    if dll is not None:
+        dll.b200_buildImageFromBases.restype = ctypes.c_int
+        dll.b200_buildImageFromBases.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                 ctypes.c_char_p, ctypes.c_char_p]
+    rc = (dll or idxlib()).b200_buildImageFromBases(len(genome.lens), names, genome.lens.ctypes.data, genome.bases.ctypes.data,
                                            img_path.encode(), prefix.encode() if prefix else None)
     if rc != 0:
         raise RuntimeError(f"image build failed rc={rc}")
