@@ -146,6 +146,8 @@ DEF_THREAD_KERNEL(body_rescue_gen)
 DEF_THREAD_KERNEL(body_rescue_gen_all)
 DEF_THREAD_KERNEL(body_rescue_apply_all)
 DEF_THREAD_KERNEL(body_rescue_fb_restore)
+DEF_THREAD_KERNEL(body_rescue_classify)
+DEF_WARP_KERNEL_DEVN(wbody_rescue_apply_heavy)
 DEF_THREAD_KERNEL(body_rescue_apply)
 DEF_THREAD_KERNEL(body_rescue_gen_multi)
 DEF_THREAD_KERNEL(body_rescue_apply_multi)

@@ -126,7 +126,7 @@ struct Engine {
 	// batch workspace
 	DBuf b_blob, b_seq, b_seqoff, b_intv, b_nintv, b_nseed, b_smem, b_seedoff, b_rbeg, b_S, b_C, b_ord, b_tmp32, b_ck, b_ks, b_srt, b_regtmp,
 	     b_nck, b_nks, b_nreg, b_regcap, b_regoff, b_regs, b_snap, b_ztmp, b_pairv, b_recs, b_nrec, b_cand, b_pairtab, b_var, b_misc,
-	     b_outwords, b_outoff, b_out, b_wsz, b_wscig, b_wsmd, b_wsxa, b_wsbrow, b_nb, b_swtask, b_swstate, b_swlist, b_tbuf, b_redo, b_heavy, b_multi, b_cand2, b_specstate, b_spectask, b_nreg0;
+	     b_outwords, b_outoff, b_out, b_wsz, b_wscig, b_wsmd, b_wsxa, b_wsbrow, b_nb, b_swtask, b_swstate, b_swlist, b_tbuf, b_redo, b_heavy, b_multi, b_cand2, b_specstate, b_spectask, b_nreg0, b_rsheavy, b_wsrt, b_wsrkey, b_wsrrank;
 	Counters last_counters; uint64_t last_n_seed = 0; int n_launches = 0;
 	std::string last_error;
 
@@ -187,13 +187,13 @@ inline void Engine::close_all()
 	DBuf* all[] = { &d_bwt, &d_sa, &d_pac, &d_ctg, &d_log, &d_names, &d_name_off, &b_blob, &b_seq, &b_seqoff, &b_intv, &b_nintv, &b_nseed, &b_smem,
 	                &b_seedoff, &b_rbeg, &b_S, &b_C, &b_ord, &b_tmp32, &b_ck, &b_ks, &b_srt, &b_regtmp, &b_nck, &b_nks, &b_nreg, &b_regcap, &b_regoff,
 	                &b_regs, &b_snap, &b_ztmp, &b_pairv, &b_recs, &b_nrec, &b_cand, &b_pairtab, &b_var, &b_misc, &b_outwords, &b_outoff, &b_out,
-	                &b_wsz, &b_wscig, &b_wsmd, &b_wsxa, &b_wsbrow, &b_nb, &b_swtask, &b_swstate, &b_swlist, &b_tbuf, &b_redo, &b_heavy, &b_multi, &b_cand2, &b_specstate, &b_spectask, &b_nreg0 };
+	                &b_wsz, &b_wscig, &b_wsmd, &b_wsxa, &b_wsbrow, &b_nb, &b_swtask, &b_swstate, &b_swlist, &b_tbuf, &b_redo, &b_heavy, &b_multi, &b_cand2, &b_specstate, &b_spectask, &b_nreg0, &b_rsheavy, &b_wsrt, &b_wsrkey, &b_wsrrank };
 	for (DBuf* b : all) b->release();
 	if (map) munmap(map, map_len);
 	map = nullptr;
 }
 
-// misc block layout (u32 words): [0] err  [1] work counter  [2] var cursor  [3] rescue task count  [4] max nb  [5] redo count  [6] heavy-read count  [7] multi-hit read count  [8..] Counters
+// misc block layout (u32 words): [20] warp-replayed rescue reads  [0] err  [1] work counter  [2] var cursor  [3] rescue task count  [4] max nb  [5] redo count  [6] heavy-read count  [7] multi-hit read count  [8..] Counters
 // Stage a request: one host pass over the blob for the read boundaries, then upload of bases and offsets.
 inline bool Engine::stage(const char* blob_in)
 {
@@ -320,6 +320,10 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 		if (!ok) { last_error = "device allocation failed (warp scratch)"; return nullptr; }
 		P.ws_z = b_wsz.as<u8>(); P.ws_cigar = b_wscig.as<u32>(); P.ws_md = b_wsmd.as<char>(); P.ws_xa = b_wsxa.as<char>();
 		P.ws_brow = nullptr; P.ws_brow_cap = 0;
+		P.ws_rt_cap = 1024; // longer region lists take the scalar de-duplication
+		ok = b_wsrt.ensure((size_t)wslots * P.ws_rt_cap * sizeof(Reg)) && b_wsrkey.ensure((size_t)wslots * (P.ws_rt_cap + 2) * 8) && b_wsrrank.ensure((size_t)wslots * (P.ws_rt_cap + 2) * 4);
+		if (!ok) { last_error = "device allocation failed (warp scratch)"; return nullptr; }
+		P.ws_rt = b_wsrt.as<Reg>(); P.ws_rkey = b_wsrkey.as<i64>(); P.ws_rrank = b_wsrrank.as<u32>();
 	}
 	// ---- thread scratch for the thread-per-item kernels (extension, finalize) and the hand-over lists
 	{
@@ -401,16 +405,19 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 	if (pe && !(opt.flag & MEM_F_NO_RESCUE)) {
 		size_t nr = (size_t)n_reads + 2, Rn = (size_t)R + 2;
 		ok = b_nb.ensure(nr * 4) && b_swtask.ensure((Rn > nr * 4 ? Rn : nr * 4) * sizeof(SwTask)) && b_swstate.ensure(nr * 4) && b_swlist.ensure(nr * 4 * 4)
-		     && b_multi.ensure(nr * 4) && b_specstate.ensure(Rn * 4) && b_spectask.ensure(Rn * 4 * 4) && b_nreg0.ensure(nr * 4);
+		     && b_multi.ensure(nr * 4) && b_specstate.ensure(Rn * 4) && b_spectask.ensure(Rn * 4 * 4) && b_nreg0.ensure(nr * 4) && b_rsheavy.ensure(nr * 4);
 		if (!ok) { last_error = "device allocation failed (rescue pools)"; return nullptr; }
 		P.nb = b_nb.as<u32>(); P.sw_tasks = b_swtask.as<SwTask>(); P.sw_state = b_swstate.as<u8>(); P.sw_list = b_swlist.as<u32>();
 		P.sw_n_list = b_misc.as<u32>() + 3; P.max_nb = b_misc.as<u32>() + 4; P.n_multi = b_misc.as<u32>() + 7;
 		P.multi = b_multi.as<u32>(); P.spec_state = b_specstate.as<u8>(); P.spec_task = b_spectask.as<u32>(); P.n_reg0 = b_nreg0.as<u32>();
 		P.force_fb = getenv("B200_TEST_RESCUE_FALLBACK") ? 1 : 0; // tests: every rescuing read takes the round-by-round path
+		P.rs_heavy = b_rsheavy.as<u32>(); P.n_rs_heavy = b_misc.as<u32>() + 20;
 		RT_THREADS(body_rescue_snap, P, (int64_t)n_reads);
+		RT_THREADS(body_rescue_classify, P, (int64_t)n_reads);
 		// the task pool holds at most sum(nb * live orientations) <= R entries (that head-room is part of reg_cap)
 		RT_THREADS(body_rescue_gen_all, P, (int64_t)n_reads);
 		RT_WARPS_DEVN(wbody_rescue_sw, P, P.sw_n_list, (int64_t)R);
+		RT_WARPS_DEVN(wbody_rescue_apply_heavy, P, P.n_rs_heavy, (int64_t)n_reads); // long chains first: they are the tail
 		RT_THREADS(body_rescue_apply_all, P, (int64_t)n_reads);
 		uint32_t hdr[8];
 		rt_d2h(hdr, b_misc.as<u32>(), sizeof(hdr));

@@ -8,6 +8,7 @@
 #pragma once
 #include "ksw.cuh"
 
+struct Reg;
 struct WarpScratch { // per-warp global scratch
 	u8* z; size_t z_cap;
 	u32* cigar; int cigar_cap;
@@ -15,6 +16,8 @@ struct WarpScratch { // per-warp global scratch
 	char* xa; int xa_cap;
 	u64* brow; int brow_cap;
 	u32* err; // engine-wide error flags
+	// region-list scratch of the warp-cooperative de-duplication (warp_sort_dedup_fast): rt_cap entries each
+	Reg* rt; i64* rkey; u32* rrank; int rt_cap;
 };
 
 
@@ -163,14 +166,16 @@ struct RegLtHash { DEVM bool operator()(const Reg& a, const Reg& b) const { retu
 #endif
 
 // mem_sort_dedup_patch; query == nullptr disables patching (the mate-rescue call sites)
+// stage: 0 = the whole procedure; 1 = the list is already sorted by end position (n_comp set); 2 = only the tail
+// (compaction of the survivors, order by (score desc, rb, qb), removal of identical hits)
 template <int W>
-DEVNI int warp_sort_dedup_patch(const DevIndex& x, const MemOpt& opt, WarpMem& wm, WarpScratch& ws, Counters* cnt, const u8* query, int n, Reg* a)
+DEVNI int warp_sort_dedup_patch(const DevIndex& x, const MemOpt& opt, WarpMem& wm, WarpScratch& ws, Counters* cnt, const u8* query, int n, Reg* a, int stage = 0)
 {
 	LANE_DECL;
 	if (n <= 1) return n;
-	LANE0_ONLY { ks_introsort<Reg, RegLtEnd>((size_t)n, a, RegLtEnd()); for (int i = 0; i < n; ++i) a[i].n_comp = 1; }
+	if (stage == 0) { LANE0_ONLY { ks_introsort<Reg, RegLtEnd>((size_t)n, a, RegLtEnd()); for (int i = 0; i < n; ++i) a[i].n_comp = 1; } }
 	WARP_SYNC();
-	for (int i = 1; i < n; ++i) {
+	for (int i = 1; i < n && stage < 2; ++i) {
 		Reg p = a[i];
 		if (p.rid != a[i - 1].rid || p.rb >= a[i - 1].re + opt.max_chain_gap) continue;
 		bool p_dirty = false;
@@ -320,4 +325,151 @@ DEVNI void warp_chain2aln(const DevIndex& x, const MemOpt& opt, WarpMem& wm, War
 		*n_av = n + 1;
 		WARP_SYNC();
 	}
+}
+
+// ---- warp-cooperative mem_sort_dedup_patch for long region lists (reads from repeats: hundreds of hits) -------------
+// The scalar procedure is two sorts around a sequential scan; run by one lane it costs ~n log n dependent steps on
+// 96-byte records, and repeat-derived reads call it with n ~ 500 once per extension and once per rescued hit.  Here:
+//   * both orders are computed by rank (n^2 / 32 comparisons per lane on a compact key array) and applied with one
+//     scatter.  When all keys are distinct every correct sort yields the same array, so the unstable introsort of
+//     the reference need not be imitated; EQUAL keys are detected while ranking and send the list to the scalar
+//     path (at that stage only), which reproduces the reference's tie order;
+//   * the redundancy scan only relates hits that lie within max_chain_gap of each other on one contig: the list,
+//     sorted by end position, falls into independent segments (repeat copies sit at unrelated loci, so segments are
+//     short) that the lanes scan concurrently, each with the scalar logic;
+//   * region patching (a banded global alignment between two colinear hits) stays on the scalar path: a dry pass over
+//     all pairs that could be examined detects candidates first.
+#define SDP_FAST_MIN 24
+#ifdef B200_SIM
+static long g_sim_sdp[5]; // kernel-debug harness only: calls, tie fallbacks (end), patch-candidate fallbacks, tie fallbacks (score), completed
+#define SDP_STAT(k) (++g_sim_sdp[k])
+#else
+#define SDP_STAT(k) ((void)0)
+#endif
+DEV bool patch_precheck(const DevIndex& x, const MemOpt& opt, const Reg& a, const Reg& b)
+{ // the tests of patch_reg that precede its alignment
+	if (a.rb < x.l_pac && b.rb >= x.l_pac) return false;
+	if (a.qb >= b.qb || a.qe >= b.qe || a.re >= b.re) return false;
+	int w = (int)((a.re - b.rb) - (a.qe - b.qb));
+	w = w > 0 ? w : -w;
+	double r = (double)(a.re - b.rb) / (double)(b.re - a.rb) - (double)(a.qe - b.qb) / (double)(b.qe - a.qb);
+	r = r > 0. ? r : -r;
+	if (a.re < b.rb || a.qe < b.qb) { if (w > opt.w << 1 || r >= (double)0.05f) return false; }
+	else if (w > opt.w << 2 || r >= (double)(0.05f * 2)) return false;
+	return true;
+}
+
+template <int W>
+DEVNI int warp_sort_dedup_fast(const DevIndex& x, const MemOpt& opt, WarpMem& wm, WarpScratch& ws, Counters* cnt, const u8* query, int n, Reg* a)
+{
+	if (W != 32 || n < SDP_FAST_MIN || n > ws.rt_cap || ws.rt == nullptr) return warp_sort_dedup_patch<W>(x, opt, wm, ws, cnt, query, n, a);
+	LANE_DECL;
+	SDP_STAT(0);
+	i64* key = ws.rkey; u32* rk = ws.rrank; Reg* t = ws.rt;
+	// ---- order by end position
+	FOR_LANES { for (int i = lane; i < n; i += W) key[i] = a[i].re; }
+	WARP_SYNC();
+	WV(bool, tie);
+	FOR_LANES {
+		bool tv = false;
+		for (int i = lane; i < n; i += W) {
+			const i64 ki = key[i];
+			u32 less = 0;
+			for (int j = 0; j < n; ++j) { const i64 kj = key[j]; less += kj < ki ? 1u : 0u; tv |= (kj == ki) & (j != i); }
+			rk[i] = less;
+		}
+		L_(tie) = tv;
+	}
+	if (wv_ballot(tie) != 0u) { SDP_STAT(1); return warp_sort_dedup_patch<W>(x, opt, wm, ws, cnt, query, n, a); } // equal keys: the scalar sort decides
+	FOR_LANES { for (int i = lane; i < n; i += W) { Reg r = a[i]; r.n_comp = 1; t[rk[i]] = r; } }
+	WARP_SYNC();
+	// ---- reach of every hit (lowest index its scan can touch) and patch candidates
+	WV(bool, cand);
+	FOR_LANES {
+		bool cv = false;
+		for (int i = lane; i < n; i += W) {
+			const Reg p = t[i];
+			int lo = i;
+			for (int j = i - 1; j >= 0 && p.rid == t[j].rid && p.rb < t[j].re + opt.max_chain_gap; --j) {
+				lo = j;
+				if (query != nullptr && t[j].rb < p.rb && patch_precheck(x, opt, t[j], p)) cv = true;
+			}
+			rk[i] = (u32)lo;
+		}
+		L_(cand) = cv;
+	}
+	const bool any_cand = wv_ballot(cand) != 0u;
+	FOR_LANES { for (int i = lane; i < n; i += W) a[i] = t[i]; } // a: sorted by end position, n_comp = 1
+	WARP_SYNC();
+	if (any_cand) { SDP_STAT(2); return warp_sort_dedup_patch<W>(x, opt, wm, ws, cnt, query, n, a, 1); }
+	// ---- segments: a boundary lies before i when no hit at or after i reaches below i (suffix minimum of the reaches)
+	int n_seg = 0;
+	u32* seg = (u32*)key; // segment start indices, ascending after the reversal below
+	LANE0_ONLY {
+		u32 mn = (u32)n;
+		int m = 0;
+		for (int i = n - 1; i >= 0; --i) { mn = rk[i] < mn ? rk[i] : mn; if (mn >= (u32)i) seg[m++] = (u32)i; }
+		for (int b = 0, e = m - 1; b < e; ++b, --e) { u32 tt = seg[b]; seg[b] = seg[e]; seg[e] = tt; }
+		seg[m] = (u32)n;
+		rk[0] = (u32)m; // (reaches are no longer needed)
+	}
+	WARP_SYNC();
+	{ WV(int, mv); FOR_LANES { L_(mv) = (int)rk[0]; } n_seg = wv_get(mv, 0); }
+	// ---- the redundancy scan, one lane per segment (scalar logic, no patching: no candidate exists)
+	FOR_LANES {
+		for (int sg = lane; sg < n_seg; sg += W) {
+			const int b = (int)seg[sg], e = (int)seg[sg + 1];
+			for (int i = b + 1; i < e; ++i) {
+				Reg p = a[i];
+				if (p.rid != a[i - 1].rid || p.rb >= a[i - 1].re + opt.max_chain_gap) continue;
+				for (int j = i - 1; j >= b && p.rid == a[j].rid && p.rb < a[j].re + opt.max_chain_gap; --j) {
+					const Reg q = a[j];
+					if (q.qe == q.qb) continue;
+					i64 or_ = q.re - p.rb;
+					i64 oq = q.qb < p.qb ? q.qe - p.qb : p.qe - q.qb;
+					i64 mr = q.re - q.rb < p.re - p.rb ? q.re - q.rb : p.re - p.rb;
+					i64 mq = q.qe - q.qb < p.qe - p.qb ? q.qe - q.qb : p.qe - p.qb;
+					if ((float)or_ > opt.mask_level_redun * (float)mr && (float)oq > opt.mask_level_redun * (float)mq) {
+						if (p.score < q.score) { a[i].qe = a[i].qb; break; }
+						else a[j].qe = a[j].qb;
+					}
+				}
+			}
+		}
+	}
+	WARP_SYNC();
+	// ---- survivors, compacted in order into t
+	int n2 = 0;
+	for (int i0 = 0; i0 < n; i0 += W) {
+		WV(bool, keep);
+		FOR_LANES { const int i = i0 + lane; L_(keep) = i < n && a[i].qe > a[i].qb; }
+		const u32 bm = wv_ballot(keep);
+		FOR_LANES { const int i = i0 + lane; if (i < n && ((bm >> lane) & 1u)) t[n2 + __popc(bm & ((1u << lane) - 1u))] = a[i]; }
+		n2 += __popc(bm);
+	}
+	WARP_SYNC();
+	// ---- order by (score desc, rb, qb); identical triples are the reference's duplicates -> scalar tail decides
+	FOR_LANES {
+		bool tv = false;
+		for (int i = lane; i < n2; i += W) {
+			const Reg ri = t[i];
+			u32 less = 0;
+			for (int j = 0; j < n2; ++j) {
+				const Reg& rj = t[j];
+				const bool lt = rj.score > ri.score || (rj.score == ri.score && (rj.rb < ri.rb || (rj.rb == ri.rb && rj.qb < ri.qb)));
+				less += lt ? 1u : 0u;
+				tv |= (rj.score == ri.score) & (rj.rb == ri.rb) & (rj.qb == ri.qb) & (j != i);
+			}
+			rk[i] = less;
+		}
+		L_(tie) = tv;
+	}
+	if (wv_ballot(tie) != 0u) { // (a still holds the scanned list: the scalar tail redoes the compaction itself)
+		SDP_STAT(3);
+		return warp_sort_dedup_patch<W>(x, opt, wm, ws, cnt, query, n, a, 2);
+	}
+	FOR_LANES { for (int i = lane; i < n2; i += W) a[rk[i]] = t[i]; }
+	WARP_SYNC();
+	SDP_STAT(4);
+	return n2;
 }

@@ -35,6 +35,8 @@ struct BatchParams {
 	i64* pe_cand;           // per pair
 	// mate rescue (rescue.cuh)
 	u32* nb; SwTask* sw_tasks; u8* sw_state; u32* sw_list; u32* sw_n_list; u32* max_nb; u32* multi; u32* n_multi; int round; int rescued;
+	u32* rs_heavy; u32* n_rs_heavy; // rescue replay by a warp (rescue.cuh rescue_is_heavy)
+	Reg* ws_rt; i64* ws_rkey; u32* ws_rrank; int ws_rt_cap; // per-warp region-list scratch (warp_sort_dedup_fast)
 	u8* spec_state; u32* spec_task; u32* n_reg0; int force_fb; // speculative rescue (rescue.cuh); multi / n_multi double as the fallback list
 	PeStat pes[4];
 	const double* pair_tab; i64 pair_tab_off[4];
@@ -149,6 +151,10 @@ DEV void make_warp_ctx(const BatchParams& P, i64 warp_slot, u8* smem, WarpMem& w
 	ws.xa = P.ws_xa + (size_t)warp_slot * P.ws_xa_cap; ws.xa_cap = P.ws_xa_cap;
 	ws.brow = P.ws_brow + (size_t)warp_slot * P.ws_brow_cap; ws.brow_cap = P.ws_brow_cap;
 	ws.err = P.err;
+	ws.rt_cap = P.ws_rt_cap;
+	ws.rt = P.ws_rt ? P.ws_rt + (size_t)warp_slot * P.ws_rt_cap : nullptr;
+	ws.rkey = P.ws_rkey ? P.ws_rkey + (size_t)warp_slot * (P.ws_rt_cap + 2) : nullptr;
+	ws.rrank = P.ws_rrank ? P.ws_rrank + (size_t)warp_slot * (P.ws_rt_cap + 2) : nullptr;
 }
 HOSTDEV size_t warp_smem_bytes(int cap) { return (size_t)(4 * (cap + 2) + 16) * 4 + (size_t)((cap + 2 + 15) & ~15); }
 
@@ -167,7 +173,7 @@ DEV void wbody_extend(const BatchParams& P, i64 r, WarpMem& wm, WarpScratch& ws)
 		const ChainK ck = P.ck[t0 + c];
 		warp_chain2aln<W>(P.x, P.opt, wm, ws, P.cnt, len, seq, ck, P.ks + t0 + ck.seed_start, P.srt + t0, av, &n_av, av_cap);
 	}
-	n_av = warp_sort_dedup_patch<W>(P.x, P.opt, wm, ws, P.cnt, seq, n_av, av);
+	n_av = warp_sort_dedup_fast<W>(P.x, P.opt, wm, ws, P.cnt, seq, n_av, av);
 	ONE_LANE { P.n_reg[r] = (u32)n_av; }
 }
 
@@ -209,6 +215,7 @@ DEV RescueIO make_rescue_io(const BatchParams& P)
 	io.snap = P.snap; io.nb = P.nb; io.tasks = P.sw_tasks; io.state = P.sw_state; io.list = P.sw_list; io.n_list = P.sw_n_list;
 	io.max_nb = P.max_nb; io.multi = P.multi; io.n_multi = P.n_multi; io.n_reads = P.n_units << 1; io.round = P.round;
 	io.spec_state = P.spec_state; io.spec_task = P.spec_task; io.n_reg0 = P.n_reg0; io.fb_list = P.multi; io.n_fb = P.n_multi; io.force_fb = P.force_fb;
+	io.hv_list = P.rs_heavy; io.n_hv = P.n_rs_heavy;
 	return io;
 }
 DEV void body_rescue_snap(const BatchParams& P, i64 r) { RescueIO io = make_rescue_io(P); rescue_snap(P.opt, io, r); }
@@ -221,7 +228,19 @@ DEV void body_rescue_apply_all(const BatchParams& P, i64 r)
 	RescueIO io = make_rescue_io(P);
 	WarpMem wm; memset(&wm, 0, sizeof(wm));
 	WarpScratch ws; memset(&ws, 0, sizeof(ws)); ws.err = P.err;
+	if (io.nb[r] == 0 || rescue_is_heavy(io, r)) return; // nothing to replay / replayed by a warp (wbody_rescue_apply_heavy)
 	if (!rescue_apply_all<1>(P.x, P.opt, P.pes, wm, ws, io, r)) { u32 slot = atomic_add_u32(io.n_fb, 1u); io.fb_list[slot] = (u32)r; }
+}
+DEV void body_rescue_classify(const BatchParams& P, i64 r) { RescueIO io = make_rescue_io(P); rescue_classify(io, r); }
+template <int W>
+DEV void wbody_rescue_apply_heavy(const BatchParams& P, i64 item, WarpMem& wm, WarpScratch& ws)
+{
+	LANE_DECL;
+	RescueIO io = make_rescue_io(P);
+	const i64 r = (i64)P.rs_heavy[item];
+	const bool ok = rescue_apply_all<W>(P.x, P.opt, P.pes, wm, ws, io, r);
+	if (!ok) { ONE_LANE { u32 slot = atomic_add_u32(io.n_fb, 1u); io.fb_list[slot] = (u32)r; } }
+	WARP_SYNC();
 }
 // round-by-round path: the mate's list of a queued read is put back to its pre-rescue state first
 DEV void body_rescue_fb_restore(const BatchParams& P, i64 i)
@@ -336,6 +355,7 @@ DEV void make_thread_ctx(const BatchParams& P, i64 tid, WarpMem& wm, WarpScratch
 	ws.md = (char*)b; ws.md_cap = P.t_md_cap; b += (P.t_md_cap + 15) & ~15;
 	ws.xa = (char*)b; ws.xa_cap = P.t_xa_cap;
 	ws.brow = nullptr; ws.brow_cap = 0;
+	ws.rt = nullptr; ws.rkey = nullptr; ws.rrank = nullptr; ws.rt_cap = 0;
 	ws.err = lerr; // limits hit here are not errors: the item is redone by a warp with the large scratch
 }
 // extension, thread per read (extend_thread.cuh): reads with few kept seeds are extended by one thread with its DP row

@@ -222,7 +222,10 @@ struct RescueIO {
 	int n_reads; int round;
 	// speculative pipeline: per snapshot slot (reg_off[r] + k) and orientation
 	u8* spec_state; u32* spec_task; u32* n_reg0; u32* fb_list; u32* n_fb; int force_fb;
+	u32* hv_list; u32* n_hv; // reads whose replay is done by a warp (long lists / several rescuing hits)
 };
+// replay by a warp (rescue_apply_all<32>, warp-cooperative de-duplication) instead of a thread?
+DEV bool rescue_is_heavy(const RescueIO& io, i64 r) { return io.nb[r] >= 2u || io.n_reg0[r ^ 1] >= (u32)SDP_FAST_MIN; }
 
 DEV void rescue_snap(const MemOpt& opt, const RescueIO& io, i64 r)
 {
@@ -235,6 +238,12 @@ DEV void rescue_snap(const MemOpt& opt, const RescueIO& io, i64 r)
 	if (m > opt.max_matesw) m = opt.max_matesw;
 	io.nb[r] = (u32)m;
 	if (m) atomic_max_u32(io.max_nb, (u32)m);
+}
+// second pass of the snapshot (needs nb and n_reg0 of both ends): queue the reads whose replay goes to a warp
+DEV void rescue_classify(const RescueIO& io, i64 r)
+{
+	if ((r | 1) >= io.n_reads || io.nb[r] == 0) return;
+	if (rescue_is_heavy(io, r)) { u32 slot = atomic_add_u32(io.n_hv, 1u); io.hv_list[slot] = (u32)r; }
 }
 
 // ---- gen: the skip test and the windows of mem_matesw for hit `round` of read r -----------------------
@@ -436,6 +445,7 @@ DEV void rescue_apply(const DevIndex& x, const MemOpt& opt, WarpMem& wm, WarpScr
 template <int W>
 DEV bool rescue_apply_all(const DevIndex& x, const MemOpt& opt, const PeStat* pes, WarpMem& wm, WarpScratch& ws, const RescueIO& io, i64 r)
 {
+	LANE_DECL;
 	const int nb = (int)io.nb[r];
 	if (nb == 0) return true;
 	const i64 m = r ^ 1;
@@ -464,12 +474,17 @@ DEV bool rescue_apply_all(const DevIndex& x, const MemOpt& opt, const PeStat* pe
 			if (skip[d]) continue;
 			if (state[d] == SW_RUN) {
 				const SwTask t = io.tasks[tix[d]];
-				if (!rescue_insert(opt, l_pac, a, t, l_ms, ma, &nm, ma_cap)) { atomic_or_u32(ws.err, ERR_REG_OVERFLOW); io.n_reg[m] = (u32)nm; return true; }
+				int nm2 = nm; bool room = true;
+				LANE0_ONLY { room = rescue_insert(opt, l_pac, a, t, l_ms, ma, &nm2, ma_cap); }
+				WARP_SYNC();
+				{ WV(int, nv); FOR_LANES { L_(nv) = room ? nm2 : -1; } nm2 = wv_get(nv, 0); }
+				if (nm2 < 0) { ONE_LANE { atomic_or_u32(ws.err, ERR_REG_OVERFLOW); io.n_reg[m] = (u32)nm; } return true; }
+				nm = nm2;
 				++n;
 			}
-			if (n) nm = warp_sort_dedup_patch<W>(x, opt, wm, ws, nullptr, nullptr, nm, ma);
+			if (n) nm = warp_sort_dedup_fast<W>(x, opt, wm, ws, nullptr, nullptr, nm, ma);
 		}
 	}
-	io.n_reg[m] = (u32)nm;
+	ONE_LANE { io.n_reg[m] = (u32)nm; }
 	return ok && !io.force_fb;
 }

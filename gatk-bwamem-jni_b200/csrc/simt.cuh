@@ -94,6 +94,7 @@ DEV u32 atomic_add_u32(u32* p, u32 v) { u32 o = *p; *p += v; return o; }
 DEV u32 atomic_or_u32(u32* p, u32 v) { u32 o = *p; *p |= v; return o; }
 DEV u32 atomic_max_u32(u32* p, u32 v) { u32 o = *p; if (v > o) *p = v; return o; }
 DEV int __ffs(u32 x) { return x ? __builtin_ctz(x) + 1 : 0; }
+DEV int __popc(u32 x) { return __builtin_popcount(x); }
 DEV int __clz(u32 x) { return x ? __builtin_clz(x) : 32; }
 #endif
 

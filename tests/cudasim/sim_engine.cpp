@@ -59,5 +59,6 @@ void* sim_createAlignments(void* h, void* opt, void* pes, char* blob, size_t* si
 void sim_free(void* p) { free(p); }
 void* sim_opt_init() { return default_options(); }
 void* sim_getRefContigNames(void* h, size_t* size) { return contig_names_blob(((Engine*)h)->img, size); }
+void sim_sdp_stats(long* out) { memcpy(out, g_sim_sdp, sizeof g_sim_sdp); }
 void sim_last_counters(void* h, uint64_t* out) { memcpy(out, &((Engine*)h)->last_counters, sizeof(Counters)); }
 }
