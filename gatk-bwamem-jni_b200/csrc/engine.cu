@@ -154,6 +154,8 @@ DEF_THREAD_KERNEL(body_rescue_apply_multi)
 DEF_WARP_KERNEL_DEVN(wbody_rescue_sw)
 DEF_WARP_KERNEL(wbody_extend)
 DEF_THREAD_QUEUE_KERNEL(body_extend_q)
+DEF_THREAD_QUEUE_KERNEL(body_extend_task_q)
+DEF_WARP_KERNEL_DEVN(wbody_heavy_prep)
 DEF_WARP_KERNEL_DEVN(wbody_extend_heavy)
 DEF_THREAD_KERNEL(body_save_regs)
 DEF_THREAD_TID_KERNEL(body_final_pe_t)

@@ -126,7 +126,7 @@ struct Engine {
 	// batch workspace
 	DBuf b_blob, b_seq, b_seqoff, b_intv, b_nintv, b_nseed, b_smem, b_seedoff, b_rbeg, b_S, b_C, b_ord, b_tmp32, b_ck, b_ks, b_srt, b_regtmp,
 	     b_nck, b_nks, b_nreg, b_regcap, b_regoff, b_regs, b_snap, b_ztmp, b_pairv, b_recs, b_nrec, b_cand, b_pairtab, b_var, b_misc,
-	     b_outwords, b_outoff, b_out, b_wsz, b_wscig, b_wsmd, b_wsxa, b_wsbrow, b_nb, b_swtask, b_swstate, b_swlist, b_tbuf, b_redo, b_heavy, b_multi, b_cand2, b_specstate, b_spectask, b_nreg0, b_rsheavy, b_wsrt, b_wsrkey, b_wsrrank;
+	     b_outwords, b_outoff, b_out, b_wsz, b_wscig, b_wsmd, b_wsxa, b_wsbrow, b_nb, b_swtask, b_swstate, b_swlist, b_tbuf, b_redo, b_heavy, b_multi, b_cand2, b_specstate, b_spectask, b_nreg0, b_rsheavy, b_wsrt, b_wsrkey, b_wsrrank, b_exttask, b_extres, b_ckrmax;
 	Counters last_counters; uint64_t last_n_seed = 0; int n_launches = 0;
 	std::string last_error;
 
@@ -187,7 +187,7 @@ inline void Engine::close_all()
 	DBuf* all[] = { &d_bwt, &d_sa, &d_pac, &d_ctg, &d_log, &d_names, &d_name_off, &b_blob, &b_seq, &b_seqoff, &b_intv, &b_nintv, &b_nseed, &b_smem,
 	                &b_seedoff, &b_rbeg, &b_S, &b_C, &b_ord, &b_tmp32, &b_ck, &b_ks, &b_srt, &b_regtmp, &b_nck, &b_nks, &b_nreg, &b_regcap, &b_regoff,
 	                &b_regs, &b_snap, &b_ztmp, &b_pairv, &b_recs, &b_nrec, &b_cand, &b_pairtab, &b_var, &b_misc, &b_outwords, &b_outoff, &b_out,
-	                &b_wsz, &b_wscig, &b_wsmd, &b_wsxa, &b_wsbrow, &b_nb, &b_swtask, &b_swstate, &b_swlist, &b_tbuf, &b_redo, &b_heavy, &b_multi, &b_cand2, &b_specstate, &b_spectask, &b_nreg0, &b_rsheavy, &b_wsrt, &b_wsrkey, &b_wsrrank };
+	                &b_wsz, &b_wscig, &b_wsmd, &b_wsxa, &b_wsbrow, &b_nb, &b_swtask, &b_swstate, &b_swlist, &b_tbuf, &b_redo, &b_heavy, &b_multi, &b_cand2, &b_specstate, &b_spectask, &b_nreg0, &b_rsheavy, &b_wsrt, &b_wsrkey, &b_wsrrank, &b_exttask, &b_extres, &b_ckrmax };
 	for (DBuf* b : all) b->release();
 	if (map) munmap(map, map_len);
 	map = nullptr;
@@ -356,7 +356,19 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 		else {
 			P.t_ext_rw = rw;
 			RT_THREADS_QUEUE_SMEM(body_extend_q, P, (int64_t)n_reads, thread_ext_smem_bytes(THREADS_PER_BLOCK, rw, wm_cap));
-			RT_WARPS_DEVN(wbody_extend_heavy, P, P.n_heavy, (int64_t)n_reads);
+			if (getenv("B200_NO_EXT_TASKS")) RT_WARPS_DEVN(wbody_extend_heavy, P, P.n_heavy, (int64_t)n_reads); // each heavy read extended by its own warp
+			else {
+				// heavy reads: every kept seed becomes an extension task for the thread-level queue, then a warp per read
+				// replays the containment decisions over the finished extensions and de-duplicates the regions
+				size_t Tn = (size_t)T + 1;
+				if (!(b_exttask.ensure(Tn * sizeof(ExtTask)) && b_extres.ensure(Tn * sizeof(ExtRes)) && b_ckrmax.ensure(Tn * 16))) { last_error = "device allocation failed (extension tasks)"; return nullptr; }
+				P.ext_tasks = b_exttask.as<ExtTask>(); P.ext_res = b_extres.as<ExtRes>(); P.ck_rmax = b_ckrmax.as<i64>(); P.n_ext_tasks = b_misc.as<u32>() + 21;
+				RT_WARPS_DEVN(wbody_heavy_prep, P, P.n_heavy, (int64_t)n_reads);
+				RT_THREADS_QUEUE_SMEM(body_extend_task_q, P, (int64_t)T, thread_ext_smem_bytes(THREADS_PER_BLOCK, rw, wm_cap));
+				P.use_ext_res = 1;
+				RT_WARPS_DEVN(wbody_extend_heavy, P, P.n_heavy, (int64_t)n_reads);
+				P.use_ext_res = 0;
+			}
 		}
 	}
 	// ---- paired-end: insert-size statistics (the one batch-global step; host)

@@ -21,6 +21,10 @@ struct WarpScratch { // per-warp global scratch
 };
 
 
+// Result of one seed of a heavy read extended ahead of time (extend_thread.cuh, task mode; consumed by warp_chain2aln)
+struct ExtRes { i64 rb, re; i32 qb, qe, score, truesc, w, valid; };
+struct ExtTask { u32 r, c, t, pad_; }; // read, chain index within the read, seed index within the chain
+
 struct Counters { u64 cells_ext, cells_glb, cells_msw, n_ext, n_glb, n_msw; };
 
 DEV int cal_max_gap(const MemOpt& opt, int qlen)
@@ -222,7 +226,7 @@ DEVNI int warp_sort_dedup_patch(const DevIndex& x, const MemOpt& opt, WarpMem& w
 // mem_chain2aln for one chain; av[0..*n_av) accumulates the regions of the read
 template <int W>
 DEVNI void warp_chain2aln(const DevIndex& x, const MemOpt& opt, WarpMem& wm, WarpScratch& ws, Counters* cnt, int l_query, const u8* query,
-                          const ChainK& c, const Seed* seeds, u64* srt, Reg* av, int* n_av, int av_cap)
+                          const ChainK& c, const Seed* seeds, u64* srt, Reg* av, int* n_av, int av_cap, const ExtRes* spec = nullptr)
 {
 	LANE_DECL;
 	const i64 l_pac = x.l_pac;
@@ -277,6 +281,11 @@ DEVNI void warp_chain2aln(const DevIndex& x, const MemOpt& opt, WarpMem& wm, War
 		memset(&a, 0, sizeof(Reg));
 		int aw0 = opt.w, aw1 = opt.w;
 		a.w = opt.w; a.score = a.truesc = -1; a.rid = c.rid;
+		const ExtRes* pre = spec ? spec + (u32)srt[k] : nullptr;
+		if (pre && pre->valid == 1) { // extended ahead of time by the task kernel (extend_thread.cuh)
+			a.rb = pre->rb; a.re = pre->re; a.qb = pre->qb; a.qe = pre->qe; a.score = pre->score; a.truesc = pre->truesc;
+			aw0 = aw1 = pre->w;
+		} else {
 		if (s.qbeg) { // left extension: both sequences reversed
 			FOR_LANES { for (int j = lane; j < s.qbeg; j += W) WQ(wm, j) = query[s.qbeg - 1 - j]; }
 			WARP_SYNC();
@@ -313,6 +322,7 @@ DEVNI void warp_chain2aln(const DevIndex& x, const MemOpt& opt, WarpMem& wm, War
 			if (er.gscore <= 0 || er.gscore <= a.score - opt.pen_clip3) { a.qe = qe + er.qle; a.re = re + er.tle; a.truesc += a.score - sc0; }
 			else { a.qe = l_query; a.re = re + er.gtle; a.truesc += er.gscore - sc0; }
 		} else { a.qe = l_query; a.re = s.rbeg + s.len; }
+		}
 		a.seedcov = 0;
 		for (i = 0; i < cn; ++i) {
 			const Seed& t = seeds[i];

@@ -38,6 +38,12 @@ DEV bool tx_all_done(bool done) { return done; }
 // Extends reads taken from `counter` until the batch is exhausted.  Every lane of the warp must call this (the loop
 // votes with the full mask).  Reads with many kept seeds, and reads that do not fit the thread-level rows, are queued
 // on the heavy list for the warp-per-read kernel.
+//
+// TASKS = true: the work items are single seeds of heavy reads (ExtTask list written by wbody_heavy_prep): a read from
+// a repeat family has hundreds of chains, and extending them one after the other in one thread or warp leaves the
+// rest of the GPU waiting for it.  Every seed is extended unconditionally (its result does not depend on the hits
+// found so far; only the decision to USE it does -- the containment test is replayed by wbody_extend_heavy).
+template <bool TASKS>
 DEV void thread_extend_queue(const BatchParams& P, i64 n_reads, u32* counter, const ThreadExtMem& tm, WarpMem& wm, WarpScratch& ws, u32* lerr)
 {
 	const DevIndex& x = P.x; const MemOpt& opt = P.opt; Counters* cnt = P.cnt; u32* err = P.err;
@@ -53,7 +59,9 @@ DEV void thread_extend_queue(const BatchParams& P, i64 n_reads, u32* counter, co
 
 	int phase = TX_FETCH, n_av = 0;
 	bool in_ext = false, done = false;
-#define TX_TO_WARP() do { u32 slot_ = atomic_add_u32(P.n_heavy, 1u); P.heavy_list[slot_] = (u32)r; phase = TX_FETCH; } while (0)
+	u64 res_slot = 0; // task mode: where the result goes
+#define TX_TO_WARP() do { if (TASKS) P.ext_res[res_slot].valid = 0; /* the replay extends this seed itself */ \
+		else { u32 slot_ = atomic_add_u32(P.n_heavy, 1u); P.heavy_list[slot_] = (u32)r; } phase = TX_FETCH; } while (0)
 	int c = -1, k = -1, cn = 0;
 	const Seed* seeds = nullptr; ChainK ck; ck.n_seeds = 0; ck.seed_start = 0; ck.rid = 0; ck.frac_rep = 0.f;
 	i64 rmax0 = 0, rmax1 = 0;
@@ -72,6 +80,33 @@ DEV void thread_extend_queue(const BatchParams& P, i64 n_reads, u32* counter, co
 		while (!in_ext && !done) {
 			switch (phase) {
 			case TX_FETCH: {
+				if (TASKS) {
+					const i64 tid = (i64)atomic_add_u32(counter, 1u);
+					if (tid >= n_reads) { done = true; break; }
+					const ExtTask tk = P.ext_tasks[tid];
+					r = (i64)tk.r;
+					const u64 t0 = P.seed_off[r];
+					ck = P.ck[t0 + tk.c];
+					res_slot = t0 + ck.seed_start + tk.t;
+					l_query = (int)(P.seq_off[r + 1] - P.seq_off[r] - 1);
+					query = P.seq + P.seq_off[r];
+					if (l_query > tm.rd_cap || (i64)2 * l_query * mx + opt.pen_clip5 + opt.pen_clip3 > 60000) { TX_TO_WARP(); break; }
+					for (int j = 0; j < l_query; ++j) tm.rd[(size_t)j * QS] = query[j];
+					seeds = P.ks + t0 + ck.seed_start; cn = 0; // (seed coverage is computed by the replay)
+					s = seeds[tk.t];
+					rmax0 = P.ck_rmax[2 * (t0 + tk.c)]; rmax1 = P.ck_rmax[2 * (t0 + tk.c) + 1];
+					memset(&a, 0, sizeof(Reg));
+					aw0 = aw1 = opt.w;
+					a.w = opt.w; a.score = a.truesc = -1; a.rid = ck.rid;
+					if (s.qbeg) {
+						side = 0; tr = 0;
+						qlen = s.qbeg; qbase = s.qbeg - 1; qdir = -1;
+						tbase = s.rbeg - 1; tdir = -1; tlen = (int)(s.rbeg - rmax0);
+						end_bonus = opt.pen_clip5; h0 = s.len * opt.a;
+						phase = TX_EXT_START;
+					} else { a.score = a.truesc = s.len * opt.a; a.qb = 0; a.rb = s.rbeg; phase = TX_RIGHT_CHECK; }
+					break;
+				}
 				r = (i64)atomic_add_u32(counter, 1u);
 				if (r >= n_reads) { done = true; break; }
 				nck = (int)P.n_ck[r];
@@ -206,6 +241,12 @@ DEV void thread_extend_queue(const BatchParams& P, i64 n_reads, u32* counter, co
 				}
 				break; }
 			case TX_FINISH_SEED: {
+				if (TASKS) {
+					ExtRes o; o.rb = a.rb; o.re = a.re; o.qb = a.qb; o.qe = a.qe; o.score = a.score; o.truesc = a.truesc; o.w = aw0 > aw1 ? aw0 : aw1; o.valid = 1;
+					P.ext_res[res_slot] = o;
+					phase = TX_FETCH;
+					break;
+				}
 				a.seedcov = 0;
 				for (int t = 0; t < cn; ++t) {
 					const Seed& u = seeds[t];

@@ -51,6 +51,8 @@ struct BatchParams {
 	u8* t_buf; size_t t_stride; int t_z_cap, t_cigar_cap, t_md_cap, t_xa_cap;
 	u32* redo_list; u32* n_redo; // items a thread-level kernel handed over to the warp-level kernel
 	u32* heavy_list; u32* n_heavy; int light_max_seeds, light_max_chains; // extension: reads with many seeds go to the warp-level kernel
+	ExtTask* ext_tasks; u32* n_ext_tasks; ExtRes* ext_res; i64* ck_rmax; // heavy reads: per-seed extension tasks, results, per-chain windows
+	int use_ext_res;        // wbody_extend consumes ext_res (set for the replay launch of the heavy reads only)
 	int t_ext_rw;           // thread-level extension: shared-memory words per thread (DP row, doubling as the two NW rings)
 	u64 rowpack[5];         // byte c of rowpack[t] = mat[t*5 + c] (score of query code c against target base t)
 	u32* err; Counters* cnt; u32* work_counter;
@@ -171,7 +173,8 @@ DEV void wbody_extend(const BatchParams& P, i64 r, WarpMem& wm, WarpScratch& ws)
 	if (len > wm.cap) { if (nck) { ONE_LANE { atomic_or_u32(P.err, ERR_QLEN_OVERFLOW); } } nck = 0; }
 	for (int c = 0; c < nck; ++c) {
 		const ChainK ck = P.ck[t0 + c];
-		warp_chain2aln<W>(P.x, P.opt, wm, ws, P.cnt, len, seq, ck, P.ks + t0 + ck.seed_start, P.srt + t0, av, &n_av, av_cap);
+		warp_chain2aln<W>(P.x, P.opt, wm, ws, P.cnt, len, seq, ck, P.ks + t0 + ck.seed_start, P.srt + t0, av, &n_av, av_cap,
+		                  P.use_ext_res ? P.ext_res + t0 + ck.seed_start : nullptr);
 	}
 	n_av = warp_sort_dedup_fast<W>(P.x, P.opt, wm, ws, P.cnt, seq, n_av, av);
 	ONE_LANE { P.n_reg[r] = (u32)n_av; }
@@ -387,7 +390,50 @@ DEV void body_extend_q(const BatchParams& P, i64 n, u32* counter, i64 tid)
 {
 	u32 lerr = 0;
 	ThreadExtMem tm; WarpMem wm; WarpScratch ws; make_thread_ext_ctx(P, tid, tm, wm, ws, &lerr);
-	thread_extend_queue(P, n, counter, tm, wm, ws, &lerr);
+	thread_extend_queue<false>(P, n, counter, tm, wm, ws, &lerr);
+}
+// heavy reads, step 1 (warp per read): the reference window of every chain and one extension task per kept seed
+template <int W>
+DEV void wbody_heavy_prep(const BatchParams& P, i64 item, WarpMem& wm, WarpScratch& ws)
+{
+	LANE_DECL;
+	(void)wm; (void)ws;
+	const i64 r = (i64)P.heavy_list[item];
+	const u64 t0 = P.seed_off[r];
+	const int nck = (int)P.n_ck[r];
+	const int l_query = (int)(P.seq_off[r + 1] - P.seq_off[r] - 1);
+	const i64 l_pac = P.x.l_pac;
+	FOR_LANES {
+		for (int c = lane; c < nck; c += W) {
+			const ChainK ck = P.ck[t0 + c];
+			const int cn = (int)ck.n_seeds;
+			if (cn == 0) continue;
+			const Seed* seeds = P.ks + t0 + ck.seed_start;
+			i64 rmax0 = l_pac << 1, rmax1 = 0;
+			for (int t = 0; t < cn; ++t) {
+				const Seed& sd = seeds[t];
+				i64 b = sd.rbeg - (sd.qbeg + cal_max_gap(P.opt, sd.qbeg));
+				i64 e = sd.rbeg + sd.len + ((l_query - sd.qbeg - sd.len) + cal_max_gap(P.opt, l_query - sd.qbeg - sd.len));
+				rmax0 = rmax0 < b ? rmax0 : b;
+				rmax1 = rmax1 > e ? rmax1 : e;
+			}
+			rmax0 = rmax0 > 0 ? rmax0 : 0;
+			rmax1 = rmax1 < l_pac << 1 ? rmax1 : l_pac << 1;
+			if (rmax0 < l_pac && l_pac < rmax1) { if (seeds[0].rbeg < l_pac) rmax1 = l_pac; else rmax0 = l_pac; }
+			ref_clip_window(P.x, rmax0, seeds[0].rbeg, rmax1);
+			P.ck_rmax[2 * (t0 + c)] = rmax0; P.ck_rmax[2 * (t0 + c) + 1] = rmax1;
+			const u32 base = atomic_add_u32(P.n_ext_tasks, (u32)cn);
+			for (int t = 0; t < cn; ++t) { ExtTask tk; tk.r = (u32)r; tk.c = (u32)c; tk.t = (u32)t; tk.pad_ = 0; P.ext_tasks[base + t] = tk; }
+		}
+	}
+}
+// heavy reads, step 2 (queue of single-seed tasks, thread-level DP)
+DEV void body_extend_task_q(const BatchParams& P, i64 n, u32* counter, i64 tid)
+{
+	(void)n;
+	u32 lerr = 0;
+	ThreadExtMem tm; WarpMem wm; WarpScratch ws; make_thread_ext_ctx(P, tid, tm, wm, ws, &lerr);
+	thread_extend_queue<true>(P, (i64)*P.n_ext_tasks, counter, tm, wm, ws, &lerr);
 }
 template <int W>
 DEV void wbody_extend_heavy(const BatchParams& P, i64 item, WarpMem& wm, WarpScratch& ws) { wbody_extend<W>(P, (i64)P.heavy_list[item], wm, ws); }
