@@ -269,12 +269,22 @@ def main():
     value = world * args.pairs * args.steps / t_dev
 
     # ---- end-to-end leg: host blob in -> host record stream out through jnibwa_createAlignments
-    e2e_t = []
+    # (the C-ABI call itself, as the JNI shim makes it: the read blob sits in a host buffer owned by the caller -- the
+    # direct ByteBuffer of BwaMemAligner.java:203-210 -- and the result is a malloc'd host buffer the caller frees)
+    dll.jnibwa_createAlignments.restype = ctypes.c_void_p
+    dll.jnibwa_createAlignments.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_size_t)]
+    dll.jnibwa_free.argtypes = [ctypes.c_void_p]
+    host_blobs = [ctypes.create_string_buffer(b, len(b)) for b in blobs]
+    checksum = 0
     for s in range(args.warmup + args.steps):
         if s == args.warmup:
             barrier(world); torch.cuda.synchronize()
             t0 = time.perf_counter()
-        out = idx.doAlignment(bytearray(blobs[s % n_distinct]), al._opts_addr, None)
+        size = ctypes.c_size_t(0)
+        res = dll.jnibwa_createAlignments(h, al._opts_addr, None, ctypes.cast(host_blobs[s % n_distinct], ctypes.c_void_p), ctypes.byref(size))
+        assert res and size.value > 0, "createAlignments failed"
+        checksum ^= ctypes.c_int32.from_address(res + size.value - 4).value  # the result is host memory: touch its last word
+        dll.jnibwa_free(res)
     torch.cuda.synchronize()
     t_e2e = allreduce_max(time.perf_counter() - t0, world)
     e2e = world * args.pairs * args.steps / t_e2e

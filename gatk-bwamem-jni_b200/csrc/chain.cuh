@@ -163,3 +163,154 @@ DEV int chain_read(const DevIndex& x, const MemOpt& opt, int len, ChainStageIO& 
 	*n_kept_seeds = n_seed_out;
 	return n_out;
 }
+
+// ---- the same procedure for reads with very many seeds, one warp per read -------------------------------------------
+// A read from a repeat family brings ~10^3 seeds that form ~10^3 single-seed chains, all overlapping on the query.
+// Two steps of the scalar formulation are then quadratic for a single thread: keeping the chain starts sorted
+// (insertion = a shift of the order array) and the filter's scan of every chain against all chains kept so far.
+// Here the order of evaluation -- and therefore every result -- is unchanged, but the shift and the scan are spread
+// over the 32 lanes: a scan step evaluates 32 kept chains at once, the first lane (in list order) that demands a
+// break wins, and only chains at or before it receive the side effects the scalar loop would have applied.
+struct ChainWarpScratch { i64* pos_sorted; u64* qbw; }; // per seed slot: start of the chain at each sorted position; (w<<32 | qe<<16 | qb) per chain in weight order
+
+template <int W>
+DEVNI int chain_read_warp(const DevIndex& x, const MemOpt& opt, int len, ChainStageIO& io, ChainWarpScratch& cs, int* n_kept_seeds)
+{
+	LANE_DECL;
+	*n_kept_seeds = 0;
+	if (len < opt.min_seed_len) return 0;
+	Seed* S = io.S; ChainW* C = io.C; u32* ord = io.ord; i64* ps = cs.pos_sorted;
+	int nch = 0, si = 0;
+	int b = 0, e = 0, l_rep = 0;
+	for (int i = 0; i < io.n_intv; ++i) {
+		const Intv& p = io.intv[i];
+		if (p.size <= (u64)opt.max_occ) continue;
+		int sb = (int)p.beg, se = (int)p.end;
+		if (sb > e) { l_rep += e - b; b = sb; e = se; }
+		else e = e > se ? e : se;
+	}
+	l_rep += e - b;
+	for (int i = 0; i < io.n_intv; ++i) {
+		const Intv p = io.intv[i];
+		int slen = (int)(p.end - p.beg);
+		i64 step = p.size > (u64)opt.max_occ ? (i64)(p.size / (u64)opt.max_occ) : 1;
+		int count = 0;
+		for (i64 k = 0; (u64)k < p.size && count < opt.max_occ; k += step, ++count) {
+			int sidx = si++;
+			Seed s; s.rbeg = io.sd_rbeg[sidx]; s.qbeg = (i32)p.beg; s.len = s.score = slen; s.next = -1;
+			ONE_LANE { S[sidx] = s; }
+			WARP_SYNC();
+			int rid = ref_intv2rid(x, s.rbeg, s.rbeg + s.len);
+			if (rid < 0) continue;
+			bool to_add = true; int at = 0;
+			if (nch) {
+				int lo = 0, hi = nch;
+				while (lo < hi) { int mid = (lo + hi) >> 1; if (ps[mid] < s.rbeg) lo = mid + 1; else hi = mid; }
+				int lower = -1;
+				if (lo < nch && ps[lo] == s.rbeg) { lower = (int)ord[lo]; at = lo + 1; }
+				else if (lo > 0) { lower = (int)ord[lo - 1]; at = lo; }
+				else at = 0;
+				if (lower >= 0) {
+					int merged = 0;
+					LANE0_ONLY { merged = chain_test_and_merge(opt, x.l_pac, C[lower], S, sidx, rid) ? 1 : 0; }
+					WARP_SYNC();
+					{ WV(int, mv); FOR_LANES { L_(mv) = merged; } merged = wv_get(mv, 0); }
+					if (merged) to_add = false;
+				}
+			}
+			if (to_add) {
+				ONE_LANE { ChainW c; c.pos = s.rbeg; c.head = c.tail = sidx; c.n = 1; c.rid = rid; c.w = 0; c.kept = 0; c.first = -1; C[nch] = c; }
+				// shift [at, nch) up by one, highest chunk first
+				for (int hi2 = nch; hi2 > at; hi2 -= W) {
+					WV(u32, to); WV(i64, tp);
+					FOR_LANES { int j = hi2 - 1 - lane; if (j >= at) { L_(to) = ord[j]; L_(tp) = ps[j]; } }
+					WARP_SYNC();
+					FOR_LANES { int j = hi2 - 1 - lane; if (j >= at) { ord[j + 1] = L_(to); ps[j + 1] = L_(tp); } }
+					WARP_SYNC();
+				}
+				ONE_LANE { ord[at] = (u32)nch; ps[at] = s.rbeg; }
+				WARP_SYNC();
+				++nch;
+			}
+		}
+	}
+	if (nch == 0) return 0;
+	float frac_rep = (float)l_rep / len;
+	// ---- weights (a lane per chain), then the chains that pass min_chain_weight, in start order
+	FOR_LANES { for (int i = lane; i < nch; i += W) { ChainW& c = C[i]; c.first = -1; c.kept = 0; c.w = (u32)chain_weight(c, S); } }
+	WARP_SYNC();
+	int n = 0;
+	LANE0_ONLY { for (int i = 0; i < nch; ++i) if ((int)C[ord[i]].w >= opt.min_chain_weight) ord[n++] = ord[i]; }
+	WARP_SYNC();
+	{ WV(int, nv); FOR_LANES { L_(nv) = n; } n = wv_get(nv, 0); }
+	if (n == 0) return 0;
+	LANE0_ONLY { ChainLtW lt; lt.C = C; ks_introsort<u32, ChainLtW>((size_t)n, ord, lt); }
+	WARP_SYNC();
+	u64* qbw = cs.qbw;
+	FOR_LANES {
+		for (int i = lane; i < n; i += W) {
+			const ChainW& c = C[ord[i]];
+			const u32 qb = (u32)S[c.head].qbeg, qe = (u32)(S[c.tail].qbeg + S[c.tail].len);
+			qbw[i] = (u64)c.w << 32 | (u64)(qe & 0xffffu) << 16 | (u64)(qb & 0xffffu);
+		}
+	}
+	WARP_SYNC();
+	u32* kl = io.tmp; int nk = 0;
+	ONE_LANE { C[ord[0]].kept = 3; kl[0] = 0; }
+	WARP_SYNC();
+	nk = 1;
+	for (int i = 1; i < n; ++i) {
+		const u64 vi = qbw[i];
+		const int ib = (int)(vi & 0xffffu), ie = (int)(vi >> 16 & 0xffffu), wi = (int)(vi >> 32);
+		bool large_ovlp = false, broke = false;
+		for (int k0 = 0; k0 < nk && !broke; k0 += W) {
+			WV(bool, ov); WV(bool, dr);
+			FOR_LANES {
+				const int k = k0 + lane;
+				bool o = false, d = false;
+				if (k < nk) {
+					const u64 vj = qbw[kl[k]];
+					const int jb = (int)(vj & 0xffffu), je = (int)(vj >> 16 & 0xffffu), wj = (int)(vj >> 32);
+					const int b_max = jb > ib ? jb : ib, e_min = je < ie ? je : ie;
+					if (e_min > b_max) {
+						const int li = ie - ib, lj = je - jb, min_l = li < lj ? li : lj;
+						if ((float)(e_min - b_max) >= (float)min_l * opt.mask_level && min_l < opt.max_chain_gap) {
+							o = true;
+							d = (float)wi < (float)wj * opt.drop_ratio && wj - wi >= opt.min_seed_len << 1;
+						}
+					}
+				}
+				L_(ov) = o; L_(dr) = d;
+			}
+			const u32 om = wv_ballot(ov), dm = wv_ballot(dr);
+			u32 eff = om; // lanes whose side effects the scalar loop would have applied
+			if (dm) { const int fb = __ffs(dm) - 1; eff = om & (fb == 31 ? 0xffffffffu : ((2u << fb) - 1u)); broke = true; }
+			if (eff) large_ovlp = true;
+			FOR_LANES { if ((eff >> lane) & 1u) { ChainW& cj = C[ord[kl[k0 + lane]]]; if (cj.first < 0) cj.first = i; } }
+			WARP_SYNC();
+		}
+		if (!broke) { ONE_LANE { kl[nk] = (u32)i; C[ord[i]].kept = large_ovlp ? 2 : 3; } WARP_SYNC(); ++nk; }
+	}
+	int n_out = 0, n_seed_out = 0;
+	LANE0_ONLY {
+		for (int i = 0; i < nk; ++i) { ChainW& c = C[ord[kl[i]]]; if (c.first >= 0) C[ord[c.first]].kept = 1; }
+		int i, k;
+		for (i = k = 0; i < n; ++i) {
+			int kept = C[ord[i]].kept;
+			if (kept == 0 || kept == 3) continue;
+			if (++k >= opt.max_chain_extend) break;
+		}
+		for (; i < n; ++i) if (C[ord[i]].kept < 3) C[ord[i]].kept = 0;
+		for (i = 0; i < n; ++i) {
+			ChainW& c = C[ord[i]];
+			if (c.kept == 0) continue;
+			ChainK o; o.seed_start = (u32)n_seed_out; o.n_seeds = (u32)c.n; o.rid = c.rid; o.frac_rep = frac_rep; o.w = c.w; o.kept = c.kept; o.pos = c.pos;
+			for (int j = c.head; j >= 0; j = S[j].next) { Seed sd = S[j]; sd.next = -1; io.ks[n_seed_out++] = sd; }
+			io.ck[n_out++] = o;
+		}
+	}
+	WARP_SYNC();
+	{ WV(int, a1); WV(int, a2); FOR_LANES { L_(a1) = n_out; L_(a2) = n_seed_out; } n_out = wv_get(a1, 0); n_seed_out = wv_get(a2, 0); }
+	*n_kept_seeds = n_seed_out;
+	return n_out;
+}

@@ -133,9 +133,13 @@ static void rt_sort_u64(const uint64_t* in, uint64_t* out, uint64_t n)
 		} }
 
 DEF_THREAD_KERNEL(body_encode)
-DEF_THREAD_TID_KERNEL(body_seed)
+#ifndef SEED_MIN_BLOCKS
+#define SEED_MIN_BLOCKS 5
+#endif
+__global__ void __launch_bounds__(THREADS_PER_BLOCK, SEED_MIN_BLOCKS) k_body_seed_q(const __grid_constant__ BatchParams P, i64 n, u32* counter) { body_seed_q(P, n, counter, (i64)blockIdx.x * blockDim.x + threadIdx.x); }
 DEF_THREAD_KERNEL(body_sal)
 DEF_THREAD_KERNEL(body_chain)
+DEF_WARP_KERNEL_DEVN(wbody_chain_heavy)
 DEF_THREAD_KERNEL(body_pe_cand)
 DEF_THREAD_KERNEL(body_reg_cap)
 DEF_THREAD_KERNEL(body_compact)
@@ -206,12 +210,6 @@ static int g_launches = 0;
 #define RT_THREADS_TID(body, P, n) do { i64 n_ = (i64)(n); if (n_ > 0) { \
 	i64 nb_ = (n_ + THREADS_PER_BLOCK - 1) / THREADS_PER_BLOCK; i64 cap_ = (i64)rt_sm_count() * SEED_BLOCKS_PER_SM; if (nb_ > cap_) nb_ = cap_; \
 	k_##body<<<(unsigned)nb_, THREADS_PER_BLOCK, 0, rt_stream()>>>(P, n_); ++g_launches; } g_timer.mark(#body); } while (0)
-// the seeding kernel: shared-memory candidate lists and read rows (kernels.cuh body_seed)
-#define RT_THREADS_SEED(body, P, n, max_len) do { i64 n_ = (i64)(n); if (n_ > 0) { \
-	i64 nb_ = (n_ + THREADS_PER_BLOCK - 1) / THREADS_PER_BLOCK; i64 cap_ = (i64)rt_sm_count() * SEED_BLOCKS_PER_SM; if (nb_ > cap_) nb_ = cap_; \
-	size_t tsm_ = (P).seed_shared ? seed_block_smem_bytes(THREADS_PER_BLOCK, (max_len)) : 0; \
-	cudaFuncSetAttribute(k_##body, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm_); \
-	k_##body<<<(unsigned)nb_, THREADS_PER_BLOCK, tsm_, rt_stream()>>>(P, n_); ++g_launches; } g_timer.mark(#body); } while (0)
 // thread kernels whose threads use the shared-memory rings (make_thread_ctx)
 #define RT_THREADS_TID_RING(body, P, n) do { i64 n_ = (i64)(n); if (n_ > 0) { \
 	i64 nb_ = (n_ + THREADS_PER_BLOCK - 1) / THREADS_PER_BLOCK; i64 cap_ = (i64)rt_sm_count() * SEED_BLOCKS_PER_SM; if (nb_ > cap_) nb_ = cap_; \
@@ -236,6 +234,12 @@ static int g_launches = 0;
 	i64 nb_ = (i64)rt_sm_count() * WARP_BLOCKS_PER_SM; \
 	cudaFuncSetAttribute(k_##wbody, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_); \
 	k_##wbody<<<(unsigned)nb_, WARPS_PER_BLOCK * 32, sm_, rt_stream()>>>(P, n_ptr, next_counter()); ++g_launches; g_timer.mark(#wbody); } while (0)
+
+__global__ void k_relayout(const u32* src, u64 bwt_size, u32* dst, u64 n_blocks)
+{
+	for (u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x; b < n_blocks; b += (u64)gridDim.x * blockDim.x) fm_relayout_block(src, bwt_size, dst, b);
+}
+#define RT_RELAYOUT(src, size, dst, nb) do { k_relayout<<<(unsigned)(rt_sm_count() * 16), 256, 0, rt_stream()>>>((src), (size), (dst), (nb)); cu_ok(cudaGetLastError(), "relayout"); } while (0)
 
 static void rt_timer_begin() { g_timer.begin(); g_launches = 0; }
 

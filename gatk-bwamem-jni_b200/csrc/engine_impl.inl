@@ -126,7 +126,7 @@ struct Engine {
 	// batch workspace
 	DBuf b_blob, b_seq, b_seqoff, b_intv, b_nintv, b_nseed, b_smem, b_seedoff, b_rbeg, b_S, b_C, b_ord, b_tmp32, b_ck, b_ks, b_srt, b_regtmp,
 	     b_nck, b_nks, b_nreg, b_regcap, b_regoff, b_regs, b_snap, b_ztmp, b_pairv, b_recs, b_nrec, b_cand, b_pairtab, b_var, b_misc,
-	     b_outwords, b_outoff, b_out, b_wsz, b_wscig, b_wsmd, b_wsxa, b_wsbrow, b_nb, b_swtask, b_swstate, b_swlist, b_tbuf, b_redo, b_heavy, b_multi, b_cand2, b_specstate, b_spectask, b_nreg0, b_rsheavy, b_wsrt, b_wsrkey, b_wsrrank, b_exttask, b_extres, b_ckrmax;
+	     b_outwords, b_outoff, b_out, b_wsz, b_wscig, b_wsmd, b_wsxa, b_wsbrow, b_nb, b_swtask, b_swstate, b_swlist, b_tbuf, b_redo, b_heavy, b_multi, b_cand2, b_specstate, b_spectask, b_nreg0, b_rsheavy, b_wsrt, b_wsrkey, b_wsrrank, b_exttask, b_extres, b_ckrmax, b_chainheavy;
 	Counters last_counters; uint64_t last_n_seed = 0; int n_launches = 0;
 	std::string last_error;
 
@@ -157,8 +157,17 @@ inline bool Engine::open_from_fd(int fd)
 inline bool Engine::upload()
 {
 	size_t bwt_bytes = (size_t)img.bwt_size * 4;
-	if (!d_bwt.ensure(bwt_bytes + 64) || !d_sa.ensure((size_t)img.n_sa * 8) || !d_pac.ensure((size_t)(img.l_pac / 4 + 1) + 16)) { last_error = "device allocation failed"; return false; }
-	rt_h2d(d_bwt.p, img.bwt, bwt_bytes);
+	const uint64_t n_blocks = (img.seq_len + 127) / 128;
+	{ // the occ-interleaved BWT goes up as it is in the image, then every 64-byte block is re-laid out for the device
+	  // (symbols as two bit-planes, fm.cuh); the staging copy is released
+		DBuf raw;
+		if (!raw.ensure(bwt_bytes + 64) || !d_bwt.ensure((size_t)n_blocks * 64 + 64)) { raw.release(); last_error = "device allocation failed"; return false; }
+		rt_h2d(raw.p, img.bwt, bwt_bytes);
+		RT_RELAYOUT((const u32*)raw.p, (u64)img.bwt_size, (u32*)d_bwt.p, n_blocks);
+		rt_sync();
+		raw.release();
+	}
+	if (!d_sa.ensure((size_t)img.n_sa * 8) || !d_pac.ensure((size_t)(img.l_pac / 4 + 1) + 16)) { last_error = "device allocation failed"; return false; }
 	rt_h2d(d_sa.p, img.sa, (size_t)img.n_sa * 8);
 	rt_h2d(d_pac.p, img.pac, (size_t)(img.l_pac / 4 + 1));
 	std::vector<int64_t> off((size_t)img.n_seqs + 1);
@@ -187,7 +196,7 @@ inline void Engine::close_all()
 	DBuf* all[] = { &d_bwt, &d_sa, &d_pac, &d_ctg, &d_log, &d_names, &d_name_off, &b_blob, &b_seq, &b_seqoff, &b_intv, &b_nintv, &b_nseed, &b_smem,
 	                &b_seedoff, &b_rbeg, &b_S, &b_C, &b_ord, &b_tmp32, &b_ck, &b_ks, &b_srt, &b_regtmp, &b_nck, &b_nks, &b_nreg, &b_regcap, &b_regoff,
 	                &b_regs, &b_snap, &b_ztmp, &b_pairv, &b_recs, &b_nrec, &b_cand, &b_pairtab, &b_var, &b_misc, &b_outwords, &b_outoff, &b_out,
-	                &b_wsz, &b_wscig, &b_wsmd, &b_wsxa, &b_wsbrow, &b_nb, &b_swtask, &b_swstate, &b_swlist, &b_tbuf, &b_redo, &b_heavy, &b_multi, &b_cand2, &b_specstate, &b_spectask, &b_nreg0, &b_rsheavy, &b_wsrt, &b_wsrkey, &b_wsrrank, &b_exttask, &b_extres, &b_ckrmax };
+	                &b_wsz, &b_wscig, &b_wsmd, &b_wsxa, &b_wsbrow, &b_nb, &b_swtask, &b_swstate, &b_swlist, &b_tbuf, &b_redo, &b_heavy, &b_multi, &b_cand2, &b_specstate, &b_spectask, &b_nreg0, &b_rsheavy, &b_wsrt, &b_wsrkey, &b_wsrrank, &b_exttask, &b_extres, &b_ckrmax, &b_chainheavy };
 	for (DBuf* b : all) b->release();
 	if (map) munmap(map, map_len);
 	map = nullptr;
@@ -293,7 +302,10 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 
 	// ---- stage 1: encode + seed
 	RT_THREADS(body_encode, P, (int64_t)blob_len);
-	RT_THREADS_SEED(body_seed, P, (int64_t)n_reads, max_len);
+	P.seed_lcap = 8; P.seed_shared_read = 0; // few candidates survive per position; the read is walked sequentially (L1)
+	if (getenv("B200_SEED_LCAP")) { int v = atoi(getenv("B200_SEED_LCAP")); if (v >= 1 && v <= SEED_LCAP) P.seed_lcap = v; } // tuning aids
+	if (getenv("B200_SEED_SHARED_READ")) P.seed_shared_read = atoi(getenv("B200_SEED_SHARED_READ"));
+	RT_THREADS_QUEUE_SMEM(body_seed_q, P, (int64_t)n_reads, P.seed_shared ? seed_block_smem_bytes(THREADS_PER_BLOCK, max_len, P.seed_lcap, P.seed_shared_read) : 0);
 	g_hp.mark("launch1");
 	uint64_t T = rt_scan_u32(P.n_seed, P.seed_off, n_reads);
 	g_hp.mark("seed_sync");
@@ -308,7 +320,11 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 	P.ck = b_ck.as<ChainK>(); P.ks = b_ks.as<Seed>(); P.srt = b_srt.as<u64>(); P.regs_tmp = b_regtmp.as<Reg>();
 	// ---- stage 2: SA lookups, chaining
 	RT_THREADS(body_sal, P, (int64_t)T);
+	if (!b_chainheavy.ensure(((size_t)n_reads + 1) * 4)) { last_error = "device allocation failed"; return nullptr; }
+	P.chain_heavy = b_chainheavy.as<u32>(); P.n_chain_heavy = b_misc.as<u32>() + 22;
+	P.chain_heavy_seeds = getenv("B200_TEST_CHAIN_ALL_WARP") ? -1 : (getenv("B200_TEST_CHAIN_ALL_THREAD") ? (1 << 30) : CHAIN_HEAVY_SEEDS);
 	RT_THREADS(body_chain, P, (int64_t)n_reads);
+	RT_WARPS_DEVN(wbody_chain_heavy, P, P.n_chain_heavy, (int64_t)n_reads);
 	// ---- warp scratch
 	{
 		const int L = max_len > 0 ? max_len : 1;

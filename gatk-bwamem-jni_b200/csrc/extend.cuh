@@ -163,11 +163,6 @@ struct RegLtEnd { DEVM bool operator()(const Reg& a, const Reg& b) const { retur
 struct RegLtScore { DEVM bool operator()(const Reg& a, const Reg& b) const { return a.score > b.score || (a.score == b.score && (a.rb < b.rb || (a.rb == b.rb && a.qb < b.qb))); } };
 struct RegLtHash { DEVM bool operator()(const Reg& a, const Reg& b) const { return a.score > b.score || (a.score == b.score && (a.is_alt < b.is_alt || (a.is_alt == b.is_alt && a.hash < b.hash))); } };
 
-#ifndef B200_SIM
-#define LANE0_ONLY wsync_<W>(); if (lane == 0)
-#else
-#define LANE0_ONLY
-#endif
 
 // mem_sort_dedup_patch; query == nullptr disables patching (the mate-rescue call sites)
 // stage: 0 = the whole procedure; 1 = the list is already sorted by end position (n_comp set); 2 = only the tail

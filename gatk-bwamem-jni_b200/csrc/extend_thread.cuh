@@ -29,11 +29,7 @@ struct ThreadExtMem {
 
 enum { TX_FETCH, TX_NEXT_CHAIN, TX_NEXT_SEED, TX_EXT_START, TX_EXT_DONE, TX_RIGHT_CHECK, TX_FINISH_SEED, TX_READ_DONE };
 
-#ifndef B200_SIM
-DEV bool tx_all_done(bool done) { return __all_sync(FULLMASK, done) != 0; }
-#else
-DEV bool tx_all_done(bool done) { return done; }
-#endif
+DEV bool tx_all_done(bool done) { return lanes_all(done); }
 
 // Extends reads taken from `counter` until the batch is exhausted.  Every lane of the warp must call this (the loop
 // votes with the full mask).  Reads with many kept seeds, and reads that do not fit the thread-level rows, are queued

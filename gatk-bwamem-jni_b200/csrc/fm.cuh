@@ -8,6 +8,12 @@
 // One occurrence block is 64 bytes = two 32-byte sectors: sector 0 holds the four u64 base counts,
 // sector 1 the 128 two-bit symbols.  A lookup is four 128-bit read-only loads of one aligned block
 // (algorithmic traffic: 64 B per block touch).
+//
+// Device layout of sector 1 (re-laid out once at upload by fm_relayout_block; counts, block index arithmetic and
+// every result are unchanged): the 128 symbols are stored as two BIT-PLANES -- words 8..11 hold the low bits
+// (symbol j at bit j & 31 of word 8 + (j >> 5)), words 12..15 the high bits.  Counting the symbols before an offset
+// then needs one position mask per 32 symbols shared by three population counts (low, high, both) instead of
+// 64-bit shift/mask/popcount sequences over interleaved pairs: ~3x fewer instructions per lookup.
 #pragma once
 #include "types.cuh"
 
@@ -21,22 +27,36 @@ DEV OccBlock load_block(const DevIndex& x, u64 blk)
 	return b;
 }
 
+// image layout -> device layout for block b (src: the image's occ-interleaved BWT of bwt_size words; dst: n_blocks * 16 words)
+DEV void fm_relayout_block(const u32* src, u64 bwt_size, u32* dst, u64 b)
+{
+	const u64 base = b << 4;
+	u32 w[16];
+	for (int t = 0; t < 16; ++t) w[t] = base + t < bwt_size ? src[base + t] : 0u;
+	u32 p0[4] = { 0, 0, 0, 0 }, p1[4] = { 0, 0, 0, 0 };
+	for (int j = 0; j < 128; ++j) {
+		const u32 sym = w[8 + (j >> 4)] >> ((15 - (j & 15)) << 1) & 3u;
+		p0[j >> 5] |= (sym & 1u) << (j & 31);
+		p1[j >> 5] |= (sym >> 1) << (j & 31);
+	}
+	for (int t = 0; t < 8; ++t) dst[base + t] = w[t];
+	for (int t = 0; t < 4; ++t) { dst[base + 8 + t] = p0[t]; dst[base + 12 + t] = p1[t]; }
+}
+
 // Occurrences of A,C,G,T in packed-BWT positions [0, kk] given the block that holds kk.  Branch-free: every lane runs
-// the same twelve population counts whatever its offset in the block, so the lanes of a warp stay together (the
-// data-dependent "how many words to count" branches of a word-at-a-time formulation split a warp four ways).
-// Symbols past the offset are masked to 00 (= A) and never counted; A is what remains of n.
+// the same twelve population counts whatever its offset in the block.  Symbols past the offset are masked out of both
+// planes (= A) and never counted; A is what remains of n.
 DEV void occ4_in_block(const OccBlock& b, u64 kk, u64 cnt[4])
 {
 	const int n = (int)(kk & 127) + 1; // 1..128 symbols of this block
-	const u64 y[4] = { (u64)b.s0.x << 32 | b.s0.y, (u64)b.s0.z << 32 | b.s0.w, (u64)b.s1.x << 32 | b.s1.y, (u64)b.s1.z << 32 | b.s1.w };
+	const u32 p0[4] = { b.s0.x, b.s0.y, b.s0.z, b.s0.w }, p1[4] = { b.s1.x, b.s1.y, b.s1.z, b.s1.w };
 	u32 sLo = 0, sHi = 0, sT = 0;
 #pragma unroll
 	for (int w = 0; w < 4; ++w) {
-		int nn = n - 32 * w; nn = nn < 0 ? 0 : (nn > 32 ? 32 : nn);
-		const u64 mask = nn == 0 ? 0ull : (~0ull << ((32 - nn) << 1)); // first symbol sits in the top bits
-		const u64 v = y[w] & mask;
-		const u64 lo = v & 0x5555555555555555ull, hi = (v >> 1) & 0x5555555555555555ull;
-		sLo += (u32)popc64(lo); sHi += (u32)popc64(hi); sT += (u32)popc64(lo & hi);
+		const int nn = n - 32 * w;
+		const u32 m = nn >= 32 ? 0xffffffffu : (nn > 0 ? (1u << nn) - 1u : 0u);
+		const u32 lo = p0[w] & m, hi = p1[w] & m;
+		sLo += (u32)__popc(lo); sHi += (u32)__popc(hi); sT += (u32)__popc(lo & hi);
 	}
 	const u32 cC = sLo - sT, cG = sHi - sT, cT = sT;
 	cnt[0] = ((u64)b.c01.x | (u64)b.c01.y << 32) + (u64)((u32)n - cC - cG - cT);
@@ -85,6 +105,36 @@ DEV void fm_extend(const DevIndex& x, const BiIntv& ik, BiIntv ok[4], int is_bac
 	else { ok[3].x0 = o3; ok[2].x0 = o2; ok[1].x0 = o1; ok[0].x0 = o0; }
 }
 
+// bwt_extend for ONE base c (the only one a caller ever consumes): no per-base arrays, so nothing is spilled to local
+// memory by lane-varying indexing.  The complementary coordinate needs the sizes of the bases above c only.
+DEV BiIntv fm_extend1(const DevIndex& x, const BiIntv& ik, int c, int is_back)
+{
+	u64 tk[4], tl[4];
+	const u64 a0 = is_back ? ik.x0 : ik.x1, oth = is_back ? ik.x1 : ik.x0, s = ik.size;
+	const u64 k = a0 - 1, l = a0 - 1 + s;
+	{
+		const bool kz = k == ~0ull, lz = l == ~0ull;
+		const u64 k_ = kz ? 0 : k - (k >= x.primary), l_ = lz ? 0 : l - (l >= x.primary);
+		OccBlock bk = load_block(x, k_ >> 7);
+		OccBlock bl = load_block(x, l_ >> 7);
+		occ4_in_block(bk, k_, tk);
+		occ4_in_block(bl, l_, tl);
+		if (kz) { tk[0] = tk[1] = tk[2] = tk[3] = 0; }
+		if (lz) { tl[0] = tl[1] = tl[2] = tl[3] = 0; }
+	}
+	const u64 s1 = tl[1] - tk[1], s2 = tl[2] - tk[2], s3 = tl[3] - tk[3];
+	const u64 kc = c == 0 ? tk[0] : c == 1 ? tk[1] : c == 2 ? tk[2] : tk[3];
+	const u64 lc = c == 0 ? tl[0] : c == 1 ? tl[1] : c == 2 ? tl[2] : tl[3];
+	const u64 L2c = c == 0 ? x.L2[0] : c == 1 ? x.L2[1] : c == 2 ? x.L2[2] : x.L2[3];
+	const u64 above = (c < 3 ? s3 : 0) + (c < 2 ? s2 : 0) + (c < 1 ? s1 : 0);
+	const u64 v = L2c + 1 + kc;
+	const u64 o = oth + ((a0 <= x.primary && a0 + s - 1 >= x.primary) ? 1 : 0) + above;
+	BiIntv r;
+	r.size = lc - kc;
+	if (is_back) { r.x0 = v; r.x1 = o; } else { r.x1 = v; r.x0 = o; }
+	return r;
+}
+
 DEV void fm_set_intv(const DevIndex& x, int c, BiIntv& ik)
 {
 	ik.x0 = x.L2[c] + 1; ik.size = x.L2[c + 1] - x.L2[c]; ik.x1 = x.L2[3 - c] + 1;
@@ -129,22 +179,25 @@ DEV void cand_get(const SeedWork& w, int k, BiIntv& b, u32& end)
 // warp meet at the same fm_extend (two occurrence-block fetches, the expensive part) and consume its result.
 // The backward phase compacts the candidate list in place: row i reads candidate j and writes at most j survivors, so
 // the "previous" and "current" lists of the textbook formulation share one array.
-enum { SM_NEXT_R1, SM_FWD, SM_BWD_ROW, SM_BWD_ITEM, SM_NEXT_R2, SM_NEXT_R3, SM_S3, SM_DONE };
+enum { SM_NEXT_R1, SM_FWD, SM_BWD_ROW, SM_BWD_ITEM, SM_NEXT_R2, SM_NEXT_R3, SM_S3, SM_DONE, SM_FETCH, SM_ALLDONE };
 enum { SMX_NONE, SMX_FWD, SMX_BWD, SMX_S3 };
 
 DEV void intv_set(Intv& t, const BiIntv& b, u32 beg, u32 end) { t.x0 = b.x0; t.x1 = b.x1; t.size = b.size; t.beg = beg; t.end = end; }
 
-DEV void fm_collect_intv(const DevIndex& x, const MemOpt& opt, int len, const u8* qg, const SeedWork& wk, IntvOut& o)
+// Reads are not assigned to lanes statically: `src.next` hands the lane its next read (a batch-wide counter), fetching is
+// one more state of the machine, and a full-mask vote per trip is both the exit test and the point where the lanes
+// of the warp meet again -- no lane idles while a neighbour works through a read with more extensions.
+template <class Src>
+DEV void fm_collect_queue(const DevIndex& x, const MemOpt& opt, const SeedWork& wk, Src& src)
 {
 	const int split_len = (int)(opt.min_seed_len * opt.split_factor + .499);
 	const int min_seed_len = opt.min_seed_len;
 	const int lcap_all = wk.lcap + wk.gcap;
-	o.n = 0; o.overflow = false;
-	// the read's codes: shared copy when provided
-	const u8* q = qg; size_t qst = 1;
-	if (wk.qs) { for (int t = 0; t < len; ++t) wk.qs[(size_t)t * wk.qstride] = qg[t]; q = wk.qs; qst = (size_t)wk.qstride; }
+	IntvOut o; o.v = nullptr; o.n = 0; o.cap = 0; o.overflow = false;
+	int len = 0; const u8* qg = nullptr;
+	const u8* q = nullptr; size_t qst = 1;
 #define Q(i_) q[(size_t)(i_) * qst]
-	int st = SM_NEXT_R1, round = 1, pend = SMX_NONE;
+	int st = SM_FETCH, round = 1, pend = SMX_NONE;
 	int xx = 0;                 // rounds 1 and 3: next start position
 	int k2 = 0, old_n = 0;      // round 2: cursor over the round-1 SMEMs
 	int start = 0, i = 0, ret = 0, c = -1, j = 0, first_out = 0;
@@ -152,8 +205,8 @@ DEV void fm_collect_intv(const DevIndex& x, const MemOpt& opt, int len, const u8
 	BiIntv ik, ext, pcur; u32 ik_end = 0, pcur_end = 0;
 	int n_prev = 0, n_curr = 0;
 	u32 last_beg = 0; bool have_out = false;
-	BiIntv ok[4];
-	ik.x0 = ik.x1 = ik.size = 0; ext = ik; pcur = ik;
+	BiIntv okc; int ext_c = 0;
+	ik.x0 = ik.x1 = ik.size = 0; ext = ik; pcur = ik; okc = ik;
 #define SM_PUSH(bi, e) do { if (n_curr < lcap_all) { cand_set(wk, n_curr, bi, e); ++n_curr; } else o.overflow = true; } while (0)
 #define SM_END_FORWARD() do { \
 		for (int a_ = 0; a_ < n_curr >> 1; ++a_) { /* longest match first */ \
@@ -164,9 +217,30 @@ DEV void fm_collect_intv(const DevIndex& x, const MemOpt& opt, int len, const u8
 #define SM_EMIT_PCUR() do { if (n_curr == 0 && (!have_out || (u32)(i + 1) < last_beg)) { \
 		Intv t_; intv_set(t_, pcur, (u32)(i + 1), pcur_end); have_out = true; last_beg = t_.beg; out_push(o, t_); } } while (0)
 	for (;;) {
-		// ---- advance to the next extension (or to the end of the read)
-		while (pend == SMX_NONE && st != SM_DONE) {
+		// ---- advance to the next extension (or to the end of the batch)
+		while (pend == SMX_NONE && st != SM_ALLDONE) {
 			switch (st) {
+			case SM_FETCH:
+				if (!src.next(len, qg, o)) { st = SM_ALLDONE; break; }
+				// the read's codes: shared copy when provided
+				q = qg; qst = 1;
+				if (wk.qs) { for (int t = 0; t < len; ++t) wk.qs[(size_t)t * wk.qstride] = qg[t]; q = wk.qs; qst = (size_t)wk.qstride; }
+				o.n = 0; o.overflow = false;
+				round = 1; xx = 0; k2 = 0; old_n = 0; n_prev = n_curr = 0; have_out = false; last_beg = 0;
+				st = SM_NEXT_R1;
+				break;
+			case SM_DONE: { // the read is finished: order its intervals by (beg, end) and hand them over
+				// Equal keys are identical intervals, so the sort algorithm is unobservable here (unlike the hazard-H4 sorts).
+				for (int a = 1; a < o.n; ++a) {
+					Intv t = o.v[a];
+					u64 key = (u64)t.beg << 32 | t.end;
+					int b = a - 1;
+					while (b >= 0 && ((u64)o.v[b].beg << 32 | o.v[b].end) > key) { o.v[b + 1] = o.v[b]; --b; }
+					o.v[b + 1] = t;
+				}
+				src.finish(o);
+				st = SM_FETCH;
+				break; }
 			case SM_NEXT_R1:
 				while (xx < len && Q(xx) > 3) ++xx;
 				if (xx >= len) { old_n = o.n; k2 = 0; round = 2; st = SM_NEXT_R2; break; }
@@ -189,7 +263,7 @@ DEV void fm_collect_intv(const DevIndex& x, const MemOpt& opt, int len, const u8
 				st = SM_FWD;
 				break; }
 			case SM_FWD: // forward phase: record the interval at every change of size
-				if (i < len && Q(i) < 4) { ext = ik; pend = SMX_FWD; break; }
+				if (i < len && Q(i) < 4) { ext = ik; ext_c = 3 - Q(i); pend = SMX_FWD; break; }
 				SM_PUSH(ik, ik_end); // i == len, or an ambiguous base ends the match
 				SM_END_FORWARD();
 				break;
@@ -208,7 +282,7 @@ DEV void fm_collect_intv(const DevIndex& x, const MemOpt& opt, int len, const u8
 					break;
 				}
 				cand_get(wk, j, pcur, pcur_end);
-				if (c >= 0) { ext = pcur; pend = SMX_BWD; break; }
+				if (c >= 0) { ext = pcur; ext_c = c; pend = SMX_BWD; break; }
 				SM_EMIT_PCUR(); // no base to extend with: the candidate cannot grow
 				++j;
 				break;
@@ -229,35 +303,34 @@ DEV void fm_collect_intv(const DevIndex& x, const MemOpt& opt, int len, const u8
 			case SM_S3: // bwt_seed_strategy1: shortest forward match of >= min_seed_len+1 bases with < max_mem_intv occurrences
 				if (i >= len) { xx = len; st = SM_NEXT_R3; break; }
 				if (Q(i) > 3) { xx = i + 1; st = SM_NEXT_R3; break; }
-				ext = ik; pend = SMX_S3;
+				ext = ik; ext_c = 3 - Q(i); pend = SMX_S3;
 				break;
 			default: st = SM_DONE; break;
 			}
 		}
-		if (st == SM_DONE && pend == SMX_NONE) break;
+		if (lanes_all(st == SM_ALLDONE)) break;
+		if (pend == SMX_NONE) continue; // (this lane has run out of reads; its neighbours have not)
 		// ---- the one place where the index is read
-		fm_extend(x, ext, ok, pend == SMX_BWD ? 1 : 0);
+		okc = fm_extend1(x, ext, ext_c, pend == SMX_BWD ? 1 : 0);
 		// ---- consume
 		if (pend == SMX_FWD) {
-			const int cc = 3 - Q(i);
 			bool stop = false;
-			if (ok[cc].size != ik.size) {
+			if (okc.size != ik.size) {
 				SM_PUSH(ik, ik_end);
-				if (ok[cc].size < min_intv) stop = true;
+				if (okc.size < min_intv) stop = true;
 			}
-			if (!stop) { ik = ok[cc]; ik_end = (u32)(i + 1); ++i; st = SM_FWD; }
+			if (!stop) { ik = okc; ik_end = (u32)(i + 1); ++i; st = SM_FWD; }
 			else SM_END_FORWARD(); // (no second push: the scan ended before i == len)
 		} else if (pend == SMX_BWD) {
-			if (ok[c].size < min_intv) SM_EMIT_PCUR();
-			else if (n_curr == 0 || ok[c].size != last_size) { cand_set(wk, n_curr, ok[c], pcur_end); ++n_curr; last_size = ok[c].size; } // n_curr <= j
+			if (okc.size < min_intv) SM_EMIT_PCUR();
+			else if (n_curr == 0 || okc.size != last_size) { cand_set(wk, n_curr, okc, pcur_end); ++n_curr; last_size = okc.size; } // n_curr <= j
 			++j;
 			st = SM_BWD_ITEM;
 		} else { // SMX_S3
-			const int cc = 3 - Q(i);
-			if (ok[cc].size < opt.max_mem_intv && i - start >= min_seed_len) {
-				if (ok[cc].size > 0) { Intv m; intv_set(m, ok[cc], (u32)start, (u32)(i + 1)); out_push(o, m); }
+			if (okc.size < opt.max_mem_intv && i - start >= min_seed_len) {
+				if (okc.size > 0) { Intv m; intv_set(m, okc, (u32)start, (u32)(i + 1)); out_push(o, m); }
 				xx = i + 1; st = SM_NEXT_R3;
-			} else { ik = ok[cc]; ++i; st = SM_S3; }
+			} else { ik = okc; ++i; st = SM_S3; }
 		}
 		pend = SMX_NONE;
 	}
@@ -265,15 +338,6 @@ DEV void fm_collect_intv(const DevIndex& x, const MemOpt& opt, int len, const u8
 #undef SM_END_FORWARD
 #undef SM_EMIT_PCUR
 #undef Q
-	// ordered by (beg, end).  Equal keys are identical intervals, so the sort algorithm is unobservable here (unlike
-	// the hazard-H4 sorts) and a plain insertion sort is used.
-	for (int a = 1; a < o.n; ++a) {
-		Intv t = o.v[a];
-		u64 key = (u64)t.beg << 32 | t.end;
-		int b = a - 1;
-		while (b >= 0 && ((u64)o.v[b].beg << 32 | o.v[b].end) > key) { o.v[b + 1] = o.v[b]; --b; }
-		o.v[b + 1] = t;
-	}
 }
 
 // ---- suffix-array resolution ----------------------------------------------------------------------
@@ -287,10 +351,10 @@ DEV u64 fm_sa(const DevIndex& x, u64 k)
 		if (k == x.primary) { k = 0; continue; }
 		u64 kk = k - (k > x.primary); // position of this row's symbol in the packed BWT
 		OccBlock b = load_block(x, kk >> 7);
-		u32 wsel = (u32)(kk & 127) >> 4;
-		u32 wd = wsel < 4 ? (wsel == 0 ? b.s0.x : wsel == 1 ? b.s0.y : wsel == 2 ? b.s0.z : b.s0.w)
-		                  : (wsel == 4 ? b.s1.x : wsel == 5 ? b.s1.y : wsel == 6 ? b.s1.z : b.s1.w);
-		int c = (int)(wd >> ((15 - (kk & 15)) << 1) & 3);
+		const u32 wsel = (u32)(kk & 127) >> 5, bit = (u32)(kk & 31);
+		const u32 lo = wsel == 0 ? b.s0.x : wsel == 1 ? b.s0.y : wsel == 2 ? b.s0.z : b.s0.w;
+		const u32 hi = wsel == 0 ? b.s1.x : wsel == 1 ? b.s1.y : wsel == 2 ? b.s1.z : b.s1.w;
+		int c = (int)((lo >> bit & 1u) | (hi >> bit & 1u) << 1);
 		// occ(k, c) counts rows [0,k]; k > primary maps to packed position k-1 == kk, k < primary to k == kk
 		u64 cnt[4];
 		occ4_in_block(b, kk, cnt);

@@ -23,7 +23,8 @@ struct BatchParams {
 	// seeding
 	Intv* intv; int intv_cap; u32* n_intv; u32* n_seed; // per read
 	Intv* smem_scratch; int smem_cap;                  // per thread: smem_cap spill entries of the candidate list
-	int seed_shared;                                    // candidate list + read codes in shared memory (fm.cuh SeedWork)
+	int seed_shared;                                    // candidate list (+ read codes) in shared memory (fm.cuh SeedWork)
+	int seed_lcap, seed_shared_read;                    // shared candidates per thread; whether the read's codes are staged in shared memory too
 	u64* seed_off;          // n_reads+1 (exclusive scan of n_seed)
 	u64 n_seed_total;
 	i64* sd_rbeg;           // [T]
@@ -52,6 +53,7 @@ struct BatchParams {
 	u32* redo_list; u32* n_redo; // items a thread-level kernel handed over to the warp-level kernel
 	u32* heavy_list; u32* n_heavy; int light_max_seeds, light_max_chains; // extension: reads with many seeds go to the warp-level kernel
 	ExtTask* ext_tasks; u32* n_ext_tasks; ExtRes* ext_res; i64* ck_rmax; // heavy reads: per-seed extension tasks, results, per-chain windows
+	u32* chain_heavy; u32* n_chain_heavy; int chain_heavy_seeds; // reads chained by a warp
 	int use_ext_res;        // wbody_extend consumes ext_res (set for the replay launch of the heavy reads only)
 	int t_ext_rw;           // thread-level extension: shared-memory words per thread (DP row, doubling as the two NW rings)
 	u64 rowpack[5];         // byte c of rowpack[t] = mat[t*5 + c] (score of query code c against target base t)
@@ -70,38 +72,52 @@ DEV void body_encode(const BatchParams& P, i64 i) { P.seq[i] = nt4_of(P.blob[i])
 
 // ---- seed: one thread per read -------------------------------------------------------------------
 #define SEED_LCAP 16   // candidates per thread kept in shared memory (16 bytes each); the rest spill to the global pool
-HOSTDEV size_t seed_block_smem_bytes(int block_threads, int max_len) { return (size_t)block_threads * (SEED_LCAP * 16 + (size_t)((max_len + 1 + 3) & ~3)); }
+HOSTDEV size_t seed_block_smem_bytes(int block_threads, int max_len, int lcap, int with_read) { return (size_t)block_threads * ((size_t)lcap * 16 + (with_read ? (size_t)((max_len + 1 + 3) & ~3) : 0)); }
 #ifdef B200_SIM
 static uint4 g_sim_seed_l[SEED_LCAP];
 #endif
-DEV void body_seed(const BatchParams& P, i64 r, i64 tid)
-{
-	const u8* seq = P.seq + P.seq_off[r];
-	int len = (int)(P.seq_off[r + 1] - P.seq_off[r] - 1);
-	IntvOut o; o.v = P.intv + (size_t)r * P.intv_cap; o.n = 0; o.cap = P.intv_cap; o.overflow = false;
-	u32 ns = 0;
-	if (len >= P.opt.min_seed_len) {
-		if (len > P.smem_cap) { atomic_or_u32(P.err, ERR_QLEN_OVERFLOW); }
-		else {
-			SeedWork wk;
-			wk.G = P.smem_scratch + (size_t)tid * P.smem_cap; wk.gcap = P.smem_cap;
-			wk.L = nullptr; wk.lstride = 0; wk.lcap = 0; wk.qs = nullptr; wk.qstride = 0;
-			if (P.seed_shared) { // packed shared-memory working set (reads of <= 255 bases, |T| < 2^40)
-#ifdef B200_SIM
-				wk.L = g_sim_seed_l; wk.lstride = 1; wk.lcap = SEED_LCAP;
-#else
-				extern __shared__ __align__(16) u8 tsm_[];
-				wk.L = (uint4*)tsm_ + threadIdx.x; wk.lstride = (int)blockDim.x; wk.lcap = SEED_LCAP;
-				wk.qs = tsm_ + (size_t)blockDim.x * SEED_LCAP * 16 + threadIdx.x; wk.qstride = (int)blockDim.x;
-#endif
-			}
-			fm_collect_intv(P.x, P.opt, len, seq, wk, o);
-			if (o.overflow) atomic_or_u32(P.err, ERR_INTV_OVERFLOW);
-			for (int i = 0; i < o.n; ++i) ns += (u32)(o.v[i].size < (u64)P.opt.max_occ ? o.v[i].size : (u64)P.opt.max_occ);
+struct SeedSrc { // hands reads to the lanes of the seeding kernel and takes their interval lists back
+	const BatchParams& P; i64 n; u32* counter; i64 r;
+	DEVM SeedSrc(const BatchParams& P_, i64 n_, u32* c_) : P(P_), n(n_), counter(c_), r(-1) {}
+	DEVM bool next(int& len, const u8*& seq, IntvOut& o)
+	{
+		for (;;) {
+			r = (i64)atomic_add_u32(counter, 1u);
+			if (r >= n) return false;
+			len = (int)(P.seq_off[r + 1] - P.seq_off[r] - 1);
+			if (len >= P.opt.min_seed_len && len <= P.smem_cap) break;
+			if (len > P.smem_cap) atomic_or_u32(P.err, ERR_QLEN_OVERFLOW);
+			P.n_intv[r] = 0; P.n_seed[r] = 0; // no seed can exist
 		}
+		seq = P.seq + P.seq_off[r];
+		o.v = P.intv + (size_t)r * P.intv_cap; o.n = 0; o.cap = P.intv_cap; o.overflow = false;
+		return true;
 	}
-	P.n_intv[r] = (u32)o.n;
-	P.n_seed[r] = ns;
+	DEVM void finish(const IntvOut& o)
+	{
+		if (o.overflow) atomic_or_u32(P.err, ERR_INTV_OVERFLOW);
+		u32 ns = 0;
+		for (int i = 0; i < o.n; ++i) ns += (u32)(o.v[i].size < (u64)P.opt.max_occ ? o.v[i].size : (u64)P.opt.max_occ);
+		P.n_intv[r] = (u32)o.n;
+		P.n_seed[r] = ns;
+	}
+};
+DEV void body_seed_q(const BatchParams& P, i64 n, u32* counter, i64 tid)
+{
+	SeedWork wk;
+	wk.G = P.smem_scratch + (size_t)tid * P.smem_cap; wk.gcap = P.smem_cap;
+	wk.L = nullptr; wk.lstride = 0; wk.lcap = 0; wk.qs = nullptr; wk.qstride = 0;
+	if (P.seed_shared) { // packed shared-memory working set (reads of <= 255 bases, |T| < 2^40)
+#ifdef B200_SIM
+		wk.L = g_sim_seed_l; wk.lstride = 1; wk.lcap = SEED_LCAP;
+#else
+		extern __shared__ __align__(16) u8 tsm_[];
+		wk.L = (uint4*)tsm_ + threadIdx.x; wk.lstride = (int)blockDim.x; wk.lcap = P.seed_lcap;
+		if (P.seed_shared_read) { wk.qs = tsm_ + (size_t)blockDim.x * P.seed_lcap * 16 + threadIdx.x; wk.qstride = (int)blockDim.x; }
+#endif
+	}
+	SeedSrc src(P, n, counter);
+	fm_collect_queue(P.x, P.opt, wk, src);
 }
 
 // ---- sal: one thread per lookup ------------------------------------------------------------------
@@ -126,9 +142,11 @@ DEV void body_sal(const BatchParams& P, i64 t)
 }
 
 // ---- chain: one thread per read ------------------------------------------------------------------
+#define CHAIN_HEAVY_SEEDS 64 // reads with more suffix-array hits than this are chained by a warp (chain.cuh chain_read_warp)
 DEV void body_chain(const BatchParams& P, i64 r)
 {
 	u64 t0 = P.seed_off[r];
+	if (P.seed_off[r + 1] - t0 > (u64)P.chain_heavy_seeds) { u32 slot = atomic_add_u32(P.n_chain_heavy, 1u); P.chain_heavy[slot] = (u32)r; return; }
 	int len = (int)(P.seq_off[r + 1] - P.seq_off[r] - 1);
 	ChainStageIO io;
 	io.intv = P.intv + (size_t)r * P.intv_cap; io.n_intv = (int)P.n_intv[r];
@@ -137,6 +155,24 @@ DEV void body_chain(const BatchParams& P, i64 r)
 	int nks = 0;
 	int nck = P.seed_off[r + 1] > t0 ? chain_read(P.x, P.opt, len, io, &nks) : 0;
 	P.n_ck[r] = (u32)nck; P.n_ks[r] = (u32)nks;
+}
+
+template <int W>
+DEV void wbody_chain_heavy(const BatchParams& P, i64 item, WarpMem& wm, WarpScratch& ws)
+{
+	LANE_DECL;
+	(void)wm; (void)ws;
+	const i64 r = (i64)P.chain_heavy[item];
+	const u64 t0 = P.seed_off[r];
+	const int len = (int)(P.seq_off[r + 1] - P.seq_off[r] - 1);
+	ChainStageIO io;
+	io.intv = P.intv + (size_t)r * P.intv_cap; io.n_intv = (int)P.n_intv[r];
+	io.sd_rbeg = P.sd_rbeg + t0;
+	io.S = P.S + t0; io.C = P.C + t0; io.ord = P.ord + t0; io.tmp = P.tmp32 + t0; io.ck = P.ck + t0; io.ks = P.ks + t0;
+	ChainWarpScratch cs; cs.pos_sorted = (i64*)(P.regs_tmp + t0); cs.qbw = P.srt + t0; // pools of later stages, free at this point
+	int nks = 0;
+	const int nck = chain_read_warp<W>(P.x, P.opt, len, io, cs, &nks);
+	ONE_LANE { P.n_ck[r] = (u32)nck; P.n_ks[r] = (u32)nks; }
 }
 
 DEV void make_warp_ctx(const BatchParams& P, i64 warp_slot, u8* smem, WarpMem& wm, WarpScratch& ws)

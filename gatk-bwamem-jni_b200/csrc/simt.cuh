@@ -43,6 +43,7 @@ template <int W> __device__ __forceinline__ void wsync_() { if (W == 32) __syncw
 #define ONE_LANE wsync_<W>(); if (lane == 0)       /* pre-synchronised single-lane write (may overwrite data other lanes just read) */
 #define ONE_LANE_NOSYNC if (lane == 0)            /* append-only single-lane write */
 #define WARP_SYNC() wsync_<W>()
+#define LANE0_ONLY wsync_<W>(); if (lane == 0)    /* a scalar section run by one lane of the item's lane group */
 
 template <class T> DEV T ldg(const T* p) { return __ldg(p); }
 DEV int popc64(u64 x) { return __popcll(x); }
@@ -56,6 +57,8 @@ template <int W, class T> DEV T wv_get_(const T& v, int l) { return W == 32 ? __
 #define wv_reduce_min(v) wv_reduce_min_<W>(v)
 #define wv_ballot(p) wv_ballot_<W>(p)
 #define wv_get(v, l) wv_get_<W>(v, l)
+// full-mask vote of a thread-per-item kernel whose 32 lanes all take part (persistent queue kernels)
+DEV bool lanes_all(bool p) { return __all_sync(FULLMASK, p) != 0; }
 DEV u64 atomic_add_u64(u64* p, u64 v) { return (u64)atomicAdd((unsigned long long*)p, (unsigned long long)v); }
 DEV u32 atomic_add_u32(u32* p, u32 v) { return atomicAdd(p, v); }
 DEV u32 atomic_or_u32(u32* p, u32 v) { return atomicOr(p, v); }
@@ -75,6 +78,7 @@ DEV u32 atomic_max_u32(u32* p, u32 v) { return atomicMax(p, v); }
 #define ONE_LANE
 #define ONE_LANE_NOSYNC
 #define WARP_SYNC()
+#define LANE0_ONLY
 
 struct uint4 { u32 x, y, z, w; };
 template <class T> DEV T ldg(const T* p) { return *p; }
@@ -89,6 +93,7 @@ template <int W, class T> DEV T wv_get_(const T (&v)[32], int l) { return v[l]; 
 #define wv_reduce_min(v) wv_reduce_min_<W>(v)
 #define wv_ballot(p) wv_ballot_<W>(p)
 #define wv_get(v, l) wv_get_<W>(v, l)
+DEV bool lanes_all(bool p) { return p; } // the harness runs one thread at a time
 DEV u64 atomic_add_u64(u64* p, u64 v) { u64 o = *p; *p += v; return o; }
 DEV u32 atomic_add_u32(u32* p, u32 v) { u32 o = *p; *p += v; return o; }
 DEV u32 atomic_or_u32(u32* p, u32 v) { u32 o = *p; *p |= v; return o; }

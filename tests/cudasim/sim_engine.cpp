@@ -31,13 +31,13 @@ static uint64_t rt_scan_u32(const uint32_t* in, uint64_t* out, uint64_t n) { uin
 #define RT_THREADS_TID_RING(body, P, n) RT_THREADS_TID(body, P, n)
 #define RT_THREADS_QUEUE_SMEM(body, P, n, bytes) do { u32 c_ = 0; body(P, (int64_t)(n), &c_, 0); } while (0)
 #define THREADS_PER_BLOCK 128
-#define RT_THREADS_SEED(body, P, n, max_len) RT_THREADS_TID(body, P, n)
 #define RT_WARPS(wbody, P, n) do { \
 	std::vector<uint8_t> sm_(warp_smem_bytes((P).wm_cap) + 64); \
 	WarpMem wm_; WarpScratch ws_; make_warp_ctx(P, 0, sm_.data(), wm_, ws_); \
 	for (int64_t i_ = 0; i_ < (int64_t)(n); ++i_) wbody<32>(P, i_, wm_, ws_); } while (0)
 
 static void rt_timer_begin() {}
+#define RT_RELAYOUT(src, size, dst, nb) do { for (u64 b_ = 0; b_ < (u64)(nb); ++b_) fm_relayout_block((src), (size), (dst), b_); } while (0)
 #define RT_WARPS_DEVN(wbody, P, n_ptr, n_max) do { \
 	std::vector<uint8_t> sm_(warp_smem_bytes((P).wm_cap) + 64); \
 	WarpMem wm_; WarpScratch ws_; make_warp_ctx(P, 0, sm_.data(), wm_, ws_); \

@@ -94,8 +94,9 @@ def test_engine_matches_oracle_mid(mid_genome, paired):
     assert a == b, first_diff(a, b, blob, paired)
 
 
-@pytest.mark.parametrize("env", [None, "B200_TEST_RESCUE_FALLBACK", "B200_TEST_TINY_SCRATCH", "B200_TEST_ALL_LIGHT", "B200_TEST_ALL_HEAVY", "B200_WARP_EXTEND", "B200_NO_EXT_TASKS"],
-                         ids=["default", "rescue_fallback", "tiny_scratch", "extend_all_thread", "extend_all_tasks", "extend_all_warp", "extend_heavy_by_warp"])
+@pytest.mark.parametrize("env", [None, "B200_TEST_RESCUE_FALLBACK", "B200_TEST_TINY_SCRATCH", "B200_TEST_ALL_LIGHT", "B200_TEST_ALL_HEAVY", "B200_WARP_EXTEND", "B200_NO_EXT_TASKS", "B200_TEST_CHAIN_ALL_WARP", "B200_TEST_CHAIN_ALL_THREAD"],
+                         ids=["default", "rescue_fallback", "tiny_scratch", "extend_all_thread", "extend_all_tasks", "extend_all_warp", "extend_heavy_by_warp",
+                              "chain_all_warp", "chain_all_thread"])
 def test_repeat_heavy_pairs_and_forced_slow_paths(small_genome, monkeypatch, env):
     """Chains of several rescuing hits per read (repeat-derived reads); the same batch with every rescuing read forced
     onto the round-by-round rescue kernels, with thread-level scratch so small that items are handed to warps, and with
@@ -106,6 +107,19 @@ def test_repeat_heavy_pairs_and_forced_slow_paths(small_genome, monkeypatch, env
     if env:
         monkeypatch.setenv(env, "1")
     b = run_blob(engine_lib(), img, blob, 2)
+    assert a == b, first_diff(a, b, blob, True)
+
+
+def test_repeat_family_genome(monkeypatch):
+    """A genome that is 30 % repeat families: reads with hundreds of hits drive the warp-level chaining, the per-seed
+    extension tasks, the warp-cooperative region de-duplication and long mate-rescue chains."""
+    g, img = synth_image("g1m_rep", 9, [600000, 400000], repeat_frac=0.3, tandem_frac=0.02, n_segdup=3)
+    blob, _ = simdata.make_reads(g, 81, 4000, 150, True, repeat_read_frac=0.6, chimeric_frac=0.05, err_rate=0.02)
+
+    def setup(al):
+        al.setNThreadsOption(8)
+    a = run_blob(oracle_lib(), img, blob, 2, None, setup)
+    b = run_blob(engine_lib(), img, blob, 2, None, setup)
     assert a == b, first_diff(a, b, blob, True)
 
 
