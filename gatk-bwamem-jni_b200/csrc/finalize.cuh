@@ -211,16 +211,41 @@ DEV MateDesc mate_of(const Aln& a, const u32* cg)
 	return m;
 }
 
-// Copies the payload of `a` (ws.cigar / ws.md) into the var pool, applies the flag finalisation bwa performs on
+// Copies the payload of a mapped alignment (ws.cigar / ws.md) into the var pool so that the warp scratch can be reused
+// before the record is written (the paired path needs both ends' alignments before it can emit either).
+// Returns the word offset, or 0xffffffff when the pool is exhausted (the error flag is raised).
+template <int W>
+DEVNI u32 warp_stash(FinalCtx& f, const Aln& p)
+{
+	LANE_DECL;
+	const int n_cigar = p.n_cigar, md_len = n_cigar ? p.md_len : 0;
+	const u32 n_words = (u32)n_cigar + (u32)((md_len + 3) >> 2);
+	const u32 off = n_words ? var_alloc<W>(f, n_words) : 0;
+	if (off == 0xffffffffu) return off;
+	FOR_LANES {
+		for (int k = lane; k < n_cigar; k += W) f.var[off + k] = f.ws->cigar[k];
+		int mdw = (md_len + 3) >> 2;
+		for (int k = lane; k < mdw; k += W) {
+			u32 wd = 0;
+			for (int b = 0; b < 4; ++b) { int ci = k * 4 + b; if (ci < md_len) wd |= (u32)(u8)f.ws->md[ci] << (8 * b); }
+			f.var[off + n_cigar + k] = wd;
+		}
+	}
+	WARP_SYNC();
+	return off;
+}
+
+// Copies the payload of `a` (ws.cigar / ws.md) into the var pool -- unless it was stashed there already (stashed:
+// its offset; stashed_ref_len: reference length of its CIGAR) --, applies the flag finalisation bwa performs on
 // copies before the formatter hook (B.14) and writes the output record.
 template <int W>
-DEVNI void warp_emit(FinalCtx& f, const Aln& a_in, const MateDesc* mate, u32 xa_off, int xa_len, AlnRec* out)
+DEVNI void warp_emit(FinalCtx& f, const Aln& a_in, const MateDesc* mate, u32 xa_off, int xa_len, AlnRec* out, const u32* stashed = nullptr, int stashed_ref_len = 0)
 {
 	LANE_DECL;
 	Aln p = a_in;
 	AlnRec r;
 	memset(&r, 0, sizeof(r));
-	int ref_len = p.rid >= 0 ? cigar_ref_len(f.ws->cigar, p.n_cigar) : 0;
+	int ref_len = stashed ? stashed_ref_len : (p.rid >= 0 ? cigar_ref_len(f.ws->cigar, p.n_cigar) : 0);
 	MateDesc m; bool has_m = mate != nullptr;
 	if (has_m) m = *mate; else { m.rid = -1; m.pos = -1; m.is_rev = 0; m.ref_len = 0; }
 	int n_cigar = p.n_cigar;
@@ -236,10 +261,10 @@ DEVNI void warp_emit(FinalCtx& f, const Aln& a_in, const MateDesc* mate, u32 xa_
 		r.rid = p.rid; r.pos = (i32)p.pos; r.NM = p.NM; r.score = p.score; r.sub = p.sub; r.n_cigar = n_cigar;
 		r.md_len = n_cigar ? p.md_len : 0;
 		u32 n_words = (u32)n_cigar + (u32)((r.md_len + 3) >> 2);
-		u32 off = n_words ? var_alloc<W>(f, n_words) : 0;
+		u32 off = stashed ? *stashed : (n_words ? var_alloc<W>(f, n_words) : 0);
 		if (off == 0xffffffffu) { off = 0; r.n_cigar = 0; r.md_len = 0; n_cigar = 0; }
 		r.var_off = off;
-		FOR_LANES {
+		if (!stashed) FOR_LANES {
 			for (int k = lane; k < n_cigar; k += W) f.var[off + k] = f.ws->cigar[k];
 			int mdw = (r.md_len + 3) >> 2;
 			for (int k = lane; k < mdw; k += W) {
@@ -654,17 +679,19 @@ DEVNI void warp_sam_pe(FinalCtx& f, u64 id, PairIO& io)
 		// records: XA first (it reuses the warp scratch), then the chosen hit of each end; the mate descriptor of end i is
 		// the other end's record before flag finalisation
 		u32 xa_off[2] = { 0, 0 }; int xa_len[2] = { 0, 0 };
-		MateDesc md[2];
-		for (int i = 0; i < 2; ++i) { // mate descriptors need pos/is_rev/ref_len of both ends first
-			Aln h = warp_reg2aln<W>(f, io.l_seq[i], io.seq[i], &io.a[i][z[i]]);
-			md[i] = mate_of(h, f.ws->cigar);
+		MateDesc md[2]; Aln hs[2]; u32 st_off[2];
+		for (int i = 0; i < 2; ++i) { // mate descriptors need pos/is_rev/ref_len of both ends first; each alignment is
+			// computed once and its CIGAR / MD parked in the var pool (the scratch is reused by the other end and by XA)
+			hs[i] = warp_reg2aln<W>(f, io.l_seq[i], io.seq[i], &io.a[i][z[i]]);
+			md[i] = mate_of(hs[i], f.ws->cigar);
+			st_off[i] = warp_stash<W>(f, hs[i]);
 		}
 		for (int i = 0; i < 2; ++i) {
 			if (!(opt.flag & MEM_F_ALL)) xa_len[i] = warp_gen_xa<W>(f, io.l_seq[i], io.seq[i], io.n[i], io.a[i], z[i], &xa_off[i]);
-			Aln h = warp_reg2aln<W>(f, io.l_seq[i], io.seq[i], &io.a[i][z[i]]);
+			Aln h = hs[i];
 			h.mapq = (u32)q_se[i];
 			h.flag |= 0x40 << i | extra_flag;
-			warp_emit<W>(f, h, &md[!i], xa_off[i], xa_len[i], &io.out[i][0]);
+			warp_emit<W>(f, h, &md[!i], xa_off[i], xa_len[i], &io.out[i][0], &st_off[i], md[i].ref_len);
 			io.n_out[i] = 1;
 		}
 		return;

@@ -326,7 +326,7 @@ void orc_collect_intv_core(const orc_index_t *x, const orc_opt_t *opt, int len, 
 
 uint64_t orc_bwt_sa(const orc_index_t *x, uint64_t k)
 {
-	uint64_t sa = 0, mask = (uint64_t)x->sa_intv - 1;
+	uint64_t sa = 0, mask = (uint64_t)x->sa_intv - 1, occ0 = orc_tls_cnt.n_occ;
 	++orc_tls_cnt.n_sa_lookup;
 	while (k & mask) {
 		++sa;
@@ -338,6 +338,7 @@ uint64_t orc_bwt_sa(const orc_index_t *x, uint64_t k)
 		}
 	}
 	++orc_tls_cnt.n_sa;
+	orc_tls_cnt.n_occ_sa += orc_tls_cnt.n_occ - occ0;
 	return sa + x->sa[k / x->sa_intv];
 }
 

@@ -114,6 +114,7 @@ typedef struct {
 	uint64_t cells_glb;  /* ksw_global2 cells */
 	uint64_t n_ext_calls, n_msw_calls, n_glb_calls;
 	uint64_t n_seeds, n_chains, n_regs;
+	uint64_t n_occ_sa;   /* the part of n_occ touched by bwt_sa walks (the rest belongs to SMEM seeding) */
 } orc_counters_t;
 
 /* ---- C-ABI of the oracle (mirrors jnibwa.h:11-16) ---- */
