@@ -290,6 +290,8 @@ def main():
     e2e = world * args.pairs * args.steps / t_e2e
 
     if rank != 0:
+        import torch.distributed as dist
+        dist.destroy_process_group()
         return
     # ---- roofline of the dominant kernel + per-kernel table (algorithmic work from the oracle's counters on a sample)
     n_s = min(args.pairs, args.cpu_sample_pairs)
@@ -370,6 +372,9 @@ def main():
             "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": out_bytes},
             "gpu_launches": int(cnt[7]) * args.steps, "roofline": roof, "stages": stage_work, "kernels": kern, "cpu_baseline": cpu, "parity": parity}
     print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

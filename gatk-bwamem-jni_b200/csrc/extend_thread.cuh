@@ -279,6 +279,7 @@ DEV void thread_extend_queue(const BatchParams& P, i64 n_reads, u32* counter, co
 				u32* rw = tm.row + (size_t)beg * RS;
 				const u8* qp = tm.rd + (size_t)(qbase + qdir * beg) * QS;
 				const ptrdiff_t qstep = (ptrdiff_t)qdir * (ptrdiff_t)QS;
+#pragma unroll 4
 				for (int j = beg; j < end; ++j) {
 					const u32 he = *rw;
 					int M = (int)(he & 0xffffu), e = (int)(he >> 16);
