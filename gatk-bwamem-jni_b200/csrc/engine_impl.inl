@@ -12,7 +12,9 @@
 #include <ctime>
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 #include <sys/mman.h>
@@ -135,7 +137,7 @@ struct Engine {
 	void close_all();
 	// staged request
 	bool st_valid = false; uint32_t st_n_reads = 0; int st_max_len = 0; uint64_t st_blob_len = 0; std::vector<uint64_t> st_seq_off;
-	bool stage(const char* blob);
+	bool stage(const char* blob, bool wait = true);
 	void* run(const MemOpt* opt, const PeStat* pes0, size_t* out_size, bool host_output);
 	void* align(const MemOpt* opt, const PeStat* pes0, char* blob, size_t* out_size);
 };
@@ -204,13 +206,42 @@ inline void Engine::close_all()
 
 // misc block layout (u32 words): [20] warp-replayed rescue reads  [0] err  [1] work counter  [2] var cursor  [3] rescue task count  [4] max nb  [5] redo count  [6] heavy-read count  [7] multi-hit read count  [8..] Counters
 // Stage a request: one host pass over the blob for the read boundaries, then upload of bases and offsets.
-inline bool Engine::stage(const char* blob_in)
+// The wire format carries no byte length (u32 count, then NUL-terminated reads; BwaMemAligner.java:198-209), so the read
+// boundaries have to be found by a sequential scan that must not look past the last NUL.  While the host scans, a
+// helper thread already uploads the scanned prefix into the (grow-only) device buffer of the previous calls; a
+// request larger than that buffer falls back to scan-then-upload.
+inline bool Engine::stage(const char* blob_in, bool wait)
 {
 	st_valid = false;
 	uint32_t n_reads; memcpy(&n_reads, blob_in, 4);
 	const char* base = blob_in + 4;
 	st_seq_off.resize((size_t)n_reads + 1);
 	int max_len = 0;
+	uint64_t uploaded = 0;
+#ifndef B200_SIM
+	std::atomic<uint64_t> scanned(0);
+	std::atomic<int> state(0); // 0 scanning, 1 scan finished, 2 abandon
+	int dev = 0; cudaGetDevice(&dev);
+	const uint64_t dcap = b_blob.cap;
+	char* dptr = (char*)b_blob.p;
+	std::thread copier;
+	const bool overlap = n_reads >= 4096 && dcap > 0 && !getenv("B200_NO_STAGE_OVERLAP");
+	if (overlap) copier = std::thread([&]() {
+		cudaSetDevice(dev);
+		const uint64_t CH = 4u << 20;
+		for (;;) {
+			const int stt = state.load(std::memory_order_acquire);
+			const uint64_t avail = scanned.load(std::memory_order_acquire);
+			if (stt == 2) break;
+			uint64_t end = avail < dcap ? avail : dcap;
+			if (end - uploaded >= CH || (stt == 1 && end > uploaded)) {
+				if (cudaMemcpyAsync(dptr + uploaded, base + uploaded, end - uploaded, cudaMemcpyHostToDevice, rt_stream()) != cudaSuccess) break;
+				uploaded = end;
+			} else if (stt == 1 || avail >= dcap) break;
+			else std::this_thread::yield();
+		}
+	});
+#endif
 	{
 		const char* p = base;
 		for (uint32_t i = 0; i < n_reads; ++i) {
@@ -218,15 +249,26 @@ inline bool Engine::stage(const char* blob_in)
 			st_seq_off[i] = (uint64_t)(p - base);
 			if ((int)l > max_len) max_len = (int)l;
 			p += l + 1;
+#ifndef B200_SIM
+			if ((i & 1023) == 1023) scanned.store((uint64_t)(p - base), std::memory_order_release);
+#endif
 		}
 		st_seq_off[n_reads] = (uint64_t)(p - base);
 	}
 	st_n_reads = n_reads; st_max_len = max_len; st_blob_len = st_seq_off[n_reads];
+#ifndef B200_SIM
+	if (overlap) {
+		scanned.store(st_blob_len, std::memory_order_release);
+		state.store(st_blob_len + 16 <= dcap ? 1 : 2, std::memory_order_release);
+		copier.join();
+		if (st_blob_len + 16 > dcap) uploaded = 0; // the buffer is about to be replaced
+	}
+#endif
 	if (n_reads) {
 		if (!(b_blob.ensure(st_blob_len + 16) && b_seqoff.ensure(((size_t)n_reads + 1) * 8))) { last_error = "device allocation failed"; return false; }
-		rt_h2d(b_blob.p, base, st_blob_len);
+		if (uploaded < st_blob_len) rt_h2d((char*)b_blob.p + uploaded, base + uploaded, st_blob_len - uploaded);
 		rt_h2d(b_seqoff.p, st_seq_off.data(), st_seq_off.size() * 8);
-		rt_sync();
+		if (wait) rt_sync();
 	}
 	st_valid = true;
 	return true;
@@ -238,7 +280,7 @@ inline void* Engine::align(const MemOpt* opt_in, const PeStat* pes0, char* blob_
 	last_error.clear();
 	*out_size = 0;
 	g_hp.begin();
-	if (!stage(blob_in)) return nullptr;
+	if (!stage(blob_in, false)) return nullptr; // same stream: the kernels queue up behind the upload
 	g_hp.mark("stage");
 	void* r = run(opt_in, pes0, out_size, true);
 	g_hp.mark("d2h_out");
