@@ -164,6 +164,11 @@ DEF_WARP_KERNEL_DEVN(wbody_extend_heavy)
 DEF_THREAD_KERNEL(body_save_regs)
 DEF_THREAD_TID_KERNEL(body_final_pe_t)
 DEF_THREAD_TID_KERNEL(body_final_se_t)
+DEF_THREAD_TID_KERNEL(body_final_pe_collect)
+DEF_THREAD_TID_KERNEL(body_final_se_collect)
+DEF_THREAD_TID_KERNEL(body_final_pe_consume)
+DEF_THREAD_TID_KERNEL(body_final_se_consume)
+DEF_THREAD_QUEUE_KERNEL(body_galign_task_q)
 DEF_WARP_KERNEL_DEVN(wbody_final_pe_redo)
 DEF_WARP_KERNEL_DEVN(wbody_final_se_redo)
 

@@ -128,7 +128,7 @@ struct Engine {
 	// batch workspace
 	DBuf b_blob, b_seq, b_seqoff, b_intv, b_nintv, b_nseed, b_smem, b_seedoff, b_rbeg, b_S, b_C, b_ord, b_tmp32, b_ck, b_ks, b_srt, b_regtmp,
 	     b_nck, b_nks, b_nreg, b_regcap, b_regoff, b_regs, b_snap, b_ztmp, b_pairv, b_recs, b_nrec, b_cand, b_pairtab, b_var, b_misc,
-	     b_outwords, b_outoff, b_out, b_wsz, b_wscig, b_wsmd, b_wsxa, b_wsbrow, b_nb, b_swtask, b_swstate, b_swlist, b_tbuf, b_redo, b_heavy, b_multi, b_cand2, b_specstate, b_spectask, b_nreg0, b_rsheavy, b_wsrt, b_wsrkey, b_wsrrank, b_exttask, b_extres, b_ckrmax, b_chainheavy;
+	     b_outwords, b_outoff, b_out, b_wsz, b_wscig, b_wsmd, b_wsxa, b_wsbrow, b_nb, b_swtask, b_swstate, b_swlist, b_tbuf, b_redo, b_heavy, b_multi, b_cand2, b_specstate, b_spectask, b_nreg0, b_rsheavy, b_wsrt, b_wsrkey, b_wsrrank, b_exttask, b_extres, b_ckrmax, b_chainheavy, b_gatask, b_gares, b_gaitem0, b_gaitemn;
 	Counters last_counters; uint64_t last_n_seed = 0; int n_launches = 0;
 	std::string last_error;
 
@@ -198,7 +198,7 @@ inline void Engine::close_all()
 	DBuf* all[] = { &d_bwt, &d_sa, &d_pac, &d_ctg, &d_log, &d_names, &d_name_off, &b_blob, &b_seq, &b_seqoff, &b_intv, &b_nintv, &b_nseed, &b_smem,
 	                &b_seedoff, &b_rbeg, &b_S, &b_C, &b_ord, &b_tmp32, &b_ck, &b_ks, &b_srt, &b_regtmp, &b_nck, &b_nks, &b_nreg, &b_regcap, &b_regoff,
 	                &b_regs, &b_snap, &b_ztmp, &b_pairv, &b_recs, &b_nrec, &b_cand, &b_pairtab, &b_var, &b_misc, &b_outwords, &b_outoff, &b_out,
-	                &b_wsz, &b_wscig, &b_wsmd, &b_wsxa, &b_wsbrow, &b_nb, &b_swtask, &b_swstate, &b_swlist, &b_tbuf, &b_redo, &b_heavy, &b_multi, &b_cand2, &b_specstate, &b_spectask, &b_nreg0, &b_rsheavy, &b_wsrt, &b_wsrkey, &b_wsrrank, &b_exttask, &b_extres, &b_ckrmax, &b_chainheavy };
+	                &b_wsz, &b_wscig, &b_wsmd, &b_wsxa, &b_wsbrow, &b_nb, &b_swtask, &b_swstate, &b_swlist, &b_tbuf, &b_redo, &b_heavy, &b_multi, &b_cand2, &b_specstate, &b_spectask, &b_nreg0, &b_rsheavy, &b_wsrt, &b_wsrkey, &b_wsrrank, &b_exttask, &b_extres, &b_ckrmax, &b_chainheavy, &b_gatask, &b_gares, &b_gaitem0, &b_gaitemn };
 	for (DBuf* b : all) b->release();
 	if (map) munmap(map, map_len);
 	map = nullptr;
@@ -398,6 +398,7 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 		if (getenv("B200_TEST_ALL_HEAVY")) P.light_max_seeds = -1;
 		if (getenv("B200_TEST_ALL_LIGHT")) { P.light_max_seeds = 1 << 30; P.light_max_chains = 1 << 30; }
 	}
+	for (int t = 0; t < 5; ++t) { P.rowpack[t] = 0; for (int c2 = 0; c2 < 5; ++c2) P.rowpack[t] |= (u64)(u8)opt.mat[t * 5 + c2] << (8 * c2); }
 	// ---- stage 3: extension + de-duplication (thread per light read with shared-memory DP rows, warp per heavy read)
 	if (getenv("B200_WARP_EXTEND")) RT_WARPS(wbody_extend, P, (int64_t)n_reads); // the all-warp formulation, kept for comparison
 	else {
@@ -409,7 +410,6 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 			size_t fit = budget / THREADS_PER_BLOCK > qb ? (budget / THREADS_PER_BLOCK - qb) / 4 : 0;
 			rw = fit >= 2 * THREAD_RING_N ? (int)fit : 0;
 		}
-		for (int t = 0; t < 5; ++t) { P.rowpack[t] = 0; for (int c2 = 0; c2 < 5; ++c2) P.rowpack[t] |= (u64)(u8)opt.mat[t * 5 + c2] << (8 * c2); }
 		if (rw == 0) RT_WARPS(wbody_extend, P, (int64_t)n_reads);
 		else {
 			P.t_ext_rw = rw;
@@ -509,8 +509,22 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 	// ---- finalize: a thread per read / pair; items that exceed the thread-level scratch are redone by a warp
 	{
 		RT_THREADS(body_save_regs, P, (int64_t)n_reads);
-		if (pe) { RT_THREADS_TID_RING(body_final_pe_t, P, (int64_t)n_units); RT_WARPS_DEVN(wbody_final_pe_redo, P, P.n_redo, (int64_t)n_units); }
-		else { RT_THREADS_TID_RING(body_final_se_t, P, (int64_t)n_reads); RT_WARPS_DEVN(wbody_final_se_redo, P, P.n_redo, (int64_t)n_reads); }
+		const int64_t n_items = pe ? (int64_t)n_units : (int64_t)n_reads;
+		if (getenv("B200_FINAL_ONE_PASS")) { // every item computes its own alignments (kept for comparison and tests)
+			if (pe) RT_THREADS_TID_RING(body_final_pe_t, P, n_items); else RT_THREADS_TID_RING(body_final_se_t, P, n_items);
+		} else {
+			// two passes around a queue of alignment tasks (galign_thread.cuh): collect -> tasks -> consume
+			P.ga_cap = (u32)std::min<uint64_t>((uint64_t)0x7fffffff, (uint64_t)n_reads * 3 + 1024);
+			ok = b_gatask.ensure((size_t)P.ga_cap * sizeof(GaTask)) && b_gares.ensure((size_t)P.ga_cap * sizeof(GaRes)) && b_gaitem0.ensure(((size_t)n_items + 1) * 4) && b_gaitemn.ensure(((size_t)n_items + 1) * 4);
+			if (!ok) { last_error = "device allocation failed (alignment tasks)"; return nullptr; }
+			P.ga_tasks = b_gatask.as<GaTask>(); P.ga_res = b_gares.as<GaRes>(); P.ga_item0 = b_gaitem0.as<u32>(); P.ga_itemn = b_gaitemn.as<u32>();
+			P.n_ga_tasks = b_misc.as<u32>() + 23;
+			if (pe) RT_THREADS_TID_RING(body_final_pe_collect, P, n_items); else RT_THREADS_TID_RING(body_final_se_collect, P, n_items);
+			rt_memset(P.var_cursor, 0, 4); // payloads written while collecting are discarded
+			RT_THREADS_QUEUE_SMEM(body_galign_task_q, P, (int64_t)P.ga_cap, thread_block_smem_bytes(THREADS_PER_BLOCK, P.wm_cap));
+			if (pe) RT_THREADS_TID_RING(body_final_pe_consume, P, n_items); else RT_THREADS_TID_RING(body_final_se_consume, P, n_items);
+		}
+		if (pe) RT_WARPS_DEVN(wbody_final_pe_redo, P, P.n_redo, n_items); else RT_WARPS_DEVN(wbody_final_se_redo, P, P.n_redo, n_items);
 	}
 	// ---- output stream
 	RT_THREADS(body_out_size, P, (int64_t)n_reads);
@@ -522,6 +536,8 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 	uint32_t misc[32];
 	rt_d2h(misc, b_misc.p, sizeof(misc));
 	memcpy(&last_counters, misc + 8, sizeof(Counters));
+	if (getenv("B200_DEBUG_STATS")) fprintf(stderr, "[bwamem-b200] reads %u: finalize redo %u, alignment tasks %u, extension-heavy reads %u / tasks %u, chain-heavy %u, rescue warp-replayed %u / fallback %u\n",
+	                                        n_reads, misc[5], misc[23], misc[6], misc[21], misc[22], misc[20], misc[7]);
 	if (misc[0]) {
 		char buf[128]; snprintf(buf, sizeof buf, "device-side capacity/limit error flags 0x%x", misc[0]);
 		last_error = buf;

@@ -364,9 +364,14 @@ DEV bool patch_precheck(const DevIndex& x, const MemOpt& opt, const Reg& a, cons
 	return true;
 }
 
+// *fixed_point (optional) is set when the call went through without any tie or patch candidate AND removed nothing:
+// the list is then in its final order with all sort keys distinct and no redundant pair in scan range, so a further
+// call on the unchanged list would return it unchanged (same end-position order => every pair is examined in the
+// same orientation and found non-redundant again; same score order).  Callers use it to skip such calls.
 template <int W>
-DEVNI int warp_sort_dedup_fast(const DevIndex& x, const MemOpt& opt, WarpMem& wm, WarpScratch& ws, Counters* cnt, const u8* query, int n, Reg* a)
+DEVNI int warp_sort_dedup_fast(const DevIndex& x, const MemOpt& opt, WarpMem& wm, WarpScratch& ws, Counters* cnt, const u8* query, int n, Reg* a, bool* fixed_point = nullptr)
 {
+	if (fixed_point) *fixed_point = false;
 	if (W != 32 || n < SDP_FAST_MIN || n > ws.rt_cap || ws.rt == nullptr) return warp_sort_dedup_patch<W>(x, opt, wm, ws, cnt, query, n, a);
 	LANE_DECL;
 	SDP_STAT(0);
@@ -476,5 +481,6 @@ DEVNI int warp_sort_dedup_fast(const DevIndex& x, const MemOpt& opt, WarpMem& wm
 	FOR_LANES { for (int i = lane; i < n2; i += W) a[rk[i]] = t[i]; }
 	WARP_SYNC();
 	SDP_STAT(4);
+	if (fixed_point) *fixed_point = n2 == n; // (a removed hit may have ended scans that would now run on: not a fixed point)
 	return n2;
 }

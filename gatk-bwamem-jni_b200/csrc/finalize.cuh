@@ -7,7 +7,19 @@
 #pragma once
 #include "extend.cuh"
 
+// ---- alignment tasks of the two-pass finalize (galign_thread.cuh) -------------------------------------------------
+#define GA_CIG_CAP 46
+#define GA_MD_CAP 176
+#define GA_ITEM_MAX 16   // alignments one item (read / pair) may request; more -> the item is finalized by a warp directly
+struct GaTask { u64 qoff; i64 rb, re; i32 qb, qe, w2, truesc; };   // query = codes at qoff + [qb, qe); band start w2
+struct GaRes { i32 score, NM, nc, ml, valid; u32 cigar[GA_CIG_CAP]; char md[GA_MD_CAP]; };
+enum { FIN_DIRECT = 0, FIN_COLLECT = 1, FIN_CONSUME = 2 };
+
 struct FinalCtx {
+	int mode;                         // FIN_DIRECT: alignments computed in place; FIN_COLLECT / FIN_CONSUME: see galign_thread.cuh
+	const u8* seq_base;               // P.seq (task descriptors hold offsets)
+	GaTask* lt; int lt_n;             // collect: this item's requests (GA_ITEM_MAX entries); lt_n counts all of them
+	const GaRes* res; int res_n, res_k; // consume: this item's results and the cursor
 	const DevIndex* x; const MemOpt* opt;
 	WarpMem* wm; WarpScratch* ws; Counters* cnt;
 	u32* var; u32 var_cap; u32* var_cursor; // bump-allocated pool for cigar / MD / XA payloads (words)
@@ -163,6 +175,21 @@ DEVNI Aln warp_reg2aln(FinalCtx& f, int l_query, const u8* query, const Reg* ar)
 	w2 = w2 > tmp ? w2 : tmp;
 	if (w2 > opt.w) w2 = w2 < r.w ? w2 : r.w;
 	int i = 0, score = 0, last_sc = -(1 << 30), NM = -1, nc = 0, ml = 0;
+	if (f.mode == FIN_COLLECT) { // record the request; the caller only needs a well-formed record to go on deciding
+		if (f.lt_n < GA_ITEM_MAX) { GaTask t; t.qoff = (u64)(query - f.seq_base); t.rb = rb; t.re = re; t.qb = qb; t.qe = qe; t.w2 = w2; t.truesc = r.truesc; f.lt[f.lt_n] = t; }
+		++f.lt_n;
+		NM = 0;
+	} else if (f.mode == FIN_CONSUME) {
+		const GaRes* g = f.res_k < f.res_n ? &f.res[f.res_k] : nullptr;
+		++f.res_k;
+		if (g == nullptr || g->valid != 1 || g->nc + 2 > f.ws->cigar_cap || g->ml > f.ws->md_cap - 16) { atomic_or_u32(f.ws->err, ERR_NEED_WARP); NM = 0; } // a warp finalizes the item
+		else {
+			score = g->score; NM = g->NM; nc = g->nc; ml = g->ml;
+			for (int k = 0; k < nc; ++k) f.ws->cigar[k] = g->cigar[k];
+			for (int k = 0; k < ml; ++k) f.ws->md[k] = g->md[k];
+			f.ws->md[ml] = 0;
+		}
+	} else
 	do {
 		w2 = w2 < opt.w << 2 ? w2 : opt.w << 2;
 		DBGP(300, w2);

@@ -54,6 +54,7 @@ struct BatchParams {
 	u32* heavy_list; u32* n_heavy; int light_max_seeds, light_max_chains; // extension: reads with many seeds go to the warp-level kernel
 	ExtTask* ext_tasks; u32* n_ext_tasks; ExtRes* ext_res; i64* ck_rmax; // heavy reads: per-seed extension tasks, results, per-chain windows
 	u32* chain_heavy; u32* n_chain_heavy; int chain_heavy_seeds; // reads chained by a warp
+	GaTask* ga_tasks; GaRes* ga_res; u32* n_ga_tasks; u32 ga_cap; u32* ga_item0; u32* ga_itemn; // two-pass finalize (galign_thread.cuh)
 	int use_ext_res;        // wbody_extend consumes ext_res (set for the replay launch of the heavy reads only)
 	int t_ext_rw;           // thread-level extension: shared-memory words per thread (DP row, doubling as the two NW rings)
 	u64 rowpack[5];         // byte c of rowpack[t] = mat[t*5 + c] (score of query code c against target base t)
@@ -61,6 +62,7 @@ struct BatchParams {
 };
 
 #include "extend_thread.cuh"
+#include "galign_thread.cuh"
 
 // ---- encode: ASCII -> nt4 (bytes already < 4 are taken as codes; hazard H12) --------------------
 DEV u8 nt4_of(u8 c)
@@ -310,8 +312,11 @@ DEV void wbody_rescue_sw(const BatchParams& P, i64 item, WarpMem& wm, WarpScratc
 	rescue_sw<W>(P.x, P.opt, wm, ws, P.cnt, io, (u32)item); // tasks are stored compactly: the item is the task index
 }
 
-DEV void make_final_ctx(const BatchParams& P, WarpMem& wm, WarpScratch& ws, FinalCtx& f)
+struct FinalMode { int mode; GaTask* lt; int lt_n; const GaRes* res; int res_n, res_k; }; // how warp_reg2aln obtains alignments
+DEV void make_final_ctx(const BatchParams& P, WarpMem& wm, WarpScratch& ws, FinalCtx& f, const FinalMode* fm = nullptr)
 {
+	f.mode = FIN_DIRECT; f.seq_base = P.seq; f.lt = nullptr; f.lt_n = 0; f.res = nullptr; f.res_n = 0; f.res_k = 0;
+	if (fm) { f.mode = fm->mode; f.lt = fm->lt; f.lt_n = fm->lt_n; f.res = fm->res; f.res_n = fm->res_n; f.res_k = fm->res_k; }
 	f.rescued = P.rescued != 0;
 	f.x = &P.x; f.opt = &P.opt; f.wm = &wm; f.ws = &ws; f.cnt = P.cnt;
 	f.var = P.var; f.var_cap = P.var_cap; f.var_cursor = P.var_cursor;
@@ -321,10 +326,10 @@ DEV void make_final_ctx(const BatchParams& P, WarpMem& wm, WarpScratch& ws, Fina
 
 // ---- finalize, single-end: one warp per read ------------------------------------------------------
 template <int W>
-DEV void wbody_final_se(const BatchParams& P, i64 r, WarpMem& wm, WarpScratch& ws)
+DEV void wbody_final_se(const BatchParams& P, i64 r, WarpMem& wm, WarpScratch& ws, FinalMode* fm = nullptr)
 {
 	LANE_DECL;
-	FinalCtx f; make_final_ctx(P, wm, ws, f);
+	FinalCtx f; make_final_ctx(P, wm, ws, f, fm);
 	int len = (int)(P.seq_off[r + 1] - P.seq_off[r] - 1);
 	const u8* seq = P.seq + P.seq_off[r];
 	Reg* a = P.regs + P.reg_off[r];
@@ -335,14 +340,15 @@ DEV void wbody_final_se(const BatchParams& P, i64 r, WarpMem& wm, WarpScratch& w
 	if (P.opt.flag & MEM_F_PRIMARY5) warp_reorder_primary5<W>(P.opt.T, n, a);
 	int nr = warp_reg2sam<W>(f, len, seq, n, a, 0, nullptr, P.recs + P.reg_off[r], (int)P.reg_cap[r]);
 	ONE_LANE { P.n_rec[r] = (u32)nr; }
+	if (fm) { fm->lt_n = f.lt_n; fm->res_k = f.res_k; }
 }
 
 // ---- finalize, paired-end: one warp per pair ------------------------------------------------------
 template <int W>
-DEV void wbody_final_pe(const BatchParams& P, i64 pr, WarpMem& wm, WarpScratch& ws)
+DEV void wbody_final_pe(const BatchParams& P, i64 pr, WarpMem& wm, WarpScratch& ws, FinalMode* fm = nullptr)
 {
 	LANE_DECL;
-	FinalCtx f; make_final_ctx(P, wm, ws, f);
+	FinalCtx f; make_final_ctx(P, wm, ws, f, fm);
 	PairIO io;
 	for (int e = 0; e < 2; ++e) {
 		i64 r = (pr << 1) + e;
@@ -356,6 +362,7 @@ DEV void wbody_final_pe(const BatchParams& P, i64 pr, WarpMem& wm, WarpScratch& 
 	io.v = P.pairv + P.reg_off[pr << 1];
 	warp_sam_pe<W>(f, (u64)pr, io);
 	ONE_LANE { P.n_rec[pr << 1] = (u32)io.n_out[0]; P.n_rec[(pr << 1) + 1] = (u32)io.n_out[1]; }
+	if (fm) { fm->lt_n = f.lt_n; fm->res_k = f.res_k; }
 }
 
 // ---- thread-per-item variants (W = 1) with hand-over of oversized items to the warp-level kernels -------------
@@ -499,6 +506,45 @@ DEV void body_final_se_t(const BatchParams& P, i64 r, i64 tid)
 	WarpMem wm; WarpScratch ws; make_thread_ctx(P, tid, wm, ws, &lerr);
 	wbody_final_se<1>(P, r, wm, ws);
 	if (lerr) { u32 slot = atomic_add_u32(P.n_redo, 1u); P.redo_list[slot] = (u32)r; }
+}
+// ---- two-pass finalize (galign_thread.cuh): collect the alignment requests of an item, later consume their results
+DEV void final_collect_item(const BatchParams& P, i64 item, i64 tid, bool pe)
+{
+	u32 sink = 0; // limits hit while collecting are not real: no alignment has been computed yet
+	WarpMem wm; WarpScratch ws; make_thread_ctx(P, tid, wm, ws, &sink);
+	GaTask lt[GA_ITEM_MAX];
+	FinalMode fm; fm.mode = FIN_COLLECT; fm.lt = lt; fm.lt_n = 0; fm.res = nullptr; fm.res_n = 0; fm.res_k = 0;
+	if (pe) wbody_final_pe<1>(P, item, wm, ws, &fm); else wbody_final_se<1>(P, item, wm, ws, &fm);
+	u32 n = (u32)fm.lt_n, base = 0;
+	bool direct = n > (u32)GA_ITEM_MAX;
+	if (!direct && n) { base = atomic_add_u32(P.n_ga_tasks, n); if (base + n > P.ga_cap) direct = true; }
+	if (!direct) for (u32 k = 0; k < n; ++k) P.ga_tasks[base + k] = lt[k];
+	P.ga_item0[item] = base; P.ga_itemn[item] = direct ? 0xffffffffu : n;
+}
+DEV void final_consume_item(const BatchParams& P, i64 item, i64 tid, bool pe)
+{
+	if (pe) { restore_regs(P, item << 1, 0, 1); restore_regs(P, (item << 1) + 1, 0, 1); } else restore_regs(P, item, 0, 1); // the collect pass edited them
+	const u32 n = P.ga_itemn[item];
+	bool redo = n == 0xffffffffu;
+	if (!redo) {
+		u32 lerr = 0;
+		WarpMem wm; WarpScratch ws; make_thread_ctx(P, tid, wm, ws, &lerr);
+		FinalMode fm; fm.mode = FIN_CONSUME; fm.lt = nullptr; fm.lt_n = 0; fm.res = P.ga_res + P.ga_item0[item]; fm.res_n = (int)n; fm.res_k = 0;
+		if (pe) wbody_final_pe<1>(P, item, wm, ws, &fm); else wbody_final_se<1>(P, item, wm, ws, &fm);
+		redo = lerr != 0 || fm.res_k != (int)n;
+	}
+	if (redo) { u32 slot = atomic_add_u32(P.n_redo, 1u); P.redo_list[slot] = (u32)item; }
+}
+DEV void body_final_pe_collect(const BatchParams& P, i64 pr, i64 tid) { final_collect_item(P, pr, tid, true); }
+DEV void body_final_se_collect(const BatchParams& P, i64 r, i64 tid) { final_collect_item(P, r, tid, false); }
+DEV void body_final_pe_consume(const BatchParams& P, i64 pr, i64 tid) { final_consume_item(P, pr, tid, true); }
+DEV void body_final_se_consume(const BatchParams& P, i64 r, i64 tid) { final_consume_item(P, r, tid, false); }
+DEV void body_galign_task_q(const BatchParams& P, i64 n, u32* counter, i64 tid)
+{
+	(void)n;
+	u32 lerr = 0;
+	WarpMem wm; WarpScratch ws; make_thread_ctx(P, tid, wm, ws, &lerr);
+	thread_galign_queue(P, (i64)*P.n_ga_tasks, counter, wm, ws, &lerr);
 }
 template <int W>
 DEV void wbody_final_pe_redo(const BatchParams& P, i64 item, WarpMem& wm, WarpScratch& ws)

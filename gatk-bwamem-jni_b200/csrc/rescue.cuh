@@ -455,6 +455,7 @@ DEV bool rescue_apply_all(const DevIndex& x, const MemOpt& opt, const PeStat* pe
 	const int l_ms = (int)(io.seq_off[m + 1] - io.seq_off[m] - 1);
 	const i64 l_pac = x.l_pac;
 	bool ok = true;
+	bool settled = false; // the list is a fixed point of the de-duplication (nothing inserted since a clean pass)
 	for (int k = 0; k < nb && ok; ++k) {
 		const Reg a = io.snap[io.reg_off[r] + k];
 		int skip[4];
@@ -479,10 +480,11 @@ DEV bool rescue_apply_all(const DevIndex& x, const MemOpt& opt, const PeStat* pe
 				WARP_SYNC();
 				{ WV(int, nv); FOR_LANES { L_(nv) = room ? nm2 : -1; } nm2 = wv_get(nv, 0); }
 				if (nm2 < 0) { ONE_LANE { atomic_or_u32(ws.err, ERR_REG_OVERFLOW); io.n_reg[m] = (u32)nm; } return true; }
+				if (nm2 != nm) settled = false;
 				nm = nm2;
 				++n;
 			}
-			if (n) nm = warp_sort_dedup_fast<W>(x, opt, wm, ws, nullptr, nullptr, nm, ma);
+			if (n && !settled) nm = warp_sort_dedup_fast<W>(x, opt, wm, ws, nullptr, nullptr, nm, ma, &settled);
 		}
 	}
 	ONE_LANE { io.n_reg[m] = (u32)nm; }
