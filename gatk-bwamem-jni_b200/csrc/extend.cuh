@@ -165,6 +165,15 @@ struct RegLtHash { DEVM bool operator()(const Reg& a, const Reg& b) const { retu
 
 
 // mem_sort_dedup_patch; query == nullptr disables patching (the mate-rescue call sites)
+// Sort keys of a region with the record's position: the scalar sorts below run the reference's (unstable) introsort on
+// these 16/24-byte pairs instead of the 96-byte records when per-warp scratch is available.  The comparator reads the
+// key alone, so the sequence of comparisons and exchanges -- hence the resulting permutation, ties included -- is the
+// one the sort of the records themselves would produce; the records are then moved once.
+struct KeyEnd { i64 re; u32 idx; u32 pad_; };
+struct KeyEndLt { DEVM bool operator()(const KeyEnd& a, const KeyEnd& b) const { return a.re < b.re; } };
+struct KeyScore { i64 rb; i32 score, qb; u32 idx; u32 pad_; };
+struct KeyScoreLt { DEVM bool operator()(const KeyScore& a, const KeyScore& b) const { return a.score > b.score || (a.score == b.score && (a.rb < b.rb || (a.rb == b.rb && a.qb < b.qb))); } };
+
 // stage: 0 = the whole procedure; 1 = the list is already sorted by end position (n_comp set); 2 = only the tail
 // (compaction of the survivors, order by (score desc, rb, qb), removal of identical hits)
 template <int W>
@@ -172,7 +181,22 @@ DEVNI int warp_sort_dedup_patch(const DevIndex& x, const MemOpt& opt, WarpMem& w
 {
 	LANE_DECL;
 	if (n <= 1) return n;
-	if (stage == 0) { LANE0_ONLY { ks_introsort<Reg, RegLtEnd>((size_t)n, a, RegLtEnd()); for (int i = 0; i < n; ++i) a[i].n_comp = 1; } }
+	// per-warp scratch ws.rt: first half = record staging, second half = the key array (n <= rt_cap / 2)
+	const bool by_key = W == 32 && ws.rt != nullptr && n >= 8 && n <= (ws.rt_cap >> 1);
+	if (stage == 0) {
+		if (by_key) {
+			KeyEnd* ke = (KeyEnd*)(ws.rt + ((size_t)ws.rt_cap >> 1));
+			{
+				FOR_LANES { for (int i = lane; i < n; i += W) { KeyEnd k; k.re = a[i].re; k.idx = (u32)i; k.pad_ = 0; ke[i] = k; } }
+				WARP_SYNC();
+				LANE0_ONLY { ks_introsort<KeyEnd, KeyEndLt>((size_t)n, ke, KeyEndLt()); }
+				WARP_SYNC();
+				FOR_LANES { for (int i = lane; i < n; i += W) { Reg r = a[ke[i].idx]; r.n_comp = 1; ws.rt[i] = r; } }
+				WARP_SYNC();
+				FOR_LANES { for (int i = lane; i < n; i += W) a[i] = ws.rt[i]; }
+			}
+		} else { LANE0_ONLY { ks_introsort<Reg, RegLtEnd>((size_t)n, a, RegLtEnd()); for (int i = 0; i < n; ++i) a[i].n_comp = 1; } }
+	}
 	WARP_SYNC();
 	for (int i = 1; i < n && stage < 2; ++i) {
 		Reg p = a[i];
@@ -208,7 +232,13 @@ DEVNI int warp_sort_dedup_patch(const DevIndex& x, const MemOpt& opt, WarpMem& w
 		int i, mm;
 		for (i = 0, mm = 0; i < n; ++i) if (a[i].qe > a[i].qb) { if (mm != i) a[mm++] = a[i]; else ++mm; }
 		int n2 = mm;
-		ks_introsort<Reg, RegLtScore>((size_t)n2, a, RegLtScore());
+		if (by_key) { // same permutation as sorting the records (see KeyScore)
+			KeyScore* ks = (KeyScore*)(ws.rt + ((size_t)ws.rt_cap >> 1));
+			for (i = 0; i < n2; ++i) { KeyScore k; k.rb = a[i].rb; k.score = a[i].score; k.qb = a[i].qb; k.idx = (u32)i; k.pad_ = 0; ks[i] = k; }
+			ks_introsort<KeyScore, KeyScoreLt>((size_t)n2, ks, KeyScoreLt());
+			for (i = 0; i < n2; ++i) ws.rt[i] = a[ks[i].idx];
+			for (i = 0; i < n2; ++i) a[i] = ws.rt[i];
+		} else ks_introsort<Reg, RegLtScore>((size_t)n2, a, RegLtScore());
 		for (i = 1; i < n2; ++i) if (a[i].score == a[i - 1].score && a[i].rb == a[i - 1].rb && a[i].qb == a[i - 1].qb) a[i].qe = a[i].qb;
 		for (i = 1, mm = 1; i < n2; ++i) if (a[i].qe > a[i].qb) { if (mm != i) a[mm++] = a[i]; else ++mm; }
 		m = n2 < 1 ? n2 : mm;
@@ -346,7 +376,7 @@ DEVNI void warp_chain2aln(const DevIndex& x, const MemOpt& opt, WarpMem& wm, War
 //     all pairs that could be examined detects candidates first.
 #define SDP_FAST_MIN 24
 #ifdef B200_SIM
-static long g_sim_sdp[5]; // kernel-debug harness only: calls, tie fallbacks (end), patch-candidate fallbacks, tie fallbacks (score), completed
+static long g_sim_sdp[8]; // kernel-debug harness only: calls, tie fallbacks (end), patch-candidate fallbacks, tie fallbacks (score), completed
 #define SDP_STAT(k) (++g_sim_sdp[k])
 #else
 #define SDP_STAT(k) ((void)0)

@@ -389,6 +389,138 @@ DEVNI void rescue_sw(const DevIndex& x, const MemOpt& opt, WarpMem& wm, WarpScra
 	WARP_SYNC();
 }
 
+// the region a finished alignment task contributes (false: the task found nothing usable)
+DEV bool rescue_make_reg(const MemOpt& opt, i64 l_pac, const Reg& a, const SwTask& t, int l_ms, Reg& b)
+{
+	if (!(t.score >= opt.min_seed_len && t.qb >= 0)) return false;
+	const int is_rev = t.is_rev;
+	memset(&b, 0, sizeof(Reg));
+	b.rid = a.rid; b.is_alt = a.is_alt;
+	b.qb = is_rev ? l_ms - (t.qe + 1) : t.qb;
+	b.qe = is_rev ? l_ms - t.qb : t.qe + 1;
+	b.rb = is_rev ? (l_pac << 1) - (t.rb + t.te + 1) : t.rb + t.tb;
+	b.re = is_rev ? (l_pac << 1) - (t.rb + t.tb) : t.rb + t.te + 1;
+	b.score = t.score; b.csub = t.score2; b.secondary = -1;
+	b.seedcov = (int)((b.re - b.rb < b.qe - b.qb ? b.re - b.rb : b.qe - b.qb) >> 1);
+	return true;
+}
+
+DEV bool sdp_redundant(const MemOpt& opt, const Reg& p, const Reg& q) // the test of mem_sort_dedup_patch; p ends after q
+{
+	i64 or_ = q.re - p.rb;
+	i64 oq = q.qb < p.qb ? q.qe - p.qb : p.qe - q.qb;
+	i64 mr = q.re - q.rb < p.re - p.rb ? q.re - q.rb : p.re - p.rb;
+	i64 mq = q.qe - q.qb < p.qe - p.qb ? q.qe - q.qb : p.qe - p.qb;
+	return (float)or_ > opt.mask_level_redun * (float)mr && (float)oq > opt.mask_level_redun * (float)mq;
+}
+
+// mem_matesw's "insert the hit, then mem_sort_dedup_patch" for ONE new hit b on a SETTLED list (in final order, all
+// end positions and all (score, rb, qb) keys distinct, every pair within scan range already found non-redundant):
+// O(n / 32) per lane instead of two sorts.  Why this is exact: with all end positions distinct the order of the scan is
+// fixed, a new element can only shorten the scans of the others (never extend them), and pairs of old elements were
+// examined in the same orientation before -- so only pairs that involve b can have an effect:
+//   * b's own scan walks down the elements that end before it, on its contig, within max_chain_gap, until the
+//     nearest element of another contig; the first redundant one with a higher score removes b, redundant ones met
+//     before that are removed by b;
+//   * the elements that end after b and reach it (same contig, start within max_chain_gap of b's end, no element of
+//     another contig in between) meet b in ascending order of their ends while it is alive: a redundant one with a
+//     lower score is removed, the first redundant one with a score >= b's removes b.
+// Returns the new length, or -1 when an equal end position / equal key makes the order the reference's unstable sort
+// would produce observable (the caller then takes the general path).  *settled stays true only if nothing was removed.
+template <int W>
+DEVNI int rescue_insert_settled(const MemOpt& opt, WarpScratch& ws, Reg* ma, int nm, const Reg& b, bool* settled)
+{
+	LANE_DECL;
+	const i64 BIG = (i64)1 << 62;
+	// pass 1: ties, the nearest elements of other contigs below / above b's end
+	WV(bool, tie); WV(i64, blo); WV(i64, bhi);
+	FOR_LANES {
+		bool tv = false; i64 lo = -BIG, hi = BIG;
+		for (int i = lane; i < nm; i += W) {
+			const Reg& e = ma[i];
+			tv |= e.re == b.re || (e.score == b.score && e.rb == b.rb && e.qb == b.qb);
+			if (e.rid != b.rid) { if (e.re < b.re) lo = e.re > lo ? e.re : lo; else hi = e.re < hi ? e.re : hi; }
+		}
+		L_(tie) = tv; L_(blo) = lo; L_(bhi) = hi;
+	}
+	SDP_STAT(5);
+	if (wv_ballot(tie) != 0u) { SDP_STAT(6); return -1; }
+	const i64 B_lo = wv_reduce_max64(blo), B_hi = wv_reduce_min64(bhi);
+	// pass 2: b's own scan (downwards): the redundant element with a higher score that ends last stops it
+	WV(i64, rs);
+	FOR_LANES {
+		i64 v = -BIG;
+		for (int i = lane; i < nm; i += W) {
+			const Reg& e = ma[i];
+			if (e.rid == b.rid && e.re < b.re && e.re > B_lo && b.rb < e.re + opt.max_chain_gap && sdp_redundant(opt, b, e) && b.score < e.score) v = e.re > v ? e.re : v;
+		}
+		L_(rs) = v;
+	}
+	const i64 R_star = wv_reduce_max64(rs);
+	bool b_alive = R_star == -BIG;
+	// pass 3: the elements above that reach b; the first (lowest end) redundant one with score >= b's removes b
+	i64 R_hat = BIG;
+	if (b_alive) {
+		WV(i64, rh);
+		FOR_LANES {
+			i64 v = BIG;
+			for (int i = lane; i < nm; i += W) {
+				const Reg& e = ma[i];
+				if (e.rid == b.rid && e.re > b.re && e.re < B_hi && e.rb < b.re + opt.max_chain_gap && sdp_redundant(opt, e, b) && !(e.score < b.score)) v = e.re < v ? e.re : v;
+			}
+			L_(rh) = v;
+		}
+		R_hat = wv_reduce_min64(rh);
+		if (R_hat != BIG) b_alive = false;
+	}
+	// pass 4: survivors in order, b at its rank; built in the scratch, then copied back
+	Reg* t = ws.rt;
+	int n_out = 0, n_del = 0;
+	bool placed = !b_alive;
+	for (int i0 = 0; i0 < nm; i0 += W) {
+		WV(bool, keep); WV(bool, before);
+		FOR_LANES {
+			const int i = i0 + lane;
+			bool kp = false, bf = false;
+			if (i < nm) {
+				const Reg& e = ma[i];
+				bool del = false;
+				if (e.rid == b.rid) {
+					if (e.re < b.re) del = e.re > B_lo && e.re > R_star && b.rb < e.re + opt.max_chain_gap && !(b.score < e.score) && sdp_redundant(opt, b, e);
+					else if (R_star == -BIG) del = e.re < B_hi && e.re < R_hat && e.rb < b.re + opt.max_chain_gap && e.score < b.score && sdp_redundant(opt, e, b);
+				}
+				kp = !del;
+				bf = e.score > b.score || (e.score == b.score && (e.rb < b.rb || (e.rb == b.rb && e.qb < b.qb))); // e sorts before b
+			}
+			L_(keep) = kp; L_(before) = bf;
+		}
+		const u32 km = wv_ballot(keep), bm = wv_ballot(before);
+		const int cnt = i0 + W <= nm ? W : nm - i0;
+		const u32 valid = cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u);
+		// the list is ordered, so the elements that sort before b form a prefix: b goes in front of the first one that does not
+		u32 after = ~bm & valid;
+		int split = (!placed && after) ? __ffs(after) - 1 : -1; // lane index in this chunk in front of which b is placed
+		FOR_LANES {
+			const int i = i0 + lane;
+			if (i < nm && ((km >> lane) & 1u)) {
+				int pos = n_out + __popc(km & ((1u << lane) - 1u));
+				if (split >= 0 && lane >= split) ++pos;
+				t[pos] = ma[i];
+			}
+		}
+		if (split >= 0) { ONE_LANE { Reg bb = b; bb.n_comp = 1; t[n_out + __popc(km & ((1u << split) - 1u))] = bb; } placed = true; ++n_out; }
+		n_out += __popc(km);
+		n_del += cnt - __popc(km);
+	}
+	if (!placed) { ONE_LANE { Reg bb = b; bb.n_comp = 1; t[n_out] = bb; } ++n_out; }
+	WARP_SYNC();
+	FOR_LANES { for (int i = lane; i < n_out; i += W) ma[i] = t[i]; }
+	WARP_SYNC();
+	*settled = n_del == 0 && b_alive;
+	if (!*settled) SDP_STAT(7);
+	return n_out;
+}
+
 // the hit of one finished alignment task, inserted by score into the mate's list (false: no room)
 DEV bool rescue_insert(const MemOpt& opt, i64 l_pac, const Reg& a, const SwTask& t, int l_ms, Reg* ma, int* n_ma, int ma_cap)
 {
@@ -460,10 +592,20 @@ DEV bool rescue_apply_all(const DevIndex& x, const MemOpt& opt, const PeStat* pe
 		const Reg a = io.snap[io.reg_off[r] + k];
 		int skip[4];
 		for (int d = 0; d < 4; ++d) skip[d] = pes[d].failed ? 1 : 0;
-		for (int i = 0; i < nm; ++i) {
-			i64 dist;
-			int d = infer_dir(l_pac, a.rb, ma[i].rb, &dist);
-			if (dist >= pes[d].low && dist <= pes[d].high) skip[d] = 1;
+		{ // which orientations already have a hit at a proper distance (lanes share the list)
+			WV(int, sk);
+			FOR_LANES {
+				int bits = 0;
+				for (int i = lane; i < nm; i += W) {
+					i64 dist;
+					int d = infer_dir(l_pac, a.rb, ma[i].rb, &dist);
+					if (dist >= pes[d].low && dist <= pes[d].high) bits |= 1 << d;
+				}
+				L_(sk) = bits;
+			}
+			int all = 0;
+			for (int d = 0; d < 4; ++d) { WV(bool, bt); FOR_LANES { L_(bt) = (L_(sk) >> d & 1) != 0; } if (wv_ballot(bt) != 0u) all |= 1 << d; }
+			for (int d = 0; d < 4; ++d) if (all >> d & 1) skip[d] = 1;
 		}
 		if (skip[0] + skip[1] + skip[2] + skip[3] == 4) continue;
 		const u8* state = io.spec_state + (io.reg_off[r] + k) * 4;
@@ -473,18 +615,24 @@ DEV bool rescue_apply_all(const DevIndex& x, const MemOpt& opt, const PeStat* pe
 		int n = 0;
 		for (int d = 0; d < 4; ++d) {
 			if (skip[d]) continue;
+			bool deduped = false; // this orientation's de-duplication has been done (fused with the insertion)
 			if (state[d] == SW_RUN) {
 				const SwTask t = io.tasks[tix[d]];
-				int nm2 = nm; bool room = true;
-				LANE0_ONLY { room = rescue_insert(opt, l_pac, a, t, l_ms, ma, &nm2, ma_cap); }
-				WARP_SYNC();
-				{ WV(int, nv); FOR_LANES { L_(nv) = room ? nm2 : -1; } nm2 = wv_get(nv, 0); }
-				if (nm2 < 0) { ONE_LANE { atomic_or_u32(ws.err, ERR_REG_OVERFLOW); io.n_reg[m] = (u32)nm; } return true; }
-				if (nm2 != nm) settled = false;
-				nm = nm2;
+				Reg b;
+				if (rescue_make_reg(opt, l_pac, a, t, l_ms, b)) {
+					if (nm >= ma_cap) { ONE_LANE { atomic_or_u32(ws.err, ERR_REG_OVERFLOW); io.n_reg[m] = (u32)nm; } return true; }
+					int nm2 = -1;
+					if (W == 32 && settled && nm >= SDP_FAST_MIN && nm + 1 <= ws.rt_cap && ws.rt != nullptr) nm2 = rescue_insert_settled<W>(opt, ws, ma, nm, b, &settled);
+					if (nm2 >= 0) { nm = nm2; deduped = true; }
+					else {
+						LANE0_ONLY { int i, tmp; for (i = 0; i < nm; ++i) if (ma[i].score < b.score) break; tmp = i; for (i = nm; i > tmp; --i) ma[i] = ma[i - 1]; ma[tmp] = b; }
+						WARP_SYNC();
+						++nm; settled = false;
+					}
+				}
 				++n;
 			}
-			if (n && !settled) nm = warp_sort_dedup_fast<W>(x, opt, wm, ws, nullptr, nullptr, nm, ma, &settled);
+			if (n && !deduped && !settled) nm = warp_sort_dedup_fast<W>(x, opt, wm, ws, nullptr, nullptr, nm, ma, &settled);
 		}
 	}
 	ONE_LANE { io.n_reg[m] = (u32)nm; }

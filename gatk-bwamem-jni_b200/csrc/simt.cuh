@@ -57,6 +57,10 @@ template <int W, class T> DEV T wv_get_(const T& v, int l) { return W == 32 ? __
 #define wv_reduce_min(v) wv_reduce_min_<W>(v)
 #define wv_ballot(p) wv_ballot_<W>(p)
 #define wv_get(v, l) wv_get_<W>(v, l)
+template <int W> DEV i64 wv_reduce_max64_(const i64& v) { i64 r = v; if (W == 32) for (int d = 16; d; d >>= 1) { i64 o = __shfl_xor_sync(FULLMASK, r, d); r = o > r ? o : r; } return r; }
+template <int W> DEV i64 wv_reduce_min64_(const i64& v) { i64 r = v; if (W == 32) for (int d = 16; d; d >>= 1) { i64 o = __shfl_xor_sync(FULLMASK, r, d); r = o < r ? o : r; } return r; }
+#define wv_reduce_max64(v) wv_reduce_max64_<W>(v)
+#define wv_reduce_min64(v) wv_reduce_min64_<W>(v)
 // full-mask vote of a thread-per-item kernel whose 32 lanes all take part (persistent queue kernels)
 DEV bool lanes_all(bool p) { return __all_sync(FULLMASK, p) != 0; }
 DEV u64 atomic_add_u64(u64* p, u64 v) { return (u64)atomicAdd((unsigned long long*)p, (unsigned long long)v); }
@@ -88,9 +92,15 @@ template <int W> DEV int wv_reduce_max_(const int (&v)[32]) { int m = v[0]; for 
 template <int W> DEV int wv_reduce_min_(const int (&v)[32]) { int m = v[0]; for (int l = 1; l < W; ++l) m = v[l] < m ? v[l] : m; return m; }
 template <int W> DEV u32 wv_ballot_(const bool (&p)[32]) { u32 m = 0; for (int l = 0; l < W; ++l) m |= (u32)(p[l] ? 1u : 0u) << l; return m; }
 template <int W, class T> DEV T wv_get_(const T (&v)[32], int l) { return v[l]; }
+template <int W> DEV i64 wv_reduce_max64_(const i64 (&v)[32]) { i64 m = v[0]; for (int l = 1; l < W; ++l) m = v[l] > m ? v[l] : m; return m; }
+template <int W> DEV i64 wv_reduce_min64_(const i64 (&v)[32]) { i64 m = v[0]; for (int l = 1; l < W; ++l) m = v[l] < m ? v[l] : m; return m; }
+template <int W> DEV int wv_reduce_add_(const int (&v)[32]) { int m = 0; for (int l = 0; l < W; ++l) m += v[l]; return m; }
 #define wv_shfl_up(dst, src, d) wv_shfl_up_<W>(dst, src, d)
 #define wv_reduce_max(v) wv_reduce_max_<W>(v)
 #define wv_reduce_min(v) wv_reduce_min_<W>(v)
+#define wv_reduce_max64(v) wv_reduce_max64_<W>(v)
+#define wv_reduce_min64(v) wv_reduce_min64_<W>(v)
+#define wv_reduce_add(v) wv_reduce_add_<W>(v)
 #define wv_ballot(p) wv_ballot_<W>(p)
 #define wv_get(v, l) wv_get_<W>(v, l)
 DEV bool lanes_all(bool p) { return p; } // the harness runs one thread at a time

@@ -128,3 +128,28 @@ def first_diff(a: bytes, b: bytes, blob: bytes, paired: bool):
         if ra[i] != rb[i]:
             return f"read {i} ({reads[i].decode('latin-1')}):\n  A={ra[i]}\n  B={rb[i]}"
     return "streams differ but decoded records are equal"
+
+
+def repeat_family_image():
+    """(genome, image) of a 1.5 Mbp genome carrying 1500 copies (3 % divergence) of one 320-bp element: reads drawn from
+    the copies have hundreds of hits, which drives the warp-level chaining, the per-seed extension tasks, the
+    warp-cooperative region de-duplication and mate-rescue chains of max_matesw hits with incremental list updates."""
+    import numpy as np
+    rng = np.random.default_rng(5)
+    L = 1_500_000
+    codes = rng.integers(0, 4, L).astype(np.uint8)
+    cons = rng.integers(0, 4, 320).astype(np.uint8)
+    iv = []
+    for _ in range(1500):
+        p = int(rng.integers(1000, L - 2000))
+        c = cons.copy()
+        m = rng.random(320) < 0.03
+        c[m] = rng.integers(0, 4, int(m.sum()))
+        codes[p:p + 320] = c
+        iv.append((p, p + 320))
+    bases = np.frombuffer(b"ACGT", dtype=np.uint8)[codes].copy()
+    g = simdata.Genome(bases, [L], ["chrR"], np.array(iv, dtype=np.int64))
+    img = os.path.join(workdir(), "repeat_family.img")
+    if not os.path.exists(img):
+        simdata.build_image(g, img)
+    return g, img

@@ -4,7 +4,7 @@ orchestration (engine_impl.inl), every device function's logic and the record en
 parity gate is tests/test_parity_gpu.py on the B200."""
 import pytest
 
-from common import first_diff, oracle_lib, run_blob, sim_lib, simdata, synth_image
+from common import first_diff, oracle_lib, repeat_family_image, run_blob, sim_lib, simdata, synth_image
 from test_oracle_kat import run_kat
 
 
@@ -46,5 +46,14 @@ def test_sim_rescue_fallback_path(small_genome, monkeypatch):
     a = run_blob(oracle_lib(), img, blob, 2)
     assert run_blob(sim_lib(), img, blob, 2) == a
     monkeypatch.setenv("B200_TEST_RESCUE_FALLBACK", "1")
+    b = run_blob(sim_lib(), img, blob, 2)
+    assert a == b, first_diff(a, b, blob, True)
+
+
+def test_sim_repeat_family_stress():
+    """Reads with hundreds of hits each (see common.repeat_family_image)."""
+    g, img = repeat_family_image()
+    blob, _ = simdata.make_reads(g, 91, 150, 150, True, repeat_read_frac=0.7, err_rate=0.01)
+    a = run_blob(oracle_lib(), img, blob, 2)
     b = run_blob(sim_lib(), img, blob, 2)
     assert a == b, first_diff(a, b, blob, True)

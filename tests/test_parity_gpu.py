@@ -3,7 +3,7 @@ options and batch boundaries.  Bar: the int32 record stream is byte-identical (f
 MD, AS, XS, XA, mate fields)."""
 import pytest
 
-from common import bwa, engine_lib, first_diff, oracle_lib, run_blob, simdata, synth_image
+from common import bwa, engine_lib, first_diff, oracle_lib, repeat_family_image, run_blob, simdata, synth_image
 from test_oracle_kat import run_kat
 
 pytestmark = pytest.mark.gpu
@@ -121,6 +121,20 @@ def test_repeat_family_genome(monkeypatch):
     a = run_blob(oracle_lib(), img, blob, 2, None, setup)
     b = run_blob(engine_lib(), img, blob, 2, None, setup)
     assert a == b, first_diff(a, b, blob, True)
+
+
+@pytest.mark.parametrize("paired", [False, True], ids=["se", "pe"])
+def test_repeat_family_stress(paired):
+    """1500 copies of one element: hundreds of hits per read, rescue chains of max_matesw hits (common.repeat_family_image)."""
+    g, img = repeat_family_image()
+    blob, _ = simdata.make_reads(g, 92, 3000, 150, paired, repeat_read_frac=0.7, err_rate=0.01)
+
+    def setup(al):
+        al.setNThreadsOption(16)
+    flag = 2 if paired else 0
+    a = run_blob(oracle_lib(), img, blob, flag, None, setup)
+    b = run_blob(engine_lib(), img, blob, flag, None, setup)
+    assert a == b, first_diff(a, b, blob, paired)
 
 
 def test_repeat_calls_are_deterministic(small_genome):
