@@ -347,7 +347,14 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 	P.seed_lcap = 8; P.seed_shared_read = 0; // few candidates survive per position; the read is walked sequentially (L1)
 	if (getenv("B200_SEED_LCAP")) { int v = atoi(getenv("B200_SEED_LCAP")); if (v >= 1 && v <= SEED_LCAP) P.seed_lcap = v; } // tuning aids
 	if (getenv("B200_SEED_SHARED_READ")) P.seed_shared_read = atoi(getenv("B200_SEED_SHARED_READ"));
-	RT_THREADS_QUEUE_SMEM(body_seed_q, P, (int64_t)n_reads, P.seed_shared ? seed_block_smem_bytes(THREADS_PER_BLOCK, max_len, P.seed_lcap, P.seed_shared_read) : 0);
+	{
+		const size_t ssm = P.seed_shared ? seed_block_smem_bytes(THREADS_PER_BLOCK, max_len, P.seed_lcap, P.seed_shared_read) : 0;
+		if (getenv("B200_SEED_ONE_LAUNCH")) RT_THREADS_QUEUE_SMEM(body_seed_q, P, (int64_t)n_reads, ssm);
+		else { // rounds 1/2 (two kinds of extension steps) and round 3 (one kind: lock-step lanes) as separate launches
+			RT_THREADS_QUEUE_SMEM(body_seed12_q, P, (int64_t)n_reads, ssm);
+			RT_THREADS_QUEUE_SMEM(body_seed3_q, P, (int64_t)n_reads, ssm);
+		}
+	}
 	g_hp.mark("launch1");
 	uint64_t T = rt_scan_u32(P.n_seed, P.seed_off, n_reads);
 	g_hp.mark("seed_sync");

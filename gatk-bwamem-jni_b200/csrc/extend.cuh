@@ -278,28 +278,43 @@ DEVNI void warp_chain2aln(const DevIndex& x, const MemOpt& opt, WarpMem& wm, War
 	for (int k = cn - 1; k >= 0; --k) {
 		const Seed s = seeds[(u32)srt[k]];
 		int n = *n_av, i;
-		for (i = 0; i < n; ++i) { // inside an earlier region and close to its diagonal?
-			const Reg& p = av[i];
-			if (s.rbeg < p.rb || s.rbeg + s.len > p.re || s.qbeg < p.qb || s.qbeg + s.len > p.qe) continue;
-			if ((double)(s.len - p.seedlen0) > .1 * (double)l_query) continue;
-			int qd = s.qbeg - p.qb; i64 rd = s.rbeg - p.rb;
-			int max_gap = cal_max_gap(opt, qd < rd ? qd : (int)rd);
-			int w = max_gap < p.w ? max_gap : p.w;
-			if (qd - rd < w && rd - qd < w) break;
-			qd = p.qe - (s.qbeg + s.len); rd = p.re - (s.rbeg + s.len);
-			max_gap = cal_max_gap(opt, qd < rd ? qd : (int)rd);
-			w = max_gap < p.w ? max_gap : p.w;
-			if (qd - rd < w && rd - qd < w) break;
-		}
-		if (i < n) { // contained: extend anyway only if an overlapping seed lies on another diagonal
-			for (i = k + 1; i < cn; ++i) {
-				if (srt[i] == 0) continue;
-				const Seed& t = seeds[(u32)srt[i]];
-				if ((double)t.len < (double)s.len * .95) continue;
-				if (s.qbeg <= t.qbeg && s.qbeg + s.len - t.qbeg >= s.len >> 2 && t.qbeg - s.qbeg != t.rbeg - s.rbeg) break;
-				if (t.qbeg <= s.qbeg && t.qbeg + t.len - s.qbeg >= s.len >> 2 && s.qbeg - t.qbeg != s.rbeg - t.rbeg) break;
+		// inside an earlier region and close to its diagonal?  (only WHETHER some region qualifies matters: lanes share the list)
+		bool contained = false;
+		{
+			WV(bool, hit);
+			FOR_LANES {
+				bool h = false;
+				for (int t = lane; t < n && !h; t += W) {
+					const Reg& p = av[t];
+					if (s.rbeg < p.rb || s.rbeg + s.len > p.re || s.qbeg < p.qb || s.qbeg + s.len > p.qe) continue;
+					if ((double)(s.len - p.seedlen0) > .1 * (double)l_query) continue;
+					int qd = s.qbeg - p.qb; i64 rd = s.rbeg - p.rb;
+					int max_gap = cal_max_gap(opt, qd < rd ? qd : (int)rd);
+					int w = max_gap < p.w ? max_gap : p.w;
+					if (qd - rd < w && rd - qd < w) { h = true; break; }
+					qd = p.qe - (s.qbeg + s.len); rd = p.re - (s.rbeg + s.len);
+					max_gap = cal_max_gap(opt, qd < rd ? qd : (int)rd);
+					w = max_gap < p.w ? max_gap : p.w;
+					if (qd - rd < w && rd - qd < w) { h = true; break; }
+				}
+				L_(hit) = h;
 			}
-			if (i == cn) { ONE_LANE { srt[k] = 0; } WARP_SYNC(); continue; }
+			contained = wv_ballot(hit) != 0u;
+		}
+		if (contained) { // extend anyway only if an overlapping seed lies on another diagonal
+			WV(bool, other);
+			FOR_LANES {
+				bool h = false;
+				for (int t = k + 1 + lane; t < cn && !h; t += W) {
+					if (srt[t] == 0) continue;
+					const Seed& u = seeds[(u32)srt[t]];
+					if ((double)u.len < (double)s.len * .95) continue;
+					if (s.qbeg <= u.qbeg && s.qbeg + s.len - u.qbeg >= s.len >> 2 && u.qbeg - s.qbeg != u.rbeg - s.rbeg) h = true;
+					else if (u.qbeg <= s.qbeg && u.qbeg + u.len - s.qbeg >= s.len >> 2 && s.qbeg - u.qbeg != s.rbeg - u.rbeg) h = true;
+				}
+				L_(other) = h;
+			}
+			if (wv_ballot(other) == 0u) { ONE_LANE { srt[k] = 0; } WARP_SYNC(); continue; }
 		}
 		if (n >= av_cap) { ONE_LANE { atomic_or_u32(ws.err, ERR_REG_OVERFLOW); } return; }
 		Reg a;

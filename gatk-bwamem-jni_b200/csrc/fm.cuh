@@ -187,7 +187,12 @@ DEV void intv_set(Intv& t, const BiIntv& b, u32 beg, u32 end) { t.x0 = b.x0; t.x
 // Reads are not assigned to lanes statically: `src.next` hands the lane its next read (a batch-wide counter), fetching is
 // one more state of the machine, and a full-mask vote per trip is both the exit test and the point where the lanes
 // of the warp meet again -- no lane idles while a neighbour works through a read with more extensions.
-template <class Src>
+//
+// PHASES selects what one launch does for a read: 3 = the three rounds in one machine; 1 = rounds 1 and 2 (SMEMs and
+// re-seeding, two kinds of extension steps); 2 = round 3 alone (forward-only seeds: one kind of step, so the lanes of a
+// warp run in lock-step).  Rounds 1/2 and round 3 are independent of each other and the interval list is ordered by
+// (begin, end) at the end, so running them in two launches yields the same list.
+template <int PHASES, class Src>
 DEV void fm_collect_queue(const DevIndex& x, const MemOpt& opt, const SeedWork& wk, Src& src)
 {
 	const int split_len = (int)(opt.min_seed_len * opt.split_factor + .499);
@@ -225,13 +230,13 @@ DEV void fm_collect_queue(const DevIndex& x, const MemOpt& opt, const SeedWork& 
 				// the read's codes: shared copy when provided
 				q = qg; qst = 1;
 				if (wk.qs) { for (int t = 0; t < len; ++t) wk.qs[(size_t)t * wk.qstride] = qg[t]; q = wk.qs; qst = (size_t)wk.qstride; }
-				o.n = 0; o.overflow = false;
 				round = 1; xx = 0; k2 = 0; old_n = 0; n_prev = n_curr = 0; have_out = false; last_beg = 0;
-				st = SM_NEXT_R1;
+				if (PHASES == 2) { round = 3; st = opt.max_mem_intv > 0 ? SM_NEXT_R3 : SM_DONE; } // (src.next set o.n to what rounds 1/2 left)
+				else st = SM_NEXT_R1;
 				break;
 			case SM_DONE: { // the read is finished: order its intervals by (beg, end) and hand them over
 				// Equal keys are identical intervals, so the sort algorithm is unobservable here (unlike the hazard-H4 sorts).
-				for (int a = 1; a < o.n; ++a) {
+				for (int a = 1; a < o.n && PHASES != 1; ++a) {
 					Intv t = o.v[a];
 					u64 key = (u64)t.beg << 32 | t.end;
 					int b = a - 1;
@@ -257,7 +262,7 @@ DEV void fm_collect_queue(const DevIndex& x, const MemOpt& opt, const SeedWork& 
 					go = true;
 					break;
 				}
-				if (!go) { xx = 0; round = 3; st = opt.max_mem_intv > 0 ? SM_NEXT_R3 : SM_DONE; break; }
+				if (!go) { xx = 0; round = 3; st = (PHASES == 3 && opt.max_mem_intv > 0) ? SM_NEXT_R3 : SM_DONE; break; }
 				if (Q(start) > 3) { ++k2; break; } // (an SMEM never holds an ambiguous base; kept for fidelity)
 				fm_set_intv(x, Q(start), ik); ik_end = (u32)(start + 1); n_curr = 0; i = start + 1;
 				st = SM_FWD;

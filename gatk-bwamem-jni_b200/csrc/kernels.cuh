@@ -78,7 +78,10 @@ HOSTDEV size_t seed_block_smem_bytes(int block_threads, int max_len, int lcap, i
 #ifdef B200_SIM
 static uint4 g_sim_seed_l[SEED_LCAP];
 #endif
-struct SeedSrc { // hands reads to the lanes of the seeding kernel and takes their interval lists back
+// hands reads to the lanes of a seeding kernel and takes their interval lists back.  PHASES as in fm_collect_queue:
+// 1 leaves the unsorted list of rounds 1/2 in place for the round-3 launch (2), which appends, sorts and counts.
+template <int PHASES>
+struct SeedSrc {
 	const BatchParams& P; i64 n; u32* counter; i64 r;
 	DEVM SeedSrc(const BatchParams& P_, i64 n_, u32* c_) : P(P_), n(n_), counter(c_), r(-1) {}
 	DEVM bool next(int& len, const u8*& seq, IntvOut& o)
@@ -88,23 +91,25 @@ struct SeedSrc { // hands reads to the lanes of the seeding kernel and takes the
 			if (r >= n) return false;
 			len = (int)(P.seq_off[r + 1] - P.seq_off[r] - 1);
 			if (len >= P.opt.min_seed_len && len <= P.smem_cap) break;
-			if (len > P.smem_cap) atomic_or_u32(P.err, ERR_QLEN_OVERFLOW);
+			if (len > P.smem_cap && PHASES != 2) atomic_or_u32(P.err, ERR_QLEN_OVERFLOW);
 			P.n_intv[r] = 0; P.n_seed[r] = 0; // no seed can exist
 		}
 		seq = P.seq + P.seq_off[r];
-		o.v = P.intv + (size_t)r * P.intv_cap; o.n = 0; o.cap = P.intv_cap; o.overflow = false;
+		o.v = P.intv + (size_t)r * P.intv_cap; o.n = PHASES == 2 ? (int)P.n_intv[r] : 0; o.cap = P.intv_cap; o.overflow = false;
 		return true;
 	}
 	DEVM void finish(const IntvOut& o)
 	{
 		if (o.overflow) atomic_or_u32(P.err, ERR_INTV_OVERFLOW);
+		P.n_intv[r] = (u32)o.n;
+		if (PHASES == 1) return;
 		u32 ns = 0;
 		for (int i = 0; i < o.n; ++i) ns += (u32)(o.v[i].size < (u64)P.opt.max_occ ? o.v[i].size : (u64)P.opt.max_occ);
-		P.n_intv[r] = (u32)o.n;
 		P.n_seed[r] = ns;
 	}
 };
-DEV void body_seed_q(const BatchParams& P, i64 n, u32* counter, i64 tid)
+template <int PHASES>
+DEV void seed_queue(const BatchParams& P, i64 n, u32* counter, i64 tid)
 {
 	SeedWork wk;
 	wk.G = P.smem_scratch + (size_t)tid * P.smem_cap; wk.gcap = P.smem_cap;
@@ -118,9 +123,12 @@ DEV void body_seed_q(const BatchParams& P, i64 n, u32* counter, i64 tid)
 		if (P.seed_shared_read) { wk.qs = tsm_ + (size_t)blockDim.x * P.seed_lcap * 16 + threadIdx.x; wk.qstride = (int)blockDim.x; }
 #endif
 	}
-	SeedSrc src(P, n, counter);
-	fm_collect_queue(P.x, P.opt, wk, src);
+	SeedSrc<PHASES> src(P, n, counter);
+	fm_collect_queue<PHASES>(P.x, P.opt, wk, src);
 }
+DEV void body_seed_q(const BatchParams& P, i64 n, u32* counter, i64 tid) { seed_queue<3>(P, n, counter, tid); }    // all rounds in one launch
+DEV void body_seed12_q(const BatchParams& P, i64 n, u32* counter, i64 tid) { seed_queue<1>(P, n, counter, tid); }  // SMEMs + re-seeding
+DEV void body_seed3_q(const BatchParams& P, i64 n, u32* counter, i64 tid) { seed_queue<2>(P, n, counter, tid); }   // forward-only seeds, sort, count
 
 // ---- sal: one thread per lookup ------------------------------------------------------------------
 DEV void body_sal(const BatchParams& P, i64 t)
