@@ -115,8 +115,10 @@ static void rt_sort_u64(const uint64_t* in, uint64_t* out, uint64_t n)
 		} }
 
 // warp kernel whose item count lives in device memory (written by the preceding kernel of the same stream)
-#define DEF_WARP_KERNEL_DEVN(wbody) \
-	__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_##wbody(const __grid_constant__ BatchParams P, const u32* n_ptr, u32* counter) { \
+#define DEF_WARP_KERNEL_DEVN(wbody) DEF_WARP_KERNEL_DEVN_LB(wbody, __launch_bounds__(WARPS_PER_BLOCK * 32))
+#define DEF_WARP_KERNEL_DEVN_MB(wbody, minb) DEF_WARP_KERNEL_DEVN_LB(wbody, __launch_bounds__(WARPS_PER_BLOCK * 32, minb))
+#define DEF_WARP_KERNEL_DEVN_LB(wbody, bounds) \
+	__global__ void bounds k_##wbody(const __grid_constant__ BatchParams P, const u32* n_ptr, u32* counter) { \
 		extern __shared__ __align__(16) u8 smem_[]; \
 		const int wib = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31); \
 		const i64 slot = (i64)blockIdx.x * WARPS_PER_BLOCK + wib; \
@@ -157,7 +159,10 @@ DEF_WARP_KERNEL_DEVN(wbody_rescue_apply_heavy)
 DEF_THREAD_KERNEL(body_rescue_apply)
 DEF_THREAD_KERNEL(body_rescue_gen_multi)
 DEF_THREAD_KERNEL(body_rescue_apply_multi)
-DEF_WARP_KERNEL_DEVN(wbody_rescue_sw)
+#ifndef RESCUE_SW_MIN_BLOCKS
+#define RESCUE_SW_MIN_BLOCKS 4 // 128 registers: four blocks (16 warps) per SM; the kernel is bound by the latency of its row recurrence
+#endif
+DEF_WARP_KERNEL_DEVN_MB(wbody_rescue_sw, RESCUE_SW_MIN_BLOCKS)
 DEF_WARP_KERNEL(wbody_extend)
 DEF_THREAD_QUEUE_KERNEL(body_extend_q)
 DEF_THREAD_QUEUE_KERNEL(body_extend_task_q)
@@ -221,31 +226,38 @@ static int g_launches = 0;
 #define RT_THREADS_TID_RING(body, P, n) do { i64 n_ = (i64)(n); if (n_ > 0) { \
 	i64 nb_ = (n_ + THREADS_PER_BLOCK - 1) / THREADS_PER_BLOCK; i64 cap_ = (i64)rt_sm_count() * SEED_BLOCKS_PER_SM; if (nb_ > cap_) nb_ = cap_; \
 	size_t tsm_ = thread_block_smem_bytes(THREADS_PER_BLOCK, (P).wm_cap); \
-	cudaFuncSetAttribute(k_##body, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm_); \
+	{ static size_t set_ = 0; if (tsm_ > set_) { cudaFuncSetAttribute(k_##body, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm_); set_ = tsm_; } } \
 	k_##body<<<(unsigned)nb_, THREADS_PER_BLOCK, tsm_, rt_stream()>>>(P, n_); ++g_launches; } g_timer.mark(#body); } while (0)
 // persistent queue kernels with an explicit dynamic shared-memory size (as many blocks per SM as that size allows)
 #define RT_THREADS_QUEUE_SMEM(body, P, n, bytes) do { i64 n_ = (i64)(n); if (n_ > 0) { \
 	size_t tsm_ = (bytes); \
 	i64 nb_ = (n_ + THREADS_PER_BLOCK - 1) / THREADS_PER_BLOCK; i64 per_sm_ = (i64)((227 * 1024) / (tsm_ + 1024)); if (per_sm_ < 1) per_sm_ = 1; if (per_sm_ > SEED_BLOCKS_PER_SM) per_sm_ = SEED_BLOCKS_PER_SM; \
 	i64 cap_ = (i64)rt_sm_count() * per_sm_; if (nb_ > cap_) nb_ = cap_; \
-	cudaFuncSetAttribute(k_##body, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm_); \
+	{ static size_t set_ = 0; if (tsm_ > set_) { cudaFuncSetAttribute(k_##body, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm_); set_ = tsm_; } } \
 	k_##body<<<(unsigned)nb_, THREADS_PER_BLOCK, tsm_, rt_stream()>>>(P, n_, next_counter()); ++g_launches; } g_timer.mark(#body); } while (0)
 #define RT_WARPS(wbody, P, n) do { i64 n_ = (i64)(n); if (n_ > 0) { \
 	size_t sm_ = ((warp_smem_bytes((P).wm_cap) + 15) & ~(size_t)15) * WARPS_PER_BLOCK; \
 	i64 nb_ = (n_ + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK; i64 cap_ = (i64)rt_sm_count() * WARP_BLOCKS_PER_SM; if (nb_ > cap_) nb_ = cap_; \
-	cudaFuncSetAttribute(k_##wbody, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_); \
+	{ static size_t set_ = 0; if (sm_ > set_) { cudaFuncSetAttribute(k_##wbody, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_); set_ = sm_; } } \
 	k_##wbody<<<(unsigned)nb_, WARPS_PER_BLOCK * 32, sm_, rt_stream()>>>(P, n_, next_counter()); ++g_launches; } g_timer.mark(#wbody); } while (0)
 
 #define RT_WARPS_DEVN(wbody, P, n_ptr, n_max) do { \
 	size_t sm_ = ((warp_smem_bytes((P).wm_cap) + 15) & ~(size_t)15) * WARPS_PER_BLOCK; \
 	i64 nb_ = (i64)rt_sm_count() * WARP_BLOCKS_PER_SM; \
-	cudaFuncSetAttribute(k_##wbody, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_); \
+	{ static size_t set_ = 0; if (sm_ > set_) { cudaFuncSetAttribute(k_##wbody, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_); set_ = sm_; } } \
 	k_##wbody<<<(unsigned)nb_, WARPS_PER_BLOCK * 32, sm_, rt_stream()>>>(P, n_ptr, next_counter()); ++g_launches; g_timer.mark(#wbody); } while (0)
 
 __global__ void k_relayout(const u32* src, u64 bwt_size, u32* dst, u64 n_blocks)
 {
 	for (u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x; b < n_blocks; b += (u64)gridDim.x * blockDim.x) fm_relayout_block(src, bwt_size, dst, b);
 }
+// denser suffix-array samples at load time: row k (a multiple of `dense`) walks to the next row the image samples
+__global__ void k_densify_sa(DevIndex x, u64 n_rows, u32 dense, u64* out)
+{
+	const u64 n_out = (n_rows + dense - 1) / dense;
+	for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < n_out; t += (u64)gridDim.x * blockDim.x) out[t] = fm_sa(x, t * dense);
+}
+#define RT_DENSIFY(x, n_rows, dense, out) do { k_densify_sa<<<(unsigned)(rt_sm_count() * 16), 256, 0, rt_stream()>>>((x), (n_rows), (dense), (out)); cu_ok(cudaGetLastError(), "densify"); } while (0)
 #define RT_RELAYOUT(src, size, dst, nb) do { k_relayout<<<(unsigned)(rt_sm_count() * 16), 256, 0, rt_stream()>>>((src), (size), (dst), (nb)); cu_ok(cudaGetLastError(), "relayout"); } while (0)
 
 static void rt_timer_begin() { g_timer.begin(); g_launches = 0; }

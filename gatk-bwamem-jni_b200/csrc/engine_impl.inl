@@ -123,7 +123,7 @@ struct Engine {
 	ImageView img;
 	// device-resident index
 	DevIndex dx;
-	DBuf d_bwt, d_sa, d_pac, d_ctg, d_log, d_names, d_name_off;
+	DBuf d_bwt, d_sa, d_sa_dense, d_pac, d_ctg, d_log, d_names, d_name_off;
 	std::mutex mu; // one batch at a time per index handle (re-entrant callers are serialised)
 	// batch workspace
 	DBuf b_blob, b_seq, b_seqoff, b_intv, b_nintv, b_nseed, b_smem, b_seedoff, b_rbeg, b_S, b_C, b_ord, b_tmp32, b_ck, b_ks, b_srt, b_regtmp,
@@ -190,12 +190,28 @@ inline bool Engine::upload()
 	dx.l_pac = img.l_pac; dx.n_seqs = img.n_seqs; dx.ctg_off = (const i64*)d_ctg.p; dx.pac = (const u8*)d_pac.p;
 	dx.log_tab = (const double*)d_log.p; dx.log_tab_n = LOG_TAB_N;
 	rt_sync();
+	// Spend HBM on the suffix array: the image samples every 32nd row (bwt_sa then walks ~15.5 LF steps per lookup, each
+	// a random 64-byte read); one LF-walk per 8th row at load time gives an 8-row sampling (6 GB at 3 Gbp) and ~3.5 steps.
+	// SA values are layout-independent, so results are unchanged.  BWA_B200_SA_INTV=32 keeps the image's sampling.
+	{
+		int want = 8;
+		if (const char* e = getenv("BWA_B200_SA_INTV")) want = atoi(e);
+		if (want >= 1 && want < (int)dx.sa_intv && (want & (want - 1)) == 0) {
+			const uint64_t n_rows = img.seq_len + 1, n_out = (n_rows + want - 1) / want;
+			if (d_sa_dense.ensure((size_t)n_out * 8)) {
+				RT_DENSIFY(dx, (u64)n_rows, (u32)want, d_sa_dense.as<u64>());
+				rt_sync();
+				dx.sa = d_sa_dense.as<u64>(); dx.sa_intv = (u32)want;
+				d_sa.release();
+			}
+		}
+	}
 	return true;
 }
 
 inline void Engine::close_all()
 {
-	DBuf* all[] = { &d_bwt, &d_sa, &d_pac, &d_ctg, &d_log, &d_names, &d_name_off, &b_blob, &b_seq, &b_seqoff, &b_intv, &b_nintv, &b_nseed, &b_smem,
+	DBuf* all[] = { &d_bwt, &d_sa, &d_sa_dense, &d_pac, &d_ctg, &d_log, &d_names, &d_name_off, &b_blob, &b_seq, &b_seqoff, &b_intv, &b_nintv, &b_nseed, &b_smem,
 	                &b_seedoff, &b_rbeg, &b_S, &b_C, &b_ord, &b_tmp32, &b_ck, &b_ks, &b_srt, &b_regtmp, &b_nck, &b_nks, &b_nreg, &b_regcap, &b_regoff,
 	                &b_regs, &b_snap, &b_ztmp, &b_pairv, &b_recs, &b_nrec, &b_cand, &b_pairtab, &b_var, &b_misc, &b_outwords, &b_outoff, &b_out,
 	                &b_wsz, &b_wscig, &b_wsmd, &b_wsxa, &b_wsbrow, &b_nb, &b_swtask, &b_swstate, &b_swlist, &b_tbuf, &b_redo, &b_heavy, &b_multi, &b_cand2, &b_specstate, &b_spectask, &b_nreg0, &b_rsheavy, &b_wsrt, &b_wsrkey, &b_wsrrank, &b_exttask, &b_extres, &b_ckrmax, &b_chainheavy, &b_gatask, &b_gares, &b_gaitem0, &b_gaitemn };
@@ -298,7 +314,6 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 	rt_timer_begin();
 	MemOpt opt = *opt_in; // the options live in a caller-owned buffer (…BwaMemIndex.c:146): snapshot them
 	const uint32_t n_reads = st_n_reads;
-	const std::vector<uint64_t>& seq_off = st_seq_off;
 	const int max_len = st_max_len;
 	const uint64_t blob_len = st_blob_len;
 	const bool pe = (opt.flag & MEM_F_PE) != 0;
@@ -307,12 +322,15 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 	// ---- option / shape validation: fail loudly instead of approximating
 	if (opt.e_del <= 0 || opt.e_ins <= 0 || opt.a <= 0 || opt.max_occ <= 0 || opt.min_seed_len <= 0) { last_error = "unsupported option values"; return nullptr; }
 	{
-		// mem_flt_chained_seeds (long-read seed re-scoring) is not on this path: refuse reads that would trigger it
-		for (uint32_t i = 0; i < n_reads; ++i) {
-			int l = (int)(seq_off[i + 1] - seq_off[i] - 1);
-			if (l < opt.min_seed_len) continue; // no seed can exist: the filter has nothing to act on
+		// mem_flt_chained_seeds (long-read seed re-scoring) is not on this path: refuse batches that would trigger it.
+		// It acts on a read of l bases (l >= min_seed_len) unless min_l > 0.05 l, min_l = 1.1 min_chain_weight or
+		// 5.5 ln l.  Both forms fail first for the LONGEST read (5.5 ln l - 0.05 l is concave and positive at
+		// min_seed_len), so testing max_len covers every read of the batch.
+		const int l = max_len;
+		if (l >= opt.min_seed_len) {
 			double min_l = opt.min_chain_weight ? 1.1f * opt.min_chain_weight : 5.5f * log((double)l);
-			if (!(min_l > 0.05f * l)) { last_error = "read length/min_chain_weight would enable mem_flt_chained_seeds (long-read path not built)"; return nullptr; }
+			double at_min = opt.min_chain_weight ? min_l : 5.5f * log((double)opt.min_seed_len);
+			if (!(min_l > 0.05f * l) || !(at_min > 0.05f * opt.min_seed_len)) { last_error = "read length/min_chain_weight would enable mem_flt_chained_seeds (long-read path not built)"; return nullptr; }
 		}
 	}
 	const int wm_cap = ((max_len + 15) / 16) * 16 + 32;
