@@ -139,7 +139,13 @@ DEF_THREAD_KERNEL(body_encode)
 #define SEED_MIN_BLOCKS 5
 #endif
 __global__ void __launch_bounds__(THREADS_PER_BLOCK, SEED_MIN_BLOCKS) k_body_seed_q(const __grid_constant__ BatchParams P, i64 n, u32* counter) { body_seed_q(P, n, counter, (i64)blockIdx.x * blockDim.x + threadIdx.x); }
+DEF_THREAD_QUEUE_KERNEL(body_seedF1_q)
+DEF_THREAD_QUEUE_KERNEL(body_seedF2_q)
+DEF_THREAD_QUEUE_KERNEL(body_seedB_q)
+DEF_THREAD_QUEUE_KERNEL(body_seedB2_q)
+DEF_WARP_KERNEL_DEVN(wbody_seedB_heavy)
 __global__ void __launch_bounds__(THREADS_PER_BLOCK, SEED_MIN_BLOCKS) k_body_seed12_q(const __grid_constant__ BatchParams P, i64 n, u32* counter) { body_seed12_q(P, n, counter, (i64)blockIdx.x * blockDim.x + threadIdx.x); }
+__global__ void __launch_bounds__(THREADS_PER_BLOCK, SEED_MIN_BLOCKS) k_body_seed12_fb_q(const __grid_constant__ BatchParams P, i64 n, u32* counter) { body_seed12_fb_q(P, n, counter, (i64)blockIdx.x * blockDim.x + threadIdx.x); }
 __global__ void __launch_bounds__(THREADS_PER_BLOCK, SEED_MIN_BLOCKS) k_body_seed3_q(const __grid_constant__ BatchParams P, i64 n, u32* counter) { body_seed3_q(P, n, counter, (i64)blockIdx.x * blockDim.x + threadIdx.x); }
 DEF_THREAD_KERNEL(body_sal)
 DEF_THREAD_KERNEL(body_chain)

@@ -128,7 +128,7 @@ struct Engine {
 	// batch workspace
 	DBuf b_blob, b_seq, b_seqoff, b_intv, b_nintv, b_nseed, b_smem, b_seedoff, b_rbeg, b_S, b_C, b_ord, b_tmp32, b_ck, b_ks, b_srt, b_regtmp,
 	     b_nck, b_nks, b_nreg, b_regcap, b_regoff, b_regs, b_snap, b_ztmp, b_pairv, b_recs, b_nrec, b_cand, b_pairtab, b_var, b_misc,
-	     b_outwords, b_outoff, b_out, b_wsz, b_wscig, b_wsmd, b_wsxa, b_wsbrow, b_nb, b_swtask, b_swstate, b_swlist, b_tbuf, b_redo, b_heavy, b_multi, b_cand2, b_specstate, b_spectask, b_nreg0, b_rsheavy, b_wsrt, b_wsrkey, b_wsrrank, b_exttask, b_extres, b_ckrmax, b_chainheavy, b_gatask, b_gares, b_gaitem0, b_gaitemn;
+	     b_outwords, b_outoff, b_out, b_wsz, b_wscig, b_wsmd, b_wsxa, b_wsbrow, b_nb, b_swtask, b_swstate, b_swlist, b_tbuf, b_redo, b_heavy, b_multi, b_cand2, b_specstate, b_spectask, b_nreg0, b_rsheavy, b_wsrt, b_wsrkey, b_wsrrank, b_exttask, b_extres, b_ckrmax, b_chainheavy, b_gatask, b_gares, b_gaitem0, b_gaitemn, b_seedpool, b_seedused, b_seedtask, b_seedfb;
 	Counters last_counters; uint64_t last_n_seed = 0; int n_launches = 0;
 	std::string last_error;
 
@@ -214,7 +214,7 @@ inline void Engine::close_all()
 	DBuf* all[] = { &d_bwt, &d_sa, &d_sa_dense, &d_pac, &d_ctg, &d_log, &d_names, &d_name_off, &b_blob, &b_seq, &b_seqoff, &b_intv, &b_nintv, &b_nseed, &b_smem,
 	                &b_seedoff, &b_rbeg, &b_S, &b_C, &b_ord, &b_tmp32, &b_ck, &b_ks, &b_srt, &b_regtmp, &b_nck, &b_nks, &b_nreg, &b_regcap, &b_regoff,
 	                &b_regs, &b_snap, &b_ztmp, &b_pairv, &b_recs, &b_nrec, &b_cand, &b_pairtab, &b_var, &b_misc, &b_outwords, &b_outoff, &b_out,
-	                &b_wsz, &b_wscig, &b_wsmd, &b_wsxa, &b_wsbrow, &b_nb, &b_swtask, &b_swstate, &b_swlist, &b_tbuf, &b_redo, &b_heavy, &b_multi, &b_cand2, &b_specstate, &b_spectask, &b_nreg0, &b_rsheavy, &b_wsrt, &b_wsrkey, &b_wsrrank, &b_exttask, &b_extres, &b_ckrmax, &b_chainheavy, &b_gatask, &b_gares, &b_gaitem0, &b_gaitemn };
+	                &b_wsz, &b_wscig, &b_wsmd, &b_wsxa, &b_wsbrow, &b_nb, &b_swtask, &b_swstate, &b_swlist, &b_tbuf, &b_redo, &b_heavy, &b_multi, &b_cand2, &b_specstate, &b_spectask, &b_nreg0, &b_rsheavy, &b_wsrt, &b_wsrkey, &b_wsrrank, &b_exttask, &b_extres, &b_ckrmax, &b_chainheavy, &b_gatask, &b_gares, &b_gaitem0, &b_gaitemn, &b_seedpool, &b_seedused, &b_seedtask, &b_seedfb };
 	for (DBuf* b : all) b->release();
 	if (map) munmap(map, map_len);
 	map = nullptr;
@@ -368,8 +368,28 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 	{
 		const size_t ssm = P.seed_shared ? seed_block_smem_bytes(THREADS_PER_BLOCK, max_len, P.seed_lcap, P.seed_shared_read) : 0;
 		if (getenv("B200_SEED_ONE_LAUNCH")) RT_THREADS_QUEUE_SMEM(body_seed_q, P, (int64_t)n_reads, ssm);
-		else { // rounds 1/2 (two kinds of extension steps) and round 3 (one kind: lock-step lanes) as separate launches
+		else if (!P.seed_shared || getenv("B200_SEED_FUSED_ROUNDS")) { // rounds 1/2 in one machine (two kinds of steps), round 3 alone
 			RT_THREADS_QUEUE_SMEM(body_seed12_q, P, (int64_t)n_reads, ssm);
+			RT_THREADS_QUEUE_SMEM(body_seed3_q, P, (int64_t)n_reads, ssm);
+		} else {
+			// every launch has ONE kind of extension step: forward scans (lane per read), backward sweeps (lane per scan),
+			// for round 1 and again for round 2, then round 3 (forward-only seeds; it also orders and counts the list)
+			P.seed_pool_cap = (u32)(6 * max_len + 16); // candidates of all scans of a round (14 KB per read); a read that needs more is redone below
+			if (getenv("B200_TEST_TINY_SEED_POOL")) P.seed_pool_cap = 24;
+			P.seed_task_cap = (u32)std::min<uint64_t>((uint64_t)0x7fffffff, (uint64_t)n_reads * 24 + 1024); // one task per forward scan (a scan per sequencing error, roughly)
+			ok = b_seedpool.ensure((size_t)n_reads * P.seed_pool_cap * 16) && b_seedused.ensure((size_t)n_reads * 4) && b_seedtask.ensure((size_t)P.seed_task_cap * sizeof(SeedTask)) && b_seedfb.ensure(((size_t)n_reads + 1) * 4);
+			if (!ok) { last_error = "device allocation failed (seeding pools)"; return nullptr; }
+			P.seed_pool = b_seedpool.as<uint4>(); P.seed_pool_used = b_seedused.as<u32>(); P.seed_tasks = b_seedtask.as<SeedTask>(); P.n_seed_tasks = b_misc.as<u32>() + 24;
+			P.seed_fb = b_seedfb.as<u32>(); P.n_seed_fb = b_misc.as<u32>() + 25; // (word 26 = heavy-scan count, behind n_seed_tasks)
+			rt_memset(P.n_intv, 0, (size_t)n_reads * 4);
+			RT_THREADS_QUEUE_SMEM(body_seedF1_q, P, (int64_t)n_reads, 0);
+			RT_WARPS_DEVN(wbody_seedB_heavy, P, P.n_seed_tasks + 2, (int64_t)n_reads); // scans with many candidates first: a warp each
+			RT_THREADS_QUEUE_SMEM(body_seedB_q, P, (int64_t)P.seed_task_cap, 0);
+			rt_memset(P.n_seed_tasks, 0, 4); rt_memset(P.n_seed_tasks + 2, 0, 4);
+			RT_THREADS_QUEUE_SMEM(body_seedF2_q, P, (int64_t)n_reads, 0);
+			RT_WARPS_DEVN(wbody_seedB_heavy, P, P.n_seed_tasks + 2, (int64_t)n_reads);
+			RT_THREADS_QUEUE_SMEM(body_seedB2_q, P, (int64_t)P.seed_task_cap, 0);
+			RT_THREADS_QUEUE_SMEM(body_seed12_fb_q, P, (int64_t)n_reads, ssm); // (usually an empty list)
 			RT_THREADS_QUEUE_SMEM(body_seed3_q, P, (int64_t)n_reads, ssm);
 		}
 	}
@@ -561,8 +581,8 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 	uint32_t misc[32];
 	rt_d2h(misc, b_misc.p, sizeof(misc));
 	memcpy(&last_counters, misc + 8, sizeof(Counters));
-	if (getenv("B200_DEBUG_STATS")) fprintf(stderr, "[bwamem-b200] reads %u: finalize redo %u, alignment tasks %u, extension-heavy reads %u / tasks %u, chain-heavy %u, rescue warp-replayed %u / fallback %u\n",
-	                                        n_reads, misc[5], misc[23], misc[6], misc[21], misc[22], misc[20], misc[7]);
+	if (getenv("B200_DEBUG_STATS")) fprintf(stderr, "[bwamem-b200] reads %u: finalize redo %u, alignment tasks %u, extension-heavy reads %u / tasks %u, chain-heavy %u, rescue warp-replayed %u / fallback %u, seed one-machine reads %u\n",
+	                                        n_reads, misc[5], misc[23], misc[6], misc[21], misc[22], misc[20], misc[7], misc[25]);
 	if (misc[0]) {
 		char buf[128]; snprintf(buf, sizeof buf, "device-side capacity/limit error flags 0x%x", misc[0]);
 		last_error = buf;

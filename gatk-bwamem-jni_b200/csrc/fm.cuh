@@ -367,3 +367,250 @@ DEV u64 fm_sa(const DevIndex& x, u64 k)
 	}
 	return sa + ldg(&x.sa[k / x.sa_intv]);
 }
+
+// ---- SMEM discovery as separate forward and backward launches -----------------------------------------------------
+// bwt_smem1a is a forward scan (extend to the right from x, remember the interval at every change of size) followed
+// by a backward sweep over the remembered intervals.  In one per-read state machine the two kinds of steps -- and the
+// bookkeeping between them -- make the lanes of a warp diverge.  The forward scans of round 1 do not depend on the
+// backward sweeps (the next scan starts where the longest match of the previous one ended, which the forward scan
+// itself knows), and the scans of round 2 only need the finished SMEMs of round 1.  So:
+//   forward launch  (a lane per read)  every scan of the read back to back: one kind of step, candidates appended to
+//                                      the read's slice of a global pool, one SeedTask per scan;
+//   backward launch (a lane per task)  the sweep of one scan, compacting its candidates in place in the pool; SMEMs
+//                                      are appended to the read's interval list with an atomic cursor (the list is
+//                                      ordered by (begin, end) at the very end, so the order of arrival is free).
+// Round 1 = forward<1> + backward, round 2 = forward<2> + backward, round 3 = fm_collect_queue<2> (which also orders
+// the list).  Candidates are packed in 16 bytes (|T| < 2^40, reads <= 255 bases; other batches use fm_collect_queue).
+struct SeedTask { u32 read, c_off, n_c, start; u64 min_intv; };
+struct SeedSplitIO {
+	const u8* seq; const u64* seq_off; i64 n_reads;
+	uint4* pool; u32 pool_cap;        // pool_cap candidates per read
+	u32* pool_used;                   // per read: candidates appended so far (round 2 continues behind round 1)
+	SeedTask* tasks; u32* n_tasks; u32 task_cap;   // light tasks fill the array from the front,
+	u32* n_heavy_tasks;                            // scans with many candidates from the back (they are swept first: longest jobs first)
+	Intv* intv; int intv_cap; u32* n_intv;
+	u32* err; int smem_cap;
+	u32* fb_list; u32* n_fb;          // reads whose scans did not fit the pool / task list: redone by fm_collect_queue<1>
+};
+#define SEED_HEAVY_CANDS 24
+#define SEED_POOL_OVERFLOW 0xffffffffu // value of pool_used[r] for such a read (its tasks are skipped)
+DEV uint4 cand_pack(const BiIntv& b, u32 end)
+{
+	uint4 e;
+	e.x = (u32)b.x0; e.y = (u32)b.x1; e.z = (u32)b.size;
+	e.w = (u32)(b.x0 >> 32 & 0xff) | (u32)(b.x1 >> 32 & 0xff) << 8 | (u32)(b.size >> 32 & 0xff) << 16 | end << 24;
+	return e;
+}
+DEV void cand_unpack(const uint4 e, BiIntv& b, u32& end)
+{
+	b.x0 = (u64)e.x | (u64)(e.w & 0xff) << 32; b.x1 = (u64)e.y | (u64)(e.w >> 8 & 0xff) << 32; b.size = (u64)e.z | (u64)(e.w >> 16 & 0xff) << 32;
+	end = e.w >> 24;
+}
+
+// ROUND 1: scans from x = 0, each starting where the longest match of the previous one ended (min_intv 1).
+// ROUND 2: one scan from the middle of every round-1 SMEM of >= split_len bases and <= split_width occurrences
+//          (min_intv = its occurrences + 1).
+template <int ROUND>
+DEV void fm_forward_queue(const DevIndex& x, const MemOpt& opt, const SeedSplitIO& io, u32* counter)
+{
+	const int split_len = (int)(opt.min_seed_len * opt.split_factor + .499);
+	enum { F_FETCH, F_NEXT, F_SCAN, F_ALLDONE };
+	int st = F_FETCH; bool pend = false;
+	i64 r = -1; int len = 0; const u8* q = nullptr;
+	int xx = 0, k2 = 0, n1 = 0, start = 0, i = 0, ext_c = 0;
+	u32 used = 0, c_off = 0, n_c = 0, ik_end = 0, last_end = 0;
+	u64 min_intv = 1;
+	BiIntv ik; ik.x0 = ik.x1 = ik.size = 0;
+	uint4* pool = nullptr;
+	bool ovf = false; // the read does not fit the pool / the task list: it is handed to the one-machine formulation
+#define F_PUSH() do { if (used < io.pool_cap) { pool[used] = cand_pack(ik, ik_end); ++used; ++n_c; last_end = ik_end; } else ovf = true; } while (0)
+#define F_END_SCAN() do { \
+		if (n_c && !ovf) { const bool hv_ = n_c >= SEED_HEAVY_CANDS; \
+			u32 slot_ = hv_ ? atomic_add_u32(io.n_heavy_tasks, 1u) : atomic_add_u32(io.n_tasks, 1u); \
+			if (hv_) slot_ = slot_ < io.task_cap ? io.task_cap - 1 - slot_ : io.task_cap; \
+			if (slot_ < io.task_cap && *io.n_tasks + *io.n_heavy_tasks <= io.task_cap) { SeedTask t_; t_.read = (u32)r; t_.c_off = c_off; t_.n_c = n_c; t_.start = (u32)start; t_.min_intv = min_intv; io.tasks[slot_] = t_; } \
+			else ovf = true; } \
+		if (ROUND == 1) xx = (int)last_end; else ++k2; \
+		st = ovf ? F_FETCH : F_NEXT; } while (0)
+	for (;;) {
+		while (!pend && st != F_ALLDONE) {
+			switch (st) {
+			case F_FETCH:
+				if (r >= 0) {
+					if (ovf) { io.pool_used[r] = SEED_POOL_OVERFLOW; const u32 slot_ = atomic_add_u32(io.n_fb, 1u); io.fb_list[slot_] = (u32)r; ovf = false; }
+					else io.pool_used[r] = used;
+				}
+				for (;;) {
+					r = (i64)atomic_add_u32(counter, 1u);
+					if (r >= io.n_reads) break;
+					len = (int)(io.seq_off[r + 1] - io.seq_off[r] - 1);
+					if (len >= opt.min_seed_len && len <= io.smem_cap && (ROUND == 1 || io.pool_used[r] != SEED_POOL_OVERFLOW)) break;
+					if (ROUND == 1) io.pool_used[r] = 0;
+				}
+				if (r >= io.n_reads) { r = -1; st = F_ALLDONE; break; }
+				q = io.seq + io.seq_off[r];
+				pool = io.pool + (size_t)r * io.pool_cap;
+				used = 0; // (round 1's candidates are dead once its sweeps have run)
+				xx = 0; k2 = 0; n1 = ROUND == 1 ? 0 : (int)io.n_intv[r];
+				st = F_NEXT;
+				break;
+			case F_NEXT:
+				if (ROUND == 1) {
+					while (xx < len && q[xx] > 3) ++xx;
+					if (xx >= len) { st = F_FETCH; break; }
+					start = xx; min_intv = 1;
+				} else {
+					const Intv* v = io.intv + (size_t)r * io.intv_cap;
+					bool go = false;
+					while (k2 < n1) {
+						const Intv p = v[k2];
+						if ((int)(p.end - p.beg) < split_len || p.size > (u64)opt.split_width) { ++k2; continue; }
+						start = (int)((p.beg + p.end) >> 1); min_intv = p.size + 1;
+						go = true;
+						break;
+					}
+					if (!go) { st = F_FETCH; break; }
+					if (q[start] > 3) { ++k2; break; } // (an SMEM never holds an ambiguous base; kept for fidelity)
+				}
+				fm_set_intv(x, q[start], ik); ik_end = (u32)(start + 1); i = start + 1;
+				c_off = used; n_c = 0; last_end = 0;
+				st = F_SCAN;
+				break;
+			case F_SCAN: // record the interval at every change of size
+				if (i < len && q[i] < 4) { ext_c = 3 - q[i]; pend = true; break; }
+				F_PUSH(); // i == len, or an ambiguous base ends the match
+				F_END_SCAN();
+				break;
+			default: st = F_ALLDONE; break;
+			}
+		}
+		if (lanes_all(st == F_ALLDONE)) break;
+		if (!pend) continue;
+		const BiIntv okc = fm_extend1(x, ik, ext_c, 0);
+		bool stop = false;
+		if (okc.size != ik.size) {
+			F_PUSH();
+			if (okc.size < min_intv) stop = true;
+		}
+		if (!stop) { ik = okc; ik_end = (u32)(i + 1); ++i; }
+		else F_END_SCAN(); // (no second push: the scan ended before i == len)
+		pend = false;
+	}
+#undef F_PUSH
+#undef F_END_SCAN
+}
+
+// The backward sweep of one forward scan.  Candidate a of the textbook list (longest match first) is pool slot
+// c_off + n_c - 1 - a; row i reads candidate j and writes at most j survivors, so the list is compacted in place.
+DEV void fm_backward_queue(const DevIndex& x, const MemOpt& opt, const SeedSplitIO& io, i64 n_tasks, u32* counter)
+{
+	enum { B_FETCH, B_ROW, B_ITEM, B_ALLDONE };
+	int st = B_FETCH; bool pend = false;
+	SeedTask tk; tk.read = 0; tk.c_off = 0; tk.n_c = 0; tk.start = 0; tk.min_intv = 1;
+	const u8* q = nullptr; uint4* cl = nullptr; // cl[-a] = candidate a
+	int i = 0, c = -1, j = 0, n_prev = 0, n_curr = 0;
+	u64 last_size = 0; u32 last_beg = 0, pcur_end = 0; bool have_out = false;
+	BiIntv pcur; pcur.x0 = pcur.x1 = pcur.size = 0;
+#define B_EMIT_PCUR() do { if (n_curr == 0 && (!have_out || (u32)(i + 1) < last_beg)) { \
+		have_out = true; last_beg = (u32)(i + 1); \
+		if ((int)(pcur_end - (u32)(i + 1)) >= opt.min_seed_len) { /* the length filter of the end of the sweep */ \
+			const u32 slot_ = atomic_add_u32(&io.n_intv[tk.read], 1u); \
+			if (slot_ < (u32)io.intv_cap) { Intv t_; t_.x0 = pcur.x0; t_.x1 = pcur.x1; t_.size = pcur.size; t_.beg = (u32)(i + 1); t_.end = pcur_end; io.intv[(size_t)tk.read * io.intv_cap + slot_] = t_; } \
+			else atomic_or_u32(io.err, ERR_INTV_OVERFLOW); } } } while (0)
+	for (;;) {
+		while (!pend && st != B_ALLDONE) {
+			switch (st) {
+			case B_FETCH: {
+				const i64 t = (i64)atomic_add_u32(counter, 1u);
+				if (t >= n_tasks) { st = B_ALLDONE; break; }
+				tk = io.tasks[t]; // (scans with many candidates sit at the other end of the array: fm_backward_task_warp)
+				if (io.pool_used[tk.read] == SEED_POOL_OVERFLOW) break; // the read is redone as a whole (stays in B_FETCH)
+				q = io.seq + io.seq_off[tk.read];
+				cl = io.pool + (size_t)tk.read * io.pool_cap + tk.c_off + (tk.n_c - 1);
+				n_prev = (int)tk.n_c; i = (int)tk.start - 1; have_out = false; last_beg = 0;
+				st = B_ROW;
+				break; }
+			case B_ROW:
+				if (i < -1) { st = B_FETCH; break; }
+				c = i < 0 ? -1 : (q[i] < 4 ? (int)q[i] : -1);
+				n_curr = 0; last_size = 0; j = 0;
+				st = B_ITEM;
+				break;
+			case B_ITEM:
+				if (j == n_prev) { // row finished
+					if (n_curr == 0) { st = B_FETCH; break; }
+					n_prev = n_curr; --i;
+					st = B_ROW;
+					break;
+				}
+				cand_unpack(cl[-j], pcur, pcur_end);
+				if (c >= 0) { pend = true; break; }
+				B_EMIT_PCUR(); // no base to extend with: the candidate cannot grow
+				++j;
+				break;
+			default: st = B_ALLDONE; break;
+			}
+		}
+		if (lanes_all(st == B_ALLDONE)) break;
+		if (!pend) continue;
+		const BiIntv okc = fm_extend1(x, pcur, c, 1);
+		if (okc.size < tk.min_intv) B_EMIT_PCUR();
+		else if (n_curr == 0 || okc.size != last_size) { cl[-n_curr] = cand_pack(okc, pcur_end); ++n_curr; last_size = okc.size; } // n_curr <= j
+		++j;
+		pend = false;
+	}
+#undef B_EMIT_PCUR
+}
+
+// The backward sweep of a scan with MANY candidates (low-complexity and repeat-derived reads: up to one candidate per
+// base), one warp per task.  Swept by a single lane such a task is ~10^4 dependent index lookups -- milliseconds, the
+// tail of the whole launch.  The extensions of the candidates of one row are independent of each other, so the lanes
+// extend 32 candidates at once; only the bookkeeping that follows (which candidate survives, which one is reported)
+// is order-dependent, and it needs nothing but the new interval sizes: every lane replays it over the 32 sizes
+// (shuffles) and then carries out the action that fell to its own candidate.
+template <int W>
+DEVNI void fm_backward_task_warp(const DevIndex& x, const MemOpt& opt, const SeedSplitIO& io, const SeedTask& tk)
+{
+	LANE_DECL;
+	if (io.pool_used[tk.read] == SEED_POOL_OVERFLOW) return; // the read is redone as a whole
+	const u8* q = io.seq + io.seq_off[tk.read];
+	uint4* cl = io.pool + (size_t)tk.read * io.pool_cap + tk.c_off + (tk.n_c - 1); // cl[-a] = candidate a
+	int n_prev = (int)tk.n_c; u32 last_beg = 0; bool have_out = false;
+	for (int i = (int)tk.start - 1; i >= -1; --i) {
+		const int c = i < 0 ? -1 : (q[i] < 4 ? (int)q[i] : -1);
+		int n_curr = 0; u64 last_size = 0;
+		for (int j0 = 0; j0 < n_prev; j0 += W) {
+			WV(BiIntv, pc); WV(u32, pe); WV(BiIntv, ok); WV(u64, sz); WV(int, act); WV(int, idx);
+			FOR_LANES {
+				const int j = j0 + lane;
+				L_(sz) = 0; L_(act) = 0; L_(idx) = 0; L_(pe) = 0;
+				L_(pc).x0 = L_(pc).x1 = L_(pc).size = 0; L_(ok) = L_(pc);
+				if (j < n_prev) {
+					cand_unpack(cl[-j], L_(pc), L_(pe));
+					if (c >= 0) { L_(ok) = fm_extend1(x, L_(pc), c, 1); L_(sz) = L_(ok).size; }
+				}
+			}
+			WARP_SYNC(); // every candidate of the chunk is in registers: slots up to j0 + 31 may now be overwritten
+			const int cnt = n_prev - j0 < W ? n_prev - j0 : W;
+			for (int t = 0; t < cnt; ++t) { // the scalar bookkeeping, replayed by all lanes on the broadcast sizes
+				const u64 s_t = wv_get(sz, t);
+				int a = 0, at = 0;
+				if (c < 0 || s_t < tk.min_intv) { // the candidate cannot grow: report it if it is the longest of its end so far
+					if (n_curr == 0 && (!have_out || (u32)(i + 1) < last_beg)) { have_out = true; last_beg = (u32)(i + 1); a = 1; }
+				} else if (n_curr == 0 || s_t != last_size) { a = 2; at = n_curr; ++n_curr; last_size = s_t; }
+				FOR_LANES { if (lane == t) { L_(act) = a; L_(idx) = at; } }
+			}
+			FOR_LANES {
+				if (L_(act) == 2) cl[-L_(idx)] = cand_pack(L_(ok), L_(pe));
+				else if (L_(act) == 1 && (int)(L_(pe) - (u32)(i + 1)) >= opt.min_seed_len) { // the length filter of the end of the sweep
+					const u32 slot = atomic_add_u32(&io.n_intv[tk.read], 1u);
+					if (slot < (u32)io.intv_cap) { Intv t_; t_.x0 = L_(pc).x0; t_.x1 = L_(pc).x1; t_.size = L_(pc).size; t_.beg = (u32)(i + 1); t_.end = L_(pe); io.intv[(size_t)tk.read * io.intv_cap + slot] = t_; }
+					else atomic_or_u32(io.err, ERR_INTV_OVERFLOW);
+				}
+			}
+			WARP_SYNC();
+		}
+		if (n_curr == 0) break;
+		n_prev = n_curr;
+	}
+}

@@ -24,6 +24,8 @@ struct BatchParams {
 	Intv* intv; int intv_cap; u32* n_intv; u32* n_seed; // per read
 	Intv* smem_scratch; int smem_cap;                  // per thread: smem_cap spill entries of the candidate list
 	int seed_shared;                                    // candidate list (+ read codes) in shared memory (fm.cuh SeedWork)
+	uint4* seed_pool; u32 seed_pool_cap; u32* seed_pool_used; SeedTask* seed_tasks; u32* n_seed_tasks; u32 seed_task_cap; // forward / backward split (fm.cuh)
+	u32* seed_fb; u32* n_seed_fb;                        // reads redone by the one-machine formulation (pool / task overflow)
 	int seed_lcap, seed_shared_read;                    // shared candidates per thread; whether the read's codes are staged in shared memory too
 	u64* seed_off;          // n_reads+1 (exclusive scan of n_seed)
 	u64 n_seed_total;
@@ -84,11 +86,13 @@ template <int PHASES>
 struct SeedSrc {
 	const BatchParams& P; i64 n; u32* counter; i64 r;
 	DEVM SeedSrc(const BatchParams& P_, i64 n_, u32* c_) : P(P_), n(n_), counter(c_), r(-1) {}
+	const u32* list = nullptr; // when set, the work items are list[0..n)
 	DEVM bool next(int& len, const u8*& seq, IntvOut& o)
 	{
 		for (;;) {
 			r = (i64)atomic_add_u32(counter, 1u);
 			if (r >= n) return false;
+			if (list) r = (i64)list[r];
 			len = (int)(P.seq_off[r + 1] - P.seq_off[r] - 1);
 			if (len >= P.opt.min_seed_len && len <= P.smem_cap) break;
 			if (len > P.smem_cap && PHASES != 2) atomic_or_u32(P.err, ERR_QLEN_OVERFLOW);
@@ -109,7 +113,7 @@ struct SeedSrc {
 	}
 };
 template <int PHASES>
-DEV void seed_queue(const BatchParams& P, i64 n, u32* counter, i64 tid)
+DEV void seed_queue(const BatchParams& P, i64 n, u32* counter, i64 tid, const u32* list = nullptr)
 {
 	SeedWork wk;
 	wk.G = P.smem_scratch + (size_t)tid * P.smem_cap; wk.gcap = P.smem_cap;
@@ -124,9 +128,38 @@ DEV void seed_queue(const BatchParams& P, i64 n, u32* counter, i64 tid)
 #endif
 	}
 	SeedSrc<PHASES> src(P, n, counter);
+	src.list = list;
 	fm_collect_queue<PHASES>(P.x, P.opt, wk, src);
 }
-DEV void body_seed_q(const BatchParams& P, i64 n, u32* counter, i64 tid) { seed_queue<3>(P, n, counter, tid); }    // all rounds in one launch
+DEV SeedSplitIO make_seed_split_io(const BatchParams& P, i64 n_reads)
+{
+	SeedSplitIO io;
+	io.seq = P.seq; io.seq_off = P.seq_off; io.n_reads = n_reads;
+	io.pool = P.seed_pool; io.pool_cap = P.seed_pool_cap; io.pool_used = P.seed_pool_used;
+	io.tasks = P.seed_tasks; io.n_tasks = P.n_seed_tasks; io.task_cap = P.seed_task_cap; io.n_heavy_tasks = P.n_seed_tasks + 2;
+	io.intv = P.intv; io.intv_cap = P.intv_cap; io.n_intv = P.n_intv;
+	io.err = P.err; io.smem_cap = P.smem_cap;
+	io.fb_list = P.seed_fb; io.n_fb = P.n_seed_fb;
+	return io;
+}
+// rounds 1 and 2 as forward scans (a lane per read) and backward sweeps (a lane per scan): fm.cuh
+DEV void body_seedF1_q(const BatchParams& P, i64 n, u32* counter, i64 tid) { (void)tid; SeedSplitIO io = make_seed_split_io(P, n); fm_forward_queue<1>(P.x, P.opt, io, counter); }
+DEV void body_seedF2_q(const BatchParams& P, i64 n, u32* counter, i64 tid) { (void)tid; SeedSplitIO io = make_seed_split_io(P, n); fm_forward_queue<2>(P.x, P.opt, io, counter); }
+DEV void body_seedB_q(const BatchParams& P, i64 n, u32* counter, i64 tid) { (void)tid; (void)n; SeedSplitIO io = make_seed_split_io(P, P.n_reads); u32 nl = P.n_seed_tasks[0], nh = P.n_seed_tasks[2]; if ((u64)nl + nh > P.seed_task_cap) { atomic_or_u32(P.err, ERR_INTV_OVERFLOW); nl = 0; nh = 0; } // the two ends of the task array met: fail the batch loudly
+	fm_backward_queue(P.x, P.opt, io, (i64)nl, counter); }
+template <int W>
+DEV void wbody_seedB_heavy(const BatchParams& P, i64 item, WarpMem& wm, WarpScratch& ws)
+{
+	(void)wm; (void)ws;
+	SeedSplitIO io = make_seed_split_io(P, P.n_reads);
+	if ((u64)P.n_seed_tasks[0] + P.n_seed_tasks[2] > P.seed_task_cap) return; // (flagged by the light launch)
+	const SeedTask tk = P.seed_tasks[P.seed_task_cap - 1 - (u32)item];
+	fm_backward_task_warp<W>(P.x, P.opt, io, tk);
+}
+DEV void body_seedB2_q(const BatchParams& P, i64 n, u32* counter, i64 tid) { body_seedB_q(P, n, counter, tid); }
+DEV void body_seed_q(const BatchParams& P, i64 n, u32* counter, i64 tid) { seed_queue<3>(P, n, counter, tid); }
+// rounds 1/2 of the reads the split launches could not hold (list written by the forward launches)
+DEV void body_seed12_fb_q(const BatchParams& P, i64 n, u32* counter, i64 tid) { (void)n; seed_queue<1>(P, (i64)*P.n_seed_fb, counter, tid, P.seed_fb); }    // all rounds in one launch
 DEV void body_seed12_q(const BatchParams& P, i64 n, u32* counter, i64 tid) { seed_queue<1>(P, n, counter, tid); }  // SMEMs + re-seeding
 DEV void body_seed3_q(const BatchParams& P, i64 n, u32* counter, i64 tid) { seed_queue<2>(P, n, counter, tid); }   // forward-only seeds, sort, count
 
