@@ -135,6 +135,41 @@ DEV BiIntv fm_extend1(const DevIndex& x, const BiIntv& ik, int c, int is_back)
 	return r;
 }
 
+// Two independent backward extensions by the same base (two candidates of one row of a backward sweep): the eight
+// block loads are issued before any of them is consumed, so one lane keeps twice as many index reads in flight.
+DEV void fm_extend1_back_x2(const DevIndex& x, const BiIntv& ia, const BiIntv& ib, int c, BiIntv& ra, BiIntv& rb)
+{
+	u64 kk[4]; bool zz[4];
+	const BiIntv* iv[2] = { &ia, &ib };
+#pragma unroll
+	for (int t = 0; t < 2; ++t) {
+		const u64 k = iv[t]->x0 - 1, l = iv[t]->x0 - 1 + iv[t]->size;
+		zz[2 * t] = k == ~0ull; zz[2 * t + 1] = l == ~0ull;
+		kk[2 * t] = zz[2 * t] ? 0 : k - (k >= x.primary);
+		kk[2 * t + 1] = zz[2 * t + 1] ? 0 : l - (l >= x.primary);
+	}
+	OccBlock b0 = load_block(x, kk[0] >> 7), b1 = load_block(x, kk[1] >> 7), b2 = load_block(x, kk[2] >> 7), b3 = load_block(x, kk[3] >> 7);
+	u64 cnt[4][4];
+	occ4_in_block(b0, kk[0], cnt[0]); occ4_in_block(b1, kk[1], cnt[1]); occ4_in_block(b2, kk[2], cnt[2]); occ4_in_block(b3, kk[3], cnt[3]);
+#pragma unroll
+	for (int t = 0; t < 4; ++t) if (zz[t]) { cnt[t][0] = cnt[t][1] = cnt[t][2] = cnt[t][3] = 0; }
+	const u64 L2c = c == 0 ? x.L2[0] : c == 1 ? x.L2[1] : c == 2 ? x.L2[2] : x.L2[3];
+#pragma unroll
+	for (int t = 0; t < 2; ++t) {
+		const u64* tk = cnt[2 * t]; const u64* tl = cnt[2 * t + 1];
+		const u64 s1 = tl[1] - tk[1], s2 = tl[2] - tk[2], s3 = tl[3] - tk[3];
+		const u64 kc = c == 0 ? tk[0] : c == 1 ? tk[1] : c == 2 ? tk[2] : tk[3];
+		const u64 lc = c == 0 ? tl[0] : c == 1 ? tl[1] : c == 2 ? tl[2] : tl[3];
+		const u64 above = (c < 3 ? s3 : 0) + (c < 2 ? s2 : 0) + (c < 1 ? s1 : 0);
+		const u64 a0 = iv[t]->x0, s = iv[t]->size;
+		BiIntv r;
+		r.size = lc - kc;
+		r.x0 = L2c + 1 + kc;
+		r.x1 = iv[t]->x1 + ((a0 <= x.primary && a0 + s - 1 >= x.primary) ? 1 : 0) + above;
+		if (t == 0) ra = r; else rb = r;
+	}
+}
+
 DEV void fm_set_intv(const DevIndex& x, int c, BiIntv& ik)
 {
 	ik.x0 = x.L2[c] + 1; ik.size = x.L2[c + 1] - x.L2[c]; ik.x1 = x.L2[3 - c] + 1;
@@ -505,12 +540,14 @@ DEV void fm_forward_queue(const DevIndex& x, const MemOpt& opt, const SeedSplitI
 DEV void fm_backward_queue(const DevIndex& x, const MemOpt& opt, const SeedSplitIO& io, i64 n_tasks, u32* counter)
 {
 	enum { B_FETCH, B_ROW, B_ITEM, B_ALLDONE };
-	int st = B_FETCH; bool pend = false;
+	int st = B_FETCH; int pend = 0; // number of candidates of the current row in flight (0, 1 or 2)
 	SeedTask tk; tk.read = 0; tk.c_off = 0; tk.n_c = 0; tk.start = 0; tk.min_intv = 1;
 	const u8* q = nullptr; uint4* cl = nullptr; // cl[-a] = candidate a
 	int i = 0, c = -1, j = 0, n_prev = 0, n_curr = 0;
 	u64 last_size = 0; u32 last_beg = 0, pcur_end = 0; bool have_out = false;
 	BiIntv pcur; pcur.x0 = pcur.x1 = pcur.size = 0;
+	BiIntv pcur2 = pcur; u32 pcur2_end = 0;
+	uint4 nxt = make_uint4(0, 0, 0, 0); // candidate j of the current row, fetched while candidate j - 1 was being extended
 #define B_EMIT_PCUR() do { if (n_curr == 0 && (!have_out || (u32)(i + 1) < last_beg)) { \
 		have_out = true; last_beg = (u32)(i + 1); \
 		if ((int)(pcur_end - (u32)(i + 1)) >= opt.min_seed_len) { /* the length filter of the end of the sweep */ \
@@ -534,6 +571,7 @@ DEV void fm_backward_queue(const DevIndex& x, const MemOpt& opt, const SeedSplit
 				if (i < -1) { st = B_FETCH; break; }
 				c = i < 0 ? -1 : (q[i] < 4 ? (int)q[i] : -1);
 				n_curr = 0; last_size = 0; j = 0;
+				nxt = cl[0];
 				st = B_ITEM;
 				break;
 			case B_ITEM:
@@ -543,8 +581,14 @@ DEV void fm_backward_queue(const DevIndex& x, const MemOpt& opt, const SeedSplit
 					st = B_ROW;
 					break;
 				}
-				cand_unpack(cl[-j], pcur, pcur_end);
-				if (c >= 0) { pend = true; break; }
+				cand_unpack(nxt, pcur, pcur_end);
+				if (c >= 0) { // the candidates of a row are independent: two of them are extended per trip
+					pend = 1;
+					if (j + 1 < n_prev) { cand_unpack(cl[-(j + 1)], pcur2, pcur2_end); pend = 2; }
+					if (j + pend < n_prev) nxt = cl[-(j + pend)]; // (in-place compaction only writes slots <= j)
+					break;
+				}
+				if (j + 1 < n_prev) nxt = cl[-(j + 1)];
 				B_EMIT_PCUR(); // no base to extend with: the candidate cannot grow
 				++j;
 				break;
@@ -553,11 +597,16 @@ DEV void fm_backward_queue(const DevIndex& x, const MemOpt& opt, const SeedSplit
 		}
 		if (lanes_all(st == B_ALLDONE)) break;
 		if (!pend) continue;
-		const BiIntv okc = fm_extend1(x, pcur, c, 1);
-		if (okc.size < tk.min_intv) B_EMIT_PCUR();
-		else if (n_curr == 0 || okc.size != last_size) { cl[-n_curr] = cand_pack(okc, pcur_end); ++n_curr; last_size = okc.size; } // n_curr <= j
-		++j;
-		pend = false;
+		BiIntv okc, okc2;
+		if (pend == 2) fm_extend1_back_x2(x, pcur, pcur2, c, okc, okc2);
+		else { okc = fm_extend1(x, pcur, c, 1); okc2 = okc; }
+		for (int t = 0; t < pend; ++t) { // consumed in list order, exactly as one at a time
+			if (t == 1) { pcur = pcur2; pcur_end = pcur2_end; okc = okc2; }
+			if (okc.size < tk.min_intv) B_EMIT_PCUR();
+			else if (n_curr == 0 || okc.size != last_size) { cl[-n_curr] = cand_pack(okc, pcur_end); ++n_curr; last_size = okc.size; } // n_curr <= j
+			++j;
+		}
+		pend = 0;
 	}
 #undef B_EMIT_PCUR
 }

@@ -85,6 +85,7 @@ DEV u32 atomic_max_u32(u32* p, u32 v) { return atomicMax(p, v); }
 #define LANE0_ONLY
 
 struct uint4 { u32 x, y, z, w; };
+static inline uint4 make_uint4(u32 x, u32 y, u32 z, u32 w) { uint4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 template <class T> DEV T ldg(const T* p) { return *p; }
 DEV int popc64(u64 x) { return __builtin_popcountll(x); }
 template <int W, class T> DEV void wv_shfl_up_(T (&dst)[32], const T (&src)[32], int d) { T t[32]; for (int l = 0; l < W; ++l) t[l] = l >= d ? src[l - d] : src[l]; for (int l = 0; l < W; ++l) dst[l] = t[l]; }
