@@ -27,10 +27,15 @@ struct ExtTask { u32 r, c, t, pad_; }; // read, chain index within the read, see
 
 struct Counters { u64 cells_ext, cells_glb, cells_msw, n_ext, n_glb, n_msw; };
 
+// cal_max_gap: l = max(int(double(qlen*a - o_del) / e_del + 1.), int(double(qlen*a - o_ins) / e_ins + 1.)), clamped to
+// [1, 2w].  Integer restatement: for x >= 0 and e > 0, int(double(x) / e + 1.) == x / e + 1 (the quotient of two ints
+// below 2^31 is off by far less than 1/e from the true value, so truncation lands on the same integer); for x < 0 the
+// value is < 1 and the clamp to >= 1 hides it.  Avoids fp64 divisions (slow on this part) in per-seed loops.
 DEV int cal_max_gap(const MemOpt& opt, int qlen)
 {
-	int l_del = (int)((double)(qlen * opt.a - opt.o_del) / opt.e_del + 1.);
-	int l_ins = (int)((double)(qlen * opt.a - opt.o_ins) / opt.e_ins + 1.);
+	const int xd = qlen * opt.a - opt.o_del, xi = qlen * opt.a - opt.o_ins;
+	const int l_del = xd >= 0 ? (opt.e_del == 1 ? xd + 1 : xd / opt.e_del + 1) : 0;
+	const int l_ins = xi >= 0 ? (opt.e_ins == 1 ? xi + 1 : xi / opt.e_ins + 1) : 0;
 	int l = l_del > l_ins ? l_del : l_ins;
 	l = l > 1 ? l : 1;
 	return l < opt.w << 1 ? l : opt.w << 1;

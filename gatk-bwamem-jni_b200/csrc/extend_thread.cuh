@@ -211,9 +211,11 @@ DEV void thread_extend_queue(const BatchParams& P, i64 n_reads, u32* counter, co
 					int v = h0 > oe_ins ? h0 - oe_ins : 0;
 					for (int j = 1; j <= qlen; ++j) { rw[(size_t)j * RS] = (u32)v; v = v > e_ins ? v - e_ins : 0; }
 				}
-				int max_ins = (int)((double)(qlen * mx + end_bonus - o_ins) / e_ins + 1.); max_ins = max_ins > 1 ? max_ins : 1;
+				// band clamp of ksw_extend2, int(double(x) / e + 1.) clamped to >= 1, in integers (see cal_max_gap)
+				const int xi_ = qlen * mx + end_bonus - o_ins, xd_ = qlen * mx + end_bonus - o_del;
+				int max_ins = xi_ >= 0 ? (e_ins == 1 ? xi_ + 1 : xi_ / e_ins + 1) : 0; max_ins = max_ins > 1 ? max_ins : 1;
 				w = w < max_ins ? w : max_ins;
-				int max_del = (int)((double)(qlen * mx + end_bonus - o_del) / e_del + 1.); max_del = max_del > 1 ? max_del : 1;
+				int max_del = xd_ >= 0 ? (e_del == 1 ? xd_ + 1 : xd_ / e_del + 1) : 0; max_del = max_del > 1 ? max_del : 1;
 				w = w < max_del ? w : max_del;
 				max = h0; max_i = -1; max_j = -1; max_ie = -1; gscore = -1; max_off = 0; beg = 0; end = qlen; i = 0;
 				++n_ext;
