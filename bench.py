@@ -319,7 +319,8 @@ def main():
     # Per-kernel table.  Algorithmic work comes from the oracle's counters on the sample, scaled to the batch
     # (DESIGN.md 5): FM-index kernels in bytes (64 B per occurrence-block touch, 8 B per suffix-array sample read),
     # DP kernels in cell updates.  Kernels that split one stage (thread-level / task / warp variants) share its work.
-    groups = {"seed": ["body_seed_q"], "sal": ["body_sal"], "chain": ["body_chain", "wbody_chain_heavy"],
+    groups = {"seed": ["body_seed_q", "body_seed12_q", "body_seed3_q", "body_seedF1_q", "body_seedF2_q", "body_seedB_q", "body_seedB2_q", "wbody_seedB_heavy", "body_seed12_fb_q"],
+              "sal": ["body_sal"], "chain": ["body_chain", "wbody_chain_heavy"],
               "extend": ["body_extend_q", "wbody_heavy_prep", "body_extend_task_q", "wbody_extend_heavy", "wbody_extend"],
               "rescue_sw": ["wbody_rescue_sw"], "finalize": ["body_final_pe_t", "wbody_final_pe_redo", "body_final_se_t", "wbody_final_se_redo"]}
     ms_of = {g: sum(t for nm, t in stages if nm in names) for g, names in groups.items()}
@@ -342,28 +343,31 @@ def main():
                     v["gcups"] = round(v["cells"] / (v["ms"] * 1e6), 2)
                 else:
                     v["gbs"] = round(v["algorithmic_bytes"] / (v["ms"] * 1e6), 1)
-    dom = max(stages, key=lambda x: x[1])
-    dom_group = next((g for g, names in groups.items() if dom[0] in names), None)
-    roof = {"bound": "hbm", "kernel": dom[0], "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None,
-            "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback"}
+    # The roofline object describes the dominant STAGE: a stage is one algorithmic step of the path and may be split over
+    # several launches (SMEM seeding = forward scans, backward sweeps, round 3: profiles/r1z_launch_summary.txt).
+    dom_group = max(ms_of, key=lambda g: ms_of[g])
+    dom_ms = ms_of[dom_group]
+    dom_kernels = [nm for nm, t in stages if nm in groups[dom_group] and t > 0]
+    roof = {"bound": "hbm", "kernel": "+".join(dom_kernels), "stage": dom_group, "ms": round(dom_ms, 3), "achieved": None, "peak": hbm_peak, "unit": "GB/s",
+            "frac": None, "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback"}
     if stage_work and dom_group in ("seed", "sal"):
         # the FM-index walks: random 64-byte occurrence-block reads of an index far larger than L2
-        roof["achieved"] = stage_work[dom_group]["algorithmic_bytes"] / (dom[1] * 1e6)
-        roof["algorithmic_bytes_per_launch"] = stage_work[dom_group]["algorithmic_bytes"]
-        roof["note"] = "achieved = 64 B x occurrence-block touches of the SMEM search (oracle counters) / kernel time, measured with CUDA events on the engine's stream"
+        roof["achieved"] = stage_work[dom_group]["algorithmic_bytes"] / (dom_ms * 1e6)
+        roof["algorithmic_bytes_per_step"] = stage_work[dom_group]["algorithmic_bytes"]
+        roof["note"] = "achieved = 64 B x occurrence-block touches of the SMEM search (oracle counters on the same reads) / summed kernel time of the stage's launches (CUDA events on the engine's stream)"
     elif stage_work and dom_group in ("extend", "rescue_sw", "finalize"):
         cells = stage_work[dom_group]["cells"]
-        roof["achieved"] = cells * 8.0 / (dom[1] * 1e6)
-        roof["gcups"] = cells / (dom[1] * 1e6)
-        roof["note"] = "dominant kernel is integer DP (no HBM or tensor roof applies): achieved = cell updates x 8 B of H/E state / time"
+        roof["achieved"] = cells * 8.0 / (dom_ms * 1e6)
+        roof["gcups"] = cells / (dom_ms * 1e6)
+        roof["note"] = "dominant stage is integer DP out of shared memory / registers (no HBM or tensor roof applies): achieved = cell updates x 8 B of H/E state / time"
     if roof["achieved"] is not None:
         roof["frac"] = roof["achieved"] / hbm_peak
-    try:  # DRAM bytes of the dominant kernel from the committed ncu --set full capture of this very workload, if one exists
+    try:  # DRAM bytes of the stage's launches from the committed ncu --set full captures of this very workload, if they exist
         prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        ent = prof.get(dom[0])
-        if ent and ent.get("pairs_per_step") == args.pairs and ent.get("genome_bp") == int(args.genome_mbp * 1e6):
-            roof["traffic"] = ent["dram_bytes_per_launch"]
-            roof["traffic_source"] = ent.get("source")
+        ents = [prof.get(k) for k in dom_kernels]
+        if all(e and e.get("pairs_per_step") == args.pairs and e.get("genome_bp") == int(args.genome_mbp * 1e6) for e in ents):
+            roof["traffic"] = sum(e["dram_bytes_per_launch"] for e in ents)
+            roof["traffic_source"] = sorted(set(e.get("source") for e in ents))
     except Exception:
         pass
     line = {"metric": "aligned read-pairs/sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -156,13 +156,11 @@ DEF_THREAD_KERNEL(body_compact)
 DEF_THREAD_KERNEL(body_out_size)
 DEF_THREAD_KERNEL(body_out_write)
 DEF_THREAD_KERNEL(body_rescue_snap)
-DEF_THREAD_KERNEL(body_rescue_gen)
 DEF_THREAD_KERNEL(body_rescue_gen_all)
 DEF_THREAD_KERNEL(body_rescue_apply_all)
 DEF_THREAD_KERNEL(body_rescue_fb_restore)
 DEF_THREAD_KERNEL(body_rescue_classify)
 DEF_WARP_KERNEL_DEVN(wbody_rescue_apply_heavy)
-DEF_THREAD_KERNEL(body_rescue_apply)
 DEF_THREAD_KERNEL(body_rescue_gen_multi)
 DEF_THREAD_KERNEL(body_rescue_apply_multi)
 #ifndef RESCUE_SW_MIN_BLOCKS
