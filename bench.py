@@ -362,6 +362,13 @@ def main():
         roof["note"] = "dominant stage is integer DP out of shared memory / registers (no HBM or tensor roof applies): achieved = cell updates x 8 B of H/E state / time"
     if roof["achieved"] is not None:
         roof["frac"] = roof["achieved"] / hbm_peak
+        if dom_group in ("seed", "sal"):
+            try:  # the roof that applies to 64-byte random reads, measured with tools/hbm_random.cu (profiles/hbm_random.json)
+                rr = json.load(open(os.path.join(ROOT, "profiles", "hbm_random.json")))["roof_for_the_fm_index_stage_gbs"]
+                roof["peak_random64"] = rr
+                roof["frac_random64"] = roof["achieved"] / rr
+            except Exception:
+                pass
     try:  # DRAM bytes of the stage's launches from the committed ncu --set full captures of this very workload, if they exist
         prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         ents = [prof.get(k) for k in dom_kernels]
