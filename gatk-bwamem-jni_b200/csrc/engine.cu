@@ -284,6 +284,7 @@ void* jnibwa_openIndex(int fd)
 	if (const char* dv = getenv("BWA_B200_DEVICE")) { // the Java API has no notion of a device
 		if (cudaSetDevice(atoi(dv)) != cudaSuccess) { fprintf(stderr, "[bwamem-b200] BWA_B200_DEVICE=%s is not a usable device\n", dv); if (fd >= 0) close(fd); return nullptr; }
 	}
+	std::lock_guard<std::mutex> lock(Engine::device_mutex());
 	Engine* e = new Engine();
 	if (!e->open_from_fd(fd)) { fprintf(stderr, "[bwamem-b200] openIndex: %s\n", e->last_error.c_str()); e->close_all(); delete e; return nullptr; }
 	return e;
@@ -292,6 +293,7 @@ void* jnibwa_openIndex(int fd)
 int jnibwa_destroyIndex(void* h)
 {
 	if (!h) return 0;
+	std::lock_guard<std::mutex> lock(Engine::device_mutex());
 	Engine* e = (Engine*)h;
 	e->close_all();
 	delete e;
@@ -322,13 +324,13 @@ const char* jnibwa_getVersion(void) { return "bwamem-b200 0.1 (sm_100a; bwa-mem 
 int b200_stageBatch(void* h, const char* seqs)
 {
 	Engine* e = (Engine*)h;
-	std::lock_guard<std::mutex> lock(e->mu);
+	std::lock_guard<std::mutex> lock(Engine::device_mutex());
 	return e->stage(seqs) ? 0 : 1;
 }
 long long b200_alignStaged(void* h, void* opt, void* pes)
 {
 	Engine* e = (Engine*)h;
-	std::lock_guard<std::mutex> lock(e->mu);
+	std::lock_guard<std::mutex> lock(Engine::device_mutex());
 	size_t size = 0;
 	g_last_cuda = cudaSuccess;
 	void* r = e->run((const MemOpt*)opt, (const PeStat*)pes, &size, false);

@@ -124,7 +124,10 @@ struct Engine {
 	// device-resident index
 	DevIndex dx;
 	DBuf d_bwt, d_sa, d_sa_dense, d_pac, d_ctg, d_log, d_names, d_name_off;
-	std::mutex mu; // one batch at a time per index handle (re-entrant callers are serialised)
+	// One batch at a time per PROCESS (= per GPU): the stream, the stage timer and the scan scratch of the runtime binding
+	// are process-wide, so callers are serialised across index handles too (BwaMemIndex objects may be shared by any
+	// number of threads, each with its own BwaMemAligner: BwaMemAligner.java:18, BwaMemIndex.java:18).
+	static std::mutex& device_mutex() { static std::mutex m; return m; }
 	// batch workspace
 	DBuf b_blob, b_seq, b_seqoff, b_intv, b_nintv, b_nseed, b_smem, b_seedoff, b_rbeg, b_S, b_C, b_ord, b_tmp32, b_ck, b_ks, b_srt, b_regtmp,
 	     b_nck, b_nks, b_nreg, b_regcap, b_regoff, b_regs, b_snap, b_ztmp, b_pairv, b_recs, b_nrec, b_cand, b_pairtab, b_var, b_misc,
@@ -292,7 +295,7 @@ inline bool Engine::stage(const char* blob_in, bool wait)
 
 inline void* Engine::align(const MemOpt* opt_in, const PeStat* pes0, char* blob_in, size_t* out_size)
 {
-	std::lock_guard<std::mutex> lock(mu);
+	std::lock_guard<std::mutex> lock(device_mutex());
 	last_error.clear();
 	*out_size = 0;
 	g_hp.begin();
