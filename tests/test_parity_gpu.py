@@ -165,3 +165,39 @@ def test_device_index_builder_matches_host_builder(tmp_path, monkeypatch, chunk)
     simdata.build_image(g, dev, dll=engine_lib().dll)
     assert os.path.getsize(host) == os.path.getsize(dev)
     assert open(host, "rb").read() == open(dev, "rb").read()
+
+
+def test_concurrent_callers_and_two_indexes(small_genome, mid_genome):
+    """The reference's usage: one shared BwaMemIndex, one BwaMemAligner per thread (BwaMemAligner.java:18); here also two
+    different indexes open at once.  Calls are serialised inside the library; every result must be the single-threaded one."""
+    import threading
+    g1, img1 = small_genome
+    g2, img2 = mid_genome
+    blobs1 = [simdata.make_reads(g1, 60 + i, 800, 150, True)[0] for i in range(3)]
+    blobs2 = [simdata.make_reads(g2, 70 + i, 800, 150, False)[0] for i in range(3)]
+    want1 = [run_blob(oracle_lib(), img1, b, 2) for b in blobs1]
+    want2 = [run_blob(oracle_lib(), img2, b, 0) for b in blobs2]
+    idx1 = bwa.BwaMemIndex(img1, lib=engine_lib())
+    idx2 = bwa.BwaMemIndex(img2, lib=engine_lib())
+    got = {}
+
+    def worker(tag, idx, blobs, flag):
+        al = bwa.BwaMemAligner(idx)
+        if flag:
+            al.alignPairs()
+        for rep in range(2):
+            for i, b in enumerate(blobs):
+                got[(tag, rep, i)] = idx.doAlignment(bytearray(b), al._opts_addr, None)
+        al.close()
+
+    threads = [threading.Thread(target=worker, args=("a", idx1, blobs1, 2)), threading.Thread(target=worker, args=("b", idx1, blobs1, 2)),
+               threading.Thread(target=worker, args=("c", idx2, blobs2, 0))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    idx1.close()
+    idx2.close()
+    for (tag, rep, i), out in got.items():
+        assert out == (want2 if tag == "c" else want1)[i], (tag, rep, i)
+    assert len(got) == 18
