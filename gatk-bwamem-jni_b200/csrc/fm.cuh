@@ -76,35 +76,6 @@ DEV void occ4(const DevIndex& x, u64 k, u64 cnt[4])
 
 struct BiIntv { u64 x0, x1, size; };
 
-// bwt_extend: ok[c] for the four bases; is_back extends the pattern to the left
-DEV void fm_extend(const DevIndex& x, const BiIntv& ik, BiIntv ok[4], int is_back)
-{
-	u64 tk[4], tl[4];
-	u64 a0 = is_back ? ik.x0 : ik.x1, oth = is_back ? ik.x1 : ik.x0, s = ik.size;
-	u64 k = a0 - 1, l = a0 - 1 + s;
-	{ // both bounds, without branches: a bound of (u64)-1 (empty prefix) reads block 0 and is zeroed afterwards; when both
-	  // bounds fall in one block the second fetch is an L1 hit (bwt_2occ4's single touch, algorithmically)
-		const bool kz = k == ~0ull, lz = l == ~0ull;
-		const u64 k_ = kz ? 0 : k - (k >= x.primary), l_ = lz ? 0 : l - (l >= x.primary);
-		OccBlock bk = load_block(x, k_ >> 7);
-		OccBlock bl = load_block(x, l_ >> 7);
-		occ4_in_block(bk, k_, tk);
-		occ4_in_block(bl, l_, tl);
-		if (kz) { tk[0] = tk[1] = tk[2] = tk[3] = 0; }
-		if (lz) { tl[0] = tl[1] = tl[2] = tl[3] = 0; }
-	}
-#pragma unroll
-	for (int c = 0; c < 4; ++c) {
-		u64 v = x.L2[c] + 1 + tk[c];
-		if (is_back) ok[c].x0 = v; else ok[c].x1 = v;
-		ok[c].size = tl[c] - tk[c];
-	}
-	u64 o3 = oth + ((a0 <= x.primary && a0 + s - 1 >= x.primary) ? 1 : 0);
-	u64 o2 = o3 + ok[3].size, o1 = o2 + ok[2].size, o0 = o1 + ok[1].size;
-	if (is_back) { ok[3].x1 = o3; ok[2].x1 = o2; ok[1].x1 = o1; ok[0].x1 = o0; }
-	else { ok[3].x0 = o3; ok[2].x0 = o2; ok[1].x0 = o1; ok[0].x0 = o0; }
-}
-
 // bwt_extend for ONE base c (the only one a caller ever consumes): no per-base arrays, so nothing is spilled to local
 // memory by lane-varying indexing.  The complementary coordinate needs the sizes of the bases above c only.
 DEV BiIntv fm_extend1(const DevIndex& x, const BiIntv& ik, int c, int is_back)
