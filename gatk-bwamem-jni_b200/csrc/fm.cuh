@@ -106,38 +106,42 @@ DEV BiIntv fm_extend1(const DevIndex& x, const BiIntv& ik, int c, int is_back)
 	return r;
 }
 
-// Two independent backward extensions by the same base (two candidates of one row of a backward sweep): the eight
-// block loads are issued before any of them is consumed, so one lane keeps twice as many index reads in flight.
-DEV void fm_extend1_back_x2(const DevIndex& x, const BiIntv& ia, const BiIntv& ib, int c, BiIntv& ra, BiIntv& rb)
+// N independent backward extensions by the same base (candidates of one row of a backward sweep): all 4N block loads
+// are issued before any of them is consumed, so one lane keeps N times as many index reads in flight.
+#ifndef SEED_BWD_WAYS
+#define SEED_BWD_WAYS 2
+#endif
+template <int N>
+DEV void fm_extend1_back_xn(const DevIndex& x, const BiIntv* iv, int c, BiIntv* out)
 {
-	u64 kk[4]; bool zz[4];
-	const BiIntv* iv[2] = { &ia, &ib };
+	u64 kk[2 * N]; bool zz[2 * N];
 #pragma unroll
-	for (int t = 0; t < 2; ++t) {
-		const u64 k = iv[t]->x0 - 1, l = iv[t]->x0 - 1 + iv[t]->size;
+	for (int t = 0; t < N; ++t) {
+		const u64 k = iv[t].x0 - 1, l = iv[t].x0 - 1 + iv[t].size;
 		zz[2 * t] = k == ~0ull; zz[2 * t + 1] = l == ~0ull;
 		kk[2 * t] = zz[2 * t] ? 0 : k - (k >= x.primary);
 		kk[2 * t + 1] = zz[2 * t + 1] ? 0 : l - (l >= x.primary);
 	}
-	OccBlock b0 = load_block(x, kk[0] >> 7), b1 = load_block(x, kk[1] >> 7), b2 = load_block(x, kk[2] >> 7), b3 = load_block(x, kk[3] >> 7);
-	u64 cnt[4][4];
-	occ4_in_block(b0, kk[0], cnt[0]); occ4_in_block(b1, kk[1], cnt[1]); occ4_in_block(b2, kk[2], cnt[2]); occ4_in_block(b3, kk[3], cnt[3]);
+	OccBlock b[2 * N];
 #pragma unroll
-	for (int t = 0; t < 4; ++t) if (zz[t]) { cnt[t][0] = cnt[t][1] = cnt[t][2] = cnt[t][3] = 0; }
+	for (int t = 0; t < 2 * N; ++t) b[t] = load_block(x, kk[t] >> 7);
 	const u64 L2c = c == 0 ? x.L2[0] : c == 1 ? x.L2[1] : c == 2 ? x.L2[2] : x.L2[3];
 #pragma unroll
-	for (int t = 0; t < 2; ++t) {
-		const u64* tk = cnt[2 * t]; const u64* tl = cnt[2 * t + 1];
+	for (int t = 0; t < N; ++t) {
+		u64 tk[4], tl[4];
+		occ4_in_block(b[2 * t], kk[2 * t], tk); occ4_in_block(b[2 * t + 1], kk[2 * t + 1], tl);
+		if (zz[2 * t]) { tk[0] = tk[1] = tk[2] = tk[3] = 0; }
+		if (zz[2 * t + 1]) { tl[0] = tl[1] = tl[2] = tl[3] = 0; }
 		const u64 s1 = tl[1] - tk[1], s2 = tl[2] - tk[2], s3 = tl[3] - tk[3];
 		const u64 kc = c == 0 ? tk[0] : c == 1 ? tk[1] : c == 2 ? tk[2] : tk[3];
 		const u64 lc = c == 0 ? tl[0] : c == 1 ? tl[1] : c == 2 ? tl[2] : tl[3];
 		const u64 above = (c < 3 ? s3 : 0) + (c < 2 ? s2 : 0) + (c < 1 ? s1 : 0);
-		const u64 a0 = iv[t]->x0, s = iv[t]->size;
+		const u64 a0 = iv[t].x0, s = iv[t].size;
 		BiIntv r;
 		r.size = lc - kc;
 		r.x0 = L2c + 1 + kc;
-		r.x1 = iv[t]->x1 + ((a0 <= x.primary && a0 + s - 1 >= x.primary) ? 1 : 0) + above;
-		if (t == 0) ra = r; else rb = r;
+		r.x1 = iv[t].x1 + ((a0 <= x.primary && a0 + s - 1 >= x.primary) ? 1 : 0) + above;
+		out[t] = r;
 	}
 }
 
@@ -398,7 +402,9 @@ struct SeedSplitIO {
 	u32* err; int smem_cap;
 	u32* fb_list; u32* n_fb;          // reads whose scans did not fit the pool / task list: redone by fm_collect_queue<1>
 };
+#ifndef SEED_HEAVY_CANDS
 #define SEED_HEAVY_CANDS 24
+#endif
 #define SEED_POOL_OVERFLOW 0xffffffffu // value of pool_used[r] for such a read (its tasks are skipped)
 DEV uint4 cand_pack(const BiIntv& b, u32 end)
 {
@@ -517,7 +523,8 @@ DEV void fm_backward_queue(const DevIndex& x, const MemOpt& opt, const SeedSplit
 	int i = 0, c = -1, j = 0, n_prev = 0, n_curr = 0;
 	u64 last_size = 0; u32 last_beg = 0, pcur_end = 0; bool have_out = false;
 	BiIntv pcur; pcur.x0 = pcur.x1 = pcur.size = 0;
-	BiIntv pcur2 = pcur; u32 pcur2_end = 0;
+	BiIntv pcs[SEED_BWD_WAYS]; u32 pes[SEED_BWD_WAYS];
+	for (int t = 0; t < SEED_BWD_WAYS; ++t) { pcs[t] = pcur; pes[t] = 0; }
 	uint4 nxt = make_uint4(0, 0, 0, 0); // candidate j of the current row, fetched while candidate j - 1 was being extended
 #define B_EMIT_PCUR() do { if (n_curr == 0 && (!have_out || (u32)(i + 1) < last_beg)) { \
 		have_out = true; last_beg = (u32)(i + 1); \
@@ -553,9 +560,11 @@ DEV void fm_backward_queue(const DevIndex& x, const MemOpt& opt, const SeedSplit
 					break;
 				}
 				cand_unpack(nxt, pcur, pcur_end);
-				if (c >= 0) { // the candidates of a row are independent: two of them are extended per trip
-					pend = 1;
-					if (j + 1 < n_prev) { cand_unpack(cl[-(j + 1)], pcur2, pcur2_end); pend = 2; }
+				if (c >= 0) { // the candidates of a row are independent: up to SEED_BWD_WAYS of them are extended per trip
+					pcs[0] = pcur; pes[0] = pcur_end;
+					pend = n_prev - j < SEED_BWD_WAYS ? n_prev - j : SEED_BWD_WAYS;
+#pragma unroll
+					for (int t = 1; t < SEED_BWD_WAYS; ++t) if (t < pend) cand_unpack(cl[-(j + t)], pcs[t], pes[t]);
 					if (j + pend < n_prev) nxt = cl[-(j + pend)]; // (in-place compaction only writes slots <= j)
 					break;
 				}
@@ -568,11 +577,15 @@ DEV void fm_backward_queue(const DevIndex& x, const MemOpt& opt, const SeedSplit
 		}
 		if (lanes_all(st == B_ALLDONE)) break;
 		if (!pend) continue;
-		BiIntv okc, okc2;
-		if (pend == 2) fm_extend1_back_x2(x, pcur, pcur2, c, okc, okc2);
-		else { okc = fm_extend1(x, pcur, c, 1); okc2 = okc; }
-		for (int t = 0; t < pend; ++t) { // consumed in list order, exactly as one at a time
-			if (t == 1) { pcur = pcur2; pcur_end = pcur2_end; okc = okc2; }
+		BiIntv oks[SEED_BWD_WAYS];
+		if (pend == SEED_BWD_WAYS) fm_extend1_back_xn<SEED_BWD_WAYS>(x, pcs, c, oks);
+		else if (SEED_BWD_WAYS > 2 && pend >= 2) { fm_extend1_back_xn<2>(x, pcs, c, oks); for (int t = 2; t < pend; ++t) oks[t] = fm_extend1(x, pcs[t], c, 1); }
+		else oks[0] = fm_extend1(x, pcs[0], c, 1);
+#pragma unroll
+		for (int t = 0; t < SEED_BWD_WAYS; ++t) { // consumed in list order, exactly as one at a time
+			if (t >= pend) break;
+			pcur = pcs[t]; pcur_end = pes[t];
+			const BiIntv okc = oks[t];
 			if (okc.size < tk.min_intv) B_EMIT_PCUR();
 			else if (n_curr == 0 || okc.size != last_size) { cl[-n_curr] = cand_pack(okc, pcur_end); ++n_curr; last_size = okc.size; } // n_curr <= j
 			++j;
