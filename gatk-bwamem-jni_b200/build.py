@@ -36,7 +36,7 @@ def build_engine(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(ENGINE_SO) and os.path.getmtime(ENGINE_SO) >= _newest_src():
         return ENGINE_SO
     cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", ENGINE_SO, os.path.join(CSRC, "engine.cu"), os.path.join(CSRC, "sa_build.cu"), os.path.join(CSRC, "index_build.cpp"), "-lz"]
+          ["-o", ENGINE_SO, os.path.join(CSRC, "engine.cu"), os.path.join(CSRC, "sa_build.cu"), os.path.join(CSRC, "index_build.cpp"), os.path.join(CSRC, "host_scan.cpp"), "-lz"]
     subprocess.check_call(cmd, cwd=HERE)
     return ENGINE_SO
 

@@ -25,6 +25,10 @@
 
 namespace b200 {
 
+#ifndef B200_SIM
+void scan_reads(const char* base, uint32_t n, uint64_t* off, int* max_len, std::atomic<uint64_t>* progress); // host_scan.cpp
+#endif
+
 bool ImageView::parse(const uint8_t* m, size_t l)
 {
 	size_t k = 0;
@@ -238,29 +242,54 @@ inline bool Engine::stage(const char* blob_in, bool wait)
 	int max_len = 0;
 	uint64_t uploaded = 0;
 #ifndef B200_SIM
+	// While the host scans, NUP helper threads move the scanned prefix in alternating 4 MiB chunks: each copies its chunk
+	// into a pinned staging buffer (a pageable cudaMemcpy would be staged by the driver on ONE thread at ~9 GB/s) and
+	// queues a true DMA on its own stream.
 	std::atomic<uint64_t> scanned(0);
 	std::atomic<int> state(0); // 0 scanning, 1 scan finished, 2 abandon
 	int dev = 0; cudaGetDevice(&dev);
 	const uint64_t dcap = b_blob.cap;
 	char* dptr = (char*)b_blob.p;
-	std::thread copier;
-	const bool overlap = n_reads >= 4096 && dcap > 0 && !getenv("B200_NO_STAGE_OVERLAP");
-	if (overlap) copier = std::thread([&]() {
-		cudaSetDevice(dev);
-		const uint64_t CH = 4u << 20;
-		for (;;) {
-			const int stt = state.load(std::memory_order_acquire);
-			const uint64_t avail = scanned.load(std::memory_order_acquire);
-			if (stt == 2) break;
-			uint64_t end = avail < dcap ? avail : dcap;
-			if (end - uploaded >= CH || (stt == 1 && end > uploaded)) {
-				if (cudaMemcpyAsync(dptr + uploaded, base + uploaded, end - uploaded, cudaMemcpyHostToDevice, rt_stream()) != cudaSuccess) break;
-				uploaded = end;
-			} else if (stt == 1 || avail >= dcap) break;
-			else std::this_thread::yield();
-		}
-	});
-#endif
+	const uint64_t CH = 4u << 20;
+	enum { NUP = 4 };
+	static cudaStream_t up_stream[NUP] = { nullptr, nullptr, nullptr, nullptr };
+	static cudaEvent_t up_done[NUP] = { nullptr, nullptr, nullptr, nullptr };
+	static char* pin = nullptr; static uint64_t pin_cap = 0; // pinned staging, grow-only like the device buffer
+	std::thread copier[NUP]; uint64_t reached[NUP] = { 0, 0, 0, 0 };
+	bool overlap = n_reads >= 4096 && dcap > 0 && !getenv("B200_NO_STAGE_OVERLAP");
+	if (overlap && pin_cap < dcap) {
+		if (pin) cudaFreeHost(pin);
+		pin = nullptr; pin_cap = 0;
+		if (cudaHostAlloc((void**)&pin, dcap, cudaHostAllocDefault) == cudaSuccess) pin_cap = dcap; else { pin = nullptr; cudaGetLastError(); overlap = false; }
+	}
+	if (overlap) {
+		for (int t = 0; t < NUP; ++t) if (!up_stream[t]) { cudaStreamCreateWithFlags(&up_stream[t], cudaStreamNonBlocking); cudaEventCreateWithFlags(&up_done[t], cudaEventDisableTiming); }
+		for (int t = 0; t < NUP; ++t) copier[t] = std::thread([&, t]() {
+			cudaSetDevice(dev);
+			for (uint64_t c = (uint64_t)t; ; c += NUP) { // chunk c = bytes [c*CH, (c+1)*CH); reached[t] = first chunk start this thread has NOT sent
+				const uint64_t lo = c * CH;
+				uint64_t hi = lo + CH;
+				reached[t] = lo;
+				for (;;) {
+					const int stt = state.load(std::memory_order_acquire);
+					const uint64_t avail = scanned.load(std::memory_order_acquire);
+					if (stt == 2 || lo >= dcap) goto out;
+					if (avail >= hi && hi <= dcap) break;
+					if (stt == 1) { hi = avail < dcap ? avail : dcap; break; } // the last, partial chunk
+					std::this_thread::yield();
+				}
+				if (hi <= lo) break;
+				memcpy(pin + lo, base + lo, hi - lo);
+				if (cudaMemcpyAsync(dptr + lo, pin + lo, hi - lo, cudaMemcpyHostToDevice, up_stream[t]) != cudaSuccess) break;
+				reached[t] = lo + NUP * CH;
+				if (hi - lo < CH) break;
+			}
+		out:
+			cudaEventRecord(up_done[t], up_stream[t]);
+		});
+	}
+	scan_reads(base, n_reads, st_seq_off.data(), &max_len, overlap ? &scanned : nullptr);
+#else
 	{
 		const char* p = base;
 		for (uint32_t i = 0; i < n_reads; ++i) {
@@ -268,19 +297,23 @@ inline bool Engine::stage(const char* blob_in, bool wait)
 			st_seq_off[i] = (uint64_t)(p - base);
 			if ((int)l > max_len) max_len = (int)l;
 			p += l + 1;
-#ifndef B200_SIM
-			if ((i & 1023) == 1023) scanned.store((uint64_t)(p - base), std::memory_order_release);
-#endif
 		}
 		st_seq_off[n_reads] = (uint64_t)(p - base);
 	}
+#endif
 	st_n_reads = n_reads; st_max_len = max_len; st_blob_len = st_seq_off[n_reads];
 #ifndef B200_SIM
 	if (overlap) {
 		scanned.store(st_blob_len, std::memory_order_release);
 		state.store(st_blob_len + 16 <= dcap ? 1 : 2, std::memory_order_release);
-		copier.join();
-		if (st_blob_len + 16 > dcap) uploaded = 0; // the buffer is about to be replaced
+		for (int t = 0; t < NUP; ++t) copier[t].join();
+		if (st_blob_len + 16 <= dcap) {
+			// the chunks alternate between the threads: everything below the lowest of the frontiers is on its way
+			uploaded = reached[0];
+			for (int t = 1; t < NUP; ++t) uploaded = reached[t] < uploaded ? reached[t] : uploaded;
+			if (uploaded > st_blob_len) uploaded = st_blob_len;
+			for (int t = 0; t < NUP; ++t) cudaStreamWaitEvent(rt_stream(), up_done[t], 0);
+		}
 	}
 #endif
 	if (n_reads) {
