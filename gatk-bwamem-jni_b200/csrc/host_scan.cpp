@@ -64,3 +64,10 @@ void scan_reads(const char* base, uint32_t n, uint64_t* off, int* max_len, std::
 }
 
 } // namespace b200
+
+// test hook (tests/test_host_scan.py): the boundaries of n reads starting at blob; returns the total length
+extern "C" uint64_t b200_scanReads(const char* blob, uint32_t n, uint64_t* off, int* max_len, int force_plain)
+{
+	if (force_plain) b200::scan_reads_plain(blob, n, off, max_len, nullptr); else b200::scan_reads(blob, n, off, max_len, nullptr);
+	return off[n];
+}

@@ -80,6 +80,9 @@ float b200_lastBatchMs(void* idx);
  * (returns its byte size, -1 on failure) */
 int b200_stageBatch(void* idx, const char* pSeq);
 long long b200_alignStaged(void* idx, void* pOpts, void* pStats);
+/* read boundaries of a request body (n NUL-terminated reads at blob): off[0..n], longest read; returns off[n].  Test hook of
+ * the host-side scan (csrc/host_scan.cpp), which never reads past the n-th NUL. */
+uint64_t b200_scanReads(const char* blob, uint32_t n, uint64_t* off, int* max_len, int force_plain);
 /* index construction straight from bases in memory (synthetic-genome tools) */
 int b200_buildImageFromBases(int n_contigs, const char* names, const int64_t* lens, const char* bases,
                              const char* imgName, const char* prefixOrNull);
