@@ -98,6 +98,9 @@ static void rt_sort_u64(const uint64_t* in, uint64_t* out, uint64_t n)
 #define DEF_THREAD_QUEUE_KERNEL(body) \
 	__global__ void __launch_bounds__(THREADS_PER_BLOCK) k_##body(const __grid_constant__ BatchParams P, i64 n, u32* counter) { \
 		body(P, n, counter, (i64)blockIdx.x * blockDim.x + threadIdx.x); }
+#define DEF_THREAD_QUEUE_KERNEL_MB(body, minb) \
+	__global__ void __launch_bounds__(THREADS_PER_BLOCK, minb) k_##body(const __grid_constant__ BatchParams P, i64 n, u32* counter) { \
+		body(P, n, counter, (i64)blockIdx.x * blockDim.x + threadIdx.x); }
 #define DEF_WARP_KERNEL(wbody) \
 	__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_##wbody(const __grid_constant__ BatchParams P, i64 n, u32* counter) { \
 		extern __shared__ __align__(16) u8 smem_[]; \
@@ -168,8 +171,11 @@ DEF_THREAD_KERNEL(body_rescue_apply_multi)
 #endif
 DEF_WARP_KERNEL_DEVN_MB(wbody_rescue_sw, RESCUE_SW_MIN_BLOCKS)
 DEF_WARP_KERNEL(wbody_extend)
-DEF_THREAD_QUEUE_KERNEL(body_extend_q)
+DEF_THREAD_QUEUE_KERNEL_MB(body_extend_q, 2) // two blocks per SM fit the shared DP rows: let the state machine keep its state in registers
 DEF_THREAD_QUEUE_KERNEL(body_extend_task_q)
+// 8-bit cells: the shared rows of four blocks fit an SM; the read-level machine needs ~170 registers, so three of its blocks do
+DEF_THREAD_QUEUE_KERNEL_MB(body_extend_q8, 3)
+DEF_THREAD_QUEUE_KERNEL_MB(body_extend_task_q8, 4)
 DEF_WARP_KERNEL_DEVN(wbody_heavy_prep)
 DEF_WARP_KERNEL_DEVN(wbody_extend_heavy)
 DEF_THREAD_KERNEL(body_save_regs)

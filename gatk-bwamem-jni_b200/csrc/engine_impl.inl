@@ -473,7 +473,8 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 		if (!ok) { last_error = "device allocation failed (thread scratch)"; return nullptr; }
 		P.t_buf = b_tbuf.as<u8>(); P.redo_list = b_redo.as<u32>(); P.n_redo = b_misc.as<u32>() + 5;
 		P.heavy_list = b_heavy.as<u32>(); P.n_heavy = b_misc.as<u32>() + 6;
-		P.light_max_seeds = 12; P.light_max_chains = 4;
+		P.light_max_seeds = 12; P.light_max_chains = 4; P.tx_chunk = 32;
+		if (getenv("B200_TX_CHUNK")) P.tx_chunk = atoi(getenv("B200_TX_CHUNK")); // tuning aid (0: whole rows)
 		if (getenv("B200_LIGHT_SEEDS")) P.light_max_seeds = atoi(getenv("B200_LIGHT_SEEDS")); // tuning aids
 		if (getenv("B200_LIGHT_CHAINS")) P.light_max_chains = atoi(getenv("B200_LIGHT_CHAINS"));
 		if (getenv("B200_TEST_ALL_HEAVY")) P.light_max_seeds = -1;
@@ -484,17 +485,24 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 	if (getenv("B200_WARP_EXTEND")) RT_WARPS(wbody_extend, P, (int64_t)n_reads); // the all-warp formulation, kept for comparison
 	else {
 		int rw = max_len - opt.min_seed_len + 2;
-		if (rw < 2 * THREAD_RING_N) rw = 2 * THREAD_RING_N;
+		// cells: H and E as 8-bit halves when no score of the batch can exceed 255 (the per-read test in the kernel is the
+		// same bound), else as 16-bit halves.  Narrow cells halve the shared memory per thread: more resident warps.
+		int mxs = 0; for (int k = 0; k < 25; ++k) mxs = mxs > opt.mat[k] ? mxs : (int)opt.mat[k];
+		const bool narrow = !getenv("B200_EXT_WIDE_CELLS") && (int64_t)max_len * mxs + opt.pen_clip5 + opt.pen_clip3 <= 255;
+		const int cell = narrow ? 2 : 4;
+		if (rw * cell < 4 * THREAD_RING_N) rw = 4 * THREAD_RING_N / cell; // room for rings of at least THREAD_RING_N / 2 slots (region patching)
 		const size_t budget = 200 * 1024; // per block of THREADS_PER_BLOCK threads
 		const size_t qb = (size_t)((wm_cap + 2 + 3) & ~3);
-		if ((size_t)THREADS_PER_BLOCK * ((size_t)rw * 4 + qb) > budget) { // long reads: shorter rows, long extensions go to the warp kernel
-			size_t fit = budget / THREADS_PER_BLOCK > qb ? (budget / THREADS_PER_BLOCK - qb) / 4 : 0;
-			rw = fit >= 2 * THREAD_RING_N ? (int)fit : 0;
+		if (thread_ext_smem_bytes(THREADS_PER_BLOCK, rw, wm_cap, cell) > budget) { // long reads: shorter rows, long extensions go to the warp kernel
+			size_t fit = budget / THREADS_PER_BLOCK > qb ? (budget / THREADS_PER_BLOCK - qb) / cell : 0;
+			rw = fit * cell >= (size_t)4 * THREAD_RING_N ? (int)fit : 0;
 		}
 		if (rw == 0) RT_WARPS(wbody_extend, P, (int64_t)n_reads);
 		else {
 			P.t_ext_rw = rw;
-			RT_THREADS_QUEUE_SMEM(body_extend_q, P, (int64_t)n_reads, thread_ext_smem_bytes(THREADS_PER_BLOCK, rw, wm_cap));
+			const size_t ext_smem = thread_ext_smem_bytes(THREADS_PER_BLOCK, rw, wm_cap, cell);
+			if (narrow) RT_THREADS_QUEUE_SMEM(body_extend_q8, P, (int64_t)n_reads, ext_smem);
+			else RT_THREADS_QUEUE_SMEM(body_extend_q, P, (int64_t)n_reads, ext_smem);
 			if (getenv("B200_NO_EXT_TASKS")) RT_WARPS_DEVN(wbody_extend_heavy, P, P.n_heavy, (int64_t)n_reads); // each heavy read extended by its own warp
 			else {
 				// heavy reads: every kept seed becomes an extension task for the thread-level queue, then a warp per read
@@ -503,7 +511,8 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 				if (!(b_exttask.ensure(Tn * sizeof(ExtTask)) && b_extres.ensure(Tn * sizeof(ExtRes)) && b_ckrmax.ensure(Tn * 16))) { last_error = "device allocation failed (extension tasks)"; return nullptr; }
 				P.ext_tasks = b_exttask.as<ExtTask>(); P.ext_res = b_extres.as<ExtRes>(); P.ck_rmax = b_ckrmax.as<i64>(); P.n_ext_tasks = b_misc.as<u32>() + 21;
 				RT_WARPS_DEVN(wbody_heavy_prep, P, P.n_heavy, (int64_t)n_reads);
-				RT_THREADS_QUEUE_SMEM(body_extend_task_q, P, (int64_t)T, thread_ext_smem_bytes(THREADS_PER_BLOCK, rw, wm_cap));
+				if (narrow) RT_THREADS_QUEUE_SMEM(body_extend_task_q8, P, (int64_t)T, ext_smem);
+				else RT_THREADS_QUEUE_SMEM(body_extend_task_q, P, (int64_t)T, ext_smem);
 				P.use_ext_res = 1;
 				RT_WARPS_DEVN(wbody_extend_heavy, P, P.n_heavy, (int64_t)n_reads);
 				P.use_ext_res = 0;

@@ -10,8 +10,9 @@
 //     right extension forwards, so no reversed copy is made;
 //   * the per-read control flow (chains, seeds by score, containment test, left / right extension, band retry) is a
 //     state machine around ONE DP-row site: each trip of the outer loop advances the machine (lane-divergent, cheap)
-//     to the next row that has to be computed, then all lanes compute one row together.  Lanes therefore stay in step
-//     at row granularity no matter how their extensions differ in length;
+//     to the next row that has to be computed, then all lanes compute up to P.tx_chunk cells of their row together (a
+//     longer row continues on the next trip).  Lanes therefore stay in step at chunk granularity no matter how their
+//     extensions differ in length and width;
 //   * reads are not assigned statically: a lane that finishes its read takes the next one from a batch-wide counter
 //     (fetching is one more state of the machine), so no lane idles while a neighbour works through a long read; a
 //     warp vote at the top of every trip is both the exit test and the reconvergence point.
@@ -22,7 +23,7 @@
 #include "extend.cuh"
 
 struct ThreadExtMem {
-	u32* row; int row_stride; int row_cap;   // DP row: element j at row[j * row_stride], j in [0, row_cap)
+	void* row; int row_stride; int row_cap;  // DP row: cell j at ((CELL*)row)[j * row_stride], j in [0, row_cap)
 	u8* rd; int rd_stride; int rd_cap;       // read codes: element j at rd[j * rd_stride]
 	const u64* rowpack;                      // [5]: byte c of rowpack[t] = mat[t*5 + c]
 };
@@ -39,7 +40,7 @@ DEV bool tx_all_done(bool done) { return lanes_all(done); }
 // a repeat family has hundreds of chains, and extending them one after the other in one thread or warp leaves the
 // rest of the GPU waiting for it.  Every seed is extended unconditionally (its result does not depend on the hits
 // found so far; only the decision to USE it does -- the containment test is replayed by wbody_extend_heavy).
-template <bool TASKS>
+template <bool TASKS, class CELL>
 DEV void thread_extend_queue(const BatchParams& P, i64 n_reads, u32* counter, const ThreadExtMem& tm, WarpMem& wm, WarpScratch& ws, u32* lerr)
 {
 	const DevIndex& x = P.x; const MemOpt& opt = P.opt; Counters* cnt = P.cnt; u32* err = P.err;
@@ -49,6 +50,12 @@ DEV void thread_extend_queue(const BatchParams& P, i64 n_reads, u32* counter, co
 	int mx = 0;
 	for (int k = 0; k < 25; ++k) mx = mx > opt.mat[k] ? mx : (int)opt.mat[k];
 	const size_t RS = (size_t)tm.row_stride, QS = (size_t)tm.rd_stride;
+	CELL* const row = (CELL*)tm.row;
+	constexpr int HB = (int)sizeof(CELL) * 4;          // bits of H and of E in one cell
+	constexpr u32 HMASK = (1u << HB) - 1u;
+	// largest score a cell may have to hold (h0 + qlen * max match <= l_query * max match), with the clipping penalties as margin
+	constexpr i64 SCORE_CAP = sizeof(CELL) == 2 ? 255 : 60000;
+	const int chunk = P.tx_chunk > 0 ? P.tx_chunk : 1 << 30;
 	// per-read state
 	i64 r = -1; int l_query = 0, nck = 0, av_cap = 0;
 	const u8* query = nullptr; const ChainK* cks = nullptr; const Seed* ks_base = nullptr; u64* srt = nullptr; Reg* av = nullptr;
@@ -70,6 +77,8 @@ DEV void thread_extend_queue(const BatchParams& P, i64 n_reads, u32* counter, co
 	int i = 0, beg = 0, end = 0, max = 0, max_i = -1, max_j = -1, max_ie = -1, gscore = -1, max_off = 0;
 	u64 cells = 0, n_ext = 0;
 	u32 pac_word = 0; i64 pac_widx = -1;
+	// row in flight (a row may span several visits of the DP site)
+	int jc = -1, h1 = 0, f = 0, m = 0, mj = -1; u64 rp = 0;
 
 	for (;;) {
 		// ---- advance to the next DP row (or to the end of the read)
@@ -86,7 +95,7 @@ DEV void thread_extend_queue(const BatchParams& P, i64 n_reads, u32* counter, co
 					res_slot = t0 + ck.seed_start + tk.t;
 					l_query = (int)(P.seq_off[r + 1] - P.seq_off[r] - 1);
 					query = P.seq + P.seq_off[r];
-					if (l_query > tm.rd_cap || (i64)2 * l_query * mx + opt.pen_clip5 + opt.pen_clip3 > 60000) { TX_TO_WARP(); break; }
+					if (l_query > tm.rd_cap || (i64)(sizeof(CELL) == 2 ? 1 : 2) * l_query * mx + opt.pen_clip5 + opt.pen_clip3 > SCORE_CAP) { TX_TO_WARP(); break; }
 					for (int j = 0; j < l_query; ++j) tm.rd[(size_t)j * QS] = query[j];
 					seeds = P.ks + t0 + ck.seed_start; cn = 0; // (seed coverage is computed by the replay)
 					s = seeds[tk.t];
@@ -113,7 +122,7 @@ DEV void thread_extend_queue(const BatchParams& P, i64 n_reads, u32* counter, co
 				l_query = (int)(P.seq_off[r + 1] - P.seq_off[r] - 1);
 				query = P.seq + P.seq_off[r];
 				// 16-bit storage bound: no H/E value exceeds (seed + left + right) scores <= 2 * l_query * mx, plus the clip bonus
-				if (l_query > tm.rd_cap || (i64)2 * l_query * mx + opt.pen_clip5 + opt.pen_clip3 > 60000) { TX_TO_WARP(); break; }
+				if (l_query > tm.rd_cap || (i64)(sizeof(CELL) == 2 ? 1 : 2) * l_query * mx + opt.pen_clip5 + opt.pen_clip3 > SCORE_CAP) { TX_TO_WARP(); break; }
 				cks = P.ck + t0; ks_base = P.ks + t0; srt = P.srt + t0; av = P.regs_tmp + t0; av_cap = nks;
 				for (int j = 0; j < l_query; ++j) tm.rd[(size_t)j * QS] = query[j];
 				c = -1; n_av = 0; *lerr = 0;
@@ -206,10 +215,10 @@ DEV void thread_extend_queue(const BatchParams& P, i64 n_reads, u32* counter, co
 				if (side == 0) aw0 = w; else aw1 = w;
 				if (qlen + 1 > tm.row_cap) { TX_TO_WARP(); break; }
 				{
-					u32* rw = tm.row;
-					rw[0] = (u32)h0;
+					CELL* rw = row;
+					rw[0] = (CELL)h0;
 					int v = h0 > oe_ins ? h0 - oe_ins : 0;
-					for (int j = 1; j <= qlen; ++j) { rw[(size_t)j * RS] = (u32)v; v = v > e_ins ? v - e_ins : 0; }
+					for (int j = 1; j <= qlen; ++j) { rw[(size_t)j * RS] = (CELL)v; v = v > e_ins ? v - e_ins : 0; }
 				}
 				// band clamp of ksw_extend2, int(double(x) / e + 1.) clamped to >= 1, in integers (see cal_max_gap)
 				const int xi_ = qlen * mx + end_bonus - o_ins, xd_ = qlen * mx + end_bonus - o_del;
@@ -260,31 +269,37 @@ DEV void thread_extend_queue(const BatchParams& P, i64 n_reads, u32* counter, co
 			}
 		}
 		if (tx_all_done(done)) break; // full-mask vote: exit test and reconvergence point
-		// ---- one DP row (the scalar recurrence of ksw_extend2, verbatim)
+		// ---- one visit of the DP site: up to P.tx_chunk cells of the current row (the scalar recurrence of ksw_extend2,
+		// verbatim).  A row longer than the chunk is continued on the next trip, so a lane with a short row waits for at
+		// most one chunk of its neighbours' long rows, not for the whole row.
 		if (in_ext) {
-			// target base of row i from the 2-bit packed reference (one 32-bit word holds 16 consecutive forward bases)
-			const i64 p = tbase + (i64)tdir * i;
-			const bool rv = p >= l_pac;
-			const i64 fp = rv ? (l_pac << 1) - 1 - p : p;
-			const i64 widx = fp >> 4;
-			if (widx != pac_widx) { pac_word = ldg((const u32*)x.pac + widx); pac_widx = widx; }
-			int tb = (int)((pac_word >> (8 * (int)((fp >> 2) & 3))) >> ((~fp & 3) << 1) & 3);
-			if (rv) tb = 3 - tb;
-			const u64 rp = tm.rowpack[tb];
-			if (beg < i - w) beg = i - w;
-			if (end > i + w + 1) end = i + w + 1;
-			if (end > qlen) end = qlen;
-			int h1, f = 0, m = 0, mj = -1;
-			if (beg == 0) { h1 = h0 - (o_del + e_del * (i + 1)); if (h1 < 0) h1 = 0; } else h1 = 0;
-			if (end > beg) cells += (u64)(end - beg);
+			if (jc < 0) { // row start
+				// target base of row i from the 2-bit packed reference (one 32-bit word holds 16 consecutive forward bases)
+				const i64 p = tbase + (i64)tdir * i;
+				const bool rv = p >= l_pac;
+				const i64 fp = rv ? (l_pac << 1) - 1 - p : p;
+				const i64 widx = fp >> 4;
+				if (widx != pac_widx) { pac_word = ldg((const u32*)x.pac + widx); pac_widx = widx; }
+				int tb = (int)((pac_word >> (8 * (int)((fp >> 2) & 3))) >> ((~fp & 3) << 1) & 3);
+				if (rv) tb = 3 - tb;
+				rp = tm.rowpack[tb];
+				if (beg < i - w) beg = i - w;
+				if (end > i + w + 1) end = i + w + 1;
+				if (end > qlen) end = qlen;
+				f = 0; m = 0; mj = -1;
+				if (beg == 0) { h1 = h0 - (o_del + e_del * (i + 1)); if (h1 < 0) h1 = 0; } else h1 = 0;
+				if (end > beg) cells += (u64)(end - beg);
+				jc = beg;
+			}
 			{
-				u32* rw = tm.row + (size_t)beg * RS;
-				const u8* qp = tm.rd + (size_t)(qbase + qdir * beg) * QS;
+				const int jstop = end - jc > chunk ? jc + chunk : end;
+				CELL* rw = row + (size_t)jc * RS;
+				const u8* qp = tm.rd + (size_t)(qbase + qdir * jc) * QS;
 				const ptrdiff_t qstep = (ptrdiff_t)qdir * (ptrdiff_t)QS;
 #pragma unroll 4
-				for (int j = beg; j < end; ++j) {
-					const u32 he = *rw;
-					int M = (int)(he & 0xffffu), e = (int)(he >> 16);
+				for (int j = jc; j < jstop; ++j) {
+					const u32 he = (u32)*rw;
+					int M = (int)(he & HMASK), e = (int)(he >> HB);
 					const int sc = (int)(i8)(rp >> (8 * (int)*qp));
 					M = M ? M + sc : 0;
 					int h = M > e ? M : e;
@@ -293,35 +308,41 @@ DEV void thread_extend_queue(const BatchParams& P, i64 n_reads, u32* counter, co
 					m = m > h ? m : h;
 					int t = M - oe_del; t = t > 0 ? t : 0;
 					e -= e_del; e = e > t ? e : t;
-					*rw = (u32)h1 | (u32)e << 16;
+					*rw = (CELL)((u32)h1 | (u32)e << HB);
 					h1 = h;
 					t = M - oe_ins; t = t > 0 ? t : 0;
 					f -= e_ins; f = f > t ? f : t;
 					rw += RS; qp += qstep;
 				}
-				tm.row[(size_t)end * RS] = (u32)h1; // H[end] = h1, E[end] = 0
+				jc = jstop > jc ? jstop : jc;
 			}
-			bool fin = false;
-			const int jfin = beg < end ? end : beg;
-			if (jfin == qlen) { max_ie = gscore > h1 ? max_ie : i; gscore = gscore > h1 ? gscore : h1; }
-			if (m == 0) fin = true;
-			else {
-				if (m > max) { max = m; max_i = i; max_j = mj; int off = iabs(mj - i); max_off = max_off > off ? max_off : off; }
-				else if (opt.zdrop > 0) {
-					if (i - max_i > mj - max_j) { if (max - m - ((i - max_i) - (mj - max_j)) * e_del > opt.zdrop) fin = true; }
-					else { if (max - m - ((mj - max_j) - (i - max_i)) * e_ins > opt.zdrop) fin = true; }
+			if (jc >= end) { // row end
+				jc = -1;
+				row[(size_t)end * RS] = (CELL)h1; // H[end] = h1, E[end] = 0
+				bool fin = false;
+				const int jfin = beg < end ? end : beg;
+				if (jfin == qlen) { max_ie = gscore > h1 ? max_ie : i; gscore = gscore > h1 ? gscore : h1; }
+				if (m == 0) fin = true;
+				else {
+					if (m > max) { max = m; max_i = i; max_j = mj; int off = iabs(mj - i); max_off = max_off > off ? max_off : off; }
+					else if (opt.zdrop > 0) {
+						if (i - max_i > mj - max_j) { if (max - m - ((i - max_i) - (mj - max_j)) * e_del > opt.zdrop) fin = true; }
+						else { if (max - m - ((mj - max_j) - (i - max_i)) * e_ins > opt.zdrop) fin = true; }
+					}
+					if (!fin) {
+						// shrink [beg, end) to the cells that can still score (leading / trailing zeros of the row)
+						int jb = beg; const CELL* pb = row + (size_t)beg * RS;
+						while (jb < end && *pb == 0) { ++jb; pb += RS; }
+						beg = jb;
+						int je = end; const CELL* pe = row + (size_t)end * RS;
+						while (je >= jb && *pe == 0) { --je; pe -= RS; }
+						end = je + 2 < qlen ? je + 2 : qlen;
+						++i;
+						if (i >= tlen) fin = true;
+					}
 				}
-				if (!fin) {
-					int j;
-					for (j = beg; j < end && tm.row[(size_t)j * RS] == 0; ++j) {}
-					beg = j;
-					for (j = end; j >= beg && tm.row[(size_t)j * RS] == 0; --j) {}
-					end = j + 2 < qlen ? j + 2 : qlen;
-					++i;
-					if (i >= tlen) fin = true;
-				}
+				if (fin) { in_ext = false; phase = TX_EXT_DONE; }
 			}
-			if (fin) { in_ext = false; phase = TX_EXT_DONE; }
 		}
 	}
 #undef TX_TO_WARP

@@ -54,6 +54,7 @@ struct BatchParams {
 	u8* t_buf; size_t t_stride; int t_z_cap, t_cigar_cap, t_md_cap, t_xa_cap;
 	u32* redo_list; u32* n_redo; // items a thread-level kernel handed over to the warp-level kernel
 	u32* heavy_list; u32* n_heavy; int light_max_seeds, light_max_chains; // extension: reads with many seeds go to the warp-level kernel
+	int tx_chunk;                           // thread-level extension: cells of one DP row per visit of the row site
 	ExtTask* ext_tasks; u32* n_ext_tasks; ExtRes* ext_res; i64* ck_rmax; // heavy reads: per-seed extension tasks, results, per-chain windows
 	u32* chain_heavy; u32* n_chain_heavy; int chain_heavy_seeds; // reads chained by a warp
 	GaTask* ga_tasks; GaRes* ga_res; u32* n_ga_tasks; u32 ga_cap; u32* ga_item0; u32* ga_itemn; // two-pass finalize (galign_thread.cuh)
@@ -447,34 +448,48 @@ DEV void make_thread_ctx(const BatchParams& P, i64 tid, WarpMem& wm, WarpScratch
 }
 // extension, thread per read (extend_thread.cuh): reads with few kept seeds are extended by one thread with its DP row
 // in shared memory; the others, and reads that do not fit the thread-level rows, are queued for the warp-per-read kernel
-HOSTDEV size_t thread_ext_smem_bytes(int block_threads, int rw, int wm_cap) { return (size_t)block_threads * ((size_t)rw * 4 + (size_t)((wm_cap + 2 + 3) & ~3)); }
+// cell = bytes of one DP cell: 4 (H and E as 16-bit halves) or 2 (8-bit halves, when no score of the batch can exceed 255)
+HOSTDEV size_t thread_ext_smem_bytes(int block_threads, int rw, int wm_cap, int cell) { return (size_t)block_threads * ((((size_t)rw * cell + 3) & ~(size_t)3) + (size_t)((wm_cap + 2 + 3) & ~3)); }
 #ifdef B200_SIM
 static u32 g_sim_ext_row[4096]; static u8 g_sim_ext_q[4096];
 #endif
+template <class CELL>
 DEV void make_thread_ext_ctx(const BatchParams& P, i64 tid, ThreadExtMem& tm, WarpMem& wm, WarpScratch& ws, u32* lerr)
 {
 	make_thread_ctx(P, tid, wm, ws, lerr); // global scratch (traceback, cigar, MD) of this thread slot
 #ifdef B200_SIM
 	u32* words = g_sim_ext_row; u8* qrow = g_sim_ext_q; const int st = 1;
+	void* rowbase = (void*)g_sim_ext_row;
 	const int rw = P.t_ext_rw < 4096 ? P.t_ext_rw : 4096;
 #else
 	extern __shared__ __align__(16) u8 tsm_[];
 	const int st = (int)blockDim.x, rw = P.t_ext_rw;
 	u32* words = (u32*)tsm_ + threadIdx.x;
-	u8* qrow = tsm_ + (size_t)st * rw * 4 + threadIdx.x;
+	void* rowbase = (void*)((CELL*)tsm_ + threadIdx.x); // cell j of this thread at element j * st + tid
+	u8* qrow = tsm_ + (size_t)st * ((((size_t)rw * sizeof(CELL)) + 3) & ~(size_t)3) + threadIdx.x;
 #endif
-	tm.row = words; tm.row_stride = st; tm.row_cap = rw;
+	tm.row = rowbase; tm.row_stride = st; tm.row_cap = rw;
 	tm.rd = qrow; tm.rd_stride = st; tm.rd_cap = P.wm_cap + 2;
 	tm.rowpack = P.rowpack;
-	// the banded global alignment of region patching runs after the extensions: its rings and query row reuse the space
-	wm.ringH = (i32*)words; wm.ringE = (i32*)words + (size_t)THREAD_RING_N * st; wm.ring_n = THREAD_RING_N; wm.ring_stride = st;
+	// the banded global alignment of region patching runs after the extensions: its rings (two of ring_n i32 per thread,
+	// a power of two that fits the space of the DP row) and query row reuse the space
+	int ring_n = THREAD_RING_N;
+	while (ring_n > 1 && (size_t)ring_n * 8 > (size_t)rw * sizeof(CELL)) ring_n >>= 1;
+	wm.ringH = (i32*)words; wm.ringE = (i32*)words + (size_t)ring_n * st; wm.ring_n = ring_n; wm.ring_stride = st;
 	wm.q = qrow; wm.q_stride = st;
 }
 DEV void body_extend_q(const BatchParams& P, i64 n, u32* counter, i64 tid)
 {
 	u32 lerr = 0;
-	ThreadExtMem tm; WarpMem wm; WarpScratch ws; make_thread_ext_ctx(P, tid, tm, wm, ws, &lerr);
-	thread_extend_queue<false>(P, n, counter, tm, wm, ws, &lerr);
+	ThreadExtMem tm; WarpMem wm; WarpScratch ws; make_thread_ext_ctx<u32>(P, tid, tm, wm, ws, &lerr);
+	thread_extend_queue<false, u32>(P, n, counter, tm, wm, ws, &lerr);
+}
+// the same with 8-bit H and E (batches whose scores cannot exceed 255: half the shared memory per thread, more warps per SM)
+DEV void body_extend_q8(const BatchParams& P, i64 n, u32* counter, i64 tid)
+{
+	u32 lerr = 0;
+	ThreadExtMem tm; WarpMem wm; WarpScratch ws; make_thread_ext_ctx<u16>(P, tid, tm, wm, ws, &lerr);
+	thread_extend_queue<false, u16>(P, n, counter, tm, wm, ws, &lerr);
 }
 // heavy reads, step 1 (warp per read): the reference window of every chain and one extension task per kept seed
 template <int W>
@@ -516,8 +531,15 @@ DEV void body_extend_task_q(const BatchParams& P, i64 n, u32* counter, i64 tid)
 {
 	(void)n;
 	u32 lerr = 0;
-	ThreadExtMem tm; WarpMem wm; WarpScratch ws; make_thread_ext_ctx(P, tid, tm, wm, ws, &lerr);
-	thread_extend_queue<true>(P, (i64)*P.n_ext_tasks, counter, tm, wm, ws, &lerr);
+	ThreadExtMem tm; WarpMem wm; WarpScratch ws; make_thread_ext_ctx<u32>(P, tid, tm, wm, ws, &lerr);
+	thread_extend_queue<true, u32>(P, (i64)*P.n_ext_tasks, counter, tm, wm, ws, &lerr);
+}
+DEV void body_extend_task_q8(const BatchParams& P, i64 n, u32* counter, i64 tid)
+{
+	(void)n;
+	u32 lerr = 0;
+	ThreadExtMem tm; WarpMem wm; WarpScratch ws; make_thread_ext_ctx<u16>(P, tid, tm, wm, ws, &lerr);
+	thread_extend_queue<true, u16>(P, (i64)*P.n_ext_tasks, counter, tm, wm, ws, &lerr);
 }
 template <int W>
 DEV void wbody_extend_heavy(const BatchParams& P, i64 item, WarpMem& wm, WarpScratch& ws) { wbody_extend<W>(P, (i64)P.heavy_list[item], wm, ws); }

@@ -50,6 +50,29 @@ def test_sim_rescue_fallback_path(small_genome, monkeypatch):
     assert a == b, first_diff(a, b, blob, True)
 
 
+def test_sim_extension_wide_cells(small_genome, monkeypatch):
+    """Thread-level extension with 16-bit H/E cells (what batches with scores above 255 use) on a batch that would
+    run with 8-bit cells."""
+    g, img = small_genome
+    blob, _ = simdata.make_reads(g, 79, 300, 150, True, repeat_read_frac=0.3, err_rate=0.03, indel_frac=0.4)
+    a = run_blob(oracle_lib(), img, blob, 2)
+    monkeypatch.setenv("B200_EXT_WIDE_CELLS", "1")
+    b = run_blob(sim_lib(), img, blob, 2)
+    assert a == b, first_diff(a, b, blob, True)
+
+
+@pytest.mark.parametrize("chunk", ["1", "7", "0"])
+def test_sim_extension_rows_in_chunks(small_genome, monkeypatch, chunk):
+    """Thread-level extension: a DP row is computed in visits of B200_TX_CHUNK cells (0: whole rows); the result must
+    not depend on the chunk."""
+    g, img = small_genome
+    blob, _ = simdata.make_reads(g, 78, 300, 150, True, repeat_read_frac=0.3, err_rate=0.03, indel_frac=0.4)
+    a = run_blob(oracle_lib(), img, blob, 2)
+    monkeypatch.setenv("B200_TX_CHUNK", chunk)
+    b = run_blob(sim_lib(), img, blob, 2)
+    assert a == b, first_diff(a, b, blob, True)
+
+
 def test_sim_repeat_family_stress():
     """Reads with hundreds of hits each (see common.repeat_family_image)."""
     g, img = repeat_family_image()

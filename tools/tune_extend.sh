@@ -1,5 +1,5 @@
-# development aid: extension routing variants
-for env in "X=1" "B200_TEST_ALL_HEAVY=1" "B200_LIGHT_SEEDS=4 B200_LIGHT_CHAINS=2" "B200_LIGHT_SEEDS=2 B200_LIGHT_CHAINS=1"; do
+# development aid: extension variants (cell width; cells of a DP row per visit of the row site)
+for env in "X=1" "B200_EXT_WIDE_CELLS=1" "B200_TX_CHUNK=0" "B200_TX_CHUNK=64"; do
   echo "== $env"
   env $env python bench.py --steps 2 --warmup 2 --no-cpu-baseline 2>/dev/null | python -c "
 import json,sys
