@@ -352,6 +352,16 @@ float b200_lastBatchMs(void* h)
 	return t;
 }
 int b200_setDevice(int dev) { return cudaSetDevice(dev) == cudaSuccess ? 0 : 1; }
+// test hook (tests/test_smem_layout.py): where thread `tid` of a block of `threads` keeps its DP row, read codes and
+// patching rings in the dynamic shared memory of the thread-level extension kernels.
+// out = { row offset, row element stride (bytes), query offset, query stride, ringH offset, ringE offset, ring stride, ring slots, block bytes }
+void b200_extLayout(int threads, int tid, int rw, int wm_cap, int cell, int patches, uint64_t* out)
+{
+	const ExtLayout L = thread_ext_layout(threads, tid, rw, wm_cap, cell, patches != 0);
+	out[0] = L.row_off; out[1] = (uint64_t)threads * cell; out[2] = L.q_off; out[3] = (uint64_t)threads;
+	out[4] = L.ringH_off; out[5] = L.ringE_off; out[6] = (uint64_t)threads * 4; out[7] = (uint64_t)L.ring_n;
+	out[8] = thread_ext_smem_bytes(threads, rw, wm_cap, cell, patches && cell == 2 ? EXT_NARROW_RING : 0);
+}
 const char* b200_lastError(void* h) { return h ? ((Engine*)h)->last_error.c_str() : ""; }
 // copies up to cap stage times (ms) of the last batch; names[i] points at static strings; returns the stage count
 int b200_lastStageTimes(void* h, float* ms, const char** names, int cap)

@@ -490,17 +490,19 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 		int mxs = 0; for (int k = 0; k < 25; ++k) mxs = mxs > opt.mat[k] ? mxs : (int)opt.mat[k];
 		const bool narrow = !getenv("B200_EXT_WIDE_CELLS") && (int64_t)max_len * mxs + opt.pen_clip5 + opt.pen_clip3 <= 255;
 		const int cell = narrow ? 2 : 4;
-		if (rw * cell < 4 * THREAD_RING_N) rw = 4 * THREAD_RING_N / cell; // room for rings of at least THREAD_RING_N / 2 slots (region patching)
+		if (!narrow && rw * cell < 4 * THREAD_RING_N) rw = 4 * THREAD_RING_N / cell; // wide cells: the patching rings reuse the row (at least THREAD_RING_N / 2 slots)
 		const size_t budget = 200 * 1024; // per block of THREADS_PER_BLOCK threads
 		const size_t qb = (size_t)((wm_cap + 2 + 3) & ~3);
-		if (thread_ext_smem_bytes(THREADS_PER_BLOCK, rw, wm_cap, cell) > budget) { // long reads: shorter rows, long extensions go to the warp kernel
-			size_t fit = budget / THREADS_PER_BLOCK > qb ? (budget / THREADS_PER_BLOCK - qb) / cell : 0;
-			rw = fit * cell >= (size_t)4 * THREAD_RING_N ? (int)fit : 0;
+		if (thread_ext_smem_bytes(THREADS_PER_BLOCK, rw, wm_cap, cell, narrow ? EXT_NARROW_RING : 0) > budget) { // long reads: shorter rows, long extensions go to the warp kernel
+			const size_t fixed = qb + (narrow ? EXT_NARROW_RING * 8 : 0);
+			size_t fit = budget / THREADS_PER_BLOCK > fixed ? (budget / THREADS_PER_BLOCK - fixed) / cell : 0;
+			rw = fit * cell >= (size_t)4 * THREAD_RING_N ? (int)fit : 0; // (narrow cells never get here: their scores bound max_len by 255)
 		}
 		if (rw == 0) RT_WARPS(wbody_extend, P, (int64_t)n_reads);
 		else {
 			P.t_ext_rw = rw;
-			const size_t ext_smem = thread_ext_smem_bytes(THREADS_PER_BLOCK, rw, wm_cap, cell);
+			const size_t ext_smem = thread_ext_smem_bytes(THREADS_PER_BLOCK, rw, wm_cap, cell, narrow ? EXT_NARROW_RING : 0); // read-level kernel (patches regions)
+			const size_t task_smem = thread_ext_smem_bytes(THREADS_PER_BLOCK, rw, wm_cap, cell, 0);                        // seed-level tasks never do
 			if (narrow) RT_THREADS_QUEUE_SMEM(body_extend_q8, P, (int64_t)n_reads, ext_smem);
 			else RT_THREADS_QUEUE_SMEM(body_extend_q, P, (int64_t)n_reads, ext_smem);
 			if (getenv("B200_NO_EXT_TASKS")) RT_WARPS_DEVN(wbody_extend_heavy, P, P.n_heavy, (int64_t)n_reads); // each heavy read extended by its own warp
@@ -511,8 +513,8 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 				if (!(b_exttask.ensure(Tn * sizeof(ExtTask)) && b_extres.ensure(Tn * sizeof(ExtRes)) && b_ckrmax.ensure(Tn * 16))) { last_error = "device allocation failed (extension tasks)"; return nullptr; }
 				P.ext_tasks = b_exttask.as<ExtTask>(); P.ext_res = b_extres.as<ExtRes>(); P.ck_rmax = b_ckrmax.as<i64>(); P.n_ext_tasks = b_misc.as<u32>() + 21;
 				RT_WARPS_DEVN(wbody_heavy_prep, P, P.n_heavy, (int64_t)n_reads);
-				if (narrow) RT_THREADS_QUEUE_SMEM(body_extend_task_q8, P, (int64_t)T, ext_smem);
-				else RT_THREADS_QUEUE_SMEM(body_extend_task_q, P, (int64_t)T, ext_smem);
+				if (narrow) RT_THREADS_QUEUE_SMEM(body_extend_task_q8, P, (int64_t)T, task_smem);
+				else RT_THREADS_QUEUE_SMEM(body_extend_task_q, P, (int64_t)T, task_smem);
 				P.use_ext_res = 1;
 				RT_WARPS_DEVN(wbody_extend_heavy, P, P.n_heavy, (int64_t)n_reads);
 				P.use_ext_res = 0;
@@ -609,10 +611,14 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 			if (!ok) { last_error = "device allocation failed (alignment tasks)"; return nullptr; }
 			P.ga_tasks = b_gatask.as<GaTask>(); P.ga_res = b_gares.as<GaRes>(); P.ga_item0 = b_gaitem0.as<u32>(); P.ga_itemn = b_gaitemn.as<u32>();
 			P.n_ga_tasks = b_misc.as<u32>() + 23;
-			if (pe) RT_THREADS_TID_RING(body_final_pe_collect, P, n_items); else RT_THREADS_TID_RING(body_final_se_collect, P, n_items);
+			// (neither pass computes an alignment itself: no shared-memory rings, which lets a third block onto each SM)
+			const bool fin_ring = getenv("B200_TEST_FINAL_RING") != nullptr;
+			if (fin_ring) { if (pe) RT_THREADS_TID_RING(body_final_pe_collect, P, n_items); else RT_THREADS_TID_RING(body_final_se_collect, P, n_items); }
+			else if (pe) RT_THREADS_TID(body_final_pe_collect, P, n_items); else RT_THREADS_TID(body_final_se_collect, P, n_items);
 			rt_memset(P.var_cursor, 0, 4); // payloads written while collecting are discarded
-			RT_THREADS_QUEUE_SMEM(body_galign_task_q, P, (int64_t)P.ga_cap, thread_block_smem_bytes(THREADS_PER_BLOCK, P.wm_cap));
-			if (pe) RT_THREADS_TID_RING(body_final_pe_consume, P, n_items); else RT_THREADS_TID_RING(body_final_se_consume, P, n_items);
+			RT_THREADS_QUEUE_SMEM(body_galign_task_q, P, (int64_t)P.ga_cap, galign_block_smem_bytes(THREADS_PER_BLOCK, P.wm_cap));
+			if (fin_ring) { if (pe) RT_THREADS_TID_RING(body_final_pe_consume, P, n_items); else RT_THREADS_TID_RING(body_final_se_consume, P, n_items); }
+			else if (pe) RT_THREADS_TID(body_final_pe_consume, P, n_items); else RT_THREADS_TID(body_final_se_consume, P, n_items);
 		}
 		if (pe) RT_WARPS_DEVN(wbody_final_pe_redo, P, P.n_redo, n_items); else RT_WARPS_DEVN(wbody_final_se_redo, P, P.n_redo, n_items);
 	}

@@ -11,8 +11,8 @@
 //            flow is a state machine around ONE DP-row site, like the seed extension (extend_thread.cuh);
 //   consume  the decision logic runs again on the restored region lists, warp_reg2aln now returning the k-th
 //            precomputed alignment of the item.
-// A task the thread-level formulation cannot take (band wider than the shared-memory ring, traceback or CIGAR larger
-// than the thread scratch) is marked invalid; its item is then redone by the warp-level kernel, as before.
+// A task the thread-level formulation cannot take (band wider than the shared-memory ring, scores beyond the 16-bit
+// rows, traceback or CIGAR larger than the thread scratch) is marked invalid; its item is then redone by the warp-level kernel, as before.
 #pragma once
 #include "finalize.cuh"
 
@@ -25,9 +25,19 @@ DEV void thread_galign_queue(const BatchParams& P, i64 n_tasks, u32* counter, Wa
 	const int o_del = opt.o_del, e_del = opt.e_del, o_ins = opt.o_ins, e_ins = opt.e_ins;
 	const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
 	const size_t qs = (size_t)wm.q_stride;
-	i32* const H = wm.ringH; i32* const E = wm.ringE;
+	// ring of column slots, H and E of a column packed into one word as 16-bit halves (one LDS + one STS per cell, half
+	// the shared memory).  "Minus infinity" shrinks with them: every value of the recurrence is either real or
+	// GA_NEG_INF plus a real offset, two infinite values compare by their offsets whatever the constant is, and an
+	// infinite one loses against every real one as long as the offsets stay below GA_SPAN -- tasks that could exceed
+	// that bound are left to the warp kernel (32-bit rows).
+	u32* const R = (u32*)wm.ringH;
 	const int rmask = wm.ring_n - 1, rstride = wm.ring_stride;
+	enum { GA_NEG_INF = -0x4000, GA_SPAN = 0x1800 };
+	int pen_max = 1;
+	for (int k = 0; k < 25; ++k) { int v = iabs((int)opt.mat[k]); pen_max = pen_max > v ? pen_max : v; }
+	pen_max = pen_max > e_del ? pen_max : e_del; pen_max = pen_max > e_ins ? pen_max : e_ins;
 #define HX(j) (((j) & rmask) * rstride)
+#define GA_PACK(h_, e_) ((u32)(u16)(i16)(h_) | (u32)(u16)(i16)(e_) << 16)
 	int phase = GA_FETCH;
 	bool in_dp = false, done = false;
 	i64 tid = -1;
@@ -81,18 +91,18 @@ DEV void thread_galign_queue(const BatchParams& P, i64 n_tasks, u32* counter, Wa
 				w = w > min_w ? w : min_w;
 				n_col = l_query < 2 * w + 1 ? l_query : 2 * w + 1;
 				zs = (n_col + 3) & ~3;
-				if ((size_t)zs * (size_t)rlen > ws.z_cap || 2 * w + 2 > wm.ring_n) { GA_INVALID(); break; } // a warp takes the item
+				if ((size_t)zs * (size_t)rlen > ws.z_cap || 2 * w + 2 > wm.ring_n || (i64)(rlen + l_query + 2) * pen_max + oe_del + oe_ins >= GA_SPAN) { GA_INVALID(); break; } // a warp takes the item
 				{ // first row of the banded global alignment (ksw_global2)
 					int j;
-					H[HX(0)] = 0; E[HX(0)] = KSW_NEG_INF;
-					for (j = 1; j <= l_query && j <= w; ++j) { H[HX(j)] = -(o_ins + e_ins * j); E[HX(j)] = KSW_NEG_INF; }
-					if (j <= l_query) { H[HX(j)] = KSW_NEG_INF; E[HX(j)] = KSW_NEG_INF; } // column w+1: only ever read after row 0 overwrote it
+					R[HX(0)] = GA_PACK(0, GA_NEG_INF);
+					for (j = 1; j <= l_query && j <= w; ++j) R[HX(j)] = GA_PACK(-(o_ins + e_ins * j), GA_NEG_INF);
+					if (j <= l_query) R[HX(j)] = GA_PACK(GA_NEG_INF, GA_NEG_INF); // column w+1: only ever read after row 0 overwrote it
 				}
 				i = 0; ++n_glb;
 				if (rlen > 0) in_dp = true; else phase = GA_DP_END;
 				break; }
 			case GA_DP_END: { // score and traceback -> CIGAR (ops are produced back to front)
-				score = H[HX(l_query)];
+				score = (int)(i16)(u16)(R[HX(l_query)] & 0xffffu);
 				const u8* z = ws.z; u32* cigar = ws.cigar; const int cigar_cap = ws.cigar_cap;
 				bool cg_ovf = false;
 				int n_cigar = 0, which = 0, ti = rlen - 1, k = (ti + w + 1 < l_query ? ti + w + 1 : l_query) - 1;
@@ -170,18 +180,19 @@ DEV void thread_galign_queue(const BatchParams& P, i64 n_tasks, u32* counter, Wa
 			int tb = (int)((pac_word >> (8 * (int)((fp >> 2) & 3))) >> ((~fp & 3) << 1) & 3);
 			if (rv) tb = 3 - tb;
 			const u64 rowpack = P.rowpack[tb];
-			int f = KSW_NEG_INF, h1, t;
+			int f = GA_NEG_INF, h1, t;
 			const int beg = i > w ? i - w : 0;
 			const int end = i + w + 1 < l_query ? i + w + 1 : l_query;
-			h1 = beg == 0 ? -(o_del + e_del * (i + 1)) : KSW_NEG_INF;
+			h1 = beg == 0 ? -(o_del + e_del * (i + 1)) : GA_NEG_INF;
 			if (end > beg) cells += (u64)(end - beg);
 			u32* zi = (u32*)(ws.z + (size_t)i * zs);
 			u32 zw = 0;
 			for (int j = beg; j < end; ++j) {
 				const int jx = HX(j);
-				int h, m = H[jx], e = E[jx];
+				const u32 he = R[jx];
+				int h, m = (int)(i16)(u16)(he & 0xffffu), e = (int)he >> 16;
 				u32 d;
-				H[jx] = h1;
+				const int hl = h1; // H(i, j-1): the value column j holds for the next row
 				m += (int)(i8)(rowpack >> (8 * (int)WQ(wm, j)));
 				d = m >= e ? 0u : 1u;
 				h = m >= e ? m : e;
@@ -192,7 +203,7 @@ DEV void thread_galign_queue(const BatchParams& P, i64 n_tasks, u32* counter, Wa
 				e -= e_del;
 				d |= e > t ? 1u << 2 : 0u;
 				e = e > t ? e : t;
-				E[jx] = e;
+				R[jx] = GA_PACK(hl, e);
 				t = m - oe_ins;
 				f -= e_ins;
 				d |= f > t ? 2u << 4 : 0u;
@@ -201,12 +212,13 @@ DEV void thread_galign_queue(const BatchParams& P, i64 n_tasks, u32* counter, Wa
 				zw |= d << ((k & 3) << 3);
 				if ((k & 3) == 3 || j == end - 1) { zi[k >> 2] = zw; zw = 0; }
 			}
-			H[HX(end)] = h1; E[HX(end)] = KSW_NEG_INF;
+			R[HX(end)] = GA_PACK(h1, GA_NEG_INF);
 			++i;
 			if (i >= rlen) { in_dp = false; phase = GA_DP_END; }
 		}
 	}
 #undef HX
+#undef GA_PACK
 #undef GA_INVALID
 	(void)qs;
 	if (P.cnt) { if (cells) atomic_add_u64(&P.cnt->cells_glb, cells); if (n_glb) atomic_add_u64(&P.cnt->n_glb, n_glb); }

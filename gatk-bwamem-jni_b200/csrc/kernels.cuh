@@ -448,47 +448,78 @@ DEV void make_thread_ctx(const BatchParams& P, i64 tid, WarpMem& wm, WarpScratch
 }
 // extension, thread per read (extend_thread.cuh): reads with few kept seeds are extended by one thread with its DP row
 // in shared memory; the others, and reads that do not fit the thread-level rows, are queued for the warp-per-read kernel
-// cell = bytes of one DP cell: 4 (H and E as 16-bit halves) or 2 (8-bit halves, when no score of the batch can exceed 255)
-HOSTDEV size_t thread_ext_smem_bytes(int block_threads, int rw, int wm_cap, int cell) { return (size_t)block_threads * ((((size_t)rw * cell + 3) & ~(size_t)3) + (size_t)((wm_cap + 2 + 3) & ~3)); }
+// cell = bytes of one DP cell: 4 (H and E as 16-bit halves) or 2 (8-bit halves, when no score of the batch can exceed 255).
+// own_ring = slots of a separate pair of i32 rings for the banded global alignment of region patching: with 4-byte
+// cells the rings simply reuse the thread's DP row (same interleaving, so the words are the thread's own); 2-byte cells
+// are interleaved differently -- a 32-bit ring word over them would belong to two other threads -- so the rings get
+// their own (small) space behind the query row, or none at all (kernels that never patch).
+#define EXT_NARROW_RING 16
+HOSTDEV size_t thread_ext_smem_bytes(int block_threads, int rw, int wm_cap, int cell, int own_ring)
+{
+	return (size_t)block_threads * ((((size_t)rw * cell + 3) & ~(size_t)3) + (size_t)((wm_cap + 2 + 3) & ~3) + (size_t)own_ring * 8);
+}
+// Byte layout of a thread's share of the block's dynamic shared memory (element k of an array sits at
+// base + (k * threads + tid) * element size: bank tid % 32 for 4-byte elements whatever k is).  A host function so
+// that tests/test_smem_layout.py can check that no two threads of a block ever share a byte (b200_extLayout).
+struct ExtLayout { size_t row_off, q_off, ringH_off, ringE_off; int ring_n; };
+HOSTDEV ExtLayout thread_ext_layout(int threads, int tid, int rw, int wm_cap, int cell, bool patches)
+{
+	ExtLayout L;
+	const size_t row_bytes = (((size_t)rw * cell) + 3) & ~(size_t)3, qb = (size_t)((wm_cap + 2 + 3) & ~3);
+	L.row_off = (size_t)tid * cell;                       // cells: stride threads * cell
+	L.q_off = (size_t)threads * row_bytes + tid;          // read codes: stride threads
+	L.ringH_off = L.ringE_off = 0; L.ring_n = 0;
+	if (!patches) return L;
+	if (cell == 4) { // the rings reuse the thread's own DP row (same interleaving)
+		int ring_n = THREAD_RING_N;
+		while (ring_n > 1 && (size_t)ring_n * 8 > (size_t)rw * cell) ring_n >>= 1;
+		L.ring_n = ring_n; L.ringH_off = (size_t)tid * 4; L.ringE_off = ((size_t)ring_n * threads + tid) * 4;
+	} else { // own space behind the query rows
+		const size_t base = (size_t)threads * (row_bytes + qb);
+		L.ring_n = EXT_NARROW_RING; L.ringH_off = base + (size_t)tid * 4; L.ringE_off = base + ((size_t)EXT_NARROW_RING * threads + tid) * 4;
+	}
+	return L;
+}
 #ifdef B200_SIM
 static u32 g_sim_ext_row[4096]; static u8 g_sim_ext_q[4096];
 #endif
 template <class CELL>
-DEV void make_thread_ext_ctx(const BatchParams& P, i64 tid, ThreadExtMem& tm, WarpMem& wm, WarpScratch& ws, u32* lerr)
+DEV void make_thread_ext_ctx(const BatchParams& P, i64 tid, ThreadExtMem& tm, WarpMem& wm, WarpScratch& ws, u32* lerr, bool patches)
 {
-	make_thread_ctx(P, tid, wm, ws, lerr); // global scratch (traceback, cigar, MD) of this thread slot
+	make_thread_ctx(P, tid, wm, ws, lerr); // global scratch (traceback, cigar, MD) of this thread slot; the rings are replaced below
 #ifdef B200_SIM
-	u32* words = g_sim_ext_row; u8* qrow = g_sim_ext_q; const int st = 1;
-	void* rowbase = (void*)g_sim_ext_row;
-	const int rw = P.t_ext_rw < 4096 ? P.t_ext_rw : 4096;
+	const int st = 1, rw = P.t_ext_rw < 4096 ? P.t_ext_rw : 4096;
+	u8* base = (u8*)g_sim_ext_row; u8* qrow = g_sim_ext_q;
+	ExtLayout L = thread_ext_layout(1, 0, rw, P.wm_cap, (int)sizeof(CELL), patches);
+	i32* ringH = sizeof(CELL) == 4 ? (i32*)base : g_sim_ring; i32* ringE = ringH + L.ring_n;
 #else
 	extern __shared__ __align__(16) u8 tsm_[];
 	const int st = (int)blockDim.x, rw = P.t_ext_rw;
-	u32* words = (u32*)tsm_ + threadIdx.x;
-	void* rowbase = (void*)((CELL*)tsm_ + threadIdx.x); // cell j of this thread at element j * st + tid
-	u8* qrow = tsm_ + (size_t)st * ((((size_t)rw * sizeof(CELL)) + 3) & ~(size_t)3) + threadIdx.x;
+	u8* base = tsm_;
+	const ExtLayout L = thread_ext_layout(st, (int)threadIdx.x, rw, P.wm_cap, (int)sizeof(CELL), patches);
+	u8* qrow = base + L.q_off;
+	i32* ringH = (i32*)(base + L.ringH_off); i32* ringE = (i32*)(base + L.ringE_off);
 #endif
-	tm.row = rowbase; tm.row_stride = st; tm.row_cap = rw;
+	tm.row = (void*)(base + L.row_off); tm.row_stride = st; tm.row_cap = rw;
 	tm.rd = qrow; tm.rd_stride = st; tm.rd_cap = P.wm_cap + 2;
 	tm.rowpack = P.rowpack;
-	// the banded global alignment of region patching runs after the extensions: its rings (two of ring_n i32 per thread,
-	// a power of two that fits the space of the DP row) and query row reuse the space
-	int ring_n = THREAD_RING_N;
-	while (ring_n > 1 && (size_t)ring_n * 8 > (size_t)rw * sizeof(CELL)) ring_n >>= 1;
-	wm.ringH = (i32*)words; wm.ringE = (i32*)words + (size_t)ring_n * st; wm.ring_n = ring_n; wm.ring_stride = st;
+	// the banded global alignment of region patching runs after the extensions: two rings of ring_n i32 per thread
+	// (a power of two) and the query row
+	if (L.ring_n == 0) { wm.ringH = nullptr; wm.ringE = nullptr; wm.ring_n = 0; wm.ring_stride = 0; }
+	else { wm.ringH = ringH; wm.ringE = ringE; wm.ring_n = L.ring_n; wm.ring_stride = st; }
 	wm.q = qrow; wm.q_stride = st;
 }
 DEV void body_extend_q(const BatchParams& P, i64 n, u32* counter, i64 tid)
 {
 	u32 lerr = 0;
-	ThreadExtMem tm; WarpMem wm; WarpScratch ws; make_thread_ext_ctx<u32>(P, tid, tm, wm, ws, &lerr);
+	ThreadExtMem tm; WarpMem wm; WarpScratch ws; make_thread_ext_ctx<u32>(P, tid, tm, wm, ws, &lerr, true);
 	thread_extend_queue<false, u32>(P, n, counter, tm, wm, ws, &lerr);
 }
 // the same with 8-bit H and E (batches whose scores cannot exceed 255: half the shared memory per thread, more warps per SM)
 DEV void body_extend_q8(const BatchParams& P, i64 n, u32* counter, i64 tid)
 {
 	u32 lerr = 0;
-	ThreadExtMem tm; WarpMem wm; WarpScratch ws; make_thread_ext_ctx<u16>(P, tid, tm, wm, ws, &lerr);
+	ThreadExtMem tm; WarpMem wm; WarpScratch ws; make_thread_ext_ctx<u16>(P, tid, tm, wm, ws, &lerr, true);
 	thread_extend_queue<false, u16>(P, n, counter, tm, wm, ws, &lerr);
 }
 // heavy reads, step 1 (warp per read): the reference window of every chain and one extension task per kept seed
@@ -531,14 +562,14 @@ DEV void body_extend_task_q(const BatchParams& P, i64 n, u32* counter, i64 tid)
 {
 	(void)n;
 	u32 lerr = 0;
-	ThreadExtMem tm; WarpMem wm; WarpScratch ws; make_thread_ext_ctx<u32>(P, tid, tm, wm, ws, &lerr);
+	ThreadExtMem tm; WarpMem wm; WarpScratch ws; make_thread_ext_ctx<u32>(P, tid, tm, wm, ws, &lerr, false);
 	thread_extend_queue<true, u32>(P, (i64)*P.n_ext_tasks, counter, tm, wm, ws, &lerr);
 }
 DEV void body_extend_task_q8(const BatchParams& P, i64 n, u32* counter, i64 tid)
 {
 	(void)n;
 	u32 lerr = 0;
-	ThreadExtMem tm; WarpMem wm; WarpScratch ws; make_thread_ext_ctx<u16>(P, tid, tm, wm, ws, &lerr);
+	ThreadExtMem tm; WarpMem wm; WarpScratch ws; make_thread_ext_ctx<u16>(P, tid, tm, wm, ws, &lerr, false);
 	thread_extend_queue<true, u16>(P, (i64)*P.n_ext_tasks, counter, tm, wm, ws, &lerr);
 }
 template <int W>
@@ -602,11 +633,20 @@ DEV void body_final_pe_collect(const BatchParams& P, i64 pr, i64 tid) { final_co
 DEV void body_final_se_collect(const BatchParams& P, i64 r, i64 tid) { final_collect_item(P, r, tid, false); }
 DEV void body_final_pe_consume(const BatchParams& P, i64 pr, i64 tid) { final_consume_item(P, pr, tid, true); }
 DEV void body_final_se_consume(const BatchParams& P, i64 r, i64 tid) { final_consume_item(P, r, tid, false); }
+// shared memory of the alignment-task kernel: one ring of THREAD_RING_N packed H/E words per thread + the query row
+HOSTDEV size_t galign_block_smem_bytes(int block_threads, int wm_cap) { return (size_t)block_threads * (THREAD_RING_N * 4 + (size_t)((wm_cap + 2 + 3) & ~3)); }
 DEV void body_galign_task_q(const BatchParams& P, i64 n, u32* counter, i64 tid)
 {
 	(void)n;
 	u32 lerr = 0;
 	WarpMem wm; WarpScratch ws; make_thread_ctx(P, tid, wm, ws, &lerr);
+#ifndef B200_SIM
+	{
+		extern __shared__ __align__(16) u8 tsm_[];
+		wm.ringH = (i32*)tsm_ + threadIdx.x; wm.ringE = nullptr; wm.ring_n = THREAD_RING_N; wm.ring_stride = (int)blockDim.x;
+		wm.q = tsm_ + (size_t)blockDim.x * THREAD_RING_N * 4 + threadIdx.x; wm.q_stride = (int)blockDim.x;
+	}
+#endif
 	thread_galign_queue(P, (i64)*P.n_ga_tasks, counter, wm, ws, &lerr);
 }
 template <int W>

@@ -83,6 +83,9 @@ long long b200_alignStaged(void* idx, void* pOpts, void* pStats);
 /* read boundaries of a request body (n NUL-terminated reads at blob): off[0..n], longest read; returns off[n].  Test hook of
  * the host-side scan (csrc/host_scan.cpp), which never reads past the n-th NUL. */
 uint64_t b200_scanReads(const char* blob, uint32_t n, uint64_t* off, int* max_len, int force_plain);
+/* test hook: shared-memory layout of the thread-level extension kernels (see csrc/kernels.cuh: thread_ext_layout);
+ * out[9] = row offset, row stride, query offset, query stride, ringH offset, ringE offset, ring stride, ring slots, block bytes */
+void b200_extLayout(int threads, int tid, int rw, int wm_cap, int cell, int patches, uint64_t* out);
 /* index construction straight from bases in memory (synthetic-genome tools) */
 int b200_buildImageFromBases(int n_contigs, const char* names, const int64_t* lens, const char* bases,
                              const char* imgName, const char* prefixOrNull);
