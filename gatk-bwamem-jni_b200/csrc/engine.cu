@@ -360,7 +360,7 @@ void b200_extLayout(int threads, int tid, int rw, int wm_cap, int cell, int patc
 	const ExtLayout L = thread_ext_layout(threads, tid, rw, wm_cap, cell, patches != 0);
 	out[0] = L.row_off; out[1] = (uint64_t)threads * cell; out[2] = L.q_off; out[3] = (uint64_t)threads;
 	out[4] = L.ringH_off; out[5] = L.ringE_off; out[6] = (uint64_t)threads * 4; out[7] = (uint64_t)L.ring_n;
-	out[8] = thread_ext_smem_bytes(threads, rw, wm_cap, cell, patches && cell == 2 ? EXT_NARROW_RING : 0);
+	out[8] = thread_ext_smem_bytes(threads, rw, wm_cap, cell);
 }
 const char* b200_lastError(void* h) { return h ? ((Engine*)h)->last_error.c_str() : ""; }
 // copies up to cap stage times (ms) of the last batch; names[i] points at static strings; returns the stage count

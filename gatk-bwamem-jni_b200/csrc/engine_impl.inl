@@ -493,16 +493,14 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 		if (!narrow && rw * cell < 4 * THREAD_RING_N) rw = 4 * THREAD_RING_N / cell; // wide cells: the patching rings reuse the row (at least THREAD_RING_N / 2 slots)
 		const size_t budget = 200 * 1024; // per block of THREADS_PER_BLOCK threads
 		const size_t qb = (size_t)((wm_cap + 2 + 3) & ~3);
-		if (thread_ext_smem_bytes(THREADS_PER_BLOCK, rw, wm_cap, cell, narrow ? EXT_NARROW_RING : 0) > budget) { // long reads: shorter rows, long extensions go to the warp kernel
-			const size_t fixed = qb + (narrow ? EXT_NARROW_RING * 8 : 0);
-			size_t fit = budget / THREADS_PER_BLOCK > fixed ? (budget / THREADS_PER_BLOCK - fixed) / cell : 0;
+		if (thread_ext_smem_bytes(THREADS_PER_BLOCK, rw, wm_cap, cell) > budget) { // long reads: shorter rows, long extensions go to the warp kernel
+			size_t fit = budget / THREADS_PER_BLOCK > qb ? (budget / THREADS_PER_BLOCK - qb) / cell : 0;
 			rw = fit * cell >= (size_t)4 * THREAD_RING_N ? (int)fit : 0; // (narrow cells never get here: their scores bound max_len by 255)
 		}
 		if (rw == 0) RT_WARPS(wbody_extend, P, (int64_t)n_reads);
 		else {
 			P.t_ext_rw = rw;
-			const size_t ext_smem = thread_ext_smem_bytes(THREADS_PER_BLOCK, rw, wm_cap, cell, narrow ? EXT_NARROW_RING : 0); // read-level kernel (patches regions)
-			const size_t task_smem = thread_ext_smem_bytes(THREADS_PER_BLOCK, rw, wm_cap, cell, 0);                        // seed-level tasks never do
+			const size_t ext_smem = thread_ext_smem_bytes(THREADS_PER_BLOCK, rw, wm_cap, cell), task_smem = ext_smem;
 			if (narrow) RT_THREADS_QUEUE_SMEM(body_extend_q8, P, (int64_t)n_reads, ext_smem);
 			else RT_THREADS_QUEUE_SMEM(body_extend_q, P, (int64_t)n_reads, ext_smem);
 			if (getenv("B200_NO_EXT_TASKS")) RT_WARPS_DEVN(wbody_extend_heavy, P, P.n_heavy, (int64_t)n_reads); // each heavy read extended by its own warp

@@ -95,9 +95,10 @@ DEVNI bool warp_gen_cigar2(const DevIndex& x, const MemOpt& opt, WarpMem& wm, Wa
 			int n_col = l_query < 2 * w + 1 ? l_query : 2 * w + 1;
 			if ((size_t)(W == 1 ? ((n_col + 3) & ~3) : n_col) * (size_t)rlen > ws.z_cap) { ONE_LANE { atomic_or_u32(ws.err, ERR_Z_OVERFLOW); } return false; }
 		}
-		if (W == 1 && (wm.ringH == nullptr || 2 * w + 2 > wm.ring_n)) { // band too wide for the thread's ring: a warp takes the item
-			atomic_or_u32(ws.err, ERR_NEED_WARP);
-			return false;
+		if (W == 1) { // thread-level rows: a shared-memory ring when the band fits it; the full rows of the thread's global scratch in kernels without rings
+			const bool ring_ok = wm.ringH != nullptr && 2 * w + 2 <= wm.ring_n;
+			const bool rows_ok = wm.ringH == nullptr && wm.H != nullptr && l_query <= wm.cap;
+			if (!ring_ok && !rows_ok) { atomic_or_u32(ws.err, ERR_NEED_WARP); return false; } // a warp takes the item
 		}
 		*score = warp_global2<W>(x, opt, wm, l_query, (int)rlen, ta, w, ws.z, want_cigar ? ws.cigar : nullptr, ws.cigar_cap, ws.err, &nc, cnt ? &cnt->cells_glb : nullptr);
 		if (cnt) { ONE_LANE { atomic_add_u64(&cnt->n_glb, 1); } }

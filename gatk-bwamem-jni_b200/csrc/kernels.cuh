@@ -449,14 +449,13 @@ DEV void make_thread_ctx(const BatchParams& P, i64 tid, WarpMem& wm, WarpScratch
 // extension, thread per read (extend_thread.cuh): reads with few kept seeds are extended by one thread with its DP row
 // in shared memory; the others, and reads that do not fit the thread-level rows, are queued for the warp-per-read kernel
 // cell = bytes of one DP cell: 4 (H and E as 16-bit halves) or 2 (8-bit halves, when no score of the batch can exceed 255).
-// own_ring = slots of a separate pair of i32 rings for the banded global alignment of region patching: with 4-byte
-// cells the rings simply reuse the thread's DP row (same interleaving, so the words are the thread's own); 2-byte cells
-// are interleaved differently -- a 32-bit ring word over them would belong to two other threads -- so the rings get
-// their own (small) space behind the query row, or none at all (kernels that never patch).
-#define EXT_NARROW_RING 16
-HOSTDEV size_t thread_ext_smem_bytes(int block_threads, int rw, int wm_cap, int cell, int own_ring)
+// The banded global alignment of region patching (rare) needs two i32 rows of its own: with 4-byte cells they are rings
+// over the thread's DP row (same interleaving, so the words are the thread's own); 2-byte cells are interleaved
+// differently -- a 32-bit word over them would belong to two other threads -- so there the alignment uses the full
+// rows of the thread's global scratch instead (shared memory spent on rings would cost the kernel L1 for its stack).
+HOSTDEV size_t thread_ext_smem_bytes(int block_threads, int rw, int wm_cap, int cell)
 {
-	return (size_t)block_threads * ((((size_t)rw * cell + 3) & ~(size_t)3) + (size_t)((wm_cap + 2 + 3) & ~3) + (size_t)own_ring * 8);
+	return (size_t)block_threads * ((((size_t)rw * cell + 3) & ~(size_t)3) + (size_t)((wm_cap + 2 + 3) & ~3));
 }
 // Byte layout of a thread's share of the block's dynamic shared memory (element k of an array sits at
 // base + (k * threads + tid) * element size: bank tid % 32 for 4-byte elements whatever k is).  A host function so
@@ -474,11 +473,9 @@ HOSTDEV ExtLayout thread_ext_layout(int threads, int tid, int rw, int wm_cap, in
 		int ring_n = THREAD_RING_N;
 		while (ring_n > 1 && (size_t)ring_n * 8 > (size_t)rw * cell) ring_n >>= 1;
 		L.ring_n = ring_n; L.ringH_off = (size_t)tid * 4; L.ringE_off = ((size_t)ring_n * threads + tid) * 4;
-	} else { // own space behind the query rows
-		const size_t base = (size_t)threads * (row_bytes + qb);
-		L.ring_n = EXT_NARROW_RING; L.ringH_off = base + (size_t)tid * 4; L.ringE_off = base + ((size_t)EXT_NARROW_RING * threads + tid) * 4;
 	}
-	return L;
+	(void)qb;
+	return L; // 2-byte cells: no rings (ring_n = 0), see thread_ext_smem_bytes
 }
 #ifdef B200_SIM
 static u32 g_sim_ext_row[4096]; static u8 g_sim_ext_q[4096];
@@ -491,7 +488,7 @@ DEV void make_thread_ext_ctx(const BatchParams& P, i64 tid, ThreadExtMem& tm, Wa
 	const int st = 1, rw = P.t_ext_rw < 4096 ? P.t_ext_rw : 4096;
 	u8* base = (u8*)g_sim_ext_row; u8* qrow = g_sim_ext_q;
 	ExtLayout L = thread_ext_layout(1, 0, rw, P.wm_cap, (int)sizeof(CELL), patches);
-	i32* ringH = sizeof(CELL) == 4 ? (i32*)base : g_sim_ring; i32* ringE = ringH + L.ring_n;
+	i32* ringH = (i32*)base; i32* ringE = ringH + L.ring_n;
 #else
 	extern __shared__ __align__(16) u8 tsm_[];
 	const int st = (int)blockDim.x, rw = P.t_ext_rw;
@@ -504,7 +501,7 @@ DEV void make_thread_ext_ctx(const BatchParams& P, i64 tid, ThreadExtMem& tm, Wa
 	tm.rd = qrow; tm.rd_stride = st; tm.rd_cap = P.wm_cap + 2;
 	tm.rowpack = P.rowpack;
 	// the banded global alignment of region patching runs after the extensions: two rings of ring_n i32 per thread
-	// (a power of two) and the query row
+	// (a power of two) over the DP row, or wm.H / wm.E in global scratch when there are none; the query row is shared
 	if (L.ring_n == 0) { wm.ringH = nullptr; wm.ringE = nullptr; wm.ring_n = 0; wm.ring_stride = 0; }
 	else { wm.ringH = ringH; wm.ringE = ringE; wm.ring_n = L.ring_n; wm.ring_stride = st; }
 	wm.q = qrow; wm.q_stride = st;

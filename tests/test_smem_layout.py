@@ -36,7 +36,7 @@ def test_no_two_threads_share_a_byte(cell, patches, read_len):
             mine.update(range(row_off + j * row_st, row_off + j * row_st + cell))
         for j in range(wm_cap + 2):
             mine.add(q_off + j * q_st)
-        if patches:
+        if patches and cell == 4:  # (2-byte cells: the patching alignment uses rows in global scratch, no rings)
             assert ring_n >= 16 and ring_n & (ring_n - 1) == 0
             for k in range(ring_n):
                 mine.update(range(rh + k * r_st, rh + k * r_st + 4))
