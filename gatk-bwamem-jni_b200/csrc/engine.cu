@@ -26,11 +26,28 @@ static inline bool cu_ok(cudaError_t e, const char* what)
 }
 static cudaStream_t g_stream = nullptr; // one stream per process (one process per GPU)
 static int g_sm_count = 0;
+// A second stream for a kernel that is independent of the next one on the main stream (a few long-running warps
+// beside a throughput kernel): rt_fork_aux() .. launches .. rt_back_to_main() .. launches .. rt_join_aux().
+static cudaStream_t g_aux_stream = nullptr, g_stream_override = nullptr;
+static cudaEvent_t g_ev_fork = nullptr, g_ev_join = nullptr;
 static cudaStream_t rt_stream()
 {
+	if (g_stream_override) return g_stream_override;
 	if (!g_stream) { cu_ok(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking), "cudaStreamCreate"); }
 	return g_stream;
 }
+static void rt_fork_aux()
+{
+	cudaStream_t main_s = rt_stream();
+	if (!g_aux_stream) {
+		cu_ok(cudaStreamCreateWithFlags(&g_aux_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+		cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&g_ev_join, cudaEventDisableTiming);
+	}
+	cudaEventRecord(g_ev_fork, main_s); cudaStreamWaitEvent(g_aux_stream, g_ev_fork, 0);
+	g_stream_override = g_aux_stream;
+}
+static void rt_back_to_main() { cudaEventRecord(g_ev_join, g_aux_stream); g_stream_override = nullptr; }
+static void rt_join_aux() { cudaStreamWaitEvent(rt_stream(), g_ev_join, 0); }
 static int rt_sm_count()
 {
 	if (!g_sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev); if (g_sm_count <= 0) g_sm_count = 148; }
@@ -152,6 +169,7 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, SEED_MIN_BLOCKS) k_body_see
 __global__ void __launch_bounds__(THREADS_PER_BLOCK, SEED_MIN_BLOCKS) k_body_seed3_q(const __grid_constant__ BatchParams P, i64 n, u32* counter) { body_seed3_q(P, n, counter, (i64)blockIdx.x * blockDim.x + threadIdx.x); }
 DEF_THREAD_KERNEL(body_sal)
 DEF_THREAD_KERNEL(body_chain)
+DEF_THREAD_KERNEL(body_chain_classify)
 DEF_WARP_KERNEL_DEVN(wbody_chain_heavy)
 DEF_THREAD_KERNEL(body_pe_cand)
 DEF_THREAD_KERNEL(body_reg_cap)
@@ -208,6 +226,7 @@ struct StageTimer { // CUDA events on the launching stream around every stage of
 		if (!init) { for (auto& e : ev) cudaEventCreate(&e); init = true; } n = 0; cudaEventRecord(ev[0], rt_stream()); }
 	void mark(const char* nm)
 	{
+		if (g_stream_override) return; // a kernel on the auxiliary stream: its time is inside the stages of the main stream it overlaps
 		if (n < MAXS) { name[n] = nm; ++n; cudaEventRecord(ev[n], rt_stream()); }
 		static const bool trace = getenv("B200_TRACE") != nullptr; // development aid: synchronise and report after every stage
 		if (trace) {

@@ -418,13 +418,22 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 			P.seed_pool = b_seedpool.as<uint4>(); P.seed_pool_used = b_seedused.as<u32>(); P.seed_tasks = b_seedtask.as<SeedTask>(); P.n_seed_tasks = b_misc.as<u32>() + 24;
 			P.seed_fb = b_seedfb.as<u32>(); P.n_seed_fb = b_misc.as<u32>() + 25; // (word 26 = heavy-scan count, behind n_seed_tasks)
 			rt_memset(P.n_intv, 0, (size_t)n_reads * 4);
+			// The scans with many candidates (a warp each: few, long-running warps) run on the auxiliary stream beside the
+			// lane-per-scan sweep of the others; both only append to per-read lists that round 3 orders afterwards.
+			const bool overlap = !getenv("B200_SEED_NO_OVERLAP");
 			RT_THREADS_QUEUE_SMEM(body_seedF1_q, P, (int64_t)n_reads, 0);
-			RT_WARPS_DEVN(wbody_seedB_heavy, P, P.n_seed_tasks + 2, (int64_t)n_reads); // scans with many candidates first: a warp each
+			if (overlap) rt_fork_aux();
+			RT_WARPS_DEVN(wbody_seedB_heavy, P, P.n_seed_tasks + 2, (int64_t)n_reads);
+			if (overlap) rt_back_to_main();
 			RT_THREADS_QUEUE_SMEM(body_seedB_q, P, (int64_t)P.seed_task_cap, 0);
+			if (overlap) rt_join_aux();
 			rt_memset(P.n_seed_tasks, 0, 4); rt_memset(P.n_seed_tasks + 2, 0, 4);
 			RT_THREADS_QUEUE_SMEM(body_seedF2_q, P, (int64_t)n_reads, 0);
+			if (overlap) rt_fork_aux();
 			RT_WARPS_DEVN(wbody_seedB_heavy, P, P.n_seed_tasks + 2, (int64_t)n_reads);
+			if (overlap) rt_back_to_main();
 			RT_THREADS_QUEUE_SMEM(body_seedB2_q, P, (int64_t)P.seed_task_cap, 0);
+			if (overlap) rt_join_aux();
 			RT_THREADS_QUEUE_SMEM(body_seed12_fb_q, P, (int64_t)n_reads, ssm); // (usually an empty list)
 			RT_THREADS_QUEUE_SMEM(body_seed3_q, P, (int64_t)n_reads, ssm);
 		}
@@ -446,8 +455,16 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 	if (!b_chainheavy.ensure(((size_t)n_reads + 1) * 4)) { last_error = "device allocation failed"; return nullptr; }
 	P.chain_heavy = b_chainheavy.as<u32>(); P.n_chain_heavy = b_misc.as<u32>() + 22;
 	P.chain_heavy_seeds = getenv("B200_TEST_CHAIN_ALL_WARP") ? -1 : (getenv("B200_TEST_CHAIN_ALL_THREAD") ? (1 << 30) : CHAIN_HEAVY_SEEDS);
-	RT_THREADS(body_chain, P, (int64_t)n_reads);
-	RT_WARPS_DEVN(wbody_chain_heavy, P, P.n_chain_heavy, (int64_t)n_reads);
+	if (getenv("B200_CHAIN_NO_OVERLAP")) { P.chain_listed = 0; RT_THREADS(body_chain, P, (int64_t)n_reads); RT_WARPS_DEVN(wbody_chain_heavy, P, P.n_chain_heavy, (int64_t)n_reads); }
+	else { // the warp-per-read kernel (few long-running warps) on the auxiliary stream beside the thread-per-read one
+		P.chain_listed = 1;
+		RT_THREADS(body_chain_classify, P, (int64_t)n_reads);
+		rt_fork_aux();
+		RT_WARPS_DEVN(wbody_chain_heavy, P, P.n_chain_heavy, (int64_t)n_reads);
+		rt_back_to_main();
+		RT_THREADS(body_chain, P, (int64_t)n_reads);
+		rt_join_aux();
+	}
 	// ---- warp scratch
 	{
 		const int L = max_len > 0 ? max_len : 1;

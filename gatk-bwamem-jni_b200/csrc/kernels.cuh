@@ -57,6 +57,7 @@ struct BatchParams {
 	int tx_chunk;                           // thread-level extension: cells of one DP row per visit of the row site
 	ExtTask* ext_tasks; u32* n_ext_tasks; ExtRes* ext_res; i64* ck_rmax; // heavy reads: per-seed extension tasks, results, per-chain windows
 	u32* chain_heavy; u32* n_chain_heavy; int chain_heavy_seeds; // reads chained by a warp
+	int chain_listed;       // the list of those reads was written beforehand (body_chain_classify): body_chain only skips them
 	GaTask* ga_tasks; GaRes* ga_res; u32* n_ga_tasks; u32 ga_cap; u32* ga_item0; u32* ga_itemn; // two-pass finalize (galign_thread.cuh)
 	int use_ext_res;        // wbody_extend consumes ext_res (set for the replay launch of the heavy reads only)
 	int t_ext_rw;           // thread-level extension: shared-memory words per thread (DP row, doubling as the two NW rings)
@@ -187,10 +188,15 @@ DEV void body_sal(const BatchParams& P, i64 t)
 
 // ---- chain: one thread per read ------------------------------------------------------------------
 #define CHAIN_HEAVY_SEEDS 64 // reads with more suffix-array hits than this are chained by a warp (chain.cuh chain_read_warp)
+// reads with many SA hits are chained by a warp each (wbody_chain_heavy); listing them first lets that kernel run beside body_chain
+DEV void body_chain_classify(const BatchParams& P, i64 r)
+{
+	if (P.seed_off[r + 1] - P.seed_off[r] > (u64)P.chain_heavy_seeds) { u32 slot = atomic_add_u32(P.n_chain_heavy, 1u); P.chain_heavy[slot] = (u32)r; }
+}
 DEV void body_chain(const BatchParams& P, i64 r)
 {
 	u64 t0 = P.seed_off[r];
-	if (P.seed_off[r + 1] - t0 > (u64)P.chain_heavy_seeds) { u32 slot = atomic_add_u32(P.n_chain_heavy, 1u); P.chain_heavy[slot] = (u32)r; return; }
+	if (P.seed_off[r + 1] - t0 > (u64)P.chain_heavy_seeds) { if (!P.chain_listed) { u32 slot = atomic_add_u32(P.n_chain_heavy, 1u); P.chain_heavy[slot] = (u32)r; } return; }
 	int len = (int)(P.seq_off[r + 1] - P.seq_off[r] - 1);
 	ChainStageIO io;
 	io.intv = P.intv + (size_t)r * P.intv_cap; io.n_intv = (int)P.n_intv[r];
