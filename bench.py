@@ -321,8 +321,13 @@ def main():
     # DP kernels in cell updates.  Kernels that split one stage (thread-level / task / warp variants) share its work.
     groups = {"seed": ["body_seed_q", "body_seed12_q", "body_seed3_q", "body_seedF1_q", "body_seedF2_q", "body_seedB_q", "body_seedB2_q", "wbody_seedB_heavy", "body_seed12_fb_q"],
               "sal": ["body_sal"], "chain": ["body_chain", "wbody_chain_heavy"],
-              "extend": ["body_extend_q", "wbody_heavy_prep", "body_extend_task_q", "wbody_extend_heavy", "wbody_extend"],
-              "rescue_sw": ["wbody_rescue_sw"], "finalize": ["body_final_pe_t", "wbody_final_pe_redo", "body_final_se_t", "wbody_final_se_redo"]}
+              "extend": ["body_extend_q", "body_extend_q8", "wbody_heavy_prep", "body_extend_task_q", "body_extend_task_q8", "wbody_extend_heavy", "wbody_extend"],
+              "rescue_sw": ["wbody_rescue_sw"],
+              "finalize": ["body_final_pe_t", "wbody_final_pe_redo", "body_final_se_t", "wbody_final_se_redo", "body_final_pe_collect", "body_final_se_collect",
+                           "body_galign_task_q", "body_final_pe_consume", "body_final_se_consume"]}
+    # kernels launched on the engine's auxiliary stream run beside a kernel of the same stage on the main stream: their entry
+    # in the stage table is only the part their neighbour did not cover (possibly 0), but their DRAM traffic counts in full
+    aux_kernels = {"seed": ["wbody_seedB_heavy"], "chain": ["wbody_chain_heavy"]}
     ms_of = {g: sum(t for nm, t in stages if nm in names) for g, names in groups.items()}
     kern = []
     tot_ms = sum(t for _, t in stages) or 1.0
@@ -371,7 +376,7 @@ def main():
                 pass
     try:  # DRAM bytes of the stage's launches from the committed ncu --set full captures of this very workload, if they exist
         prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        ents = [prof.get(k) for k in dom_kernels]
+        ents = [prof.get(k) for k in dom_kernels + [k for k in aux_kernels.get(dom_group, []) if k not in dom_kernels]]
         if all(e and e.get("pairs_per_step") == args.pairs and e.get("genome_bp") == int(args.genome_mbp * 1e6) for e in ents):
             roof["traffic"] = sum(e["dram_bytes_per_launch"] for e in ents)
             roof["traffic_source"] = sorted(set(e.get("source") for e in ents))

@@ -47,7 +47,6 @@ static void rt_fork_aux()
 	g_stream_override = g_aux_stream;
 }
 static void rt_back_to_main() { cudaEventRecord(g_ev_join, g_aux_stream); g_stream_override = nullptr; }
-static void rt_join_aux() { cudaStreamWaitEvent(rt_stream(), g_ev_join, 0); }
 static int rt_sm_count()
 {
 	if (!g_sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev); if (g_sm_count <= 0) g_sm_count = 148; }
@@ -243,6 +242,9 @@ struct StageTimer { // CUDA events on the launching stream around every stage of
 	}
 };
 static StageTimer g_timer;
+// the main stream waits for the auxiliary one; the stage table shows the wait (the part of the auxiliary kernel that its
+// neighbour did not cover) under the auxiliary kernel's name
+static void rt_join_aux(const char* nm) { cudaStreamWaitEvent(rt_stream(), g_ev_join, 0); g_timer.mark(nm); }
 static int g_launches = 0;
 
 #define RT_THREADS(body, P, n) do { i64 n_ = (i64)(n); if (n_ > 0) { \

@@ -426,14 +426,14 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 			RT_WARPS_DEVN(wbody_seedB_heavy, P, P.n_seed_tasks + 2, (int64_t)n_reads);
 			if (overlap) rt_back_to_main();
 			RT_THREADS_QUEUE_SMEM(body_seedB_q, P, (int64_t)P.seed_task_cap, 0);
-			if (overlap) rt_join_aux();
+			if (overlap) rt_join_aux("wbody_seedB_heavy");
 			rt_memset(P.n_seed_tasks, 0, 4); rt_memset(P.n_seed_tasks + 2, 0, 4);
 			RT_THREADS_QUEUE_SMEM(body_seedF2_q, P, (int64_t)n_reads, 0);
 			if (overlap) rt_fork_aux();
 			RT_WARPS_DEVN(wbody_seedB_heavy, P, P.n_seed_tasks + 2, (int64_t)n_reads);
 			if (overlap) rt_back_to_main();
 			RT_THREADS_QUEUE_SMEM(body_seedB2_q, P, (int64_t)P.seed_task_cap, 0);
-			if (overlap) rt_join_aux();
+			if (overlap) rt_join_aux("wbody_seedB_heavy");
 			RT_THREADS_QUEUE_SMEM(body_seed12_fb_q, P, (int64_t)n_reads, ssm); // (usually an empty list)
 			RT_THREADS_QUEUE_SMEM(body_seed3_q, P, (int64_t)n_reads, ssm);
 		}
@@ -463,7 +463,7 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 		RT_WARPS_DEVN(wbody_chain_heavy, P, P.n_chain_heavy, (int64_t)n_reads);
 		rt_back_to_main();
 		RT_THREADS(body_chain, P, (int64_t)n_reads);
-		rt_join_aux();
+		rt_join_aux("wbody_chain_heavy");
 	}
 	// ---- warp scratch
 	{

@@ -21,7 +21,7 @@ static void rt_memset(void* d, int v, size_t n) { memset(d, v, n); }
 static void rt_sync() {}
 static void rt_fork_aux() {}
 static void rt_back_to_main() {}
-static void rt_join_aux() {}
+static void rt_join_aux(const char*) {}
 static int64_t rt_thread_slots() { return 1; }
 static int64_t rt_warp_slots() { return 1; }
 static void rt_sort_u64(const uint64_t* in, uint64_t* out, uint64_t n) { memcpy(out, in, n * 8); std::sort(out, out + n); }
