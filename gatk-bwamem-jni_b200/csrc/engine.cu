@@ -40,7 +40,9 @@ static void rt_fork_aux()
 {
 	cudaStream_t main_s = rt_stream();
 	if (!g_aux_stream) {
-		cu_ok(cudaStreamCreateWithFlags(&g_aux_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+		int prio_low = 0, prio_high = 0; // highest priority: the few blocks of the auxiliary kernel are placed before the grid that fills the rest of the GPU
+		cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high);
+		cu_ok(cudaStreamCreateWithPriority(&g_aux_stream, cudaStreamNonBlocking, prio_high), "cudaStreamCreate");
 		cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&g_ev_join, cudaEventDisableTiming);
 	}
 	cudaEventRecord(g_ev_fork, main_s); cudaStreamWaitEvent(g_aux_stream, g_ev_fork, 0);
