@@ -389,6 +389,10 @@ class BwaMemIndex:
     def isOpen(self) -> bool:
         return self._addr is not None
 
+    def _addr_as_void(self):
+        """The native handle as a ctypes pointer (for the b200_* instrumentation calls, which take void*)."""
+        return ctypes.c_void_p(self._addr)
+
     def getReferenceContigNames(self) -> List[str]:
         return list(self._names)
 

@@ -10,6 +10,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <unistd.h>
+#include <atomic>
+#include <string>
+#include <vector>
 #include <cuda_runtime.h>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
@@ -18,48 +21,95 @@
 #include "simt.cuh"
 
 // ---- runtime vocabulary expected by engine_impl.inl ------------------------------------------------
+// Every createAlignments call runs inside a CONTEXT (RtCtx): its own streams, events, stage timer, launch counter and
+// scan scratch on one device.  A host thread binds a context for the duration of a call (rt_bind sets the CUDA device
+// of the thread -- the current device is per host thread -- and the thread-local pointer the rt_* helpers read), so
+// any number of Java threads may be inside the library at once, each on its own context, on any GPU of the pool.
+#define RT_MAX_DEV 16
 static thread_local cudaError_t g_last_cuda = cudaSuccess;
 static inline bool cu_ok(cudaError_t e, const char* what)
 {
 	if (e != cudaSuccess) { g_last_cuda = e; fprintf(stderr, "[bwamem-b200] CUDA error in %s: %s\n", what, cudaGetErrorString(e)); return false; }
 	return true;
 }
-static cudaStream_t g_stream = nullptr; // one stream per process (one process per GPU)
-static int g_sm_count = 0;
-// A second stream for a kernel that is independent of the next one on the main stream (a few long-running warps
-// beside a throughput kernel): rt_fork_aux() .. launches .. rt_back_to_main() .. launches .. rt_join_aux().
-static cudaStream_t g_aux_stream = nullptr, g_stream_override = nullptr;
-static cudaEvent_t g_ev_fork = nullptr, g_ev_join = nullptr;
-static cudaStream_t rt_stream()
+struct RtCtx {
+	int dev = 0, sm_count = 148;
+	cudaStream_t stream = nullptr;   // the context's main stream
+	// A second stream for a kernel that is independent of the next one on the main stream (a few long-running warps
+	// beside a throughput kernel): rt_fork_aux() .. launches .. rt_back_to_main() .. launches .. rt_join_aux().
+	cudaStream_t aux = nullptr, override_ = nullptr;
+	cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+	void* scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
+	unsigned* counters = nullptr; int counter_next = 0;
+	int launches = 0;
+	// CUDA events on the launching stream around every stage of the last batch
+	static const int MAXS = 512;
+	cudaEvent_t ev[MAXS + 1]; const char* name[MAXS]; int n_marks = 0; bool timer_init = false;
+	bool trace = false;
+};
+static thread_local RtCtx* t_rt = nullptr;
+static RtCtx* rt_ctx_create(int dev)
 {
-	if (g_stream_override) return g_stream_override;
-	if (!g_stream) { cu_ok(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking), "cudaStreamCreate"); }
-	return g_stream;
+	if (!cu_ok(cudaSetDevice(dev), "cudaSetDevice")) return nullptr;
+	RtCtx* c = new RtCtx();
+	c->dev = dev;
+	int prio_low = 0, prio_high = 0; // highest priority: the few blocks of the auxiliary kernel are placed before the grid that fills the rest of the GPU
+	bool ok = cu_ok(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute");
+	if (c->sm_count <= 0) c->sm_count = 148;
+	ok = ok && cu_ok(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high), "cudaDeviceGetStreamPriorityRange");
+	ok = ok && cu_ok(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+	ok = ok && cu_ok(cudaStreamCreateWithPriority(&c->aux, cudaStreamNonBlocking, prio_high), "cudaStreamCreate");
+	ok = ok && cu_ok(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming), "cudaEventCreate");
+	ok = ok && cu_ok(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming), "cudaEventCreate");
+	ok = ok && cu_ok(cudaMalloc(&c->counters, 64 * sizeof(unsigned)), "cudaMalloc");
+	for (int i = 0; ok && i <= RtCtx::MAXS; ++i) ok = cu_ok(cudaEventCreate(&c->ev[i]), "cudaEventCreate");
+	c->timer_init = ok;
+	c->trace = getenv("B200_TRACE") != nullptr; // development aid: synchronise and report after every stage
+	if (!ok) { delete c; return nullptr; } // (a device that cannot give a stream is unusable: nothing worth releasing piecemeal)
+	return c;
 }
+static void rt_ctx_destroy(RtCtx* c)
+{
+	if (!c) return;
+	cudaSetDevice(c->dev);
+	if (c->stream) cudaStreamDestroy(c->stream);
+	if (c->aux) cudaStreamDestroy(c->aux);
+	if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+	if (c->ev_join) cudaEventDestroy(c->ev_join);
+	if (c->scan_tmp) cudaFree(c->scan_tmp);
+	if (c->counters) cudaFree(c->counters);
+	if (c->timer_init) for (auto& e : c->ev) cudaEventDestroy(e);
+	if (t_rt == c) t_rt = nullptr;
+	delete c;
+}
+// bind the calling host thread to a context (and to its device) until the next rt_bind
+static bool rt_bind(RtCtx* c) { t_rt = c; return c ? cu_ok(cudaSetDevice(c->dev), "cudaSetDevice") : true; }
+static int rt_device_count() { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
+static int rt_current_device() { int d = 0; if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); return 0; } return d; }
+static cudaStream_t rt_stream() { return t_rt->override_ ? t_rt->override_ : t_rt->stream; }
 static void rt_fork_aux()
 {
-	cudaStream_t main_s = rt_stream();
-	if (!g_aux_stream) {
-		int prio_low = 0, prio_high = 0; // highest priority: the few blocks of the auxiliary kernel are placed before the grid that fills the rest of the GPU
-		cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high);
-		cu_ok(cudaStreamCreateWithPriority(&g_aux_stream, cudaStreamNonBlocking, prio_high), "cudaStreamCreate");
-		cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&g_ev_join, cudaEventDisableTiming);
-	}
-	cudaEventRecord(g_ev_fork, main_s); cudaStreamWaitEvent(g_aux_stream, g_ev_fork, 0);
-	g_stream_override = g_aux_stream;
+	cu_ok(cudaEventRecord(t_rt->ev_fork, t_rt->stream), "fork"); cu_ok(cudaStreamWaitEvent(t_rt->aux, t_rt->ev_fork, 0), "fork");
+	t_rt->override_ = t_rt->aux;
 }
-static void rt_back_to_main() { cudaEventRecord(g_ev_join, g_aux_stream); g_stream_override = nullptr; }
-static int rt_sm_count()
-{
-	if (!g_sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev); if (g_sm_count <= 0) g_sm_count = 148; }
-	return g_sm_count;
-}
+static void rt_back_to_main() { cu_ok(cudaEventRecord(t_rt->ev_join, t_rt->aux), "join"); t_rt->override_ = nullptr; }
+static int rt_sm_count() { return t_rt->sm_count; }
 static void* rt_malloc(size_t n) { void* p = nullptr; if (!cu_ok(cudaMalloc(&p, n ? n : 1), "cudaMalloc")) return nullptr; return p; }
 static void rt_free(void* p) { cudaFree(p); }
 static void rt_h2d(void* d, const void* s, size_t n) { if (n) cu_ok(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, rt_stream()), "h2d"); }
 static void rt_d2h(void* d, const void* s, size_t n) { if (n) { cu_ok(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, rt_stream()), "d2h"); cu_ok(cudaStreamSynchronize(rt_stream()), "d2h sync"); } }
 static void rt_memset(void* d, int v, size_t n) { cu_ok(cudaMemsetAsync(d, v, n, rt_stream()), "memset"); }
 static void rt_sync() { cu_ok(cudaStreamSynchronize(rt_stream()), "sync"); }
+// index replica k > 0 of a device pool: device-to-device over NVLink from the replica that took the host upload
+static bool rt_peer_copy(void* dst, int dst_dev, const void* src, int src_dev, size_t n)
+{
+	if (!n) return true;
+	return cu_ok(cudaMemcpyPeerAsync(dst, dst_dev, src, src_dev, n, rt_stream()), "peer copy");
+}
+// pinned host memory (staging of request / result bytes)
+static void* rt_host_alloc(size_t n) { void* p = nullptr; if (cudaHostAlloc(&p, n ? n : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; } return p; }
+static void rt_host_free(void* p) { if (p) cudaFreeHost(p); }
+static bool g_last_cuda_ok() { return g_last_cuda == cudaSuccess; }
 
 #define THREADS_PER_BLOCK 128
 #define WARPS_PER_BLOCK 4
@@ -75,17 +125,25 @@ static unsigned* g_ckpt_host = nullptr;
 #include "kernels.cuh"
 
 // exclusive scan of u32 counts into u64 offsets (out[n] = total); returns the total
-static void* g_scan_tmp = nullptr; static size_t g_scan_tmp_bytes = 0;
 struct U32ToU64 { __host__ __device__ u64 operator()(const u32& v) const { return (u64)v; } };
 __global__ void k_scan_close(const u32* in, u64* out, u64 n) { out[n] = n ? out[n - 1] + in[n - 1] : 0; }
+static bool rt_scratch(size_t need)
+{
+	if (need <= t_rt->scan_tmp_bytes) return true;
+	if (t_rt->scan_tmp) cudaFree(t_rt->scan_tmp);
+	t_rt->scan_tmp = nullptr; t_rt->scan_tmp_bytes = 0;
+	if (!cu_ok(cudaMalloc(&t_rt->scan_tmp, need + 1024), "cudaMalloc (scan scratch)")) return false;
+	t_rt->scan_tmp_bytes = need + 1024;
+	return true;
+}
 static uint64_t rt_scan_u32(const uint32_t* in, uint64_t* out, uint64_t n)
 {
 	if (n) {
 		cub::TransformInputIterator<u64, U32ToU64, const u32*> it(in, U32ToU64());
 		size_t need = 0;
-		cub::DeviceScan::ExclusiveSum(nullptr, need, it, out, (int64_t)n, rt_stream());
-		if (need > g_scan_tmp_bytes) { if (g_scan_tmp) cudaFree(g_scan_tmp); cudaMalloc(&g_scan_tmp, need + 1024); g_scan_tmp_bytes = need + 1024; }
-		cub::DeviceScan::ExclusiveSum(g_scan_tmp, need, it, out, (int64_t)n, rt_stream());
+		cu_ok(cub::DeviceScan::ExclusiveSum(nullptr, need, it, out, (int64_t)n, rt_stream()), "scan");
+		if (!rt_scratch(need)) return 0; // (g_last_cuda is set: the batch fails)
+		cu_ok(cub::DeviceScan::ExclusiveSum(t_rt->scan_tmp, need, it, out, (int64_t)n, rt_stream()), "scan");
 	}
 	k_scan_close<<<1, 1, 0, rt_stream()>>>(in, out, n);
 	uint64_t total = 0;
@@ -97,9 +155,18 @@ static void rt_sort_u64(const uint64_t* in, uint64_t* out, uint64_t n)
 {
 	if (!n) return;
 	size_t need = 0;
-	cub::DeviceRadixSort::SortKeys(nullptr, need, in, out, (int64_t)n, 0, 64, rt_stream());
-	if (need > g_scan_tmp_bytes) { if (g_scan_tmp) cudaFree(g_scan_tmp); cudaMalloc(&g_scan_tmp, need + 1024); g_scan_tmp_bytes = need + 1024; }
-	cub::DeviceRadixSort::SortKeys(g_scan_tmp, need, in, out, (int64_t)n, 0, 64, rt_stream());
+	cu_ok(cub::DeviceRadixSort::SortKeys(nullptr, need, in, out, (int64_t)n, 0, 64, rt_stream()), "sort");
+	if (!rt_scratch(need)) return;
+	cu_ok(cub::DeviceRadixSort::SortKeys(t_rt->scan_tmp, need, in, out, (int64_t)n, 0, 64, rt_stream()), "sort");
+}
+// order u32 payloads by u32 keys (stable); used to bucket work items so that the lanes of a warp get similar ones
+static void rt_sort_pairs_u32(const uint32_t* kin, uint32_t* kout, const uint32_t* vin, uint32_t* vout, uint64_t n, int end_bit)
+{
+	if (!n) return;
+	size_t need = 0;
+	cu_ok(cub::DeviceRadixSort::SortPairs(nullptr, need, kin, kout, vin, vout, (int64_t)n, 0, end_bit, rt_stream()), "sort pairs");
+	if (!rt_scratch(need)) return;
+	cu_ok(cub::DeviceRadixSort::SortPairs(t_rt->scan_tmp, need, kin, kout, vin, vout, (int64_t)n, 0, end_bit, rt_stream()), "sort pairs");
 }
 
 // ---- launchers ---------------------------------------------------------------------------------------
@@ -208,77 +275,76 @@ DEF_THREAD_QUEUE_KERNEL(body_galign_task_q)
 DEF_WARP_KERNEL_DEVN(wbody_final_pe_redo)
 DEF_WARP_KERNEL_DEVN(wbody_final_se_redo)
 
-static u32* g_counters = nullptr; static int g_counter_next = 0;
 static u32* next_counter()
 {
-	if (!g_counters) { cudaMalloc(&g_counters, 64 * sizeof(u32)); }
-	u32* c = g_counters + (g_counter_next++ & 63);
-	cudaMemsetAsync(c, 0, sizeof(u32), rt_stream());
+	u32* c = t_rt->counters + (t_rt->counter_next++ & 63);
+	cu_ok(cudaMemsetAsync(c, 0, sizeof(u32), rt_stream()), "memset");
 	return c;
 }
 
-struct StageTimer { // CUDA events on the launching stream around every stage of the last batch
-	static const int MAXS = 512;
-	cudaEvent_t ev[MAXS + 1]; const char* name[MAXS]; int n = 0; bool init = false;
-	void begin() {
+static void rt_timer_begin()
+{
 #ifdef B200_DEBUG_CKPT
-		if (!g_ckpt_host) { cudaHostAlloc(&g_ckpt_host, 1024, cudaHostAllocMapped); memset(g_ckpt_host, 0, 1024); unsigned* d = nullptr; cudaHostGetDevicePointer(&d, g_ckpt_host, 0); cudaMemcpyToSymbol(g_ckpt, &d, sizeof(d)); }
+	if (!g_ckpt_host) { cudaHostAlloc(&g_ckpt_host, 1024, cudaHostAllocMapped); memset(g_ckpt_host, 0, 1024); unsigned* d = nullptr; cudaHostGetDevicePointer(&d, g_ckpt_host, 0); cudaMemcpyToSymbol(g_ckpt, &d, sizeof(d)); }
 #endif
-		if (!init) { for (auto& e : ev) cudaEventCreate(&e); init = true; } n = 0; cudaEventRecord(ev[0], rt_stream()); }
-	void mark(const char* nm)
-	{
-		if (g_stream_override) return; // a kernel on the auxiliary stream: its time is inside the stages of the main stream it overlaps
-		if (n < MAXS) { name[n] = nm; ++n; cudaEventRecord(ev[n], rt_stream()); }
-		static const bool trace = getenv("B200_TRACE") != nullptr; // development aid: synchronise and report after every stage
-		if (trace) {
+	t_rt->n_marks = 0; t_rt->launches = 0;
+	cudaEventRecord(t_rt->ev[0], rt_stream());
+}
+static void rt_mark(const char* nm)
+{
+	RtCtx* c = t_rt;
+	if (c->override_) return; // a kernel on the auxiliary stream: its time is inside the stages of the main stream it overlaps
+	if (c->n_marks < RtCtx::MAXS) { c->name[c->n_marks] = nm; ++c->n_marks; cudaEventRecord(c->ev[c->n_marks], rt_stream()); }
+	if (c->trace) {
 #ifdef B200_DEBUG_CKPT
-			for (int t = 0; t < 100 && cudaStreamQuery(rt_stream()) == cudaErrorNotReady; ++t) usleep(100000);
-			if (cudaStreamQuery(rt_stream()) == cudaErrorNotReady) {
-				fprintf(stderr, "[bwamem-b200] stage %s HUNG; checkpoints (warp: code val):", nm);
-				for (int w = 0; w < 16; ++w) fprintf(stderr, " %d:%u/%u", w, g_ckpt_host[2 * w], g_ckpt_host[2 * w + 1]);
-				fprintf(stderr, "\n"); fflush(stderr); _exit(3);
-			}
-#endif
-			cudaError_t e = cudaStreamSynchronize(rt_stream()); fprintf(stderr, "[bwamem-b200] stage %s: %s\n", nm, cudaGetErrorString(e)); fflush(stderr);
+		for (int t = 0; t < 100 && cudaStreamQuery(rt_stream()) == cudaErrorNotReady; ++t) usleep(100000);
+		if (cudaStreamQuery(rt_stream()) == cudaErrorNotReady) {
+			fprintf(stderr, "[bwamem-b200] stage %s HUNG; checkpoints (warp: code val):", nm);
+			for (int w = 0; w < 16; ++w) fprintf(stderr, " %d:%u/%u", w, g_ckpt_host[2 * w], g_ckpt_host[2 * w + 1]);
+			fprintf(stderr, "\n"); fflush(stderr); _exit(3);
 		}
+#endif
+		cudaError_t e = cudaStreamSynchronize(rt_stream()); fprintf(stderr, "[bwamem-b200] stage %s: %s\n", nm, cudaGetErrorString(e)); fflush(stderr);
 	}
-};
-static StageTimer g_timer;
+}
 // the main stream waits for the auxiliary one; the stage table shows the wait (the part of the auxiliary kernel that its
 // neighbour did not cover) under the auxiliary kernel's name
-static void rt_join_aux(const char* nm) { cudaStreamWaitEvent(rt_stream(), g_ev_join, 0); g_timer.mark(nm); }
-static int g_launches = 0;
+static void rt_join_aux(const char* nm) { cu_ok(cudaStreamWaitEvent(rt_stream(), t_rt->ev_join, 0), "join"); rt_mark(nm); }
+static int rt_launches() { return t_rt ? t_rt->launches : 0; }
+// opt-in dynamic shared memory is a per-device function attribute: remembered per launch site and device
+#define RT_SET_SMEM(kern, bytes) do { static std::atomic<size_t> set_[RT_MAX_DEV]; const int d_ = t_rt->dev & (RT_MAX_DEV - 1); \
+	if ((bytes) > set_[d_].load(std::memory_order_relaxed)) { cu_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)), "cudaFuncSetAttribute"); set_[d_].store((bytes), std::memory_order_relaxed); } } while (0)
 
 #define RT_THREADS(body, P, n) do { i64 n_ = (i64)(n); if (n_ > 0) { \
 	i64 nb_ = (n_ + THREADS_PER_BLOCK - 1) / THREADS_PER_BLOCK; i64 cap_ = (i64)rt_sm_count() * 16; if (nb_ > cap_) nb_ = cap_; \
-	k_##body<<<(unsigned)nb_, THREADS_PER_BLOCK, 0, rt_stream()>>>(P, n_); ++g_launches; } g_timer.mark(#body); } while (0)
+	k_##body<<<(unsigned)nb_, THREADS_PER_BLOCK, 0, rt_stream()>>>(P, n_); ++t_rt->launches; } rt_mark(#body); } while (0)
 #define RT_THREADS_TID(body, P, n) do { i64 n_ = (i64)(n); if (n_ > 0) { \
 	i64 nb_ = (n_ + THREADS_PER_BLOCK - 1) / THREADS_PER_BLOCK; i64 cap_ = (i64)rt_sm_count() * SEED_BLOCKS_PER_SM; if (nb_ > cap_) nb_ = cap_; \
-	k_##body<<<(unsigned)nb_, THREADS_PER_BLOCK, 0, rt_stream()>>>(P, n_); ++g_launches; } g_timer.mark(#body); } while (0)
+	k_##body<<<(unsigned)nb_, THREADS_PER_BLOCK, 0, rt_stream()>>>(P, n_); ++t_rt->launches; } rt_mark(#body); } while (0)
 // thread kernels whose threads use the shared-memory rings (make_thread_ctx)
 #define RT_THREADS_TID_RING(body, P, n) do { i64 n_ = (i64)(n); if (n_ > 0) { \
 	i64 nb_ = (n_ + THREADS_PER_BLOCK - 1) / THREADS_PER_BLOCK; i64 cap_ = (i64)rt_sm_count() * SEED_BLOCKS_PER_SM; if (nb_ > cap_) nb_ = cap_; \
 	size_t tsm_ = thread_block_smem_bytes(THREADS_PER_BLOCK, (P).wm_cap); \
-	{ static size_t set_ = 0; if (tsm_ > set_) { cudaFuncSetAttribute(k_##body, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm_); set_ = tsm_; } } \
-	k_##body<<<(unsigned)nb_, THREADS_PER_BLOCK, tsm_, rt_stream()>>>(P, n_); ++g_launches; } g_timer.mark(#body); } while (0)
+	RT_SET_SMEM(k_##body, tsm_); \
+	k_##body<<<(unsigned)nb_, THREADS_PER_BLOCK, tsm_, rt_stream()>>>(P, n_); ++t_rt->launches; } rt_mark(#body); } while (0)
 // persistent queue kernels with an explicit dynamic shared-memory size (as many blocks per SM as that size allows)
 #define RT_THREADS_QUEUE_SMEM(body, P, n, bytes) do { i64 n_ = (i64)(n); if (n_ > 0) { \
 	size_t tsm_ = (bytes); \
 	i64 nb_ = (n_ + THREADS_PER_BLOCK - 1) / THREADS_PER_BLOCK; i64 per_sm_ = (i64)((227 * 1024) / (tsm_ + 1024)); if (per_sm_ < 1) per_sm_ = 1; if (per_sm_ > SEED_BLOCKS_PER_SM) per_sm_ = SEED_BLOCKS_PER_SM; \
 	i64 cap_ = (i64)rt_sm_count() * per_sm_; if (nb_ > cap_) nb_ = cap_; \
-	{ static size_t set_ = 0; if (tsm_ > set_) { cudaFuncSetAttribute(k_##body, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm_); set_ = tsm_; } } \
-	k_##body<<<(unsigned)nb_, THREADS_PER_BLOCK, tsm_, rt_stream()>>>(P, n_, next_counter()); ++g_launches; } g_timer.mark(#body); } while (0)
+	RT_SET_SMEM(k_##body, tsm_); \
+	k_##body<<<(unsigned)nb_, THREADS_PER_BLOCK, tsm_, rt_stream()>>>(P, n_, next_counter()); ++t_rt->launches; } rt_mark(#body); } while (0)
 #define RT_WARPS(wbody, P, n) do { i64 n_ = (i64)(n); if (n_ > 0) { \
 	size_t sm_ = ((warp_smem_bytes((P).wm_cap) + 15) & ~(size_t)15) * WARPS_PER_BLOCK; \
 	i64 nb_ = (n_ + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK; i64 cap_ = (i64)rt_sm_count() * WARP_BLOCKS_PER_SM; if (nb_ > cap_) nb_ = cap_; \
-	{ static size_t set_ = 0; if (sm_ > set_) { cudaFuncSetAttribute(k_##wbody, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_); set_ = sm_; } } \
-	k_##wbody<<<(unsigned)nb_, WARPS_PER_BLOCK * 32, sm_, rt_stream()>>>(P, n_, next_counter()); ++g_launches; } g_timer.mark(#wbody); } while (0)
+	RT_SET_SMEM(k_##wbody, sm_); \
+	k_##wbody<<<(unsigned)nb_, WARPS_PER_BLOCK * 32, sm_, rt_stream()>>>(P, n_, next_counter()); ++t_rt->launches; } rt_mark(#wbody); } while (0)
 
 #define RT_WARPS_DEVN(wbody, P, n_ptr, n_max) do { \
 	size_t sm_ = ((warp_smem_bytes((P).wm_cap) + 15) & ~(size_t)15) * WARPS_PER_BLOCK; \
 	i64 nb_ = (i64)rt_sm_count() * WARP_BLOCKS_PER_SM; \
-	{ static size_t set_ = 0; if (sm_ > set_) { cudaFuncSetAttribute(k_##wbody, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_); set_ = sm_; } } \
-	k_##wbody<<<(unsigned)nb_, WARPS_PER_BLOCK * 32, sm_, rt_stream()>>>(P, n_ptr, next_counter()); ++g_launches; g_timer.mark(#wbody); } while (0)
+	RT_SET_SMEM(k_##wbody, sm_); \
+	k_##wbody<<<(unsigned)nb_, WARPS_PER_BLOCK * 32, sm_, rt_stream()>>>(P, n_ptr, next_counter()); ++t_rt->launches; rt_mark(#wbody); } while (0)
 
 __global__ void k_relayout(const u32* src, u64 bwt_size, u32* dst, u64 n_blocks)
 {
@@ -293,88 +359,136 @@ __global__ void k_densify_sa(DevIndex x, u64 n_rows, u32 dense, u64* out)
 #define RT_DENSIFY(x, n_rows, dense, out) do { k_densify_sa<<<(unsigned)(rt_sm_count() * 16), 256, 0, rt_stream()>>>((x), (n_rows), (dense), (out)); cu_ok(cudaGetLastError(), "densify"); } while (0)
 #define RT_RELAYOUT(src, size, dst, nb) do { k_relayout<<<(unsigned)(rt_sm_count() * 16), 256, 0, rt_stream()>>>((src), (size), (dst), (nb)); cu_ok(cudaGetLastError(), "relayout"); } while (0)
 
-static void rt_timer_begin() { g_timer.begin(); g_launches = 0; }
 
 #include "engine_impl.inl"
 
 using namespace b200;
 
 // ---- C-ABI (include/bwamem_b200.h) ---------------------------------------------------------------------
+// Devices of a handle: BWA_B200_DEVICES = "all" or a comma-separated list of ordinals (an in-library pool: one index
+// replica per listed GPU, calls go to the least busy one); else BWA_B200_DEVICE = one ordinal; else the CUDA device
+// current on the opening thread (b200_setDevice / cudaSetDevice).  The Java API has no notion of a device.
+static bool devices_from_env(std::vector<int>& out, std::string& err)
+{
+	int ndev = rt_device_count();
+	if (ndev <= 0) { err = "no CUDA device: this engine has no CPU fallback"; return false; }
+	if (ndev > RT_MAX_DEV) ndev = RT_MAX_DEV;
+	const char* list = getenv("BWA_B200_DEVICES");
+	if (list && *list) {
+		if (strcmp(list, "all") == 0) { for (int d = 0; d < ndev; ++d) out.push_back(d); return true; }
+		for (const char* p = list; *p;) {
+			char* e = nullptr; long v = strtol(p, &e, 10);
+			if (e == p || v < 0 || v >= ndev) { err = std::string("BWA_B200_DEVICES=") + list + " names an unusable device"; return false; }
+			bool dup = false; for (int d : out) dup |= d == (int)v;
+			if (!dup) out.push_back((int)v);
+			p = *e == ',' ? e + 1 : e;
+			if (*e && *e != ',') { err = std::string("BWA_B200_DEVICES=") + list + " is malformed"; return false; }
+		}
+		return !out.empty();
+	}
+	if (const char* dv = getenv("BWA_B200_DEVICE")) {
+		const int v = atoi(dv);
+		if (v < 0 || v >= ndev) { err = std::string("BWA_B200_DEVICE=") + dv + " is not a usable device"; return false; }
+		out.push_back(v);
+		return true;
+	}
+	out.push_back(rt_current_device());
+	return true;
+}
+
 extern "C" {
 
 void* jnibwa_openIndex(int fd)
 {
-	int ndev = 0;
-	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
-		fprintf(stderr, "[bwamem-b200] no CUDA device: this engine has no CPU fallback\n");
+	std::vector<int> devs; std::string err;
+	if (!devices_from_env(devs, err)) {
+		fprintf(stderr, "[bwamem-b200] %s\n", err.c_str());
 		if (fd >= 0) close(fd);
 		return nullptr;
 	}
-	if (const char* dv = getenv("BWA_B200_DEVICE")) { // the Java API has no notion of a device
-		if (cudaSetDevice(atoi(dv)) != cudaSuccess) { fprintf(stderr, "[bwamem-b200] BWA_B200_DEVICE=%s is not a usable device\n", dv); if (fd >= 0) close(fd); return nullptr; }
-	}
-	std::lock_guard<std::mutex> lock(Engine::device_mutex());
+	const int dev0 = rt_current_device(); // the caller's own current device is left as it was
+	g_last_cuda = cudaSuccess;
 	Engine* e = new Engine();
-	if (!e->open_from_fd(fd)) { fprintf(stderr, "[bwamem-b200] openIndex: %s\n", e->last_error.c_str()); e->close_all(); delete e; return nullptr; }
+	const bool ok = e->open_from_fd(fd, devs);
+	if (!ok) { fprintf(stderr, "[bwamem-b200] openIndex: %s\n", e->last_error.c_str()); e->close_all(); delete e; e = nullptr; }
+	cudaSetDevice(dev0);
 	return e;
 }
 
 int jnibwa_destroyIndex(void* h)
 {
 	if (!h) return 0;
-	std::lock_guard<std::mutex> lock(Engine::device_mutex());
 	Engine* e = (Engine*)h;
-	e->close_all();
+	const int dev0 = rt_current_device();
+	e->close_all(); // (Java serialises close() and refuses it while aligners are alive: BwaMemIndex.java:383-397)
 	delete e;
+	cudaSetDevice(dev0);
 	return 0;
 }
 
 void* jnibwa_getRefContigNames(void* h, size_t* size) { return h ? contig_names_blob(((Engine*)h)->img, size) : nullptr; }
 
+// Re-entrant: every call borrows one of the handle's contexts (its own device binding, streams and workspace), so
+// threads overlap up to the number of contexts and queue beyond it.
 void* jnibwa_createAlignments(void* h, void* opt, void* pes, char* seqs, size_t* size)
 {
 	if (!h || !opt || !seqs || !size) return nullptr;
 	Engine* e = (Engine*)h;
+	Batch* b = e->acquire();
+	if (!b) return nullptr;
 	g_last_cuda = cudaSuccess;
-	void* r = e->align((const MemOpt*)opt, (const PeStat*)pes, seqs, size);
-	e->n_launches = g_launches;
-	if (r && (g_last_cuda != cudaSuccess || cudaGetLastError() != cudaSuccess)) { free(r); r = nullptr; e->last_error = "CUDA error during the batch"; }
-	if (!r) fprintf(stderr, "[bwamem-b200] createAlignments: %s\n", e->last_error.c_str());
+	void* r = b->align((const MemOpt*)opt, (const PeStat*)pes, seqs, size);
+	if (r && (g_last_cuda != cudaSuccess || cudaGetLastError() != cudaSuccess)) { free(r); r = nullptr; b->last_error = "CUDA error during the batch"; }
+	if (!r) fprintf(stderr, "[bwamem-b200] createAlignments: %s\n", b->last_error.c_str());
+	e->release(b);
 	return r;
 }
 
 void* mem_opt_init(void) { return default_options(); }
 void jnibwa_free(void* p) { free(p); }
-const char* jnibwa_getVersion(void) { return "bwamem-b200 0.1 (sm_100a; bwa-mem semantics of lh3/bwa cb95061)"; }
+const char* jnibwa_getVersion(void) { return "bwamem-b200 0.2 (sm_100a; bwa-mem semantics of lh3/bwa cb95061)"; }
 
 // ---- instrumentation for bench.py ------------------------------------------------------------------
 // HBM-resident measurement: stage a request (host parse + upload, untimed by the caller), then run the device
-// pipeline on it leaving the record stream in device memory.  Returns the stream's byte size, or -1.
+// pipeline on it leaving the record stream in device memory.  Both use context 0 of the handle (the first device of
+// its pool).  alignStaged returns the stream's byte size, or -1.
 int b200_stageBatch(void* h, const char* seqs)
 {
 	Engine* e = (Engine*)h;
-	std::lock_guard<std::mutex> lock(Engine::device_mutex());
-	return e->stage(seqs) ? 0 : 1;
+	if (!e || e->ctxs.empty()) return 1;
+	Batch* b = e->acquire(e->ctxs[0]);
+	g_last_cuda = cudaSuccess;
+	const bool ok = b->stage(seqs) && g_last_cuda == cudaSuccess;
+	e->release(b);
+	return ok ? 0 : 1;
 }
 long long b200_alignStaged(void* h, void* opt, void* pes)
 {
 	Engine* e = (Engine*)h;
-	std::lock_guard<std::mutex> lock(Engine::device_mutex());
+	if (!e || e->ctxs.empty()) return -1;
+	Batch* b = e->acquire(e->ctxs[0]);
 	size_t size = 0;
 	g_last_cuda = cudaSuccess;
-	void* r = e->run((const MemOpt*)opt, (const PeStat*)pes, &size, false);
-	e->n_launches = g_launches;
-	if (!r || g_last_cuda != cudaSuccess) { fprintf(stderr, "[bwamem-b200] alignStaged: %s\n", e->last_error.c_str()); return -1; }
-	return (long long)size;
+	void* r = b->run((const MemOpt*)opt, (const PeStat*)pes, &size, false);
+	const bool ok = r && g_last_cuda == cudaSuccess;
+	if (!ok) fprintf(stderr, "[bwamem-b200] alignStaged: %s\n", b->last_error.c_str());
+	e->release(b);
+	return ok ? (long long)size : -1;
 }
-// device time of the last batch: first to last stage event on the engine's stream (ms)
+// device time of the last batch of context 0: first to last stage event on its stream (ms)
 float b200_lastBatchMs(void* h)
 {
-	(void)h; float t = 0;
-	if (g_timer.n > 0) cudaEventElapsedTime(&t, g_timer.ev[0], g_timer.ev[g_timer.n]);
+	Engine* e = (Engine*)h; float t = 0;
+	if (!e || e->ctxs.empty()) return 0;
+	RtCtx* c = e->ctxs[0]->rt;
+	cudaSetDevice(c->dev);
+	if (c->n_marks > 0) cudaEventElapsedTime(&t, c->ev[0], c->ev[c->n_marks]);
 	return t;
 }
 int b200_setDevice(int dev) { return cudaSetDevice(dev) == cudaSuccess ? 0 : 1; }
+// contexts of a handle (devices x batches in flight per device) and the device of context i
+int b200_contextCount(void* h) { return h ? (int)((Engine*)h)->ctxs.size() : 0; }
+int b200_contextDevice(void* h, int i) { Engine* e = (Engine*)h; return e && i >= 0 && i < (int)e->ctxs.size() ? e->ctxs[(size_t)i]->rep->dev : -1; }
 // test hook (tests/test_smem_layout.py): where thread `tid` of a block of `threads` keeps its DP row, read codes and
 // patching rings in the dynamic shared memory of the thread-level extension kernels.
 // out = { row offset, row element stride (bytes), query offset, query stride, ringH offset, ringE offset, ring stride, ring slots, block bytes }
@@ -386,24 +500,28 @@ void b200_extLayout(int threads, int tid, int rw, int wm_cap, int cell, int patc
 	out[8] = thread_ext_smem_bytes(threads, rw, wm_cap, cell);
 }
 const char* b200_lastError(void* h) { return h ? ((Engine*)h)->last_error.c_str() : ""; }
-// copies up to cap stage times (ms) of the last batch; names[i] points at static strings; returns the stage count
+// copies up to cap stage times (ms) of the last batch of context 0; names[i] points at static strings; returns the stage count
 int b200_lastStageTimes(void* h, float* ms, const char** names, int cap)
 {
-	(void)h;
+	Engine* e = (Engine*)h;
+	if (!e || e->ctxs.empty()) return 0;
+	RtCtx* c = e->ctxs[0]->rt;
+	cudaSetDevice(c->dev);
 	int n = 0; // aggregated by stage name, in order of first appearance
-	for (int i = 0; i < g_timer.n; ++i) {
-		float t = 0; cudaEventElapsedTime(&t, g_timer.ev[i], g_timer.ev[i + 1]);
+	for (int i = 0; i < c->n_marks; ++i) {
+		float t = 0; cudaEventElapsedTime(&t, c->ev[i], c->ev[i + 1]);
 		int j = 0;
-		for (; j < n; ++j) if (strcmp(names[j], g_timer.name[i]) == 0) break;
-		if (j == n) { if (n >= cap) continue; names[n] = g_timer.name[i]; ms[n] = 0; ++n; }
+		for (; j < n; ++j) if (strcmp(names[j], c->name[i]) == 0) break;
+		if (j == n) { if (n >= cap) continue; names[n] = c->name[i]; ms[n] = 0; ++n; }
 		ms[j] += t;
 	}
 	return n;
 }
-// counters: cells_ext, cells_glb, cells_msw, n_ext, n_glb, n_msw, n_seed_lookups, n_launches
+// counters of the most recent call on the handle: cells_ext, cells_glb, cells_msw, n_ext, n_glb, n_msw, n_seed_lookups, n_launches
 void b200_lastCounters(void* h, uint64_t* out)
 {
 	Engine* e = (Engine*)h;
+	std::lock_guard<std::mutex> lock(e->mu);
 	memcpy(out, &e->last_counters, sizeof(Counters));
 	out[6] = e->last_n_seed;
 	out[7] = (uint64_t)e->n_launches;

@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <atomic>
 #include <mutex>
+#include <condition_variable>
 #include <thread>
 #include <string>
 #include <vector>
@@ -64,14 +65,48 @@ bool ImageView::parse(const uint8_t* m, size_t l)
 
 // development aid (B200_HOSTPROF=1): wall-clock marks of the host side of one call, printed to stderr
 struct HostProf {
-	bool on = getenv("B200_HOSTPROF") != nullptr;
+	bool on = false;
 	std::vector<std::pair<const char*, double>> marks; double t0 = 0;
 	static double now() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
 	void begin() { if (on) { marks.clear(); t0 = now(); } }
 	void mark(const char* nm) { if (on) marks.push_back({ nm, now() }); }
 	void report() { if (!on) return; double p = t0; fprintf(stderr, "[hostprof]"); for (auto& m : marks) { fprintf(stderr, " %s=%.2f", m.first, m.second - p); p = m.second; } fprintf(stderr, " total=%.2f ms\n", p - t0); }
 };
-static HostProf g_hp;
+
+// Everything the environment can say about a handle, read ONCE by jnibwa_openIndex (never per batch).  The BWA_B200_*
+// variables are the deployment knobs of INTEGRATION.md; B200_HOSTPROF / B200_DEBUG_STATS are reporting aids.  The
+// remaining B200_* variables force kernel variants and capacity limits for the parity tests and for tuning runs: they
+// change which kernels a call launches, so they are honoured only when B200_TEST_HOOKS=1 is set as well.
+struct EngineConfig {
+	int sa_intv = 8;             // BWA_B200_SA_INTV
+	int contexts = 2;            // BWA_B200_CONTEXTS: batches in flight per device
+	bool hostprof = false, debug_stats = false;
+	// ---- test hooks / tuning aids (B200_TEST_HOOKS=1)
+	bool no_stage_overlap = false, seed_one_launch = false, seed_fused_rounds = false, tiny_seed_pool = false, tiny_seed_tasks = false, seed_no_overlap = false;
+	bool chain_all_warp = false, chain_all_thread = false, chain_no_overlap = false, tiny_scratch = false, all_heavy = false, all_light = false;
+	bool warp_extend = false, ext_wide_cells = false, no_ext_tasks = false, rescue_fallback = false, final_one_pass = false, final_ring = false, tiny_ga_cap = false;
+	bool ext_legacy = false, ext_no_sort = false;
+	int seed_lcap = 0, seed_shared_read = -1, tx_chunk = -1, light_seeds = -1, light_chains = -1;
+	static bool flag(const char* nm) { return getenv(nm) != nullptr; }
+	static int num(const char* nm, int dflt) { const char* e = getenv(nm); return e ? atoi(e) : dflt; }
+	void read_env()
+	{
+		sa_intv = num("BWA_B200_SA_INTV", sa_intv);
+		contexts = num("BWA_B200_CONTEXTS", contexts); if (contexts < 1) contexts = 1; if (contexts > 8) contexts = 8;
+		hostprof = flag("B200_HOSTPROF"); debug_stats = flag("B200_DEBUG_STATS");
+		const char* th = getenv("B200_TEST_HOOKS");
+		if (!th || atoi(th) == 0) return;
+		no_stage_overlap = flag("B200_NO_STAGE_OVERLAP"); seed_one_launch = flag("B200_SEED_ONE_LAUNCH"); seed_fused_rounds = flag("B200_SEED_FUSED_ROUNDS");
+		tiny_seed_pool = flag("B200_TEST_TINY_SEED_POOL"); tiny_seed_tasks = flag("B200_TEST_TINY_SEED_TASKS"); seed_no_overlap = flag("B200_SEED_NO_OVERLAP");
+		chain_all_warp = flag("B200_TEST_CHAIN_ALL_WARP"); chain_all_thread = flag("B200_TEST_CHAIN_ALL_THREAD"); chain_no_overlap = flag("B200_CHAIN_NO_OVERLAP");
+		tiny_scratch = flag("B200_TEST_TINY_SCRATCH"); all_heavy = flag("B200_TEST_ALL_HEAVY"); all_light = flag("B200_TEST_ALL_LIGHT");
+		warp_extend = flag("B200_WARP_EXTEND"); ext_wide_cells = flag("B200_EXT_WIDE_CELLS"); no_ext_tasks = flag("B200_NO_EXT_TASKS");
+		rescue_fallback = flag("B200_TEST_RESCUE_FALLBACK"); final_one_pass = flag("B200_FINAL_ONE_PASS"); final_ring = flag("B200_TEST_FINAL_RING");
+		tiny_ga_cap = flag("B200_TEST_TINY_GA_CAP"); ext_legacy = flag("B200_EXT_LEGACY"); ext_no_sort = flag("B200_EXT_NO_SORT");
+		seed_lcap = num("B200_SEED_LCAP", 0); seed_shared_read = num("B200_SEED_SHARED_READ", -1); tx_chunk = num("B200_TX_CHUNK", -1);
+		light_seeds = num("B200_LIGHT_SEEDS", -1); light_chains = num("B200_LIGHT_CHAINS", -1);
+	}
+};
 
 struct DBuf { // growable device buffer
 	void* p = nullptr; size_t cap = 0;
@@ -121,36 +156,103 @@ inline void* contig_names_blob(const ImageView& img, size_t* size)
 	return buf;
 }
 
+struct Engine;
+// The index resident in the HBM of ONE device (uploaded once by jnibwa_openIndex; read-only afterwards, shared by every
+// context of that device).
+struct Replica {
+	int dev = 0;
+	DevIndex dx;
+	DBuf d_bwt, d_sa, d_sa_dense, d_pac, d_ctg, d_log, d_names, d_name_off;
+	int busy = 0; // contexts of this device inside a call (guarded by Engine::mu)
+	void release_all() { DBuf* all[] = { &d_bwt, &d_sa, &d_sa_dense, &d_pac, &d_ctg, &d_log, &d_names, &d_name_off }; for (DBuf* b : all) b->release(); }
+};
+
+// One batch in flight: a runtime context (streams, events, timer: engine.cu RtCtx) on one device, the grow-only batch
+// workspace in that device's HBM, the pinned staging of the request and the staged request itself.  A createAlignments
+// call borrows a Batch for its whole duration; callers on different Batches overlap freely (stage of call N+1 beside
+// the kernels of call N beside the result copy of call N-1), which is the reference's threading contract: one
+// BwaMemIndex shared by any number of threads, each with its own BwaMemAligner (BwaMemAligner.java:18, BwaMemIndex.java:18,26-27).
+struct Batch {
+	Engine* eng = nullptr; Replica* rep = nullptr; RtCtx* rt = nullptr;
+	bool in_use = false; // guarded by Engine::mu
+	HostProf hp;
+	// batch workspace
+	DBuf b_blob, b_seq, b_seqoff, b_intv, b_nintv, b_nseed, b_smem, b_seedoff, b_rbeg, b_S, b_C, b_ord, b_tmp32, b_ck, b_ks, b_srt, b_regtmp,
+	     b_nck, b_nks, b_nreg, b_regcap, b_regoff, b_regs, b_snap, b_ztmp, b_pairv, b_recs, b_nrec, b_cand, b_pairtab, b_var, b_misc,
+	     b_outwords, b_outoff, b_out, b_wsz, b_wscig, b_wsmd, b_wsxa, b_wsbrow, b_nb, b_swtask, b_swstate, b_swlist, b_tbuf, b_redo, b_heavy, b_multi, b_cand2, b_specstate, b_spectask, b_nreg0, b_rsheavy, b_wsrt, b_wsrkey, b_wsrrank, b_exttask, b_extres, b_ckrmax, b_chainheavy, b_gatask, b_gares, b_gaitem0, b_gaitemn, b_seedpool, b_seedused, b_seedtask, b_seedfb,
+	     b_xtkey, b_xtkey2, b_xtidx, b_xtidx2;
+	Counters last_counters; uint64_t last_n_seed = 0; int n_launches = 0;
+	std::string last_error;
+	// staged request
+	bool st_valid = false; uint32_t st_n_reads = 0; int st_max_len = 0; uint64_t st_blob_len = 0; std::vector<uint64_t> st_seq_off;
+#ifndef B200_SIM
+	enum { NUP = 4 };
+	cudaStream_t up_stream[NUP] = { nullptr, nullptr, nullptr, nullptr };
+	cudaEvent_t up_done[NUP] = { nullptr, nullptr, nullptr, nullptr };
+	char* pin = nullptr; uint64_t pin_cap = 0; // pinned staging of the request bytes, grow-only like the device buffer
+#endif
+	bool stage(const char* blob, bool wait = true);
+	void* run(const MemOpt* opt, const PeStat* pes0, size_t* out_size, bool host_output);
+	void* align(const MemOpt* opt, const PeStat* pes0, char* blob, size_t* out_size);
+	void release_all();
+};
+
 struct Engine {
 	// host view of the image
 	void* map = nullptr; size_t map_len = 0;
 	ImageView img;
-	// device-resident index
-	DevIndex dx;
-	DBuf d_bwt, d_sa, d_sa_dense, d_pac, d_ctg, d_log, d_names, d_name_off;
-	// One batch at a time per PROCESS (= per GPU): the stream, the stage timer and the scan scratch of the runtime binding
-	// are process-wide, so callers are serialised across index handles too (BwaMemIndex objects may be shared by any
-	// number of threads, each with its own BwaMemAligner: BwaMemAligner.java:18, BwaMemIndex.java:18).
-	static std::mutex& device_mutex() { static std::mutex m; return m; }
-	// batch workspace
-	DBuf b_blob, b_seq, b_seqoff, b_intv, b_nintv, b_nseed, b_smem, b_seedoff, b_rbeg, b_S, b_C, b_ord, b_tmp32, b_ck, b_ks, b_srt, b_regtmp,
-	     b_nck, b_nks, b_nreg, b_regcap, b_regoff, b_regs, b_snap, b_ztmp, b_pairv, b_recs, b_nrec, b_cand, b_pairtab, b_var, b_misc,
-	     b_outwords, b_outoff, b_out, b_wsz, b_wscig, b_wsmd, b_wsxa, b_wsbrow, b_nb, b_swtask, b_swstate, b_swlist, b_tbuf, b_redo, b_heavy, b_multi, b_cand2, b_specstate, b_spectask, b_nreg0, b_rsheavy, b_wsrt, b_wsrkey, b_wsrrank, b_exttask, b_extres, b_ckrmax, b_chainheavy, b_gatask, b_gares, b_gaitem0, b_gaitemn, b_seedpool, b_seedused, b_seedtask, b_seedfb;
-	Counters last_counters; uint64_t last_n_seed = 0; int n_launches = 0;
-	std::string last_error;
+	EngineConfig cfg;
+	std::vector<Replica*> reps;   // one per device of the pool (BWA_B200_DEVICES; default: the opening thread's device)
+	std::vector<Batch*> ctxs;     // cfg.contexts per replica
+	std::mutex mu; std::condition_variable cv;
+	std::string last_error;       // of the most recent failed call on this handle
+	Counters last_counters; uint64_t last_n_seed = 0; int n_launches = 0; // of the most recent call (instrumentation)
+	Batch* last_batch = nullptr;
 
-	bool open_from_fd(int fd);
-	bool upload();
+	bool open_from_fd(int fd, const std::vector<int>& devices);
+	bool open_from_fd(int fd) { return open_from_fd(fd, std::vector<int>(1, rt_current_device())); }
+	bool upload(Replica& r, const Replica* from);
 	void close_all();
-	// staged request
-	bool st_valid = false; uint32_t st_n_reads = 0; int st_max_len = 0; uint64_t st_blob_len = 0; std::vector<uint64_t> st_seq_off;
-	bool stage(const char* blob, bool wait = true);
-	void* run(const MemOpt* opt, const PeStat* pes0, size_t* out_size, bool host_output);
+	// borrow the idle context of the least busy device (blocks while all are busy); `want` pins a particular one
+	Batch* acquire(Batch* want = nullptr);
+	void release(Batch* b);
 	void* align(const MemOpt* opt, const PeStat* pes0, char* blob, size_t* out_size);
 };
 
-inline bool Engine::open_from_fd(int fd)
+inline Batch* Engine::acquire(Batch* want)
 {
+	std::unique_lock<std::mutex> lock(mu);
+	for (;;) {
+		Batch* best = nullptr;
+		if (want) { if (!want->in_use) best = want; }
+		else for (Batch* b : ctxs) if (!b->in_use && (!best || b->rep->busy < best->rep->busy)) best = b;
+		if (best) { best->in_use = true; ++best->rep->busy; rt_bind(best->rt); return best; }
+		if (ctxs.empty()) return nullptr;
+		cv.wait(lock);
+	}
+}
+inline void Engine::release(Batch* b)
+{
+	{
+		std::lock_guard<std::mutex> lock(mu);
+		if (!b->last_error.empty()) last_error = b->last_error;
+		last_counters = b->last_counters; last_n_seed = b->last_n_seed; n_launches = b->n_launches; last_batch = b;
+		b->in_use = false; --b->rep->busy;
+	}
+	cv.notify_one();
+}
+inline void* Engine::align(const MemOpt* opt, const PeStat* pes0, char* blob, size_t* out_size)
+{
+	Batch* b = acquire();
+	if (!b) { last_error = "index handle has no device context"; return nullptr; }
+	void* r = b->align(opt, pes0, blob, out_size);
+	release(b);
+	return r;
+}
+
+inline bool Engine::open_from_fd(int fd, const std::vector<int>& devices)
+{
+	cfg.read_env();
 	struct stat st;
 	if (fstat(fd, &st) == -1) { close(fd); return false; }
 	void* m = mmap(0, st.st_size, PROT_READ, MAP_SHARED, fd, 0);
@@ -158,51 +260,88 @@ inline bool Engine::open_from_fd(int fd)
 	if (m == MAP_FAILED) return false;
 	map = m; map_len = (size_t)st.st_size;
 	if (!img.parse((const uint8_t*)map, map_len)) { last_error = "malformed index image"; return false; }
-	for (auto& c : img.contigs) if (c.is_alt) { last_error = "ALT contigs are not supported by this engine"; return false; }
 	if (img.sa_intv <= 0 || (img.sa_intv & (img.sa_intv - 1))) { last_error = "SA interval must be a power of two"; return false; }
-	return upload();
+	for (auto& c : img.contigs) if (c.is_alt) { last_error = "ALT contigs are not supported by this engine"; return false; }
+	if (devices.empty()) { last_error = "no device"; return false; }
+	for (size_t k = 0; k < devices.size(); ++k) {
+		Replica* r = new Replica(); r->dev = devices[k];
+		reps.push_back(r);
+		for (int c = 0; c < cfg.contexts; ++c) {
+			RtCtx* rt = rt_ctx_create(r->dev);
+			if (!rt) { last_error = "cannot create a device context"; return false; }
+			Batch* b = new Batch(); b->eng = this; b->rep = r; b->rt = rt; b->hp.on = cfg.hostprof;
+			ctxs.push_back(b);
+		}
+		rt_bind(ctxs[k * (size_t)cfg.contexts]->rt);
+		if (!upload(*r, k ? reps[0] : nullptr)) return false;
+	}
+	return true;
 }
 
-inline bool Engine::upload()
+// Replica 0 takes the image from the host (and re-lays it out on the device); the others copy the finished arrays
+// device to device (NVLink), so a pool of N GPUs costs one host upload.
+inline bool Engine::upload(Replica& R, const Replica* from)
 {
+	DBuf& d_bwt = R.d_bwt; DBuf& d_sa = R.d_sa; DBuf& d_sa_dense = R.d_sa_dense; DBuf& d_pac = R.d_pac; DBuf& d_ctg = R.d_ctg; DBuf& d_log = R.d_log;
+	DBuf& d_names = R.d_names; DBuf& d_name_off = R.d_name_off; DevIndex& dx = R.dx;
 	size_t bwt_bytes = (size_t)img.bwt_size * 4;
 	const uint64_t n_blocks = (img.seq_len + 127) / 128;
-	{ // the occ-interleaved BWT goes up as it is in the image, then every 64-byte block is re-laid out for the device
-	  // (symbols as two bit-planes, fm.cuh); the staging copy is released
-		DBuf raw;
-		if (!raw.ensure(bwt_bytes + 64) || !d_bwt.ensure((size_t)n_blocks * 64 + 64)) { raw.release(); last_error = "device allocation failed"; return false; }
-		rt_h2d(raw.p, img.bwt, bwt_bytes);
-		RT_RELAYOUT((const u32*)raw.p, (u64)img.bwt_size, (u32*)d_bwt.p, n_blocks);
-		rt_sync();
-		raw.release();
+	const size_t pac_bytes = (size_t)(img.l_pac / 4 + 1);
+	if (from) {
+		const bool dense = from->d_sa_dense.p != nullptr;
+		const size_t sa_bytes = dense ? from->d_sa_dense.cap : (size_t)img.n_sa * 8;
+		bool ok = d_bwt.ensure((size_t)n_blocks * 64 + 64) && (dense ? d_sa_dense : d_sa).ensure(sa_bytes) && d_pac.ensure(pac_bytes + 16);
+		if (!ok) { last_error = "device allocation failed"; return false; }
+		ok = rt_peer_copy(d_bwt.p, R.dev, from->d_bwt.p, from->dev, (size_t)n_blocks * 64)
+		     && rt_peer_copy((dense ? d_sa_dense : d_sa).p, R.dev, (dense ? from->d_sa_dense : from->d_sa).p, from->dev, dense ? (size_t)((img.seq_len + 1 + from->dx.sa_intv - 1) / from->dx.sa_intv) * 8 : sa_bytes)
+		     && rt_peer_copy(d_pac.p, R.dev, from->d_pac.p, from->dev, pac_bytes);
+		if (!ok) { last_error = "peer copy of the index failed"; return false; }
+	} else {
+		{ // the occ-interleaved BWT goes up as it is in the image, then every 64-byte block is re-laid out for the device
+		  // (symbols as two bit-planes, fm.cuh); the staging copy is released
+			DBuf raw;
+			if (!raw.ensure(bwt_bytes + 64) || !d_bwt.ensure((size_t)n_blocks * 64 + 64)) { raw.release(); last_error = "device allocation failed"; return false; }
+			rt_h2d(raw.p, img.bwt, bwt_bytes);
+			RT_RELAYOUT((const u32*)raw.p, (u64)img.bwt_size, (u32*)d_bwt.p, n_blocks);
+			rt_sync();
+			raw.release();
+		}
+		if (!d_sa.ensure((size_t)img.n_sa * 8) || !d_pac.ensure(pac_bytes + 16)) { last_error = "device allocation failed"; return false; }
+		rt_h2d(d_sa.p, img.sa, (size_t)img.n_sa * 8);
+		rt_h2d(d_pac.p, img.pac, pac_bytes);
 	}
-	if (!d_sa.ensure((size_t)img.n_sa * 8) || !d_pac.ensure((size_t)(img.l_pac / 4 + 1) + 16)) { last_error = "device allocation failed"; return false; }
-	rt_h2d(d_sa.p, img.sa, (size_t)img.n_sa * 8);
-	rt_h2d(d_pac.p, img.pac, (size_t)(img.l_pac / 4 + 1));
 	std::vector<int64_t> off((size_t)img.n_seqs + 1);
 	for (int i = 0; i < img.n_seqs; ++i) off[i] = img.contigs[i].offset;
 	off[img.n_seqs] = img.l_pac;
-	d_ctg.ensure(off.size() * 8); rt_h2d(d_ctg.p, off.data(), off.size() * 8);
 	std::vector<double> lt(LOG_TAB_N);
 	for (int i = 0; i < LOG_TAB_N; ++i) lt[i] = log((double)i); // glibc values (hazard H5)
-	d_log.ensure(lt.size() * 8); rt_h2d(d_log.p, lt.data(), lt.size() * 8);
 	std::string names; std::vector<uint32_t> noff;
 	for (auto& c : img.contigs) { noff.push_back((uint32_t)names.size()); names += c.name; names.push_back('\0'); }
 	noff.push_back((uint32_t)names.size());
-	d_names.ensure(names.size() + 1); rt_h2d(d_names.p, names.data(), names.size());
-	d_name_off.ensure(noff.size() * 4); rt_h2d(d_name_off.p, noff.data(), noff.size() * 4);
+	std::vector<u8> alt((size_t)img.n_seqs + 1, 0);
+	for (int i = 0; i < img.n_seqs; ++i) alt[i] = img.contigs[i].is_alt ? 1 : 0;
+	if (!(d_ctg.ensure(off.size() * 8 + alt.size()) && d_log.ensure(lt.size() * 8) && d_names.ensure(names.size() + 1) && d_name_off.ensure(noff.size() * 4))) { last_error = "device allocation failed"; return false; }
+	rt_h2d(d_ctg.p, off.data(), off.size() * 8);
+	rt_h2d((u8*)d_ctg.p + off.size() * 8, alt.data(), alt.size());
+	rt_h2d(d_log.p, lt.data(), lt.size() * 8);
+	rt_h2d(d_names.p, names.data(), names.size());
+	rt_h2d(d_name_off.p, noff.data(), noff.size() * 4);
 	memset(&dx, 0, sizeof(dx));
 	dx.primary = img.primary; memcpy(dx.L2, img.L2, 40); dx.seq_len = img.seq_len;
 	dx.bwt = (const uint4*)d_bwt.p; dx.sa = (const u64*)d_sa.p; dx.sa_intv = (u32)img.sa_intv;
 	dx.l_pac = img.l_pac; dx.n_seqs = img.n_seqs; dx.ctg_off = (const i64*)d_ctg.p; dx.pac = (const u8*)d_pac.p;
+	dx.ctg_alt = (const u8*)d_ctg.p + off.size() * 8;
 	dx.log_tab = (const double*)d_log.p; dx.log_tab_n = LOG_TAB_N;
 	rt_sync();
+	if (from) {
+		if (from->d_sa_dense.p) { dx.sa = d_sa_dense.as<u64>(); dx.sa_intv = from->dx.sa_intv; }
+		return g_last_cuda_ok();
+	}
 	// Spend HBM on the suffix array: the image samples every 32nd row (bwt_sa then walks ~15.5 LF steps per lookup, each
 	// a random 64-byte read); one LF-walk per 8th row at load time gives an 8-row sampling (6 GB at 3 Gbp) and ~3.5 steps.
 	// SA values are layout-independent, so results are unchanged.  BWA_B200_SA_INTV=32 keeps the image's sampling.
 	{
-		int want = 8;
-		if (const char* e = getenv("BWA_B200_SA_INTV")) want = atoi(e);
+		const int want = cfg.sa_intv;
 		if (want >= 1 && want < (int)dx.sa_intv && (want & (want - 1)) == 0) {
 			const uint64_t n_rows = img.seq_len + 1, n_out = (n_rows + want - 1) / want;
 			if (d_sa_dense.ensure((size_t)n_out * 8)) {
@@ -213,16 +352,31 @@ inline bool Engine::upload()
 			}
 		}
 	}
-	return true;
+	return g_last_cuda_ok();
+}
+
+inline void Batch::release_all()
+{
+	DBuf* all[] = { &b_blob, &b_seq, &b_seqoff, &b_intv, &b_nintv, &b_nseed, &b_smem,
+	                &b_seedoff, &b_rbeg, &b_S, &b_C, &b_ord, &b_tmp32, &b_ck, &b_ks, &b_srt, &b_regtmp, &b_nck, &b_nks, &b_nreg, &b_regcap, &b_regoff,
+	                &b_regs, &b_snap, &b_ztmp, &b_pairv, &b_recs, &b_nrec, &b_cand, &b_pairtab, &b_var, &b_misc, &b_outwords, &b_outoff, &b_out,
+	                &b_wsz, &b_wscig, &b_wsmd, &b_wsxa, &b_wsbrow, &b_nb, &b_swtask, &b_swstate, &b_swlist, &b_tbuf, &b_redo, &b_heavy, &b_multi, &b_cand2, &b_specstate, &b_spectask, &b_nreg0, &b_rsheavy, &b_wsrt, &b_wsrkey, &b_wsrrank, &b_exttask, &b_extres, &b_ckrmax, &b_chainheavy, &b_gatask, &b_gares, &b_gaitem0, &b_gaitemn, &b_seedpool, &b_seedused, &b_seedtask, &b_seedfb,
+	                &b_xtkey, &b_xtkey2, &b_xtidx, &b_xtidx2 };
+	for (DBuf* b : all) b->release();
+#ifndef B200_SIM
+	for (int t = 0; t < NUP; ++t) { if (up_stream[t]) cudaStreamDestroy(up_stream[t]); if (up_done[t]) cudaEventDestroy(up_done[t]); up_stream[t] = nullptr; up_done[t] = nullptr; }
+	rt_host_free(pin); pin = nullptr; pin_cap = 0;
+#endif
 }
 
 inline void Engine::close_all()
 {
-	DBuf* all[] = { &d_bwt, &d_sa, &d_sa_dense, &d_pac, &d_ctg, &d_log, &d_names, &d_name_off, &b_blob, &b_seq, &b_seqoff, &b_intv, &b_nintv, &b_nseed, &b_smem,
-	                &b_seedoff, &b_rbeg, &b_S, &b_C, &b_ord, &b_tmp32, &b_ck, &b_ks, &b_srt, &b_regtmp, &b_nck, &b_nks, &b_nreg, &b_regcap, &b_regoff,
-	                &b_regs, &b_snap, &b_ztmp, &b_pairv, &b_recs, &b_nrec, &b_cand, &b_pairtab, &b_var, &b_misc, &b_outwords, &b_outoff, &b_out,
-	                &b_wsz, &b_wscig, &b_wsmd, &b_wsxa, &b_wsbrow, &b_nb, &b_swtask, &b_swstate, &b_swlist, &b_tbuf, &b_redo, &b_heavy, &b_multi, &b_cand2, &b_specstate, &b_spectask, &b_nreg0, &b_rsheavy, &b_wsrt, &b_wsrkey, &b_wsrrank, &b_exttask, &b_extres, &b_ckrmax, &b_chainheavy, &b_gatask, &b_gares, &b_gaitem0, &b_gaitemn, &b_seedpool, &b_seedused, &b_seedtask, &b_seedfb };
-	for (DBuf* b : all) b->release();
+	for (Batch* b : ctxs) { rt_bind(b->rt); b->release_all(); }
+	for (size_t k = 0; k < reps.size(); ++k) { if (k * (size_t)cfg.contexts < ctxs.size()) rt_bind(ctxs[k * (size_t)cfg.contexts]->rt); reps[k]->release_all(); }
+	for (Batch* b : ctxs) { rt_ctx_destroy(b->rt); delete b; }
+	for (Replica* r : reps) delete r;
+	ctxs.clear(); reps.clear();
+	rt_bind(nullptr);
 	if (map) munmap(map, map_len);
 	map = nullptr;
 }
@@ -233,7 +387,7 @@ inline void Engine::close_all()
 // boundaries have to be found by a sequential scan that must not look past the last NUL.  While the host scans, a
 // helper thread already uploads the scanned prefix into the (grow-only) device buffer of the previous calls; a
 // request larger than that buffer falls back to scan-then-upload.
-inline bool Engine::stage(const char* blob_in, bool wait)
+inline bool Batch::stage(const char* blob_in, bool wait)
 {
 	st_valid = false;
 	uint32_t n_reads; memcpy(&n_reads, blob_in, 4);
@@ -247,23 +401,24 @@ inline bool Engine::stage(const char* blob_in, bool wait)
 	// queues a true DMA on its own stream.
 	std::atomic<uint64_t> scanned(0);
 	std::atomic<int> state(0); // 0 scanning, 1 scan finished, 2 abandon
-	int dev = 0; cudaGetDevice(&dev);
+	const int dev = rep->dev;
 	const uint64_t dcap = b_blob.cap;
 	char* dptr = (char*)b_blob.p;
 	const uint64_t CH = 4u << 20;
-	enum { NUP = 4 };
-	static cudaStream_t up_stream[NUP] = { nullptr, nullptr, nullptr, nullptr };
-	static cudaEvent_t up_done[NUP] = { nullptr, nullptr, nullptr, nullptr };
-	static char* pin = nullptr; static uint64_t pin_cap = 0; // pinned staging, grow-only like the device buffer
 	std::thread copier[NUP]; uint64_t reached[NUP] = { 0, 0, 0, 0 };
-	bool overlap = n_reads >= 4096 && dcap > 0 && !getenv("B200_NO_STAGE_OVERLAP");
+	bool overlap = n_reads >= 4096 && dcap > 0 && !eng->cfg.no_stage_overlap;
 	if (overlap && pin_cap < dcap) {
-		if (pin) cudaFreeHost(pin);
-		pin = nullptr; pin_cap = 0;
-		if (cudaHostAlloc((void**)&pin, dcap, cudaHostAllocDefault) == cudaSuccess) pin_cap = dcap; else { pin = nullptr; cudaGetLastError(); overlap = false; }
+		rt_host_free(pin);
+		pin = (char*)rt_host_alloc(dcap); pin_cap = pin ? dcap : 0;
+		if (!pin) overlap = false;
 	}
 	if (overlap) {
-		for (int t = 0; t < NUP; ++t) if (!up_stream[t]) { cudaStreamCreateWithFlags(&up_stream[t], cudaStreamNonBlocking); cudaEventCreateWithFlags(&up_done[t], cudaEventDisableTiming); }
+		for (int t = 0; t < NUP && overlap; ++t) if (!up_stream[t]) {
+			if (!cu_ok(cudaStreamCreateWithFlags(&up_stream[t], cudaStreamNonBlocking), "cudaStreamCreate") || !cu_ok(cudaEventCreateWithFlags(&up_done[t], cudaEventDisableTiming), "cudaEventCreate")) overlap = false;
+		}
+	}
+	std::atomic<int> copy_failed(0);
+	if (overlap) {
 		for (int t = 0; t < NUP; ++t) copier[t] = std::thread([&, t]() {
 			cudaSetDevice(dev);
 			for (uint64_t c = (uint64_t)t; ; c += NUP) { // chunk c = bytes [c*CH, (c+1)*CH); reached[t] = first chunk start this thread has NOT sent
@@ -280,12 +435,12 @@ inline bool Engine::stage(const char* blob_in, bool wait)
 				}
 				if (hi <= lo) break;
 				memcpy(pin + lo, base + lo, hi - lo);
-				if (cudaMemcpyAsync(dptr + lo, pin + lo, hi - lo, cudaMemcpyHostToDevice, up_stream[t]) != cudaSuccess) break;
+				if (cudaMemcpyAsync(dptr + lo, pin + lo, hi - lo, cudaMemcpyHostToDevice, up_stream[t]) != cudaSuccess) { copy_failed.store(1); break; }
 				reached[t] = lo + NUP * CH;
 				if (hi - lo < CH) break;
 			}
 		out:
-			cudaEventRecord(up_done[t], up_stream[t]);
+			if (cudaEventRecord(up_done[t], up_stream[t]) != cudaSuccess) copy_failed.store(1);
 		});
 	}
 	scan_reads(base, n_reads, st_seq_off.data(), &max_len, overlap ? &scanned : nullptr);
@@ -307,6 +462,7 @@ inline bool Engine::stage(const char* blob_in, bool wait)
 		scanned.store(st_blob_len, std::memory_order_release);
 		state.store(st_blob_len + 16 <= dcap ? 1 : 2, std::memory_order_release);
 		for (int t = 0; t < NUP; ++t) copier[t].join();
+		if (copy_failed.load()) { cudaGetLastError(); last_error = "staging copy failed"; return false; }
 		if (st_blob_len + 16 <= dcap) {
 			// the chunks alternate between the threads: everything below the lowest of the frontiers is on its way
 			uploaded = reached[0];
@@ -326,29 +482,30 @@ inline bool Engine::stage(const char* blob_in, bool wait)
 	return true;
 }
 
-inline void* Engine::align(const MemOpt* opt_in, const PeStat* pes0, char* blob_in, size_t* out_size)
+inline void* Batch::align(const MemOpt* opt_in, const PeStat* pes0, char* blob_in, size_t* out_size)
 {
-	std::lock_guard<std::mutex> lock(device_mutex());
 	last_error.clear();
 	*out_size = 0;
-	g_hp.begin();
+	hp.begin();
 	if (!stage(blob_in, false)) return nullptr; // same stream: the kernels queue up behind the upload
-	g_hp.mark("stage");
+	hp.mark("stage");
 	void* r = run(opt_in, pes0, out_size, true);
-	g_hp.mark("d2h_out");
-	g_hp.report();
+	hp.mark("d2h_out");
+	hp.report();
 	return r;
 }
 
 // Run the device pipeline on the staged request.  host_output: copy the record stream into a malloc'd buffer (the
 // reference contract); otherwise it stays in device memory (bench.py's HBM-resident measurement) and a non-null
 // sentinel is returned.
-inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_size, bool host_output)
+inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_size, bool host_output)
 {
 	*out_size = 0;
 	if (!st_valid) { last_error = "no staged request"; return nullptr; }
 	rt_timer_begin();
 	MemOpt opt = *opt_in; // the options live in a caller-owned buffer (…BwaMemIndex.c:146): snapshot them
+	const EngineConfig& cfg = eng->cfg; const ImageView& img = eng->img; const DevIndex& dx = rep->dx;
+	DBuf& d_names = rep->d_names; DBuf& d_name_off = rep->d_name_off;
 	const uint32_t n_reads = st_n_reads;
 	const int max_len = st_max_len;
 	const uint64_t blob_len = st_blob_len;
@@ -399,38 +556,39 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 	// ---- stage 1: encode + seed
 	RT_THREADS(body_encode, P, (int64_t)blob_len);
 	P.seed_lcap = 8; P.seed_shared_read = 0; // few candidates survive per position; the read is walked sequentially (L1)
-	if (getenv("B200_SEED_LCAP")) { int v = atoi(getenv("B200_SEED_LCAP")); if (v >= 1 && v <= SEED_LCAP) P.seed_lcap = v; } // tuning aids
-	if (getenv("B200_SEED_SHARED_READ")) P.seed_shared_read = atoi(getenv("B200_SEED_SHARED_READ"));
+	if (cfg.seed_lcap >= 1 && cfg.seed_lcap <= SEED_LCAP) P.seed_lcap = cfg.seed_lcap; // tuning aids
+	if (cfg.seed_shared_read >= 0) P.seed_shared_read = cfg.seed_shared_read;
 	{
 		const size_t ssm = P.seed_shared ? seed_block_smem_bytes(THREADS_PER_BLOCK, max_len, P.seed_lcap, P.seed_shared_read) : 0;
-		if (getenv("B200_SEED_ONE_LAUNCH")) RT_THREADS_QUEUE_SMEM(body_seed_q, P, (int64_t)n_reads, ssm);
-		else if (!P.seed_shared || getenv("B200_SEED_FUSED_ROUNDS")) { // rounds 1/2 in one machine (two kinds of steps), round 3 alone
+		if (cfg.seed_one_launch) RT_THREADS_QUEUE_SMEM(body_seed_q, P, (int64_t)n_reads, ssm);
+		else if (!P.seed_shared || cfg.seed_fused_rounds) { // rounds 1/2 in one machine (two kinds of steps), round 3 alone
 			RT_THREADS_QUEUE_SMEM(body_seed12_q, P, (int64_t)n_reads, ssm);
 			RT_THREADS_QUEUE_SMEM(body_seed3_q, P, (int64_t)n_reads, ssm);
 		} else {
 			// every launch has ONE kind of extension step: forward scans (lane per read), backward sweeps (lane per scan),
 			// for round 1 and again for round 2, then round 3 (forward-only seeds; it also orders and counts the list)
 			P.seed_pool_cap = (u32)(6 * max_len + 16); // candidates of all scans of a round (14 KB per read); a read that needs more is redone below
-			if (getenv("B200_TEST_TINY_SEED_POOL")) P.seed_pool_cap = 24;
-			P.seed_task_cap = (u32)std::min<uint64_t>((uint64_t)0x7fffffff, (uint64_t)n_reads * 24 + 1024); // one task per forward scan (a scan per sequencing error, roughly)
+			if (cfg.tiny_seed_pool) P.seed_pool_cap = 24;
+			P.seed_task_cap = (u32)std::min<uint64_t>((uint64_t)0x7fffffff, (uint64_t)n_reads * 24 + 1024); // one task per forward scan (a scan per sequencing error, roughly); reads whose scans do not fit are redone below
+			if (cfg.tiny_seed_tasks) P.seed_task_cap = 48;
 			ok = b_seedpool.ensure((size_t)n_reads * P.seed_pool_cap * 16) && b_seedused.ensure((size_t)n_reads * 4) && b_seedtask.ensure((size_t)P.seed_task_cap * sizeof(SeedTask)) && b_seedfb.ensure(((size_t)n_reads + 1) * 4);
 			if (!ok) { last_error = "device allocation failed (seeding pools)"; return nullptr; }
-			P.seed_pool = b_seedpool.as<uint4>(); P.seed_pool_used = b_seedused.as<u32>(); P.seed_tasks = b_seedtask.as<SeedTask>(); P.n_seed_tasks = b_misc.as<u32>() + 24;
-			P.seed_fb = b_seedfb.as<u32>(); P.n_seed_fb = b_misc.as<u32>() + 25; // (word 26 = heavy-scan count, behind n_seed_tasks)
+			P.seed_pool = b_seedpool.as<uint4>(); P.seed_pool_used = b_seedused.as<u32>(); P.seed_tasks = b_seedtask.as<SeedTask>(); P.n_seed_tasks = b_misc.as<u32>() + 24; // words 24..27: the 64-bit reservation counter and the counts of a full list (fm.cuh seed_task_reserve)
+			P.seed_fb = b_seedfb.as<u32>(); P.n_seed_fb = b_misc.as<u32>() + 28;
 			rt_memset(P.n_intv, 0, (size_t)n_reads * 4);
 			// The scans with many candidates (a warp each: few, long-running warps) run on the auxiliary stream beside the
 			// lane-per-scan sweep of the others; both only append to per-read lists that round 3 orders afterwards.
-			const bool overlap = !getenv("B200_SEED_NO_OVERLAP");
+			const bool overlap = !cfg.seed_no_overlap;
 			RT_THREADS_QUEUE_SMEM(body_seedF1_q, P, (int64_t)n_reads, 0);
 			if (overlap) rt_fork_aux();
-			RT_WARPS_DEVN(wbody_seedB_heavy, P, P.n_seed_tasks + 2, (int64_t)n_reads);
+			RT_WARPS_DEVN(wbody_seedB_heavy, P, P.n_seed_tasks + 1, (int64_t)n_reads);
 			if (overlap) rt_back_to_main();
 			RT_THREADS_QUEUE_SMEM(body_seedB_q, P, (int64_t)P.seed_task_cap, 0);
 			if (overlap) rt_join_aux("wbody_seedB_heavy");
-			rt_memset(P.n_seed_tasks, 0, 4); rt_memset(P.n_seed_tasks + 2, 0, 4);
+			rt_memset(P.n_seed_tasks, 0, 16);
 			RT_THREADS_QUEUE_SMEM(body_seedF2_q, P, (int64_t)n_reads, 0);
 			if (overlap) rt_fork_aux();
-			RT_WARPS_DEVN(wbody_seedB_heavy, P, P.n_seed_tasks + 2, (int64_t)n_reads);
+			RT_WARPS_DEVN(wbody_seedB_heavy, P, P.n_seed_tasks + 1, (int64_t)n_reads);
 			if (overlap) rt_back_to_main();
 			RT_THREADS_QUEUE_SMEM(body_seedB2_q, P, (int64_t)P.seed_task_cap, 0);
 			if (overlap) rt_join_aux("wbody_seedB_heavy");
@@ -438,9 +596,9 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 			RT_THREADS_QUEUE_SMEM(body_seed3_q, P, (int64_t)n_reads, ssm);
 		}
 	}
-	g_hp.mark("launch1");
+	hp.mark("launch1");
 	uint64_t T = rt_scan_u32(P.n_seed, P.seed_off, n_reads);
-	g_hp.mark("seed_sync");
+	hp.mark("seed_sync");
 	P.n_seed_total = T; last_n_seed = T;
 	{
 		size_t Tn = (size_t)T + 1;
@@ -454,8 +612,8 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 	RT_THREADS(body_sal, P, (int64_t)T);
 	if (!b_chainheavy.ensure(((size_t)n_reads + 1) * 4)) { last_error = "device allocation failed"; return nullptr; }
 	P.chain_heavy = b_chainheavy.as<u32>(); P.n_chain_heavy = b_misc.as<u32>() + 22;
-	P.chain_heavy_seeds = getenv("B200_TEST_CHAIN_ALL_WARP") ? -1 : (getenv("B200_TEST_CHAIN_ALL_THREAD") ? (1 << 30) : CHAIN_HEAVY_SEEDS);
-	if (getenv("B200_CHAIN_NO_OVERLAP")) { P.chain_listed = 0; RT_THREADS(body_chain, P, (int64_t)n_reads); RT_WARPS_DEVN(wbody_chain_heavy, P, P.n_chain_heavy, (int64_t)n_reads); }
+	P.chain_heavy_seeds = cfg.chain_all_warp ? -1 : (cfg.chain_all_thread ? (1 << 30) : CHAIN_HEAVY_SEEDS);
+	if (cfg.chain_no_overlap) { P.chain_listed = 0; RT_THREADS(body_chain, P, (int64_t)n_reads); RT_WARPS_DEVN(wbody_chain_heavy, P, P.n_chain_heavy, (int64_t)n_reads); }
 	else { // the warp-per-read kernel (few long-running warps) on the auxiliary stream beside the thread-per-read one
 		P.chain_listed = 1;
 		RT_THREADS(body_chain_classify, P, (int64_t)n_reads);
@@ -484,28 +642,28 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 	// ---- thread scratch for the thread-per-item kernels (extension, finalize) and the hand-over lists
 	{
 		P.t_z_cap = 8192; P.t_cigar_cap = 48; P.t_md_cap = 192; P.t_xa_cap = 1024;
-		if (getenv("B200_TEST_TINY_SCRATCH")) { P.t_z_cap = 1024; P.t_cigar_cap = 6; P.t_md_cap = 24; P.t_xa_cap = 80; } // tests: force hand-overs
+		if (cfg.tiny_scratch) { P.t_z_cap = 1024; P.t_cigar_cap = 6; P.t_md_cap = 24; P.t_xa_cap = 80; } // tests: force hand-overs
 		P.t_stride = thread_scratch_bytes(P.wm_cap, P.t_z_cap, P.t_cigar_cap, P.t_md_cap, P.t_xa_cap);
 		ok = b_tbuf.ensure((size_t)tslots * P.t_stride) && b_redo.ensure(((size_t)n_reads + 1) * 4) && b_heavy.ensure(((size_t)n_reads + 1) * 4);
 		if (!ok) { last_error = "device allocation failed (thread scratch)"; return nullptr; }
 		P.t_buf = b_tbuf.as<u8>(); P.redo_list = b_redo.as<u32>(); P.n_redo = b_misc.as<u32>() + 5;
 		P.heavy_list = b_heavy.as<u32>(); P.n_heavy = b_misc.as<u32>() + 6;
 		P.light_max_seeds = 12; P.light_max_chains = 4; P.tx_chunk = 32;
-		if (getenv("B200_TX_CHUNK")) P.tx_chunk = atoi(getenv("B200_TX_CHUNK")); // tuning aid (0: whole rows)
-		if (getenv("B200_LIGHT_SEEDS")) P.light_max_seeds = atoi(getenv("B200_LIGHT_SEEDS")); // tuning aids
-		if (getenv("B200_LIGHT_CHAINS")) P.light_max_chains = atoi(getenv("B200_LIGHT_CHAINS"));
-		if (getenv("B200_TEST_ALL_HEAVY")) P.light_max_seeds = -1;
-		if (getenv("B200_TEST_ALL_LIGHT")) { P.light_max_seeds = 1 << 30; P.light_max_chains = 1 << 30; }
+		if (cfg.tx_chunk >= 0) P.tx_chunk = cfg.tx_chunk; // tuning aid (0: whole rows)
+		if (cfg.light_seeds >= 0) P.light_max_seeds = cfg.light_seeds; // tuning aids
+		if (cfg.light_chains >= 0) P.light_max_chains = cfg.light_chains;
+		if (cfg.all_heavy) P.light_max_seeds = -1;
+		if (cfg.all_light) { P.light_max_seeds = 1 << 30; P.light_max_chains = 1 << 30; }
 	}
 	for (int t = 0; t < 5; ++t) { P.rowpack[t] = 0; for (int c2 = 0; c2 < 5; ++c2) P.rowpack[t] |= (u64)(u8)opt.mat[t * 5 + c2] << (8 * c2); }
 	// ---- stage 3: extension + de-duplication (thread per light read with shared-memory DP rows, warp per heavy read)
-	if (getenv("B200_WARP_EXTEND")) RT_WARPS(wbody_extend, P, (int64_t)n_reads); // the all-warp formulation, kept for comparison
+	if (cfg.warp_extend) RT_WARPS(wbody_extend, P, (int64_t)n_reads); // the all-warp formulation, kept for comparison
 	else {
 		int rw = max_len - opt.min_seed_len + 2;
 		// cells: H and E as 8-bit halves when no score of the batch can exceed 255 (the per-read test in the kernel is the
 		// same bound), else as 16-bit halves.  Narrow cells halve the shared memory per thread: more resident warps.
 		int mxs = 0; for (int k = 0; k < 25; ++k) mxs = mxs > opt.mat[k] ? mxs : (int)opt.mat[k];
-		const bool narrow = !getenv("B200_EXT_WIDE_CELLS") && (int64_t)max_len * mxs + opt.pen_clip5 + opt.pen_clip3 <= 255;
+		const bool narrow = !cfg.ext_wide_cells && (int64_t)max_len * mxs + opt.pen_clip5 + opt.pen_clip3 <= 255;
 		const int cell = narrow ? 2 : 4;
 		if (!narrow && rw * cell < 4 * THREAD_RING_N) rw = 4 * THREAD_RING_N / cell; // wide cells: the patching rings reuse the row (at least THREAD_RING_N / 2 slots)
 		const size_t budget = 200 * 1024; // per block of THREADS_PER_BLOCK threads
@@ -520,7 +678,7 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 			const size_t ext_smem = thread_ext_smem_bytes(THREADS_PER_BLOCK, rw, wm_cap, cell), task_smem = ext_smem;
 			if (narrow) RT_THREADS_QUEUE_SMEM(body_extend_q8, P, (int64_t)n_reads, ext_smem);
 			else RT_THREADS_QUEUE_SMEM(body_extend_q, P, (int64_t)n_reads, ext_smem);
-			if (getenv("B200_NO_EXT_TASKS")) RT_WARPS_DEVN(wbody_extend_heavy, P, P.n_heavy, (int64_t)n_reads); // each heavy read extended by its own warp
+			if (cfg.no_ext_tasks) RT_WARPS_DEVN(wbody_extend_heavy, P, P.n_heavy, (int64_t)n_reads); // each heavy read extended by its own warp
 			else {
 				// heavy reads: every kept seed becomes an extension task for the thread-level queue, then a warp per read
 				// replays the containment decisions over the finished extensions and de-duplicates the regions
@@ -549,9 +707,9 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 			rt_sort_u64((const uint64_t*)P.pe_cand, b_cand2.as<uint64_t>(), (uint64_t)n_units);
 			std::vector<int64_t> cand((size_t)n_units);
 			rt_d2h(cand.data(), b_cand2.p, (size_t)n_units * 8);
-			g_hp.mark("extend_sync");
+			hp.mark("extend_sync");
 			host_mem_pestat(opt, cand.data(), n_units, P.pes, true);
-			g_hp.mark("pestat");
+			hp.mark("pestat");
 		}
 		std::vector<double> tab; int64_t off[4];
 		if (!host_pair_table(opt, P.pes, tab, off)) { last_error = "insert-size range too wide to tabulate"; return nullptr; }
@@ -567,7 +725,7 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 	// ---- region capacity, offsets, compaction
 	RT_THREADS(body_reg_cap, P, (int64_t)n_reads);
 	uint64_t R = rt_scan_u32(P.reg_cap, P.reg_off, n_reads);
-	g_hp.mark("regcap_sync");
+	hp.mark("regcap_sync");
 	{
 		size_t Rn = (size_t)R + 2;
 		ok = b_regs.ensure(Rn * sizeof(Reg)) && b_snap.ensure(Rn * sizeof(Reg)) && b_ztmp.ensure(Rn * 4) && b_pairv.ensure(Rn * sizeof(Pair64)) && b_recs.ensure(Rn * sizeof(AlnRec));
@@ -587,7 +745,7 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 		P.nb = b_nb.as<u32>(); P.sw_tasks = b_swtask.as<SwTask>(); P.sw_state = b_swstate.as<u8>(); P.sw_list = b_swlist.as<u32>();
 		P.sw_n_list = b_misc.as<u32>() + 3; P.max_nb = b_misc.as<u32>() + 4; P.n_multi = b_misc.as<u32>() + 7;
 		P.multi = b_multi.as<u32>(); P.spec_state = b_specstate.as<u8>(); P.spec_task = b_spectask.as<u32>(); P.n_reg0 = b_nreg0.as<u32>();
-		P.force_fb = getenv("B200_TEST_RESCUE_FALLBACK") ? 1 : 0; // tests: every rescuing read takes the round-by-round path
+		P.force_fb = cfg.rescue_fallback ? 1 : 0; // tests: every rescuing read takes the round-by-round path
 		P.rs_heavy = b_rsheavy.as<u32>(); P.n_rs_heavy = b_misc.as<u32>() + 20;
 		RT_THREADS(body_rescue_snap, P, (int64_t)n_reads);
 		RT_THREADS(body_rescue_classify, P, (int64_t)n_reads);
@@ -599,7 +757,7 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 		uint32_t hdr[8];
 		rt_d2h(hdr, b_misc.as<u32>(), sizeof(hdr));
 		const uint32_t max_nb = hdr[4], n_fb = hdr[7];
-		g_hp.mark("rescue_sync");
+		hp.mark("rescue_sync");
 		if (n_fb) {
 			RT_THREADS(body_rescue_fb_restore, P, (int64_t)n_fb);
 			int rounds = (int)max_nb < opt.max_matesw ? (int)max_nb : opt.max_matesw;
@@ -617,17 +775,18 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 	{
 		RT_THREADS(body_save_regs, P, (int64_t)n_reads);
 		const int64_t n_items = pe ? (int64_t)n_units : (int64_t)n_reads;
-		if (getenv("B200_FINAL_ONE_PASS")) { // every item computes its own alignments (kept for comparison and tests)
+		if (cfg.final_one_pass) { // every item computes its own alignments (kept for comparison and tests)
 			if (pe) RT_THREADS_TID_RING(body_final_pe_t, P, n_items); else RT_THREADS_TID_RING(body_final_se_t, P, n_items);
 		} else {
 			// two passes around a queue of alignment tasks (galign_thread.cuh): collect -> tasks -> consume
-			P.ga_cap = (u32)std::min<uint64_t>((uint64_t)0x7fffffff, (uint64_t)n_reads * 3 + 1024);
+			P.ga_cap = (u32)std::min<uint64_t>((uint64_t)0x7fffffff, (uint64_t)n_reads * 4 + 1024); // items that find the pool full are redone by a warp
+			if (cfg.tiny_ga_cap) P.ga_cap = 40;
 			ok = b_gatask.ensure((size_t)P.ga_cap * sizeof(GaTask)) && b_gares.ensure((size_t)P.ga_cap * sizeof(GaRes)) && b_gaitem0.ensure(((size_t)n_items + 1) * 4) && b_gaitemn.ensure(((size_t)n_items + 1) * 4);
 			if (!ok) { last_error = "device allocation failed (alignment tasks)"; return nullptr; }
 			P.ga_tasks = b_gatask.as<GaTask>(); P.ga_res = b_gares.as<GaRes>(); P.ga_item0 = b_gaitem0.as<u32>(); P.ga_itemn = b_gaitemn.as<u32>();
 			P.n_ga_tasks = b_misc.as<u32>() + 23;
 			// (neither pass computes an alignment itself: no shared-memory rings, which lets a third block onto each SM)
-			const bool fin_ring = getenv("B200_TEST_FINAL_RING") != nullptr;
+			const bool fin_ring = cfg.final_ring;
 			if (fin_ring) { if (pe) RT_THREADS_TID_RING(body_final_pe_collect, P, n_items); else RT_THREADS_TID_RING(body_final_se_collect, P, n_items); }
 			else if (pe) RT_THREADS_TID(body_final_pe_collect, P, n_items); else RT_THREADS_TID(body_final_se_collect, P, n_items);
 			rt_memset(P.var_cursor, 0, 4); // payloads written while collecting are discarded
@@ -640,22 +799,23 @@ inline void* Engine::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_s
 	// ---- output stream
 	RT_THREADS(body_out_size, P, (int64_t)n_reads);
 	uint64_t W = rt_scan_u32(P.out_words, P.out_off, n_reads);
-	g_hp.mark("final_sync");
+	hp.mark("final_sync");
 	if (!b_out.ensure((size_t)W * 4 + 16)) { last_error = "device allocation failed (output)"; return nullptr; }
 	P.out = b_out.as<u32>();
 	RT_THREADS(body_out_write, P, (int64_t)n_reads);
 	uint32_t misc[32];
 	rt_d2h(misc, b_misc.p, sizeof(misc));
 	memcpy(&last_counters, misc + 8, sizeof(Counters));
-	if (getenv("B200_DEBUG_STATS")) fprintf(stderr, "[bwamem-b200] reads %u: finalize redo %u, alignment tasks %u, extension-heavy reads %u / tasks %u, chain-heavy %u, rescue warp-replayed %u / fallback %u, seed one-machine reads %u\n",
-	                                        n_reads, misc[5], misc[23], misc[6], misc[21], misc[22], misc[20], misc[7], misc[25]);
+	n_launches = rt_launches();
+	if (cfg.debug_stats) fprintf(stderr, "[bwamem-b200] reads %u: finalize redo %u, alignment tasks %u, extension-heavy reads %u / tasks %u, chain-heavy %u, rescue warp-replayed %u / fallback %u, seed one-machine reads %u\n",
+	                                        n_reads, misc[5], misc[23], misc[6], misc[21], misc[22], misc[20], misc[7], misc[28]);
 	if (misc[0]) {
 		char buf[128]; snprintf(buf, sizeof buf, "device-side capacity/limit error flags 0x%x", misc[0]);
 		last_error = buf;
 		return nullptr;
 	}
 	if (!host_output) { *out_size = (size_t)W * 4; rt_sync(); return (void*)b_out.p; }
-	g_hp.mark("write_sync");
+	hp.mark("write_sync");
 	void* res = malloc((size_t)W * 4 + 4);
 	if (!res) { last_error = "host allocation failed"; return nullptr; }
 	rt_d2h(res, P.out, (size_t)W * 4);

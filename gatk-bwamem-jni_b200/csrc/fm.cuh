@@ -396,8 +396,9 @@ struct SeedSplitIO {
 	const u8* seq; const u64* seq_off; i64 n_reads;
 	uint4* pool; u32 pool_cap;        // pool_cap candidates per read
 	u32* pool_used;                   // per read: candidates appended so far (round 2 continues behind round 1)
-	SeedTask* tasks; u32* n_tasks; u32 task_cap;   // light tasks fill the array from the front,
-	u32* n_heavy_tasks;                            // scans with many candidates from the back (they are swept first: longest jobs first)
+	SeedTask* tasks; u32 task_cap;    // light tasks fill the array from the front, scans with many candidates from the back (swept first: longest jobs first)
+	u32* n_tasks;                     // [0],[1]: ONE 64-bit reservation counter (low word = light scans, high word = heavy scans);
+	                                  // [2],[3]: the two counts at the moment the list became full (written by the reservation that found it so)
 	Intv* intv; int intv_cap; u32* n_intv;
 	u32* err; int smem_cap;
 	u32* fb_list; u32* n_fb;          // reads whose scans did not fit the pool / task list: redone by fm_collect_queue<1>
@@ -406,6 +407,24 @@ struct SeedSplitIO {
 #define SEED_HEAVY_CANDS 24
 #endif
 #define SEED_POOL_OVERFLOW 0xffffffffu // value of pool_used[r] for such a read (its tasks are skipped)
+// Reservation of a task slot.  Both counts live in one 64-bit word, so the atomic add returns a consistent pair: the
+// first task_cap reservations (in the order of the atomics) succeed and own distinct slots, every later one fails --
+// its read is redone as a whole by the one-machine kernel (fb_list) -- and the one that finds the list exactly full
+// records the two counts, which is what the backward launches then run (the counters themselves overshoot).
+DEV bool seed_task_reserve(const SeedSplitIO& io, bool heavy, u32& slot)
+{
+	const u64 old = atomic_add_u64((u64*)io.n_tasks, heavy ? (u64)1 << 32 : (u64)1);
+	const u32 nl = (u32)old, nh = (u32)(old >> 32);
+	const u64 tot = (u64)nl + nh;
+	if (tot >= io.task_cap) { if (tot == io.task_cap) { io.n_tasks[2] = nl; io.n_tasks[3] = nh; } return false; }
+	slot = heavy ? io.task_cap - 1 - nh : nl;
+	return true;
+}
+DEV void seed_task_counts(const SeedSplitIO& io, u32& nl, u32& nh)
+{
+	nl = io.n_tasks[0]; nh = io.n_tasks[1];
+	if ((u64)nl + nh > io.task_cap) { nl = io.n_tasks[2]; nh = io.n_tasks[3]; }
+}
 DEV uint4 cand_pack(const BiIntv& b, u32 end)
 {
 	uint4 e;
@@ -437,10 +456,8 @@ DEV void fm_forward_queue(const DevIndex& x, const MemOpt& opt, const SeedSplitI
 	bool ovf = false; // the read does not fit the pool / the task list: it is handed to the one-machine formulation
 #define F_PUSH() do { if (used < io.pool_cap) { pool[used] = cand_pack(ik, ik_end); ++used; ++n_c; last_end = ik_end; } else ovf = true; } while (0)
 #define F_END_SCAN() do { \
-		if (n_c && !ovf) { const bool hv_ = n_c >= SEED_HEAVY_CANDS; \
-			u32 slot_ = hv_ ? atomic_add_u32(io.n_heavy_tasks, 1u) : atomic_add_u32(io.n_tasks, 1u); \
-			if (hv_) slot_ = slot_ < io.task_cap ? io.task_cap - 1 - slot_ : io.task_cap; \
-			if (slot_ < io.task_cap && *io.n_tasks + *io.n_heavy_tasks <= io.task_cap) { SeedTask t_; t_.read = (u32)r; t_.c_off = c_off; t_.n_c = n_c; t_.start = (u32)start; t_.min_intv = min_intv; io.tasks[slot_] = t_; } \
+		if (n_c && !ovf) { u32 slot_ = 0; \
+			if (seed_task_reserve(io, n_c >= SEED_HEAVY_CANDS, slot_)) { SeedTask t_; t_.read = (u32)r; t_.c_off = c_off; t_.n_c = n_c; t_.start = (u32)start; t_.min_intv = min_intv; io.tasks[slot_] = t_; } \
 			else ovf = true; } \
 		if (ROUND == 1) xx = (int)last_end; else ++k2; \
 		st = ovf ? F_FETCH : F_NEXT; } while (0)

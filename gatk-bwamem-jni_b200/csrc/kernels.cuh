@@ -138,7 +138,7 @@ DEV SeedSplitIO make_seed_split_io(const BatchParams& P, i64 n_reads)
 	SeedSplitIO io;
 	io.seq = P.seq; io.seq_off = P.seq_off; io.n_reads = n_reads;
 	io.pool = P.seed_pool; io.pool_cap = P.seed_pool_cap; io.pool_used = P.seed_pool_used;
-	io.tasks = P.seed_tasks; io.n_tasks = P.n_seed_tasks; io.task_cap = P.seed_task_cap; io.n_heavy_tasks = P.n_seed_tasks + 2;
+	io.tasks = P.seed_tasks; io.n_tasks = P.n_seed_tasks; io.task_cap = P.seed_task_cap;
 	io.intv = P.intv; io.intv_cap = P.intv_cap; io.n_intv = P.n_intv;
 	io.err = P.err; io.smem_cap = P.smem_cap;
 	io.fb_list = P.seed_fb; io.n_fb = P.n_seed_fb;
@@ -147,14 +147,15 @@ DEV SeedSplitIO make_seed_split_io(const BatchParams& P, i64 n_reads)
 // rounds 1 and 2 as forward scans (a lane per read) and backward sweeps (a lane per scan): fm.cuh
 DEV void body_seedF1_q(const BatchParams& P, i64 n, u32* counter, i64 tid) { (void)tid; SeedSplitIO io = make_seed_split_io(P, n); fm_forward_queue<1>(P.x, P.opt, io, counter); }
 DEV void body_seedF2_q(const BatchParams& P, i64 n, u32* counter, i64 tid) { (void)tid; SeedSplitIO io = make_seed_split_io(P, n); fm_forward_queue<2>(P.x, P.opt, io, counter); }
-DEV void body_seedB_q(const BatchParams& P, i64 n, u32* counter, i64 tid) { (void)tid; (void)n; SeedSplitIO io = make_seed_split_io(P, P.n_reads); u32 nl = P.n_seed_tasks[0], nh = P.n_seed_tasks[2]; if ((u64)nl + nh > P.seed_task_cap) { atomic_or_u32(P.err, ERR_INTV_OVERFLOW); nl = 0; nh = 0; } // the two ends of the task array met: fail the batch loudly
+DEV void body_seedB_q(const BatchParams& P, i64 n, u32* counter, i64 tid) { (void)tid; (void)n; SeedSplitIO io = make_seed_split_io(P, P.n_reads); u32 nl, nh; seed_task_counts(io, nl, nh);
 	fm_backward_queue(P.x, P.opt, io, (i64)nl, counter); }
 template <int W>
 DEV void wbody_seedB_heavy(const BatchParams& P, i64 item, WarpMem& wm, WarpScratch& ws)
 {
 	(void)wm; (void)ws;
 	SeedSplitIO io = make_seed_split_io(P, P.n_reads);
-	if ((u64)P.n_seed_tasks[0] + P.n_seed_tasks[2] > P.seed_task_cap) return; // (flagged by the light launch)
+	u32 nl, nh; seed_task_counts(io, nl, nh);
+	if ((u32)item >= nh) return; // (a reservation past the end of the task list: that read is redone as a whole)
 	const SeedTask tk = P.seed_tasks[P.seed_task_cap - 1 - (u32)item];
 	fm_backward_task_warp<W>(P.x, P.opt, io, tk);
 }
@@ -614,7 +615,14 @@ DEV void final_collect_item(const BatchParams& P, i64 item, i64 tid, bool pe)
 	if (pe) wbody_final_pe<1>(P, item, wm, ws, &fm); else wbody_final_se<1>(P, item, wm, ws, &fm);
 	u32 n = (u32)fm.lt_n, base = 0;
 	bool direct = n > (u32)GA_ITEM_MAX;
-	if (!direct && n) { base = atomic_add_u32(P.n_ga_tasks, n); if (base + n > P.ga_cap) direct = true; }
+	if (!direct && n) {
+		base = atomic_add_u32(P.n_ga_tasks, n);
+		if ((u64)base + n > (u64)P.ga_cap) { // the pool is full: a warp redoes the item.  The counter stays above ga_cap; the task kernel runs
+			direct = true;                    // min(counter, ga_cap) slots, so the slots this item reserved below the cap are blanked (l_query = 0: skipped)
+			GaTask z; memset(&z, 0, sizeof(z));
+			for (u64 k = base; k < (u64)P.ga_cap; ++k) P.ga_tasks[k] = z;
+		}
+	}
 	if (!direct) for (u32 k = 0; k < n; ++k) P.ga_tasks[base + k] = lt[k];
 	P.ga_item0[item] = base; P.ga_itemn[item] = direct ? 0xffffffffu : n;
 }
@@ -650,7 +658,8 @@ DEV void body_galign_task_q(const BatchParams& P, i64 n, u32* counter, i64 tid)
 		wm.q = tsm_ + (size_t)blockDim.x * THREAD_RING_N * 4 + threadIdx.x; wm.q_stride = (int)blockDim.x;
 	}
 #endif
-	thread_galign_queue(P, (i64)*P.n_ga_tasks, counter, wm, ws, &lerr);
+	const u32 n_res = *P.n_ga_tasks; // (reservations may have run past the pool: final_collect_item)
+	thread_galign_queue(P, (i64)(n_res < P.ga_cap ? n_res : P.ga_cap), counter, wm, ws, &lerr);
 }
 template <int W>
 DEV void wbody_final_pe_redo(const BatchParams& P, i64 item, WarpMem& wm, WarpScratch& ws)

@@ -50,6 +50,7 @@ struct DevIndex {
 	i64 l_pac;
 	i32 n_seqs;
 	const i64* ctg_off; // n_seqs+1 cumulative contig offsets on the forward strand
+	const u8* ctg_alt;  // n_seqs: 1 for an ALT contig (bntann1_t.is_alt)
 	const u8* pac;      // 2 bits per base
 	const double* log_tab;  // glibc log(i), i in [0, LOG_TAB_N)  (hazard H5: libm results are tabulated on the host)
 	i32 log_tab_n;

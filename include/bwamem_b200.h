@@ -72,6 +72,10 @@ const char* jnibwa_getVersion(void);
 
 /* ---- instrumentation (not part of the reference surface; used by bench.py) ---- */
 int b200_setDevice(int dev);
+/* contexts of a handle = devices of its pool (BWA_B200_DEVICES) x batches in flight per device (BWA_B200_CONTEXTS);
+ * the device of context i.  The b200_*Staged / lastBatchMs / lastStageTimes calls below act on context 0. */
+int b200_contextCount(void* idx);
+int b200_contextDevice(void* idx, int i);
 const char* b200_lastError(void* idx);
 int b200_lastStageTimes(void* idx, float* ms, const char** names, int cap);
 void b200_lastCounters(void* idx, uint64_t* out8);

@@ -4,6 +4,9 @@ import sys
 import pytest
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+# The B200_TEST_* / tuning variables that force kernel variants and tiny capacities are honoured by the library only
+# behind this gate (read once per jnibwa_openIndex: engine_impl.inl EngineConfig).
+os.environ.setdefault("B200_TEST_HOOKS", "1")
 
 
 def pytest_configure(config):

@@ -19,6 +19,23 @@ static void rt_h2d(void* d, const void* s, size_t n) { memcpy(d, s, n); }
 static void rt_d2h(void* d, const void* s, size_t n) { memcpy(d, s, n); }
 static void rt_memset(void* d, int v, size_t n) { memset(d, v, n); }
 static void rt_sync() {}
+struct RtCtx { int dev = 0; };
+static RtCtx* rt_ctx_create(int dev) { RtCtx* c = new RtCtx(); c->dev = dev; return c; }
+static void rt_ctx_destroy(RtCtx* c) { delete c; }
+static bool rt_bind(RtCtx*) { return true; }
+static int rt_current_device() { return 0; }
+static int rt_launches() { return 0; }
+static bool g_last_cuda_ok() { return true; }
+static bool rt_peer_copy(void* dst, int, const void* src, int, size_t n) { memcpy(dst, src, n); return true; }
+static void* rt_host_alloc(size_t n) { return malloc(n ? n : 1); }
+static void rt_host_free(void* p) { free(p); }
+static bool cu_ok(int, const char*) { return true; }
+static void rt_sort_pairs_u32(const uint32_t* kin, uint32_t* kout, const uint32_t* vin, uint32_t* vout, uint64_t n, int)
+{
+	std::vector<uint32_t> ord(n); for (uint64_t i = 0; i < n; ++i) ord[i] = (uint32_t)i;
+	std::stable_sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return kin[a] < kin[b]; });
+	for (uint64_t i = 0; i < n; ++i) { kout[i] = kin[ord[i]]; vout[i] = vin[ord[i]]; }
+}
 static void rt_fork_aux() {}
 static void rt_back_to_main() {}
 static void rt_join_aux(const char*) {}

@@ -80,3 +80,16 @@ def test_sim_repeat_family_stress():
     a = run_blob(oracle_lib(), img, blob, 2)
     b = run_blob(sim_lib(), img, blob, 2)
     assert a == b, first_diff(a, b, blob, True)
+
+
+@pytest.mark.parametrize("env", ["B200_TEST_TINY_GA_CAP", "B200_TEST_TINY_SEED_TASKS", "B200_TEST_TINY_SEED_POOL"])
+def test_sim_pool_overflows_fall_back(small_genome, monkeypatch, env):
+    """Capacity fall-backs: the alignment-task pool of the two-pass finalize (items that find it full are redone by a
+    warp; the task kernel must not run past the pool), the seed-task list and the seed-candidate pool (reads whose
+    scans do not fit are redone by the one-machine kernel).  None of them may fail the batch."""
+    g, img = small_genome
+    blob, _ = simdata.make_reads(g, 83, 300, 150, True, repeat_read_frac=0.3, chimeric_frac=0.1, err_rate=0.03, indel_frac=0.4)
+    a = run_blob(oracle_lib(), img, blob, 2)
+    monkeypatch.setenv(env, "1")
+    b = run_blob(sim_lib(), img, blob, 2)
+    assert a == b, first_diff(a, b, blob, True)

@@ -94,9 +94,9 @@ def test_engine_matches_oracle_mid(mid_genome, paired):
     assert a == b, first_diff(a, b, blob, paired)
 
 
-@pytest.mark.parametrize("env", [None, "B200_TEST_RESCUE_FALLBACK", "B200_TEST_TINY_SCRATCH", "B200_TEST_ALL_LIGHT", "B200_TEST_ALL_HEAVY", "B200_WARP_EXTEND", "B200_NO_EXT_TASKS", "B200_TEST_CHAIN_ALL_WARP", "B200_TEST_CHAIN_ALL_THREAD", "B200_FINAL_ONE_PASS", "B200_SEED_ONE_LAUNCH", "B200_SEED_FUSED_ROUNDS", "B200_TEST_TINY_SEED_POOL", "B200_TX_CHUNK=1", "B200_TX_CHUNK=0", "B200_EXT_WIDE_CELLS", "B200_SEED_NO_OVERLAP", "B200_CHAIN_NO_OVERLAP", "B200_TEST_FINAL_RING"],
+@pytest.mark.parametrize("env", [None, "B200_TEST_RESCUE_FALLBACK", "B200_TEST_TINY_SCRATCH", "B200_TEST_ALL_LIGHT", "B200_TEST_ALL_HEAVY", "B200_WARP_EXTEND", "B200_NO_EXT_TASKS", "B200_TEST_CHAIN_ALL_WARP", "B200_TEST_CHAIN_ALL_THREAD", "B200_FINAL_ONE_PASS", "B200_SEED_ONE_LAUNCH", "B200_SEED_FUSED_ROUNDS", "B200_TEST_TINY_SEED_POOL", "B200_TX_CHUNK=1", "B200_TX_CHUNK=0", "B200_EXT_WIDE_CELLS", "B200_SEED_NO_OVERLAP", "B200_CHAIN_NO_OVERLAP", "B200_TEST_FINAL_RING", "B200_TEST_TINY_GA_CAP", "B200_TEST_TINY_SEED_TASKS", "B200_EXT_LEGACY", "B200_EXT_NO_SORT"],
                          ids=["default", "rescue_fallback", "tiny_scratch", "extend_all_thread", "extend_all_tasks", "extend_all_warp", "extend_heavy_by_warp",
-                              "chain_all_warp", "chain_all_thread", "final_one_pass", "seed_one_launch", "seed_fused_rounds", "seed_pool_overflow", "extend_rows_cell_by_cell", "extend_whole_rows", "extend_wide_cells", "seed_no_stream_overlap", "chain_no_stream_overlap", "final_passes_with_ring_smem"])
+                              "chain_all_warp", "chain_all_thread", "final_one_pass", "seed_one_launch", "seed_fused_rounds", "seed_pool_overflow", "extend_rows_cell_by_cell", "extend_whole_rows", "extend_wide_cells", "seed_no_stream_overlap", "chain_no_stream_overlap", "final_passes_with_ring_smem", "alignment_task_pool_overflow", "seed_task_list_overflow", "extend_read_level_machine", "extend_tasks_unsorted"])
 def test_repeat_heavy_pairs_and_forced_slow_paths(small_genome, monkeypatch, env):
     """Chains of several rescuing hits per read (repeat-derived reads); the same batch with every rescuing read forced
     onto the round-by-round rescue kernels, with thread-level scratch so small that items are handed to warps, and with
@@ -170,7 +170,7 @@ def test_device_index_builder_matches_host_builder(tmp_path, monkeypatch, chunk)
 
 def test_concurrent_callers_and_two_indexes(small_genome, mid_genome):
     """The reference's usage: one shared BwaMemIndex, one BwaMemAligner per thread (BwaMemAligner.java:18); here also two
-    different indexes open at once.  Calls are serialised inside the library; every result must be the single-threaded one."""
+    different indexes open at once.  Callers overlap on the handle's contexts; every result must be the single-threaded one."""
     import threading
     g1, img1 = small_genome
     g2, img2 = mid_genome
@@ -202,3 +202,87 @@ def test_concurrent_callers_and_two_indexes(small_genome, mid_genome):
     for (tag, rep, i), out in got.items():
         assert out == (want2 if tag == "c" else want1)[i], (tag, rep, i)
     assert len(got) == 18
+
+
+def _pool_api():
+    import ctypes
+    dll = engine_lib().dll
+    dll.b200_contextCount.argtypes = [ctypes.c_void_p]
+    dll.b200_contextDevice.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    return dll
+
+
+def _fresh_thread(fn):
+    """Run fn on a new host thread (CUDA's current device is per thread: a fresh thread starts on device 0)."""
+    import threading
+    box = {}
+
+    def run():
+        try:
+            box["v"] = fn()
+        except BaseException as e:  # noqa: BLE001
+            box["e"] = e
+    t = threading.Thread(target=run)
+    t.start(); t.join()
+    if "e" in box:
+        raise box["e"]
+    return box["v"]
+
+
+def test_index_on_second_device_called_from_fresh_threads(small_genome, monkeypatch):
+    """The handle remembers its device: an index opened with BWA_B200_DEVICE=1 is used from threads whose current CUDA
+    device is 0 (every Spark task thread of the reference's deployment).  Needs two GPUs (gpurun --gpus 2)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 CUDA devices")
+    g, img = small_genome
+    blob, _ = simdata.make_reads(g, 55, 2000, 150, True)
+    want = run_blob(oracle_lib(), img, blob, 2)
+    monkeypatch.setenv("BWA_B200_DEVICE", "1")
+    idx = _fresh_thread(lambda: bwa.BwaMemIndex(img, lib=engine_lib()))
+    assert _pool_api().b200_contextDevice(idx._addr_as_void(), 0) == 1
+
+    def call():
+        al = bwa.BwaMemAligner(idx)
+        al.alignPairs()
+        out = idx.doAlignment(bytearray(blob), al._opts_addr, None)
+        al.close()
+        return out
+    for _ in range(3):
+        assert _fresh_thread(call) == want
+    idx.close()
+
+
+def test_device_pool_single_process(small_genome, monkeypatch):
+    """BWA_B200_DEVICES=all: one index replica per GPU inside one process (replicas 1.. are copied device to device),
+    calls from many threads spread over the pool; every result equals the single-GPU one."""
+    import threading
+    import torch
+    ndev = torch.cuda.device_count()
+    g, img = small_genome
+    blobs = [simdata.make_reads(g, 160 + i, 1500, 150, True)[0] for i in range(6)]
+    want = [run_blob(oracle_lib(), img, b, 2) for b in blobs]
+    monkeypatch.setenv("BWA_B200_DEVICES", "all")
+    monkeypatch.setenv("BWA_B200_CONTEXTS", "2")
+    idx = bwa.BwaMemIndex(img, lib=engine_lib())
+    dll = _pool_api()
+    assert dll.b200_contextCount(idx._addr_as_void()) == 2 * ndev
+    assert sorted({dll.b200_contextDevice(idx._addr_as_void(), i) for i in range(2 * ndev)}) == list(range(ndev))
+    got = {}
+
+    def worker(t):
+        al = bwa.BwaMemAligner(idx)
+        al.alignPairs()
+        for rep in range(2):
+            for i, b in enumerate(blobs):
+                got[(t, rep, i)] = idx.doAlignment(bytearray(b), al._opts_addr, None)
+        al.close()
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(2 * ndev + 1)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    idx.close()
+    assert len(got) == (2 * ndev + 1) * 12
+    for (t, rep, i), out in got.items():
+        assert out == want[i], (t, rep, i)
