@@ -159,6 +159,8 @@ static void rt_sort_u64(const uint64_t* in, uint64_t* out, uint64_t n)
 	if (!rt_scratch(need)) return;
 	cu_ok(cub::DeviceRadixSort::SortKeys(t_rt->scan_tmp, need, in, out, (int64_t)n, 0, 64, rt_stream()), "sort");
 }
+__global__ void k_iota_u32(u32* p, u64 n) { for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) p[i] = (u32)i; }
+static void rt_iota_u32(uint32_t* p, uint64_t n) { if (n) k_iota_u32<<<(unsigned)((n + 255) / 256 < 65535 ? (n + 255) / 256 : 65535), 256, 0, rt_stream()>>>(p, n); }
 // order u32 payloads by u32 keys (stable); used to bucket work items so that the lanes of a warp get similar ones
 static void rt_sort_pairs_u32(const uint32_t* kin, uint32_t* kout, const uint32_t* vin, uint32_t* vout, uint64_t n, int end_bit)
 {
@@ -263,6 +265,12 @@ DEF_THREAD_QUEUE_KERNEL(body_extend_task_q)
 DEF_THREAD_QUEUE_KERNEL_MB(body_extend_q8, 3)
 DEF_THREAD_QUEUE_KERNEL_MB(body_extend_task_q8, 4)
 DEF_WARP_KERNEL_DEVN(wbody_heavy_prep)
+DEF_THREAD_KERNEL(body_ext_prep)
+DEF_THREAD_QUEUE_KERNEL_MB(body_ext_left_q, 2)
+DEF_THREAD_QUEUE_KERNEL_MB(body_ext_right_q, 2)
+DEF_THREAD_QUEUE_KERNEL_MB(body_ext_left_q8, 4)
+DEF_THREAD_QUEUE_KERNEL_MB(body_ext_right_q8, 4)
+DEF_THREAD_TID_KERNEL(body_ext_replay)
 DEF_WARP_KERNEL_DEVN(wbody_extend_heavy)
 DEF_THREAD_KERNEL(body_save_regs)
 DEF_THREAD_TID_KERNEL(body_final_pe_t)

@@ -673,7 +673,36 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 			rw = fit * cell >= (size_t)4 * THREAD_RING_N ? (int)fit : 0; // (narrow cells never get here: their scores bound max_len by 255)
 		}
 		if (rw == 0) RT_WARPS(wbody_extend, P, (int64_t)n_reads);
-		else {
+		else if (!cfg.ext_legacy) {
+			// uniform side tasks (extend_thread.cuh): prep -> left sides -> right sides -> replay; see the comment there
+			P.t_ext_rw = rw;
+			const size_t ext_smem = thread_ext_smem_bytes(THREADS_PER_BLOCK, rw, wm_cap, cell);
+			const size_t Tn = (size_t)T + 1;
+			ok = b_exttask.ensure(Tn * sizeof(ExtTask)) && b_extres.ensure(Tn * sizeof(ExtRes)) && b_ckrmax.ensure(Tn * 16) && b_xtkey.ensure(Tn * 8) && b_xtkey2.ensure(Tn * 8) && b_xtidx.ensure(Tn * 4) && b_xtidx2.ensure(Tn * 8);
+			if (!ok) { last_error = "device allocation failed (extension tasks)"; return nullptr; }
+			P.ext_tasks = b_exttask.as<ExtTask>(); P.ext_res = b_extres.as<ExtRes>(); P.ck_rmax = b_ckrmax.as<i64>(); P.n_ext_tasks = b_misc.as<u32>() + 21;
+			P.ext_key_l = b_xtkey.as<u32>(); P.ext_key_r = b_xtkey.as<u32>() + Tn; P.ext_order_l = nullptr; P.ext_order_r = nullptr;
+			P.ext_sides = 1;
+			rt_memset(P.ext_res, 0, Tn * sizeof(ExtRes)); // valid = 0: "not extended ahead of time"
+			RT_THREADS(body_ext_prep, P, (int64_t)n_reads);
+			RT_WARPS_DEVN(wbody_heavy_prep, P, P.n_heavy, (int64_t)n_reads);
+			uint32_t n_t = 0;
+			rt_d2h(&n_t, P.n_ext_tasks, 4);
+			hp.mark("ext_prep_sync");
+			if (n_t && !cfg.ext_no_sort) { // order the tasks of each side by query length: the lanes of a warp then run rows of similar width
+				int bits = 1; while ((1 << bits) <= max_len && bits < 31) ++bits;
+				rt_iota_u32(b_xtidx.as<u32>(), n_t);
+				rt_sort_pairs_u32(P.ext_key_l, b_xtkey2.as<u32>(), b_xtidx.as<u32>(), b_xtidx2.as<u32>(), n_t, bits);
+				rt_sort_pairs_u32(P.ext_key_r, b_xtkey2.as<u32>() + Tn, b_xtidx.as<u32>(), b_xtidx2.as<u32>() + Tn, n_t, bits);
+				P.ext_order_l = b_xtidx2.as<u32>(); P.ext_order_r = b_xtidx2.as<u32>() + Tn;
+			}
+			if (narrow) { RT_THREADS_QUEUE_SMEM(body_ext_left_q8, P, (int64_t)n_t, ext_smem); RT_THREADS_QUEUE_SMEM(body_ext_right_q8, P, (int64_t)n_t, ext_smem); }
+			else { RT_THREADS_QUEUE_SMEM(body_ext_left_q, P, (int64_t)n_t, ext_smem); RT_THREADS_QUEUE_SMEM(body_ext_right_q, P, (int64_t)n_t, ext_smem); }
+			RT_THREADS_TID(body_ext_replay, P, (int64_t)n_reads);
+			P.use_ext_res = 1;
+			RT_WARPS_DEVN(wbody_extend_heavy, P, P.n_heavy, (int64_t)n_reads); // heavy reads, and light ones the replay could not finish
+			P.use_ext_res = 0;
+		} else {
 			P.t_ext_rw = rw;
 			const size_t ext_smem = thread_ext_smem_bytes(THREADS_PER_BLOCK, rw, wm_cap, cell), task_smem = ext_smem;
 			if (narrow) RT_THREADS_QUEUE_SMEM(body_extend_q8, P, (int64_t)n_reads, ext_smem);

@@ -257,7 +257,7 @@ DEVNI int warp_sort_dedup_patch(const DevIndex& x, const MemOpt& opt, WarpMem& w
 // mem_chain2aln for one chain; av[0..*n_av) accumulates the regions of the read
 template <int W>
 DEVNI void warp_chain2aln(const DevIndex& x, const MemOpt& opt, WarpMem& wm, WarpScratch& ws, Counters* cnt, int l_query, const u8* query,
-                          const ChainK& c, const Seed* seeds, u64* srt, Reg* av, int* n_av, int av_cap, const ExtRes* spec = nullptr)
+                          const ChainK& c, const Seed* seeds, u64* srt, Reg* av, int* n_av, int av_cap, const ExtRes* spec = nullptr, bool spec_only = false)
 {
 	LANE_DECL;
 	const i64 l_pac = x.l_pac;
@@ -331,6 +331,9 @@ DEVNI void warp_chain2aln(const DevIndex& x, const MemOpt& opt, WarpMem& wm, War
 		if (pre && pre->valid == 1) { // extended ahead of time by the task kernel (extend_thread.cuh)
 			a.rb = pre->rb; a.re = pre->re; a.qb = pre->qb; a.qe = pre->qe; a.score = pre->score; a.truesc = pre->truesc;
 			aw0 = aw1 = pre->w;
+		} else if (spec_only) { // the caller cannot extend (replay by a thread): the read goes to the warp kernel
+			ONE_LANE { atomic_or_u32(ws.err, ERR_NEED_WARP); }
+			return;
 		} else {
 		if (s.qbeg) { // left extension: both sequences reversed
 			FOR_LANES { for (int j = lane; j < s.qbeg; j += W) WQ(wm, j) = query[s.qbeg - 1 - j]; }

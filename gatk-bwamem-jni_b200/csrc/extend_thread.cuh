@@ -130,8 +130,8 @@ DEV void thread_extend_queue(const BatchParams& P, i64 n_reads, u32* counter, co
 				break; }
 			case TX_READ_DONE: { // region de-duplication / patching of the read, then the next read
 				int n2 = warp_sort_dedup_patch<1>(x, opt, wm, ws, cnt, query, n_av, av);
-				if (*lerr & ERR_NEED_WARP) { TX_TO_WARP(); break; } // recomputed from scratch by a warp
-				if (*lerr) atomic_or_u32(err, *lerr);
+				if (err_peek(lerr) & ERR_NEED_WARP) { TX_TO_WARP(); break; } // recomputed from scratch by a warp
+				if (err_peek(lerr)) atomic_or_u32(err, err_peek(lerr));
 				P.n_reg[r] = (u32)n2;
 				phase = TX_FETCH;
 				break; }
@@ -347,4 +347,202 @@ DEV void thread_extend_queue(const BatchParams& P, i64 n_reads, u32* counter, co
 	}
 #undef TX_TO_WARP
 	if (cnt) { if (cells) atomic_add_u64(&cnt->cells_ext, cells); if (n_ext) atomic_add_u64(&cnt->n_ext, n_ext); }
+}
+
+// =====================================================================================================================
+// Extension as UNIFORM SIDE TASKS (the production route; the read-level machine above is kept as the comparison route
+// behind B200_EXT_LEGACY).
+//
+// The read-level machine spends ~45 % of its instructions in per-read control flow executed by 1-3 lanes of a warp.
+// Here the stage is three kinds of launches with no state machine in any of them:
+//   prep    (thread per light read, warp per heavy read)  reference windows of the chains, seeds ordered by score, and
+//           one extension TASK per seed that bwa will certainly or probably extend: the best seed of every chain of a
+//           light read, every kept seed of a heavy read;
+//   sides   two launches, LEFT then RIGHT.  A task's left and right extensions are separate work items (the right one
+//           starts from the left one's score), each list ordered by its query length, and a warp takes 32 neighbours
+//           of that order at a time: its lanes run the plain nested loops of ksw_extend2 over rows of (nearly) the
+//           same width, so they stay converged through the inner loop and meet again at every row end;
+//   replay  (thread per light read, warp per heavy read)  mem_chain2aln's decision sequence -- containment tests, the
+//           "seed on another diagonal" exception, seed coverage -- consuming the finished extensions.  An extension the
+//           replay needs but nobody computed (a second seed of a chain that turns out not to be contained) sends the
+//           read to the warp kernel, which computes it itself.
+// Exactness: an extension's result does not depend on the hits found so far; only the decision to USE it does, and
+// that is replayed in the reference's order.
+
+template <class CELL>
+struct TxCell {
+	static constexpr int HB = (int)sizeof(CELL) * 4;
+	static constexpr u32 HMASK = (1u << HB) - 1u;
+	static constexpr i64 SCORE_CAP = sizeof(CELL) == 2 ? 255 : 60000;
+};
+
+// ksw_extend2 by one thread over its shared-memory row: the scalar recurrence verbatim, H and E of a
+// column in one CELL.  rd[j * QS] = query code of DP column j (already in DP orientation).
+template <class CELL>
+DEV void tx_extend2(const DevIndex& x, const MemOpt& opt, const ThreadExtMem& tm, int mx, int qlen, int tlen, i64 tbase, int tdir,
+                    int w, int end_bonus, int h0, ExtResult& res, u64& cells)
+{
+	constexpr int HB = TxCell<CELL>::HB; constexpr u32 HMASK = TxCell<CELL>::HMASK;
+	const int o_del = opt.o_del, e_del = opt.e_del, o_ins = opt.o_ins, e_ins = opt.e_ins;
+	const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins, zdrop = opt.zdrop;
+	const size_t RS = (size_t)tm.row_stride, QS = (size_t)tm.rd_stride;
+	CELL* const row = (CELL*)tm.row;
+	const i64 l_pac = x.l_pac;
+	{
+		CELL* rw = row;
+		rw[0] = (CELL)h0;
+		int v = h0 > oe_ins ? h0 - oe_ins : 0;
+		for (int j = 1; j <= qlen; ++j) { rw[(size_t)j * RS] = (CELL)v; v = v > e_ins ? v - e_ins : 0; }
+	}
+	// band clamp of ksw_extend2, int(double(x) / e + 1.) clamped to >= 1, in integers (see cal_max_gap)
+	const int xi_ = qlen * mx + end_bonus - o_ins, xd_ = qlen * mx + end_bonus - o_del;
+	int max_ins = xi_ >= 0 ? (e_ins == 1 ? xi_ + 1 : xi_ / e_ins + 1) : 0; max_ins = max_ins > 1 ? max_ins : 1;
+	w = w < max_ins ? w : max_ins;
+	int max_del = xd_ >= 0 ? (e_del == 1 ? xd_ + 1 : xd_ / e_del + 1) : 0; max_del = max_del > 1 ? max_del : 1;
+	w = w < max_del ? w : max_del;
+	int max = h0, max_i = -1, max_j = -1, max_ie = -1, gscore = -1, max_off = 0, beg = 0, end = qlen;
+	u32 pac_word = 0; i64 pac_widx = -1;
+	for (int i = 0; i < tlen; ++i) {
+		// target base of row i from the 2-bit packed reference (one 32-bit word holds 16 consecutive forward bases)
+		const i64 p = tbase + (i64)tdir * i;
+		const bool rv = p >= l_pac;
+		const i64 fp = rv ? (l_pac << 1) - 1 - p : p;
+		const i64 widx = fp >> 4;
+		if (widx != pac_widx) { pac_word = ldg((const u32*)x.pac + widx); pac_widx = widx; }
+		int tb = (int)((pac_word >> (8 * (int)((fp >> 2) & 3))) >> ((~fp & 3) << 1) & 3);
+		if (rv) tb = 3 - tb;
+		const u64 rp = tm.rowpack[tb];
+		if (beg < i - w) beg = i - w;
+		if (end > i + w + 1) end = i + w + 1;
+		if (end > qlen) end = qlen;
+		int f = 0, m = 0, mj = -1, h1;
+		if (beg == 0) { h1 = h0 - (o_del + e_del * (i + 1)); if (h1 < 0) h1 = 0; } else h1 = 0;
+		if (end > beg) cells += (u64)(end - beg);
+		{
+			CELL* rw = row + (size_t)beg * RS;
+			const u8* qp = tm.rd + (size_t)beg * QS;
+#pragma unroll 4
+			for (int j = beg; j < end; ++j) {
+				const u32 he = (u32)*rw;
+				int M = (int)(he & HMASK), e = (int)(he >> HB);
+				const int sc = (int)(i8)(rp >> (8 * (int)*qp));
+				M = M ? M + sc : 0;
+				int h = M > e ? M : e;
+				h = h > f ? h : f;
+				mj = m > h ? mj : j;
+				m = m > h ? m : h;
+				int t = M - oe_del; t = t > 0 ? t : 0;
+				e -= e_del; e = e > t ? e : t;
+				*rw = (CELL)((u32)h1 | (u32)e << HB);
+				h1 = h;
+				t = M - oe_ins; t = t > 0 ? t : 0;
+				f -= e_ins; f = f > t ? f : t;
+				rw += RS; qp += QS;
+			}
+		}
+		row[(size_t)end * RS] = (CELL)h1; // H[end] = h1, E[end] = 0
+		const int jfin = beg < end ? end : beg;
+		if (jfin == qlen) { max_ie = gscore > h1 ? max_ie : i; gscore = gscore > h1 ? gscore : h1; }
+		if (m == 0) break;
+		if (m > max) { max = m; max_i = i; max_j = mj; int off = iabs(mj - i); max_off = max_off > off ? max_off : off; }
+		else if (zdrop > 0) {
+			if (i - max_i > mj - max_j) { if (max - m - ((i - max_i) - (mj - max_j)) * e_del > zdrop) break; }
+			else { if (max - m - ((mj - max_j) - (i - max_i)) * e_ins > zdrop) break; }
+		}
+		// shrink [beg, end) to the cells that can still score (leading / trailing zeros of the row)
+		int jb = beg; const CELL* pb = row + (size_t)beg * RS;
+		while (jb < end && *pb == 0) { ++jb; pb += RS; }
+		beg = jb;
+		int je = end; const CELL* pe = row + (size_t)end * RS;
+		while (je >= jb && *pe == 0) { --je; pe -= RS; }
+		end = je + 2 < qlen ? je + 2 : qlen;
+	}
+	res.score = max; res.qle = max_j + 1; res.tle = max_i + 1; res.gtle = max_ie + 1; res.gscore = gscore; res.max_off = max_off;
+}
+
+// One launch = one side (0 left, 1 right) of every task.  `order` lists task indices by ascending query length of that
+// side; warps take 32 neighbours at a time from the long end (longest jobs first).
+template <int SIDE, class CELL>
+DEV void thread_extend_sides(const BatchParams& P, u32* counter, const ThreadExtMem& tm)
+{
+	const DevIndex& x = P.x; const MemOpt& opt = P.opt;
+	const i64 n = (i64)*P.n_ext_tasks;
+	const u32* order = SIDE == 0 ? P.ext_order_l : P.ext_order_r;
+	int mx = 0;
+	for (int k = 0; k < 25; ++k) mx = mx > opt.mat[k] ? mx : (int)opt.mat[k];
+	const size_t QS = (size_t)tm.rd_stride;
+	const int lane = simt_lane();
+	u64 cells = 0, n_ext = 0;
+	for (;;) {
+		u32 base = 0;
+		if (lane == 0) base = atomic_add_u32(counter, (u32)SIMT_GROUP);
+		base = lane_bcast0(base);
+		if ((i64)base >= n) break;
+		const i64 pos = n - 1 - ((i64)base + lane);
+		if (pos >= 0) {
+			const u32 ti = order ? order[pos] : (u32)pos;
+			const ExtTask tk = P.ext_tasks[ti];
+			const i64 r = (i64)tk.r;
+			const u64 t0 = P.seed_off[r];
+			const ChainK ck = P.ck[t0 + tk.c];
+			const u64 slot = t0 + ck.seed_start + tk.t;
+			const Seed s = P.ks[slot];
+			const int l_query = (int)(P.seq_off[r + 1] - P.seq_off[r] - 1);
+			const u8* query = P.seq + P.seq_off[r];
+			ExtRes o = P.ext_res[slot];
+			const int qlen = SIDE == 0 ? s.qbeg : l_query - (s.qbeg + s.len);
+			// 8-/16-bit storage bound: no H/E value exceeds (seed + left + right) scores <= l_query * mx, plus the clip bonus
+			const bool fits = qlen + 1 <= tm.row_cap && qlen <= tm.rd_cap && (i64)(sizeof(CELL) == 2 ? 1 : 2) * l_query * mx + opt.pen_clip5 + opt.pen_clip3 <= TxCell<CELL>::SCORE_CAP;
+			if (SIDE == 0) {
+				if (qlen == 0) { o.score = o.truesc = s.len * opt.a; o.qb = 0; o.rb = s.rbeg; o.w = opt.w; o.valid = 2; }
+				else if (!fits) o.valid = 0; // the replay extends this seed itself
+				else {
+					for (int j = 0; j < qlen; ++j) tm.rd[(size_t)j * QS] = query[s.qbeg - 1 - j]; // both sequences walked backwards
+					const int tlen = (int)(s.rbeg - P.ck_rmax[2 * (t0 + tk.c)]);
+					ExtResult er; er.score = -1; er.qle = er.tle = er.gtle = 0; er.gscore = -1; er.max_off = 0;
+					int score = -1, aw = opt.w;
+					for (int tr = 0; tr < 2; ++tr) {
+						const int prev = score;
+						aw = opt.w << tr;
+						if (tlen > 0) tx_extend2<CELL>(x, opt, tm, mx, qlen, tlen, s.rbeg - 1, -1, aw, opt.pen_clip5, s.len * opt.a, er, cells);
+						else { er.score = s.len * opt.a; er.qle = er.tle = er.gtle = 0; er.gscore = -1; er.max_off = 0; }
+						++n_ext;
+						score = er.score;
+						if (score == prev || er.max_off < (aw >> 1) + (aw >> 2)) break;
+					}
+					o.score = score;
+					if (er.gscore <= 0 || er.gscore <= score - opt.pen_clip5) { o.qb = s.qbeg - er.qle; o.rb = s.rbeg - er.tle; o.truesc = score; }
+					else { o.qb = 0; o.rb = s.rbeg - er.gtle; o.truesc = er.gscore; }
+					o.w = aw; o.valid = 2;
+				}
+			} else if (o.valid == 2) { // (0: the left side was refused)
+				const int qe = s.qbeg + s.len; const i64 re = s.rbeg + s.len;
+				if (qlen == 0) { o.qe = l_query; o.re = re; o.valid = 1; }
+				else if (!fits) o.valid = 0;
+				else {
+					for (int j = 0; j < qlen; ++j) tm.rd[(size_t)j * QS] = query[qe + j];
+					const int tlen = (int)(P.ck_rmax[2 * (t0 + tk.c) + 1] - re);
+					const int sc0 = o.score;
+					ExtResult er; er.score = -1; er.qle = er.tle = er.gtle = 0; er.gscore = -1; er.max_off = 0;
+					int score = sc0, aw = opt.w;
+					for (int tr = 0; tr < 2; ++tr) {
+						const int prev = score;
+						aw = opt.w << tr;
+						if (tlen > 0) tx_extend2<CELL>(x, opt, tm, mx, qlen, tlen, re, 1, aw, opt.pen_clip3, sc0, er, cells);
+						else { er.score = sc0; er.qle = er.tle = er.gtle = 0; er.gscore = -1; er.max_off = 0; }
+						++n_ext;
+						score = er.score;
+						if (score == prev || er.max_off < (aw >> 1) + (aw >> 2)) break;
+					}
+					if (er.gscore <= 0 || er.gscore <= score - opt.pen_clip3) { o.qe = qe + er.qle; o.re = re + er.tle; o.truesc += score - sc0; }
+					else { o.qe = l_query; o.re = re + er.gtle; o.truesc += er.gscore - sc0; }
+					o.score = score;
+					o.w = o.w > aw ? o.w : aw; o.valid = 1;
+				}
+			}
+			P.ext_res[slot] = o;
+		}
+		warp_converge();
+	}
+	if (P.cnt) { if (cells) atomic_add_u64(&P.cnt->cells_ext, cells); if (n_ext) atomic_add_u64(&P.cnt->n_ext, n_ext); }
 }

@@ -486,6 +486,18 @@ extern "C" int jnibwa_createReferenceIndex(const char* refFileName, const char* 
 	return write_index_files(ref, fm, indexPrefix) ? 0 : 2;
 }
 
+// bwa_idx_build (un-vendored lh3/bwa bwtindex.c) as the reference's own JNI glue calls it: ...BwaMemIndex.c:59
+// `bwa_idx_build(reference_file_name, index_prefix, algo_type, -1)` with algo_type 0 = auto, 1 = rb2, 3 = is (:50-52).
+// Exported so that the reference's unmodified glue links against this library (option A).  Returns 0
+// on success like bwa's; block_size only tunes bwa's own construction and has no meaning here.
+extern "C" int bwa_idx_build(const char* fa, const char* prefix, int algo_type, int block_size)
+{
+	(void)block_size;
+	const char* name = algo_type == 0 ? "auto" : algo_type == 1 ? "rb2" : algo_type == 3 ? "is" : nullptr;
+	if (!name || !fa || !prefix) return 1;
+	return jnibwa_createReferenceIndex(fa, prefix, name) == 0 ? 0 : 1;
+}
+
 // Build an image straight from base codes held in memory (used by the synthetic-genome tools and bench.py).
 // names: n NUL-terminated strings back to back; bases: ASCII, contigs concatenated; lens[n].
 extern "C" int b200_buildImageFromBases(int n_contigs, const char* names, const int64_t* lens, const char* bases, const char* imgName, const char* prefixOrNull)

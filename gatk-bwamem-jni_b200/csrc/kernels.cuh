@@ -55,7 +55,9 @@ struct BatchParams {
 	u32* redo_list; u32* n_redo; // items a thread-level kernel handed over to the warp-level kernel
 	u32* heavy_list; u32* n_heavy; int light_max_seeds, light_max_chains; // extension: reads with many seeds go to the warp-level kernel
 	int tx_chunk;                           // thread-level extension: cells of one DP row per visit of the row site
-	ExtTask* ext_tasks; u32* n_ext_tasks; ExtRes* ext_res; i64* ck_rmax; // heavy reads: per-seed extension tasks, results, per-chain windows
+	ExtTask* ext_tasks; u32* n_ext_tasks; ExtRes* ext_res; i64* ck_rmax; // per-seed extension tasks, results, per-chain windows
+	u32* ext_key_l; u32* ext_key_r; const u32* ext_order_l; const u32* ext_order_r; // query length of a task's left / right side; task indices ordered by it (nullptr: unordered)
+	int ext_sides;          // the side-task route (extend_thread.cuh thread_extend_sides) is in use: tasks carry keys
 	u32* chain_heavy; u32* n_chain_heavy; int chain_heavy_seeds; // reads chained by a warp
 	int chain_listed;       // the list of those reads was written beforehand (body_chain_classify): body_chain only skips them
 	GaTask* ga_tasks; GaRes* ga_res; u32* n_ga_tasks; u32 ga_cap; u32* ga_item0; u32* ga_itemn; // two-pass finalize (galign_thread.cuh)
@@ -418,6 +420,7 @@ DEV void wbody_final_pe(const BatchParams& P, i64 pr, WarpMem& wm, WarpScratch& 
 HOSTDEV size_t thread_scratch_bytes(int wm_cap, int z_cap, int cigar_cap, int md_cap, int xa_cap)
 {
 	size_t n = (size_t)(2 * (wm_cap + 2)) * 4 + (size_t)((wm_cap + 2 + 15) & ~15) + (size_t)((z_cap + 15) & ~15) + (size_t)cigar_cap * 4 + (size_t)((md_cap + 15) & ~15) + (size_t)((xa_cap + 15) & ~15);
+	n += 16; // the thread's error word (thread_err_word)
 	return (n + 127) & ~(size_t)127;
 }
 #ifdef B200_SIM
@@ -425,7 +428,11 @@ static i32 g_sim_ring[2 * THREAD_RING_N];
 #endif
 // shared memory of a thread-level block: two rings of THREAD_RING_N i32 per thread
 HOSTDEV size_t thread_block_smem_bytes(int block_threads, int wm_cap) { return (size_t)block_threads * (THREAD_RING_N * 2 * 4 + (size_t)((wm_cap + 2 + 3) & ~3)); }
-DEV void make_thread_ctx(const BatchParams& P, i64 tid, WarpMem& wm, WarpScratch& ws, u32* lerr)
+// Limit flags raised by a thread-level item ("redo me with the warp-level scratch") are collected in a word of the
+// thread's GLOBAL scratch, not in a local variable: the device functions raise flags with atomicOr through a generic
+// pointer, and an atomic on an address in the local window is an illegal access when it is not inlined away.
+DEV u32* thread_err_word(const BatchParams& P, i64 tid) { return (u32*)(P.t_buf + (size_t)(tid + 1) * P.t_stride - 16); }
+DEV void make_thread_ctx(const BatchParams& P, i64 tid, WarpMem& wm, WarpScratch& ws, u32* lerr, bool shared_rings = true)
 {
 	const int cap = P.wm_cap;
 	u8* b = P.t_buf + (size_t)tid * P.t_stride;
@@ -434,10 +441,11 @@ DEV void make_thread_ctx(const BatchParams& P, i64 tid, WarpMem& wm, WarpScratch
 	b += (size_t)(2 * (cap + 2)) * 4;
 	wm.q = b; wm.q_stride = 1; b += (cap + 2 + 15) & ~15;
 	wm.cap = cap;
+	wm.ringH = nullptr; wm.ringE = nullptr; wm.ring_n = 0; wm.ring_stride = 0;
 #ifdef B200_SIM
-	wm.ringH = g_sim_ring; wm.ringE = g_sim_ring + THREAD_RING_N; wm.ring_n = THREAD_RING_N; wm.ring_stride = 1;
+	if (shared_rings) { wm.ringH = g_sim_ring; wm.ringE = g_sim_ring + THREAD_RING_N; wm.ring_n = THREAD_RING_N; wm.ring_stride = 1; }
 #else
-	{
+	if (shared_rings) { // (kernels launched without dynamic shared memory keep the rows and the query in the thread's global scratch)
 		extern __shared__ __align__(16) u8 tsm_[];
 		i32* r = (i32*)tsm_;
 		wm.ringH = r + threadIdx.x; wm.ringE = r + (size_t)blockDim.x * THREAD_RING_N + threadIdx.x;
@@ -515,16 +523,16 @@ DEV void make_thread_ext_ctx(const BatchParams& P, i64 tid, ThreadExtMem& tm, Wa
 }
 DEV void body_extend_q(const BatchParams& P, i64 n, u32* counter, i64 tid)
 {
-	u32 lerr = 0;
-	ThreadExtMem tm; WarpMem wm; WarpScratch ws; make_thread_ext_ctx<u32>(P, tid, tm, wm, ws, &lerr, true);
-	thread_extend_queue<false, u32>(P, n, counter, tm, wm, ws, &lerr);
+	u32* const lerr = thread_err_word(P, tid); *lerr = 0;
+	ThreadExtMem tm; WarpMem wm; WarpScratch ws; make_thread_ext_ctx<u32>(P, tid, tm, wm, ws, lerr, true);
+	thread_extend_queue<false, u32>(P, n, counter, tm, wm, ws, lerr);
 }
 // the same with 8-bit H and E (batches whose scores cannot exceed 255: half the shared memory per thread, more warps per SM)
 DEV void body_extend_q8(const BatchParams& P, i64 n, u32* counter, i64 tid)
 {
-	u32 lerr = 0;
-	ThreadExtMem tm; WarpMem wm; WarpScratch ws; make_thread_ext_ctx<u16>(P, tid, tm, wm, ws, &lerr, true);
-	thread_extend_queue<false, u16>(P, n, counter, tm, wm, ws, &lerr);
+	u32* const lerr = thread_err_word(P, tid); *lerr = 0;
+	ThreadExtMem tm; WarpMem wm; WarpScratch ws; make_thread_ext_ctx<u16>(P, tid, tm, wm, ws, lerr, true);
+	thread_extend_queue<false, u16>(P, n, counter, tm, wm, ws, lerr);
 }
 // heavy reads, step 1 (warp per read): the reference window of every chain and one extension task per kept seed
 template <int W>
@@ -557,24 +565,97 @@ DEV void wbody_heavy_prep(const BatchParams& P, i64 item, WarpMem& wm, WarpScrat
 			ref_clip_window(P.x, rmax0, seeds[0].rbeg, rmax1);
 			P.ck_rmax[2 * (t0 + c)] = rmax0; P.ck_rmax[2 * (t0 + c) + 1] = rmax1;
 			const u32 base = atomic_add_u32(P.n_ext_tasks, (u32)cn);
-			for (int t = 0; t < cn; ++t) { ExtTask tk; tk.r = (u32)r; tk.c = (u32)c; tk.t = (u32)t; tk.pad_ = 0; P.ext_tasks[base + t] = tk; }
+			for (int t = 0; t < cn; ++t) {
+				ExtTask tk; tk.r = (u32)r; tk.c = (u32)c; tk.t = (u32)t; tk.pad_ = 0; P.ext_tasks[base + t] = tk;
+				if (P.ext_sides) { P.ext_key_l[base + t] = (u32)seeds[t].qbeg; P.ext_key_r[base + t] = (u32)(l_query - seeds[t].qbeg - seeds[t].len); }
+			}
 		}
 	}
+}
+// light reads (thread per read): the reference window of every chain and ONE task per chain, its best-scoring seed --
+// the first one mem_chain2aln visits.  Further seeds of a chain are almost always contained in that seed's region; the
+// replay sends the read to the warp kernel when one is not.  Reads with many seeds or chains go on the heavy list.
+DEV void body_ext_prep(const BatchParams& P, i64 r)
+{
+	const int nck = (int)P.n_ck[r], nks = (int)P.n_ks[r];
+	if (nck == 0) { P.n_reg[r] = 0; return; }
+	if (nks > P.light_max_seeds || nck > P.light_max_chains) { const u32 slot = atomic_add_u32(P.n_heavy, 1u); P.heavy_list[slot] = (u32)r; return; }
+	const u64 t0 = P.seed_off[r];
+	const int l_query = (int)(P.seq_off[r + 1] - P.seq_off[r] - 1);
+	const i64 l_pac = P.x.l_pac;
+	int n_t = 0;
+	for (int c = 0; c < nck; ++c) if (P.ck[t0 + c].n_seeds) ++n_t;
+	u32 base = n_t ? atomic_add_u32(P.n_ext_tasks, (u32)n_t) : 0u;
+	for (int c = 0; c < nck; ++c) {
+		const ChainK ck = P.ck[t0 + c];
+		const int cn = (int)ck.n_seeds;
+		if (cn == 0) continue;
+		const Seed* seeds = P.ks + t0 + ck.seed_start;
+		i64 rmax0 = l_pac << 1, rmax1 = 0;
+		int best = 0; u64 best_key = 0;
+		for (int t = 0; t < cn; ++t) {
+			const Seed& sd = seeds[t];
+			i64 b = sd.rbeg - (sd.qbeg + cal_max_gap(P.opt, sd.qbeg));
+			i64 e = sd.rbeg + sd.len + ((l_query - sd.qbeg - sd.len) + cal_max_gap(P.opt, l_query - sd.qbeg - sd.len));
+			rmax0 = rmax0 < b ? rmax0 : b;
+			rmax1 = rmax1 > e ? rmax1 : e;
+			const u64 key = (u64)(u32)sd.score << 32 | (u32)t; // mem_chain2aln visits the seeds by descending (score, index)
+			if (key >= best_key) { best_key = key; best = t; }
+		}
+		rmax0 = rmax0 > 0 ? rmax0 : 0;
+		rmax1 = rmax1 < l_pac << 1 ? rmax1 : l_pac << 1;
+		if (rmax0 < l_pac && l_pac < rmax1) { if (seeds[0].rbeg < l_pac) rmax1 = l_pac; else rmax0 = l_pac; }
+		ref_clip_window(P.x, rmax0, seeds[0].rbeg, rmax1);
+		P.ck_rmax[2 * (t0 + c)] = rmax0; P.ck_rmax[2 * (t0 + c) + 1] = rmax1;
+		ExtTask tk; tk.r = (u32)r; tk.c = (u32)c; tk.t = (u32)best; tk.pad_ = 0;
+		P.ext_tasks[base] = tk;
+		P.ext_key_l[base] = (u32)seeds[best].qbeg; P.ext_key_r[base] = (u32)(l_query - seeds[best].qbeg - seeds[best].len);
+		++base;
+	}
+}
+// the two side launches (extend_thread.cuh): left, then right
+DEV void body_ext_left_q(const BatchParams& P, i64 n, u32* counter, i64 tid) { (void)n; u32* const lerr = thread_err_word(P, tid); *lerr = 0; ThreadExtMem tm; WarpMem wm; WarpScratch ws; make_thread_ext_ctx<u32>(P, tid, tm, wm, ws, lerr, false); thread_extend_sides<0, u32>(P, counter, tm); }
+DEV void body_ext_right_q(const BatchParams& P, i64 n, u32* counter, i64 tid) { (void)n; u32* const lerr = thread_err_word(P, tid); *lerr = 0; ThreadExtMem tm; WarpMem wm; WarpScratch ws; make_thread_ext_ctx<u32>(P, tid, tm, wm, ws, lerr, false); thread_extend_sides<1, u32>(P, counter, tm); }
+DEV void body_ext_left_q8(const BatchParams& P, i64 n, u32* counter, i64 tid) { (void)n; u32* const lerr = thread_err_word(P, tid); *lerr = 0; ThreadExtMem tm; WarpMem wm; WarpScratch ws; make_thread_ext_ctx<u16>(P, tid, tm, wm, ws, lerr, false); thread_extend_sides<0, u16>(P, counter, tm); }
+DEV void body_ext_right_q8(const BatchParams& P, i64 n, u32* counter, i64 tid) { (void)n; u32* const lerr = thread_err_word(P, tid); *lerr = 0; ThreadExtMem tm; WarpMem wm; WarpScratch ws; make_thread_ext_ctx<u16>(P, tid, tm, wm, ws, lerr, false); thread_extend_sides<1, u16>(P, counter, tm); }
+// replay of the light reads (thread per read): mem_chain2aln's decisions over the finished extensions, then region
+// de-duplication.  A missing extension, or a patching alignment beyond the thread-level rows, hands the read to the
+// warp kernel (heavy list), which redoes it from the chains.
+DEV void body_ext_replay(const BatchParams& P, i64 r, i64 tid)
+{
+	const int nck = (int)P.n_ck[r], nks = (int)P.n_ks[r];
+	if (nck == 0 || nks > P.light_max_seeds || nck > P.light_max_chains) return; // nothing to do / a heavy read
+	u32* const lerr = thread_err_word(P, tid); *lerr = 0;
+	WarpMem wm; WarpScratch ws; make_thread_ctx(P, tid, wm, ws, lerr, false);
+	const u64 t0 = P.seed_off[r];
+	const int len = (int)(P.seq_off[r + 1] - P.seq_off[r] - 1);
+	const u8* seq = P.seq + P.seq_off[r];
+	int n_av = 0; const int av_cap = nks;
+	Reg* av = P.regs_tmp + t0;
+	for (int c = 0; c < nck && !err_peek(lerr); ++c) {
+		const ChainK ck = P.ck[t0 + c];
+		warp_chain2aln<1>(P.x, P.opt, wm, ws, P.cnt, len, seq, ck, P.ks + t0 + ck.seed_start, P.srt + t0, av, &n_av, av_cap, P.ext_res + t0 + ck.seed_start, true);
+	}
+	int n2 = 0;
+	if (!err_peek(lerr)) n2 = warp_sort_dedup_patch<1>(P.x, P.opt, wm, ws, P.cnt, seq, n_av, av);
+	if (err_peek(lerr) & ERR_NEED_WARP) { const u32 slot = atomic_add_u32(P.n_heavy, 1u); P.heavy_list[slot] = (u32)r; return; }
+	if (err_peek(lerr)) atomic_or_u32(P.err, err_peek(lerr));
+	P.n_reg[r] = (u32)n2;
 }
 // heavy reads, step 2 (queue of single-seed tasks, thread-level DP)
 DEV void body_extend_task_q(const BatchParams& P, i64 n, u32* counter, i64 tid)
 {
 	(void)n;
-	u32 lerr = 0;
-	ThreadExtMem tm; WarpMem wm; WarpScratch ws; make_thread_ext_ctx<u32>(P, tid, tm, wm, ws, &lerr, false);
-	thread_extend_queue<true, u32>(P, (i64)*P.n_ext_tasks, counter, tm, wm, ws, &lerr);
+	u32* const lerr = thread_err_word(P, tid); *lerr = 0;
+	ThreadExtMem tm; WarpMem wm; WarpScratch ws; make_thread_ext_ctx<u32>(P, tid, tm, wm, ws, lerr, false);
+	thread_extend_queue<true, u32>(P, (i64)*P.n_ext_tasks, counter, tm, wm, ws, lerr);
 }
 DEV void body_extend_task_q8(const BatchParams& P, i64 n, u32* counter, i64 tid)
 {
 	(void)n;
-	u32 lerr = 0;
-	ThreadExtMem tm; WarpMem wm; WarpScratch ws; make_thread_ext_ctx<u16>(P, tid, tm, wm, ws, &lerr, false);
-	thread_extend_queue<true, u16>(P, (i64)*P.n_ext_tasks, counter, tm, wm, ws, &lerr);
+	u32* const lerr = thread_err_word(P, tid); *lerr = 0;
+	ThreadExtMem tm; WarpMem wm; WarpScratch ws; make_thread_ext_ctx<u16>(P, tid, tm, wm, ws, lerr, false);
+	thread_extend_queue<true, u16>(P, (i64)*P.n_ext_tasks, counter, tm, wm, ws, lerr);
 }
 template <int W>
 DEV void wbody_extend_heavy(const BatchParams& P, i64 item, WarpMem& wm, WarpScratch& ws) { wbody_extend<W>(P, (i64)P.heavy_list[item], wm, ws); }
@@ -593,23 +674,23 @@ DEV void restore_regs(const BatchParams& P, i64 r, int lane, int W)
 }
 DEV void body_final_pe_t(const BatchParams& P, i64 pr, i64 tid)
 {
-	u32 lerr = 0;
-	WarpMem wm; WarpScratch ws; make_thread_ctx(P, tid, wm, ws, &lerr);
+	u32* const lerr = thread_err_word(P, tid); *lerr = 0;
+	WarpMem wm; WarpScratch ws; make_thread_ctx(P, tid, wm, ws, lerr);
 	wbody_final_pe<1>(P, pr, wm, ws);
-	if (lerr) { u32 slot = atomic_add_u32(P.n_redo, 1u); P.redo_list[slot] = (u32)pr; }
+	if (err_peek(lerr)) { u32 slot = atomic_add_u32(P.n_redo, 1u); P.redo_list[slot] = (u32)pr; }
 }
 DEV void body_final_se_t(const BatchParams& P, i64 r, i64 tid)
 {
-	u32 lerr = 0;
-	WarpMem wm; WarpScratch ws; make_thread_ctx(P, tid, wm, ws, &lerr);
+	u32* const lerr = thread_err_word(P, tid); *lerr = 0;
+	WarpMem wm; WarpScratch ws; make_thread_ctx(P, tid, wm, ws, lerr);
 	wbody_final_se<1>(P, r, wm, ws);
-	if (lerr) { u32 slot = atomic_add_u32(P.n_redo, 1u); P.redo_list[slot] = (u32)r; }
+	if (err_peek(lerr)) { u32 slot = atomic_add_u32(P.n_redo, 1u); P.redo_list[slot] = (u32)r; }
 }
 // ---- two-pass finalize (galign_thread.cuh): collect the alignment requests of an item, later consume their results
 DEV void final_collect_item(const BatchParams& P, i64 item, i64 tid, bool pe)
 {
-	u32 sink = 0; // limits hit while collecting are not real: no alignment has been computed yet
-	WarpMem wm; WarpScratch ws; make_thread_ctx(P, tid, wm, ws, &sink);
+	u32* const sink = thread_err_word(P, tid); *sink = 0; // limits hit while collecting are not real: no alignment has been computed yet
+	WarpMem wm; WarpScratch ws; make_thread_ctx(P, tid, wm, ws, sink);
 	GaTask lt[GA_ITEM_MAX];
 	FinalMode fm; fm.mode = FIN_COLLECT; fm.lt = lt; fm.lt_n = 0; fm.res = nullptr; fm.res_n = 0; fm.res_k = 0;
 	if (pe) wbody_final_pe<1>(P, item, wm, ws, &fm); else wbody_final_se<1>(P, item, wm, ws, &fm);
@@ -632,11 +713,11 @@ DEV void final_consume_item(const BatchParams& P, i64 item, i64 tid, bool pe)
 	const u32 n = P.ga_itemn[item];
 	bool redo = n == 0xffffffffu;
 	if (!redo) {
-		u32 lerr = 0;
-		WarpMem wm; WarpScratch ws; make_thread_ctx(P, tid, wm, ws, &lerr);
+		u32* const lerr = thread_err_word(P, tid); *lerr = 0;
+		WarpMem wm; WarpScratch ws; make_thread_ctx(P, tid, wm, ws, lerr);
 		FinalMode fm; fm.mode = FIN_CONSUME; fm.lt = nullptr; fm.lt_n = 0; fm.res = P.ga_res + P.ga_item0[item]; fm.res_n = (int)n; fm.res_k = 0;
 		if (pe) wbody_final_pe<1>(P, item, wm, ws, &fm); else wbody_final_se<1>(P, item, wm, ws, &fm);
-		redo = lerr != 0 || fm.res_k != (int)n;
+		redo = err_peek(lerr) != 0 || fm.res_k != (int)n;
 	}
 	if (redo) { u32 slot = atomic_add_u32(P.n_redo, 1u); P.redo_list[slot] = (u32)item; }
 }
@@ -649,8 +730,8 @@ HOSTDEV size_t galign_block_smem_bytes(int block_threads, int wm_cap) { return (
 DEV void body_galign_task_q(const BatchParams& P, i64 n, u32* counter, i64 tid)
 {
 	(void)n;
-	u32 lerr = 0;
-	WarpMem wm; WarpScratch ws; make_thread_ctx(P, tid, wm, ws, &lerr);
+	u32* const lerr = thread_err_word(P, tid); *lerr = 0;
+	WarpMem wm; WarpScratch ws; make_thread_ctx(P, tid, wm, ws, lerr);
 #ifndef B200_SIM
 	{
 		extern __shared__ __align__(16) u8 tsm_[];
@@ -659,7 +740,7 @@ DEV void body_galign_task_q(const BatchParams& P, i64 n, u32* counter, i64 tid)
 	}
 #endif
 	const u32 n_res = *P.n_ga_tasks; // (reservations may have run past the pool: final_collect_item)
-	thread_galign_queue(P, (i64)(n_res < P.ga_cap ? n_res : P.ga_cap), counter, wm, ws, &lerr);
+	thread_galign_queue(P, (i64)(n_res < P.ga_cap ? n_res : P.ga_cap), counter, wm, ws, lerr);
 }
 template <int W>
 DEV void wbody_final_pe_redo(const BatchParams& P, i64 item, WarpMem& wm, WarpScratch& ws)

@@ -64,6 +64,12 @@ template <int W> DEV i64 wv_reduce_min64_(const i64& v) { i64 r = v; if (W == 32
 #define wv_reduce_min64(v) wv_reduce_min64_<W>(v)
 // full-mask vote of a thread-per-item kernel whose 32 lanes all take part (persistent queue kernels)
 DEV bool lanes_all(bool p) { return __all_sync(FULLMASK, p) != 0; }
+// thread-per-item kernels that hand out work to a whole warp at a time: lanes per hand-out, this thread's lane, a
+// broadcast of lane 0's value and the point where the lanes meet again
+#define SIMT_GROUP 32
+DEV int simt_lane() { return (int)(threadIdx.x & 31); }
+DEV u32 lane_bcast0(u32 v) { return __shfl_sync(FULLMASK, v, 0); }
+DEV void warp_converge() { __syncwarp(); }
 DEV u64 atomic_add_u64(u64* p, u64 v) { return (u64)atomicAdd((unsigned long long*)p, (unsigned long long)v); }
 DEV u32 atomic_add_u32(u32* p, u32 v) { return atomicAdd(p, v); }
 DEV u32 atomic_or_u32(u32* p, u32 v) { return atomicOr(p, v); }
@@ -106,6 +112,10 @@ template <int W> DEV int wv_reduce_add_(const int (&v)[32]) { int m = 0; for (in
 #define wv_ballot(p) wv_ballot_<W>(p)
 #define wv_get(v, l) wv_get_<W>(v, l)
 DEV bool lanes_all(bool p) { return p; } // the harness runs one thread at a time
+#define SIMT_GROUP 1
+DEV int simt_lane() { return 0; }
+DEV u32 lane_bcast0(u32 v) { return v; }
+DEV void warp_converge() {}
 DEV u64 atomic_add_u64(u64* p, u64 v) { u64 o = *p; *p += v; return o; }
 DEV u32 atomic_add_u32(u32* p, u32 v) { u32 o = *p; *p += v; return o; }
 DEV u32 atomic_or_u32(u32* p, u32 v) { u32 o = *p; *p |= v; return o; }
@@ -124,6 +134,8 @@ extern __device__ volatile unsigned* g_ckpt;
 #define DBGP(code, val) do {} while (0)
 #endif
 
+// read of a flag word that this thread's own atomics may have changed (bypasses the non-coherent L1)
+DEV u32 err_peek(const u32* p) { return *(const volatile u32*)p; }
 template <class T> DEV T imax(T a, T b) { return a > b ? a : b; }
 template <class T> DEV T imin(T a, T b) { return a < b ? a : b; }
 DEV int iabs(int a) { return a < 0 ? -a : a; }

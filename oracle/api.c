@@ -100,6 +100,7 @@ typedef struct {
 	blob_t *sam;
 	orc_pestat_t pes[4];
 	int n_units, phase, n_threads;
+	int next; /* next unit to hand out (work stealing over reads, like kt_for) */
 } batch_t;
 
 typedef struct { batch_t *b; int tid; } targ_t;
@@ -131,7 +132,13 @@ static void *thread_main(void *p_)
 	targ_t *t = (targ_t *)p_;
 	batch_t *b = t->b;
 	int i;
-	for (i = t->tid; i < b->n_units; i += b->n_threads) do_unit(b, i); /* results do not depend on the schedule */
+	(void)t;
+	for (;;) { /* units are handed out in small runs from a shared cursor: no thread waits for a slow neighbour's static share */
+		int lo = __atomic_fetch_add(&b->next, 16, __ATOMIC_RELAXED), hi = lo + 16;
+		if (lo >= b->n_units) break;
+		if (hi > b->n_units) hi = b->n_units;
+		for (i = lo; i < hi; ++i) do_unit(b, i); /* results do not depend on the schedule */
+	}
 	flush_counters();
 	return 0;
 }
@@ -139,7 +146,7 @@ static void *thread_main(void *p_)
 static void run_phase(batch_t *b, int phase)
 {
 	int t, nt = b->n_threads;
-	b->phase = phase;
+	b->phase = phase; b->next = 0;
 	if (nt <= 1) { int i; for (i = 0; i < b->n_units; ++i) do_unit(b, i); flush_counters(); return; }
 	{
 		pthread_t *tid = malloc(sizeof(pthread_t) * nt);

@@ -72,9 +72,9 @@ int orc_ksw_extend2(int qlen, const uint8_t *query, int tlen, const uint8_t *tar
 			max_off = max_off > abs(mj - i) ? max_off : abs(mj - i);
 		} else if (zdrop > 0) {
 			if (i - max_i > mj - max_j) {
-				if (max - m - ((i - max_i) - (mj - max_j)) * e_del > zdrop) break;
+				if (max - m - ((i - max_i) - (mj - max_j)) * e_del > zdrop) { ++orc_tls_cnt.n_ext_zdrop; break; }
 			} else {
-				if (max - m - ((mj - max_j) - (i - max_i)) * e_ins > zdrop) break;
+				if (max - m - ((mj - max_j) - (i - max_i)) * e_ins > zdrop) { ++orc_tls_cnt.n_ext_zdrop; break; }
 			}
 		}
 		for (j = beg; j < end && H[j] == 0 && E[j] == 0; ++j) {}

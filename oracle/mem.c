@@ -327,6 +327,7 @@ void orc_mem_chain2aln(const orc_index_t *x, const orc_opt_t *opt, int l_query, 
 			for (i = 0; i < MAX_BAND_TRY; ++i) {
 				int prev = a->score;
 				aw[0] = opt->w << i;
+				if (i) ++orc_tls_cnt.n_ext_retry;
 				a->score = orc_ksw_extend2(s->qbeg, qs, (int)tmp, rs, opt->mat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins,
 				                           aw[0], opt->pen_clip5, opt->zdrop, s->len * opt->a, &qle, &tle, &gtle, &gscore, &max_off[0]);
 				if (a->score == prev || max_off[0] < (aw[0] >> 1) + (aw[0] >> 2)) break;
@@ -348,6 +349,7 @@ void orc_mem_chain2aln(const orc_index_t *x, const orc_opt_t *opt, int l_query, 
 			for (i = 0; i < MAX_BAND_TRY; ++i) {
 				int prev = a->score;
 				aw[1] = opt->w << i;
+				if (i) ++orc_tls_cnt.n_ext_retry;
 				a->score = orc_ksw_extend2(l_query - qe, query + qe, (int)(rmax[1] - rmax[0] - re), rseq + re, opt->mat,
 				                           opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, aw[1], opt->pen_clip3, opt->zdrop, sc0,
 				                           &qle, &tle, &gtle, &gscore, &max_off[1]);

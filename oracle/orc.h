@@ -115,6 +115,8 @@ typedef struct {
 	uint64_t n_ext_calls, n_msw_calls, n_glb_calls;
 	uint64_t n_seeds, n_chains, n_regs;
 	uint64_t n_occ_sa;   /* the part of n_occ touched by bwt_sa walks (the rest belongs to SMEM seeding) */
+	uint64_t n_ext_retry;/* ksw_extend2 calls that were a second band try (w doubled) */
+	uint64_t n_ext_zdrop;/* ksw_extend2 calls ended by the z-drop test */
 } orc_counters_t;
 
 /* ---- C-ABI of the oracle (mirrors jnibwa.h:11-16) ---- */

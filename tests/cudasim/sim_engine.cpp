@@ -36,6 +36,7 @@ static void rt_sort_pairs_u32(const uint32_t* kin, uint32_t* kout, const uint32_
 	std::stable_sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return kin[a] < kin[b]; });
 	for (uint64_t i = 0; i < n; ++i) { kout[i] = kin[ord[i]]; vout[i] = vin[ord[i]]; }
 }
+static void rt_iota_u32(uint32_t* p, uint64_t n) { for (uint64_t i = 0; i < n; ++i) p[i] = (uint32_t)i; }
 static void rt_fork_aux() {}
 static void rt_back_to_main() {}
 static void rt_join_aux(const char*) {}

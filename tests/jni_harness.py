@@ -7,14 +7,32 @@ import subprocess
 from common import ROOT, PKG_DIR, bwa
 
 SO = os.path.join(ROOT, "tests", "jni_mock", "libjnimock.so")
+SO_REFGLUE = os.path.join(ROOT, "tests", "jni_mock", "libjnimock_refglue.so")
+REF_C = "/root/reference/src/main/c"
 P = "Java_org_broadinstitute_hellbender_utils_bwa_BwaMemIndex_"
 
 
-def build():
-    srcs = [os.path.join(ROOT, "jni", "jni_shim.c"), os.path.join(ROOT, "tests", "jni_mock", "mock_env.c")]
+def have_reference_glue() -> bool:
+    return os.path.isfile(os.path.join(REF_C, "org_broadinstitute_hellbender_utils_bwa_BwaMemIndex.c"))
+
+
+def build(variant: str = "shim"):
+    """variant "shim": jni/jni_shim.c (ours).  variant "reference_glue": the reference's OWN JNI files, unmodified and
+    compiled where they lie (/root/reference/src/main/c/org_..._BwaMemIndex.c + init.c), against include/compat
+    (jni.h, bwa/bwamem.h, bwa/bwa_commit.h) and linked with -lbwa_b200 -- INTEGRATION.md option A."""
+    lib = os.path.join(PKG_DIR, "lib")
+    mock = os.path.join(ROOT, "tests", "jni_mock", "mock_env.c")
+    if variant == "reference_glue":
+        srcs = [os.path.join(REF_C, "org_broadinstitute_hellbender_utils_bwa_BwaMemIndex.c"), os.path.join(REF_C, "init.c"), mock]
+        compat = os.path.join(ROOT, "include", "compat")
+        deps = srcs + [os.path.join(compat, "jni.h"), os.path.join(compat, "bwa", "bwamem.h"), os.path.join(compat, "bwa", "bwa_commit.h"), os.path.join(ROOT, "jni", "jni_min.h")]
+        if not os.path.exists(SO_REFGLUE) or os.path.getmtime(SO_REFGLUE) < max(os.path.getmtime(f) for f in deps):
+            subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-w", "-I", compat, "-I", os.path.join(ROOT, "jni"), "-I", os.path.join(ROOT, "include"),
+                                   "-o", SO_REFGLUE] + srcs + ["-L", lib, "-lbwa_b200", "-Wl,-rpath," + lib])
+        return SO_REFGLUE
+    srcs = [os.path.join(ROOT, "jni", "jni_shim.c"), mock]
     deps = srcs + [os.path.join(ROOT, "jni", "jni_min.h"), os.path.join(ROOT, "include", "bwamem_b200.h")]
     if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(f) for f in deps):
-        lib = os.path.join(PKG_DIR, "lib")
         subprocess.check_call(["gcc", "-O2", "-Wall", "-Werror", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "jni"),
                                "-o", SO] + srcs + ["-L", lib, "-lbwa_b200", "-Wl,-rpath," + lib])
     return SO
@@ -23,8 +41,8 @@ def build():
 class MockJvm:
     """Loads the shim like System.load + JNI_OnLoad, and exposes the natives with Java-like signatures."""
 
-    def __init__(self):
-        self.dll = d = ctypes.CDLL(build())
+    def __init__(self, variant: str = "shim"):
+        self.dll = d = ctypes.CDLL(build(variant))
         vp, ll, i32 = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int
         for name, res, args in [("mock_env", vp, []), ("mock_vm", vp, []), ("mock_new_buffer", vp, [vp, ll]), ("mock_buffer_addr", vp, [vp]),
                                 ("mock_buffer_cap", ll, [vp]), ("mock_free_buffer_object", None, [vp]),

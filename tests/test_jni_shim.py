@@ -1,4 +1,6 @@
-"""The JNI shim (jni/jni_shim.c) under a mock JNIEnv: symbol surface, JNI_OnLoad field-ID cache, option block, error
+"""The JNI layer under a mock JNIEnv, in two builds: our shim (jni/jni_shim.c) and the reference's OWN glue files compiled
+unmodified against include/compat and linked with libbwa_b200.so (INTEGRATION.md option A; skipped where
+/root/reference does not exist, e.g. on the GPU box).  Checked: symbol surface, JNI_OnLoad field-ID cache, option block, error
 behaviour (CPU), and the full createAlignments path against the oracle (GPU).  Mirrors what BwaMemIndexTest.java
 exercises through a real JVM (/root/reference/src/test/java/.../BwaMemIndexTest.java:27-43,84-127)."""
 import ctypes
@@ -14,13 +16,18 @@ NATIVES = ["createReferenceIndex", "createIndexImageFile", "openIndex", "destroy
            "createAlignments", "destroyByteBuffer", "getVersion"]
 
 
-@pytest.fixture(scope="module")
-def jvm():
-    return jni_harness.MockJvm()
+@pytest.fixture(scope="module", params=["shim", "reference_glue"])
+def jvm(request):
+    if request.param == "reference_glue" and not jni_harness.have_reference_glue():
+        pytest.skip("/root/reference is not on this machine")
+    return jni_harness.MockJvm(request.param)
 
 
-def test_exports_the_nine_natives_and_onload():
-    out = subprocess.check_output(["nm", "-D", "--defined-only", jni_harness.build()], text=True)
+@pytest.mark.parametrize("variant", ["shim", "reference_glue"])
+def test_exports_the_nine_natives_and_onload(variant):
+    if variant == "reference_glue" and not jni_harness.have_reference_glue():
+        pytest.skip("/root/reference is not on this machine")
+    out = subprocess.check_output(["nm", "-D", "--defined-only", jni_harness.build(variant)], text=True)
     syms = {l.split()[-1] for l in out.splitlines() if " T " in l}
     assert "JNI_OnLoad" in syms
     for n in NATIVES:
@@ -64,6 +71,22 @@ def test_image_creation_and_open_failure_modes(jvm):
     assert jvm.call("openIndex", b"/no/such/image") == 0  # -> CouldNotReadImageException in Java
     assert jvm.call("destroyIndex", 0) == 0
     assert not jvm.call("getRefContigNames", 0)
+
+
+@pytest.mark.parametrize("algo", [b"auto", b"is", b"rb2"])
+def test_reference_index_through_the_natives(jvm, tmp_path, algo):
+    """createReferenceIndex + createIndexImageFile (BwaMemIndex.java:218-230) on the reference's own FASTA reproduce the
+    reference's checked-in index files and the image built from them, byte for byte -- through bwa_idx_build when the
+    glue is the reference's own (...BwaMemIndex.c:59)."""
+    fa = os.path.join(GOLDEN, "rotavirus", "ref.fa")
+    prefix = str(tmp_path / "idx")
+    assert jvm.call("createReferenceIndex", fa.encode(), prefix.encode(), algo) == 1
+    for ext in (".amb", ".ann", ".bwt", ".pac", ".sa"):
+        assert open(prefix + ext, "rb").read() == open(fa + ext, "rb").read(), ext
+    img = str(tmp_path / "idx.img")
+    assert jvm.call("createIndexImageFile", prefix.encode(), img.encode()) == 1
+    assert open(img, "rb").read() == open(fixture_image(), "rb").read()
+    assert jvm.dll.mock_live_strings() == 0
 
 
 @pytest.mark.gpu
