@@ -66,6 +66,7 @@ def parse_args():
     ap.add_argument("--parity-seconds", type=float, default=150.0, help="oracle wall-time budget of the parity check (at least one full batch is always compared)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the oracle (no cpu_baseline, no parity): development only")
     ap.add_argument("--single-process", action="store_true")
+    ap.add_argument("--device-only", action="store_true", help="HBM-resident leg only (no e2e legs, no oracle): what the ncu captures under profiles/ run")
     ap.add_argument("--contexts", type=int, default=2, help="batches in flight per device (BWA_B200_CONTEXTS)")
     return ap.parse_args()
 
@@ -461,7 +462,10 @@ def main():
         assert cursor["fail"] is None, cursor["fail"]
         return allreduce(dt, world, "max"), cursor["bytes"]
 
-    if single:
+    if args.device_only:
+        e2e1 = e2e2 = 0.0
+        args.no_cpu_baseline = True
+    elif single:
         k_steps = max(args.steps, n_callers) * 2
         t_pool, ob = e2e_leg(n_callers, k_steps, max(2, args.warmup))
         out_bytes = ob
@@ -533,9 +537,9 @@ def main():
               "sal": ["body_sal"], "chain": ["body_chain", "wbody_chain_heavy", "body_chain_classify"],
               "extend": ["body_extend_q", "body_extend_q8", "wbody_heavy_prep", "body_extend_task_q", "body_extend_task_q8", "wbody_extend_heavy", "wbody_extend",
                          "body_ext_prep", "body_ext_left_q", "body_ext_right_q", "body_ext_left_q8", "body_ext_right_q8", "body_ext_replay"],
-              "rescue_sw": ["wbody_rescue_sw"],
+              "rescue_sw": ["wbody_rescue_sw", "body_tsw_fwd_q", "body_tsw_rev_q", "wbody_rescue_sw_fb"],
               "finalize": ["body_final_pe_t", "wbody_final_pe_redo", "body_final_se_t", "wbody_final_se_redo", "body_final_pe_collect", "body_final_se_collect",
-                           "body_galign_task_q", "body_final_pe_consume", "body_final_se_consume"]}
+                           "body_galign_task_q", "wbody_galign_fb", "body_final_pe_consume", "body_final_se_consume"]}
     # kernels launched on the context's auxiliary stream run beside a kernel of the same stage on the main stream: their entry
     # in the stage table is only the part their neighbour did not cover (possibly 0), but their DRAM traffic counts in full
     aux_kernels = {"seed": ["wbody_seedB_heavy"], "chain": ["wbody_chain_heavy"]}
@@ -556,8 +560,9 @@ def main():
         # DP roof (tools/dpx_peak.cu -> profiles/dpx_peak.json): the min/max pipe issues R three-input min/max
         # instructions per second; a cell of the affine-gap recurrence needs DPX_PER_CELL of them in the scalar (one
         # cell per instruction) formulation these kernels use: peak cells/s = R / DPX_PER_CELL.
-        dpx_per_cell = {"extend": 4.0, "rescue_sw": 5.0, "finalize": 5.0}
-        r32 = min(dpx.get("vimax3_s32", 0.0), dpx.get("viaddmax_s32_relu", 0.0)) if dpx else 0.0
+        # (rescue_sw runs the packed s16x2 forms, two cells per instruction: 4 DPX + 1 PRMT-class instructions per PAIR of cells)
+        dpx_per_cell = {"extend": 4.0, "rescue_sw": 2.0, "finalize": 5.0}
+        r32 = min(dpx.get("vimax3_s32", 0.0), dpx.get("viaddmax_s32_relu", 0.0), dpx.get("vimax3_s16x2", 1e30), dpx.get("viaddmax_s16x2_relu", 1e30)) if dpx else 0.0
         for k_, v in stage_work.items():
             if v["ms"] > 0:
                 if "cells" in v:

@@ -42,6 +42,9 @@ struct RtCtx {
 	void* scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
 	unsigned* counters = nullptr; int counter_next = 0;
 	int launches = 0;
+	// per-batch limit on resident blocks of the kernels that own per-thread / per-warp scratch (0: SEED_BLOCKS_PER_SM /
+	// WARP_BLOCKS_PER_SM blocks per SM).  Batches of long reads need megabytes of scratch per slot: they run with fewer slots.
+	int thread_block_cap = 0, warp_block_cap = 0;
 	// CUDA events on the launching stream around every stage of the last batch
 	static const int MAXS = 512;
 	cudaEvent_t ev[MAXS + 1]; const char* name[MAXS]; int n_marks = 0; bool timer_init = false;
@@ -115,8 +118,13 @@ static bool g_last_cuda_ok() { return g_last_cuda == cudaSuccess; }
 #define WARPS_PER_BLOCK 4
 #define SEED_BLOCKS_PER_SM 8
 #define WARP_BLOCKS_PER_SM 8
-static int64_t rt_thread_slots() { return (int64_t)rt_sm_count() * SEED_BLOCKS_PER_SM * THREADS_PER_BLOCK; }
-static int64_t rt_warp_slots() { return (int64_t)rt_sm_count() * WARP_BLOCKS_PER_SM * WARPS_PER_BLOCK; }
+static int64_t rt_thread_blocks() { const int64_t d = (int64_t)rt_sm_count() * SEED_BLOCKS_PER_SM; return t_rt->thread_block_cap > 0 && t_rt->thread_block_cap < d ? t_rt->thread_block_cap : d; }
+static int64_t rt_warp_blocks() { const int64_t d = (int64_t)rt_sm_count() * WARP_BLOCKS_PER_SM; return t_rt->warp_block_cap > 0 && t_rt->warp_block_cap < d ? t_rt->warp_block_cap : d; }
+static int64_t rt_thread_slots() { return rt_thread_blocks() * THREADS_PER_BLOCK; }
+static int64_t rt_warp_slots() { return rt_warp_blocks() * WARPS_PER_BLOCK; }
+static void rt_set_slot_caps(int64_t thread_blocks, int64_t warp_blocks) { t_rt->thread_block_cap = (int)thread_blocks; t_rt->warp_block_cap = (int)warp_blocks; }
+static int64_t rt_default_thread_slots() { return (int64_t)rt_sm_count() * SEED_BLOCKS_PER_SM * THREADS_PER_BLOCK; }
+static int64_t rt_default_warp_slots() { return (int64_t)rt_sm_count() * WARP_BLOCKS_PER_SM * WARPS_PER_BLOCK; }
 
 #ifdef B200_DEBUG_CKPT
 __device__ volatile unsigned* g_ckpt = nullptr;
@@ -161,6 +169,21 @@ static void rt_sort_u64(const uint64_t* in, uint64_t* out, uint64_t n)
 }
 __global__ void k_iota_u32(u32* p, u64 n) { for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) p[i] = (u32)i; }
 static void rt_iota_u32(uint32_t* p, uint64_t n) { if (n) k_iota_u32<<<(unsigned)((n + 255) / 256 < 65535 ? (n + 255) / 256 : 65535), 256, 0, rt_stream()>>>(p, n); }
+// out[k] = first position of the ascending array keys[0..n) whose value is >= thr[k]  (k < n_thr <= 8)
+struct Thr8 { u32 v[8]; };
+__global__ void k_lower_bounds_u32(const u32* keys, u64 n, Thr8 thr, int n_thr, u32* out)
+{
+	const int k = (int)threadIdx.x;
+	if (k >= n_thr) return;
+	u64 lo = 0, hi = n;
+	while (lo < hi) { const u64 mid = (lo + hi) >> 1; if (keys[mid] < thr.v[k]) lo = mid + 1; else hi = mid; }
+	out[k] = (u32)lo;
+}
+static void rt_lower_bounds_u32(const uint32_t* keys, uint64_t n, const uint32_t* thr, int n_thr, uint32_t* out)
+{
+	Thr8 t; for (int k = 0; k < 8; ++k) t.v[k] = k < n_thr ? thr[k] : 0xffffffffu;
+	k_lower_bounds_u32<<<1, 32, 0, rt_stream()>>>(keys, n, t, n_thr, out);
+}
 // order u32 payloads by u32 keys (stable); used to bucket work items so that the lanes of a warp get similar ones
 static void rt_sort_pairs_u32(const uint32_t* kin, uint32_t* kout, const uint32_t* vin, uint32_t* vout, uint64_t n, int end_bit)
 {
@@ -194,7 +217,7 @@ static void rt_sort_pairs_u32(const uint32_t* kin, uint32_t* kout, const uint32_
 		const int wib = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31); \
 		const i64 slot = (i64)blockIdx.x * WARPS_PER_BLOCK + wib; \
 		WarpMem wm; WarpScratch ws; \
-		make_warp_ctx(P, slot, smem_ + (size_t)wib * ((warp_smem_bytes(P.wm_cap) + 15) & ~(size_t)15), wm, ws); \
+		make_warp_ctx(P, slot, smem_ + (size_t)wib * ((warp_smem_bytes(P.wm_smem_cap) + 15) & ~(size_t)15), wm, ws); \
 		for (;;) { \
 			u32 item = 0; \
 			if (lane == 0) item = atomicAdd(counter, 1u); \
@@ -214,7 +237,7 @@ static void rt_sort_pairs_u32(const uint32_t* kin, uint32_t* kout, const uint32_
 		const i64 slot = (i64)blockIdx.x * WARPS_PER_BLOCK + wib; \
 		const i64 n = (i64)*n_ptr; \
 		WarpMem wm; WarpScratch ws; \
-		make_warp_ctx(P, slot, smem_ + (size_t)wib * ((warp_smem_bytes(P.wm_cap) + 15) & ~(size_t)15), wm, ws); \
+		make_warp_ctx(P, slot, smem_ + (size_t)wib * ((warp_smem_bytes(P.wm_smem_cap) + 15) & ~(size_t)15), wm, ws); \
 		for (;;) { \
 			u32 item = 0; \
 			if (lane == 0) item = atomicAdd(counter, 1u); \
@@ -241,6 +264,9 @@ DEF_THREAD_KERNEL(body_sal)
 DEF_THREAD_KERNEL(body_chain)
 DEF_THREAD_KERNEL(body_chain_classify)
 DEF_WARP_KERNEL_DEVN(wbody_chain_heavy)
+DEF_THREAD_KERNEL(body_flt_gen)
+DEF_WARP_KERNEL_DEVN(wbody_flt_sw)
+DEF_THREAD_KERNEL(body_flt_apply)
 DEF_THREAD_KERNEL(body_pe_cand)
 DEF_THREAD_KERNEL(body_reg_cap)
 DEF_THREAD_KERNEL(body_compact)
@@ -258,6 +284,9 @@ DEF_THREAD_KERNEL(body_rescue_apply_multi)
 #define RESCUE_SW_MIN_BLOCKS 4 // 128 registers: four blocks (16 warps) per SM; the kernel is bound by the latency of its row recurrence
 #endif
 DEF_WARP_KERNEL_DEVN_MB(wbody_rescue_sw, RESCUE_SW_MIN_BLOCKS)
+DEF_WARP_KERNEL_DEVN_MB(wbody_rescue_sw_fb, RESCUE_SW_MIN_BLOCKS)
+DEF_THREAD_QUEUE_KERNEL_MB(body_tsw_fwd_q, 2)
+DEF_THREAD_QUEUE_KERNEL_MB(body_tsw_rev_q, 2)
 DEF_WARP_KERNEL(wbody_extend)
 DEF_THREAD_QUEUE_KERNEL_MB(body_extend_q, 2) // two blocks per SM fit the shared DP rows: let the state machine keep its state in registers
 DEF_THREAD_QUEUE_KERNEL(body_extend_task_q)
@@ -266,10 +295,10 @@ DEF_THREAD_QUEUE_KERNEL_MB(body_extend_q8, 3)
 DEF_THREAD_QUEUE_KERNEL_MB(body_extend_task_q8, 4)
 DEF_WARP_KERNEL_DEVN(wbody_heavy_prep)
 DEF_THREAD_KERNEL(body_ext_prep)
-DEF_THREAD_QUEUE_KERNEL_MB(body_ext_left_q, 2)
-DEF_THREAD_QUEUE_KERNEL_MB(body_ext_right_q, 2)
-DEF_THREAD_QUEUE_KERNEL_MB(body_ext_left_q8, 4)
-DEF_THREAD_QUEUE_KERNEL_MB(body_ext_right_q8, 4)
+DEF_THREAD_QUEUE_KERNEL_MB(body_ext_left_q, 6)
+DEF_THREAD_QUEUE_KERNEL_MB(body_ext_right_q, 6)
+DEF_THREAD_QUEUE_KERNEL_MB(body_ext_left_q8, 6)
+DEF_THREAD_QUEUE_KERNEL_MB(body_ext_right_q8, 6)
 DEF_THREAD_TID_KERNEL(body_ext_replay)
 DEF_WARP_KERNEL_DEVN(wbody_extend_heavy)
 DEF_THREAD_KERNEL(body_save_regs)
@@ -280,6 +309,7 @@ DEF_THREAD_TID_KERNEL(body_final_se_collect)
 DEF_THREAD_TID_KERNEL(body_final_pe_consume)
 DEF_THREAD_TID_KERNEL(body_final_se_consume)
 DEF_THREAD_QUEUE_KERNEL(body_galign_task_q)
+DEF_WARP_KERNEL_DEVN(wbody_galign_fb)
 DEF_WARP_KERNEL_DEVN(wbody_final_pe_redo)
 DEF_WARP_KERNEL_DEVN(wbody_final_se_redo)
 
@@ -327,11 +357,11 @@ static int rt_launches() { return t_rt ? t_rt->launches : 0; }
 	i64 nb_ = (n_ + THREADS_PER_BLOCK - 1) / THREADS_PER_BLOCK; i64 cap_ = (i64)rt_sm_count() * 16; if (nb_ > cap_) nb_ = cap_; \
 	k_##body<<<(unsigned)nb_, THREADS_PER_BLOCK, 0, rt_stream()>>>(P, n_); ++t_rt->launches; } rt_mark(#body); } while (0)
 #define RT_THREADS_TID(body, P, n) do { i64 n_ = (i64)(n); if (n_ > 0) { \
-	i64 nb_ = (n_ + THREADS_PER_BLOCK - 1) / THREADS_PER_BLOCK; i64 cap_ = (i64)rt_sm_count() * SEED_BLOCKS_PER_SM; if (nb_ > cap_) nb_ = cap_; \
+	i64 nb_ = (n_ + THREADS_PER_BLOCK - 1) / THREADS_PER_BLOCK; i64 cap_ = rt_thread_blocks(); if (nb_ > cap_) nb_ = cap_; \
 	k_##body<<<(unsigned)nb_, THREADS_PER_BLOCK, 0, rt_stream()>>>(P, n_); ++t_rt->launches; } rt_mark(#body); } while (0)
 // thread kernels whose threads use the shared-memory rings (make_thread_ctx)
 #define RT_THREADS_TID_RING(body, P, n) do { i64 n_ = (i64)(n); if (n_ > 0) { \
-	i64 nb_ = (n_ + THREADS_PER_BLOCK - 1) / THREADS_PER_BLOCK; i64 cap_ = (i64)rt_sm_count() * SEED_BLOCKS_PER_SM; if (nb_ > cap_) nb_ = cap_; \
+	i64 nb_ = (n_ + THREADS_PER_BLOCK - 1) / THREADS_PER_BLOCK; i64 cap_ = rt_thread_blocks(); if (nb_ > cap_) nb_ = cap_; \
 	size_t tsm_ = thread_block_smem_bytes(THREADS_PER_BLOCK, (P).wm_cap); \
 	RT_SET_SMEM(k_##body, tsm_); \
 	k_##body<<<(unsigned)nb_, THREADS_PER_BLOCK, tsm_, rt_stream()>>>(P, n_); ++t_rt->launches; } rt_mark(#body); } while (0)
@@ -339,18 +369,18 @@ static int rt_launches() { return t_rt ? t_rt->launches : 0; }
 #define RT_THREADS_QUEUE_SMEM(body, P, n, bytes) do { i64 n_ = (i64)(n); if (n_ > 0) { \
 	size_t tsm_ = (bytes); \
 	i64 nb_ = (n_ + THREADS_PER_BLOCK - 1) / THREADS_PER_BLOCK; i64 per_sm_ = (i64)((227 * 1024) / (tsm_ + 1024)); if (per_sm_ < 1) per_sm_ = 1; if (per_sm_ > SEED_BLOCKS_PER_SM) per_sm_ = SEED_BLOCKS_PER_SM; \
-	i64 cap_ = (i64)rt_sm_count() * per_sm_; if (nb_ > cap_) nb_ = cap_; \
+	i64 cap_ = (i64)rt_sm_count() * per_sm_; if (cap_ > rt_thread_blocks()) cap_ = rt_thread_blocks(); if (nb_ > cap_) nb_ = cap_; \
 	RT_SET_SMEM(k_##body, tsm_); \
 	k_##body<<<(unsigned)nb_, THREADS_PER_BLOCK, tsm_, rt_stream()>>>(P, n_, next_counter()); ++t_rt->launches; } rt_mark(#body); } while (0)
 #define RT_WARPS(wbody, P, n) do { i64 n_ = (i64)(n); if (n_ > 0) { \
-	size_t sm_ = ((warp_smem_bytes((P).wm_cap) + 15) & ~(size_t)15) * WARPS_PER_BLOCK; \
-	i64 nb_ = (n_ + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK; i64 cap_ = (i64)rt_sm_count() * WARP_BLOCKS_PER_SM; if (nb_ > cap_) nb_ = cap_; \
+	size_t sm_ = ((warp_smem_bytes((P).wm_smem_cap) + 15) & ~(size_t)15) * WARPS_PER_BLOCK; \
+	i64 nb_ = (n_ + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK; i64 cap_ = rt_warp_blocks(); if (nb_ > cap_) nb_ = cap_; \
 	RT_SET_SMEM(k_##wbody, sm_); \
 	k_##wbody<<<(unsigned)nb_, WARPS_PER_BLOCK * 32, sm_, rt_stream()>>>(P, n_, next_counter()); ++t_rt->launches; } rt_mark(#wbody); } while (0)
 
 #define RT_WARPS_DEVN(wbody, P, n_ptr, n_max) do { \
-	size_t sm_ = ((warp_smem_bytes((P).wm_cap) + 15) & ~(size_t)15) * WARPS_PER_BLOCK; \
-	i64 nb_ = (i64)rt_sm_count() * WARP_BLOCKS_PER_SM; \
+	size_t sm_ = ((warp_smem_bytes((P).wm_smem_cap) + 15) & ~(size_t)15) * WARPS_PER_BLOCK; \
+	i64 nb_ = rt_warp_blocks(); \
 	RT_SET_SMEM(k_##wbody, sm_); \
 	k_##wbody<<<(unsigned)nb_, WARPS_PER_BLOCK * 32, sm_, rt_stream()>>>(P, n_ptr, next_counter()); ++t_rt->launches; rt_mark(#wbody); } while (0)
 

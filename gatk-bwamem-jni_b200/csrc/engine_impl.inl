@@ -85,7 +85,7 @@ struct EngineConfig {
 	bool no_stage_overlap = false, seed_one_launch = false, seed_fused_rounds = false, tiny_seed_pool = false, tiny_seed_tasks = false, seed_no_overlap = false;
 	bool chain_all_warp = false, chain_all_thread = false, chain_no_overlap = false, tiny_scratch = false, all_heavy = false, all_light = false;
 	bool warp_extend = false, ext_wide_cells = false, no_ext_tasks = false, rescue_fallback = false, final_one_pass = false, final_ring = false, tiny_ga_cap = false;
-	bool ext_legacy = false, ext_no_sort = false;
+	bool ext_legacy = false, ext_no_sort = false, force_long_mode = false, rescue_warp_sw = false, ga_no_sort = false;
 	int seed_lcap = 0, seed_shared_read = -1, tx_chunk = -1, light_seeds = -1, light_chains = -1;
 	static bool flag(const char* nm) { return getenv(nm) != nullptr; }
 	static int num(const char* nm, int dflt) { const char* e = getenv(nm); return e ? atoi(e) : dflt; }
@@ -102,7 +102,7 @@ struct EngineConfig {
 		tiny_scratch = flag("B200_TEST_TINY_SCRATCH"); all_heavy = flag("B200_TEST_ALL_HEAVY"); all_light = flag("B200_TEST_ALL_LIGHT");
 		warp_extend = flag("B200_WARP_EXTEND"); ext_wide_cells = flag("B200_EXT_WIDE_CELLS"); no_ext_tasks = flag("B200_NO_EXT_TASKS");
 		rescue_fallback = flag("B200_TEST_RESCUE_FALLBACK"); final_one_pass = flag("B200_FINAL_ONE_PASS"); final_ring = flag("B200_TEST_FINAL_RING");
-		tiny_ga_cap = flag("B200_TEST_TINY_GA_CAP"); ext_legacy = flag("B200_EXT_LEGACY"); ext_no_sort = flag("B200_EXT_NO_SORT");
+		tiny_ga_cap = flag("B200_TEST_TINY_GA_CAP"); ext_legacy = flag("B200_EXT_LEGACY"); ext_no_sort = flag("B200_EXT_NO_SORT"); force_long_mode = flag("B200_TEST_LONG_MODE"); rescue_warp_sw = flag("B200_RESCUE_WARP_SW"); ga_no_sort = flag("B200_GA_NO_SORT");
 		seed_lcap = num("B200_SEED_LCAP", 0); seed_shared_read = num("B200_SEED_SHARED_READ", -1); tx_chunk = num("B200_TX_CHUNK", -1);
 		light_seeds = num("B200_LIGHT_SEEDS", -1); light_chains = num("B200_LIGHT_CHAINS", -1);
 	}
@@ -180,7 +180,7 @@ struct Batch {
 	DBuf b_blob, b_seq, b_seqoff, b_intv, b_nintv, b_nseed, b_smem, b_seedoff, b_rbeg, b_S, b_C, b_ord, b_tmp32, b_ck, b_ks, b_srt, b_regtmp,
 	     b_nck, b_nks, b_nreg, b_regcap, b_regoff, b_regs, b_snap, b_ztmp, b_pairv, b_recs, b_nrec, b_cand, b_pairtab, b_var, b_misc,
 	     b_outwords, b_outoff, b_out, b_wsz, b_wscig, b_wsmd, b_wsxa, b_wsbrow, b_nb, b_swtask, b_swstate, b_swlist, b_tbuf, b_redo, b_heavy, b_multi, b_cand2, b_specstate, b_spectask, b_nreg0, b_rsheavy, b_wsrt, b_wsrkey, b_wsrrank, b_exttask, b_extres, b_ckrmax, b_chainheavy, b_gatask, b_gares, b_gaitem0, b_gaitemn, b_seedpool, b_seedused, b_seedtask, b_seedfb,
-	     b_xtkey, b_xtkey2, b_xtidx, b_xtidx2;
+	     b_xtkey, b_xtkey2, b_xtidx, b_xtidx2, b_wsrows, b_flttask, b_tswhmax, b_tswbrow, b_swrev, b_swfb, b_gakey, b_gakey2, b_gaiota, b_gaorder, b_gafb;
 	Counters last_counters; uint64_t last_n_seed = 0; int n_launches = 0;
 	std::string last_error;
 	// staged request
@@ -361,7 +361,7 @@ inline void Batch::release_all()
 	                &b_seedoff, &b_rbeg, &b_S, &b_C, &b_ord, &b_tmp32, &b_ck, &b_ks, &b_srt, &b_regtmp, &b_nck, &b_nks, &b_nreg, &b_regcap, &b_regoff,
 	                &b_regs, &b_snap, &b_ztmp, &b_pairv, &b_recs, &b_nrec, &b_cand, &b_pairtab, &b_var, &b_misc, &b_outwords, &b_outoff, &b_out,
 	                &b_wsz, &b_wscig, &b_wsmd, &b_wsxa, &b_wsbrow, &b_nb, &b_swtask, &b_swstate, &b_swlist, &b_tbuf, &b_redo, &b_heavy, &b_multi, &b_cand2, &b_specstate, &b_spectask, &b_nreg0, &b_rsheavy, &b_wsrt, &b_wsrkey, &b_wsrrank, &b_exttask, &b_extres, &b_ckrmax, &b_chainheavy, &b_gatask, &b_gares, &b_gaitem0, &b_gaitemn, &b_seedpool, &b_seedused, &b_seedtask, &b_seedfb,
-	                &b_xtkey, &b_xtkey2, &b_xtidx, &b_xtidx2 };
+	                &b_xtkey, &b_xtkey2, &b_xtidx, &b_xtidx2, &b_wsrows, &b_flttask, &b_tswhmax, &b_tswbrow, &b_swrev, &b_swfb, &b_gakey, &b_gakey2, &b_gaiota, &b_gaorder, &b_gafb };
 	for (DBuf* b : all) b->release();
 #ifndef B200_SIM
 	for (int t = 0; t < NUP; ++t) { if (up_stream[t]) cudaStreamDestroy(up_stream[t]); if (up_done[t]) cudaEventDestroy(up_done[t]); up_stream[t] = nullptr; up_done[t] = nullptr; }
@@ -514,20 +514,33 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 	if (n_reads == 0) { void* r = malloc(1); return r; }
 	// ---- option / shape validation: fail loudly instead of approximating
 	if (opt.e_del <= 0 || opt.e_ins <= 0 || opt.a <= 0 || opt.max_occ <= 0 || opt.min_seed_len <= 0) { last_error = "unsupported option values"; return nullptr; }
-	{
-		// mem_flt_chained_seeds (long-read seed re-scoring) is not on this path: refuse batches that would trigger it.
-		// It acts on a read of l bases (l >= min_seed_len) unless min_l > 0.05 l, min_l = 1.1 min_chain_weight or
-		// 5.5 ln l.  Both forms fail first for the LONGEST read (5.5 ln l - 0.05 l is concave and positive at
-		// min_seed_len), so testing max_len covers every read of the batch.
-		const int l = max_len;
-		if (l >= opt.min_seed_len) {
-			double min_l = opt.min_chain_weight ? 1.1f * opt.min_chain_weight : 5.5f * log((double)l);
-			double at_min = opt.min_chain_weight ? min_l : 5.5f * log((double)opt.min_seed_len);
-			if (!(min_l > 0.05f * l) || !(at_min > 0.05f * opt.min_seed_len)) { last_error = "read length/min_chain_weight would enable mem_flt_chained_seeds (long-read path not built)"; return nullptr; }
-		}
+	// mem_flt_chained_seeds (B10) acts on a read of l bases unless min_l > 0.05 l, min_l = 1.1 min_chain_weight or 5.5 ln l.
+	// 5.5 ln l - 0.05 l is concave, so with default options the test fails first for the LONGEST read: when it holds
+	// for max_len (and for min_seed_len) no read of the batch needs the filter and its launches are skipped.
+	bool flt_possible = false;
+	if (max_len >= opt.min_seed_len) {
+		const double min_l = opt.min_chain_weight ? 1.1f * opt.min_chain_weight : 5.5f * log((double)max_len);
+		const double at_min = opt.min_chain_weight ? min_l : 5.5f * log((double)opt.min_seed_len);
+		flt_possible = !(min_l > 0.05f * max_len) || !(at_min > 0.05f * opt.min_seed_len);
 	}
+	// Batches with long reads (assembled contigs of 0.5-50 kbp, BwaMemAligner.java:140-146): the per-thread / per-warp
+	// scratch grows with the read length (candidate lists, DP rows, traceback), so such batches run every read on the
+	// warp-level kernels with rows in global memory, on as many slots as a fixed scratch budget allows.
+	const bool long_mode = max_len > 1000 || cfg.force_long_mode;
 	const int wm_cap = ((max_len + 15) / 16) * 16 + 32;
-	const int intv_cap = max_len < 64 ? 64 : (max_len > 512 ? 512 : max_len);
+	const int intv_cap = max_len < 64 ? 64 : (max_len > 512 ? 512 + (max_len - 512) / 6 : max_len); // SMEMs of a read; long reads: one per ~6 bases at most, or the batch fails with ERR_INTV_OVERFLOW
+	const int L_ = max_len > 0 ? max_len : 1;
+	// traceback of the banded global alignment: n_col <= min(l_query, 2 w + 1) bytes per reference row, w <= max(4 opt.w, dl + 3)
+	const size_t ws_z_cap = (size_t)((L_ < 8 * opt.w + 17 ? L_ : 8 * opt.w + 17) + 4) * (size_t)(L_ + 8 * opt.w + 64);
+	const int ws_cigar_cap = 3 * L_ + 4 * opt.w + 64, ws_md_cap = 4 * L_ + 8 * opt.w + 128, ws_xa_cap = 8192 + (long_mode ? 8 * L_ : 0), ws_rt_cap = 1024;
+	rt_set_slot_caps(0, 0);
+	if (long_mode) {
+		const size_t per_thread = (size_t)(max_len + 1) * sizeof(Intv) + thread_scratch_bytes(wm_cap, 64, 48, 192, 1024);
+		const size_t per_warp = ws_z_cap + (size_t)ws_cigar_cap * 4 + ws_md_cap + ws_xa_cap + (size_t)ws_rt_cap * (sizeof(Reg) + 12) + warp_smem_bytes(wm_cap) + (size_t)(max_len + 10064) * 8;
+		const size_t budget_t = (size_t)6 << 30, budget_w = (size_t)12 << 30;
+		int64_t tb = (int64_t)(budget_t / per_thread / THREADS_PER_BLOCK), wb = (int64_t)(budget_w / per_warp / WARPS_PER_BLOCK);
+		rt_set_slot_caps(tb < 1 ? 1 : tb, wb < 1 ? 1 : wb);
+	}
 
 	BatchParams P;
 	memset(&P, 0, sizeof(P));
@@ -551,7 +564,12 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 	P.seed_off = b_seedoff.as<u64>(); P.n_ck = b_nck.as<u32>(); P.n_ks = b_nks.as<u32>(); P.n_reg = b_nreg.as<u32>();
 	P.reg_cap = b_regcap.as<u32>(); P.reg_off = b_regoff.as<u64>(); P.n_rec = b_nrec.as<u32>();
 	P.out_words = b_outwords.as<u32>(); P.out_off = b_outoff.as<u64>();
-	P.wm_cap = wm_cap;
+	P.wm_cap = wm_cap; P.wm_smem_cap = wm_cap;
+	if (long_mode) { // the DP rows of a warp slot in global memory (kernels.cuh make_warp_ctx), for every warp kernel of the batch
+		P.ws_rows_stride = (warp_smem_bytes(wm_cap) + 255) & ~(size_t)255;
+		if (!b_wsrows.ensure((size_t)wslots * P.ws_rows_stride)) { last_error = "device allocation failed (warp rows)"; return nullptr; }
+		P.ws_rows = b_wsrows.as<u8>(); P.wm_smem_cap = 0;
+	}
 
 	// ---- stage 1: encode + seed
 	RT_THREADS(body_encode, P, (int64_t)blob_len);
@@ -625,16 +643,12 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 	}
 	// ---- warp scratch
 	{
-		const int L = max_len > 0 ? max_len : 1;
-		P.ws_z_cap = (size_t)(L + 1) * (size_t)(2 * L + 4 * opt.w + 64);
-		P.ws_cigar_cap = 3 * L + 4 * opt.w + 64;
-		P.ws_md_cap = 4 * L + 8 * opt.w + 128;
-		P.ws_xa_cap = 8192;
+		P.ws_z_cap = ws_z_cap; P.ws_cigar_cap = ws_cigar_cap; P.ws_md_cap = ws_md_cap; P.ws_xa_cap = ws_xa_cap;
 		ok = b_wsz.ensure((size_t)wslots * P.ws_z_cap) && b_wscig.ensure((size_t)wslots * P.ws_cigar_cap * 4) && b_wsmd.ensure((size_t)wslots * P.ws_md_cap) && b_wsxa.ensure((size_t)wslots * P.ws_xa_cap);
 		if (!ok) { last_error = "device allocation failed (warp scratch)"; return nullptr; }
 		P.ws_z = b_wsz.as<u8>(); P.ws_cigar = b_wscig.as<u32>(); P.ws_md = b_wsmd.as<char>(); P.ws_xa = b_wsxa.as<char>();
 		P.ws_brow = nullptr; P.ws_brow_cap = 0;
-		P.ws_rt_cap = 1024; // longer region lists take the scalar de-duplication
+		P.ws_rt_cap = ws_rt_cap; // longer region lists take the scalar de-duplication
 		ok = b_wsrt.ensure((size_t)wslots * P.ws_rt_cap * sizeof(Reg)) && b_wsrkey.ensure((size_t)wslots * (P.ws_rt_cap + 2) * 8) && b_wsrrank.ensure((size_t)wslots * (P.ws_rt_cap + 2) * 4);
 		if (!ok) { last_error = "device allocation failed (warp scratch)"; return nullptr; }
 		P.ws_rt = b_wsrt.as<Reg>(); P.ws_rkey = b_wsrkey.as<i64>(); P.ws_rrank = b_wsrrank.as<u32>();
@@ -643,6 +657,7 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 	{
 		P.t_z_cap = 8192; P.t_cigar_cap = 48; P.t_md_cap = 192; P.t_xa_cap = 1024;
 		if (cfg.tiny_scratch) { P.t_z_cap = 1024; P.t_cigar_cap = 6; P.t_md_cap = 24; P.t_xa_cap = 80; } // tests: force hand-overs
+		if (long_mode) P.t_z_cap = 64; // (no thread-level alignment runs in this mode)
 		P.t_stride = thread_scratch_bytes(P.wm_cap, P.t_z_cap, P.t_cigar_cap, P.t_md_cap, P.t_xa_cap);
 		ok = b_tbuf.ensure((size_t)tslots * P.t_stride) && b_redo.ensure(((size_t)n_reads + 1) * 4) && b_heavy.ensure(((size_t)n_reads + 1) * 4);
 		if (!ok) { last_error = "device allocation failed (thread scratch)"; return nullptr; }
@@ -656,8 +671,16 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 		if (cfg.all_light) { P.light_max_seeds = 1 << 30; P.light_max_chains = 1 << 30; }
 	}
 	for (int t = 0; t < 5; ++t) { P.rowpack[t] = 0; for (int c2 = 0; c2 < 5; ++c2) P.rowpack[t] |= (u64)(u8)opt.mat[t * 5 + c2] << (8 * c2); }
+	// ---- mem_flt_chained_seeds (long reads): re-score the seeds of the kept chains, drop the weak ones (kernels.cuh)
+	if (flt_possible) {
+		if (!b_flttask.ensure(((size_t)T + 1) * 8)) { last_error = "device allocation failed (seed filter)"; return nullptr; }
+		P.flt_tasks = b_flttask.as<u32>(); P.n_flt_tasks = b_misc.as<u32>() + 29;
+		RT_THREADS(body_flt_gen, P, (int64_t)n_reads);
+		RT_WARPS_DEVN(wbody_flt_sw, P, P.n_flt_tasks, (int64_t)T);
+		RT_THREADS(body_flt_apply, P, (int64_t)n_reads);
+	}
 	// ---- stage 3: extension + de-duplication (thread per light read with shared-memory DP rows, warp per heavy read)
-	if (cfg.warp_extend) RT_WARPS(wbody_extend, P, (int64_t)n_reads); // the all-warp formulation, kept for comparison
+	if (cfg.warp_extend || long_mode) RT_WARPS(wbody_extend, P, (int64_t)n_reads); // the all-warp formulation (long reads; kept for comparison otherwise)
 	else {
 		int rw = max_len - opt.min_seed_len + 2;
 		// cells: H and E as 8-bit halves when no score of the batch can exceed 255 (the per-read test in the kernel is the
@@ -676,7 +699,6 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 		else if (!cfg.ext_legacy) {
 			// uniform side tasks (extend_thread.cuh): prep -> left sides -> right sides -> replay; see the comment there
 			P.t_ext_rw = rw;
-			const size_t ext_smem = thread_ext_smem_bytes(THREADS_PER_BLOCK, rw, wm_cap, cell);
 			const size_t Tn = (size_t)T + 1;
 			ok = b_exttask.ensure(Tn * sizeof(ExtTask)) && b_extres.ensure(Tn * sizeof(ExtRes)) && b_ckrmax.ensure(Tn * 16) && b_xtkey.ensure(Tn * 8) && b_xtkey2.ensure(Tn * 8) && b_xtidx.ensure(Tn * 4) && b_xtidx2.ensure(Tn * 8);
 			if (!ok) { last_error = "device allocation failed (extension tasks)"; return nullptr; }
@@ -689,15 +711,36 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 			uint32_t n_t = 0;
 			rt_d2h(&n_t, P.n_ext_tasks, 4);
 			hp.mark("ext_prep_sync");
+			// classes of query length: a launch per class and side, rows sized for the class (short sides are the bulk: small
+			// rows let many warps be resident); without the ordering there is one class with the longest rows
+			enum { NCLS = 4 };
+			const uint32_t thr[NCLS] = { 24u, 48u, 96u, 0xffffffffu }; // a class holds the sides with fewer than thr bases (and at least the class below's)
+			uint32_t bnd[2 * NCLS];
+			for (int k = 0; k < 2 * NCLS; ++k) bnd[k] = (k % NCLS == NCLS - 1) ? n_t : 0u; // (unordered: everything in the last class)
 			if (n_t && !cfg.ext_no_sort) { // order the tasks of each side by query length: the lanes of a warp then run rows of similar width
 				int bits = 1; while ((1 << bits) <= max_len && bits < 31) ++bits;
 				rt_iota_u32(b_xtidx.as<u32>(), n_t);
 				rt_sort_pairs_u32(P.ext_key_l, b_xtkey2.as<u32>(), b_xtidx.as<u32>(), b_xtidx2.as<u32>(), n_t, bits);
 				rt_sort_pairs_u32(P.ext_key_r, b_xtkey2.as<u32>() + Tn, b_xtidx.as<u32>(), b_xtidx2.as<u32>() + Tn, n_t, bits);
 				P.ext_order_l = b_xtidx2.as<u32>(); P.ext_order_r = b_xtidx2.as<u32>() + Tn;
+				// class boundaries in the two sorted key arrays (first position whose key is >= thr)
+				rt_lower_bounds_u32(b_xtkey2.as<u32>(), n_t, thr, NCLS - 1, b_xtidx.as<u32>());
+				rt_lower_bounds_u32(b_xtkey2.as<u32>() + Tn, n_t, thr, NCLS - 1, b_xtidx.as<u32>() + NCLS);
+				rt_d2h(bnd, b_xtidx.p, sizeof(bnd));
+				bnd[NCLS - 1] = n_t; bnd[2 * NCLS - 1] = n_t;
+				hp.mark("ext_class_sync");
 			}
-			if (narrow) { RT_THREADS_QUEUE_SMEM(body_ext_left_q8, P, (int64_t)n_t, ext_smem); RT_THREADS_QUEUE_SMEM(body_ext_right_q8, P, (int64_t)n_t, ext_smem); }
-			else { RT_THREADS_QUEUE_SMEM(body_ext_left_q, P, (int64_t)n_t, ext_smem); RT_THREADS_QUEUE_SMEM(body_ext_right_q, P, (int64_t)n_t, ext_smem); }
+			for (int side = 0; side < 2; ++side) {
+				for (int k = NCLS - 1; k >= 0; --k) { // longest class first
+					const uint32_t lo = k ? bnd[side * NCLS + k - 1] : 0u, hi = bnd[side * NCLS + k];
+					if (hi <= lo) continue;
+					int crw = thr[k] < (uint32_t)rw ? (int)thr[k] : rw; // sides of < thr bases need thr cells (H[0..qlen])
+					P.ext_lo = lo; P.ext_hi = hi; P.ext_rw = crw;
+					const size_t sm = side_smem_bytes(THREADS_PER_BLOCK, crw, cell);
+					if (narrow) { if (side == 0) RT_THREADS_QUEUE_SMEM(body_ext_left_q8, P, (int64_t)(hi - lo), sm); else RT_THREADS_QUEUE_SMEM(body_ext_right_q8, P, (int64_t)(hi - lo), sm); }
+					else { if (side == 0) RT_THREADS_QUEUE_SMEM(body_ext_left_q, P, (int64_t)(hi - lo), sm); else RT_THREADS_QUEUE_SMEM(body_ext_right_q, P, (int64_t)(hi - lo), sm); }
+				}
+			}
 			RT_THREADS_TID(body_ext_replay, P, (int64_t)n_reads);
 			P.use_ext_res = 1;
 			RT_WARPS_DEVN(wbody_extend_heavy, P, P.n_heavy, (int64_t)n_reads); // heavy reads, and light ones the replay could not finish
@@ -758,7 +801,7 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 	{
 		size_t Rn = (size_t)R + 2;
 		ok = b_regs.ensure(Rn * sizeof(Reg)) && b_snap.ensure(Rn * sizeof(Reg)) && b_ztmp.ensure(Rn * 4) && b_pairv.ensure(Rn * sizeof(Pair64)) && b_recs.ensure(Rn * sizeof(AlnRec));
-		P.var_cap = (u32)std::min<uint64_t>((uint64_t)0xfffffff0u, (uint64_t)R * 24 + (uint64_t)n_reads * 8 + 4096);
+		P.var_cap = (u32)std::min<uint64_t>((uint64_t)0xfffffff0u, (uint64_t)R * 24 + (uint64_t)n_reads * 8 + 4096 + (long_mode ? 2 * blob_len : 0)); // CIGAR + MD words of the records
 		ok = ok && b_var.ensure((size_t)P.var_cap * 4);
 		if (!ok) { last_error = "device allocation failed (region pools)"; return nullptr; }
 	}
@@ -780,7 +823,27 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 		RT_THREADS(body_rescue_classify, P, (int64_t)n_reads);
 		// the task pool holds at most sum(nb * live orientations) <= R entries (that head-room is part of reg_cap)
 		RT_THREADS(body_rescue_gen_all, P, (int64_t)n_reads);
-		RT_WARPS_DEVN(wbody_rescue_sw, P, P.sw_n_list, (int64_t)R);
+		if (cfg.rescue_warp_sw || long_mode) RT_WARPS_DEVN(wbody_rescue_sw, P, P.sw_n_list, (int64_t)R); // the warp-per-task formulation (comparison, long reads)
+		else {
+			// thread-per-task alignments with two cells per register (sw_thread.cuh): forward pass of every task, reverse pass of
+			// those that scored, the warp-per-task kernel for the tasks the byte formulation does not take
+			int shift = 127, mmax = 0;
+			for (int k = 0; k < 25; ++k) { if (opt.mat[k] < shift) shift = opt.mat[k]; if (opt.mat[k] > mmax) mmax = opt.mat[k]; }
+			shift = (256 - (shift & 0xff)) & 0xff; // uint8 arithmetic of the profile builder (ksw_qinit)
+			P.sw_shift = shift; P.sw_mmax = mmax;
+			for (int t = 0; t < 4; ++t) { P.swtab[t] = 0; for (int c = 0; c < 6; ++c) P.swtab[t] |= (u64)(u8)((c < 5 ? (int)opt.mat[t * 5 + c] : 0) + shift) << (8 * c); }
+			P.tsw_capw = ((max_len + 15) / 16) * 8;
+			if (P.tsw_capw > 160) P.tsw_capw = 160; // (queries of up to 320 bases; longer ones take the warp kernel)
+			P.tsw_brow_cap = P.ws_brow_cap;
+			ok = b_tswhmax.ensure((size_t)((tslots + 31) / 32 * 32) * P.tsw_capw * 4 + 4096) && b_tswbrow.ensure((size_t)tslots * P.tsw_brow_cap * 8 + 64) && b_swrev.ensure(Rn * 4) && b_swfb.ensure(Rn * 4);
+			if (!ok) { last_error = "device allocation failed (rescue alignment scratch)"; return nullptr; }
+			P.tsw_hmax = b_tswhmax.as<u32>(); P.tsw_brow = b_tswbrow.as<u64>(); P.sw_rev = b_swrev.as<u32>(); P.sw_fb = b_swfb.as<u32>();
+			P.n_sw_rev = b_misc.as<u32>() + 30; P.n_sw_fb = b_misc.as<u32>() + 31;
+			const size_t sm = tsw_block_smem_bytes(THREADS_PER_BLOCK, P.tsw_capw);
+			RT_THREADS_QUEUE_SMEM(body_tsw_fwd_q, P, (int64_t)R, sm);
+			RT_THREADS_QUEUE_SMEM(body_tsw_rev_q, P, (int64_t)R, sm);
+			RT_WARPS_DEVN(wbody_rescue_sw_fb, P, P.n_sw_fb, (int64_t)R);
+		}
 		RT_WARPS_DEVN(wbody_rescue_apply_heavy, P, P.n_rs_heavy, (int64_t)n_reads); // long chains first: they are the tail
 		RT_THREADS(body_rescue_apply_all, P, (int64_t)n_reads);
 		uint32_t hdr[8];
@@ -804,7 +867,12 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 	{
 		RT_THREADS(body_save_regs, P, (int64_t)n_reads);
 		const int64_t n_items = pe ? (int64_t)n_units : (int64_t)n_reads;
-		if (cfg.final_one_pass) { // every item computes its own alignments (kept for comparison and tests)
+		if (long_mode) { // every item straight to the warp-level kernel
+			rt_iota_u32(P.redo_list, (uint64_t)n_items);
+			const uint32_t ni = (uint32_t)n_items; rt_h2d(P.n_redo, &ni, 4); rt_sync();
+		}
+		if (long_mode) {}
+		else if (cfg.final_one_pass) { // every item computes its own alignments (kept for comparison and tests)
 			if (pe) RT_THREADS_TID_RING(body_final_pe_t, P, n_items); else RT_THREADS_TID_RING(body_final_se_t, P, n_items);
 		} else {
 			// two passes around a queue of alignment tasks (galign_thread.cuh): collect -> tasks -> consume
@@ -814,12 +882,27 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 			if (!ok) { last_error = "device allocation failed (alignment tasks)"; return nullptr; }
 			P.ga_tasks = b_gatask.as<GaTask>(); P.ga_res = b_gares.as<GaRes>(); P.ga_item0 = b_gaitem0.as<u32>(); P.ga_itemn = b_gaitemn.as<u32>();
 			P.n_ga_tasks = b_misc.as<u32>() + 23;
+			ok = b_gakey.ensure((size_t)P.ga_cap * 4) && b_gakey2.ensure((size_t)P.ga_cap * 4) && b_gaiota.ensure((size_t)P.ga_cap * 4) && b_gaorder.ensure((size_t)P.ga_cap * 4) && b_gafb.ensure((size_t)P.ga_cap * 4);
+			if (!ok) { last_error = "device allocation failed (alignment tasks)"; return nullptr; }
+			P.ga_key = cfg.ga_no_sort ? nullptr : b_gakey.as<u32>(); P.ga_order = nullptr; P.ga_fb = b_gafb.as<u32>(); P.n_ga_fb = b_misc.as<u32>() + 32;
 			// (neither pass computes an alignment itself: no shared-memory rings, which lets a third block onto each SM)
 			const bool fin_ring = cfg.final_ring;
 			if (fin_ring) { if (pe) RT_THREADS_TID_RING(body_final_pe_collect, P, n_items); else RT_THREADS_TID_RING(body_final_se_collect, P, n_items); }
 			else if (pe) RT_THREADS_TID(body_final_pe_collect, P, n_items); else RT_THREADS_TID(body_final_se_collect, P, n_items);
 			rt_memset(P.var_cursor, 0, 4); // payloads written while collecting are discarded
+			if (P.ga_key) { // order the tasks by cost (ungapped sums first, then by band area): the lanes of a warp then work on similar tasks
+				uint32_t n_ga = 0;
+				rt_d2h(&n_ga, P.n_ga_tasks, 4);
+				hp.mark("ga_sync");
+				if (n_ga > P.ga_cap) n_ga = P.ga_cap;
+				if (n_ga) {
+					rt_iota_u32(b_gaiota.as<u32>(), n_ga);
+					rt_sort_pairs_u32(P.ga_key, b_gakey2.as<u32>(), b_gaiota.as<u32>(), b_gaorder.as<u32>(), n_ga, 17);
+					P.ga_order = b_gaorder.as<u32>();
+				}
+			}
 			RT_THREADS_QUEUE_SMEM(body_galign_task_q, P, (int64_t)P.ga_cap, galign_block_smem_bytes(THREADS_PER_BLOCK, P.wm_cap));
+			RT_WARPS_DEVN(wbody_galign_fb, P, P.n_ga_fb, (int64_t)P.ga_cap); // bands / tracebacks beyond the thread-level kernel
 			if (fin_ring) { if (pe) RT_THREADS_TID_RING(body_final_pe_consume, P, n_items); else RT_THREADS_TID_RING(body_final_se_consume, P, n_items); }
 			else if (pe) RT_THREADS_TID(body_final_pe_consume, P, n_items); else RT_THREADS_TID(body_final_se_consume, P, n_items);
 		}
@@ -832,7 +915,7 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 	if (!b_out.ensure((size_t)W * 4 + 16)) { last_error = "device allocation failed (output)"; return nullptr; }
 	P.out = b_out.as<u32>();
 	RT_THREADS(body_out_write, P, (int64_t)n_reads);
-	uint32_t misc[32];
+	uint32_t misc[40];
 	rt_d2h(misc, b_misc.p, sizeof(misc));
 	memcpy(&last_counters, misc + 8, sizeof(Counters));
 	n_launches = rt_launches();

@@ -466,7 +466,7 @@ template <int SIDE, class CELL>
 DEV void thread_extend_sides(const BatchParams& P, u32* counter, const ThreadExtMem& tm)
 {
 	const DevIndex& x = P.x; const MemOpt& opt = P.opt;
-	const i64 n = (i64)*P.n_ext_tasks;
+	const i64 lo = (i64)P.ext_lo, n = (i64)P.ext_hi - lo; // this launch: positions [ext_lo, ext_hi) of the side's order
 	const u32* order = SIDE == 0 ? P.ext_order_l : P.ext_order_r;
 	int mx = 0;
 	for (int k = 0; k < 25; ++k) mx = mx > opt.mat[k] ? mx : (int)opt.mat[k];
@@ -478,8 +478,8 @@ DEV void thread_extend_sides(const BatchParams& P, u32* counter, const ThreadExt
 		if (lane == 0) base = atomic_add_u32(counter, (u32)SIMT_GROUP);
 		base = lane_bcast0(base);
 		if ((i64)base >= n) break;
-		const i64 pos = n - 1 - ((i64)base + lane);
-		if (pos >= 0) {
+		const i64 pos = lo + n - 1 - ((i64)base + lane);
+		if (pos >= lo) {
 			const u32 ti = order ? order[pos] : (u32)pos;
 			const ExtTask tk = P.ext_tasks[ti];
 			const i64 r = (i64)tk.r;

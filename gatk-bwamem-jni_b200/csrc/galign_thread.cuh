@@ -48,13 +48,16 @@ DEV void thread_galign_queue(const BatchParams& P, i64 n_tasks, u32* counter, Wa
 	int w = 0, n_col = 0, zs = 0, i = 0;
 	u64 cells = 0, n_glb = 0;
 	u32 pac_word = 0; i64 pac_widx = -1;
-#define GA_INVALID() do { P.ga_res[tid].valid = 0; phase = GA_FETCH; } while (0)
+// a task this formulation cannot take goes on the list of the warp-per-task kernel (wbody_galign_fb); valid = 0 stands
+// until that kernel has produced the alignment (an item whose task stays invalid is redone by a warp as a whole)
+#define GA_INVALID() do { P.ga_res[tid].valid = 0; { const u32 s_ = atomic_add_u32(P.n_ga_fb, 1u); P.ga_fb[s_] = (u32)tid; } phase = GA_FETCH; } while (0)
 	for (;;) {
 		while (!in_dp && !done) {
 			switch (phase) {
 			case GA_FETCH: {
 				tid = (i64)atomic_add_u32(counter, 1u);
 				if (tid >= n_tasks) { done = true; break; }
+				if (P.ga_order) tid = (i64)P.ga_order[n_tasks - 1 - tid]; // tasks by descending cost: the lanes of a warp hold similar ones
 				tk = P.ga_tasks[tid];
 				l_query = tk.qe - tk.qb; rlen = (int)(tk.re - tk.rb);
 				if (l_query <= 0 || tk.rb >= tk.re || (tk.rb < l_pac && tk.re > l_pac) || l_query > wm.cap) { GA_INVALID(); break; }

@@ -9,6 +9,7 @@
 #include "chain.cuh"
 #include "finalize.cuh"
 #include "rescue.cuh"
+#include "sw_thread.cuh"
 
 struct BatchParams {
 	DevIndex x;
@@ -39,6 +40,9 @@ struct BatchParams {
 	// mate rescue (rescue.cuh)
 	u32* nb; SwTask* sw_tasks; u8* sw_state; u32* sw_list; u32* sw_n_list; u32* max_nb; u32* multi; u32* n_multi; int round; int rescued;
 	u32* rs_heavy; u32* n_rs_heavy; // rescue replay by a warp (rescue.cuh rescue_is_heavy)
+	// thread-per-task rescue alignments (sw_thread.cuh): score tables, shared-memory words per array, global scratch, and the
+	// lists of tasks that need the reverse pass / stay with the warp-per-task kernel
+	u64 swtab[4]; int sw_shift, sw_mmax, tsw_capw, tsw_brow_cap; u32* tsw_hmax; u64* tsw_brow; u32* sw_rev; u32* n_sw_rev; u32* sw_fb; u32* n_sw_fb;
 	Reg* ws_rt; i64* ws_rkey; u32* ws_rrank; int ws_rt_cap; // per-warp region-list scratch (warp_sort_dedup_fast)
 	u8* spec_state; u32* spec_task; u32* n_reg0; int force_fb; // speculative rescue (rescue.cuh); multi / n_multi double as the fallback list
 	PeStat pes[4];
@@ -50,17 +54,23 @@ struct BatchParams {
 	// warp scratch (per resident warp)
 	u8* ws_z; size_t ws_z_cap; u32* ws_cigar; int ws_cigar_cap; char* ws_md; int ws_md_cap; char* ws_xa; int ws_xa_cap; u64* ws_brow; int ws_brow_cap;
 	int wm_cap;             // per-warp DP column capacity
+	int wm_smem_cap;        // ... as far as the rows live in shared memory: wm_cap, or 0 when
+	u8* ws_rows; size_t ws_rows_stride; // the rows of a warp slot live in global memory (batches of long reads: warp_smem_bytes(wm_cap) exceeds an SM)
 	// thread scratch (per resident thread of the thread-per-item kernels): DP rows, traceback, cigar, MD, XA
 	u8* t_buf; size_t t_stride; int t_z_cap, t_cigar_cap, t_md_cap, t_xa_cap;
 	u32* redo_list; u32* n_redo; // items a thread-level kernel handed over to the warp-level kernel
 	u32* heavy_list; u32* n_heavy; int light_max_seeds, light_max_chains; // extension: reads with many seeds go to the warp-level kernel
 	int tx_chunk;                           // thread-level extension: cells of one DP row per visit of the row site
+	u32* flt_tasks; u32* n_flt_tasks; // mem_flt_chained_seeds: (read, seed slot) pairs
 	ExtTask* ext_tasks; u32* n_ext_tasks; ExtRes* ext_res; i64* ck_rmax; // per-seed extension tasks, results, per-chain windows
 	u32* ext_key_l; u32* ext_key_r; const u32* ext_order_l; const u32* ext_order_r; // query length of a task's left / right side; task indices ordered by it (nullptr: unordered)
 	int ext_sides;          // the side-task route (extend_thread.cuh thread_extend_sides) is in use: tasks carry keys
+	u32 ext_lo, ext_hi;     // one side launch covers positions [ext_lo, ext_hi) of the order (a class of query lengths)
+	int ext_rw;             // ... with shared-memory rows of ext_rw cells per thread (query lengths < ext_rw)
 	u32* chain_heavy; u32* n_chain_heavy; int chain_heavy_seeds; // reads chained by a warp
 	int chain_listed;       // the list of those reads was written beforehand (body_chain_classify): body_chain only skips them
 	GaTask* ga_tasks; GaRes* ga_res; u32* n_ga_tasks; u32 ga_cap; u32* ga_item0; u32* ga_itemn; // two-pass finalize (galign_thread.cuh)
+	u32* ga_key; const u32* ga_order; u32* ga_fb; u32* n_ga_fb; // cost key per task, tasks ordered by it, tasks left to the warp-per-task kernel
 	int use_ext_res;        // wbody_extend consumes ext_res (set for the replay launch of the heavy reads only)
 	int t_ext_rw;           // thread-level extension: shared-memory words per thread (DP row, doubling as the two NW rings)
 	u64 rowpack[5];         // byte c of rowpack[t] = mat[t*5 + c] (score of query code c against target base t)
@@ -228,10 +238,93 @@ DEV void wbody_chain_heavy(const BatchParams& P, i64 item, WarpMem& wm, WarpScra
 	ONE_LANE { P.n_ck[r] = (u32)nck; P.n_ks[r] = (u32)nks; }
 }
 
+// ---- mem_flt_chained_seeds / mem_seed_sw (SURVEY.md App. B.5 tail; reads long enough that 5.5 ln l <= 0.05 l, or
+// min_chain_weight > 0): every seed of a kept chain shorter than 200 bases is re-scored by a local alignment of the
+// seed +-50 bases against the reference +-50 bases; seeds scoring below min_HSP_score are dropped from their chain.
+DEV bool flt_applies(const DevIndex& x, const MemOpt& opt, int l_query, int* min_hsp, u32* err)
+{
+	// log(l_query) from the host's table (glibc values, hazard H5); the arithmetic is bwa's: float constants, double products
+	double lg = 0.;
+	if (!opt.min_chain_weight) { if (l_query < x.log_tab_n) lg = x.log_tab[l_query]; else { atomic_or_u32(err, ERR_QLEN_OVERFLOW); return false; } }
+	const double min_l = opt.min_chain_weight ? (double)(1.1f * (float)opt.min_chain_weight) : (double)5.5f * lg;
+	*min_hsp = (int)((double)opt.a * min_l + .499);
+	return !(min_l > (double)(0.05f * (float)l_query));
+}
+// thread per read: one task per seed of its kept chains (task = slot of the seed in the kept-seed pool)
+DEV void body_flt_gen(const BatchParams& P, i64 r)
+{
+	const int l_query = (int)(P.seq_off[r + 1] - P.seq_off[r] - 1);
+	int min_hsp;
+	if (l_query < 1 || P.n_ck[r] == 0 || !flt_applies(P.x, P.opt, l_query, &min_hsp, P.err)) return;
+	const u64 t0 = P.seed_off[r];
+	const u32 nks = P.n_ks[r];
+	if (!nks) return;
+	const u32 base = atomic_add_u32(P.n_flt_tasks, nks);
+	for (u32 k = 0; k < nks; ++k) { P.flt_tasks[2 * (size_t)(base + k)] = (u32)r; P.flt_tasks[2 * (size_t)(base + k) + 1] = k; }
+}
+// warp per task: mem_seed_sw.  The score goes to tmp32[slot] (-1: the seed is exempt).
+template <int W>
+DEV void wbody_flt_sw(const BatchParams& P, i64 item, WarpMem& wm, WarpScratch& ws)
+{
+	LANE_DECL;
+	const i64 r = (i64)P.flt_tasks[2 * (size_t)item];
+	const u64 slot = P.seed_off[r] + P.flt_tasks[2 * (size_t)item + 1];
+	const Seed s = P.ks[slot];
+	const int l_query = (int)(P.seq_off[r + 1] - P.seq_off[r] - 1);
+	const u8* query = P.seq + P.seq_off[r];
+	const i64 l_pac = P.x.l_pac;
+	int score = -1;
+	if (s.len < 200) {
+		int qb = s.qbeg, qe = s.qbeg + s.len;
+		i64 rb = s.rbeg, re = s.rbeg + s.len;
+		const i64 mid = (rb + re) >> 1;
+		qb -= 50; qb = qb > 0 ? qb : 0;
+		qe += 50; qe = qe < l_query ? qe : l_query;
+		rb -= 50; rb = rb > 0 ? rb : 0;
+		re += 50; re = re < l_pac << 1 ? re : l_pac << 1;
+		if (rb < l_pac && l_pac < re) { if (mid < l_pac) re = l_pac; else rb = l_pac; }
+		if (!(qe - qb >= 200 || re - rb >= 200)) {
+			ref_clip_window(P.x, rb, mid, re); // bns_fetch_seq clips the window to the contig of its middle
+			const int qlen = qe - qb, tlen = (int)(re - rb);
+			// ksw_align2 without KSW_XBYTE: the 16-bit kernel (8 lanes); only the forward score is consumed
+			const int lanes_simd = 8, slen = (qlen + lanes_simd - 1) / lanes_simd, plen = slen * lanes_simd;
+			if (plen + 2 > wm.cap) { ONE_LANE { atomic_or_u32(ws.err, ERR_QLEN_OVERFLOW); } }
+			else {
+				FOR_LANES { for (int j = lane; j < plen; j += W) WQ(wm, j) = j < qlen ? query[qb + j] : (u8)5; }
+				WARP_SYNC();
+				TAcc ta; ta.base = rb; ta.stride = 1; ta.piv = -1;
+				const SwFwd fw = warp_sw_striped<W>(P.x, P.opt, wm, lanes_simd, false, qlen, tlen, ta, KSW_XSTART, ws.brow, P.cnt ? &P.cnt->cells_msw : nullptr);
+				score = fw.score;
+			}
+		}
+	}
+	ONE_LANE { P.tmp32[slot] = (u32)score; }
+}
+// thread per read: drop the seeds that scored below min_HSP_score, chain by chain, keeping the order
+DEV void body_flt_apply(const BatchParams& P, i64 r)
+{
+	const int l_query = (int)(P.seq_off[r + 1] - P.seq_off[r] - 1);
+	int min_hsp;
+	if (l_query < 1 || P.n_ck[r] == 0 || !flt_applies(P.x, P.opt, l_query, &min_hsp, P.err)) return;
+	const u64 t0 = P.seed_off[r];
+	const int nck = (int)P.n_ck[r];
+	for (int c = 0; c < nck; ++c) {
+		ChainK& ck = P.ck[t0 + c];
+		Seed* seeds = P.ks + t0 + ck.seed_start;
+		u32 k = 0;
+		for (u32 j = 0; j < ck.n_seeds; ++j) {
+			Seed s = seeds[j];
+			const int sc = (int)P.tmp32[t0 + ck.seed_start + j];
+			if (sc < 0 || sc >= min_hsp) { s.score = sc < 0 ? s.len * P.opt.a : sc; seeds[k++] = s; }
+		}
+		ck.n_seeds = k;
+	}
+}
+
 DEV void make_warp_ctx(const BatchParams& P, i64 warp_slot, u8* smem, WarpMem& wm, WarpScratch& ws)
 {
 	int cap = P.wm_cap;
-	i32* p = (i32*)smem;
+	i32* p = P.ws_rows ? (i32*)(P.ws_rows + (size_t)warp_slot * P.ws_rows_stride) : (i32*)smem;
 	wm.H = p; wm.E = p + (cap + 2); wm.H2 = p + 2 * (cap + 2); wm.Hm = p + 3 * (cap + 2); wm.fend = p + 4 * (cap + 2);
 	wm.ringH = nullptr; wm.ringE = nullptr; wm.ring_n = 0; wm.ring_stride = 0;
 	wm.q = (u8*)(p + 4 * (cap + 2) + 16); wm.q_stride = 1;
@@ -362,6 +455,74 @@ DEV void wbody_rescue_sw(const BatchParams& P, i64 item, WarpMem& wm, WarpScratc
 	RescueIO io = make_rescue_io(P);
 	rescue_sw<W>(P.x, P.opt, wm, ws, P.cnt, io, (u32)item); // tasks are stored compactly: the item is the task index
 }
+
+// the warp-per-task kernel over the tasks the thread-level one left on its fall-back list
+template <int W>
+DEV void wbody_rescue_sw_fb(const BatchParams& P, i64 item, WarpMem& wm, WarpScratch& ws)
+{
+	RescueIO io = make_rescue_io(P);
+	rescue_sw<W>(P.x, P.opt, wm, ws, P.cnt, io, P.sw_fb[item]);
+}
+HOSTDEV size_t tsw_block_smem_bytes(int block_threads, int capw) { return (size_t)block_threads * (size_t)capw * 10; }
+#ifdef B200_SIM
+static u32 g_sim_tsw_h[4096], g_sim_tsw_e[4096]; static u16 g_sim_tsw_s[4096];
+#endif
+// DIR 0: the forward pass of every task (tasks with a score at or above the threshold are listed for the reverse pass);
+// DIR 1: the reverse pass of the listed tasks.  A warp takes 32 tasks at a time.
+template <int DIR>
+DEV void thread_sw_queue(const BatchParams& P, u32* counter, i64 tid)
+{
+	TswMem tm;
+	tm.capw = P.tsw_capw;
+#ifdef B200_SIM
+	tm.H = g_sim_tsw_h; tm.E = g_sim_tsw_e; tm.sel = g_sim_tsw_s; tm.stride = 1; if (tm.capw > 4096) tm.capw = 4096;
+#else
+	extern __shared__ __align__(16) u8 tsm_[];
+	const int T = (int)blockDim.x;
+	tm.H = (u32*)tsm_ + threadIdx.x; tm.E = (u32*)tsm_ + (size_t)tm.capw * T + threadIdx.x; tm.sel = (u16*)(tsm_ + (size_t)tm.capw * T * 8) + threadIdx.x; tm.stride = T;
+#endif
+	tm.hmax = P.tsw_hmax + (size_t)(tid >> 5) * (size_t)P.tsw_capw * 32 + (size_t)(tid & 31); tm.hmax_stride = 32;
+	tm.brow = P.tsw_brow + (size_t)tid * (size_t)P.tsw_brow_cap; tm.brow_cap = P.tsw_brow_cap;
+	const i64 n = DIR == 0 ? (i64)*P.sw_n_list : (i64)*P.n_sw_rev;
+	const int lane = simt_lane();
+	const int thr = P.opt.min_seed_len * P.opt.a; // KSW_XSUBO threshold of mem_matesw
+	u64 cells = 0, n_msw = 0;
+	for (;;) {
+		u32 base = 0;
+		if (lane == 0) base = atomic_add_u32(counter, (u32)SIMT_GROUP);
+		base = lane_bcast0(base);
+		if ((i64)base >= n) break;
+		const i64 idx = (i64)base + lane;
+		if (idx < n) {
+			const u32 id = DIR == 0 ? (u32)idx : P.sw_rev[idx];
+			SwTask t = P.sw_tasks[id];
+			const u8* ms = P.seq + P.seq_off[t.read];
+			const int l_ms = (int)(P.seq_off[t.read + 1] - P.seq_off[t.read] - 1);
+			const int tlen = (int)(t.re - t.rb);
+			if (DIR == 0) {
+				if (!tsw_takes(P.opt, l_ms, tlen, tm.capw, tm.brow_cap)) { const u32 slot = atomic_add_u32(P.n_sw_fb, 1u); P.sw_fb[slot] = id; }
+				else {
+					QAcc qa; qa.ms = ms; qa.l_ms = l_ms; qa.is_rev = t.is_rev; qa.piv = -1;
+					TAcc ta; ta.base = t.rb; ta.stride = 1; ta.piv = -1;
+					const SwFwd fw = tsw_pass_u8(P.x, P.opt, tm, P.swtab, P.sw_shift, P.sw_mmax, l_ms, qa, tlen, ta, KSW_XSUBO | KSW_XSTART | KSW_XBYTE | thr, cells);
+					++n_msw;
+					SwTask* o = &P.sw_tasks[id];
+					o->score = fw.score; o->te = fw.te; o->qe = fw.qe; o->score2 = fw.score2; o->te2 = fw.te2; o->tb = -1; o->qb = -1;
+					if (!(fw.score < thr)) { const u32 slot = atomic_add_u32(P.n_sw_rev, 1u); P.sw_rev[slot] = id; } // XSUBO: the start is searched only for scores at or above the threshold
+				}
+			} else {
+				QAcc qa; qa.ms = ms; qa.l_ms = l_ms; qa.is_rev = t.is_rev; qa.piv = t.qe;
+				TAcc tr; tr.base = t.rb; tr.stride = 1; tr.piv = t.te; // target prefix [0, te] reversed, the rest untouched
+				const SwFwd rv = tsw_pass_u8(P.x, P.opt, tm, P.swtab, P.sw_shift, P.sw_mmax, t.qe + 1, qa, tlen, tr, KSW_XSTOP | t.score, cells);
+				if (t.score == rv.score) { SwTask* o = &P.sw_tasks[id]; o->tb = t.te - rv.te; o->qb = t.qe - rv.qe; }
+			}
+		}
+		warp_converge();
+	}
+	if (P.cnt) { if (cells) atomic_add_u64(&P.cnt->cells_msw, cells); if (n_msw) atomic_add_u64(&P.cnt->n_msw, n_msw); }
+}
+DEV void body_tsw_fwd_q(const BatchParams& P, i64 n, u32* counter, i64 tid) { (void)n; thread_sw_queue<0>(P, counter, tid); }
+DEV void body_tsw_rev_q(const BatchParams& P, i64 n, u32* counter, i64 tid) { (void)n; thread_sw_queue<1>(P, counter, tid); }
 
 struct FinalMode { int mode; GaTask* lt; int lt_n; const GaRes* res; int res_n, res_k; }; // how warp_reg2aln obtains alignments
 DEV void make_final_ctx(const BatchParams& P, WarpMem& wm, WarpScratch& ws, FinalCtx& f, const FinalMode* fm = nullptr)
@@ -613,11 +774,34 @@ DEV void body_ext_prep(const BatchParams& P, i64 r)
 		++base;
 	}
 }
-// the two side launches (extend_thread.cuh): left, then right
-DEV void body_ext_left_q(const BatchParams& P, i64 n, u32* counter, i64 tid) { (void)n; u32* const lerr = thread_err_word(P, tid); *lerr = 0; ThreadExtMem tm; WarpMem wm; WarpScratch ws; make_thread_ext_ctx<u32>(P, tid, tm, wm, ws, lerr, false); thread_extend_sides<0, u32>(P, counter, tm); }
-DEV void body_ext_right_q(const BatchParams& P, i64 n, u32* counter, i64 tid) { (void)n; u32* const lerr = thread_err_word(P, tid); *lerr = 0; ThreadExtMem tm; WarpMem wm; WarpScratch ws; make_thread_ext_ctx<u32>(P, tid, tm, wm, ws, lerr, false); thread_extend_sides<1, u32>(P, counter, tm); }
-DEV void body_ext_left_q8(const BatchParams& P, i64 n, u32* counter, i64 tid) { (void)n; u32* const lerr = thread_err_word(P, tid); *lerr = 0; ThreadExtMem tm; WarpMem wm; WarpScratch ws; make_thread_ext_ctx<u16>(P, tid, tm, wm, ws, lerr, false); thread_extend_sides<0, u16>(P, counter, tm); }
-DEV void body_ext_right_q8(const BatchParams& P, i64 n, u32* counter, i64 tid) { (void)n; u32* const lerr = thread_err_word(P, tid); *lerr = 0; ThreadExtMem tm; WarpMem wm; WarpScratch ws; make_thread_ext_ctx<u16>(P, tid, tm, wm, ws, lerr, false); thread_extend_sides<1, u16>(P, counter, tm); }
+// Shared memory of a side launch: per thread a DP row of rw cells and the rw query codes of the side, both interleaved
+// over the threads of the block (element k at (k * threads + tid) * element size: bank tid % 32 for 4-byte elements).
+// The launches are split by query-length class, so short sides -- the bulk -- run with small rows and many resident warps.
+HOSTDEV size_t side_smem_bytes(int block_threads, int rw, int cell) { return (size_t)block_threads * ((((size_t)rw * cell + 3) & ~(size_t)3) + (size_t)((rw + 3) & ~3)); }
+#ifdef B200_SIM
+static u32 g_sim_side_row[65536]; static u8 g_sim_side_q[65536];
+#endif
+template <class CELL>
+DEV void make_side_mem(const BatchParams& P, ThreadExtMem& tm)
+{
+	const int rw = P.ext_rw;
+#ifdef B200_SIM
+	tm.row = (void*)g_sim_side_row; tm.row_stride = 1; tm.row_cap = rw < 65536 ? rw : 65536;
+	tm.rd = g_sim_side_q; tm.rd_stride = 1; tm.rd_cap = tm.row_cap;
+#else
+	extern __shared__ __align__(16) u8 tsm_[];
+	const int st = (int)blockDim.x;
+	const size_t row_bytes = (((size_t)rw * sizeof(CELL)) + 3) & ~(size_t)3;
+	tm.row = (void*)(tsm_ + (size_t)threadIdx.x * sizeof(CELL)); tm.row_stride = st; tm.row_cap = rw;
+	tm.rd = tsm_ + (size_t)st * row_bytes + threadIdx.x; tm.rd_stride = st; tm.rd_cap = rw;
+#endif
+	tm.rowpack = P.rowpack;
+}
+// the side launches (extend_thread.cuh): left, then right
+DEV void body_ext_left_q(const BatchParams& P, i64 n, u32* counter, i64 tid) { (void)n; (void)tid; ThreadExtMem tm; make_side_mem<u32>(P, tm); thread_extend_sides<0, u32>(P, counter, tm); }
+DEV void body_ext_right_q(const BatchParams& P, i64 n, u32* counter, i64 tid) { (void)n; (void)tid; ThreadExtMem tm; make_side_mem<u32>(P, tm); thread_extend_sides<1, u32>(P, counter, tm); }
+DEV void body_ext_left_q8(const BatchParams& P, i64 n, u32* counter, i64 tid) { (void)n; (void)tid; ThreadExtMem tm; make_side_mem<u16>(P, tm); thread_extend_sides<0, u16>(P, counter, tm); }
+DEV void body_ext_right_q8(const BatchParams& P, i64 n, u32* counter, i64 tid) { (void)n; (void)tid; ThreadExtMem tm; make_side_mem<u16>(P, tm); thread_extend_sides<1, u16>(P, counter, tm); }
 // replay of the light reads (thread per read): mem_chain2aln's decisions over the finished extensions, then region
 // de-duplication.  A missing extension, or a patching alignment beyond the thread-level rows, hands the read to the
 // warp kernel (heavy list), which redoes it from the chains.
@@ -686,6 +870,44 @@ DEV void body_final_se_t(const BatchParams& P, i64 r, i64 tid)
 	wbody_final_se<1>(P, r, wm, ws);
 	if (err_peek(lerr)) { u32 slot = atomic_add_u32(P.n_redo, 1u); P.redo_list[slot] = (u32)r; }
 }
+// cost class of an alignment task (sort key): 0 blank, 1 ungapped (a direct sum), else ~ reference rows x band columns
+DEV u32 ga_cost_key(const MemOpt& opt, const GaTask& t)
+{
+	const int l_query = t.qe - t.qb; const i64 rlen = t.re - t.rb;
+	if (l_query <= 0 || rlen <= 0) return 0u;
+	if ((i64)l_query == rlen && t.w2 == 0) return 1u;
+	int w = t.w2 < opt.w << 2 ? t.w2 : opt.w << 2;
+	const i64 dl = rlen > l_query ? rlen - l_query : l_query - rlen;
+	if (w < dl + 3) w = (int)(dl + 3);
+	const i64 band = 2 * (i64)w + 1 < l_query ? 2 * (i64)w + 1 : l_query;
+	const i64 cost = (rlen * band) >> 6;
+	return 2u + (u32)(cost < 65000 ? cost : 65000);
+}
+// the tasks the thread-level kernel could not take (band beyond its shared-memory ring, traceback beyond its scratch),
+// one warp each: mem_reg2aln's band loop around bwa_gen_cigar2, result into the task's GaRes
+template <int W>
+DEV void wbody_galign_fb(const BatchParams& P, i64 item, WarpMem& wm, WarpScratch& ws)
+{
+	LANE_DECL;
+	const u32 tid = P.ga_fb[item];
+	const GaTask tk = P.ga_tasks[tid];
+	const MemOpt& opt = P.opt;
+	int w2 = tk.w2, i = 0, score = 0, last_sc = -(1 << 30), NM = -1, nc = 0, ml = 0;
+	bool ok = true;
+	do {
+		w2 = w2 < opt.w << 2 ? w2 : opt.w << 2;
+		ok = warp_gen_cigar2<W>(P.x, opt, wm, ws, P.cnt, w2, tk.qe - tk.qb, P.seq + tk.qoff + tk.qb, tk.rb, tk.re, &score, true, &nc, &NM, &ml);
+		if (!ok || score == last_sc || w2 == opt.w << 2) break;
+		last_sc = score;
+		w2 <<= 1;
+	} while (++i < 3 && score < tk.truesc - opt.a);
+	GaRes* o = &P.ga_res[tid];
+	if (!ok || nc > GA_CIG_CAP || ml > GA_MD_CAP) return; // (valid stays 0: the item is redone as a whole)
+	FOR_LANES { for (int k = lane; k < nc; k += W) o->cigar[k] = ws.cigar[k]; for (int k = lane; k < ml; k += W) o->md[k] = ws.md[k]; }
+	ONE_LANE { o->score = score; o->NM = NM; o->nc = nc; o->ml = ml; o->valid = 1; }
+	WARP_SYNC();
+}
+
 // ---- two-pass finalize (galign_thread.cuh): collect the alignment requests of an item, later consume their results
 DEV void final_collect_item(const BatchParams& P, i64 item, i64 tid, bool pe)
 {
@@ -701,10 +923,10 @@ DEV void final_collect_item(const BatchParams& P, i64 item, i64 tid, bool pe)
 		if ((u64)base + n > (u64)P.ga_cap) { // the pool is full: a warp redoes the item.  The counter stays above ga_cap; the task kernel runs
 			direct = true;                    // min(counter, ga_cap) slots, so the slots this item reserved below the cap are blanked (l_query = 0: skipped)
 			GaTask z; memset(&z, 0, sizeof(z));
-			for (u64 k = base; k < (u64)P.ga_cap; ++k) P.ga_tasks[k] = z;
+			for (u64 k = base; k < (u64)P.ga_cap; ++k) { P.ga_tasks[k] = z; if (P.ga_key) P.ga_key[k] = 0u; }
 		}
 	}
-	if (!direct) for (u32 k = 0; k < n; ++k) P.ga_tasks[base + k] = lt[k];
+	if (!direct) for (u32 k = 0; k < n; ++k) { P.ga_tasks[base + k] = lt[k]; if (P.ga_key) P.ga_key[base + k] = ga_cost_key(P.opt, lt[k]); }
 	P.ga_item0[item] = base; P.ga_itemn[item] = direct ? 0xffffffffu : n;
 }
 DEV void final_consume_item(const BatchParams& P, i64 item, i64 tid, bool pe)

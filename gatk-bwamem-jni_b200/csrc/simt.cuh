@@ -62,6 +62,13 @@ template <int W> DEV i64 wv_reduce_max64_(const i64& v) { i64 r = v; if (W == 32
 template <int W> DEV i64 wv_reduce_min64_(const i64& v) { i64 r = v; if (W == 32) for (int d = 16; d; d >>= 1) { i64 o = __shfl_xor_sync(FULLMASK, r, d); r = o < r ? o : r; } return r; }
 #define wv_reduce_max64(v) wv_reduce_max64_<W>(v)
 #define wv_reduce_min64(v) wv_reduce_min64_<W>(v)
+// Blackwell DPX: two signed 16-bit cells per 32-bit register (VIADDMNMX.S16x2[.RELU], VIMNMX3.S16x2 in SASS)
+DEV u32 dpx_addmin_s16x2(u32 a, u32 b, u32 c) { return __viaddmin_s16x2(a, b, c); }            // min(a + b, c) per half
+DEV u32 dpx_addmax_relu_s16x2(u32 a, u32 b, u32 c) { return __viaddmax_s16x2_relu(a, b, c); }  // max(a + b, c, 0) per half
+DEV u32 dpx_max3_s16x2(u32 a, u32 b, u32 c) { return __vimax3_s16x2(a, b, c); }                // max(a, b, c) per half
+DEV u32 v_add2(u32 a, u32 b) { return __vadd2(a, b); }                                         // a + b per half (wrapping)
+DEV u32 v_maxs2(u32 a, u32 b) { return __vmaxs2(a, b); }                                       // max(a, b) per half (signed)
+DEV u32 byte_perm(u32 a, u32 b, u32 s) { return __byte_perm(a, b, s); }                        // PRMT: 4 bytes of {a, b} picked by nibbles (bit 3: sign fill)
 // full-mask vote of a thread-per-item kernel whose 32 lanes all take part (persistent queue kernels)
 DEV bool lanes_all(bool p) { return __all_sync(FULLMASK, p) != 0; }
 // thread-per-item kernels that hand out work to a whole warp at a time: lanes per hand-out, this thread's lane, a
@@ -111,6 +118,19 @@ template <int W> DEV int wv_reduce_add_(const int (&v)[32]) { int m = 0; for (in
 #define wv_reduce_add(v) wv_reduce_add_<W>(v)
 #define wv_ballot(p) wv_ballot_<W>(p)
 #define wv_get(v, l) wv_get_<W>(v, l)
+static inline i32 h16_(u32 v, int k) { return (i32)(i16)(u16)(v >> (16 * k)); }
+static inline u32 pk16_(i32 lo, i32 hi) { return (u32)(u16)(i16)lo | (u32)(u16)(i16)hi << 16; }
+DEV u32 dpx_addmin_s16x2(u32 a, u32 b, u32 c) { i32 r[2]; for (int k = 0; k < 2; ++k) { i32 t = (i32)(i16)(h16_(a, k) + h16_(b, k)); r[k] = t < h16_(c, k) ? t : h16_(c, k); } return pk16_(r[0], r[1]); }
+DEV u32 dpx_addmax_relu_s16x2(u32 a, u32 b, u32 c) { i32 r[2]; for (int k = 0; k < 2; ++k) { i32 t = (i32)(i16)(h16_(a, k) + h16_(b, k)); t = t > h16_(c, k) ? t : h16_(c, k); r[k] = t > 0 ? t : 0; } return pk16_(r[0], r[1]); }
+DEV u32 dpx_max3_s16x2(u32 a, u32 b, u32 c) { i32 r[2]; for (int k = 0; k < 2; ++k) { i32 t = h16_(a, k) > h16_(b, k) ? h16_(a, k) : h16_(b, k); r[k] = t > h16_(c, k) ? t : h16_(c, k); } return pk16_(r[0], r[1]); }
+DEV u32 v_add2(u32 a, u32 b) { return pk16_(h16_(a, 0) + h16_(b, 0), h16_(a, 1) + h16_(b, 1)); }
+DEV u32 v_maxs2(u32 a, u32 b) { return pk16_(h16_(a, 0) > h16_(b, 0) ? h16_(a, 0) : h16_(b, 0), h16_(a, 1) > h16_(b, 1) ? h16_(a, 1) : h16_(b, 1)); }
+DEV u32 byte_perm(u32 a, u32 b, u32 s)
+{
+	const u64 src = (u64)a | (u64)b << 32; u32 r = 0;
+	for (int k = 0; k < 4; ++k) { const u32 n = s >> (4 * k) & 0xf; u32 byte = (u32)(src >> (8 * (n & 7)) & 0xff); if (n & 8) byte = (byte & 0x80) ? 0xffu : 0u; r |= byte << (8 * k); }
+	return r;
+}
 DEV bool lanes_all(bool p) { return p; } // the harness runs one thread at a time
 #define SIMT_GROUP 1
 DEV int simt_lane() { return 0; }

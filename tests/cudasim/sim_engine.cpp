@@ -37,6 +37,11 @@ static void rt_sort_pairs_u32(const uint32_t* kin, uint32_t* kout, const uint32_
 	for (uint64_t i = 0; i < n; ++i) { kout[i] = kin[ord[i]]; vout[i] = vin[ord[i]]; }
 }
 static void rt_iota_u32(uint32_t* p, uint64_t n) { for (uint64_t i = 0; i < n; ++i) p[i] = (uint32_t)i; }
+static void rt_lower_bounds_u32(const uint32_t* keys, uint64_t n, const uint32_t* thr, int n_thr, uint32_t* out)
+{
+	for (int k = 0; k < n_thr; ++k) out[k] = (uint32_t)(std::lower_bound(keys, keys + n, thr[k]) - keys);
+}
+static void rt_set_slot_caps(int64_t, int64_t) {}
 static void rt_fork_aux() {}
 static void rt_back_to_main() {}
 static void rt_join_aux(const char*) {}
@@ -52,6 +57,7 @@ static uint64_t rt_scan_u32(const uint32_t* in, uint64_t* out, uint64_t n) { uin
 #define RT_THREADS_TID_RING(body, P, n) RT_THREADS_TID(body, P, n)
 #define RT_THREADS_QUEUE_SMEM(body, P, n, bytes) do { u32 c_ = 0; body(P, (int64_t)(n), &c_, 0); } while (0)
 #define THREADS_PER_BLOCK 128
+#define WARPS_PER_BLOCK 4
 #define RT_WARPS(wbody, P, n) do { \
 	std::vector<uint8_t> sm_(warp_smem_bytes((P).wm_cap) + 64); \
 	WarpMem wm_; WarpScratch ws_; make_warp_ctx(P, 0, sm_.data(), wm_, ws_); \

@@ -93,3 +93,44 @@ def test_sim_pool_overflows_fall_back(small_genome, monkeypatch, env):
     monkeypatch.setenv(env, "1")
     b = run_blob(sim_lib(), img, blob, 2)
     assert a == b, first_diff(a, b, blob, True)
+
+
+LONG_CASES = [(800, 40, dict(err_rate=0.02)), (1500, 24, dict(err_rate=0.03, mut_rate=0.01, indel_frac=0.5)),
+              (5000, 8, dict(err_rate=0.02, mut_rate=0.005, indel_frac=0.4))]
+
+
+@pytest.mark.parametrize("intra", [False, True], ids=["default_options", "intra_ctg_options"])
+@pytest.mark.parametrize("read_len,n,kw", LONG_CASES, ids=[f"{c[0]}bp" for c in LONG_CASES])
+def test_sim_long_reads(small_genome, read_len, n, kw, intra):
+    """Long queries (assembled contigs; BwaMemAligner.setIntraCtgOptions, BwaMemAligner.java:140-146): reads of >= ~730
+    bases enable mem_flt_chained_seeds / mem_seed_sw (B10); reads above 1000 bases run in the long-read mode (warp-level
+    kernels, DP rows and traceback in global memory)."""
+    g, img = small_genome
+    blob, _ = simdata.make_reads(g, 12, n, read_len, False, **kw)
+    setup = (lambda al: al.setIntraCtgOptions()) if intra else None
+    a = run_blob(oracle_lib(), img, blob, 0, None, setup)
+    b = run_blob(sim_lib(), img, blob, 0, None, setup)
+    assert a == b, first_diff(a, b, blob, False)
+
+
+def test_sim_long_read_pairs_and_min_chain_weight(small_genome):
+    g, img = small_genome
+    blob, _ = simdata.make_reads(g, 21, 16, 1200, True, ins_mean=3000, ins_std=200, err_rate=0.02)
+    assert run_blob(sim_lib(), img, blob, 2) == run_blob(oracle_lib(), img, blob, 2)
+    # min_chain_weight > 0 switches the seed filter on for short reads too
+    blob, _ = simdata.make_reads(g, 22, 200, 150, False, err_rate=0.03)
+    setup = lambda al: al.setMinChainWeightOption(40)
+    a = run_blob(oracle_lib(), img, blob, 0, None, setup)
+    b = run_blob(sim_lib(), img, blob, 0, None, setup)
+    assert a == b, first_diff(a, b, blob, False)
+
+
+def test_sim_forced_long_mode_on_short_reads(small_genome, monkeypatch):
+    """The long-read mode (every read on the warp-level kernels, rows in global memory, every finalize item by a warp)
+    forced onto a paired batch of short reads: same records."""
+    g, img = small_genome
+    blob, _ = simdata.make_reads(g, 12, 200, 150, True, repeat_read_frac=0.3, chimeric_frac=0.1)
+    a = run_blob(oracle_lib(), img, blob, 2)
+    monkeypatch.setenv("B200_TEST_LONG_MODE", "1")
+    b = run_blob(sim_lib(), img, blob, 2)
+    assert a == b, first_diff(a, b, blob, True)

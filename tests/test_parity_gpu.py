@@ -81,6 +81,44 @@ def test_intractg_options(small_genome):
     assert a == b, first_diff(a, b, blob, False)
 
 
+LONG_CASES = [(1000, 400, dict(err_rate=0.02)), (5000, 120, dict(err_rate=0.03, mut_rate=0.01, indel_frac=0.5)),
+              (20000, 40, dict(err_rate=0.02, mut_rate=0.005, indel_frac=0.4)), (50000, 12, dict(err_rate=0.01, mut_rate=0.005, indel_frac=0.4))]
+
+
+@pytest.mark.parametrize("intra", [False, True], ids=["default_options", "intra_ctg_options"])
+@pytest.mark.parametrize("read_len,n,kw", LONG_CASES, ids=[f"{c[0]}bp" for c in LONG_CASES])
+def test_long_queries(mid_genome, read_len, n, kw, intra):
+    """Long queries, 1-50 kbp (GATK's SV pipeline aligns assembled contigs with setIntraCtgOptions,
+    BwaMemAligner.java:140-146): mem_flt_chained_seeds / mem_seed_sw on the device and the long-read mode (warp-level
+    kernels with DP rows and traceback in global memory).  Hazard H1: the intra-contig preset changes a/b/gap-open
+    but not the scoring matrix."""
+    g, img = mid_genome
+    blob, _ = simdata.make_reads(g, 12, n, read_len, False, **kw)
+
+    def setup(al):
+        al.setNThreadsOption(8)
+        if intra:
+            al.setIntraCtgOptions()
+    a = run_blob(oracle_lib(), img, blob, 0, None, setup)
+    b = run_blob(engine_lib(), img, blob, 0, None, setup)
+    assert a == b, first_diff(a, b, blob, False)
+
+
+def test_long_and_short_reads_in_one_batch_and_min_chain_weight(mid_genome):
+    g, img = mid_genome
+    short = simdata.split_blob(bytes(simdata.make_reads(g, 31, 300, 150, False)[0]))
+    long_ = simdata.split_blob(bytes(simdata.make_reads(g, 32, 30, 3000, False, err_rate=0.02)[0]))
+    blob = bwa.pack_sequences([r for pair in zip(short[:30], long_) for r in pair] + short[30:])
+    a = run_blob(oracle_lib(), img, blob, 0)
+    b = run_blob(engine_lib(), img, blob, 0)
+    assert a == b, first_diff(a, b, blob, False)
+    blob2, _ = simdata.make_reads(g, 33, 2000, 150, True, err_rate=0.03)
+    setup = lambda al: al.setMinChainWeightOption(40)
+    a = run_blob(oracle_lib(), img, blob2, 2, None, setup)
+    b = run_blob(engine_lib(), img, blob2, 2, None, setup)
+    assert a == b, first_diff(a, b, blob2, True)
+
+
 @pytest.mark.parametrize("paired", [False, True], ids=["se", "pe"])
 def test_engine_matches_oracle_mid(mid_genome, paired):
     g, img = mid_genome
@@ -94,9 +132,9 @@ def test_engine_matches_oracle_mid(mid_genome, paired):
     assert a == b, first_diff(a, b, blob, paired)
 
 
-@pytest.mark.parametrize("env", [None, "B200_TEST_RESCUE_FALLBACK", "B200_TEST_TINY_SCRATCH", "B200_TEST_ALL_LIGHT", "B200_TEST_ALL_HEAVY", "B200_WARP_EXTEND", "B200_NO_EXT_TASKS", "B200_TEST_CHAIN_ALL_WARP", "B200_TEST_CHAIN_ALL_THREAD", "B200_FINAL_ONE_PASS", "B200_SEED_ONE_LAUNCH", "B200_SEED_FUSED_ROUNDS", "B200_TEST_TINY_SEED_POOL", "B200_TX_CHUNK=1", "B200_TX_CHUNK=0", "B200_EXT_WIDE_CELLS", "B200_SEED_NO_OVERLAP", "B200_CHAIN_NO_OVERLAP", "B200_TEST_FINAL_RING", "B200_TEST_TINY_GA_CAP", "B200_TEST_TINY_SEED_TASKS", "B200_EXT_LEGACY", "B200_EXT_NO_SORT"],
+@pytest.mark.parametrize("env", [None, "B200_TEST_RESCUE_FALLBACK", "B200_TEST_TINY_SCRATCH", "B200_TEST_ALL_LIGHT", "B200_TEST_ALL_HEAVY", "B200_WARP_EXTEND", "B200_NO_EXT_TASKS", "B200_TEST_CHAIN_ALL_WARP", "B200_TEST_CHAIN_ALL_THREAD", "B200_FINAL_ONE_PASS", "B200_SEED_ONE_LAUNCH", "B200_SEED_FUSED_ROUNDS", "B200_TEST_TINY_SEED_POOL", "B200_TX_CHUNK=1", "B200_TX_CHUNK=0", "B200_EXT_WIDE_CELLS", "B200_SEED_NO_OVERLAP", "B200_CHAIN_NO_OVERLAP", "B200_TEST_FINAL_RING", "B200_TEST_TINY_GA_CAP", "B200_TEST_TINY_SEED_TASKS", "B200_EXT_LEGACY", "B200_EXT_NO_SORT", "B200_TEST_LONG_MODE", "B200_RESCUE_WARP_SW"],
                          ids=["default", "rescue_fallback", "tiny_scratch", "extend_all_thread", "extend_all_tasks", "extend_all_warp", "extend_heavy_by_warp",
-                              "chain_all_warp", "chain_all_thread", "final_one_pass", "seed_one_launch", "seed_fused_rounds", "seed_pool_overflow", "extend_rows_cell_by_cell", "extend_whole_rows", "extend_wide_cells", "seed_no_stream_overlap", "chain_no_stream_overlap", "final_passes_with_ring_smem", "alignment_task_pool_overflow", "seed_task_list_overflow", "extend_read_level_machine", "extend_tasks_unsorted"])
+                              "chain_all_warp", "chain_all_thread", "final_one_pass", "seed_one_launch", "seed_fused_rounds", "seed_pool_overflow", "extend_rows_cell_by_cell", "extend_whole_rows", "extend_wide_cells", "seed_no_stream_overlap", "chain_no_stream_overlap", "final_passes_with_ring_smem", "alignment_task_pool_overflow", "seed_task_list_overflow", "extend_read_level_machine", "extend_tasks_unsorted", "long_read_mode_forced", "rescue_alignments_by_warps"])
 def test_repeat_heavy_pairs_and_forced_slow_paths(small_genome, monkeypatch, env):
     """Chains of several rescuing hits per read (repeat-derived reads); the same batch with every rescuing read forced
     onto the round-by-round rescue kernels, with thread-level scratch so small that items are handed to warps, and with
