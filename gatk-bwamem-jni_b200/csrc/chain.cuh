@@ -130,7 +130,7 @@ DEV int chain_read(const DevIndex& x, const MemOpt& opt, int len, ChainStageIO& 
 			ChainW& cj = C[ord[kl[k]]];
 			int jb = S[cj.head].qbeg, je = S[cj.tail].qbeg + S[cj.tail].len;
 			int b_max = jb > ib ? jb : ib, e_min = je < ie ? je : ie;
-			if (e_min > b_max) { // ALT contigs are refused at index open, so the is_alt clause is always true
+			if (e_min > b_max && (!x.ctg_alt[cj.rid] || x.ctg_alt[ci.rid])) { // (a chain on an ALT contig never masks one on the primary assembly)
 				int li = ie - ib, lj = je - jb, min_l = li < lj ? li : lj;
 				if ((float)(e_min - b_max) >= (float)min_l * opt.mask_level && min_l < opt.max_chain_gap) {
 					large_ovlp = true;
@@ -251,7 +251,7 @@ DEVNI int chain_read_warp(const DevIndex& x, const MemOpt& opt, int len, ChainSt
 		for (int i = lane; i < n; i += W) {
 			const ChainW& c = C[ord[i]];
 			const u32 qb = (u32)S[c.head].qbeg, qe = (u32)(S[c.tail].qbeg + S[c.tail].len);
-			qbw[i] = (u64)c.w << 32 | (u64)(qe & 0xffffu) << 16 | (u64)(qb & 0xffffu);
+			qbw[i] = (u64)(x.ctg_alt[c.rid] ? 1 : 0) << 63 | (u64)c.w << 32 | (u64)(qe & 0xffffu) << 16 | (u64)(qb & 0xffffu);
 		}
 	}
 	WARP_SYNC();
@@ -261,7 +261,7 @@ DEVNI int chain_read_warp(const DevIndex& x, const MemOpt& opt, int len, ChainSt
 	nk = 1;
 	for (int i = 1; i < n; ++i) {
 		const u64 vi = qbw[i];
-		const int ib = (int)(vi & 0xffffu), ie = (int)(vi >> 16 & 0xffffu), wi = (int)(vi >> 32);
+		const int ib = (int)(vi & 0xffffu), ie = (int)(vi >> 16 & 0xffffu), wi = (int)(vi >> 32 & 0x7fffffffu); const bool alt_i = (vi >> 63) != 0;
 		bool large_ovlp = false, broke = false;
 		for (int k0 = 0; k0 < nk && !broke; k0 += W) {
 			WV(bool, ov); WV(bool, dr);
@@ -270,9 +270,9 @@ DEVNI int chain_read_warp(const DevIndex& x, const MemOpt& opt, int len, ChainSt
 				bool o = false, d = false;
 				if (k < nk) {
 					const u64 vj = qbw[kl[k]];
-					const int jb = (int)(vj & 0xffffu), je = (int)(vj >> 16 & 0xffffu), wj = (int)(vj >> 32);
+					const int jb = (int)(vj & 0xffffu), je = (int)(vj >> 16 & 0xffffu), wj = (int)(vj >> 32 & 0x7fffffffu);
 					const int b_max = jb > ib ? jb : ib, e_min = je < ie ? je : ie;
-					if (e_min > b_max) {
+					if (e_min > b_max && (!(vj >> 63) || alt_i)) {
 						const int li = ie - ib, lj = je - jb, min_l = li < lj ? li : lj;
 						if ((float)(e_min - b_max) >= (float)min_l * opt.mask_level && min_l < opt.max_chain_gap) {
 							o = true;

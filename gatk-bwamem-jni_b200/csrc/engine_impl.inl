@@ -261,7 +261,6 @@ inline bool Engine::open_from_fd(int fd, const std::vector<int>& devices)
 	map = m; map_len = (size_t)st.st_size;
 	if (!img.parse((const uint8_t*)map, map_len)) { last_error = "malformed index image"; return false; }
 	if (img.sa_intv <= 0 || (img.sa_intv & (img.sa_intv - 1))) { last_error = "SA interval must be a power of two"; return false; }
-	for (auto& c : img.contigs) if (c.is_alt) { last_error = "ALT contigs are not supported by this engine"; return false; }
 	if (devices.empty()) { last_error = "no device"; return false; }
 	for (size_t k = 0; k < devices.size(); ++k) {
 		Replica* r = new Replica(); r->dev = devices[k];
@@ -601,14 +600,14 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 			if (overlap) rt_fork_aux();
 			RT_WARPS_DEVN(wbody_seedB_heavy, P, P.n_seed_tasks + 1, (int64_t)n_reads);
 			if (overlap) rt_back_to_main();
-			RT_THREADS_QUEUE_SMEM(body_seedB_q, P, (int64_t)P.seed_task_cap, 0);
+			RT_THREADS_QUEUE_SMEM(body_seedB_q, P, (int64_t)P.seed_task_cap, seed_bwd_smem_bytes(THREADS_PER_BLOCK));
 			if (overlap) rt_join_aux("wbody_seedB_heavy");
 			rt_memset(P.n_seed_tasks, 0, 16);
 			RT_THREADS_QUEUE_SMEM(body_seedF2_q, P, (int64_t)n_reads, 0);
 			if (overlap) rt_fork_aux();
 			RT_WARPS_DEVN(wbody_seedB_heavy, P, P.n_seed_tasks + 1, (int64_t)n_reads);
 			if (overlap) rt_back_to_main();
-			RT_THREADS_QUEUE_SMEM(body_seedB2_q, P, (int64_t)P.seed_task_cap, 0);
+			RT_THREADS_QUEUE_SMEM(body_seedB2_q, P, (int64_t)P.seed_task_cap, seed_bwd_smem_bytes(THREADS_PER_BLOCK));
 			if (overlap) rt_join_aux("wbody_seedB_heavy");
 			RT_THREADS_QUEUE_SMEM(body_seed12_fb_q, P, (int64_t)n_reads, ssm); // (usually an empty list)
 			RT_THREADS_QUEUE_SMEM(body_seed3_q, P, (int64_t)n_reads, ssm);
@@ -686,7 +685,7 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 		// cells: H and E as 8-bit halves when no score of the batch can exceed 255 (the per-read test in the kernel is the
 		// same bound), else as 16-bit halves.  Narrow cells halve the shared memory per thread: more resident warps.
 		int mxs = 0; for (int k = 0; k < 25; ++k) mxs = mxs > opt.mat[k] ? mxs : (int)opt.mat[k];
-		const bool narrow = !cfg.ext_wide_cells && (int64_t)max_len * mxs + opt.pen_clip5 + opt.pen_clip3 <= 255;
+		const bool narrow = !cfg.ext_wide_cells && (int64_t)max_len * (mxs > opt.a ? mxs : opt.a) <= 255;
 		const int cell = narrow ? 2 : 4;
 		if (!narrow && rw * cell < 4 * THREAD_RING_N) rw = 4 * THREAD_RING_N / cell; // wide cells: the patching rings reuse the row (at least THREAD_RING_N / 2 slots)
 		const size_t budget = 200 * 1024; // per block of THREADS_PER_BLOCK threads

@@ -53,7 +53,8 @@ DEV void thread_extend_queue(const BatchParams& P, i64 n_reads, u32* counter, co
 	CELL* const row = (CELL*)tm.row;
 	constexpr int HB = (int)sizeof(CELL) * 4;          // bits of H and of E in one cell
 	constexpr u32 HMASK = (1u << HB) - 1u;
-	// largest score a cell may have to hold (h0 + qlen * max match <= l_query * max match), with the clipping penalties as margin
+	// largest score a cell may have to hold: h0 + qlen * max match <= l_query * max(match, a) -- an extension starts from at
+	// most (bases before it) * a and gains at most max match per base; the clipping bonus is only ever compared, never stored
 	constexpr i64 SCORE_CAP = sizeof(CELL) == 2 ? 255 : 60000;
 	const int chunk = P.tx_chunk > 0 ? P.tx_chunk : 1 << 30;
 	// per-read state
@@ -95,7 +96,7 @@ DEV void thread_extend_queue(const BatchParams& P, i64 n_reads, u32* counter, co
 					res_slot = t0 + ck.seed_start + tk.t;
 					l_query = (int)(P.seq_off[r + 1] - P.seq_off[r] - 1);
 					query = P.seq + P.seq_off[r];
-					if (l_query > tm.rd_cap || (i64)(sizeof(CELL) == 2 ? 1 : 2) * l_query * mx + opt.pen_clip5 + opt.pen_clip3 > SCORE_CAP) { TX_TO_WARP(); break; }
+					if (l_query > tm.rd_cap || (i64)(sizeof(CELL) == 2 ? 1 : 2) * l_query * (mx > opt.a ? mx : opt.a) > SCORE_CAP) { TX_TO_WARP(); break; }
 					for (int j = 0; j < l_query; ++j) tm.rd[(size_t)j * QS] = query[j];
 					seeds = P.ks + t0 + ck.seed_start; cn = 0; // (seed coverage is computed by the replay)
 					s = seeds[tk.t];
@@ -121,8 +122,8 @@ DEV void thread_extend_queue(const BatchParams& P, i64 n_reads, u32* counter, co
 				const u64 t0 = P.seed_off[r];
 				l_query = (int)(P.seq_off[r + 1] - P.seq_off[r] - 1);
 				query = P.seq + P.seq_off[r];
-				// 16-bit storage bound: no H/E value exceeds (seed + left + right) scores <= 2 * l_query * mx, plus the clip bonus
-				if (l_query > tm.rd_cap || (i64)(sizeof(CELL) == 2 ? 1 : 2) * l_query * mx + opt.pen_clip5 + opt.pen_clip3 > SCORE_CAP) { TX_TO_WARP(); break; }
+				// storage bound: no H/E value exceeds (seed + left + right) scores <= l_query * max(match, a)
+				if (l_query > tm.rd_cap || (i64)(sizeof(CELL) == 2 ? 1 : 2) * l_query * (mx > opt.a ? mx : opt.a) > SCORE_CAP) { TX_TO_WARP(); break; }
 				cks = P.ck + t0; ks_base = P.ks + t0; srt = P.srt + t0; av = P.regs_tmp + t0; av_cap = nks;
 				for (int j = 0; j < l_query; ++j) tm.rd[(size_t)j * QS] = query[j];
 				c = -1; n_av = 0; *lerr = 0;
@@ -491,8 +492,8 @@ DEV void thread_extend_sides(const BatchParams& P, u32* counter, const ThreadExt
 			const u8* query = P.seq + P.seq_off[r];
 			ExtRes o = P.ext_res[slot];
 			const int qlen = SIDE == 0 ? s.qbeg : l_query - (s.qbeg + s.len);
-			// 8-/16-bit storage bound: no H/E value exceeds (seed + left + right) scores <= l_query * mx, plus the clip bonus
-			const bool fits = qlen + 1 <= tm.row_cap && qlen <= tm.rd_cap && (i64)(sizeof(CELL) == 2 ? 1 : 2) * l_query * mx + opt.pen_clip5 + opt.pen_clip3 <= TxCell<CELL>::SCORE_CAP;
+			// 8-/16-bit storage bound: no H/E value exceeds (seed + left + right) scores <= l_query * max(match, a)
+			const bool fits = qlen + 1 <= tm.row_cap && qlen <= tm.rd_cap && (i64)(sizeof(CELL) == 2 ? 1 : 2) * l_query * (mx > opt.a ? mx : opt.a) <= TxCell<CELL>::SCORE_CAP;
 			if (SIDE == 0) {
 				if (qlen == 0) { o.score = o.truesc = s.len * opt.a; o.qb = 0; o.rb = s.rbeg; o.w = opt.w; o.valid = 2; }
 				else if (!fits) o.valid = 0; // the replay extends this seed itself

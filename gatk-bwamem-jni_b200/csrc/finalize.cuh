@@ -72,20 +72,42 @@ DEV void mark_primary_core(const MemOpt& opt, int n, Reg* a, u32* z)
 	}
 }
 
-// returns n_pri (== n: ALT contigs are refused at index open)
+// mem_mark_primary_se; returns n_pri, the number of hits on the primary assembly.  With hits on ALT contigs (n_pri < n)
+// the marking runs twice: over all hits (kept in secondary_all; a primary-assembly hit shadowed by an ALT hit remembers
+// that hit's score in alt_sc), then -- hits re-ordered with the primary-assembly ones first -- over those alone.
+// ztmp: n words of scratch (the z list of the core, then the rank table of the re-ordering).
+struct RegLtHash2 { DEVM bool operator()(const Reg& a, const Reg& b) const { return a.is_alt < b.is_alt || (a.is_alt == b.is_alt && (a.score > b.score || (a.score == b.score && a.hash < b.hash))); } };
 template <int W>
 DEVNI int warp_mark_primary_se(const MemOpt& opt, int n, Reg* a, i64 id, u32* ztmp)
 {
 	LANE_DECL;
 	if (n == 0) return 0;
+	int n_pri = 0;
+	for (int i = 0; i < n; ++i) if (!a[i].is_alt) ++n_pri;
 	LANE0_ONLY {
 		for (int i = 0; i < n; ++i) { a[i].sub = a[i].alt_sc = 0; a[i].secondary = a[i].secondary_all = -1; a[i].hash = hash64((u64)(id + i)); }
 		ks_introsort<Reg, RegLtHash>((size_t)n, a, RegLtHash());
 		mark_primary_core(opt, n, a, ztmp);
-		for (int i = 0; i < n; ++i) a[i].secondary_all = a[i].secondary;
+		if (n_pri == n) { for (int i = 0; i < n; ++i) a[i].secondary_all = a[i].secondary; }
+		else {
+			for (int i = 0; i < n; ++i) {
+				a[i].secondary_all = i; // keep the rank of the first round
+				if (!a[i].is_alt && a[i].secondary >= 0 && a[a[i].secondary].is_alt) a[i].alt_sc = a[a[i].secondary].score;
+			}
+			if (n_pri > 0) ks_introsort<Reg, RegLtHash2>((size_t)n, a, RegLtHash2());
+			for (int i = 0; i < n; ++i) ztmp[a[i].secondary_all] = (u32)i;
+			for (int i = 0; i < n; ++i) {
+				if (a[i].secondary >= 0) { a[i].secondary_all = (int)ztmp[a[i].secondary]; if (a[i].is_alt) a[i].secondary = 0x7fffffff; }
+				else a[i].secondary_all = -1;
+			}
+			if (n_pri > 0) { // mark primary for hits to the primary assembly only
+				for (int i = 0; i < n_pri; ++i) { a[i].sub = 0; a[i].secondary = -1; }
+				mark_primary_core(opt, n_pri, a, ztmp);
+			}
+		}
 	}
 	WARP_SYNC();
-	return n;
+	return n_pri;
 }
 
 template <int W>
@@ -332,10 +354,10 @@ DEVNI int warp_gen_xa(FinalCtx& f, int l_query, const u8* query, int n, const Re
 	LANE_DECL;
 	const MemOpt& opt = *f.opt;
 	*xa_off = 0;
-	int cnt = 0;
+	int cnt = 0; bool has_alt = false;
 	double ratio = (double)opt.XA_drop_ratio;
-	for (int i = 0; i < n; ++i) if (get_pri_idx(ratio, a, i) == pri) ++cnt;
-	if (cnt == 0 || cnt > opt.max_XA_hits_alt || cnt > opt.max_XA_hits) return 0; // (no ALT contigs: has_alt is always false)
+	for (int i = 0; i < n; ++i) if (get_pri_idx(ratio, a, i) == pri) { ++cnt; if (a[i].is_alt) has_alt = true; }
+	if (cnt == 0 || cnt > opt.max_XA_hits_alt || (!has_alt && cnt > opt.max_XA_hits)) return 0;
 	char* xa = f.ws->xa; const int cap = f.ws->xa_cap - 32;
 	int xl = 0; bool ovf = false;
 #define XA_PUTC(ch) do { const char c_ = (char)(ch); if (xl < cap) { ONE_LANE_NOSYNC { xa[xl] = c_; } ++xl; } else ovf = true; } while (0)
@@ -720,6 +742,17 @@ DEVNI void warp_sam_pe(FinalCtx& f, u64 id, PairIO& io)
 			h.flag |= 0x40 << i | extra_flag;
 			warp_emit<W>(f, h, &md[!i], xa_off[i], xa_len[i], &io.out[i][0], &st_off[i], md[i].ref_len);
 			io.n_out[i] = 1;
+			if (n_pri[i] < io.n[i]) { // the read has ALT hits: its best ALT hit goes out as a supplementary record
+				const Reg& pa = io.a[i][n_pri[i]];
+				if (!(pa.score < opt.T || pa.secondary >= 0 || !pa.is_alt) && io.out_cap[i] >= 2) {
+					u32 xo = 0; int xl = 0;
+					if (!(opt.flag & MEM_F_ALL)) xl = warp_gen_xa<W>(f, io.l_seq[i], io.seq[i], io.n[i], io.a[i], n_pri[i], &xo);
+					Aln g = warp_reg2aln<W>(f, io.l_seq[i], io.seq[i], &pa);
+					g.flag |= 0x800 | 0x40 << i | extra_flag;
+					warp_emit<W>(f, g, &md[!i], xo, xl, &io.out[i][1]);
+					io.n_out[i] = 2;
+				}
+			}
 		}
 		return;
 	}
@@ -727,7 +760,7 @@ DEVNI void warp_sam_pe(FinalCtx& f, u64 id, PairIO& io)
 	MateDesc h[2];
 	for (int i = 0; i < 2; ++i) {
 		int which = -1;
-		if (io.n[i]) { if (io.a[i][0].score >= opt.T) which = 0; } // (the ALT alternative n_pri < n never applies)
+		if (io.n[i]) { if (io.a[i][0].score >= opt.T) which = 0; else if (n_pri[i] < io.n[i] && io.a[i][n_pri[i]].score >= opt.T) which = n_pri[i]; }
 		Aln t = warp_reg2aln<W>(f, io.l_seq[i], io.seq[i], which >= 0 ? &io.a[i][which] : nullptr);
 		h[i] = mate_of(t, f.ws->cigar);
 	}

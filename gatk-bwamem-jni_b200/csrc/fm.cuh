@@ -531,18 +531,38 @@ DEV void fm_forward_queue(const DevIndex& x, const MemOpt& opt, const SeedSplitI
 
 // The backward sweep of one forward scan.  Candidate a of the textbook list (longest match first) is pool slot
 // c_off + n_c - 1 - a; row i reads candidate j and writes at most j survivors, so the list is compacted in place.
+//
+// A lane per scan.  The candidates of a scan (< SEED_HEAVY_CANDS of them) are copied into the lane's column of shared
+// memory when the scan is taken, so the bookkeeping between two index reads -- which runs with the lanes of a warp
+// diverged -- touches no global memory.  Lanes that have finished their scan wait (state B_IDLE) until SEED_REFILL_MIN
+// lanes of the warp are idle and then take new scans TOGETHER: one reservation, one round of task / candidate loads for
+// all of them, instead of one full memory latency paid by the whole warp for every single lane's fetch.
+#ifndef SEED_REFILL_MIN
+#define SEED_REFILL_MIN 8
+#endif
+HOSTDEV size_t seed_bwd_smem_bytes(int block_threads) { return (size_t)block_threads * SEED_HEAVY_CANDS * 16; }
+#ifdef B200_SIM
+static uint4 g_sim_bwd_cands[SEED_HEAVY_CANDS];
+#endif
 DEV void fm_backward_queue(const DevIndex& x, const MemOpt& opt, const SeedSplitIO& io, i64 n_tasks, u32* counter)
 {
-	enum { B_FETCH, B_ROW, B_ITEM, B_ALLDONE };
-	int st = B_FETCH; int pend = 0; // number of candidates of the current row in flight (0, 1 or 2)
+	enum { B_IDLE, B_ROW, B_ITEM, B_ALLDONE };
+#ifdef B200_SIM
+	uint4* const sc = g_sim_bwd_cands; const size_t SS = 1;
+#else
+	extern __shared__ __align__(16) u8 tsm_[];
+	uint4* const sc = (uint4*)tsm_ + threadIdx.x; const size_t SS = (size_t)blockDim.x;
+#endif
+#define CL(a_) sc[(size_t)(a_) * SS] /* candidate a of the current row's list */
+	const int lane = simt_lane();
+	int st = B_IDLE; int pend = 0; // number of candidates of the current row in flight (0, 1 or 2)
 	SeedTask tk; tk.read = 0; tk.c_off = 0; tk.n_c = 0; tk.start = 0; tk.min_intv = 1;
-	const u8* q = nullptr; uint4* cl = nullptr; // cl[-a] = candidate a
+	const u8* q = nullptr;
 	int i = 0, c = -1, j = 0, n_prev = 0, n_curr = 0;
 	u64 last_size = 0; u32 last_beg = 0, pcur_end = 0; bool have_out = false;
 	BiIntv pcur; pcur.x0 = pcur.x1 = pcur.size = 0;
 	BiIntv pcs[SEED_BWD_WAYS]; u32 pes[SEED_BWD_WAYS];
 	for (int t = 0; t < SEED_BWD_WAYS; ++t) { pcs[t] = pcur; pes[t] = 0; }
-	uint4 nxt = make_uint4(0, 0, 0, 0); // candidate j of the current row, fetched while candidate j - 1 was being extended
 #define B_EMIT_PCUR() do { if (n_curr == 0 && (!have_out || (u32)(i + 1) < last_beg)) { \
 		have_out = true; last_beg = (u32)(i + 1); \
 		if ((int)(pcur_end - (u32)(i + 1)) >= opt.min_seed_len) { /* the length filter of the end of the sweep */ \
@@ -550,49 +570,56 @@ DEV void fm_backward_queue(const DevIndex& x, const MemOpt& opt, const SeedSplit
 			if (slot_ < (u32)io.intv_cap) { Intv t_; t_.x0 = pcur.x0; t_.x1 = pcur.x1; t_.size = pcur.size; t_.beg = (u32)(i + 1); t_.end = pcur_end; io.intv[(size_t)tk.read * io.intv_cap + slot_] = t_; } \
 			else atomic_or_u32(io.err, ERR_INTV_OVERFLOW); } } } while (0)
 	for (;;) {
-		while (!pend && st != B_ALLDONE) {
-			switch (st) {
-			case B_FETCH: {
-				const i64 t = (i64)atomic_add_u32(counter, 1u);
-				if (t >= n_tasks) { st = B_ALLDONE; break; }
-				tk = io.tasks[t]; // (scans with many candidates sit at the other end of the array: fm_backward_task_warp)
-				if (io.pool_used[tk.read] == SEED_POOL_OVERFLOW) break; // the read is redone as a whole (stays in B_FETCH)
-				q = io.seq + io.seq_off[tk.read];
-				cl = io.pool + (size_t)tk.read * io.pool_cap + tk.c_off + (tk.n_c - 1);
-				n_prev = (int)tk.n_c; i = (int)tk.start - 1; have_out = false; last_beg = 0;
-				st = B_ROW;
-				break; }
-			case B_ROW:
-				if (i < -1) { st = B_FETCH; break; }
+		// ---- idle lanes take new scans together
+		const u32 idle = lanes_ballot(st == B_IDLE), busy = lanes_ballot(st == B_ROW || st == B_ITEM);
+		if (idle != 0u && (__popc(idle) >= SEED_REFILL_MIN || busy == 0u)) {
+			const int leader = __ffs(idle) - 1;
+			u32 base = 0;
+			if (lane == leader) base = atomic_add_u32(counter, (u32)__popc(idle));
+			base = lanes_shfl(base, leader);
+			if (st == B_IDLE) {
+				const i64 t = (i64)base + __popc(idle & ((1u << lane) - 1u));
+				if (t >= n_tasks) st = B_ALLDONE;
+				else {
+					tk = io.tasks[t]; // (scans with many candidates sit at the other end of the array: fm_backward_task_warp)
+					if (io.pool_used[tk.read] != SEED_POOL_OVERFLOW && tk.n_c <= (u32)SEED_HEAVY_CANDS) { // (else the read is redone as a whole: stay idle)
+						q = io.seq + io.seq_off[tk.read];
+						const uint4* src = io.pool + (size_t)tk.read * io.pool_cap + tk.c_off + (tk.n_c - 1);
+						for (int a = 0; a < (int)tk.n_c; ++a) CL(a) = src[-a];
+						n_prev = (int)tk.n_c; i = (int)tk.start - 1; have_out = false; last_beg = 0;
+						st = B_ROW;
+					}
+				}
+			}
+		}
+		if (lanes_ballot(st != B_ALLDONE) == 0u) break;
+		// ---- bookkeeping up to the next index read (shared memory and registers only, but for the read's bases)
+		while (!pend && (st == B_ROW || st == B_ITEM)) {
+			if (st == B_ROW) {
+				if (i < -1) { st = B_IDLE; break; }
 				c = i < 0 ? -1 : (q[i] < 4 ? (int)q[i] : -1);
 				n_curr = 0; last_size = 0; j = 0;
-				nxt = cl[0];
 				st = B_ITEM;
-				break;
-			case B_ITEM:
+			} else {
 				if (j == n_prev) { // row finished
-					if (n_curr == 0) { st = B_FETCH; break; }
+					if (n_curr == 0) { st = B_IDLE; break; }
 					n_prev = n_curr; --i;
 					st = B_ROW;
-					break;
+					continue;
 				}
-				cand_unpack(nxt, pcur, pcur_end);
+				cand_unpack(CL(j), pcur, pcur_end);
 				if (c >= 0) { // the candidates of a row are independent: up to SEED_BWD_WAYS of them are extended per trip
 					pcs[0] = pcur; pes[0] = pcur_end;
 					pend = n_prev - j < SEED_BWD_WAYS ? n_prev - j : SEED_BWD_WAYS;
 #pragma unroll
-					for (int t = 1; t < SEED_BWD_WAYS; ++t) if (t < pend) cand_unpack(cl[-(j + t)], pcs[t], pes[t]);
-					if (j + pend < n_prev) nxt = cl[-(j + pend)]; // (in-place compaction only writes slots <= j)
+					for (int t = 1; t < SEED_BWD_WAYS; ++t) if (t < pend) cand_unpack(CL(j + t), pcs[t], pes[t]);
 					break;
 				}
-				if (j + 1 < n_prev) nxt = cl[-(j + 1)];
 				B_EMIT_PCUR(); // no base to extend with: the candidate cannot grow
 				++j;
-				break;
-			default: st = B_ALLDONE; break;
 			}
 		}
-		if (lanes_all(st == B_ALLDONE)) break;
+		if (lanes_ballot(pend != 0) == 0u) continue;
 		if (!pend) continue;
 		BiIntv oks[SEED_BWD_WAYS];
 		if (pend == SEED_BWD_WAYS) fm_extend1_back_xn<SEED_BWD_WAYS>(x, pcs, c, oks);
@@ -604,12 +631,13 @@ DEV void fm_backward_queue(const DevIndex& x, const MemOpt& opt, const SeedSplit
 			pcur = pcs[t]; pcur_end = pes[t];
 			const BiIntv okc = oks[t];
 			if (okc.size < tk.min_intv) B_EMIT_PCUR();
-			else if (n_curr == 0 || okc.size != last_size) { cl[-n_curr] = cand_pack(okc, pcur_end); ++n_curr; last_size = okc.size; } // n_curr <= j
+			else if (n_curr == 0 || okc.size != last_size) { CL(n_curr) = cand_pack(okc, pcur_end); ++n_curr; last_size = okc.size; } // n_curr <= j (in-place compaction only writes slots <= j)
 			++j;
 		}
 		pend = 0;
 	}
 #undef B_EMIT_PCUR
+#undef CL
 }
 
 // The backward sweep of a scan with MANY candidates (low-complexity and repeat-derived reads: up to one candidate per

@@ -458,10 +458,27 @@ static int hw_threads()
 	return n ? (int)n : 4;
 }
 
+// <prefix>.alt (bwa bns_restore): the first field of every line that does not start with '@' names an ALT contig
+static void mark_alt_contigs(const char* prefix, RefSeqs& ref)
+{
+	FILE* fp = fopen((std::string(prefix) + ".alt").c_str(), "r");
+	if (!fp) return;
+	std::string tok; int c;
+	while ((c = fgetc(fp)) != EOF) {
+		if (c == '\t' || c == '\n' || c == '\r') {
+			if (!tok.empty() && tok[0] != '@') for (auto& ctg : ref.contigs) if (ctg.name == tok) ctg.is_alt = 1;
+			while (c != '\n' && c != EOF) c = fgetc(fp);
+			tok.clear();
+		} else tok.push_back((char)c);
+	}
+	fclose(fp);
+}
+
 extern "C" int jnibwa_createIndexFile(const char* refName, const char* imgName)
 {
 	RefSeqs ref; FmIndex fm;
 	if (!load_index_files(refName, ref, fm)) { printf("Failed to load bwa index files with prefix %s\n", refName); return 2; }
+	mark_alt_contigs(refName, ref); // bwa_idx_load (jnibwa.c:127) reads <prefix>.alt when it exists
 	std::vector<uint8_t> img;
 	serialize_image(ref, fm, img);
 	FILE* f = fopen(imgName, "wb");

@@ -390,7 +390,7 @@ DEV void body_compact(const BatchParams& P, i64 r)
 	const Reg* s = P.regs_tmp + P.seed_off[r];
 	Reg* d = P.regs + P.reg_off[r];
 	int n = (int)P.n_reg[r];
-	for (int i = 0; i < n; ++i) d[i] = s[i];
+	for (int i = 0; i < n; ++i) { Reg t = s[i]; if (t.rid >= 0 && P.x.ctg_alt[t.rid]) t.is_alt = 1; d[i] = t; } // (mem_align1_core tags the hits on ALT contigs)
 }
 
 DEV RescueIO make_rescue_io(const BatchParams& P)

@@ -74,6 +74,8 @@ DEV bool lanes_all(bool p) { return __all_sync(FULLMASK, p) != 0; }
 // thread-per-item kernels that hand out work to a whole warp at a time: lanes per hand-out, this thread's lane, a
 // broadcast of lane 0's value and the point where the lanes meet again
 #define SIMT_GROUP 32
+DEV u32 lanes_ballot(bool p) { return __ballot_sync(FULLMASK, p); }
+DEV u32 lanes_shfl(u32 v, int src) { return __shfl_sync(FULLMASK, v, src); }
 DEV int simt_lane() { return (int)(threadIdx.x & 31); }
 DEV u32 lane_bcast0(u32 v) { return __shfl_sync(FULLMASK, v, 0); }
 DEV void warp_converge() { __syncwarp(); }
@@ -133,6 +135,8 @@ DEV u32 byte_perm(u32 a, u32 b, u32 s)
 }
 DEV bool lanes_all(bool p) { return p; } // the harness runs one thread at a time
 #define SIMT_GROUP 1
+DEV u32 lanes_ballot(bool p) { return p ? 1u : 0u; }
+DEV u32 lanes_shfl(u32 v, int) { return v; }
 DEV int simt_lane() { return 0; }
 DEV u32 lane_bcast0(u32 v) { return v; }
 DEV void warp_converge() {}

@@ -484,6 +484,8 @@ static int patch_reg(const orc_index_t *x, const orc_opt_t *opt, uint8_t *query,
 ORC_SORT_DECL(reg_end, reg_t, REG_LT_END)
 ORC_SORT_DECL(reg_score, reg_t, REG_LT_SCORE)
 ORC_SORT_DECL(reg_hash, reg_t, REG_LT_HASH)
+#define REG_LT_HASH2(a, b) ((a).is_alt < (b).is_alt || ((a).is_alt == (b).is_alt && ((a).score > (b).score || ((a).score == (b).score && (a).hash < (b).hash))))
+ORC_SORT_DECL(reg_hash2, reg_t, REG_LT_HASH2)
 
 int orc_mem_sort_dedup_patch(const orc_index_t *x, const orc_opt_t *opt, uint8_t *query, int n, reg_t *a)
 {
@@ -595,8 +597,9 @@ static void mark_primary_core(const orc_opt_t *opt, int n, reg_t *a, int_v *z)
 	}
 }
 
-/* ALT contigs are outside the scope of this restatement (no is_alt contig is ever produced by the tools here);
- * the n_pri < n branch of the reference is therefore not restated and callers must reject such indices. */
+/* mem_mark_primary_se (B.11).  With hits on ALT contigs (n_pri < n) the marking runs twice: once over all hits (kept in
+ * secondary_all; a primary-assembly hit shadowed by an ALT hit remembers that hit's score in alt_sc), then -- hits
+ * re-ordered with the primary-assembly ones first -- over the primary-assembly hits alone (kept in secondary). */
 int orc_mem_mark_primary_se(const orc_opt_t *opt, int n, reg_t *a, int64_t id)
 {
 	int i, n_pri;
@@ -609,7 +612,29 @@ int orc_mem_mark_primary_se(const orc_opt_t *opt, int n, reg_t *a, int64_t id)
 	}
 	orc_sort_reg_hash(n, a);
 	mark_primary_core(opt, n, a, &z);
-	for (i = 0; i < n; ++i) a[i].secondary_all = a[i].secondary;
+	for (i = 0; i < n; ++i) {
+		reg_t *p = &a[i];
+		p->secondary_all = i; /* keep the rank of the first round */
+		if (!p->is_alt && p->secondary >= 0 && a[p->secondary].is_alt) p->alt_sc = a[p->secondary].score;
+	}
+	if (n_pri >= 0 && n_pri < n) {
+		int *rank = malloc(sizeof(int) * n);
+		if (n_pri > 0) orc_sort_reg_hash2(n, a);
+		for (i = 0; i < n; ++i) rank[a[i].secondary_all] = i;
+		for (i = 0; i < n; ++i) {
+			if (a[i].secondary >= 0) {
+				a[i].secondary_all = rank[a[i].secondary];
+				if (a[i].is_alt) a[i].secondary = INT_MAX;
+			} else a[i].secondary_all = -1;
+		}
+		free(rank);
+		if (n_pri > 0) { /* mark primary for hits to the primary assembly only */
+			for (i = 0; i < n_pri; ++i) { a[i].sub = 0; a[i].secondary = -1; }
+			mark_primary_core(opt, n_pri, a, &z);
+		}
+	} else {
+		for (i = 0; i < n; ++i) a[i].secondary_all = a[i].secondary;
+	}
 	vec_free(z);
 	return n_pri;
 }

@@ -293,14 +293,28 @@ int orc_mem_sam_pe(const orc_index_t *x, const orc_opt_t *opt, const orc_pestat_
 		if (!(opt->flag & ORC_F_ALL)) {
 			for (i = 0; i < 2; ++i) XA[i] = orc_mem_gen_alt(x, opt, &a[i], l_seq[i], seq[i]);
 		} else XA[0] = XA[1] = 0;
-		for (i = 0; i < 2; ++i) {
-			h[i] = orc_mem_reg2aln(x, opt, l_seq[i], seq[i], &a[i].a[z[i]]);
-			h[i].mapq = (uint32_t)q_se[i];
-			h[i].flag |= 0x40 << i | extra_flag;
-			h[i].XA = XA[i] ? XA[i][z[i]] : 0;
+		{
+			aln_t aa[2][2]; int n_aa[2] = { 0, 0 };
+			for (i = 0; i < 2; ++i) {
+				h[i] = orc_mem_reg2aln(x, opt, l_seq[i], seq[i], &a[i].a[z[i]]);
+				h[i].mapq = (uint32_t)q_se[i];
+				h[i].flag |= 0x40 << i | extra_flag;
+				h[i].XA = XA[i] ? XA[i][z[i]] : 0;
+				aa[i][n_aa[i]++] = h[i];
+				if (n_pri[i] < (int)a[i].n) { /* the read has ALT hits: its best ALT hit goes out as a supplementary record */
+					reg_t *p = &a[i].a[n_pri[i]];
+					aln_t g;
+					if (p->score < opt->T || p->secondary >= 0 || !p->is_alt) continue;
+					g = orc_mem_reg2aln(x, opt, l_seq[i], seq[i], p);
+					g.flag |= 0x800 | 0x40 << i | extra_flag;
+					g.XA = XA[i] ? XA[i][n_pri[i]] : 0;
+					aa[i][n_aa[i]++] = g;
+				}
+			}
+			for (i = 0; i < n_aa[0]; ++i) orc_aln2blob(&out[0], n_aa[0], aa[0], i, &h[1]);
+			for (i = 0; i < n_aa[1]; ++i) orc_aln2blob(&out[1], n_aa[1], aa[1], i, &h[0]);
+			for (i = 0; i < 2; ++i) if (n_aa[i] > 1) free(aa[i][1].cigar);
 		}
-		orc_aln2blob(&out[0], 1, &h[0], 0, &h[1]);
-		orc_aln2blob(&out[1], 1, &h[1], 0, &h[0]);
 		for (i = 0; i < 2; ++i) {
 			free(h[i].cigar);
 			if (XA[i]) { for (j = 0; j < (int)a[i].n; ++j) free(XA[i][j]); free(XA[i]); }

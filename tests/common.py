@@ -153,3 +153,36 @@ def repeat_family_image():
     if not os.path.exists(img):
         simdata.build_image(g, img)
     return g, img
+
+
+def alt_contig_image():
+    """(genome, image) of a genome with two primary contigs and three ALT contigs (diverged copies of primary regions,
+    named in <prefix>.alt, which jnibwa_createIndexFile reads like bwa_idx_load does: jnibwa.c:127).  Reads drawn from it
+    hit both the primary assembly and the ALT contigs: exercises is_alt in chain filtering, the two-round primary
+    marking, XA with max_XA_hits_alt and the extra supplementary record of paired output."""
+    import numpy as np
+    rng = np.random.default_rng(17)
+    base = simdata.make_genome(41, [90000, 50000], repeat_frac=0.04, tandem_frac=0.005, n_segdup=2)
+    prim = base.bases
+    alts, names = [], ["chr1", "chr2"]
+    for k, (off, ln, div) in enumerate([(20000, 6000, 0.02), (100000, 4000, 0.03), (60000, 5000, 0.01)]):
+        c = prim[off:off + ln].copy()
+        m = rng.random(ln) < div
+        c[m] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, int(m.sum()))]
+        if k == 1:  # one ALT with a 30-base deletion and a 12-base insertion
+            c = np.concatenate([c[:1500], c[1530:3000], np.frombuffer(b"ACGTTGCAAGCT", dtype=np.uint8), c[3000:]])
+        alts.append(c); names.append(f"alt{k + 1}")
+    bases = np.concatenate([prim] + alts)
+    lens = [90000, 50000] + [len(a) for a in alts]
+    g = simdata.Genome(bases, lens, names, base.repeats)
+    img = os.path.join(workdir(), "alt_contigs.img")
+    if not os.path.exists(img):
+        prefix = os.path.join(workdir(), "alt_contigs.fa")
+        simdata.write_fasta(g, prefix)
+        assert simdata.idxlib().jnibwa_createReferenceIndex(prefix.encode(), prefix.encode(), b"auto") == 0
+        with open(prefix + ".alt", "w") as f:
+            f.write("@SQ\tSN:chr1\n")
+            for nm in names[2:]:
+                f.write(f"{nm}\t0\tchr1\t1\t0\t100M\t*\t0\t0\t*\t*\n")
+        assert simdata.idxlib().jnibwa_createIndexFile(prefix.encode(), img.encode()) == 0
+    return g, img

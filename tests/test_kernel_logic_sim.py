@@ -4,7 +4,7 @@ orchestration (engine_impl.inl), every device function's logic and the record en
 parity gate is tests/test_parity_gpu.py on the B200."""
 import pytest
 
-from common import first_diff, oracle_lib, repeat_family_image, run_blob, sim_lib, simdata, synth_image
+from common import alt_contig_image, first_diff, oracle_lib, repeat_family_image, run_blob, sim_lib, simdata, synth_image
 from test_oracle_kat import run_kat
 
 
@@ -134,3 +134,13 @@ def test_sim_forced_long_mode_on_short_reads(small_genome, monkeypatch):
     monkeypatch.setenv("B200_TEST_LONG_MODE", "1")
     b = run_blob(sim_lib(), img, blob, 2)
     assert a == b, first_diff(a, b, blob, True)
+
+
+@pytest.mark.parametrize("paired,flag", [(False, 0), (True, 2), (False, 8), (True, 2 | 0x800)], ids=["se", "pe", "se_all", "pe_primary5"])
+def test_sim_alt_contigs(paired, flag):
+    """An image with ALT contigs (see common.alt_contig_image)."""
+    g, img = alt_contig_image()
+    blob, _ = simdata.make_reads(g, 51, 300, 150, paired, err_rate=0.01)
+    a = run_blob(oracle_lib(), img, blob, flag)
+    b = run_blob(sim_lib(), img, blob, flag)
+    assert a == b, first_diff(a, b, blob, paired)

@@ -3,7 +3,7 @@ options and batch boundaries.  Bar: the int32 record stream is byte-identical (f
 MD, AS, XS, XA, mate fields)."""
 import pytest
 
-from common import bwa, engine_lib, first_diff, oracle_lib, repeat_family_image, run_blob, simdata, synth_image
+from common import alt_contig_image, bwa, engine_lib, first_diff, oracle_lib, repeat_family_image, run_blob, simdata, synth_image
 from test_oracle_kat import run_kat
 
 pytestmark = pytest.mark.gpu
@@ -324,3 +324,21 @@ def test_device_pool_single_process(small_genome, monkeypatch):
     assert len(got) == (2 * ndev + 1) * 12
     for (t, rep, i), out in got.items():
         assert out == want[i], (t, rep, i)
+
+
+@pytest.mark.parametrize("paired,flag", [(False, 0), (True, 2), (False, 8), (True, 2 | 0x800), (True, 2 | 0x20)], ids=["se", "pe", "se_all", "pe_primary5", "pe_no_rescue"])
+def test_alt_contigs(paired, flag):
+    """An image with ALT contigs (is_alt from <prefix>.alt, jnibwa.c:127): ALT-aware chain filtering, the two-round primary
+    marking with alt_sc, XA lists up to max_XA_hits_alt (setMaxXAHitsAltOption, BwaMemAligner.java:124-125), the extra
+    supplementary record of paired output."""
+    g, img = alt_contig_image()
+    blob, _ = simdata.make_reads(g, 51, 4000, 150, paired, err_rate=0.01)
+    a = run_blob(oracle_lib(), img, blob, flag)
+    b = run_blob(engine_lib(), img, blob, flag)
+    assert a == b, first_diff(a, b, blob, paired)
+    n = 4000 * (2 if paired else 1)
+    recs = bwa.decode_alignments(b, n)
+    names = bwa.BwaMemIndex(img, lib=oracle_lib())
+    alt_ids = {i for i, nm in enumerate(names.getReferenceContigNames()) if nm.startswith("alt")}
+    names.close()
+    assert any(al.refId in alt_ids for alns in recs for al in alns), "no record on an ALT contig: the case is not exercised"
