@@ -79,13 +79,13 @@ struct HostProf {
 // change which kernels a call launches, so they are honoured only when B200_TEST_HOOKS=1 is set as well.
 struct EngineConfig {
 	int sa_intv = 8;             // BWA_B200_SA_INTV
-	int contexts = 2;            // BWA_B200_CONTEXTS: batches in flight per device
+	int contexts = 3;            // BWA_B200_CONTEXTS: batches in flight per device
 	bool hostprof = false, debug_stats = false;
 	// ---- test hooks / tuning aids (B200_TEST_HOOKS=1)
 	bool no_stage_overlap = false, seed_one_launch = false, seed_fused_rounds = false, tiny_seed_pool = false, tiny_seed_tasks = false, seed_no_overlap = false;
 	bool chain_all_warp = false, chain_all_thread = false, chain_no_overlap = false, tiny_scratch = false, all_heavy = false, all_light = false;
 	bool warp_extend = false, ext_wide_cells = false, no_ext_tasks = false, rescue_fallback = false, final_one_pass = false, final_ring = false, tiny_ga_cap = false;
-	bool ext_legacy = false, ext_no_sort = false, force_long_mode = false, rescue_warp_sw = false, ga_no_sort = false;
+	bool ext_legacy = false, ext_no_sort = false, force_long_mode = false, rescue_warp_sw = false, ga_no_sort = false, ext_task_machine = false;
 	int seed_lcap = 0, seed_shared_read = -1, tx_chunk = -1, light_seeds = -1, light_chains = -1;
 	static bool flag(const char* nm) { return getenv(nm) != nullptr; }
 	static int num(const char* nm, int dflt) { const char* e = getenv(nm); return e ? atoi(e) : dflt; }
@@ -102,7 +102,7 @@ struct EngineConfig {
 		tiny_scratch = flag("B200_TEST_TINY_SCRATCH"); all_heavy = flag("B200_TEST_ALL_HEAVY"); all_light = flag("B200_TEST_ALL_LIGHT");
 		warp_extend = flag("B200_WARP_EXTEND"); ext_wide_cells = flag("B200_EXT_WIDE_CELLS"); no_ext_tasks = flag("B200_NO_EXT_TASKS");
 		rescue_fallback = flag("B200_TEST_RESCUE_FALLBACK"); final_one_pass = flag("B200_FINAL_ONE_PASS"); final_ring = flag("B200_TEST_FINAL_RING");
-		tiny_ga_cap = flag("B200_TEST_TINY_GA_CAP"); ext_legacy = flag("B200_EXT_LEGACY"); ext_no_sort = flag("B200_EXT_NO_SORT"); force_long_mode = flag("B200_TEST_LONG_MODE"); rescue_warp_sw = flag("B200_RESCUE_WARP_SW"); ga_no_sort = flag("B200_GA_NO_SORT");
+		tiny_ga_cap = flag("B200_TEST_TINY_GA_CAP"); ext_legacy = flag("B200_EXT_LEGACY"); ext_no_sort = flag("B200_EXT_NO_SORT"); force_long_mode = flag("B200_TEST_LONG_MODE"); rescue_warp_sw = flag("B200_RESCUE_WARP_SW"); ga_no_sort = flag("B200_GA_NO_SORT"); ext_task_machine = flag("B200_EXT_TASK_MACHINE");
 		seed_lcap = num("B200_SEED_LCAP", 0); seed_shared_read = num("B200_SEED_SHARED_READ", -1); tx_chunk = num("B200_TX_CHUNK", -1);
 		light_seeds = num("B200_LIGHT_SEEDS", -1); light_chains = num("B200_LIGHT_CHAINS", -1);
 	}
@@ -190,7 +190,9 @@ struct Batch {
 	cudaStream_t up_stream[NUP] = { nullptr, nullptr, nullptr, nullptr };
 	cudaEvent_t up_done[NUP] = { nullptr, nullptr, nullptr, nullptr };
 	char* pin = nullptr; uint64_t pin_cap = 0; // pinned staging of the request bytes, grow-only like the device buffer
+	char* pin_out = nullptr; uint64_t pin_out_cap = 0; std::vector<cudaEvent_t> out_done; // pinned staging of the record stream, one event per chunk
 #endif
+	bool fetch_result(void* dst, const void* dev_src, size_t bytes);
 	bool stage(const char* blob, bool wait = true);
 	void* run(const MemOpt* opt, const PeStat* pes0, size_t* out_size, bool host_output);
 	void* align(const MemOpt* opt, const PeStat* pes0, char* blob, size_t* out_size);
@@ -365,6 +367,9 @@ inline void Batch::release_all()
 #ifndef B200_SIM
 	for (int t = 0; t < NUP; ++t) { if (up_stream[t]) cudaStreamDestroy(up_stream[t]); if (up_done[t]) cudaEventDestroy(up_done[t]); up_stream[t] = nullptr; up_done[t] = nullptr; }
 	rt_host_free(pin); pin = nullptr; pin_cap = 0;
+	rt_host_free(pin_out); pin_out = nullptr; pin_out_cap = 0;
+	for (cudaEvent_t e : out_done) cudaEventDestroy(e);
+	out_done.clear();
 #endif
 }
 
@@ -478,6 +483,55 @@ inline bool Batch::stage(const char* blob_in, bool wait)
 		if (wait) rt_sync();
 	}
 	st_valid = true;
+	return true;
+}
+
+// The record stream back to the caller's malloc'd buffer (Java frees it with free(): ...BwaMemIndex.c:157-160).  A copy from
+// the device straight into fresh pageable memory runs at ~2 GB/s (the driver stages it and every page faults on first
+// touch); instead the stream comes down in chunks into the context's pinned buffer at DMA speed while helper threads copy
+// the chunks that have arrived into the destination, faulting its pages in parallel.
+inline bool Batch::fetch_result(void* dst, const void* dev_src, size_t bytes)
+{
+#ifndef B200_SIM
+	const size_t CH = (size_t)4 << 20;
+	enum { NDOWN = 4 };
+	if (bytes >= 2 * CH) {
+		if (pin_out_cap < bytes) {
+			rt_host_free(pin_out);
+			const size_t want = bytes + bytes / 4;
+			pin_out = (char*)rt_host_alloc(want); pin_out_cap = pin_out ? want : 0;
+		}
+		const size_t n_ch = (bytes + CH - 1) / CH;
+		bool ok = pin_out != nullptr;
+		while (ok && out_done.size() < n_ch) { cudaEvent_t e; ok = cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess; if (ok) out_done.push_back(e); }
+		if (ok) {
+			for (size_t c = 0; c < n_ch && ok; ++c) {
+				const size_t lo = c * CH, len = bytes - lo < CH ? bytes - lo : CH;
+				ok = cu_ok(cudaMemcpyAsync(pin_out + lo, (const char*)dev_src + lo, len, cudaMemcpyDeviceToHost, rt_stream()), "d2h") && cu_ok(cudaEventRecord(out_done[c], rt_stream()), "d2h event");
+			}
+			if (ok) {
+				std::atomic<int> failed(0);
+				const int dev = rep->dev;
+				std::thread th[NDOWN];
+				for (int t = 0; t < NDOWN; ++t) th[t] = std::thread([&, t]() {
+					cudaSetDevice(dev);
+					for (size_t c = (size_t)t; c < n_ch; c += NDOWN) {
+						if (cudaEventSynchronize(out_done[c]) != cudaSuccess) { failed.store(1); return; }
+						const size_t lo = c * CH, len = bytes - lo < CH ? bytes - lo : CH;
+						memcpy((char*)dst + lo, pin_out + lo, len);
+					}
+				});
+				for (int t = 0; t < NDOWN; ++t) th[t].join();
+				if (!failed.load()) return true;
+			}
+			cudaGetLastError();
+			rt_sync();
+			return false;
+		}
+		cudaGetLastError(); // (no pinned memory to be had: the plain copy below)
+	}
+#endif
+	rt_d2h(dst, dev_src, bytes);
 	return true;
 }
 
@@ -729,6 +783,12 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 				bnd[NCLS - 1] = n_t; bnd[2 * NCLS - 1] = n_t;
 				hp.mark("ext_class_sync");
 			}
+			if (cfg.ext_task_machine) { // comparison route: both sides of a task by the per-lane machine of the read-level kernel (extend_thread.cuh, TASKS = true)
+				P.ext_sides = 0;
+				const size_t task_smem = thread_ext_smem_bytes(THREADS_PER_BLOCK, rw, wm_cap, cell);
+				if (narrow) RT_THREADS_QUEUE_SMEM(body_extend_task_q8, P, (int64_t)n_t, task_smem);
+				else RT_THREADS_QUEUE_SMEM(body_extend_task_q, P, (int64_t)n_t, task_smem);
+			} else
 			for (int side = 0; side < 2; ++side) {
 				for (int k = NCLS - 1; k >= 0; --k) { // longest class first
 					const uint32_t lo = k ? bnd[side * NCLS + k - 1] : 0u, hi = bnd[side * NCLS + k];
@@ -929,7 +989,7 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 	hp.mark("write_sync");
 	void* res = malloc((size_t)W * 4 + 4);
 	if (!res) { last_error = "host allocation failed"; return nullptr; }
-	rt_d2h(res, P.out, (size_t)W * 4);
+	if (!fetch_result(res, P.out, (size_t)W * 4)) { free(res); last_error = "result copy failed"; return nullptr; }
 	*out_size = (size_t)W * 4;
 	return res;
 }

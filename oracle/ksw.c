@@ -268,17 +268,35 @@ static void revseq(int l, uint8_t *s)
 	for (i = 0; i < l >> 1; ++i) { t = s[i]; s[i] = s[l - 1 - i]; s[l - 1 - i] = t; }
 }
 
+/* which form of the striped kernel orc_ksw_align2 runs: the SSE2 one (ksw_sse2.c; default where SSE2 exists, as bwa
+ * itself is built) or the scalar emulation above.  Results are identical (tests/test_oracle_kat.py). */
+static int g_simd = -1;
+void orc_set_simd(int on) { g_simd = on ? orc_have_sse2() : 0; }
+int orc_get_simd(void) { if (g_simd < 0) g_simd = orc_have_sse2(); return g_simd; }
+
+static sw_fwd_t sw_pass(int lanes, int is_u8, int qlen, const uint8_t *query, int tlen, const uint8_t *target,
+                        const int8_t *mat, int o_del, int e_del, int o_ins, int e_ins, int xtra)
+{
+	if (orc_get_simd()) {
+		int o[5]; sw_fwd_t r;
+		orc_sw_striped_sse2(is_u8, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, xtra, o);
+		r.score = o[0]; r.te = o[1]; r.qe = o[2]; r.score2 = o[3]; r.te2 = o[4];
+		return r;
+	}
+	return sw_striped(lanes, is_u8, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, xtra);
+}
+
 orc_kswr_t orc_ksw_align2(int qlen, uint8_t *query, int tlen, uint8_t *target, const int8_t *mat,
                           int o_del, int e_del, int o_ins, int e_ins, int xtra)
 {
 	orc_kswr_t r = { 0, -1, -1, -1, -1, -1, -1 };
 	int is_u8 = (xtra & ORC_KSW_XBYTE) ? 1 : 0, lanes = is_u8 ? 16 : 8;
 	sw_fwd_t f, rr;
-	f = sw_striped(lanes, is_u8, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, xtra);
+	f = sw_pass(lanes, is_u8, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, xtra);
 	r.score = f.score; r.te = f.te; r.qe = f.qe; r.score2 = f.score2; r.te2 = f.te2;
 	if ((xtra & ORC_KSW_XSTART) == 0 || ((xtra & ORC_KSW_XSUBO) && r.score < (xtra & 0xffff))) return r;
 	revseq(r.qe + 1, query); revseq(r.te + 1, target);
-	rr = sw_striped(lanes, is_u8, r.qe + 1, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, ORC_KSW_XSTOP | r.score);
+	rr = sw_pass(lanes, is_u8, r.qe + 1, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, ORC_KSW_XSTOP | r.score);
 	revseq(r.qe + 1, query); revseq(r.te + 1, target);
 	if (r.score == rr.score) { r.tb = r.te - rr.te; r.qb = r.qe - rr.qe; }
 	return r;

@@ -159,6 +159,12 @@ typedef struct { int score, te, qe, score2, te2, tb, qb; } orc_kswr_t;
 orc_kswr_t orc_ksw_align2(int qlen, uint8_t *query, int tlen, uint8_t *target, const int8_t *mat,
                           int o_del, int e_del, int o_ins, int e_ins, int xtra);
 uint64_t orc_bwt_sa(const orc_index_t *idx, uint64_t k);
+/* ksw_align2's striped kernel: 1 = SSE2 intrinsics (ksw_sse2.c; the default on x86-64), 0 = the scalar emulation */
+void orc_set_simd(int on);
+int orc_get_simd(void);
+int orc_have_sse2(void);
+void orc_sw_striped_sse2(int is_u8, int qlen, const uint8_t *query, int tlen, const uint8_t *target, const int8_t *mat,
+                         int o_del, int e_del, int o_ins, int e_ins, int xtra, int out[5]);
 
 #define ORC_KSW_XBYTE  0x10000
 #define ORC_KSW_XSTOP  0x20000
