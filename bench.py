@@ -405,7 +405,6 @@ def main():
         if rank != 0:
             shm = shared_memory.SharedMemory(name=name)
         gather = (shm, slot, ctypes.addressof(ctypes.c_char.from_buffer(shm.buf)))
-    results = {}
     lock = threading.Lock()
 
     def e2e_leg(n_threads: int, steps: int, warm_per_thread: int):
@@ -442,8 +441,6 @@ def main():
                 if gather is not None:  # ordered gather: slot of (call parity, rank) in the shared host buffer
                     shm, slot, base = gather
                     ctypes.memmove(base + ((i & 1) * world + rank) * slot, res, min(sz, slot))
-                if i not in results or n_threads == 1:
-                    results[i % n_distinct] = ctypes.string_at(res, sz) if (i % n_distinct) not in results else results[i % n_distinct]
                 dll.jnibwa_free(res)
                 with lock:
                     cursor["sum"] ^= last; cursor["bytes"] = sz
@@ -501,9 +498,9 @@ def main():
                 break
             dt, oc, ref_out = run_oracle(img, blobs[b], flag, cores)
             spent += dt
-            got = results.get(b)
-            if got is None:  # (a batch the e2e legs never reached: run it now)
-                got = idx.doAlignment(bytearray(blobs[b]), al._opts_addr, None)
+            # the engine's record stream for this batch through the same C-ABI call the e2e legs timed (re-run untimed: copying
+            # 65 MB results out inside the timed loop would hold the interpreter lock against the other caller threads)
+            got = idx.doAlignment(bytearray(blobs[b]), al._opts_addr, None)
             n_cmp += 1
             n_ok += int(got == ref_out)
             if b == 0:

@@ -394,6 +394,12 @@ __global__ void k_densify_sa(DevIndex x, u64 n_rows, u32 dense, u64* out)
 	const u64 n_out = (n_rows + dense - 1) / dense;
 	for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < n_out; t += (u64)gridDim.x * blockDim.x) out[t] = fm_sa(x, t * dense);
 }
+// one level of the prefix tables (fm.cuh kmer_build_entry): entry e of level L1 from level L1 - 1
+__global__ void k_kmer_level(DevIndex x, uint4* tab, int L1, u64 n)
+{
+	for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (u64)gridDim.x * blockDim.x) kmer_build_entry(x, tab, L1, e);
+}
+#define RT_KMER_LEVEL(x, tab, L1, n) do { k_kmer_level<<<(unsigned)(rt_sm_count() * 16), 256, 0, rt_stream()>>>((x), (tab), (L1), (n)); cu_ok(cudaGetLastError(), "kmer level"); } while (0)
 #define RT_DENSIFY(x, n_rows, dense, out) do { k_densify_sa<<<(unsigned)(rt_sm_count() * 16), 256, 0, rt_stream()>>>((x), (n_rows), (dense), (out)); cu_ok(cudaGetLastError(), "densify"); } while (0)
 #define RT_RELAYOUT(src, size, dst, nb) do { k_relayout<<<(unsigned)(rt_sm_count() * 16), 256, 0, rt_stream()>>>((src), (size), (dst), (nb)); cu_ok(cudaGetLastError(), "relayout"); } while (0)
 

@@ -15,6 +15,7 @@
 #include <atomic>
 #include <mutex>
 #include <condition_variable>
+#include <chrono>
 #include <thread>
 #include <string>
 #include <vector>
@@ -80,6 +81,7 @@ struct HostProf {
 struct EngineConfig {
 	int sa_intv = 8;             // BWA_B200_SA_INTV
 	int contexts = 3;            // BWA_B200_CONTEXTS: batches in flight per device
+	int kmer_k = 12;             // BWA_B200_KMER: longest string of the prefix tables (0: none; 12 = 358 MB)
 	bool hostprof = false, debug_stats = false;
 	// ---- test hooks / tuning aids (B200_TEST_HOOKS=1)
 	bool no_stage_overlap = false, seed_one_launch = false, seed_fused_rounds = false, tiny_seed_pool = false, tiny_seed_tasks = false, seed_no_overlap = false;
@@ -93,6 +95,7 @@ struct EngineConfig {
 	{
 		sa_intv = num("BWA_B200_SA_INTV", sa_intv);
 		contexts = num("BWA_B200_CONTEXTS", contexts); if (contexts < 1) contexts = 1; if (contexts > 8) contexts = 8;
+		kmer_k = num("BWA_B200_KMER", kmer_k); if (kmer_k < 2) kmer_k = 0; if (kmer_k > 13) kmer_k = 13;
 		hostprof = flag("B200_HOSTPROF"); debug_stats = flag("B200_DEBUG_STATS");
 		const char* th = getenv("B200_TEST_HOOKS");
 		if (!th || atoi(th) == 0) return;
@@ -162,9 +165,9 @@ struct Engine;
 struct Replica {
 	int dev = 0;
 	DevIndex dx;
-	DBuf d_bwt, d_sa, d_sa_dense, d_pac, d_ctg, d_log, d_names, d_name_off;
+	DBuf d_bwt, d_sa, d_sa_dense, d_pac, d_ctg, d_log, d_names, d_name_off, d_kmer;
 	int busy = 0; // contexts of this device inside a call (guarded by Engine::mu)
-	void release_all() { DBuf* all[] = { &d_bwt, &d_sa, &d_sa_dense, &d_pac, &d_ctg, &d_log, &d_names, &d_name_off }; for (DBuf* b : all) b->release(); }
+	void release_all() { DBuf* all[] = { &d_bwt, &d_sa, &d_sa_dense, &d_pac, &d_ctg, &d_log, &d_names, &d_name_off, &d_kmer }; for (DBuf* b : all) b->release(); }
 };
 
 // One batch in flight: a runtime context (streams, events, timer: engine.cu RtCtx) on one device, the grow-only batch
@@ -284,7 +287,7 @@ inline bool Engine::open_from_fd(int fd, const std::vector<int>& devices)
 inline bool Engine::upload(Replica& R, const Replica* from)
 {
 	DBuf& d_bwt = R.d_bwt; DBuf& d_sa = R.d_sa; DBuf& d_sa_dense = R.d_sa_dense; DBuf& d_pac = R.d_pac; DBuf& d_ctg = R.d_ctg; DBuf& d_log = R.d_log;
-	DBuf& d_names = R.d_names; DBuf& d_name_off = R.d_name_off; DevIndex& dx = R.dx;
+	DBuf& d_names = R.d_names; DBuf& d_name_off = R.d_name_off; DBuf& d_kmer = R.d_kmer; DevIndex& dx = R.dx;
 	size_t bwt_bytes = (size_t)img.bwt_size * 4;
 	const uint64_t n_blocks = (img.seq_len + 127) / 128;
 	const size_t pac_bytes = (size_t)(img.l_pac / 4 + 1);
@@ -336,6 +339,10 @@ inline bool Engine::upload(Replica& R, const Replica* from)
 	rt_sync();
 	if (from) {
 		if (from->d_sa_dense.p) { dx.sa = d_sa_dense.as<u64>(); dx.sa_intv = from->dx.sa_intv; }
+		if (from->dx.kmer_tab) {
+			const size_t kb = (size_t)kmer_level_off(from->dx.kmer_k + 1) * 16;
+			if (d_kmer.ensure(kb) && rt_peer_copy(d_kmer.p, R.dev, from->d_kmer.p, from->dev, kb)) { rt_sync(); dx.kmer_tab = d_kmer.as<uint4>(); dx.kmer_k = from->dx.kmer_k; }
+		}
 		return g_last_cuda_ok();
 	}
 	// Spend HBM on the suffix array: the image samples every 32nd row (bwt_sa then walks ~15.5 LF steps per lookup, each
@@ -351,6 +358,18 @@ inline bool Engine::upload(Replica& R, const Replica* from)
 				dx.sa = d_sa_dense.as<u64>(); dx.sa_intv = (u32)want;
 				d_sa.release();
 			}
+		}
+	}
+	// Spend HBM on the first steps of every forward scan too: the bidirectional interval of every string of 2..K bases
+	// (4^K * 16 * 4/3 bytes: 358 MB at K = 12), built level by level from the index itself, so a scan's first K - 1
+	// extensions are one 16-byte read each (mostly L2 hits) instead of two 64-byte block walks.  Same intervals, so
+	// results are unchanged.  Only worth it when the index is much larger than the tables.
+	if (cfg.kmer_k >= 2 && img.seq_len >= ((uint64_t)1 << (2 * cfg.kmer_k + 2))) {
+		const int K = cfg.kmer_k;
+		if (d_kmer.ensure((size_t)kmer_level_off(K + 1) * 16)) {
+			for (int L1 = 2; L1 <= K; ++L1) RT_KMER_LEVEL(dx, d_kmer.as<uint4>(), L1, (u64)1 << (2 * L1));
+			rt_sync();
+			if (g_last_cuda_ok()) { dx.kmer_tab = d_kmer.as<uint4>(); dx.kmer_k = K; }
 		}
 	}
 	return g_last_cuda_ok();
@@ -435,7 +454,7 @@ inline bool Batch::stage(const char* blob_in, bool wait)
 					if (stt == 2 || lo >= dcap) goto out;
 					if (avail >= hi && hi <= dcap) break;
 					if (stt == 1) { hi = avail < dcap ? avail : dcap; break; } // the last, partial chunk
-					std::this_thread::yield();
+					std::this_thread::sleep_for(std::chrono::microseconds(20)); // (a spinning helper would take a core from another caller's scan)
 				}
 				if (hi <= lo) break;
 				memcpy(pin + lo, base + lo, hi - lo);

@@ -386,7 +386,7 @@ DEV void tx_extend2(const DevIndex& x, const MemOpt& opt, const ThreadExtMem& tm
 	constexpr int HB = TxCell<CELL>::HB; constexpr u32 HMASK = TxCell<CELL>::HMASK;
 	const int o_del = opt.o_del, e_del = opt.e_del, o_ins = opt.o_ins, e_ins = opt.e_ins;
 	const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins, zdrop = opt.zdrop;
-	const size_t RS = (size_t)tm.row_stride, QS = (size_t)tm.rd_stride;
+	constexpr size_t RS = TX_STRIDE, QS = TX_STRIDE;
 	CELL* const row = (CELL*)tm.row;
 	const i64 l_pac = x.l_pac;
 	{
@@ -422,16 +422,19 @@ DEV void tx_extend2(const DevIndex& x, const MemOpt& opt, const ThreadExtMem& tm
 		{
 			CELL* rw = row + (size_t)beg * RS;
 			const u8* qp = tm.rd + (size_t)beg * QS;
+			// the row maximum and the LAST column that attains it in one running maximum of (h << 16 | j) -- `mj = m > h ? mj : j`
+			// moves to j whenever h >= m (h < 2^15, j < 2^16)
+			u32 mk = 0u;
 #pragma unroll 4
 			for (int j = beg; j < end; ++j) {
 				const u32 he = (u32)*rw;
 				int M = (int)(he & HMASK), e = (int)(he >> HB);
-				const int sc = (int)(i8)(rp >> (8 * (int)*qp));
+				const int sc = (int)(i8)(rp >> (int)*qp); // (the codes are stored times 8: the shift count)
 				M = M ? M + sc : 0;
 				int h = M > e ? M : e;
 				h = h > f ? h : f;
-				mj = m > h ? mj : j;
-				m = m > h ? m : h;
+				const u32 key = (u32)h << 16 | (u32)j;
+				mk = mk > key ? mk : key;
 				int t = M - oe_del; t = t > 0 ? t : 0;
 				e -= e_del; e = e > t ? e : t;
 				*rw = (CELL)((u32)h1 | (u32)e << HB);
@@ -440,6 +443,7 @@ DEV void tx_extend2(const DevIndex& x, const MemOpt& opt, const ThreadExtMem& tm
 				f -= e_ins; f = f > t ? f : t;
 				rw += RS; qp += QS;
 			}
+			if (end > beg) { m = (int)(mk >> 16); mj = (int)(mk & 0xffffu); }
 		}
 		row[(size_t)end * RS] = (CELL)h1; // H[end] = h1, E[end] = 0
 		const int jfin = beg < end ? end : beg;
@@ -498,7 +502,7 @@ DEV void thread_extend_sides(const BatchParams& P, u32* counter, const ThreadExt
 				if (qlen == 0) { o.score = o.truesc = s.len * opt.a; o.qb = 0; o.rb = s.rbeg; o.w = opt.w; o.valid = 2; }
 				else if (!fits) o.valid = 0; // the replay extends this seed itself
 				else {
-					for (int j = 0; j < qlen; ++j) tm.rd[(size_t)j * QS] = query[s.qbeg - 1 - j]; // both sequences walked backwards
+					for (int j = 0; j < qlen; ++j) tm.rd[(size_t)j * QS] = (u8)(query[s.qbeg - 1 - j] << 3); // both sequences walked backwards; codes times 8 (tx_extend2)
 					const int tlen = (int)(s.rbeg - P.ck_rmax[2 * (t0 + tk.c)]);
 					ExtResult er; er.score = -1; er.qle = er.tle = er.gtle = 0; er.gscore = -1; er.max_off = 0;
 					int score = -1, aw = opt.w;
@@ -521,7 +525,7 @@ DEV void thread_extend_sides(const BatchParams& P, u32* counter, const ThreadExt
 				if (qlen == 0) { o.qe = l_query; o.re = re; o.valid = 1; }
 				else if (!fits) o.valid = 0;
 				else {
-					for (int j = 0; j < qlen; ++j) tm.rd[(size_t)j * QS] = query[qe + j];
+					for (int j = 0; j < qlen; ++j) tm.rd[(size_t)j * QS] = (u8)(query[qe + j] << 3);
 					const int tlen = (int)(P.ck_rmax[2 * (t0 + tk.c) + 1] - re);
 					const int sc0 = o.score;
 					ExtResult er; er.score = -1; er.qle = er.tle = er.gtle = 0; er.gscore = -1; er.max_off = 0;

@@ -150,6 +150,34 @@ DEV void fm_set_intv(const DevIndex& x, int c, BiIntv& ik)
 	ik.x0 = x.L2[c] + 1; ik.size = x.L2[c + 1] - x.L2[c]; ik.x1 = x.L2[3 - c] + 1;
 }
 
+// ---- prefix tables -------------------------------------------------------------------------------
+DEV uint4 cand_pack(const BiIntv& b, u32 end);
+DEV void cand_unpack(const uint4 e, BiIntv& b, u32& end);
+HOSTDEV u64 kmer_level_off(int L) { return (((u64)1 << (2 * L)) - 16) / 3; } // entries of the levels 2 .. L-1
+// level L + 1 from level L (thread per entry of level L + 1): the forward extension of string p by base c is entry p * 4 + c
+DEV void kmer_build_entry(const DevIndex& x, uint4* tab, int L1, u64 e)
+{
+	const u64 p = e >> 2; const int c = (int)(e & 3);
+	BiIntv ik; u32 dummy;
+	if (L1 == 2) fm_set_intv(x, (int)p, ik); else cand_unpack(tab[kmer_level_off(L1 - 1) + p], ik, dummy);
+	const BiIntv ok = fm_extend1(x, ik, 3 - c, 0);
+	tab[kmer_level_off(L1) + e] = cand_pack(ok, 0u);
+}
+// One forward extension of a scan that has consumed `plen` bases whose codes form `pidx` (base-4, first base most
+// significant), by base code c < 4: from the tables when the extended string still fits them, else from the index.  Both
+// sources are read unconditionally (the unused one at a harmless address) so that a warp whose lanes mix the two pays
+// one memory latency, not two.
+DEV BiIntv fm_extend_fwd(const DevIndex& x, const BiIntv& ik, int c, int plen, u32 pidx)
+{
+	const bool tab = x.kmer_tab != nullptr && plen >= 1 && plen < x.kmer_k;
+	BiIntv in = ik;
+	if (tab) { in.x0 = 1; in.x1 = 1; in.size = 1; }
+	const uint4 te = ldg(x.kmer_tab ? x.kmer_tab + (tab ? kmer_level_off(plen + 1) + ((u64)pidx << 2 | (u32)c) : 0) : (const uint4*)x.bwt);
+	BiIntv ok = fm_extend1(x, in, 3 - c, 0);
+	if (tab) { u32 dummy; cand_unpack(te, ok, dummy); }
+	return ok;
+}
+
 // ---- SMEM discovery -----------------------------------------------------------------------------
 // Working set of one read (one thread): the candidate list of the SMEM search in flight and the read's base codes.
 // Both live in shared memory, interleaved over the threads of the block (element k of this thread's row is at
@@ -221,6 +249,7 @@ DEV void fm_collect_queue(const DevIndex& x, const MemOpt& opt, const SeedWork& 
 	int n_prev = 0, n_curr = 0;
 	u32 last_beg = 0; bool have_out = false;
 	BiIntv okc; int ext_c = 0;
+	int plen = 0; u32 pidx = 0; // bases consumed by the forward scan in flight and their codes (prefix tables: fm_extend_fwd)
 	ik.x0 = ik.x1 = ik.size = 0; ext = ik; pcur = ik; okc = ik;
 #define SM_PUSH(bi, e) do { if (n_curr < lcap_all) { cand_set(wk, n_curr, bi, e); ++n_curr; } else o.overflow = true; } while (0)
 #define SM_END_FORWARD() do { \
@@ -260,7 +289,7 @@ DEV void fm_collect_queue(const DevIndex& x, const MemOpt& opt, const SeedWork& 
 				while (xx < len && Q(xx) > 3) ++xx;
 				if (xx >= len) { old_n = o.n; k2 = 0; round = 2; st = SM_NEXT_R2; break; }
 				start = xx; min_intv = 1;
-				fm_set_intv(x, Q(start), ik); ik_end = (u32)(start + 1); n_curr = 0; i = start + 1;
+				fm_set_intv(x, Q(start), ik); ik_end = (u32)(start + 1); n_curr = 0; i = start + 1; plen = 1; pidx = (u32)Q(start);
 				st = SM_FWD;
 				break;
 			case SM_NEXT_R2: {
@@ -274,7 +303,7 @@ DEV void fm_collect_queue(const DevIndex& x, const MemOpt& opt, const SeedWork& 
 				}
 				if (!go) { xx = 0; round = 3; st = (PHASES == 3 && opt.max_mem_intv > 0) ? SM_NEXT_R3 : SM_DONE; break; }
 				if (Q(start) > 3) { ++k2; break; } // (an SMEM never holds an ambiguous base; kept for fidelity)
-				fm_set_intv(x, Q(start), ik); ik_end = (u32)(start + 1); n_curr = 0; i = start + 1;
+				fm_set_intv(x, Q(start), ik); ik_end = (u32)(start + 1); n_curr = 0; i = start + 1; plen = 1; pidx = (u32)Q(start);
 				st = SM_FWD;
 				break; }
 			case SM_FWD: // forward phase: record the interval at every change of size
@@ -312,7 +341,7 @@ DEV void fm_collect_queue(const DevIndex& x, const MemOpt& opt, const SeedWork& 
 				while (xx < len && Q(xx) > 3) ++xx;
 				if (xx >= len) { st = SM_DONE; break; }
 				start = xx;
-				fm_set_intv(x, Q(start), ik); i = start + 1;
+				fm_set_intv(x, Q(start), ik); i = start + 1; plen = 1; pidx = (u32)Q(start);
 				st = SM_S3;
 				break;
 			case SM_S3: // bwt_seed_strategy1: shortest forward match of >= min_seed_len+1 bases with < max_mem_intv occurrences
@@ -325,8 +354,9 @@ DEV void fm_collect_queue(const DevIndex& x, const MemOpt& opt, const SeedWork& 
 		}
 		if (lanes_all(st == SM_ALLDONE)) break;
 		if (pend == SMX_NONE) continue; // (this lane has run out of reads; its neighbours have not)
-		// ---- the one place where the index is read
-		okc = fm_extend1(x, ext, ext_c, pend == SMX_BWD ? 1 : 0);
+		// ---- the one place where the index is read (forward steps: the prefix tables while the scan is short enough)
+		if (pend == SMX_BWD) okc = fm_extend1(x, ext, ext_c, 1);
+		else { okc = fm_extend_fwd(x, ext, 3 - ext_c, plen, pidx); pidx = pidx << 2 | (u32)(3 - ext_c); ++plen; }
 		// ---- consume
 		if (pend == SMX_FWD) {
 			bool stop = false;
@@ -451,6 +481,7 @@ DEV void fm_forward_queue(const DevIndex& x, const MemOpt& opt, const SeedSplitI
 	int xx = 0, k2 = 0, n1 = 0, start = 0, i = 0, ext_c = 0;
 	u32 used = 0, c_off = 0, n_c = 0, ik_end = 0, last_end = 0;
 	u64 min_intv = 1;
+	int plen = 0; u32 pidx = 0; // bases consumed by the scan in flight and their codes (prefix tables: fm_extend_fwd)
 	BiIntv ik; ik.x0 = ik.x1 = ik.size = 0;
 	uint4* pool = nullptr;
 	bool ovf = false; // the read does not fit the pool / the task list: it is handed to the one-machine formulation
@@ -501,7 +532,7 @@ DEV void fm_forward_queue(const DevIndex& x, const MemOpt& opt, const SeedSplitI
 					if (!go) { st = F_FETCH; break; }
 					if (q[start] > 3) { ++k2; break; } // (an SMEM never holds an ambiguous base; kept for fidelity)
 				}
-				fm_set_intv(x, q[start], ik); ik_end = (u32)(start + 1); i = start + 1;
+				fm_set_intv(x, q[start], ik); ik_end = (u32)(start + 1); i = start + 1; plen = 1; pidx = (u32)q[start];
 				c_off = used; n_c = 0; last_end = 0;
 				st = F_SCAN;
 				break;
@@ -515,7 +546,8 @@ DEV void fm_forward_queue(const DevIndex& x, const MemOpt& opt, const SeedSplitI
 		}
 		if (lanes_all(st == F_ALLDONE)) break;
 		if (!pend) continue;
-		const BiIntv okc = fm_extend1(x, ik, ext_c, 0);
+		const BiIntv okc = fm_extend_fwd(x, ik, 3 - ext_c, plen, pidx);
+		pidx = pidx << 2 | (u32)(3 - ext_c); ++plen;
 		bool stop = false;
 		if (okc.size != ik.size) {
 			F_PUSH();

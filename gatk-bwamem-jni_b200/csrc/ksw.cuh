@@ -40,6 +40,13 @@ struct WarpMem {
 	i32* ringH; i32* ringE; int ring_n; int ring_stride;
 };
 #define THREAD_RING_N 64
+// element stride of a thread's shared-memory arrays in the extension-side / rescue task kernels: the block size, a
+// compile-time constant there, so that the unrolled cells of a row are addressed with immediate offsets
+#ifdef B200_SIM
+#define TX_STRIDE 1
+#else
+#define TX_STRIDE THREADS_PER_BLOCK
+#endif
 #define WQ(wm_, j_) (wm_).q[(size_t)(j_) * (wm_).q_stride]
 
 // target accessor over the doubled reference text

@@ -41,7 +41,7 @@ DEV SwFwd tsw_pass_u8(const DevIndex& x, const MemOpt& opt, const TswMem& tm, co
 	SwFwd r; r.score = 0; r.te = -1; r.qe = -1; r.score2 = -1; r.te2 = -1;
 	const int slen = (qlen + 15) >> 4, nw = slen << 3;
 	if (slen == 0) return r;
-	const size_t ST = (size_t)tm.stride;
+	constexpr size_t ST = TX_STRIDE; // (== tm.stride)
 	const int e_ins = opt.e_ins;
 	const u32 NEG_EDEL = pk2(-opt.e_del), NEG_OEDEL = pk2(-(opt.o_del + opt.e_del)), NEG_EINS = pk2(-opt.e_ins), NEG_OEINS = pk2(-(opt.o_ins + opt.e_ins));
 	const u32 NEG_SHIFT = pk2(-shift), SAT = 0x00ff00ffu;

@@ -54,6 +54,10 @@ struct DevIndex {
 	const u8* pac;      // 2 bits per base
 	const double* log_tab;  // glibc log(i), i in [0, LOG_TAB_N)  (hazard H5: libm results are tabulated on the host)
 	i32 log_tab_n;
+	// Bidirectional intervals of every string of 2..kmer_k bases (forward extension from its first base), 16 bytes each,
+	// level L at offset (4^L - 16) / 3: a forward scan reads its first kmer_k - 1 extensions here (one 16-byte read,
+	// mostly from L2) instead of walking two 64-byte occurrence blocks each.  nullptr / 0: no tables.
+	const uint4* kmer_tab; i32 kmer_k;
 };
 
 // ---- per-batch stage records ------------------------------------------------------------------

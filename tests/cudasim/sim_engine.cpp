@@ -64,6 +64,7 @@ static uint64_t rt_scan_u32(const uint32_t* in, uint64_t* out, uint64_t n) { uin
 	for (int64_t i_ = 0; i_ < (int64_t)(n); ++i_) wbody<32>(P, i_, wm_, ws_); } while (0)
 
 static void rt_timer_begin() {}
+#define RT_KMER_LEVEL(x, tab, L1, n) do { for (u64 e_ = 0; e_ < (u64)(n); ++e_) kmer_build_entry((x), (tab), (L1), e_); } while (0)
 #define RT_DENSIFY(x, n_rows, dense, out) do { for (u64 t_ = 0; t_ < ((u64)(n_rows) + (dense) - 1) / (dense); ++t_) (out)[t_] = fm_sa((x), t_ * (dense)); } while (0)
 #define RT_RELAYOUT(src, size, dst, nb) do { for (u64 b_ = 0; b_ < (u64)(nb); ++b_) fm_relayout_block((src), (size), (dst), b_); } while (0)
 #define RT_WARPS_DEVN(wbody, P, n_ptr, n_max) do { \
