@@ -18,6 +18,7 @@ struct ChainStageIO {
 	const Intv* intv; int n_intv;
 	const i64* sd_rbeg;       // SA values, in (interval, occurrence) order
 	Seed* S; ChainW* C; u32* ord; u32* tmp; // scratch, one slot per lookup
+	u64* kq;                  // scratch, one slot per lookup: (ALT << 63 | weight << 32 | query end << 16 | query begin) of the chains kept so far
 	ChainK* ck; Seed* ks;     // outputs (same slot range)
 };
 
@@ -120,27 +121,33 @@ DEV int chain_read(const DevIndex& x, const MemOpt& opt, int len, ChainStageIO& 
 	if (n == 0) return 0;
 	ChainLtW lt; lt.C = C;
 	ks_introsort<u32, ChainLtW>((size_t)n, ord, lt);
-	u32* kl = io.tmp; int nk = 0; // positions (in ord) of chains kept so far
-	C[ord[0]].kept = 3; kl[nk++] = 0;
+	// The scan of a chain against all chains kept so far is quadratic; what it needs of a kept chain -- query span, weight,
+	// ALT flag -- sits in one word of a compact list (kq), so a comparison is one sequential load instead of three dependent ones.
+	u32* kl = io.tmp; u64* kq = io.kq; int nk = 0; // positions (in ord) of chains kept so far
+#define CHAIN_PACK(c_) ((u64)(x.ctg_alt[(c_).rid] ? 1 : 0) << 63 | (u64)(c_).w << 32 | (u64)((u32)(S[(c_).tail].qbeg + S[(c_).tail].len) & 0xffffu) << 16 | (u64)((u32)S[(c_).head].qbeg & 0xffffu))
+	C[ord[0]].kept = 3; kl[0] = 0; kq[0] = CHAIN_PACK(C[ord[0]]); nk = 1;
 	for (int i = 1; i < n; ++i) {
 		ChainW& ci = C[ord[i]];
-		int ib = S[ci.head].qbeg, ie = S[ci.tail].qbeg + S[ci.tail].len;
+		const u64 vi = CHAIN_PACK(ci);
+		const int ib = (int)(vi & 0xffffu), ie = (int)(vi >> 16 & 0xffffu), wi = (int)(vi >> 32 & 0x7fffffffu); const bool alt_i = (vi >> 63) != 0;
 		bool large_ovlp = false; int k;
 		for (k = 0; k < nk; ++k) {
-			ChainW& cj = C[ord[kl[k]]];
-			int jb = S[cj.head].qbeg, je = S[cj.tail].qbeg + S[cj.tail].len;
+			const u64 vj = kq[k];
+			const int jb = (int)(vj & 0xffffu), je = (int)(vj >> 16 & 0xffffu), wj = (int)(vj >> 32 & 0x7fffffffu);
 			int b_max = jb > ib ? jb : ib, e_min = je < ie ? je : ie;
-			if (e_min > b_max && (!x.ctg_alt[cj.rid] || x.ctg_alt[ci.rid])) { // (a chain on an ALT contig never masks one on the primary assembly)
+			if (e_min > b_max && (!(vj >> 63) || alt_i)) { // (a chain on an ALT contig never masks one on the primary assembly)
 				int li = ie - ib, lj = je - jb, min_l = li < lj ? li : lj;
 				if ((float)(e_min - b_max) >= (float)min_l * opt.mask_level && min_l < opt.max_chain_gap) {
 					large_ovlp = true;
+					ChainW& cj = C[ord[kl[k]]];
 					if (cj.first < 0) cj.first = i;
-					if ((float)(int)ci.w < (float)(int)cj.w * opt.drop_ratio && (int)cj.w - (int)ci.w >= opt.min_seed_len << 1) break;
+					if ((float)wi < (float)wj * opt.drop_ratio && wj - wi >= opt.min_seed_len << 1) break;
 				}
 			}
 		}
-		if (k == nk) { kl[nk++] = (u32)i; ci.kept = large_ovlp ? 2 : 3; }
+		if (k == nk) { kl[nk] = (u32)i; kq[nk] = vi; ++nk; ci.kept = large_ovlp ? 2 : 3; }
 	}
+#undef CHAIN_PACK
 	for (int i = 0; i < nk; ++i) { ChainW& c = C[ord[kl[i]]]; if (c.first >= 0) C[ord[c.first]].kept = 1; }
 	{
 		int i, k;

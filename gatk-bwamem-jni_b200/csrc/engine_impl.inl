@@ -88,7 +88,7 @@ struct EngineConfig {
 	bool chain_all_warp = false, chain_all_thread = false, chain_no_overlap = false, tiny_scratch = false, all_heavy = false, all_light = false;
 	bool warp_extend = false, ext_wide_cells = false, no_ext_tasks = false, rescue_fallback = false, final_one_pass = false, final_ring = false, tiny_ga_cap = false;
 	bool ext_legacy = false, ext_no_sort = false, force_long_mode = false, rescue_warp_sw = false, ga_no_sort = false, ext_task_machine = false;
-	int seed_lcap = 0, seed_shared_read = -1, tx_chunk = -1, light_seeds = -1, light_chains = -1;
+	int seed_lcap = 0, seed_shared_read = -1, tx_chunk = -1, light_seeds = -1, light_chains = -1, final_heavy_hits = -1;
 	static bool flag(const char* nm) { return getenv(nm) != nullptr; }
 	static int num(const char* nm, int dflt) { const char* e = getenv(nm); return e ? atoi(e) : dflt; }
 	void read_env()
@@ -107,7 +107,7 @@ struct EngineConfig {
 		rescue_fallback = flag("B200_TEST_RESCUE_FALLBACK"); final_one_pass = flag("B200_FINAL_ONE_PASS"); final_ring = flag("B200_TEST_FINAL_RING");
 		tiny_ga_cap = flag("B200_TEST_TINY_GA_CAP"); ext_legacy = flag("B200_EXT_LEGACY"); ext_no_sort = flag("B200_EXT_NO_SORT"); force_long_mode = flag("B200_TEST_LONG_MODE"); rescue_warp_sw = flag("B200_RESCUE_WARP_SW"); ga_no_sort = flag("B200_GA_NO_SORT"); ext_task_machine = flag("B200_EXT_TASK_MACHINE");
 		seed_lcap = num("B200_SEED_LCAP", 0); seed_shared_read = num("B200_SEED_SHARED_READ", -1); tx_chunk = num("B200_TX_CHUNK", -1);
-		light_seeds = num("B200_LIGHT_SEEDS", -1); light_chains = num("B200_LIGHT_CHAINS", -1);
+		light_seeds = num("B200_LIGHT_SEEDS", -1); light_chains = num("B200_LIGHT_CHAINS", -1); final_heavy_hits = num("B200_FINAL_HEAVY_HITS", -1);
 	}
 };
 
@@ -586,6 +586,7 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 	if (n_reads == 0) { void* r = malloc(1); return r; }
 	// ---- option / shape validation: fail loudly instead of approximating
 	if (opt.e_del <= 0 || opt.e_ins <= 0 || opt.a <= 0 || opt.max_occ <= 0 || opt.min_seed_len <= 0) { last_error = "unsupported option values"; return nullptr; }
+	if (max_len > 65535) { last_error = "reads longer than 65535 bases are not supported"; return nullptr; } // (query coordinates are packed in 16 bits in the chain filter)
 	// mem_flt_chained_seeds (B10) acts on a read of l bases unless min_l > 0.05 l, min_l = 1.1 min_chain_weight or 5.5 ln l.
 	// 5.5 ln l - 0.05 l is concave, so with default options the test fails first for the LONGEST read: when it holds
 	// for max_len (and for min_seed_len) no read of the batch needs the filter and its launches are skipped.
@@ -786,18 +787,19 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 			// classes of query length: a launch per class and side, rows sized for the class (short sides are the bulk: small
 			// rows let many warps be resident); without the ordering there is one class with the longest rows
 			enum { NCLS = 4 };
-			const uint32_t thr[NCLS] = { 24u, 48u, 96u, 0xffffffffu }; // a class holds the sides with fewer than thr bases (and at least the class below's)
+			const uint32_t thr[NCLS] = { 24u, 48u, 96u, 0x7fffffffu }; // a class holds the sides with fewer than thr bases (and at least the class below's)
+			uint32_t thr_key[NCLS]; for (int k = 0; k < NCLS; ++k) thr_key[k] = thr[k] << 1; // (keys are query length * 2 + kind of read)
 			uint32_t bnd[2 * NCLS];
 			for (int k = 0; k < 2 * NCLS; ++k) bnd[k] = (k % NCLS == NCLS - 1) ? n_t : 0u; // (unordered: everything in the last class)
 			if (n_t && !cfg.ext_no_sort) { // order the tasks of each side by query length: the lanes of a warp then run rows of similar width
-				int bits = 1; while ((1 << bits) <= max_len && bits < 31) ++bits;
+				int bits = 2; while ((1 << (bits - 1)) <= max_len && bits < 31) ++bits;
 				rt_iota_u32(b_xtidx.as<u32>(), n_t);
 				rt_sort_pairs_u32(P.ext_key_l, b_xtkey2.as<u32>(), b_xtidx.as<u32>(), b_xtidx2.as<u32>(), n_t, bits);
 				rt_sort_pairs_u32(P.ext_key_r, b_xtkey2.as<u32>() + Tn, b_xtidx.as<u32>(), b_xtidx2.as<u32>() + Tn, n_t, bits);
 				P.ext_order_l = b_xtidx2.as<u32>(); P.ext_order_r = b_xtidx2.as<u32>() + Tn;
 				// class boundaries in the two sorted key arrays (first position whose key is >= thr)
-				rt_lower_bounds_u32(b_xtkey2.as<u32>(), n_t, thr, NCLS - 1, b_xtidx.as<u32>());
-				rt_lower_bounds_u32(b_xtkey2.as<u32>() + Tn, n_t, thr, NCLS - 1, b_xtidx.as<u32>() + NCLS);
+				rt_lower_bounds_u32(b_xtkey2.as<u32>(), n_t, thr_key, NCLS - 1, b_xtidx.as<u32>());
+				rt_lower_bounds_u32(b_xtkey2.as<u32>() + Tn, n_t, thr_key, NCLS - 1, b_xtidx.as<u32>() + NCLS);
 				rt_d2h(bnd, b_xtidx.p, sizeof(bnd));
 				bnd[NCLS - 1] = n_t; bnd[2 * NCLS - 1] = n_t;
 				hp.mark("ext_class_sync");
@@ -960,6 +962,7 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 			if (!ok) { last_error = "device allocation failed (alignment tasks)"; return nullptr; }
 			P.ga_tasks = b_gatask.as<GaTask>(); P.ga_res = b_gares.as<GaRes>(); P.ga_item0 = b_gaitem0.as<u32>(); P.ga_itemn = b_gaitemn.as<u32>();
 			P.n_ga_tasks = b_misc.as<u32>() + 23;
+			P.final_heavy_hits = cfg.final_heavy_hits >= 0 ? cfg.final_heavy_hits : 24;
 			ok = b_gakey.ensure((size_t)P.ga_cap * 4) && b_gakey2.ensure((size_t)P.ga_cap * 4) && b_gaiota.ensure((size_t)P.ga_cap * 4) && b_gaorder.ensure((size_t)P.ga_cap * 4) && b_gafb.ensure((size_t)P.ga_cap * 4);
 			if (!ok) { last_error = "device allocation failed (alignment tasks)"; return nullptr; }
 			P.ga_key = cfg.ga_no_sort ? nullptr : b_gakey.as<u32>(); P.ga_order = nullptr; P.ga_fb = b_gafb.as<u32>(); P.n_ga_fb = b_misc.as<u32>() + 32;

@@ -178,6 +178,10 @@ DEV BiIntv fm_extend_fwd(const DevIndex& x, const BiIntv& ik, int c, int plen, u
 	return ok;
 }
 
+// (The interval of a string does not depend on the order in which it was grown, so the backward sweeps could read their
+// short extended strings here as well; measured on the B200 that made them slower -- 14.3 -> 20.0 ms: they are bound by
+// instruction issue and latency, not by DRAM traffic, and the second source adds instructions to every trip.)
+
 // ---- SMEM discovery -----------------------------------------------------------------------------
 // Working set of one read (one thread): the candidate list of the SMEM search in flight and the read's base codes.
 // Both live in shared memory, interleaved over the threads of the block (element k of this thread's row is at

@@ -70,6 +70,7 @@ struct BatchParams {
 	u32* chain_heavy; u32* n_chain_heavy; int chain_heavy_seeds; // reads chained by a warp
 	int chain_listed;       // the list of those reads was written beforehand (body_chain_classify): body_chain only skips them
 	GaTask* ga_tasks; GaRes* ga_res; u32* n_ga_tasks; u32 ga_cap; u32* ga_item0; u32* ga_itemn; // two-pass finalize (galign_thread.cuh)
+	int final_heavy_hits;   // finalize items with more hits than this skip the thread-level passes (warp-level kernel)
 	u32* ga_key; const u32* ga_order; u32* ga_fb; u32* n_ga_fb; // cost key per task, tasks ordered by it, tasks left to the warp-per-task kernel
 	int use_ext_res;        // wbody_extend consumes ext_res (set for the replay launch of the heavy reads only)
 	int t_ext_rw;           // thread-level extension: shared-memory words per thread (DP row, doubling as the two NW rings)
@@ -215,6 +216,7 @@ DEV void body_chain(const BatchParams& P, i64 r)
 	io.intv = P.intv + (size_t)r * P.intv_cap; io.n_intv = (int)P.n_intv[r];
 	io.sd_rbeg = P.sd_rbeg + t0;
 	io.S = P.S + t0; io.C = P.C + t0; io.ord = P.ord + t0; io.tmp = P.tmp32 + t0; io.ck = P.ck + t0; io.ks = P.ks + t0;
+	io.kq = P.srt + t0; // (a pool of the extension stage, free at this point)
 	int nks = 0;
 	int nck = P.seed_off[r + 1] > t0 ? chain_read(P.x, P.opt, len, io, &nks) : 0;
 	P.n_ck[r] = (u32)nck; P.n_ks[r] = (u32)nks;
@@ -232,6 +234,7 @@ DEV void wbody_chain_heavy(const BatchParams& P, i64 item, WarpMem& wm, WarpScra
 	io.intv = P.intv + (size_t)r * P.intv_cap; io.n_intv = (int)P.n_intv[r];
 	io.sd_rbeg = P.sd_rbeg + t0;
 	io.S = P.S + t0; io.C = P.C + t0; io.ord = P.ord + t0; io.tmp = P.tmp32 + t0; io.ck = P.ck + t0; io.ks = P.ks + t0;
+	io.kq = nullptr;
 	ChainWarpScratch cs; cs.pos_sorted = (i64*)(P.regs_tmp + t0); cs.qbw = P.srt + t0; // pools of later stages, free at this point
 	int nks = 0;
 	const int nck = chain_read_warp<W>(P.x, P.opt, len, io, cs, &nks);
@@ -728,7 +731,9 @@ DEV void wbody_heavy_prep(const BatchParams& P, i64 item, WarpMem& wm, WarpScrat
 			const u32 base = atomic_add_u32(P.n_ext_tasks, (u32)cn);
 			for (int t = 0; t < cn; ++t) {
 				ExtTask tk; tk.r = (u32)r; tk.c = (u32)c; tk.t = (u32)t; tk.pad_ = 0; P.ext_tasks[base + t] = tk;
-				if (P.ext_sides) { P.ext_key_l[base + t] = (u32)seeds[t].qbeg; P.ext_key_r[base + t] = (u32)(l_query - seeds[t].qbeg - seeds[t].len); }
+				// sort key of a side: query length, then the kind of read (tasks of repeat-derived reads end at scattered rows; those
+				// of ordinary reads mostly run to the end of the read: kept apart, a warp's 32 tasks stay in step longer)
+				if (P.ext_sides) { P.ext_key_l[base + t] = (u32)seeds[t].qbeg << 1 | 1u; P.ext_key_r[base + t] = (u32)(l_query - seeds[t].qbeg - seeds[t].len) << 1 | 1u; }
 			}
 		}
 	}
@@ -770,7 +775,7 @@ DEV void body_ext_prep(const BatchParams& P, i64 r)
 		P.ck_rmax[2 * (t0 + c)] = rmax0; P.ck_rmax[2 * (t0 + c) + 1] = rmax1;
 		ExtTask tk; tk.r = (u32)r; tk.c = (u32)c; tk.t = (u32)best; tk.pad_ = 0;
 		P.ext_tasks[base] = tk;
-		P.ext_key_l[base] = (u32)seeds[best].qbeg; P.ext_key_r[base] = (u32)(l_query - seeds[best].qbeg - seeds[best].len);
+		P.ext_key_l[base] = (u32)seeds[best].qbeg << 1; P.ext_key_r[base] = (u32)(l_query - seeds[best].qbeg - seeds[best].len) << 1;
 		++base;
 	}
 }
@@ -911,6 +916,12 @@ DEV void wbody_galign_fb(const BatchParams& P, i64 item, WarpMem& wm, WarpScratc
 // ---- two-pass finalize (galign_thread.cuh): collect the alignment requests of an item, later consume their results
 DEV void final_collect_item(const BatchParams& P, i64 item, i64 tid, bool pe)
 {
+	// An item with many hits (reads from repeats) costs a thread quadratic work in both passes and holds its warp's other 31
+	// lanes back: it goes straight to the warp-level kernel, which runs the decision logic once with its scans spread over the lanes.
+	{
+		const u32 nh = pe ? P.n_reg[item << 1] + P.n_reg[(item << 1) + 1] : P.n_reg[item];
+		if (nh > (u32)P.final_heavy_hits) { P.ga_item0[item] = 0; P.ga_itemn[item] = 0xffffffffu; return; }
+	}
 	u32* const sink = thread_err_word(P, tid); *sink = 0; // limits hit while collecting are not real: no alignment has been computed yet
 	WarpMem wm; WarpScratch ws; make_thread_ctx(P, tid, wm, ws, sink);
 	GaTask lt[GA_ITEM_MAX];
@@ -931,9 +942,9 @@ DEV void final_collect_item(const BatchParams& P, i64 item, i64 tid, bool pe)
 }
 DEV void final_consume_item(const BatchParams& P, i64 item, i64 tid, bool pe)
 {
-	if (pe) { restore_regs(P, item << 1, 0, 1); restore_regs(P, (item << 1) + 1, 0, 1); } else restore_regs(P, item, 0, 1); // the collect pass edited them
 	const u32 n = P.ga_itemn[item];
 	bool redo = n == 0xffffffffu;
+	if (!redo) { if (pe) { restore_regs(P, item << 1, 0, 1); restore_regs(P, (item << 1) + 1, 0, 1); } else restore_regs(P, item, 0, 1); } // the collect pass edited them (the redo kernel restores them itself)
 	if (!redo) {
 		u32* const lerr = thread_err_word(P, tid); *lerr = 0;
 		WarpMem wm; WarpScratch ws; make_thread_ctx(P, tid, wm, ws, lerr);

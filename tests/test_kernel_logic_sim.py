@@ -144,3 +144,15 @@ def test_sim_alt_contigs(paired, flag):
     a = run_blob(oracle_lib(), img, blob, flag)
     b = run_blob(sim_lib(), img, blob, flag)
     assert a == b, first_diff(a, b, blob, paired)
+
+
+@pytest.mark.parametrize("k", ["2", "5", "7"])
+def test_sim_prefix_tables(small_genome, monkeypatch, k):
+    """Prefix tables (BWA_B200_KMER): the first extensions of every forward scan and the backward extensions that yield short
+    strings are table reads; the intervals, hence the records, are the same."""
+    g, img = small_genome
+    blob, _ = simdata.make_reads(g, 84, 300, 150, True, repeat_read_frac=0.3, n_rate=0.01, err_rate=0.03)
+    a = run_blob(oracle_lib(), img, blob, 2)
+    monkeypatch.setenv("BWA_B200_KMER", k)
+    b = run_blob(sim_lib(), img, blob, 2)
+    assert a == b, first_diff(a, b, blob, True)
