@@ -384,9 +384,9 @@ static int rt_launches() { return t_rt ? t_rt->launches : 0; }
 	RT_SET_SMEM(k_##wbody, sm_); \
 	k_##wbody<<<(unsigned)nb_, WARPS_PER_BLOCK * 32, sm_, rt_stream()>>>(P, n_ptr, next_counter()); ++t_rt->launches; rt_mark(#wbody); } while (0)
 
-__global__ void k_relayout(const u32* src, u64 bwt_size, u32* dst, u64 n_blocks)
+__global__ void k_relayout(const u32* src, u64 bwt_size, u32* dst, u64 n_blocks, const u64* sb, int sb_shift)
 {
-	for (u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x; b < n_blocks; b += (u64)gridDim.x * blockDim.x) fm_relayout_block(src, bwt_size, dst, b);
+	for (u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x; b < n_blocks; b += (u64)gridDim.x * blockDim.x) fm_relayout_block(src, bwt_size, dst, b, sb, sb_shift);
 }
 // denser suffix-array samples at load time: row k (a multiple of `dense`) walks to the next row the image samples
 __global__ void k_densify_sa(DevIndex x, u64 n_rows, u32 dense, u64* out)
@@ -401,7 +401,7 @@ __global__ void k_kmer_level(DevIndex x, uint4* tab, int L1, u64 n)
 }
 #define RT_KMER_LEVEL(x, tab, L1, n) do { k_kmer_level<<<(unsigned)(rt_sm_count() * 16), 256, 0, rt_stream()>>>((x), (tab), (L1), (n)); cu_ok(cudaGetLastError(), "kmer level"); } while (0)
 #define RT_DENSIFY(x, n_rows, dense, out) do { k_densify_sa<<<(unsigned)(rt_sm_count() * 16), 256, 0, rt_stream()>>>((x), (n_rows), (dense), (out)); cu_ok(cudaGetLastError(), "densify"); } while (0)
-#define RT_RELAYOUT(src, size, dst, nb) do { k_relayout<<<(unsigned)(rt_sm_count() * 16), 256, 0, rt_stream()>>>((src), (size), (dst), (nb)); cu_ok(cudaGetLastError(), "relayout"); } while (0)
+#define RT_RELAYOUT(src, size, dst, nb, sb, sbs) do { k_relayout<<<(unsigned)(rt_sm_count() * 16), 256, 0, rt_stream()>>>((src), (size), (dst), (nb), (sb), (sbs)); cu_ok(cudaGetLastError(), "relayout"); } while (0)
 
 
 #include "engine_impl.inl"

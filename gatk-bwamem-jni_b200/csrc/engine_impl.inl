@@ -88,7 +88,7 @@ struct EngineConfig {
 	bool chain_all_warp = false, chain_all_thread = false, chain_no_overlap = false, tiny_scratch = false, all_heavy = false, all_light = false;
 	bool warp_extend = false, ext_wide_cells = false, no_ext_tasks = false, rescue_fallback = false, final_one_pass = false, final_ring = false, tiny_ga_cap = false;
 	bool ext_legacy = false, ext_no_sort = false, force_long_mode = false, rescue_warp_sw = false, ga_no_sort = false, ext_task_machine = false;
-	int seed_lcap = 0, seed_shared_read = -1, tx_chunk = -1, light_seeds = -1, light_chains = -1, final_heavy_hits = -1;
+	int seed_lcap = 0, seed_shared_read = -1, tx_chunk = -1, light_seeds = -1, light_chains = -1, final_heavy_hits = -1, occ_sb_shift = 0;
 	static bool flag(const char* nm) { return getenv(nm) != nullptr; }
 	static int num(const char* nm, int dflt) { const char* e = getenv(nm); return e ? atoi(e) : dflt; }
 	void read_env()
@@ -108,6 +108,7 @@ struct EngineConfig {
 		tiny_ga_cap = flag("B200_TEST_TINY_GA_CAP"); ext_legacy = flag("B200_EXT_LEGACY"); ext_no_sort = flag("B200_EXT_NO_SORT"); force_long_mode = flag("B200_TEST_LONG_MODE"); rescue_warp_sw = flag("B200_RESCUE_WARP_SW"); ga_no_sort = flag("B200_GA_NO_SORT"); ext_task_machine = flag("B200_EXT_TASK_MACHINE");
 		seed_lcap = num("B200_SEED_LCAP", 0); seed_shared_read = num("B200_SEED_SHARED_READ", -1); tx_chunk = num("B200_TX_CHUNK", -1);
 		light_seeds = num("B200_LIGHT_SEEDS", -1); light_chains = num("B200_LIGHT_CHAINS", -1); final_heavy_hits = num("B200_FINAL_HEAVY_HITS", -1);
+		occ_sb_shift = num("B200_TEST_OCC_SB", 0); if (occ_sb_shift < 0 || occ_sb_shift > 40) occ_sb_shift = 0; // force super-block bases every 2^n sectors
 	}
 };
 
@@ -165,9 +166,9 @@ struct Engine;
 struct Replica {
 	int dev = 0;
 	DevIndex dx;
-	DBuf d_bwt, d_sa, d_sa_dense, d_pac, d_ctg, d_log, d_names, d_name_off, d_kmer;
+	DBuf d_bwt, d_occ_sb, d_sa, d_sa_dense, d_pac, d_ctg, d_log, d_names, d_name_off, d_kmer;
 	int busy = 0; // contexts of this device inside a call (guarded by Engine::mu)
-	void release_all() { DBuf* all[] = { &d_bwt, &d_sa, &d_sa_dense, &d_pac, &d_ctg, &d_log, &d_names, &d_name_off, &d_kmer }; for (DBuf* b : all) b->release(); }
+	void release_all() { DBuf* all[] = { &d_bwt, &d_occ_sb, &d_sa, &d_sa_dense, &d_pac, &d_ctg, &d_log, &d_names, &d_name_off, &d_kmer }; for (DBuf* b : all) b->release(); }
 };
 
 // One batch in flight: a runtime context (streams, events, timer: engine.cu RtCtx) on one device, the grow-only batch
@@ -291,6 +292,22 @@ inline bool Engine::upload(Replica& R, const Replica* from)
 	size_t bwt_bytes = (size_t)img.bwt_size * 4;
 	const uint64_t n_blocks = (img.seq_len + 127) / 128;
 	const size_t pac_bytes = (size_t)(img.l_pac / 4 + 1);
+	// The device keeps u32 counts per sector (fm.cuh).  A text in which one base occurs 2^32 times or more gets super-block
+	// bases (u64, every 2^31 rows) that the counts are relative to; they are read off the image's own blocks here.
+	std::vector<uint64_t> occ_sb; int occ_sb_shift = 0;
+	{
+		bool wide = false;
+		for (int c = 0; c < 4; ++c) wide = wide || img.L2[c + 1] - img.L2[c] >= ((uint64_t)1 << 32);
+		if (wide) occ_sb_shift = 25;
+		if (cfg.occ_sb_shift >= 1) occ_sb_shift = cfg.occ_sb_shift;
+		if (occ_sb_shift) {
+			const uint64_t n_sb = ((2 * n_blocks) >> occ_sb_shift) + 1;
+			occ_sb.resize((size_t)n_sb * 4);
+			for (uint64_t t = 0; t < n_sb; ++t) fm_image_counts((const u32*)img.bwt, (u64)img.bwt_size, (t << occ_sb_shift) >> 1, &occ_sb[(size_t)t * 4]);
+			if (!R.d_occ_sb.ensure(occ_sb.size() * 8)) { last_error = "device allocation failed"; return false; }
+			rt_h2d(R.d_occ_sb.p, occ_sb.data(), occ_sb.size() * 8);
+		}
+	}
 	if (from) {
 		const bool dense = from->d_sa_dense.p != nullptr;
 		const size_t sa_bytes = dense ? from->d_sa_dense.cap : (size_t)img.n_sa * 8;
@@ -302,11 +319,11 @@ inline bool Engine::upload(Replica& R, const Replica* from)
 		if (!ok) { last_error = "peer copy of the index failed"; return false; }
 	} else {
 		{ // the occ-interleaved BWT goes up as it is in the image, then every 64-byte block is re-laid out for the device
-		  // (symbols as two bit-planes, fm.cuh); the staging copy is released
+		  // (two 32-byte sectors: u32 counts, symbols as two bit-planes; fm.cuh); the staging copy is released
 			DBuf raw;
 			if (!raw.ensure(bwt_bytes + 64) || !d_bwt.ensure((size_t)n_blocks * 64 + 64)) { raw.release(); last_error = "device allocation failed"; return false; }
 			rt_h2d(raw.p, img.bwt, bwt_bytes);
-			RT_RELAYOUT((const u32*)raw.p, (u64)img.bwt_size, (u32*)d_bwt.p, n_blocks);
+			RT_RELAYOUT((const u32*)raw.p, (u64)img.bwt_size, (u32*)d_bwt.p, n_blocks, occ_sb_shift ? (const u64*)R.d_occ_sb.p : (const u64*)nullptr, occ_sb_shift);
 			rt_sync();
 			raw.release();
 		}
@@ -332,7 +349,7 @@ inline bool Engine::upload(Replica& R, const Replica* from)
 	rt_h2d(d_name_off.p, noff.data(), noff.size() * 4);
 	memset(&dx, 0, sizeof(dx));
 	dx.primary = img.primary; memcpy(dx.L2, img.L2, 40); dx.seq_len = img.seq_len;
-	dx.bwt = (const uint4*)d_bwt.p; dx.sa = (const u64*)d_sa.p; dx.sa_intv = (u32)img.sa_intv;
+	dx.bwt = (const uint4*)d_bwt.p; dx.occ_sb = occ_sb_shift ? (const u64*)R.d_occ_sb.p : nullptr; dx.occ_sb_shift = occ_sb_shift; dx.sa = (const u64*)d_sa.p; dx.sa_intv = (u32)img.sa_intv;
 	dx.l_pac = img.l_pac; dx.n_seqs = img.n_seqs; dx.ctg_off = (const i64*)d_ctg.p; dx.pac = (const u8*)d_pac.p;
 	dx.ctg_alt = (const u8*)d_ctg.p + off.size() * 8;
 	dx.log_tab = (const double*)d_log.p; dx.log_tab_n = LOG_TAB_N;

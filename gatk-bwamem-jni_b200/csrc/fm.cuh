@@ -5,64 +5,89 @@
 // bwa at :214): bwt_occ4 / bwt_2occ4 / bwt_extend / bwt_smem1a / bwt_seed_strategy1 /
 // mem_collect_intv / bwt_sa / bwt_invPsi of un-vendored lh3/bwa.
 //
-// One occurrence block is 64 bytes = two 32-byte sectors: sector 0 holds the four u64 base counts,
-// sector 1 the 128 two-bit symbols.  A lookup is four 128-bit read-only loads of one aligned block
-// (algorithmic traffic: 64 B per block touch).
-//
-// Device layout of sector 1 (re-laid out once at upload by fm_relayout_block; counts, block index arithmetic and
-// every result are unchanged): the 128 symbols are stored as two BIT-PLANES -- words 8..11 hold the low bits
-// (symbol j at bit j & 31 of word 8 + (j >> 5)), words 12..15 the high bits.  Counting the symbols before an offset
-// then needs one position mask per 32 symbols shared by three population counts (low, high, both) instead of
-// 64-bit shift/mask/popcount sequences over interleaved pairs: ~3x fewer instructions per lookup.
+// DEVICE LAYOUT OF THE OCCURRENCE ARRAY (re-laid out once at upload by fm_relayout_block; every result is unchanged).
+// The image interleaves 4 x u64 running counts with 128 two-bit symbols: a 64-byte block.  The device keeps one 32-byte
+// SECTOR per 64 rows instead:
+//   words 0..3  the counts of A, C, G, T before the sector, as u32 -- relative to the sector's SUPER-BLOCK when a base
+//               occurs 2^32 times or more in the text (DevIndex.occ_sb: u64 counts at every 2^occ_sb_shift-th sector;
+//               nullptr for every genome whose per-base totals fit 32 bits, e.g. human: the common case reads nothing
+//               extra and pays one uniform branch);
+//   words 4..5  the low bits of the 64 symbols (symbol j at bit j & 31 of word 4 + (j >> 5)), words 6..7 the high bits.
+// A lookup is two 128-bit read-only loads of one aligned sector and six population counts (one position mask per 32
+// symbols shared by the low, high and both planes): half the load instructions, L1 requests and population counts of a
+// lookup in the image layout, same bytes in HBM.  (The L2 fetches 64 bytes from HBM on a miss whatever the request and
+// ignores the fetch-granularity hint, so DRAM traffic is unchanged -- profiles/README.md -- the gain is instruction issue.
+// Three 40-bit counts with A derived from the position need no super-blocks, but their decoding made the compiler
+// split the batched sector loads of the backward sweeps: 12.8 -> 16.4 ms.)
 #pragma once
 #include "types.cuh"
 
-struct OccBlock { uint4 c01, c23, s0, s1; };
+struct OccBlock { uint4 cnt, sym; };
+#define OCC_SHIFT 6 /* rows per sector = 64 */
+#define OCC_MASK 63
 
 DEV OccBlock load_block(const DevIndex& x, u64 blk)
 {
-	const uint4* p = x.bwt + (blk << 2);
+	const uint4* p = x.bwt + (blk << 1);
 	OccBlock b;
-	b.c01 = ldg(p); b.c23 = ldg(p + 1); b.s0 = ldg(p + 2); b.s1 = ldg(p + 3);
+	b.cnt = ldg(p); b.sym = ldg(p + 1);
 	return b;
 }
 
-// image layout -> device layout for block b (src: the image's occ-interleaved BWT of bwt_size words; dst: n_blocks * 16 words)
-DEV void fm_relayout_block(const u32* src, u64 bwt_size, u32* dst, u64 b)
+// image layout -> device layout for image block b (src: the image's occ-interleaved BWT of bwt_size words; dst: two
+// sectors = 16 words per image block).  sb / sb_shift: the super-block table (or nullptr), read here as the base to
+// subtract; super-blocks start on image-block boundaries (sb_shift >= 1).
+HOSTDEV void fm_image_counts(const u32* src, u64 bwt_size, u64 b, u64 cnt[4])
+{
+	for (int c = 0; c < 4; ++c) { const u64 i = (b << 4) + 2 * c; cnt[c] = i + 1 < bwt_size ? ((u64)src[i] | (u64)src[i + 1] << 32) : 0; }
+}
+DEV void fm_relayout_block(const u32* src, u64 bwt_size, u32* dst, u64 b, const u64* sb, int sb_shift)
 {
 	const u64 base = b << 4;
 	u32 w[16];
 	for (int t = 0; t < 16; ++t) w[t] = base + t < bwt_size ? src[base + t] : 0u;
-	u32 p0[4] = { 0, 0, 0, 0 }, p1[4] = { 0, 0, 0, 0 };
-	for (int j = 0; j < 128; ++j) {
-		const u32 sym = w[8 + (j >> 4)] >> ((15 - (j & 15)) << 1) & 3u;
-		p0[j >> 5] |= (sym & 1u) << (j & 31);
-		p1[j >> 5] |= (sym >> 1) << (j & 31);
+	u64 cnt[4];
+	for (int c = 0; c < 4; ++c) cnt[c] = (u64)w[2 * c] | (u64)w[2 * c + 1] << 32;
+	for (int h = 0; h < 2; ++h) {
+		const u64 sec = b * 2 + h;
+		u32 p0[2] = { 0, 0 }, p1[2] = { 0, 0 }; u32 n[4] = { 0, 0, 0, 0 };
+		for (int j = 0; j < 64; ++j) {
+			const int jj = h * 64 + j;
+			const u32 sym = w[8 + (jj >> 4)] >> ((15 - (jj & 15)) << 1) & 3u;
+			p0[j >> 5] |= (sym & 1u) << (j & 31);
+			p1[j >> 5] |= (sym >> 1) << (j & 31);
+			++n[sym];
+		}
+		u32* d = dst + sec * 8;
+		for (int c = 0; c < 4; ++c) d[c] = (u32)(cnt[c] - (sb ? sb[(sec >> sb_shift) * 4 + c] : 0));
+		d[4] = p0[0]; d[5] = p0[1]; d[6] = p1[0]; d[7] = p1[1];
+		for (int c = 0; c < 4; ++c) cnt[c] += n[c]; // (padding symbols past the end of the text count as A: never looked up)
 	}
-	for (int t = 0; t < 8; ++t) dst[base + t] = w[t];
-	for (int t = 0; t < 4; ++t) { dst[base + 8 + t] = p0[t]; dst[base + 12 + t] = p1[t]; }
 }
 
-// Occurrences of A,C,G,T in packed-BWT positions [0, kk] given the block that holds kk.  Branch-free: every lane runs
-// the same twelve population counts whatever its offset in the block.  Symbols past the offset are masked out of both
+// (a call on purpose: inlined, these few loads are if-converted and every lookup of the common case -- no super-blocks --
+// issues them predicated off: ~12 % of the instructions of a backward sweep)
+DEVNI u64 occ_super_block_base(const u64* sb, u64 idx, int c) { return ldg(sb + idx * 4 + c); }
+
+// Occurrences of A,C,G,T in packed-BWT positions [0, kk] given the sector that holds kk.  Branch-free: every lane runs
+// the same six population counts whatever its offset in the sector.  Symbols past the offset are masked out of both
 // planes (= A) and never counted; A is what remains of n.
-DEV void occ4_in_block(const OccBlock& b, u64 kk, u64 cnt[4])
+DEV void occ4_in_block(const DevIndex& x, const OccBlock& b, u64 kk, u64 cnt[4])
 {
-	const int n = (int)(kk & 127) + 1; // 1..128 symbols of this block
-	const u32 p0[4] = { b.s0.x, b.s0.y, b.s0.z, b.s0.w }, p1[4] = { b.s1.x, b.s1.y, b.s1.z, b.s1.w };
-	u32 sLo = 0, sHi = 0, sT = 0;
-#pragma unroll
-	for (int w = 0; w < 4; ++w) {
-		const int nn = n - 32 * w;
-		const u32 m = nn >= 32 ? 0xffffffffu : (nn > 0 ? (1u << nn) - 1u : 0u);
-		const u32 lo = p0[w] & m, hi = p1[w] & m;
-		sLo += (u32)__popc(lo); sHi += (u32)__popc(hi); sT += (u32)__popc(lo & hi);
-	}
+	const int n = (int)(kk & OCC_MASK) + 1; // 1..64 symbols of this sector
+	const u32 m0 = n >= 32 ? 0xffffffffu : (1u << n) - 1u, m1 = n >= 64 ? 0xffffffffu : (n > 32 ? (1u << (n - 32)) - 1u : 0u);
+	const u32 lo0 = b.sym.x & m0, lo1 = b.sym.y & m1, hi0 = b.sym.z & m0, hi1 = b.sym.w & m1;
+	const u32 sLo = (u32)__popc(lo0) + (u32)__popc(lo1), sHi = (u32)__popc(hi0) + (u32)__popc(hi1), sT = (u32)__popc(lo0 & hi0) + (u32)__popc(lo1 & hi1);
 	const u32 cC = sLo - sT, cG = sHi - sT, cT = sT;
-	cnt[0] = ((u64)b.c01.x | (u64)b.c01.y << 32) + (u64)((u32)n - cC - cG - cT);
-	cnt[1] = ((u64)b.c01.z | (u64)b.c01.w << 32) + cC;
-	cnt[2] = ((u64)b.c23.x | (u64)b.c23.y << 32) + cG;
-	cnt[3] = ((u64)b.c23.z | (u64)b.c23.w << 32) + cT;
+	cnt[0] = (u64)(b.cnt.x + ((u32)n - cC - cG - cT));
+	cnt[1] = (u64)(b.cnt.y + cC);
+	cnt[2] = (u64)(b.cnt.z + cG);
+	cnt[3] = (u64)(b.cnt.w + cT);
+	if (x.occ_sb) { // (uniform over the launch)
+		const u64 idx = (kk >> OCC_SHIFT) >> x.occ_sb_shift;
+		cnt[0] += occ_super_block_base(x.occ_sb, idx, 0); cnt[1] += occ_super_block_base(x.occ_sb, idx, 1);
+		cnt[2] += occ_super_block_base(x.occ_sb, idx, 2); cnt[3] += occ_super_block_base(x.occ_sb, idx, 3);
+	}
 }
 
 // k is an SA row number including the '$' row; (u64)-1 yields zeros
@@ -70,29 +95,33 @@ DEV void occ4(const DevIndex& x, u64 k, u64 cnt[4])
 {
 	if (k == ~0ull) { cnt[0] = cnt[1] = cnt[2] = cnt[3] = 0; return; }
 	k -= (k >= x.primary);
-	OccBlock b = load_block(x, k >> 7);
-	occ4_in_block(b, k, cnt);
+	OccBlock b = load_block(x, k >> OCC_SHIFT);
+	occ4_in_block(x, b, k, cnt);
 }
 
 struct BiIntv { u64 x0, x1, size; };
 
 // bwt_extend for ONE base c (the only one a caller ever consumes): no per-base arrays, so nothing is spilled to local
 // memory by lane-varying indexing.  The complementary coordinate needs the sizes of the bases above c only.
-DEV BiIntv fm_extend1(const DevIndex& x, const BiIntv& ik, int c, int is_back)
+// (in two halves, so that a caller can issue the sector loads of several kinds of step together)
+struct ExtRows { u64 k_, l_; bool kz, lz; };
+DEV ExtRows fm_extend1_rows(const DevIndex& x, const BiIntv& ik, int is_back)
+{
+	const u64 a0 = is_back ? ik.x0 : ik.x1;
+	const u64 k = a0 - 1, l = a0 - 1 + ik.size;
+	ExtRows r;
+	r.kz = k == ~0ull; r.lz = l == ~0ull;
+	r.k_ = r.kz ? 0 : k - (k >= x.primary); r.l_ = r.lz ? 0 : l - (l >= x.primary);
+	return r;
+}
+DEV BiIntv fm_extend1_finish(const DevIndex& x, const BiIntv& ik, int c, int is_back, const ExtRows& er, const OccBlock& bk, const OccBlock& bl)
 {
 	u64 tk[4], tl[4];
 	const u64 a0 = is_back ? ik.x0 : ik.x1, oth = is_back ? ik.x1 : ik.x0, s = ik.size;
-	const u64 k = a0 - 1, l = a0 - 1 + s;
-	{
-		const bool kz = k == ~0ull, lz = l == ~0ull;
-		const u64 k_ = kz ? 0 : k - (k >= x.primary), l_ = lz ? 0 : l - (l >= x.primary);
-		OccBlock bk = load_block(x, k_ >> 7);
-		OccBlock bl = load_block(x, l_ >> 7);
-		occ4_in_block(bk, k_, tk);
-		occ4_in_block(bl, l_, tl);
-		if (kz) { tk[0] = tk[1] = tk[2] = tk[3] = 0; }
-		if (lz) { tl[0] = tl[1] = tl[2] = tl[3] = 0; }
-	}
+	occ4_in_block(x, bk, er.k_, tk);
+	occ4_in_block(x, bl, er.l_, tl);
+	if (er.kz) { tk[0] = tk[1] = tk[2] = tk[3] = 0; }
+	if (er.lz) { tl[0] = tl[1] = tl[2] = tl[3] = 0; }
 	const u64 s1 = tl[1] - tk[1], s2 = tl[2] - tk[2], s3 = tl[3] - tk[3];
 	const u64 kc = c == 0 ? tk[0] : c == 1 ? tk[1] : c == 2 ? tk[2] : tk[3];
 	const u64 lc = c == 0 ? tl[0] : c == 1 ? tl[1] : c == 2 ? tl[2] : tl[3];
@@ -104,6 +133,13 @@ DEV BiIntv fm_extend1(const DevIndex& x, const BiIntv& ik, int c, int is_back)
 	r.size = lc - kc;
 	if (is_back) { r.x0 = v; r.x1 = o; } else { r.x1 = v; r.x0 = o; }
 	return r;
+}
+DEV BiIntv fm_extend1(const DevIndex& x, const BiIntv& ik, int c, int is_back)
+{
+	const ExtRows er = fm_extend1_rows(x, ik, is_back);
+	const OccBlock bk = load_block(x, er.k_ >> OCC_SHIFT);
+	const OccBlock bl = load_block(x, er.l_ >> OCC_SHIFT);
+	return fm_extend1_finish(x, ik, c, is_back, er, bk, bl);
 }
 
 // N independent backward extensions by the same base (candidates of one row of a backward sweep): all 4N block loads
@@ -124,12 +160,12 @@ DEV void fm_extend1_back_xn(const DevIndex& x, const BiIntv* iv, int c, BiIntv* 
 	}
 	OccBlock b[2 * N];
 #pragma unroll
-	for (int t = 0; t < 2 * N; ++t) b[t] = load_block(x, kk[t] >> 7);
+	for (int t = 0; t < 2 * N; ++t) b[t] = load_block(x, kk[t] >> OCC_SHIFT);
 	const u64 L2c = c == 0 ? x.L2[0] : c == 1 ? x.L2[1] : c == 2 ? x.L2[2] : x.L2[3];
 #pragma unroll
 	for (int t = 0; t < N; ++t) {
 		u64 tk[4], tl[4];
-		occ4_in_block(b[2 * t], kk[2 * t], tk); occ4_in_block(b[2 * t + 1], kk[2 * t + 1], tl);
+		occ4_in_block(x, b[2 * t], kk[2 * t], tk); occ4_in_block(x, b[2 * t + 1], kk[2 * t + 1], tl);
 		if (zz[2 * t]) { tk[0] = tk[1] = tk[2] = tk[3] = 0; }
 		if (zz[2 * t + 1]) { tl[0] = tl[1] = tl[2] = tl[3] = 0; }
 		const u64 s1 = tl[1] - tk[1], s2 = tl[2] - tk[2], s3 = tl[3] - tk[3];
@@ -390,24 +426,28 @@ DEV void fm_collect_queue(const DevIndex& x, const MemOpt& opt, const SeedWork& 
 }
 
 // ---- suffix-array resolution ----------------------------------------------------------------------
-// bwt_sa: LF-walk from row k to a sampled row.  One block touch per step (the BWT symbol and its rank
-// live in the same 64-byte block) + one 8-byte SA read.
+// bwt_sa: LF-walk from row k to a sampled row.  One sector touch per step (the BWT symbol and its rank
+// live in the same 32-byte sector) + one 8-byte SA read.
+// (one LF step from row k != primary, given the sector of its packed position kk = k - (k > primary))
+DEV u64 fm_lf_finish(const DevIndex& x, const OccBlock& b, u64 kk)
+{
+	const u32 bit = (u32)(kk & 31);
+	const u32 lo = (kk & 32) ? b.sym.y : b.sym.x, hi = (kk & 32) ? b.sym.w : b.sym.z;
+	const int c = (int)((lo >> bit & 1u) | (hi >> bit & 1u) << 1);
+	// occ(k, c) counts rows [0,k]; k > primary maps to packed position k-1 == kk, k < primary to k == kk
+	u64 cnt[4];
+	occ4_in_block(x, b, kk, cnt);
+	return x.L2[c] + cnt[c];
+}
 DEV u64 fm_sa(const DevIndex& x, u64 k)
 {
 	u64 sa = 0, mask = (u64)x.sa_intv - 1;
 	while (k & mask) {
 		++sa;
 		if (k == x.primary) { k = 0; continue; }
-		u64 kk = k - (k > x.primary); // position of this row's symbol in the packed BWT
-		OccBlock b = load_block(x, kk >> 7);
-		const u32 wsel = (u32)(kk & 127) >> 5, bit = (u32)(kk & 31);
-		const u32 lo = wsel == 0 ? b.s0.x : wsel == 1 ? b.s0.y : wsel == 2 ? b.s0.z : b.s0.w;
-		const u32 hi = wsel == 0 ? b.s1.x : wsel == 1 ? b.s1.y : wsel == 2 ? b.s1.z : b.s1.w;
-		int c = (int)((lo >> bit & 1u) | (hi >> bit & 1u) << 1);
-		// occ(k, c) counts rows [0,k]; k > primary maps to packed position k-1 == kk, k < primary to k == kk
-		u64 cnt[4];
-		occ4_in_block(b, kk, cnt);
-		k = x.L2[c] + cnt[c];
+		const u64 kk = k - (k > x.primary); // position of this row's symbol in the packed BWT
+		const OccBlock b = load_block(x, kk >> OCC_SHIFT);
+		k = fm_lf_finish(x, b, kk);
 	}
 	return sa + ldg(&x.sa[k / x.sa_intv]);
 }
@@ -658,6 +698,8 @@ DEV void fm_backward_queue(const DevIndex& x, const MemOpt& opt, const SeedSplit
 		if (lanes_ballot(pend != 0) == 0u) continue;
 		if (!pend) continue;
 		BiIntv oks[SEED_BWD_WAYS];
+		// (two code paths on purpose: in the late rows of a sweep no lane of the warp has a second candidate and the warp
+		// skips the wide one altogether -- folding the two into one measured 15 % slower)
 		if (pend == SEED_BWD_WAYS) fm_extend1_back_xn<SEED_BWD_WAYS>(x, pcs, c, oks);
 		else if (SEED_BWD_WAYS > 2 && pend >= 2) { fm_extend1_back_xn<2>(x, pcs, c, oks); for (int t = 2; t < pend; ++t) oks[t] = fm_extend1(x, pcs[t], c, 1); }
 		else oks[0] = fm_extend1(x, pcs[0], c, 1);

@@ -44,7 +44,8 @@ static_assert(sizeof(PeStat) == 32, "mem_pestat_t layout");
 // ---- index resident in HBM --------------------------------------------------------------------
 struct DevIndex {
 	u64 primary, L2[5], seq_len;
-	const uint4* bwt;   // occ-interleaved BWT: one 64-byte block (4 x u64 counts + 128 x 2-bit symbols) per 128 rows
+	const uint4* bwt;   // occurrence array: one 32-byte sector (4 x u32 counts + 64 symbols as two bit-planes) per 64 rows (fm.cuh)
+	const u64* occ_sb; i32 occ_sb_shift; // super-block bases of the u32 counts (4 x u64 per 2^shift sectors); nullptr: counts are absolute
 	const u64* sa;      // sampled suffix array (row k*sa_intv -> text position)
 	u32 sa_intv;        // power of two (32 in the image; smaller when densified at load)
 	i64 l_pac;

@@ -66,7 +66,7 @@ static uint64_t rt_scan_u32(const uint32_t* in, uint64_t* out, uint64_t n) { uin
 static void rt_timer_begin() {}
 #define RT_KMER_LEVEL(x, tab, L1, n) do { for (u64 e_ = 0; e_ < (u64)(n); ++e_) kmer_build_entry((x), (tab), (L1), e_); } while (0)
 #define RT_DENSIFY(x, n_rows, dense, out) do { for (u64 t_ = 0; t_ < ((u64)(n_rows) + (dense) - 1) / (dense); ++t_) (out)[t_] = fm_sa((x), t_ * (dense)); } while (0)
-#define RT_RELAYOUT(src, size, dst, nb) do { for (u64 b_ = 0; b_ < (u64)(nb); ++b_) fm_relayout_block((src), (size), (dst), b_); } while (0)
+#define RT_RELAYOUT(src, size, dst, nb, sb, sbs) do { for (u64 b_ = 0; b_ < (u64)(nb); ++b_) fm_relayout_block((src), (size), (dst), b_, (sb), (sbs)); } while (0)
 #define RT_WARPS_DEVN(wbody, P, n_ptr, n_max) do { \
 	std::vector<uint8_t> sm_(warp_smem_bytes((P).wm_cap) + 64); \
 	WarpMem wm_; WarpScratch ws_; make_warp_ctx(P, 0, sm_.data(), wm_, ws_); \

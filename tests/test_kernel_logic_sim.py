@@ -149,10 +149,23 @@ def test_sim_alt_contigs(paired, flag):
 @pytest.mark.parametrize("k", ["2", "5", "7"])
 def test_sim_prefix_tables(small_genome, monkeypatch, k):
     """Prefix tables (BWA_B200_KMER): the first extensions of every forward scan and the backward extensions that yield short
-    strings are table reads; the intervals, hence the records, are the same."""
+    strings are table reads (forward scans only since the sweeps measured slower with them); the intervals, hence the records, are the same."""
     g, img = small_genome
     blob, _ = simdata.make_reads(g, 84, 300, 150, True, repeat_read_frac=0.3, n_rate=0.01, err_rate=0.03)
     a = run_blob(oracle_lib(), img, blob, 2)
     monkeypatch.setenv("BWA_B200_KMER", k)
+    b = run_blob(sim_lib(), img, blob, 2)
+    assert a == b, first_diff(a, b, blob, True)
+
+
+@pytest.mark.parametrize("shift", ["1", "4", "9"])
+def test_sim_occurrence_super_blocks(small_genome, monkeypatch, shift):
+    """The device keeps u32 occurrence counts per 32-byte sector; a text in which a base occurs 2^32 times or more makes
+    them relative to u64 super-block bases (fm.cuh).  No test genome is that large, so the hook forces bases every 2^shift
+    sectors: every lookup then adds a base, and the records must not change."""
+    g, img = small_genome
+    blob, _ = simdata.make_reads(g, 85, 300, 150, True, repeat_read_frac=0.3, n_rate=0.01, err_rate=0.03)
+    a = run_blob(oracle_lib(), img, blob, 2)
+    monkeypatch.setenv("B200_TEST_OCC_SB", shift)
     b = run_blob(sim_lib(), img, blob, 2)
     assert a == b, first_diff(a, b, blob, True)
