@@ -60,6 +60,7 @@ DEV int chain_weight(const ChainW& c, const Seed* S)
 }
 
 struct ChainLtW { const ChainW* C; DEVM bool operator()(u32 a, u32 b) const { return C[a].w > C[b].w; } };
+struct ChainKeyLtW { DEVM bool operator()(u64 a, u64 b) const { return (u32)(a >> 32) > (u32)(b >> 32); } }; // keys (weight << 32 | chain)
 
 // returns the number of kept chains; *n_kept_seeds gets the number of seeds they hold
 DEV int chain_read(const DevIndex& x, const MemOpt& opt, int len, ChainStageIO& io, int* n_kept_seeds)
@@ -67,7 +68,7 @@ DEV int chain_read(const DevIndex& x, const MemOpt& opt, int len, ChainStageIO& 
 	*n_kept_seeds = 0;
 	if (len < opt.min_seed_len) return 0;
 	Seed* S = io.S; ChainW* C = io.C; u32* ord = io.ord;
-	int nch = 0, si = 0;
+	int nch = 0, si = 0, rid_hint = -1;
 	// l_rep: query bases covered by intervals that are too repetitive to be enumerated fully
 	int b = 0, e = 0, l_rep = 0;
 	for (int i = 0; i < io.n_intv; ++i) {
@@ -87,8 +88,9 @@ DEV int chain_read(const DevIndex& x, const MemOpt& opt, int len, ChainStageIO& 
 			int sidx = si++;
 			Seed s; s.rbeg = io.sd_rbeg[sidx]; s.qbeg = (i32)p.beg; s.len = s.score = slen; s.next = -1;
 			S[sidx] = s;
-			int rid = ref_intv2rid(x, s.rbeg, s.rbeg + s.len);
+			int rid = ref_intv2rid(x, s.rbeg, s.rbeg + s.len, rid_hint);
 			if (rid < 0) continue; // spans two contigs or the forward/reverse junction
+			rid_hint = rid;
 			bool to_add = true; int at = 0;
 			if (nch) {
 				int lo = 0, hi = nch;
@@ -199,47 +201,75 @@ DEVNI int chain_read_warp(const DevIndex& x, const MemOpt& opt, int len, ChainSt
 	l_rep += e - b;
 	for (int i = 0; i < io.n_intv; ++i) {
 		const Intv p = io.intv[i];
-		int slen = (int)(p.end - p.beg);
-		i64 step = p.size > (u64)opt.max_occ ? (i64)(p.size / (u64)opt.max_occ) : 1;
-		int count = 0;
-		for (i64 k = 0; (u64)k < p.size && count < opt.max_occ; k += step, ++count) {
-			int sidx = si++;
-			Seed s; s.rbeg = io.sd_rbeg[sidx]; s.qbeg = (i32)p.beg; s.len = s.score = slen; s.next = -1;
-			ONE_LANE { S[sidx] = s; }
-			WARP_SYNC();
-			int rid = ref_intv2rid(x, s.rbeg, s.rbeg + s.len);
-			if (rid < 0) continue;
-			bool to_add = true; int at = 0;
-			if (nch) {
-				int lo = 0, hi = nch;
-				while (lo < hi) { int mid = (lo + hi) >> 1; if (ps[mid] < s.rbeg) lo = mid + 1; else hi = mid; }
-				int lower = -1;
-				if (lo < nch && ps[lo] == s.rbeg) { lower = (int)ord[lo]; at = lo + 1; }
-				else if (lo > 0) { lower = (int)ord[lo - 1]; at = lo; }
-				else at = 0;
-				if (lower >= 0) {
-					int merged = 0;
-					LANE0_ONLY { merged = chain_test_and_merge(opt, x.l_pac, C[lower], S, sidx, rid) ? 1 : 0; }
-					WARP_SYNC();
-					{ WV(int, mv); FOR_LANES { L_(mv) = merged; } merged = wv_get(mv, 0); }
-					if (merged) to_add = false;
+		const int slen = (int)(p.end - p.beg);
+		const i64 step = p.size > (u64)opt.max_occ ? (i64)(p.size / (u64)opt.max_occ) : 1;
+		int m = 0; // seeds of this interval (the scalar loop: k = 0, step, ... while k < size and fewer than max_occ taken)
+		{ const u64 by_size = (p.size + (u64)step - 1) / (u64)step; m = (int)(by_size < (u64)opt.max_occ ? by_size : (u64)opt.max_occ); }
+		for (int c0 = 0; c0 < m; c0 += W) {
+			// a lane per seed: its record and its contig (nothing here depends on the chains built so far) ...
+			WV(i64, rbv); WV(int, ridv);
+			FOR_LANES {
+				const int j = c0 + lane;
+				L_(rbv) = 0; L_(ridv) = -1;
+				if (j < m) {
+					Seed s; s.rbeg = io.sd_rbeg[si + j]; s.qbeg = (i32)p.beg; s.len = s.score = slen; s.next = -1;
+					S[si + j] = s;
+					L_(rbv) = s.rbeg; L_(ridv) = ref_intv2rid(x, s.rbeg, s.rbeg + s.len);
 				}
 			}
-			if (to_add) {
-				ONE_LANE { ChainW c; c.pos = s.rbeg; c.head = c.tail = sidx; c.n = 1; c.rid = rid; c.w = 0; c.kept = 0; c.first = -1; C[nch] = c; }
-				// shift [at, nch) up by one, highest chunk first
-				for (int hi2 = nch; hi2 > at; hi2 -= W) {
-					WV(u32, to); WV(i64, tp);
-					FOR_LANES { int j = hi2 - 1 - lane; if (j >= at) { L_(to) = ord[j]; L_(tp) = ps[j]; } }
-					WARP_SYNC();
-					FOR_LANES { int j = hi2 - 1 - lane; if (j >= at) { ord[j + 1] = L_(to); ps[j + 1] = L_(tp); } }
-					WARP_SYNC();
+			WARP_SYNC();
+			// ... then the seeds one after the other, in order, as the scalar loop inserts them
+			const int mt = m - c0 < W ? m - c0 : W;
+			for (int t = 0; t < mt; ++t) {
+				const int sidx = si + c0 + t;
+				const i64 rbeg = wv_get(rbv, t); const int rid = wv_get(ridv, t);
+				if (rid < 0) continue;
+				bool to_add = true; int at = 0;
+				if (nch) {
+					// lower bound of rbeg among the chain starts: W probes per round instead of one
+					int lo = 0, hi = nch;
+					while (hi - lo > W) {
+						const int stride = (hi - lo + W - 1) / W;
+						WV(bool, below);
+						FOR_LANES { const int pos = lo + (lane + 1) * stride - 1; L_(below) = pos < hi ? ps[pos] < rbeg : false; }
+						const int cnt = __popc(wv_ballot(below)); // (sorted: the lanes below rbeg are a prefix)
+						const int nlo = lo + cnt * stride, nhi = lo + (cnt + 1) * stride - 1;
+						lo = nlo < hi ? nlo : hi; hi = nhi < hi ? nhi : hi;
+					}
+					{
+						WV(bool, below);
+						FOR_LANES { const int pos = lo + lane; L_(below) = pos < hi ? ps[pos] < rbeg : false; }
+						lo += __popc(wv_ballot(below));
+					}
+					int lower = -1;
+					if (lo < nch && ps[lo] == rbeg) { lower = (int)ord[lo]; at = lo + 1; }
+					else if (lo > 0) { lower = (int)ord[lo - 1]; at = lo; }
+					else at = 0;
+					if (lower >= 0) {
+						int merged = 0;
+						LANE0_ONLY { merged = chain_test_and_merge(opt, x.l_pac, C[lower], S, sidx, rid) ? 1 : 0; }
+						WARP_SYNC();
+						{ WV(int, mv); FOR_LANES { L_(mv) = merged; } merged = wv_get(mv, 0); }
+						if (merged) to_add = false;
+					}
 				}
-				ONE_LANE { ord[at] = (u32)nch; ps[at] = s.rbeg; }
-				WARP_SYNC();
-				++nch;
+				if (to_add) {
+					ONE_LANE { ChainW c; c.pos = rbeg; c.head = c.tail = sidx; c.n = 1; c.rid = rid; c.w = 0; c.kept = 0; c.first = -1; C[nch] = c; }
+					// shift [at, nch) up by one, highest chunk first
+					for (int hi2 = nch; hi2 > at; hi2 -= W) {
+						WV(u32, to); WV(i64, tp);
+						FOR_LANES { int j = hi2 - 1 - lane; if (j >= at) { L_(to) = ord[j]; L_(tp) = ps[j]; } }
+						WARP_SYNC();
+						FOR_LANES { int j = hi2 - 1 - lane; if (j >= at) { ord[j + 1] = L_(to); ps[j + 1] = L_(tp); } }
+						WARP_SYNC();
+					}
+					ONE_LANE { ord[at] = (u32)nch; ps[at] = rbeg; }
+					WARP_SYNC();
+					++nch;
+				}
 			}
 		}
+		si += m;
 	}
 	if (nch == 0) return 0;
 	float frac_rep = (float)l_rep / len;
@@ -251,11 +281,15 @@ DEVNI int chain_read_warp(const DevIndex& x, const MemOpt& opt, int len, ChainSt
 	WARP_SYNC();
 	{ WV(int, nv); FOR_LANES { L_(nv) = n; } n = wv_get(nv, 0); }
 	if (n == 0) return 0;
-	LANE0_ONLY { ChainLtW lt; lt.C = C; ks_introsort<u32, ChainLtW>((size_t)n, ord, lt); }
-	WARP_SYNC();
+	// The weight-descending introsort (tie order observable: one lane, the algorithm itself) over (weight, chain) pairs in
+	// one word each: the same comparisons in the same order as on the chain indices, without two dependent loads per compare.
 	u64* qbw = cs.qbw;
+	FOR_LANES { for (int i = lane; i < n; i += W) qbw[i] = (u64)C[ord[i]].w << 32 | ord[i]; }
+	LANE0_ONLY { ChainKeyLtW lt; ks_introsort<u64, ChainKeyLtW>((size_t)n, qbw, lt); }
+	WARP_SYNC();
 	FOR_LANES {
 		for (int i = lane; i < n; i += W) {
+			ord[i] = (u32)qbw[i];
 			const ChainW& c = C[ord[i]];
 			const u32 qb = (u32)S[c.head].qbeg, qe = (u32)(S[c.tail].qbeg + S[c.tail].len);
 			qbw[i] = (u64)(x.ctg_alt[c.rid] ? 1 : 0) << 63 | (u64)c.w << 32 | (u64)(qe & 0xffffu) << 16 | (u64)(qb & 0xffffu);

@@ -79,7 +79,7 @@ struct HostProf {
 // remaining B200_* variables force kernel variants and capacity limits for the parity tests and for tuning runs: they
 // change which kernels a call launches, so they are honoured only when B200_TEST_HOOKS=1 is set as well.
 struct EngineConfig {
-	int sa_intv = 8;             // BWA_B200_SA_INTV
+	int sa_intv = 4;             // BWA_B200_SA_INTV: suffix-array samples kept on the device (8 B per 4 rows = 12.4 GB for a human genome)
 	int contexts = 3;            // BWA_B200_CONTEXTS: batches in flight per device
 	int kmer_k = 12;             // BWA_B200_KMER: longest string of the prefix tables (0: none; 12 = 358 MB)
 	bool hostprof = false, debug_stats = false;

@@ -21,13 +21,18 @@ DEV int ref_pos2rid(const DevIndex& x, i64 pos_f)
 	return mid;
 }
 
-DEV int ref_intv2rid(const DevIndex& x, i64 rb, i64 re)
+// (ctg_off has n_seqs + 1 entries, the last one l_pac: "pos_f lies in contig r" is one pair of comparisons)
+DEV bool ref_pos_in_rid(const DevIndex& x, i64 pos_f, int r) { return pos_f >= x.ctg_off[r] && pos_f < x.ctg_off[r + 1]; }
+
+// hint: a contig to try before searching (the previous seed's: the seeds of a read mostly share one); -1: none
+DEV int ref_intv2rid(const DevIndex& x, i64 rb, i64 re, int hint = -1)
 {
 	int is_rev;
 	if (rb < x.l_pac && re > x.l_pac) return -2;
-	int rid_b = ref_pos2rid(x, ref_depos(x, rb, is_rev));
-	int rid_e = rb < re ? ref_pos2rid(x, ref_depos(x, re - 1, is_rev)) : rid_b;
-	return rid_b == rid_e ? rid_b : -1;
+	const i64 pb = ref_depos(x, rb, is_rev);
+	const int rid_b = (hint >= 0 && ref_pos_in_rid(x, pb, hint)) ? hint : ref_pos2rid(x, pb);
+	if (!(rb < re)) return rid_b;
+	return ref_pos_in_rid(x, ref_depos(x, re - 1, is_rev), rid_b) ? rid_b : -1; // (the end in another contig: the search would return that one)
 }
 
 DEV int pac_base(const u8* pac, i64 l) { return pac[l >> 2] >> ((~l & 3) << 1) & 3; }
