@@ -444,7 +444,7 @@ def main():
                 dll.jnibwa_free(res)
                 with lock:
                     cursor["sum"] ^= last; cursor["bytes"] = sz
-        ths = [threading.Thread(target=worker, args=(t,)) for t in range(n_threads)]
+        ths = [threading.Thread(target=worker, args=(t,), daemon=True) for t in range(n_threads)]  # (daemon: a failure in the main thread must end the process)
         for t in ths:
             t.start()
         ready.wait()
@@ -626,4 +626,12 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except SystemExit:
+        raise
+    except BaseException:  # noqa: BLE001 -- a failed run must END (helper threads may be blocked inside the library), never hang the box
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush(); sys.stdout.flush()
+        os._exit(1)

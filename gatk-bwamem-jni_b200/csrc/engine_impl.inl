@@ -201,6 +201,7 @@ struct Batch {
 	void* run(const MemOpt* opt, const PeStat* pes0, size_t* out_size, bool host_output);
 	void* align(const MemOpt* opt, const PeStat* pes0, char* blob, size_t* out_size);
 	void release_all();
+	size_t workspace_bytes(); // device bytes this context holds
 };
 
 struct Engine {
@@ -392,6 +393,21 @@ inline bool Engine::upload(Replica& R, const Replica* from)
 	return g_last_cuda_ok();
 }
 
+inline size_t Batch::workspace_bytes()
+{
+	DBuf* all[] = { &b_blob, &b_seq, &b_seqoff, &b_intv, &b_nintv, &b_nseed, &b_smem,
+	                &b_seedoff, &b_rbeg, &b_S, &b_C, &b_ord, &b_tmp32, &b_ck, &b_ks, &b_srt, &b_regtmp, &b_nck, &b_nks, &b_nreg, &b_regcap, &b_regoff,
+	                &b_regs, &b_snap, &b_ztmp, &b_pairv, &b_recs, &b_nrec, &b_cand, &b_pairtab, &b_var, &b_misc, &b_outwords, &b_outoff, &b_out,
+	                &b_wsz, &b_wscig, &b_wsmd, &b_wsxa, &b_wsbrow, &b_nb, &b_swtask, &b_swstate, &b_swlist, &b_tbuf, &b_redo, &b_heavy, &b_multi, &b_cand2, &b_specstate, &b_spectask, &b_nreg0, &b_rsheavy, &b_wsrt, &b_wsrkey, &b_wsrrank, &b_exttask, &b_extres, &b_ckrmax, &b_chainheavy, &b_gatask, &b_gares, &b_gaitem0, &b_gaitemn, &b_seedpool, &b_seedused, &b_seedtask, &b_seedfb,
+	                &b_xtkey, &b_xtkey2, &b_xtidx, &b_xtidx2, &b_wsrows, &b_flttask, &b_tswhmax, &b_tswbrow, &b_swrev, &b_swfb, &b_gakey, &b_gakey2, &b_gaiota, &b_gaorder, &b_gafb };
+	size_t n = 0;
+	for (DBuf* b : all) n += b->cap;
+	if (eng->cfg.debug_stats) { // the largest buffers by name
+		static const char* const names[] = { "b_blob", "b_seq", "b_seqoff", "b_intv", "b_nintv", "b_nseed", "b_smem", "b_seedoff", "b_rbeg", "b_S", "b_C", "b_ord", "b_tmp32", "b_ck", "b_ks", "b_srt", "b_regtmp", "b_nck", "b_nks", "b_nreg", "b_regcap", "b_regoff", "b_regs", "b_snap", "b_ztmp", "b_pairv", "b_recs", "b_nrec", "b_cand", "b_pairtab", "b_var", "b_misc", "b_outwords", "b_outoff", "b_out", "b_wsz", "b_wscig", "b_wsmd", "b_wsxa", "b_wsbrow", "b_nb", "b_swtask", "b_swstate", "b_swlist", "b_tbuf", "b_redo", "b_heavy", "b_multi", "b_cand2", "b_specstate", "b_spectask", "b_nreg0", "b_rsheavy", "b_wsrt", "b_wsrkey", "b_wsrrank", "b_exttask", "b_extres", "b_ckrmax", "b_chainheavy", "b_gatask", "b_gares", "b_gaitem0", "b_gaitemn", "b_seedpool", "b_seedused", "b_seedtask", "b_seedfb", "b_xtkey", "b_xtkey2", "b_xtidx", "b_xtidx2", "b_wsrows", "b_flttask", "b_tswhmax", "b_tswbrow", "b_swrev", "b_swfb", "b_gakey", "b_gakey2", "b_gaiota", "b_gaorder", "b_gafb" };
+		for (size_t k = 0; k < sizeof(all) / sizeof(all[0]); ++k) if (all[k]->cap >= ((size_t)1 << 29)) fprintf(stderr, "[bwamem-b200]   %-12s %.2f GB\n", names[k], (double)all[k]->cap / 1e9);
+	}
+	return n;
+}
 inline void Batch::release_all()
 {
 	DBuf* all[] = { &b_blob, &b_seq, &b_seqoff, &b_intv, &b_nintv, &b_nseed, &b_smem,
@@ -675,7 +691,10 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 		} else {
 			// every launch has ONE kind of extension step: forward scans (lane per read), backward sweeps (lane per scan),
 			// for round 1 and again for round 2, then round 3 (forward-only seeds; it also orders and counts the list)
-			P.seed_pool_cap = (u32)(6 * max_len + 16); // candidates of all scans of a round (14 KB per read); a read that needs more is redone below
+			// Candidates of all scans of a round: 14 KB per read, 18 GB of the ~41 GB a context holds for 500 000 pairs.  Ordinary
+			// reads use a tenth of it, but the few made of low-complexity sequence need it all, and with a third of it (measured)
+			// 20-30 reads per million fall to the one-machine kernel below, where a single thread takes 30 ms over one of them.
+			P.seed_pool_cap = (u32)(6 * max_len + 16);
 			if (cfg.tiny_seed_pool) P.seed_pool_cap = 24;
 			P.seed_task_cap = (u32)std::min<uint64_t>((uint64_t)0x7fffffff, (uint64_t)n_reads * 24 + 1024); // one task per forward scan (a scan per sequencing error, roughly); reads whose scans do not fit are redone below
 			if (cfg.tiny_seed_tasks) P.seed_task_cap = 48;
@@ -706,6 +725,7 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 	}
 	hp.mark("launch1");
 	uint64_t T = rt_scan_u32(P.n_seed, P.seed_off, n_reads);
+	if (!g_last_cuda_ok()) { last_error = "device error or allocation failure (scan / sort scratch)"; return nullptr; }
 	hp.mark("seed_sync");
 	P.n_seed_total = T; last_n_seed = T;
 	{
@@ -813,6 +833,7 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 				rt_iota_u32(b_xtidx.as<u32>(), n_t);
 				rt_sort_pairs_u32(P.ext_key_l, b_xtkey2.as<u32>(), b_xtidx.as<u32>(), b_xtidx2.as<u32>(), n_t, bits);
 				rt_sort_pairs_u32(P.ext_key_r, b_xtkey2.as<u32>() + Tn, b_xtidx.as<u32>(), b_xtidx2.as<u32>() + Tn, n_t, bits);
+				if (!g_last_cuda_ok()) { last_error = "device error or allocation failure (scan / sort scratch)"; return nullptr; } // (an unsorted order array would send the side kernels to arbitrary tasks)
 				P.ext_order_l = b_xtidx2.as<u32>(); P.ext_order_r = b_xtidx2.as<u32>() + Tn;
 				// class boundaries in the two sorted key arrays (first position whose key is >= thr)
 				rt_lower_bounds_u32(b_xtkey2.as<u32>(), n_t, thr_key, NCLS - 1, b_xtidx.as<u32>());
@@ -874,6 +895,7 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 			// sorted on the device (keys dir<<48 | isize; -1 = no candidate sorts last as unsigned), summed on the host
 			if (!b_cand2.ensure((size_t)(n_units + 1) * 8)) { last_error = "device allocation failed"; return nullptr; }
 			rt_sort_u64((const uint64_t*)P.pe_cand, b_cand2.as<uint64_t>(), (uint64_t)n_units);
+			if (!g_last_cuda_ok()) { last_error = "device error or allocation failure (scan / sort scratch)"; return nullptr; }
 			std::vector<int64_t> cand((size_t)n_units);
 			rt_d2h(cand.data(), b_cand2.p, (size_t)n_units * 8);
 			hp.mark("extend_sync");
@@ -894,6 +916,7 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 	// ---- region capacity, offsets, compaction
 	RT_THREADS(body_reg_cap, P, (int64_t)n_reads);
 	uint64_t R = rt_scan_u32(P.reg_cap, P.reg_off, n_reads);
+	if (!g_last_cuda_ok()) { last_error = "device error or allocation failure (scan / sort scratch)"; return nullptr; }
 	hp.mark("regcap_sync");
 	{
 		size_t Rn = (size_t)R + 2;
@@ -996,6 +1019,7 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 				if (n_ga) {
 					rt_iota_u32(b_gaiota.as<u32>(), n_ga);
 					rt_sort_pairs_u32(P.ga_key, b_gakey2.as<u32>(), b_gaiota.as<u32>(), b_gaorder.as<u32>(), n_ga, 17);
+					if (!g_last_cuda_ok()) { last_error = "device error or allocation failure (scan / sort scratch)"; return nullptr; }
 					P.ga_order = b_gaorder.as<u32>();
 				}
 			}
@@ -1009,6 +1033,7 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 	// ---- output stream
 	RT_THREADS(body_out_size, P, (int64_t)n_reads);
 	uint64_t W = rt_scan_u32(P.out_words, P.out_off, n_reads);
+	if (!g_last_cuda_ok()) { last_error = "device error or allocation failure (scan / sort scratch)"; return nullptr; }
 	hp.mark("final_sync");
 	if (!b_out.ensure((size_t)W * 4 + 16)) { last_error = "device allocation failed (output)"; return nullptr; }
 	P.out = b_out.as<u32>();
@@ -1017,6 +1042,7 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 	rt_d2h(misc, b_misc.p, sizeof(misc));
 	memcpy(&last_counters, misc + 8, sizeof(Counters));
 	n_launches = rt_launches();
+	if (cfg.debug_stats) fprintf(stderr, "[bwamem-b200] workspace of this context: %.2f GB\n", (double)workspace_bytes() / 1e9);
 	if (cfg.debug_stats) fprintf(stderr, "[bwamem-b200] reads %u: finalize redo %u, alignment tasks %u, extension-heavy reads %u / tasks %u, chain-heavy %u, rescue warp-replayed %u / fallback %u, seed one-machine reads %u\n",
 	                                        n_reads, misc[5], misc[23], misc[6], misc[21], misc[22], misc[20], misc[7], misc[28]);
 	if (misc[0]) {
