@@ -117,7 +117,8 @@ struct DBuf { // growable device buffer
 	bool ensure(size_t bytes) {
 		if (bytes <= cap) return true;
 		if (p) rt_free(p);
-		size_t want = bytes + bytes / 4 + 256;
+		const size_t slack = bytes / 4 < ((size_t)512 << 20) ? bytes / 4 : ((size_t)512 << 20); // (grow-only: room for the next, slightly larger batch)
+		size_t want = bytes + slack + 256;
 		p = rt_malloc(want); cap = p ? want : 0;
 		return p != nullptr;
 	}
