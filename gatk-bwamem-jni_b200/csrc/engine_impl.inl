@@ -81,6 +81,7 @@ struct HostProf {
 struct EngineConfig {
 	int sa_intv = 4;             // BWA_B200_SA_INTV: suffix-array samples kept on the device (8 B per 4 rows = 12.4 GB for a human genome)
 	int contexts = 3;            // BWA_B200_CONTEXTS: batches in flight per device
+	int seed_pool_gb = 20;       // BWA_B200_SEED_POOL_GB: largest candidate pool of the seeding stage; larger batches are seeded in slices of reads (each slice costs ~1 % of the step)
 	int kmer_k = 12;             // BWA_B200_KMER: longest string of the prefix tables (0: none; 12 = 358 MB)
 	bool hostprof = false, debug_stats = false;
 	// ---- test hooks / tuning aids (B200_TEST_HOOKS=1)
@@ -88,13 +89,14 @@ struct EngineConfig {
 	bool chain_all_warp = false, chain_all_thread = false, chain_no_overlap = false, tiny_scratch = false, all_heavy = false, all_light = false;
 	bool warp_extend = false, ext_wide_cells = false, no_ext_tasks = false, rescue_fallback = false, final_one_pass = false, final_ring = false, tiny_ga_cap = false;
 	bool ext_legacy = false, ext_no_sort = false, force_long_mode = false, rescue_warp_sw = false, ga_no_sort = false, ext_task_machine = false;
-	int seed_lcap = 0, seed_shared_read = -1, tx_chunk = -1, light_seeds = -1, light_chains = -1, final_heavy_hits = -1, occ_sb_shift = 0;
+	int seed_lcap = 0, seed_shared_read = -1, tx_chunk = -1, light_seeds = -1, light_chains = -1, final_heavy_hits = -1, occ_sb_shift = 0, seed_slices = 0;
 	static bool flag(const char* nm) { return getenv(nm) != nullptr; }
 	static int num(const char* nm, int dflt) { const char* e = getenv(nm); return e ? atoi(e) : dflt; }
 	void read_env()
 	{
 		sa_intv = num("BWA_B200_SA_INTV", sa_intv);
 		contexts = num("BWA_B200_CONTEXTS", contexts); if (contexts < 1) contexts = 1; if (contexts > 8) contexts = 8;
+		seed_pool_gb = num("BWA_B200_SEED_POOL_GB", seed_pool_gb); if (seed_pool_gb < 1) seed_pool_gb = 1;
 		kmer_k = num("BWA_B200_KMER", kmer_k); if (kmer_k < 2) kmer_k = 0; if (kmer_k > 13) kmer_k = 13;
 		hostprof = flag("B200_HOSTPROF"); debug_stats = flag("B200_DEBUG_STATS");
 		const char* th = getenv("B200_TEST_HOOKS");
@@ -108,6 +110,7 @@ struct EngineConfig {
 		tiny_ga_cap = flag("B200_TEST_TINY_GA_CAP"); ext_legacy = flag("B200_EXT_LEGACY"); ext_no_sort = flag("B200_EXT_NO_SORT"); force_long_mode = flag("B200_TEST_LONG_MODE"); rescue_warp_sw = flag("B200_RESCUE_WARP_SW"); ga_no_sort = flag("B200_GA_NO_SORT"); ext_task_machine = flag("B200_EXT_TASK_MACHINE");
 		seed_lcap = num("B200_SEED_LCAP", 0); seed_shared_read = num("B200_SEED_SHARED_READ", -1); tx_chunk = num("B200_TX_CHUNK", -1);
 		light_seeds = num("B200_LIGHT_SEEDS", -1); light_chains = num("B200_LIGHT_CHAINS", -1); final_heavy_hits = num("B200_FINAL_HEAVY_HITS", -1);
+		seed_slices = num("B200_TEST_SEED_SLICES", 0);
 		occ_sb_shift = num("B200_TEST_OCC_SB", 0); if (occ_sb_shift < 0 || occ_sb_shift > 40) occ_sb_shift = 0; // force super-block bases every 2^n sectors
 	}
 };
@@ -692,14 +695,22 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 		} else {
 			// every launch has ONE kind of extension step: forward scans (lane per read), backward sweeps (lane per scan),
 			// for round 1 and again for round 2, then round 3 (forward-only seeds; it also orders and counts the list)
-			// Candidates of all scans of a round: 14 KB per read, 18 GB of the ~41 GB a context holds for 500 000 pairs.  Ordinary
-			// reads use a tenth of it, but the few made of low-complexity sequence need it all, and with a third of it (measured)
-			// 20-30 reads per million fall to the one-machine kernel below, where a single thread takes 30 ms over one of them.
+			// Candidates of all scans of a round: 6 x length + 16 per read (14 KB at 150 bases).  Ordinary reads use a tenth of
+			// it, but the few made of low-complexity sequence need it all -- with a third of it (measured) 20-30 reads per
+			// million fall to the one-machine kernel below, where a single thread takes 30 ms over one of them.  So the cap
+			// stays and the BATCH is seeded in slices of reads instead, as many as keep the pool under cfg.seed_pool_gb
+			// (default 20 GB: 500 000 pairs of 150 bases need 17 GB and run as one slice, of 250 bases 23 GB and run as two; rounds 1/2
+			// of a slice are complete before the next begins; measured cost: 2.4 ms of a 105 ms step for two slices).
 			P.seed_pool_cap = (u32)(6 * max_len + 16);
 			if (cfg.tiny_seed_pool) P.seed_pool_cap = 24;
-			P.seed_task_cap = (u32)std::min<uint64_t>((uint64_t)0x7fffffff, (uint64_t)n_reads * 24 + 1024); // one task per forward scan (a scan per sequencing error, roughly); reads whose scans do not fit are redone below
+			int n_slices = (int)(((size_t)n_reads * P.seed_pool_cap * 16 + ((size_t)cfg.seed_pool_gb << 30) - 1) / ((size_t)cfg.seed_pool_gb << 30));
+			if (cfg.seed_slices > 0) n_slices = cfg.seed_slices;
+			if (n_slices < 1) n_slices = 1;
+			if ((int64_t)n_slices > (int64_t)n_reads) n_slices = (int)n_reads;
+			const int64_t slice_reads = ((int64_t)n_reads + n_slices - 1) / n_slices;
+			P.seed_task_cap = (u32)std::min<uint64_t>((uint64_t)0x7fffffff, (uint64_t)slice_reads * 24 + 1024); // one task per forward scan (a scan per sequencing error, roughly); reads whose scans do not fit are redone below
 			if (cfg.tiny_seed_tasks) P.seed_task_cap = 48;
-			ok = b_seedpool.ensure((size_t)n_reads * P.seed_pool_cap * 16) && b_seedused.ensure((size_t)n_reads * 4) && b_seedtask.ensure((size_t)P.seed_task_cap * sizeof(SeedTask)) && b_seedfb.ensure(((size_t)n_reads + 1) * 4);
+			ok = b_seedpool.ensure((size_t)slice_reads * P.seed_pool_cap * 16) && b_seedused.ensure((size_t)n_reads * 4) && b_seedtask.ensure((size_t)P.seed_task_cap * sizeof(SeedTask)) && b_seedfb.ensure(((size_t)n_reads + 1) * 4);
 			if (!ok) { last_error = "device allocation failed (seeding pools)"; return nullptr; }
 			P.seed_pool = b_seedpool.as<uint4>(); P.seed_pool_used = b_seedused.as<u32>(); P.seed_tasks = b_seedtask.as<SeedTask>(); P.n_seed_tasks = b_misc.as<u32>() + 24; // words 24..27: the 64-bit reservation counter and the counts of a full list (fm.cuh seed_task_reserve)
 			P.seed_fb = b_seedfb.as<u32>(); P.n_seed_fb = b_misc.as<u32>() + 28;
@@ -707,19 +718,25 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 			// The scans with many candidates (a warp each: few, long-running warps) run on the auxiliary stream beside the
 			// lane-per-scan sweep of the others; both only append to per-read lists that round 3 orders afterwards.
 			const bool overlap = !cfg.seed_no_overlap;
-			RT_THREADS_QUEUE_SMEM(body_seedF1_q, P, (int64_t)n_reads, 0);
-			if (overlap) rt_fork_aux();
-			RT_WARPS_DEVN(wbody_seedB_heavy, P, P.n_seed_tasks + 1, (int64_t)n_reads);
-			if (overlap) rt_back_to_main();
-			RT_THREADS_QUEUE_SMEM(body_seedB_q, P, (int64_t)P.seed_task_cap, seed_bwd_smem_bytes(THREADS_PER_BLOCK));
-			if (overlap) rt_join_aux("wbody_seedB_heavy");
-			rt_memset(P.n_seed_tasks, 0, 16);
-			RT_THREADS_QUEUE_SMEM(body_seedF2_q, P, (int64_t)n_reads, 0);
-			if (overlap) rt_fork_aux();
-			RT_WARPS_DEVN(wbody_seedB_heavy, P, P.n_seed_tasks + 1, (int64_t)n_reads);
-			if (overlap) rt_back_to_main();
-			RT_THREADS_QUEUE_SMEM(body_seedB2_q, P, (int64_t)P.seed_task_cap, seed_bwd_smem_bytes(THREADS_PER_BLOCK));
-			if (overlap) rt_join_aux("wbody_seedB_heavy");
+			for (int64_t r0 = 0; r0 < (int64_t)n_reads; r0 += slice_reads) {
+				const int64_t nr = std::min<int64_t>(slice_reads, (int64_t)n_reads - r0);
+				P.seed_read_base = r0;
+				if (r0) rt_memset(P.n_seed_tasks, 0, 16);
+				RT_THREADS_QUEUE_SMEM(body_seedF1_q, P, nr, 0);
+				if (overlap) rt_fork_aux();
+				RT_WARPS_DEVN(wbody_seedB_heavy, P, P.n_seed_tasks + 1, nr);
+				if (overlap) rt_back_to_main();
+				RT_THREADS_QUEUE_SMEM(body_seedB_q, P, (int64_t)P.seed_task_cap, seed_bwd_smem_bytes(THREADS_PER_BLOCK));
+				if (overlap) rt_join_aux("wbody_seedB_heavy");
+				rt_memset(P.n_seed_tasks, 0, 16);
+				RT_THREADS_QUEUE_SMEM(body_seedF2_q, P, nr, 0);
+				if (overlap) rt_fork_aux();
+				RT_WARPS_DEVN(wbody_seedB_heavy, P, P.n_seed_tasks + 1, nr);
+				if (overlap) rt_back_to_main();
+				RT_THREADS_QUEUE_SMEM(body_seedB2_q, P, (int64_t)P.seed_task_cap, seed_bwd_smem_bytes(THREADS_PER_BLOCK));
+				if (overlap) rt_join_aux("wbody_seedB_heavy");
+			}
+			P.seed_read_base = 0;
 			RT_THREADS_QUEUE_SMEM(body_seed12_fb_q, P, (int64_t)n_reads, ssm); // (usually an empty list)
 			RT_THREADS_QUEUE_SMEM(body_seed3_q, P, (int64_t)n_reads, ssm);
 		}

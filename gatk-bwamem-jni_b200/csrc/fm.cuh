@@ -468,7 +468,8 @@ DEV u64 fm_sa(const DevIndex& x, u64 k)
 struct SeedTask { u32 read, c_off, n_c, start; u64 min_intv; };
 struct SeedSplitIO {
 	const u8* seq; const u64* seq_off; i64 n_reads;
-	uint4* pool; u32 pool_cap;        // pool_cap candidates per read
+	i64 read_base;                    // the forward launch covers reads [read_base, read_base + n_reads): a batch is seeded in slices when its pool would be too large
+	uint4* pool; u32 pool_cap;        // pool_cap candidates per read of the slice (row = read - read_base)
 	u32* pool_used;                   // per read: candidates appended so far (round 2 continues behind round 1)
 	SeedTask* tasks; u32 task_cap;    // light tasks fill the array from the front, scans with many candidates from the back (swept first: longest jobs first)
 	u32* n_tasks;                     // [0],[1]: ONE 64-bit reservation counter (low word = light scans, high word = heavy scans);
@@ -545,15 +546,15 @@ DEV void fm_forward_queue(const DevIndex& x, const MemOpt& opt, const SeedSplitI
 					else io.pool_used[r] = used;
 				}
 				for (;;) {
-					r = (i64)atomic_add_u32(counter, 1u);
-					if (r >= io.n_reads) break;
+					r = io.read_base + (i64)atomic_add_u32(counter, 1u);
+					if (r >= io.read_base + io.n_reads) break;
 					len = (int)(io.seq_off[r + 1] - io.seq_off[r] - 1);
 					if (len >= opt.min_seed_len && len <= io.smem_cap && (ROUND == 1 || io.pool_used[r] != SEED_POOL_OVERFLOW)) break;
 					if (ROUND == 1) io.pool_used[r] = 0;
 				}
-				if (r >= io.n_reads) { r = -1; st = F_ALLDONE; break; }
+				if (r >= io.read_base + io.n_reads) { r = -1; st = F_ALLDONE; break; }
 				q = io.seq + io.seq_off[r];
-				pool = io.pool + (size_t)r * io.pool_cap;
+				pool = io.pool + (size_t)(r - io.read_base) * io.pool_cap;
 				used = 0; // (round 1's candidates are dead once its sweeps have run)
 				xx = 0; k2 = 0; n1 = ROUND == 1 ? 0 : (int)io.n_intv[r];
 				st = F_NEXT;
@@ -660,7 +661,7 @@ DEV void fm_backward_queue(const DevIndex& x, const MemOpt& opt, const SeedSplit
 					tk = io.tasks[t]; // (scans with many candidates sit at the other end of the array: fm_backward_task_warp)
 					if (io.pool_used[tk.read] != SEED_POOL_OVERFLOW && tk.n_c <= (u32)SEED_HEAVY_CANDS) { // (else the read is redone as a whole: stay idle)
 						q = io.seq + io.seq_off[tk.read];
-						const uint4* src = io.pool + (size_t)tk.read * io.pool_cap + tk.c_off + (tk.n_c - 1);
+						const uint4* src = io.pool + (size_t)((i64)tk.read - io.read_base) * io.pool_cap + tk.c_off + (tk.n_c - 1);
 						for (int a = 0; a < (int)tk.n_c; ++a) CL(a) = src[-a];
 						n_prev = (int)tk.n_c; i = (int)tk.start - 1; have_out = false; last_beg = 0;
 						st = B_ROW;
@@ -730,7 +731,7 @@ DEVNI void fm_backward_task_warp(const DevIndex& x, const MemOpt& opt, const See
 	LANE_DECL;
 	if (io.pool_used[tk.read] == SEED_POOL_OVERFLOW) return; // the read is redone as a whole
 	const u8* q = io.seq + io.seq_off[tk.read];
-	uint4* cl = io.pool + (size_t)tk.read * io.pool_cap + tk.c_off + (tk.n_c - 1); // cl[-a] = candidate a
+	uint4* cl = io.pool + (size_t)((i64)tk.read - io.read_base) * io.pool_cap + tk.c_off + (tk.n_c - 1); // cl[-a] = candidate a
 	int n_prev = (int)tk.n_c; u32 last_beg = 0; bool have_out = false;
 	for (int i = (int)tk.start - 1; i >= -1; --i) {
 		const int c = i < 0 ? -1 : (q[i] < 4 ? (int)q[i] : -1);

@@ -67,6 +67,7 @@ struct BatchParams {
 	int ext_sides;          // the side-task route (extend_thread.cuh thread_extend_sides) is in use: tasks carry keys
 	u32 ext_lo, ext_hi;     // one side launch covers positions [ext_lo, ext_hi) of the order (a class of query lengths)
 	int ext_rw;             // ... with shared-memory rows of ext_rw cells per thread (query lengths < ext_rw)
+	i64 seed_read_base;     // rounds 1/2 of the seeding run over reads [seed_read_base, ...) of the batch (slices: engine_impl.inl)
 	u32* chain_heavy; u32* n_chain_heavy; int chain_heavy_seeds; // reads chained by a warp
 	int chain_listed;       // the list of those reads was written beforehand (body_chain_classify): body_chain only skips them
 	GaTask* ga_tasks; GaRes* ga_res; u32* n_ga_tasks; u32 ga_cap; u32* ga_item0; u32* ga_itemn; // two-pass finalize (galign_thread.cuh)
@@ -149,7 +150,7 @@ DEV void seed_queue(const BatchParams& P, i64 n, u32* counter, i64 tid, const u3
 DEV SeedSplitIO make_seed_split_io(const BatchParams& P, i64 n_reads)
 {
 	SeedSplitIO io;
-	io.seq = P.seq; io.seq_off = P.seq_off; io.n_reads = n_reads;
+	io.seq = P.seq; io.seq_off = P.seq_off; io.n_reads = n_reads; io.read_base = P.seed_read_base;
 	io.pool = P.seed_pool; io.pool_cap = P.seed_pool_cap; io.pool_used = P.seed_pool_used;
 	io.tasks = P.seed_tasks; io.n_tasks = P.n_seed_tasks; io.task_cap = P.seed_task_cap;
 	io.intv = P.intv; io.intv_cap = P.intv_cap; io.n_intv = P.n_intv;

@@ -169,3 +169,15 @@ def test_sim_occurrence_super_blocks(small_genome, monkeypatch, shift):
     monkeypatch.setenv("B200_TEST_OCC_SB", shift)
     b = run_blob(sim_lib(), img, blob, 2)
     assert a == b, first_diff(a, b, blob, True)
+
+
+@pytest.mark.parametrize("slices", ["2", "7"])
+def test_sim_seeding_in_slices(small_genome, monkeypatch, slices):
+    """A batch whose candidate pool would exceed BWA_B200_SEED_POOL_GB is seeded in slices of reads (rounds 1/2 of a
+    slice complete before the next one starts, the pool holds one slice); forced here on a small batch."""
+    g, img = small_genome
+    blob, _ = simdata.make_reads(g, 86, 301, 150, True, repeat_read_frac=0.3, n_rate=0.01, err_rate=0.03)
+    a = run_blob(oracle_lib(), img, blob, 2)
+    monkeypatch.setenv("B200_TEST_SEED_SLICES", slices)
+    b = run_blob(sim_lib(), img, blob, 2)
+    assert a == b, first_diff(a, b, blob, True)
