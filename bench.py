@@ -570,6 +570,9 @@ def main():
                 else:
                     v["gbs"] = round(v["algorithmic_bytes"] / (v["ms"] * 1e6), 1)
                     v["frac_hbm"] = round(v["gbs"] / hbm_peak, 4)
+                    if k_ == "sal":  # the reference walks to a sample every 32 rows, the device keeps one every 4 (BWA_B200_SA_INTV):
+                        v["frac_hbm"] = None  # ~8x fewer steps than the algorithmic count, so this rate is not a bandwidth
+                        v["note"] = "algorithmic bytes are the reference's (SA sample every 32 rows); the device keeps a sample every 4 rows and walks ~8x fewer LF steps"
     # The roofline object describes the dominant STAGE: a stage is one algorithmic step of the path and may be split over
     # several launches (SMEM seeding = forward scans, backward sweeps, round 3: profiles/*_launch_summary.txt).
     roof = None
@@ -583,7 +586,7 @@ def main():
             # the FM-index walks: random 64-byte occurrence-block reads of an index far larger than L2
             roof["achieved"] = stage_work[dom_group]["algorithmic_bytes"] / (dom_ms * 1e6)
             roof["algorithmic_bytes_per_step"] = stage_work[dom_group]["algorithmic_bytes"]
-            roof["note"] = "achieved = 64 B x occurrence-block touches of the SMEM search (oracle counters on the same batch) / summed kernel time of the stage's launches (CUDA events on the context's stream)"
+            roof["note"] = "achieved = 64 B x occurrence-block touches of the SMEM search (oracle counters on the same batch; the reference's 64-byte block per touch -- the device reads a 32-byte sector per touch and a prefix table for the first 11 extensions of every forward scan) / summed kernel time of the stage's launches (CUDA events on the context's stream)"
         elif stage_work and dom_group in ("extend", "rescue_sw", "finalize"):
             cells = stage_work[dom_group]["cells"]
             roof["achieved"] = cells * 8.0 / (dom_ms * 1e6)
