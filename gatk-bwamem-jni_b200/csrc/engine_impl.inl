@@ -87,7 +87,7 @@ struct EngineConfig {
 	// ---- test hooks / tuning aids (B200_TEST_HOOKS=1)
 	bool no_stage_overlap = false, seed_one_launch = false, seed_fused_rounds = false, tiny_seed_pool = false, tiny_seed_tasks = false, seed_no_overlap = false;
 	bool chain_all_warp = false, chain_all_thread = false, chain_no_overlap = false, tiny_scratch = false, all_heavy = false, all_light = false;
-	bool warp_extend = false, ext_wide_cells = false, no_ext_tasks = false, rescue_fallback = false, final_one_pass = false, final_ring = false, tiny_ga_cap = false;
+	bool warp_extend = false, ext_wide_cells = false, no_ext_tasks = false, rescue_fallback = false, final_one_pass = false, final_ring = false, tiny_ga_cap = false, tiny_intv_cap = false;
 	bool ext_legacy = false, ext_no_sort = false, force_long_mode = false, rescue_warp_sw = false, ga_no_sort = false, ext_task_machine = false;
 	int seed_lcap = 0, seed_shared_read = -1, tx_chunk = -1, light_seeds = -1, light_chains = -1, final_heavy_hits = -1, occ_sb_shift = 0, seed_slices = 0;
 	static bool flag(const char* nm) { return getenv(nm) != nullptr; }
@@ -107,7 +107,7 @@ struct EngineConfig {
 		tiny_scratch = flag("B200_TEST_TINY_SCRATCH"); all_heavy = flag("B200_TEST_ALL_HEAVY"); all_light = flag("B200_TEST_ALL_LIGHT");
 		warp_extend = flag("B200_WARP_EXTEND"); ext_wide_cells = flag("B200_EXT_WIDE_CELLS"); no_ext_tasks = flag("B200_NO_EXT_TASKS");
 		rescue_fallback = flag("B200_TEST_RESCUE_FALLBACK"); final_one_pass = flag("B200_FINAL_ONE_PASS"); final_ring = flag("B200_TEST_FINAL_RING");
-		tiny_ga_cap = flag("B200_TEST_TINY_GA_CAP"); ext_legacy = flag("B200_EXT_LEGACY"); ext_no_sort = flag("B200_EXT_NO_SORT"); force_long_mode = flag("B200_TEST_LONG_MODE"); rescue_warp_sw = flag("B200_RESCUE_WARP_SW"); ga_no_sort = flag("B200_GA_NO_SORT"); ext_task_machine = flag("B200_EXT_TASK_MACHINE");
+		tiny_ga_cap = flag("B200_TEST_TINY_GA_CAP"); tiny_intv_cap = flag("B200_TEST_TINY_INTV_CAP"); ext_legacy = flag("B200_EXT_LEGACY"); ext_no_sort = flag("B200_EXT_NO_SORT"); force_long_mode = flag("B200_TEST_LONG_MODE"); rescue_warp_sw = flag("B200_RESCUE_WARP_SW"); ga_no_sort = flag("B200_GA_NO_SORT"); ext_task_machine = flag("B200_EXT_TASK_MACHINE");
 		seed_lcap = num("B200_SEED_LCAP", 0); seed_shared_read = num("B200_SEED_SHARED_READ", -1); tx_chunk = num("B200_TX_CHUNK", -1);
 		light_seeds = num("B200_LIGHT_SEEDS", -1); light_chains = num("B200_LIGHT_CHAINS", -1); final_heavy_hits = num("B200_FINAL_HEAVY_HITS", -1);
 		seed_slices = num("B200_TEST_SEED_SLICES", 0);
@@ -183,6 +183,7 @@ struct Replica {
 struct Batch {
 	Engine* eng = nullptr; Replica* rep = nullptr; RtCtx* rt = nullptr;
 	bool in_use = false; // guarded by Engine::mu
+	int intv_scale = 1;  // interval-list capacity multiplier: doubled when a batch overflowed its lists (Batch::run)
 	HostProf hp;
 	// batch workspace
 	DBuf b_blob, b_seq, b_seqoff, b_intv, b_nintv, b_nseed, b_smem, b_seedoff, b_rbeg, b_S, b_C, b_ord, b_tmp32, b_ck, b_ks, b_srt, b_regtmp,
@@ -638,7 +639,13 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 	// warp-level kernels with rows in global memory, on as many slots as a fixed scratch budget allows.
 	const bool long_mode = max_len > 1000 || cfg.force_long_mode;
 	const int wm_cap = ((max_len + 15) / 16) * 16 + 32;
-	const int intv_cap = max_len < 64 ? 64 : (max_len > 512 ? 512 + (max_len - 512) / 6 : max_len); // SMEMs of a read; long reads: one per ~6 bases at most, or the batch fails with ERR_INTV_OVERFLOW
+	// SMEMs of a read.  A read from a family of many diverged repeat copies has a new SMEM every base or two: up to
+	// len - min_seed_len from round 1 and as many again from a re-seeding scan (185 seen for 150 bases on the 3 Gbp bench
+	// genome), so 2 len + 64; long reads: one per ~6 bases.  A read that still overflows has its list clamped
+	// (kernels.cuh SeedSrc::next), the flag is read right after the seeding stage, and the whole batch is run again with
+	// twice the capacity, which this context then keeps (intv_scale).
+	const int intv_cap0 = cfg.tiny_intv_cap ? 4 : (max_len > 512 ? 512 + (max_len - 512) / 6 : 2 * (max_len < 64 ? 64 : max_len) + 64);
+	const int intv_cap = intv_cap0 * intv_scale;
 	const int L_ = max_len > 0 ? max_len : 1;
 	// traceback of the banded global alignment: n_col <= min(l_query, 2 w + 1) bytes per reference row, w <= max(4 opt.w, dl + 3)
 	const size_t ws_z_cap = (size_t)((L_ < 8 * opt.w + 17 ? L_ : 8 * opt.w + 17) + 4) * (size_t)(L_ + 8 * opt.w + 64);
@@ -742,9 +749,27 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 		}
 	}
 	hp.mark("launch1");
+	if (cfg.debug_stats) { // the longest interval list of the batch (capacity: intv_cap per read)
+		std::vector<uint32_t> ni((size_t)n_reads);
+		rt_d2h(ni.data(), P.n_intv, (size_t)n_reads * 4);
+		size_t am = 0; for (size_t r = 0; r < (size_t)n_reads; ++r) if (ni[r] > ni[am]) am = r;
+		std::vector<uint64_t> so(2); rt_d2h(so.data(), P.seq_off + am, 16);
+		std::string rd((size_t)(so[1] - so[0]), '\0'); rt_d2h(&rd[0], P.seq + so[0], rd.size());
+		for (char& c : rd) c = (unsigned char)c < 4 ? "ACGT"[(int)c] : 'N';
+		fprintf(stderr, "[bwamem-b200] longest interval list: %u of %d (read %zu: %s)\n", ni[am], intv_cap, am, rd.c_str());
+	}
 	uint64_t T = rt_scan_u32(P.n_seed, P.seed_off, n_reads);
 	if (!g_last_cuda_ok()) { last_error = "device error or allocation failure (scan / sort scratch)"; return nullptr; }
 	hp.mark("seed_sync");
+	{ // interval lists that did not fit: again, with twice the room
+		uint32_t e0 = 0;
+		rt_d2h(&e0, P.err, 4);
+		if ((e0 & ERR_INTV_OVERFLOW) && intv_scale < 256) {
+			intv_scale *= 2;
+			if (cfg.debug_stats) fprintf(stderr, "[bwamem-b200] interval lists overflowed %d entries per read: re-running the batch with %d\n", intv_cap, intv_cap0 * intv_scale);
+			return run(opt_in, pes0, out_size, host_output);
+		}
+	}
 	P.n_seed_total = T; last_n_seed = T;
 	{
 		size_t Tn = (size_t)T + 1;

@@ -556,7 +556,7 @@ DEV void fm_forward_queue(const DevIndex& x, const MemOpt& opt, const SeedSplitI
 				q = io.seq + io.seq_off[r];
 				pool = io.pool + (size_t)(r - io.read_base) * io.pool_cap;
 				used = 0; // (round 1's candidates are dead once its sweeps have run)
-				xx = 0; k2 = 0; n1 = ROUND == 1 ? 0 : (int)io.n_intv[r];
+				xx = 0; k2 = 0; n1 = ROUND == 1 ? 0 : (int)(io.n_intv[r] < (u32)io.intv_cap ? io.n_intv[r] : (u32)io.intv_cap);
 				st = F_NEXT;
 				break;
 			case F_NEXT:

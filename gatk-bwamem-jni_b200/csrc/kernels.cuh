@@ -116,6 +116,7 @@ struct SeedSrc {
 		}
 		seq = P.seq + P.seq_off[r];
 		o.v = P.intv + (size_t)r * P.intv_cap; o.n = PHASES == 2 ? (int)P.n_intv[r] : 0; o.cap = P.intv_cap; o.overflow = false;
+		if (o.n > o.cap) { o.n = o.cap; o.overflow = true; } // (the sweeps count what they could not store: the batch is run again with more room)
 		return true;
 	}
 	DEVM void finish(const IntvOut& o)

@@ -181,3 +181,14 @@ def test_sim_seeding_in_slices(small_genome, monkeypatch, slices):
     monkeypatch.setenv("B200_TEST_SEED_SLICES", slices)
     b = run_blob(sim_lib(), img, blob, 2)
     assert a == b, first_diff(a, b, blob, True)
+
+
+def test_sim_interval_lists_regrown(small_genome, monkeypatch):
+    """A read whose SMEM list outgrows its slice (reads from families of diverged repeats: a new SMEM every base or two) has
+    the list clamped, and the batch is run again with twice the room until every list fits; forced with 4 entries per read."""
+    g, img = small_genome
+    blob, _ = simdata.make_reads(g, 87, 300, 150, True, repeat_read_frac=0.3, n_rate=0.01, err_rate=0.03)
+    a = run_blob(oracle_lib(), img, blob, 2)
+    monkeypatch.setenv("B200_TEST_TINY_INTV_CAP", "1")
+    b = run_blob(sim_lib(), img, blob, 2)
+    assert a == b, first_diff(a, b, blob, True)
