@@ -87,7 +87,7 @@ struct EngineConfig {
 	// ---- test hooks / tuning aids (B200_TEST_HOOKS=1)
 	bool no_stage_overlap = false, seed_one_launch = false, seed_fused_rounds = false, tiny_seed_pool = false, tiny_seed_tasks = false, seed_no_overlap = false;
 	bool chain_all_warp = false, chain_all_thread = false, chain_no_overlap = false, tiny_scratch = false, all_heavy = false, all_light = false;
-	bool warp_extend = false, ext_wide_cells = false, no_ext_tasks = false, rescue_fallback = false, final_one_pass = false, final_ring = false, tiny_ga_cap = false, tiny_intv_cap = false;
+	bool warp_extend = false, ext_wide_cells = false, no_ext_tasks = false, rescue_fallback = false, final_one_pass = false, final_ring = false, tiny_ga_cap = false, tiny_intv_cap = false, tiny_warp_scratch = false;
 	bool ext_legacy = false, ext_no_sort = false, force_long_mode = false, rescue_warp_sw = false, ga_no_sort = false, ext_task_machine = false;
 	int seed_lcap = 0, seed_shared_read = -1, tx_chunk = -1, light_seeds = -1, light_chains = -1, final_heavy_hits = -1, occ_sb_shift = 0, seed_slices = 0;
 	static bool flag(const char* nm) { return getenv(nm) != nullptr; }
@@ -107,7 +107,7 @@ struct EngineConfig {
 		tiny_scratch = flag("B200_TEST_TINY_SCRATCH"); all_heavy = flag("B200_TEST_ALL_HEAVY"); all_light = flag("B200_TEST_ALL_LIGHT");
 		warp_extend = flag("B200_WARP_EXTEND"); ext_wide_cells = flag("B200_EXT_WIDE_CELLS"); no_ext_tasks = flag("B200_NO_EXT_TASKS");
 		rescue_fallback = flag("B200_TEST_RESCUE_FALLBACK"); final_one_pass = flag("B200_FINAL_ONE_PASS"); final_ring = flag("B200_TEST_FINAL_RING");
-		tiny_ga_cap = flag("B200_TEST_TINY_GA_CAP"); tiny_intv_cap = flag("B200_TEST_TINY_INTV_CAP"); ext_legacy = flag("B200_EXT_LEGACY"); ext_no_sort = flag("B200_EXT_NO_SORT"); force_long_mode = flag("B200_TEST_LONG_MODE"); rescue_warp_sw = flag("B200_RESCUE_WARP_SW"); ga_no_sort = flag("B200_GA_NO_SORT"); ext_task_machine = flag("B200_EXT_TASK_MACHINE");
+		tiny_ga_cap = flag("B200_TEST_TINY_GA_CAP"); tiny_intv_cap = flag("B200_TEST_TINY_INTV_CAP"); tiny_warp_scratch = flag("B200_TEST_TINY_WARP_SCRATCH"); ext_legacy = flag("B200_EXT_LEGACY"); ext_no_sort = flag("B200_EXT_NO_SORT"); force_long_mode = flag("B200_TEST_LONG_MODE"); rescue_warp_sw = flag("B200_RESCUE_WARP_SW"); ga_no_sort = flag("B200_GA_NO_SORT"); ext_task_machine = flag("B200_EXT_TASK_MACHINE");
 		seed_lcap = num("B200_SEED_LCAP", 0); seed_shared_read = num("B200_SEED_SHARED_READ", -1); tx_chunk = num("B200_TX_CHUNK", -1);
 		light_seeds = num("B200_LIGHT_SEEDS", -1); light_chains = num("B200_LIGHT_CHAINS", -1); final_heavy_hits = num("B200_FINAL_HEAVY_HITS", -1);
 		seed_slices = num("B200_TEST_SEED_SLICES", 0);
@@ -183,6 +183,7 @@ struct Replica {
 struct Batch {
 	Engine* eng = nullptr; Replica* rep = nullptr; RtCtx* rt = nullptr;
 	bool in_use = false; // guarded by Engine::mu
+	int scratch_scale = 1; // multiplier of the warp-level scratch capacities: doubled when an item of a batch outgrew one (Batch::run)
 	int intv_scale = 1;  // interval-list capacity multiplier: doubled when a batch overflowed its lists (Batch::run)
 	HostProf hp;
 	// batch workspace
@@ -648,8 +649,14 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 	const int intv_cap = intv_cap0 * intv_scale;
 	const int L_ = max_len > 0 ? max_len : 1;
 	// traceback of the banded global alignment: n_col <= min(l_query, 2 w + 1) bytes per reference row, w <= max(4 opt.w, dl + 3)
-	const size_t ws_z_cap = (size_t)((L_ < 8 * opt.w + 17 ? L_ : 8 * opt.w + 17) + 4) * (size_t)(L_ + 8 * opt.w + 64);
-	const int ws_cigar_cap = 3 * L_ + 4 * opt.w + 64, ws_md_cap = 4 * L_ + 8 * opt.w + 128, ws_xa_cap = 8192 + (long_mode ? 8 * L_ : 0), ws_rt_cap = 1024;
+	// These capacities of the warp-level scratch are bounds for ordinary data, not proofs (an XA string of 200 ALT hits on
+	// contigs with long names, a CIGAR of a pathological alignment).  An item that outgrows one raises a flag and is cut
+	// short; the flags are read at the end of the batch and the WHOLE batch is run again with every one of them doubled
+	// (scratch_scale, kept by the context) instead of failing the call.  (B200_TEST_TINY_WARP_SCRATCH starts at 1/64.)
+	const int sdiv = cfg.tiny_warp_scratch ? 64 : 1;
+	const size_t ws_z_cap = std::max<size_t>(64, (size_t)((L_ < 8 * opt.w + 17 ? L_ : 8 * opt.w + 17) + 4) * (size_t)(L_ + 8 * opt.w + 64) * (size_t)scratch_scale / sdiv);
+	const int ws_cigar_cap = std::max(4, (3 * L_ + 4 * opt.w + 64) * scratch_scale / sdiv), ws_md_cap = std::max(8, (4 * L_ + 8 * opt.w + 128) * scratch_scale / sdiv),
+	          ws_xa_cap = std::max(64, (8192 + (long_mode ? 8 * L_ : 0)) * scratch_scale / sdiv), ws_rt_cap = 1024;
 	rt_set_slot_caps(0, 0);
 	if (long_mode) {
 		const size_t per_thread = (size_t)(max_len + 1) * sizeof(Intv) + thread_scratch_bytes(wm_cap, 64, 48, 192, 1024);
@@ -952,7 +959,7 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 		P.pair_tab = b_pairtab.as<double>();
 		int max_win = 0;
 		for (int d = 0; d < 4; ++d) { P.pair_tab_off[d] = off[d]; if (!P.pes[d].failed) { int wd = P.pes[d].high - P.pes[d].low + 1; if (wd > max_win) max_win = wd; } }
-		P.ws_brow_cap = max_win + max_len + 64;
+		P.ws_brow_cap = std::max(16, (max_win + max_len + 64) * scratch_scale / sdiv);
 		if (!b_wsbrow.ensure((size_t)wslots * P.ws_brow_cap * 8)) { last_error = "device allocation failed"; return nullptr; }
 		P.ws_brow = b_wsbrow.as<u64>();
 	}
@@ -964,7 +971,7 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 	{
 		size_t Rn = (size_t)R + 2;
 		ok = b_regs.ensure(Rn * sizeof(Reg)) && b_snap.ensure(Rn * sizeof(Reg)) && b_ztmp.ensure(Rn * 4) && b_pairv.ensure(Rn * sizeof(Pair64)) && b_recs.ensure(Rn * sizeof(AlnRec));
-		P.var_cap = (u32)std::min<uint64_t>((uint64_t)0xfffffff0u, (uint64_t)R * 24 + (uint64_t)n_reads * 8 + 4096 + (long_mode ? 2 * blob_len : 0)); // CIGAR + MD words of the records
+		P.var_cap = (u32)std::min<uint64_t>((uint64_t)0xfffffff0u, ((uint64_t)R * 24 + (uint64_t)n_reads * 8 + 4096 + (long_mode ? 2 * blob_len : 0)) * (uint64_t)scratch_scale / (uint64_t)sdiv); // CIGAR + MD + XA words of the records
 		ok = ok && b_var.ensure((size_t)P.var_cap * 4);
 		if (!ok) { last_error = "device allocation failed (region pools)"; return nullptr; }
 	}
@@ -1088,6 +1095,14 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 	if (cfg.debug_stats) fprintf(stderr, "[bwamem-b200] workspace of this context: %.2f GB\n", (double)workspace_bytes() / 1e9);
 	if (cfg.debug_stats) fprintf(stderr, "[bwamem-b200] reads %u: finalize redo %u, alignment tasks %u, extension-heavy reads %u / tasks %u, chain-heavy %u, rescue warp-replayed %u / fallback %u, seed one-machine reads %u\n",
 	                                        n_reads, misc[5], misc[23], misc[6], misc[21], misc[22], misc[20], misc[7], misc[28]);
+	{
+		const uint32_t scratch_flags = ERR_Z_OVERFLOW | ERR_CIGAR_OVERFLOW | ERR_MD_OVERFLOW | ERR_XA_OVERFLOW | ERR_BROW_OVERFLOW | ERR_VAR_OVERFLOW;
+		if (misc[0] && !(misc[0] & ~scratch_flags) && scratch_scale < 64) { // an item outgrew the warp-level scratch: once more, with twice the room
+			scratch_scale *= 2;
+			if (cfg.debug_stats) fprintf(stderr, "[bwamem-b200] warp-level scratch overflowed (flags 0x%x): re-running the batch with %dx the capacities\n", misc[0], scratch_scale);
+			return run(opt_in, pes0, out_size, host_output);
+		}
+	}
 	if (misc[0]) {
 		char buf[128]; snprintf(buf, sizeof buf, "device-side capacity/limit error flags 0x%x", misc[0]);
 		last_error = buf;

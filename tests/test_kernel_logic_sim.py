@@ -192,3 +192,18 @@ def test_sim_interval_lists_regrown(small_genome, monkeypatch):
     monkeypatch.setenv("B200_TEST_TINY_INTV_CAP", "1")
     b = run_blob(sim_lib(), img, blob, 2)
     assert a == b, first_diff(a, b, blob, True)
+
+
+@pytest.mark.parametrize("extra", [None, "B200_TEST_ALL_HEAVY"])
+def test_sim_warp_scratch_regrown(small_genome, monkeypatch, extra):
+    """An item that outgrows a capacity of the warp-level scratch (traceback, CIGAR, MD, XA, row-maxima list, the records'
+    payload pool) raises a flag; the batch is then run again with every capacity doubled instead of failing the call.
+    Forced by starting at 1/64 of the capacities; with every read on the warp-level kernels as well."""
+    g, img = small_genome
+    blob, _ = simdata.make_reads(g, 88, 300, 150, True, repeat_read_frac=0.3, n_rate=0.01, err_rate=0.03)
+    a = run_blob(oracle_lib(), img, blob, 2)
+    monkeypatch.setenv("B200_TEST_TINY_WARP_SCRATCH", "1")
+    if extra:
+        monkeypatch.setenv(extra, "1")
+    b = run_blob(sim_lib(), img, blob, 2)
+    assert a == b, first_diff(a, b, blob, True)

@@ -132,9 +132,9 @@ def test_engine_matches_oracle_mid(mid_genome, paired):
     assert a == b, first_diff(a, b, blob, paired)
 
 
-@pytest.mark.parametrize("env", [None, "B200_TEST_RESCUE_FALLBACK", "B200_TEST_TINY_SCRATCH", "B200_TEST_ALL_LIGHT", "B200_TEST_ALL_HEAVY", "B200_WARP_EXTEND", "B200_NO_EXT_TASKS", "B200_TEST_CHAIN_ALL_WARP", "B200_TEST_CHAIN_ALL_THREAD", "B200_FINAL_ONE_PASS", "B200_SEED_ONE_LAUNCH", "B200_SEED_FUSED_ROUNDS", "B200_TEST_TINY_SEED_POOL", "B200_TX_CHUNK=1", "B200_TX_CHUNK=0", "B200_EXT_WIDE_CELLS", "B200_SEED_NO_OVERLAP", "B200_CHAIN_NO_OVERLAP", "B200_TEST_FINAL_RING", "B200_TEST_TINY_GA_CAP", "B200_TEST_TINY_SEED_TASKS", "B200_EXT_LEGACY", "B200_EXT_NO_SORT", "B200_TEST_LONG_MODE", "B200_RESCUE_WARP_SW", "B200_EXT_TASK_MACHINE", "B200_GA_NO_SORT", "BWA_B200_KMER=6", "BWA_B200_KMER=0", "B200_TEST_OCC_SB=3", "B200_TEST_SEED_SLICES=3", "B200_TEST_TINY_INTV_CAP"],
+@pytest.mark.parametrize("env", [None, "B200_TEST_RESCUE_FALLBACK", "B200_TEST_TINY_SCRATCH", "B200_TEST_ALL_LIGHT", "B200_TEST_ALL_HEAVY", "B200_WARP_EXTEND", "B200_NO_EXT_TASKS", "B200_TEST_CHAIN_ALL_WARP", "B200_TEST_CHAIN_ALL_THREAD", "B200_FINAL_ONE_PASS", "B200_SEED_ONE_LAUNCH", "B200_SEED_FUSED_ROUNDS", "B200_TEST_TINY_SEED_POOL", "B200_TX_CHUNK=1", "B200_TX_CHUNK=0", "B200_EXT_WIDE_CELLS", "B200_SEED_NO_OVERLAP", "B200_CHAIN_NO_OVERLAP", "B200_TEST_FINAL_RING", "B200_TEST_TINY_GA_CAP", "B200_TEST_TINY_SEED_TASKS", "B200_EXT_LEGACY", "B200_EXT_NO_SORT", "B200_TEST_LONG_MODE", "B200_RESCUE_WARP_SW", "B200_EXT_TASK_MACHINE", "B200_GA_NO_SORT", "BWA_B200_KMER=6", "BWA_B200_KMER=0", "B200_TEST_OCC_SB=3", "B200_TEST_SEED_SLICES=3", "B200_TEST_TINY_INTV_CAP", "B200_TEST_TINY_WARP_SCRATCH"],
                          ids=["default", "rescue_fallback", "tiny_scratch", "extend_all_thread", "extend_all_tasks", "extend_all_warp", "extend_heavy_by_warp",
-                              "chain_all_warp", "chain_all_thread", "final_one_pass", "seed_one_launch", "seed_fused_rounds", "seed_pool_overflow", "extend_rows_cell_by_cell", "extend_whole_rows", "extend_wide_cells", "seed_no_stream_overlap", "chain_no_stream_overlap", "final_passes_with_ring_smem", "alignment_task_pool_overflow", "seed_task_list_overflow", "extend_read_level_machine", "extend_tasks_unsorted", "long_read_mode_forced", "rescue_alignments_by_warps", "extend_tasks_by_lane_machine", "alignment_tasks_unsorted", "prefix_tables_of_6_mers", "no_prefix_tables", "occ_super_blocks", "seeding_in_slices", "interval_lists_regrown"])
+                              "chain_all_warp", "chain_all_thread", "final_one_pass", "seed_one_launch", "seed_fused_rounds", "seed_pool_overflow", "extend_rows_cell_by_cell", "extend_whole_rows", "extend_wide_cells", "seed_no_stream_overlap", "chain_no_stream_overlap", "final_passes_with_ring_smem", "alignment_task_pool_overflow", "seed_task_list_overflow", "extend_read_level_machine", "extend_tasks_unsorted", "long_read_mode_forced", "rescue_alignments_by_warps", "extend_tasks_by_lane_machine", "alignment_tasks_unsorted", "prefix_tables_of_6_mers", "no_prefix_tables", "occ_super_blocks", "seeding_in_slices", "interval_lists_regrown", "warp_scratch_regrown"])
 def test_repeat_heavy_pairs_and_forced_slow_paths(small_genome, monkeypatch, env):
     """Chains of several rescuing hits per read (repeat-derived reads); the same batch with every rescuing read forced
     onto the round-by-round rescue kernels, with thread-level scratch so small that items are handed to warps, and with
