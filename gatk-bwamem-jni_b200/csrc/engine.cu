@@ -11,6 +11,7 @@
 #include <cstring>
 #include <unistd.h>
 #include <atomic>
+#include <mutex>
 #include <string>
 #include <vector>
 #include <cuda_runtime.h>
@@ -123,8 +124,6 @@ static int64_t rt_warp_blocks() { const int64_t d = (int64_t)rt_sm_count() * WAR
 static int64_t rt_thread_slots() { return rt_thread_blocks() * THREADS_PER_BLOCK; }
 static int64_t rt_warp_slots() { return rt_warp_blocks() * WARPS_PER_BLOCK; }
 static void rt_set_slot_caps(int64_t thread_blocks, int64_t warp_blocks) { t_rt->thread_block_cap = (int)thread_blocks; t_rt->warp_block_cap = (int)warp_blocks; }
-static int64_t rt_default_thread_slots() { return (int64_t)rt_sm_count() * SEED_BLOCKS_PER_SM * THREADS_PER_BLOCK; }
-static int64_t rt_default_warp_slots() { return (int64_t)rt_sm_count() * WARP_BLOCKS_PER_SM * WARPS_PER_BLOCK; }
 
 #ifdef B200_DEBUG_CKPT
 __device__ volatile unsigned* g_ckpt = nullptr;
@@ -135,6 +134,12 @@ static unsigned* g_ckpt_host = nullptr;
 // exclusive scan of u32 counts into u64 offsets (out[n] = total); returns the total
 struct U32ToU64 { __host__ __device__ u64 operator()(const u32& v) const { return (u64)v; } };
 __global__ void k_scan_close(const u32* in, u64* out, u64 n) { out[n] = n ? out[n - 1] + in[n - 1] : 0; }
+// an error left behind by an earlier call of this thread (CUB returns whatever it finds in that slot as its own)
+static void rt_report_pending(const char* where)
+{
+	const cudaError_t le = cudaGetLastError();
+	if (le != cudaSuccess) { g_last_cuda = le; fprintf(stderr, "[bwamem-b200] pending CUDA error %s: %s\n", where, cudaGetErrorString(le)); }
+}
 static bool rt_scratch(size_t need)
 {
 	if (need <= t_rt->scan_tmp_bytes) return true;
@@ -146,6 +151,7 @@ static bool rt_scratch(size_t need)
 }
 static uint64_t rt_scan_u32(const uint32_t* in, uint64_t* out, uint64_t n)
 {
+	rt_report_pending("before a scan / sort");
 	if (n) {
 		cub::TransformInputIterator<u64, U32ToU64, const u32*> it(in, U32ToU64());
 		size_t need = 0;
@@ -161,6 +167,7 @@ static uint64_t rt_scan_u32(const uint32_t* in, uint64_t* out, uint64_t n)
 
 static void rt_sort_u64(const uint64_t* in, uint64_t* out, uint64_t n)
 {
+	rt_report_pending("before a scan / sort");
 	if (!n) return;
 	size_t need = 0;
 	cu_ok(cub::DeviceRadixSort::SortKeys(nullptr, need, in, out, (int64_t)n, 0, 64, rt_stream()), "sort");
@@ -187,6 +194,7 @@ static void rt_lower_bounds_u32(const uint32_t* keys, uint64_t n, const uint32_t
 // order u32 payloads by u32 keys (stable); used to bucket work items so that the lanes of a warp get similar ones
 static void rt_sort_pairs_u32(const uint32_t* kin, uint32_t* kout, const uint32_t* vin, uint32_t* vout, uint64_t n, int end_bit)
 {
+	rt_report_pending("before a scan / sort");
 	if (!n) return;
 	size_t need = 0;
 	cu_ok(cub::DeviceRadixSort::SortPairs(nullptr, need, kin, kout, vin, vout, (int64_t)n, 0, end_bit, rt_stream()), "sort pairs");
@@ -331,6 +339,10 @@ static void rt_timer_begin()
 static void rt_mark(const char* nm)
 {
 	RtCtx* c = t_rt;
+	{ // a launch that was refused (configuration, resources) leaves its error behind: catch it here, under the stage's name
+		const cudaError_t le = cudaGetLastError();
+		if (le != cudaSuccess) { g_last_cuda = le; fprintf(stderr, "[bwamem-b200] CUDA error at the launch of %s: %s\n", nm, cudaGetErrorString(le)); }
+	}
 	if (c->override_) return; // a kernel on the auxiliary stream: its time is inside the stages of the main stream it overlaps
 	if (c->n_marks < RtCtx::MAXS) { c->name[c->n_marks] = nm; ++c->n_marks; cudaEventRecord(c->ev[c->n_marks], rt_stream()); }
 	if (c->trace) {
@@ -350,8 +362,22 @@ static void rt_mark(const char* nm)
 static void rt_join_aux(const char* nm) { cu_ok(cudaStreamWaitEvent(rt_stream(), t_rt->ev_join, 0), "join"); rt_mark(nm); }
 static int rt_launches() { return t_rt ? t_rt->launches : 0; }
 // opt-in dynamic shared memory is a per-device function attribute: remembered per launch site and device
-#define RT_SET_SMEM(kern, bytes) do { static std::atomic<size_t> set_[RT_MAX_DEV]; const int d_ = t_rt->dev & (RT_MAX_DEV - 1); \
-	if ((bytes) > set_[d_].load(std::memory_order_relaxed)) { cu_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)), "cudaFuncSetAttribute"); set_[d_].store((bytes), std::memory_order_relaxed); } } while (0)
+// Opt-in to more than 48 KB of dynamic shared memory: per KERNEL and device, only ever raised.  (Round 2 kept this state per
+// launch SITE: a kernel launched from two sites had its attribute LOWERED by the second site's first, smaller request, and
+// the first site's next launch was refused with "invalid argument" -- found by tests/fuzz_sim.py on batches of different
+// read lengths through one process.  The refused launch left its error unread; rt_mark now reads it.)
+template <auto Kern>
+static void rt_set_smem(size_t bytes, int dev)
+{
+	static std::atomic<size_t> cur[RT_MAX_DEV];
+	static std::mutex mu;
+	const int d = dev & (RT_MAX_DEV - 1);
+	if (bytes <= cur[d].load(std::memory_order_acquire)) return;
+	std::lock_guard<std::mutex> g(mu);
+	if (bytes <= cur[d].load(std::memory_order_relaxed)) return;
+	if (cu_ok(cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes), "cudaFuncSetAttribute")) cur[d].store(bytes, std::memory_order_release);
+}
+#define RT_SET_SMEM(kern, bytes) rt_set_smem<kern>((size_t)(bytes), t_rt->dev)
 
 #define RT_THREADS(body, P, n) do { i64 n_ = (i64)(n); if (n_ > 0) { \
 	i64 nb_ = (n_ + THREADS_PER_BLOCK - 1) / THREADS_PER_BLOCK; i64 cap_ = (i64)rt_sm_count() * 16; if (nb_ > cap_) nb_ = cap_; \

@@ -261,7 +261,6 @@ DEV void body_flt_gen(const BatchParams& P, i64 r)
 	const int l_query = (int)(P.seq_off[r + 1] - P.seq_off[r] - 1);
 	int min_hsp;
 	if (l_query < 1 || P.n_ck[r] == 0 || !flt_applies(P.x, P.opt, l_query, &min_hsp, P.err)) return;
-	const u64 t0 = P.seed_off[r];
 	const u32 nks = P.n_ks[r];
 	if (!nks) return;
 	const u32 base = atomic_add_u32(P.n_flt_tasks, nks);

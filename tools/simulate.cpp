@@ -180,6 +180,7 @@ int64_t sim_reads(uint64_t seed, const char* genome, int n_contigs, const int64_
 		r1.assign(frag, 0, (size_t)read_len);
 		if (chimeric_frac > 0 && r.uni() < chimeric_frac) { // splice a second locus behind a breakpoint
 			int bp = 30 + (int)r.below((uint64_t)std::max(1, read_len - 60));
+			if (bp >= read_len) bp = read_len / 2; // (reads shorter than 60 bases)
 			int64_t s2 = pick_start(read_len + 64);
 			fragment(s2, read_len - bp, seg2);
 			if (r.next() & 1) { revcomp(seg2, tmp); seg2.swap(tmp); }
