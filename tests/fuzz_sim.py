@@ -20,7 +20,8 @@ which = sys.argv[3] if len(sys.argv) > 3 else 'sim'
 rng = random.Random(seed0)
 genomes = [common.synth_image("g200k", 7, [120000, 60000, 20000], repeat_frac=0.08, tandem_frac=0.01, n_segdup=3),
            common.synth_image("g30k_rep", 11, [20000, 8000, 2000], repeat_frac=0.3, tandem_frac=0.05, n_segdup=4),
-           common.synth_image("g3k", 13, [3000], repeat_frac=0.1, tandem_frac=0.02, n_segdup=1)]
+           common.synth_image("g3k", 13, [3000], repeat_frac=0.1, tandem_frac=0.02, n_segdup=1),
+           common.alt_contig_image()]
 t0 = time.time(); it = 0; bad = 0
 while time.time() - t0 < tmax:
     it += 1
@@ -60,9 +61,13 @@ while time.time() - t0 < tmax:
         for k, v in opts.items():
             getattr(al, "set" + k)(v)
     if os.environ.get('FUZZ_VERBOSE'): print('CFG', it, dict(rl=rl, n=n, paired=paired, kw=kw, opts=opts_dbg, flag=hex(flag), img=os.path.basename(img)), flush=True)
+    stats = None  # pestat: inferred per call, declared failed, or given (BwaMemAligner.java:178-190)
+    if paired and rng.random() < 0.25:
+        stats = bwa.BwaMemPairEndStats.DO_NOT_INFER if rng.random() < 0.3 else bwa.BwaMemPairEndStats.of(rng.choice([200.0, 400.0, 800.0]), rng.choice([10.0, 50.0, 150.0]), rng.choice([1, 100]), rng.choice([600, 1200, 5000]))
+        opts_dbg['stats'] = str(stats)
     try:
-        a = run_blob(oracle_lib(), img, blob, flag, None, setup)
-        b = run_blob(engine_lib() if which == 'engine' else sim_lib(), img, blob, flag, None, setup)
+        a = run_blob(oracle_lib(), img, blob, flag, stats, setup)
+        b = run_blob(engine_lib() if which == 'engine' else sim_lib(), img, blob, flag, stats, setup)
     except Exception as e:
         print("EXC", it, e, dict(rl=rl, n=n, paired=paired, kw=kw, opts=opts_dbg, flag=hex(flag), img=os.path.basename(img))); bad += 1; continue
     if a != b:
