@@ -437,7 +437,7 @@ DEV void body_rescue_fb_restore(const BatchParams& P, i64 i)
 	const i64 r = (i64)P.multi[i], m = r ^ 1;
 	const Reg* s = P.regs_tmp + P.seed_off[m]; Reg* d = P.regs + P.reg_off[m];
 	const int n = (int)P.n_reg0[m];
-	for (int k = 0; k < n; ++k) d[k] = s[k];
+	for (int k = 0; k < n; ++k) { Reg t = s[k]; if (t.rid >= 0 && P.x.ctg_alt[t.rid]) t.is_alt = 1; d[k] = t; } // (as body_compact: the temporary list is untagged)
 	P.n_reg[m] = (u32)n;
 }
 // the round-by-round kernels visit only the queued reads (compact list)

@@ -207,3 +207,15 @@ def test_sim_warp_scratch_regrown(small_genome, monkeypatch, extra):
         monkeypatch.setenv(extra, "1")
     b = run_blob(sim_lib(), img, blob, 2)
     assert a == b, first_diff(a, b, blob, True)
+
+
+def test_sim_alt_contigs_round_by_round_rescue(monkeypatch):
+    """ALT contigs with every rescuing read on the round-by-round rescue kernels: those restore the mate's hit list from
+    the temporary (untagged) regions and have to tag the hits on ALT contigs again (found by tests/fuzz_sim.py)."""
+    g, img = alt_contig_image()
+    monkeypatch.setenv("B200_TEST_RESCUE_FALLBACK", "1")
+    for seed in (5005, 5011):
+        blob, _ = simdata.make_reads(g, seed, 40, 50, True, err_rate=0.05, n_rate=0.1, chimeric_frac=0.2, mut_rate=0.02, ins_mean=400, ins_std=10)
+        a = run_blob(oracle_lib(), img, blob, 2)
+        b = run_blob(sim_lib(), img, blob, 2)
+        assert a == b, first_diff(a, b, blob, True)

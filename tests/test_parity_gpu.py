@@ -342,3 +342,14 @@ def test_alt_contigs(paired, flag):
     alt_ids = {i for i, nm in enumerate(names.getReferenceContigNames()) if nm.startswith("alt")}
     names.close()
     assert any(al.refId in alt_ids for alns in recs for al in alns), "no record on an ALT contig: the case is not exercised"
+
+
+def test_alt_contigs_round_by_round_rescue(monkeypatch):
+    """ALT contigs with every rescuing read forced onto the round-by-round rescue kernels (which restore the mate's hits
+    from the untagged temporary regions and tag them again)."""
+    g, img = alt_contig_image()
+    monkeypatch.setenv("B200_TEST_RESCUE_FALLBACK", "1")
+    blob, _ = simdata.make_reads(g, 52, 3000, 100, True, err_rate=0.03, mut_rate=0.02, chimeric_frac=0.1)
+    a = run_blob(oracle_lib(), img, blob, 2)
+    b = run_blob(engine_lib(), img, blob, 2)
+    assert a == b, first_diff(a, b, blob, True)
