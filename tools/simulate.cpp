@@ -145,7 +145,9 @@ int64_t sim_reads(uint64_t seed, const char* genome, int n_contigs, const int64_
 		while ((int64_t)frag.size() < flen) frag.push_back(kBase[r.below(4)]); // ran off the contig end
 		frag.resize((size_t)flen);
 	};
+	int64_t longest = 0; for (int i = 0; i < n_contigs; ++i) longest = std::max<int64_t>(longest, lens[i]);
 	auto pick_start = [&](int64_t span) -> int64_t {
+		if (span > longest) span = longest; // (a fragment longer than every contig: it runs off the end and is padded)
 		for (;;) {
 			int64_t s;
 			if (n_rep > 0 && rep_iv && r.uni() < repeat_read_frac) {
