@@ -1092,6 +1092,7 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 	rt_d2h(misc, b_misc.p, sizeof(misc));
 	memcpy(&last_counters, misc + 8, sizeof(Counters));
 	n_launches = rt_launches();
+	if (!g_last_cuda_ok()) { last_error = "a CUDA call of this batch failed (see stderr for the stage)"; return nullptr; } // (refused launches included: rt_mark)
 	if (cfg.debug_stats) fprintf(stderr, "[bwamem-b200] workspace of this context: %.2f GB\n", (double)workspace_bytes() / 1e9);
 	if (cfg.debug_stats) fprintf(stderr, "[bwamem-b200] reads %u: finalize redo %u, alignment tasks %u, extension-heavy reads %u / tasks %u, chain-heavy %u, rescue warp-replayed %u / fallback %u, seed one-machine reads %u\n",
 	                                        n_reads, misc[5], misc[23], misc[6], misc[21], misc[22], misc[20], misc[7], misc[28]);
