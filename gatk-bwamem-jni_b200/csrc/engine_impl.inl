@@ -771,7 +771,7 @@ inline void* Batch::run(const MemOpt* opt_in, const PeStat* pes0, size_t* out_si
 	{ // interval lists that did not fit: again, with twice the room
 		uint32_t e0 = 0;
 		rt_d2h(&e0, P.err, 4);
-		if ((e0 & ERR_INTV_OVERFLOW) && intv_scale < 256) {
+		if ((e0 & ERR_INTV_OVERFLOW) && intv_scale < 65536) {
 			intv_scale *= 2;
 			if (cfg.debug_stats) fprintf(stderr, "[bwamem-b200] interval lists overflowed %d entries per read: re-running the batch with %d\n", intv_cap, intv_cap0 * intv_scale);
 			return run(opt_in, pes0, out_size, host_output);
