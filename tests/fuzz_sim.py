@@ -37,6 +37,20 @@ while time.time() - t0 < tmax:
               chimeric_frac=rng.choice([0, 0, 0.2]), mut_rate=rng.choice([0.001, 0.02]), indel_frac=rng.choice([0.15, 0.5]))
     if paired: kw.update(ins_mean=rng.choice([200, 400, 800]) + (rl if rl > 301 else 0), ins_std=rng.choice([10, 50, 150]))
     blob, _ = simdata.make_reads(g, rng.randrange(1 << 30), n, rl, paired, **kw)
+    if rng.random() < 0.15 and rl <= 301:  # a ragged batch: units of a second length (down to the empty read) spliced in
+        import struct
+        rl2 = rng.choice([0, 1, 18, 19, 33, 120, 251])
+        units = [simdata.split_blob(bytes(blob))[k:k + (2 if paired else 1)] for k in range(0, n * (2 if paired else 1), 2 if paired else 1)]
+        if rl2 >= 18:
+            blob2, _ = simdata.make_reads(g, rng.randrange(1 << 30), max(1, n // 3), rl2, paired, **kw)
+            r2 = simdata.split_blob(bytes(blob2))
+            units += [r2[k:k + (2 if paired else 1)] for k in range(0, len(r2), 2 if paired else 1)]
+        else:
+            units += [[b'ACGTN'[:rl2]] * (2 if paired else 1) for _ in range(3)]
+        rng.shuffle(units)
+        reads = [r for u in units for r in u]
+        blob = bytearray(struct.pack('<I', len(reads)) + b''.join(r + b'\0' for r in reads))
+        kw = dict(kw, ragged=rl2)
     opts = {}
     if rng.random() < 0.7:
         for name, choices in [("MinSeedLengthOption", [10, 15, 19, 25]), ("BandwidthOption", [5, 30, 100, 200]), ("ZDropOption", [10, 100, 300]),
