@@ -2,7 +2,7 @@
 """Randomised parity sweep, CPU only: the kernel sources compiled for the host (tests/cudasim) against the oracle over
 random read shapes (20-301 bases, single / paired, error, N, repeat and chimeric rates), random option values and flags
 of the Java API, and random subsets of the forced fall-back paths (B200_TEST_* hooks), on three small genomes.
-usage: python tests/fuzz_sim.py [seed] [seconds] [sim|engine] [fraction of long-query calls]   -- prints every mismatch and a summary; exit status 1 on any.
+usage: python tests/fuzz_sim.py [seed] [seconds] [sim|engine] [fraction of long-query calls] [fraction of ragged batches]   -- prints every mismatch and a summary; exit status 1 on any.
 `engine` runs the same sweep through the CUDA library on a B200 (tests/test_fuzz_sim.py::test_fuzz_slice_gpu).
 (tests/test_fuzz_sim.py runs a short fixed-seed slice of it in the CPU suite.)"""
 import os
@@ -18,6 +18,7 @@ seed0 = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 tmax = float(sys.argv[2]) if len(sys.argv) > 2 else 300
 which = sys.argv[3] if len(sys.argv) > 3 else 'sim'
 LONG_FRAC = float(sys.argv[4]) if len(sys.argv) > 4 else 0.03
+RAGGED_FRAC = float(sys.argv[5]) if len(sys.argv) > 5 else 0.15
 rng = random.Random(seed0)
 genomes = [common.synth_image("g200k", 7, [120000, 60000, 20000], repeat_frac=0.08, tandem_frac=0.01, n_segdup=3),
            common.synth_image("g30k_rep", 11, [20000, 8000, 2000], repeat_frac=0.3, tandem_frac=0.05, n_segdup=4),
@@ -37,7 +38,7 @@ while time.time() - t0 < tmax:
               chimeric_frac=rng.choice([0, 0, 0.2]), mut_rate=rng.choice([0.001, 0.02]), indel_frac=rng.choice([0.15, 0.5]))
     if paired: kw.update(ins_mean=rng.choice([200, 400, 800]) + (rl if rl > 301 else 0), ins_std=rng.choice([10, 50, 150]))
     blob, _ = simdata.make_reads(g, rng.randrange(1 << 30), n, rl, paired, **kw)
-    if rng.random() < 0.15 and rl <= 301:  # a ragged batch: units of a second length (down to the empty read) spliced in
+    if rng.random() < RAGGED_FRAC and rl <= 301:  # a ragged batch: units of a second length (down to the empty read) spliced in
         import struct
         rl2 = rng.choice([0, 1, 18, 19, 33, 120, 251])
         units = [simdata.split_blob(bytes(blob))[k:k + (2 if paired else 1)] for k in range(0, n * (2 if paired else 1), 2 if paired else 1)]

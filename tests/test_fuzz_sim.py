@@ -17,6 +17,6 @@ def test_fuzz_slice():
 @pytest.mark.gpu
 def test_fuzz_slice_gpu():
     """The same sweep through the CUDA library (another seed, 40 s)."""
-    p = subprocess.run([sys.executable, os.path.join(HERE, "fuzz_sim.py"), "6", "40", "engine", "0"], capture_output=True, text=True, timeout=900)
+    p = subprocess.run([sys.executable, os.path.join(HERE, "fuzz_sim.py"), "6", "40", "engine", "0", "0"], capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
     assert "bad 0" in p.stdout
